@@ -1,0 +1,514 @@
+"""Oracle: ensemble facades (RGPE / TransBO_RGPE / OBTLV "topo" / TST / NoTL).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Citations are relative
+to ``/root/reference``.
+
+Source histories are passed as ``[(X_k float64[T_k, d], y_k float64[T_k]), ...]``
+(the array form of the reference's ``OrderedDict{Configuration -> perf}`` after
+``convert_configurations_to_array``, base_facade.py:66-71).
+"""
+import itertools
+
+import numpy as np
+from scipy.optimize import minimize
+
+from oracle.gp import OracleGP, VERY_SMALL_NUMBER
+
+
+def zero_one_normalization(X, lower=None, upper=None):
+    """tlbo/utils/normalization.py:4-13."""
+    if lower is None:
+        lower = np.min(X, axis=0)
+    if upper is None:
+        upper = np.max(X, axis=0)
+    return np.true_divide((X - lower), (upper - lower)), lower, upper
+
+
+def zero_mean_unit_var_normalization(X, mean=None, std=None):
+    """tlbo/utils/normalization.py:20-28."""
+    if mean is None:
+        mean = np.mean(X, axis=0)
+    if std is None:
+        std = np.std(X, axis=0)
+    return (X - mean) / std, mean, std
+
+
+# ---- pair counting ----------------------------------------------------------
+
+def rank_loss_literal(y, sampled_y, row_lo, row_hi):
+    """The reference's pure-Python double loop (rgpe.py:78-82, 98-102)."""
+    n = len(y)
+    rank_loss = 0
+    for i in range(row_lo, row_hi):
+        for j in range(n):
+            if (y[i] < y[j]) ^ (sampled_y[i] < sampled_y[j]):
+                rank_loss += 1
+    return rank_loss
+
+
+def rank_loss_vectorised(y, sampled_y, row_lo, row_hi):
+    """Same count, numpy broadcasting (best-effort CPU variant)."""
+    y = np.asarray(y).reshape(-1)
+    s = np.asarray(sampled_y).reshape(-1)
+    a = y[row_lo:row_hi, None] < y[None, :]
+    b = s[row_lo:row_hi, None] < s[None, :]
+    return int(np.count_nonzero(a ^ b))
+
+
+class OracleFacade(object):
+    """``BaseFacade`` (tlbo/facade/base_facade.py:15-183)."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, literal_loops=False):
+        self.method_id = None
+        self.types = np.asarray(types)
+        self.random_seed = seed
+        self.K = len(source_hpo_data)
+        self.num_src_hpo_trial = num_src_hpo_trial
+        self.source_hpo_data = source_hpo_data
+        self.source_surrogates = None
+        self.target_surrogate = None
+        self.var_threshold = VERY_SMALL_NUMBER
+        self.w = None
+        self.eta_list = list()
+        self.target_weight = []
+        self.literal_loops = literal_loops
+        self._rank_loss = rank_loss_literal if literal_loops else rank_loss_vectorised
+
+    def build_source_surrogates(self, normalize):
+        """base_facade.py:58-91."""
+        self.source_surrogates = list()
+        for X, y in self.source_hpo_data:
+            model = OracleGP(self.types, self.random_seed)
+            X = np.asarray(X, dtype=np.float64)[:self.num_src_hpo_trial]
+            y = np.array(y, dtype=np.float64)[:self.num_src_hpo_trial]
+            if normalize == 'standardize':
+                if (y == y[0]).all():
+                    y[0] += 1e-4
+                y, _, _ = zero_mean_unit_var_normalization(y)
+            elif normalize == 'scale':
+                if (y == y[0]).all():
+                    y[0] += 1e-4
+                y, _, _ = zero_one_normalization(y)
+                y = 2 * y - 1.
+            else:
+                raise ValueError('Invalid parameter in norm.')
+            self.eta_list.append(np.min(y))
+            model.train(X, y)
+            self.source_surrogates.append(model)
+
+    def build_single_surrogate(self, X, y, normalize):
+        """base_facade.py:93-108 (mutates the caller's ``y`` in the all-equal case)."""
+        assert normalize in ['standardize', 'scale', 'none']
+        model = OracleGP(self.types, self.random_seed)
+        if normalize == 'standardize':
+            if (y == y[0]).all():
+                y[0] += 1e-4
+            y, _, _ = zero_mean_unit_var_normalization(y)
+        elif normalize == 'scale':
+            if (y == y[0]).all():
+                y[0] += 1e-4
+            y, _, _ = zero_one_normalization(y)
+        model.train(X, y)
+        return model
+
+    def predict_marginalized_over_instances(self, X):
+        """base_facade.py:110-143."""
+        if len(X.shape) != 2:
+            raise ValueError('Expected 2d array, got %dd array!' % len(X.shape))
+        if X.shape[1] != len(self.types):
+            raise ValueError('Rows in X should have %d entries but have %d!' % (len(self.types), X.shape[1]))
+        mean, var = self.predict(X)
+        var[var < self.var_threshold] = self.var_threshold
+        var[np.isnan(var)] = self.var_threshold
+        return mean, var
+
+    def combine_predictions(self, X, combination_method='idp_lc'):
+        """base_facade.py:145-183, 'idp_lc' branch."""
+        n = X.shape[0]
+        mu, var = np.zeros((n, 1)), np.zeros((n, 1))
+        w = self.w
+        for i in range(0, self.K + 1):
+            if i == self.K:
+                if self.target_surrogate is None:
+                    raise ValueError('Target surrogate is none.')
+                _mu, _var = self.target_surrogate.predict(X)
+            else:
+                _mu, _var = self.source_surrogates[i].predict(X)
+            mu += w[i] * _mu
+            var += w[i] * w[i] * _var
+        if combination_method != 'idp_lc':
+            raise ValueError('Invalid combination method %s.' % combination_method)
+        return mu, var
+
+
+class OracleNoTL(OracleFacade):
+    """tlbo/facade/notl.py."""
+
+    def __init__(self, types, source_hpo_data, seed, **kw):
+        super().__init__(types, source_hpo_data, seed, **kw)
+        self.method_id = 'notl'
+
+    def train(self, X, y):
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='standardize')
+
+    def predict(self, X):
+        return self.target_surrogate.predict(X)
+
+
+class OracleRGPE(OracleFacade):
+    """tlbo/facade/rgpe.py (``smooth=None``) and tlbo/facade/topo.py
+    ``TransBO_RGPE`` (``smooth=0.7``): identical bootstrap ranking loss, the
+    latter with the extra weight smoothing of topo.py:111-133."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, only_source=False,
+                 smooth=None, literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, literal_loops)
+        self.method_id = 'rgpe' if smooth is None else 'trans_rgpe'
+        self.only_source = only_source
+        self.smooth = smooth
+        self.build_source_surrogates(normalize='standardize')
+        if smooth is None:
+            self.w = [1. / self.K] * self.K + [0.]
+        else:
+            self.w = np.array([1. / self.K] * self.K + [0.])
+        self.num_sample = 30
+        self.ignored_flag = [False] * self.K
+        self.hist_ws = list()
+        self.iteration_id = 0
+        self.last_losses = None
+
+    def train(self, X, y):
+        """rgpe.py:24-139 / topo.py:24-145.  Normal draws come from the GLOBAL
+        legacy ``np.random`` stream, scale = the predictive VARIANCE (rgpe.py:77)."""
+        mu_list, var_list = list(), list()
+        for id in range(self.K):
+            mu, var = self.source_surrogates[id].predict(X)
+            mu_list.append(mu)
+            var_list.append(var)
+
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='standardize')
+
+        k_fold_num = 5
+        cached_mu_list, cached_var_list = list(), list()
+        instance_num = len(y)
+        skip_target_surrogate = False if instance_num >= k_fold_num else True
+
+        if not skip_target_surrogate:
+            # (the instance_num < k_fold_num branch of rgpe.py:45-54 is dead code)
+            fold_num = instance_num // k_fold_num
+            for i in range(k_fold_num):
+                row_indexs = list(range(instance_num))
+                bound = (instance_num - i * fold_num) if i == (k_fold_num - 1) else fold_num
+                for index in range(bound):
+                    del row_indexs[i * fold_num]
+                if (y[row_indexs] == y[row_indexs[0]]).all():
+                    y[row_indexs[0]] += 1e-4
+                model = self.build_single_surrogate(X[row_indexs, :], y[row_indexs], normalize='standardize')
+                mu, var = model.predict(X)
+                cached_mu_list.append(mu)
+                cached_var_list.append(var)
+
+        argmin_list = [0] * (self.K + 1)
+        ranking_loss_caches = list()
+        for _ in range(self.num_sample):
+            ranking_loss_list = list()
+            for id in range(self.K):
+                sampled_y = np.random.normal(mu_list[id], var_list[id])
+                ranking_loss_list.append(self._rank_loss(y, sampled_y, 0, len(y)))
+
+            rank_loss = 0
+            if not skip_target_surrogate:
+                fold_num = instance_num // k_fold_num
+                for fold in range(k_fold_num):
+                    sampled_y = np.random.normal(cached_mu_list[fold], cached_var_list[fold])
+                    bound = instance_num if fold == (k_fold_num - 1) else (fold + 1) * fold_num
+                    rank_loss += self._rank_loss(y, sampled_y, fold_num * fold, bound)
+            else:
+                rank_loss = instance_num * instance_num
+            ranking_loss_list.append(rank_loss)
+            ranking_loss_caches.append(ranking_loss_list)
+            argmin_task = np.argmin(ranking_loss_list)
+            argmin_list[argmin_task] += 1
+
+        ranking_loss_caches = np.array(ranking_loss_caches)
+        self.last_losses = ranking_loss_caches
+        if self.smooth is None:
+            for id in range(self.K + 1):
+                self.w[id] = argmin_list[id] / self.num_sample
+        else:
+            new_weights = np.zeros(self.K + 1)
+            for id in range(self.K + 1):
+                new_weights[id] = argmin_list[id] / self.num_sample
+
+        threshold = sorted(ranking_loss_caches[:, -1])[int(self.num_sample * 0.95)]
+        for id in range(self.K):
+            median = sorted(ranking_loss_caches[:, id])[int(self.num_sample * 0.5)]
+            self.ignored_flag[id] = median > threshold
+
+        if self.smooth is None:
+            if self.only_source:
+                self.w[-1] = 0.
+                if np.sum(self.w) == 0:
+                    self.w = [1. / self.K] * self.K + [0.]
+                else:
+                    self.w[:-1] = np.array(self.w[:-1]) / np.sum(self.w[:-1])
+        else:
+            min_num_y = 5
+            w_target = new_weights[-1]
+            w_source = np.array(new_weights[:-1])
+            if instance_num >= min_num_y:
+                if instance_num >= 2 * min_num_y:
+                    w_target = np.max([w_target, self.w[-1]])
+                if np.sum(w_source) > 0:
+                    w_source = w_source / np.sum(w_source) * (1 - w_target)
+            w_new = np.array(list(w_source) + [w_target])
+            rho = self.smooth
+            self.w = rho * w_new + (1 - rho) * self.w
+
+        w = self.w.copy()
+        for id in range(self.K):
+            if self.ignored_flag[id]:
+                w[id] = 0.
+        self.target_weight.append(w[-1])
+        self.hist_ws.append(w)
+        self.iteration_id += 1
+
+    def predict(self, X):
+        """rgpe.py:141-153."""
+        mu, var = self.target_surrogate.predict(X)
+        mu *= self.w[-1]
+        var *= (self.w[-1] * self.w[-1])
+        for i in range(0, self.K):
+            if not self.ignored_flag[i]:
+                mu_t, var_t = self.source_surrogates[i].predict(X)
+                mu += self.w[i] * mu_t
+                var += self.w[i] * self.w[i] * var_t
+        return mu, var
+
+
+# ---- OBTLV ("--methods topo"): pairwise logistic loss + SLSQP ----------------
+
+def ranking_pairs(true_y):
+    """Pairs (i, j) with true_y[i] > true_y[j] in the reference's enumeration
+    order (utils/scipy_solver.py:15-22)."""
+    pairs = list()
+    for (i, j) in itertools.combinations(range(true_y.shape[0]), 2):
+        if true_y[i] > true_y[j]:
+            pairs.append((i, j))
+        elif true_y[i] < true_y[j]:
+            pairs.append((j, i))
+    return pairs
+
+
+def loss_func3(true_y, pred_y, literal=False):
+    """``Loss_func(..., func_id=3)``: utils/scipy_solver.py:6-40."""
+    true_y = np.asarray(true_y).reshape(-1)
+    pred_y = np.asarray(pred_y).reshape(-1)
+    pairs = ranking_pairs(true_y)
+    if len(pairs) == 0:
+        return 0.
+    if literal:
+        loss = 0.
+        for (i, j) in pairs:
+            loss += np.log(1 + np.exp(pred_y[j] - pred_y[i]))
+        return loss / len(pairs)
+    ii = np.array([p[0] for p in pairs])
+    jj = np.array([p[1] for p in pairs])
+    return float(np.sum(np.log(1 + np.exp(pred_y[jj] - pred_y[ii]))) / len(pairs))
+
+
+def loss_der3(true_y, A, x, literal=False):
+    """``Loss_der(..., func_id=3)``: utils/scipy_solver.py:43-78."""
+    A = np.asarray(A)
+    true_y = np.asarray(true_y).reshape(-1)
+    pred_y = A.dot(np.asarray(x).reshape(-1))
+    pairs = ranking_pairs(true_y)
+    grad = np.zeros(A.shape[1])
+    if len(pairs) == 0:
+        return grad
+    if literal:
+        for (i, j) in pairs:
+            e_z = np.exp(pred_y[j] - pred_y[i])
+            grad += e_z / (1 + e_z) * (A[j] - A[i])
+        return grad / len(pairs)
+    ii = np.array([p[0] for p in pairs])
+    jj = np.array([p[1] for p in pairs])
+    e_z = np.exp(pred_y[jj] - pred_y[ii])
+    s = e_z / (1 + e_z)
+    return (s[:, None] * (A[jj] - A[ii])).sum(0) / len(pairs)
+
+
+def scipy_solve(A, b, loss_fn=loss_func3, der_fn=loss_der3):
+    """utils/scipy_solver.py:81-115 with ``loss_type=3``.  ``loss_fn`` /
+    ``der_fn`` are injectable so the product path can run the same SLSQP
+    driver over its device loss (the product has its own copy of this driver;
+    it never imports the oracle)."""
+    A = np.asarray(A)
+    n, m = A.shape
+    ineq_cons = {'type': 'ineq', 'fun': lambda x: np.array(x), 'jac': lambda x: np.eye(len(x))}
+    eq_cons = {'type': 'eq', 'fun': lambda x: np.array([sum(x) - 1]), 'jac': lambda x: np.array([1.] * len(x))}
+    x0 = np.array([1. / m] * m)
+
+    def f(x):
+        return loss_fn(b, A.dot(x))
+
+    def f_der(x):
+        return der_fn(b, A, x)
+
+    res = minimize(f, x0, method='SLSQP', jac=f_der, constraints=[eq_cons, ineq_cons],
+                   options={'ftol': 1e-8, 'disp': False})
+    status = False if np.isnan(res.x).any() else True
+    if not res.success and status:
+        res.x[res.x < 0.] = 0.
+        res.x[res.x > 1.] = 1.
+        if sum(res.x) > 1.5:
+            status = False
+    return res.x, status
+
+
+def kfold_indices(n, n_splits=5):
+    """sklearn ``KFold(n_splits, shuffle=False).split``: the first ``n % k``
+    folds get one extra row (used by topo_variant1.py:42-44)."""
+    fold_sizes = np.full(n_splits, n // n_splits, dtype=int)
+    fold_sizes[:n % n_splits] += 1
+    idx = np.arange(n)
+    out, cur = [], 0
+    for fs in fold_sizes:
+        val = idx[cur:cur + fs]
+        train = np.concatenate([idx[:cur], idx[cur + fs:]])
+        out.append((train, val))
+        cur += fs
+    return out
+
+
+class OracleOBTLV(OracleFacade):
+    """tlbo/facade/topo_variant1.py -- what ``--methods topo`` runs
+    (tools/offline_benchmark.py:310-311)."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, fusion_method='idp_lc',
+                 only_source=False, literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, literal_loops)
+        self.method_id = 'topo_v1'
+        self.fusion_method = fusion_method
+        self.build_source_surrogates(normalize='standardize')
+        self.only_source = only_source
+        self.w = np.array([1. / self.K] * self.K + [0.])
+        self.min_num_y = 5
+        self.hist_ws = list()
+        self.iteration_id = 0
+        self.target_y_range = None
+
+    def _solve(self, A, y):
+        lit = self.literal_loops
+        return scipy_solve(A, y, lambda b, p: loss_func3(b, p, lit), lambda b, A_, x: loss_der3(b, A_, x, lit))
+
+    def batch_predict(self, X):
+        """topo_variant1.py:27-35."""
+        pred_y = None
+        for i in range(0, self.K):
+            mu, _ = self.source_surrogates[i].predict(X)
+            pred_y = mu if pred_y is None else np.c_[pred_y, mu]
+        return pred_y
+
+    def predict_target_surrogate_cv(self, X, y):
+        """topo_variant1.py:37-53."""
+        _mu, _var = list(), list()
+        for train_idx, val_idx in kfold_indices(X.shape[0], 5):
+            X_train, X_val, y_train = X[train_idx, :], X[val_idx, :], y[train_idx]
+            model = self.build_single_surrogate(X_train, y_train, normalize='standardize')
+            mu, var = model.predict(X_val)
+            _mu.extend(list(mu.flatten()))
+            _var.extend(list(var.flatten()))
+        return np.asarray(_mu), np.asarray(_var)
+
+    def train(self, X, y):
+        """topo_variant1.py:55-86."""
+        instance_num = X.shape[0]
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='standardize')
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        pred_y = self.batch_predict(X)
+
+        x, status = self._solve(pred_y, y)            # learn_source_weights :88-92
+        if status:
+            x[x < 1e-3] = 0.
+            self.w[:self.K] = x
+        w_source = self.w[:self.K]
+        w_target = 0.
+        if not self.only_source:
+            if instance_num >= self.min_num_y:
+                _t_pred_y, _ = self.predict_target_surrogate_cv(X, y)
+                _pred_y = np.c_[pred_y, _t_pred_y.reshape((-1, 1))]
+                x, status = self._solve(_pred_y, y)   # compute_target_weight :94-100
+                if status:
+                    x[x < 1e-3] = 0.
+                    w_target = x[-1]
+                else:
+                    w_target = self.w[-1]
+                if instance_num >= 2 * self.min_num_y:
+                    w_target = np.max([w_target, self.w[-1]])
+                w_source *= (1 - w_target)
+        w_new = np.asarray(list(w_source) + [w_target])
+        rho = 0.6
+        self.w = rho * w_new + (1 - rho) * self.w
+        w = self.w.copy()
+        self.target_weight.append(w[-1])
+        self.hist_ws.append(w)
+        self.iteration_id += 1
+
+    def predict(self, X):
+        return self.combine_predictions(X, self.fusion_method)
+
+
+class OracleTST(OracleFacade):
+    """tlbo/facade/tst.py (``use_metafeatures=False``)."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, only_source=False, literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, literal_loops)
+        self.method_id = 'tst'
+        self.only_source = only_source
+        self.build_source_surrogates(normalize='scale')
+        self.w = [0.75] * (self.K + 1)
+        self.bandwidth = 0.45
+        self.hist_ws = list()
+        self.iteration_id = 0
+
+    def train(self, X, y):
+        """tst.py:30-62: discordant pairs over i<j."""
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='scale')
+        n_sample = X.shape[0]
+        for _id in range(self.K):
+            mu, _ = self.source_surrogates[_id].predict(X)
+            mu = mu.reshape(-1)
+            if self.literal_loops:
+                discordant, total = 0, 0
+                for i in range(n_sample):
+                    for j in range(i + 1, n_sample):
+                        if (y[i] < y[j]) ^ (mu[i] < mu[j]):
+                            discordant += 1
+                        total += 1
+            else:
+                iu = np.triu_indices(n_sample, 1)
+                a = (y[:, None] < y[None, :])[iu]
+                b = (mu[:, None] < mu[None, :])[iu]
+                discordant, total = int(np.count_nonzero(a ^ b)), len(iu[0])
+            tmp = discordant / total / self.bandwidth
+            self.w[_id] = 0.75 * (1 - tmp * tmp) if tmp <= 1 else 0
+        if self.only_source:
+            self.w[-1] = 0.
+            self.w = np.array(self.w) / np.sum(self.w)
+        w = self.w.copy()
+        self.target_weight.append(w[-1] / sum(w))
+        self.hist_ws.append(w)
+        self.iteration_id += 1
+
+    def predict(self, X):
+        """tst.py:64-73."""
+        mu, var = self.target_surrogate.predict(X)
+        denominator = 0.75
+        for i in range(0, self.K):
+            weight = self.w[i]
+            mu_t, _ = self.source_surrogates[i].predict(X)
+            mu += weight * mu_t
+            denominator += weight
+        mu /= denominator
+        return mu, var
