@@ -1,0 +1,94 @@
+// C-ABI plumbing shared by all entry points + the FP64 rate probes used for the roofline.
+#include "tlbo_common.cuh"
+#include <string.h>
+#include <stdio.h>
+
+static thread_local char g_err[256] = "";
+
+void tlbo_set_error(const char* msg) {
+  strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+extern "C" const char* tlbo_last_error(void) { return g_err; }
+extern "C" int tlbo_version(void) { return 100; }
+
+// Column permutation: continuous columns (types == 0) first, categorical after, each group
+// in the reference's column order (model_builder.py:38-39: cont_dims / cat_dims).
+int tlbo_make_space(int d, const int32_t* h_types, SpaceDesc* sp) {
+  if (d <= 0 || d > TLBO_MAX_D || !h_types) { tlbo_set_error("bad d / types"); return TLBO_E_BADARG; }
+  sp->d = d;
+  int k = 0;
+  for (int i = 0; i < d; i++) if (h_types[i] == 0) sp->perm[k++] = i;
+  sp->d_cont = k;
+  for (int i = 0; i < d; i++) if (h_types[i] != 0) sp->perm[k++] = i;
+  sp->d_cat = d - sp->d_cont;
+  for (int i = d; i < TLBO_HMAX; i++) sp->perm[i] = 0;
+  return 0;
+}
+
+// ---- FP64 rate probes -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double seed) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = seed * 1e-3 + (threadIdx.x & 3) * 1e-4, b = 1e-3 + (threadIdx.x >> 2) * 1e-5;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[k][0]), "+d"(c[k][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int tlbo_fp64_peak_probe(double* h_out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  double* d_out = nullptr;
+  TLBO_CUDA_CHECK(cudaMalloc(&d_out, 64));
+  cudaEvent_t e0, e1;
+  TLBO_CUDA_CHECK(cudaEventCreate(&e0));
+  TLBO_CUDA_CHECK(cudaEventCreate(&e1));
+  const int grid = 148 * 8, iters = 20000;
+  float ms = 0.f;
+  double best[2] = {0.0, 0.0};
+  for (int rep = 0; rep < 4; rep++) {
+    TLBO_CUDA_CHECK(cudaEventRecord(e0, s));
+    dfma_probe_kernel<<<grid, 256, 0, s>>>(d_out, iters, 1.0);
+    TLBO_CUDA_CHECK(cudaEventRecord(e1, s));
+    TLBO_CUDA_CHECK(cudaEventSynchronize(e1));
+    TLBO_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 8.0 * (double)iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best[0]) best[0] = tf;
+    TLBO_CUDA_CHECK(cudaEventRecord(e0, s));
+    dmma_probe_kernel<<<grid, 256, 0, s>>>(d_out, iters / 8, 1.0);
+    TLBO_CUDA_CHECK(cudaEventRecord(e1, s));
+    TLBO_CUDA_CHECK(cudaEventSynchronize(e1));
+    TLBO_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    // one m8n8k4 = 256 MAC per warp
+    tf = 2.0 * 256.0 * 8.0 * (double)(iters / 8) * 8.0 * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best[1]) best[1] = tf;
+  }
+  h_out[0] = best[0];
+  h_out[1] = best[1];
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return 0;
+}

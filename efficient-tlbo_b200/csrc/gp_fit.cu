@@ -1,0 +1,654 @@
+// Batched GP fit on device: one CTA per (surrogate, restart) runs the complete
+// bound-constrained L-BFGS-B MAP optimisation of the GP hyper-parameters with zero host
+// round trips; a second kernel picks the best restart and factorises.
+//
+// Replaces reference tlbo/model/gp.py:98-248 (GaussianProcess._train/_nll/_optimize) and
+// the sklearn-0.21 / skopt GaussianProcessRegressor.fit + log_marginal_likelihood under it
+// (kernel stack: tlbo/model/gp_kernels.py, priors: tlbo/model/gp_base_prior.py).
+//
+// Per NLL evaluation, inside one CTA with the whole problem in shared memory:
+//   1. K (lower triangle) from theta: Matern-5/2 x Hamming x c + s2*I.
+//   2. ONE square-root-free elimination sweep over the (n+1) x n panel [K ; I ; y^T]
+//      (one __syncthreads per column) that leaves, in a single n x n array, the pivots of
+//      L, the columns of L below the diagonal, L^-T above it and L^-1 y in the extra row.
+//   3. alpha = L^-T (L^-1 y);  LML = -1/2 |L^-1 y|^2 - 1/2 sum log piv - n/2 log 2pi.
+//   4. gradient: 1/2 tr((alpha alpha^T - K^-1) dK/dtheta_h) with K^-1_ij formed on the fly
+//      from rows of L^-T and dK/dtheta recomputed per pair -- never materialised (n^2 H).
+//   5. + log-priors (lognormal on c, horseshoe on s2) and their gradients.
+#include "tlbo_common.cuh"
+#include "lbfgsb_dense.cuh"
+
+#define FIT_THREADS 256
+
+struct FitWs {
+  double* A;       // [(n+1) * lda]  elimination panel
+  double* Xr;      // [n * d]  raw inputs, permuted columns
+  double* Xs;      // [n * d]  cont columns / l, cat columns raw
+  double* y;       // [n]
+  double* piv;     // [n]
+  double* dinv;    // [n]  1/sqrt(piv)
+  double* alpha;   // [n]
+  double* red;     // [8 * 32] reduction scratch
+  double* hyp;     // [2 * TLBO_HMAX] per permuted column: l (cont) or 1/(2 l^2) (cat); then 1/l^3 (cat)
+  int n, lda, d;
+};
+
+__host__ __device__ inline int fit_lda(int n) { return (n & 1) ? n : n + 1; }
+
+__host__ inline size_t fit_small_bytes(int ncap, int d) {
+  // Xr, Xs, y, piv, dinv, alpha, red, hyp
+  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 8);
+}
+__host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
+
+__device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* panel_global, int n, int ncap,
+                                         int d) {
+  double* p = reinterpret_cast<double*>(smem);
+  S.n = n; S.d = d; S.lda = fit_lda(n);
+  S.Xr = p; p += (size_t)ncap * d;
+  S.Xs = p; p += (size_t)ncap * d;
+  S.y = p; p += ncap;
+  S.piv = p; p += ncap;
+  S.dinv = p; p += ncap;
+  S.alpha = p; p += ncap;
+  S.red = p; p += 8 * 32;
+  S.hyp = p; p += 2 * TLBO_HMAX;
+  S.A = panel_global ? panel_global : p;
+}
+
+__device__ __forceinline__ void load_problem(const FitWs& S, const SpaceDesc& sp, const double* X,
+                                             const double* y, int ncap) {
+  const int n = S.n, d = S.d;
+  for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
+    const int i = idx / d, p = idx - i * d;
+    S.Xr[idx] = X[(size_t)i * d + sp.perm[p]];
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) S.y[i] = y[i];
+  (void)ncap;
+}
+
+// Steps 1-2.  Returns false (uniformly) if a pivot is not positive (Cholesky would fail).
+// On success: A[i][k] i>k = L_ik*sqrt(piv_k) (unscaled), piv[], dinv[], and -- scaled --
+// A[i][k] i<k = (L^-1)_ki,  A[n][k] = (L^-1 y)_k.   If scale_lower, A[i][k] i>=k = L_ik.
+__device__ bool build_and_eliminate(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                    bool scale_lower) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double* A = S.A;
+  __syncthreads();
+  if (tid < d) {
+    const double l = exp(theta[1 + tid]);
+    if (tid < dc) { S.hyp[tid] = l; }
+    else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+  }
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  __syncthreads();
+  for (int idx = tid; idx < n * d; idx += T) {
+    const int p = idx % d;
+    double v = S.Xr[idx];
+    if (p < dc) v = v / S.hyp[p];
+    S.Xs[idx] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (n + 1) * n; idx += T) {
+    const int i = idx / n, j = idx - i * n;
+    double v;
+    if (i == n) v = S.y[j];
+    else if (i < j) v = 0.0;
+    else if (i == j) v = c + noise;
+    else {
+      const double* xi = S.Xs + (size_t)i * d;
+      const double* xj = S.Xs + (size_t)j * d;
+      double s = 0.0, hs = 0.0;
+      for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+      for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+      v = matern_hamming(c, s, hs);
+    }
+    A[(size_t)i * lda + j] = v;
+  }
+  bool ok = true;
+  const int tx = tid & 15, ty = tid >> 4, TY = T >> 4;
+  for (int k = 0; k < n; k++) {
+    __syncthreads();
+    const double piv = A[(size_t)k * lda + k];
+    if (!(piv > 0.0)) { ok = false; break; }
+    const double ip = 1.0 / piv;
+    if (tid == 0) S.piv[k] = piv;
+    for (int j = k + 1 + tx; j < n; j += 16) {
+      const double fj = A[(size_t)j * lda + k] * ip;
+      for (int i = ty; i <= n; i += TY) {
+        double ck;
+        if (i >= j || i < k) ck = A[(size_t)i * lda + k];
+        else if (i == k) ck = 1.0;
+        else continue;
+        A[(size_t)i * lda + j] -= ck * fj;
+      }
+    }
+  }
+  __syncthreads();
+  if (!ok) return false;
+  for (int k = tid; k < n; k += T) S.dinv[k] = 1.0 / sqrt(S.piv[k]);
+  __syncthreads();
+  for (int idx = tid; idx < (n + 1) * n; idx += T) {
+    const int i = idx / n, k = idx - i * n;
+    if (i < k || i == n) A[(size_t)i * lda + k] *= S.dinv[k];
+    else if (scale_lower) {
+      if (i == k) A[(size_t)i * lda + k] = sqrt(S.piv[k]);
+      else A[(size_t)i * lda + k] *= S.dinv[k];
+    }
+  }
+  __syncthreads();
+  // alpha_i = sum_{k>=i} (L^-1)_ki z_k
+  for (int i = tid; i < n; i += T) {
+    const double* ri = A + (size_t)i * lda;
+    const double* z = A + (size_t)n * lda;
+    double a = S.dinv[i] * z[i];
+    for (int k = i + 1; k < n; k++) a += ri[k] * z[k];
+    S.alpha[i] = a;
+  }
+  __syncthreads();
+  return true;
+}
+
+// One evaluation of GaussianProcess._nll (gp.py:164-197).  Result: out[0] = f, out[1..H] = g
+// (shared memory), visible to all threads on return.  Returns Cholesky success.
+template <int DMAX>
+__device__ bool nll_eval(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const bool ok = build_and_eliminate(S, sp, theta, false);
+  if (!ok) {
+    if (tid == 0) out[0] = 1e25;
+    if (tid < H) out[1 + tid] = 0.0;
+    __syncthreads();
+    return false;
+  }
+  const double* A = S.A;
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  // data fit and log-determinant
+  double part = 0.0;
+  for (int k = tid; k < n; k += T) {
+    const double z = A[(size_t)n * lda + k];
+    part += 0.5 * z * z + 0.5 * log(S.piv[k]);
+  }
+  const double nll_data = block_sum(part, S.red);
+
+  // gradient accumulators: g0 (log c), gacc[p] (length scales, permuted order), gn (log s2)
+  double g0 = 0.0, gn = 0.0;
+  double gacc[DMAX];
+#pragma unroll
+  for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
+
+  const int npairs = n * (n - 1) / 2;
+  for (int q = tid; q < npairs; q += T) {
+    int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+    while (i * (i - 1) / 2 > q) i--;
+    while ((i + 1) * i / 2 <= q) i++;
+    const int j = q - i * (i - 1) / 2;   // j < i
+    const double* ri = A + (size_t)i * lda;
+    const double* rj = A + (size_t)j * lda;
+    double kin = S.dinv[i] * rj[i];
+    for (int k = i + 1; k < n; k++) kin += ri[k] * rj[k];
+    const double W = S.alpha[i] * S.alpha[j] - kin;
+    const double* xi = S.Xs + (size_t)i * d;
+    const double* xj = S.Xs + (size_t)j * d;
+    double s = 0.0, hs = 0.0;
+    for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+    for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+    const double t = sqrt(s) * SQRT5;
+    const double e = exp(-t), eh = exp(-hs);
+    const double Kc = c * ((1.0 + t + t * t / 3.0) * e) * eh;
+    const double WK = W * Kc;
+    g0 += WK;
+    const double coef = W * c * eh * (5.0 / 3.0) * (t + 1.0) * e;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < dc) { const double df = xi[p] - xj[p]; gacc[p] += coef * (df * df); }
+      else if (p < d) { if (xi[p] != xj[p]) gacc[p] += WK * S.hyp[TLBO_HMAX + p]; }
+    }
+  }
+  for (int i = tid; i < n; i += T) {
+    const double* ri = A + (size_t)i * lda;
+    double kin = S.dinv[i] * S.dinv[i];
+    for (int k = i + 1; k < n; k++) kin += ri[k] * ri[k];
+    const double W = S.alpha[i] * S.alpha[i] - kin;
+    g0 += 0.5 * W * c;
+    gn += 0.5 * W * noise;
+  }
+  // reduce H values across the block
+  const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  __syncthreads();
+  {
+    double v = warp_sum(g0);
+    if (lane == 0) S.red[wid * 32 + 0] = v;
+    v = warp_sum(gn);
+    if (lane == 0) S.red[wid * 32 + (d + 1)] = v;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < d) {
+        v = warp_sum(gacc[p]);
+        if (lane == 0) S.red[wid * 32 + 1 + p] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < H) {
+    double v = 0.0;
+    for (int w = 0; w < nw; w++) v += S.red[w * 32 + tid];
+    out[1 + tid] = v;       // d LML / d theta_h (without priors)
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double lml = -nll_data - 0.5 * (double)n * LOG_2PI;
+    // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
+    const double v0 = exp(theta[0]);
+    double lp0, gp0;
+    if (v0 <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
+    else {
+      const double lv = log(v0);
+      lp0 = -(lv * lv) / 2.0 - log(2.5066282746310002 * v0);
+      gp0 = -(1.0 + lv) / v0 * v0;
+    }
+    // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
+    const double vn = exp(theta[H - 1]);
+    const double s2 = 0.1 * 0.1;
+    double lpn, gpn;
+    if (vn == 0.0) { lpn = INFINITY; gpn = INFINITY; }
+    else {
+      const double a = log(1.0 + 3.0 * (s2 / (vn * vn)));
+      lpn = log(a + VERY_SMALL_NUMBER);
+      double b = 3.0 * s2 + vn * vn;
+      b *= log(3.0 * s2 * (1.0 / (vn * vn)) + 1.0);
+      b = fmax(b, 1e-14);
+      gpn = -(6.0 * s2) / b;
+    }
+    lml += lp0 + lpn;
+    out[1] += gp0;
+    out[H] += gpn;
+    bool fin = isfinite(lml);
+    for (int h = 0; h < H; h++) fin = fin && isfinite(out[1 + h]);
+    if (!fin) {
+      out[0] = 1e25;
+      for (int h = 0; h < H; h++) out[1 + h] = 0.0;
+    } else {
+      out[0] = -lml;
+      for (int h = 0; h < H; h++) out[1 + h] = -out[1 + h];
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+struct FitArgs {
+  const double* X; const double* y; const int32_t* n;
+  int B, R, ncap, d;
+  SpaceDesc sp;
+  const double* p0; const double* lo; const double* hi;
+  int do_optimize;
+  double* restart_theta; double* restart_f; int32_t* restart_info;
+  double* panels;        // global panels (NULL -> shared memory)
+  size_t panel_stride;   // doubles
+};
+
+template <int DMAX>
+__global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int b = blockIdx.x / a.R, r = blockIdx.x - b * a.R;
+  const int n = a.n[b], d = a.d, H = d + 2;
+  const int tid = threadIdx.x;
+  __shared__ double th[TLBO_HMAX];
+  __shared__ double fg[1 + TLBO_HMAX];
+  __shared__ int act;
+  LbfgsbState* st = reinterpret_cast<LbfgsbState*>(smem);
+  unsigned char* rest = smem + ((sizeof(LbfgsbState) + 15) / 16) * 16;
+  FitWs S;
+  carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d);
+  load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
+  if (tid < H) th[tid] = a.p0[(size_t)r * H + tid];
+  __syncthreads();
+  int bumps = 0;
+  if (r == 0) {
+    // gp.py:127-140: the initial GaussianProcessRegressor.fit at the default theta retries
+    // with noise += 1 on LinAlgError; the bumped theta then becomes start point 0.
+    for (int tries = 0; tries < 10; tries++) {
+      if (build_and_eliminate(S, a.sp, th, false)) break;
+      if (tid == 0) th[H - 1] = log(exp(th[H - 1]) + 1.0);
+      bumps++;
+      __syncthreads();
+    }
+  }
+  int nfev = 0;
+  if (!a.do_optimize) {
+    nll_eval<DMAX>(S, a.sp, th, fg);
+    nfev = 1;
+    if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = th[tid];
+    if (tid == 0) {
+      a.restart_f[(size_t)b * a.R + r] = fg[0];
+      int32_t* info = a.restart_info + ((size_t)b * a.R + r) * 4;
+      info[0] = nfev; info[1] = 0; info[2] = -1; info[3] = bumps;
+    }
+    return;
+  }
+  if (tid == 0) lbfgsb_init(*st, H, th, a.lo, a.hi);
+  __syncthreads();
+  for (;;) {
+    if (tid < H) th[tid] = st->x[tid];
+    __syncthreads();
+    nll_eval<DMAX>(S, a.sp, th, fg);
+    nfev++;
+    if (tid == 0) act = lbfgsb_feed(*st, fg[0], fg + 1);
+    __syncthreads();
+    if (act == LB_DONE) break;
+  }
+  if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = st->x[tid];
+  if (tid == 0) {
+    a.restart_f[(size_t)b * a.R + r] = st->f_last;
+    int32_t* info = a.restart_info + ((size_t)b * a.R + r) * 4;
+    info[0] = nfev; info[1] = st->iter; info[2] = st->status; info[3] = bumps;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct FacArgs {
+  const double* X; const double* y; const int32_t* n;
+  int B, R, ncap, d;
+  SpaceDesc sp;
+  const double* theta_in;     // [B, R, H] candidates (R = 1 -> given theta)
+  const double* f_in;         // [B, R] or NULL
+  const double* ymean; const double* ystd;   // device copies [B]
+  tlbo_pack pack; int slot0;
+  double* L; double* Kinv; int32_t* status;
+  double* panels; size_t panel_stride;
+};
+
+__global__ void __launch_bounds__(FIT_THREADS, 1) gp_factorize_kernel(FacArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int b = blockIdx.x;
+  const int n = a.n[b], d = a.d, H = d + 2, dc = a.sp.d_cont, ncap = a.ncap;
+  const int tid = threadIdx.x, T = blockDim.x;
+  __shared__ double th[TLBO_HMAX];
+  __shared__ int best;
+  FitWs S;
+  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, ncap, d);
+  load_problem(S, a.sp, a.X + (size_t)b * ncap * d, a.y + (size_t)b * ncap, ncap);
+  if (tid == 0) {
+    // gp.py:241-248: first strict improvement wins
+    int br = -1;
+    if (a.f_in) {
+      double fstar = INFINITY;
+      for (int r = 0; r < a.R; r++) {
+        const double f = a.f_in[(size_t)b * a.R + r];
+        if (f < fstar) { fstar = f; br = r; }
+      }
+    } else br = 0;
+    best = br;
+  }
+  __syncthreads();
+  const int slot = a.slot0 + b;
+  const int pncap = a.pack.ncap;
+  if (best < 0) {
+    if (tid == 0) { a.status[b] = 2; a.pack.d_n[slot] = 0; }
+    return;
+  }
+  if (tid < H) th[tid] = a.theta_in[((size_t)b * a.R + best) * H + tid];
+  __syncthreads();
+  const bool ok = build_and_eliminate(S, a.sp, th, a.L != nullptr);
+  if (tid == 0) { a.status[b] = ok ? 0 : 1; a.pack.d_n[slot] = ok ? n : 0; }
+  if (tid < H) a.pack.d_theta[(size_t)slot * H + tid] = th[tid];
+  if (!ok) return;
+  const int lda = S.lda;
+  const double* A = S.A;
+  // hyp row
+  double* hyp = a.pack.d_hyp + (size_t)slot * TLBO_HYP_STRIDE;
+  if (tid == 0) {
+    const double c = exp(th[0]), noise = exp(th[H - 1]);
+    hyp[0] = c; hyp[1] = noise; hyp[2] = a.ymean[b]; hyp[3] = a.ystd[b]; hyp[4] = c + noise;
+    hyp[5] = 0.0; hyp[6] = 0.0; hyp[7] = 0.0;
+  }
+  if (tid < d) hyp[8 + tid] = (tid < dc) ? 1.0 / S.hyp[tid] : S.hyp[tid];
+  // Xs (multiplied by 1/l: the predict kernels scale candidates the same way)
+  double* Xs = a.pack.d_Xs + (size_t)slot * pncap * d;
+  for (int idx = tid; idx < pncap * d; idx += T) {
+    const int i = idx / d, p = idx - i * d;
+    double v = 0.0;
+    if (i < n) { v = S.Xr[(size_t)i * d + p]; if (p < dc) v = v * (1.0 / S.hyp[p]); }
+    Xs[idx] = v;
+  }
+  double* al = a.pack.d_alpha + (size_t)slot * pncap;
+  for (int i = tid; i < pncap; i += T) al[i] = (i < n) ? S.alpha[i] : 0.0;
+  const int ldl = TLBO_LDL(pncap);
+  double* Li = a.pack.d_Linv + (size_t)slot * pncap * ldl;
+  for (int idx = tid; idx < pncap * ldl; idx += T) {
+    const int k = idx / ldl, i = idx - k * ldl;    // Linv[k][i]
+    double v = 0.0;
+    if (k < n && i < n) {
+      if (i < k) v = A[(size_t)i * lda + k];
+      else if (i == k) v = S.dinv[k];
+    }
+    Li[idx] = v;
+  }
+  if (a.L) {
+    double* Lo = a.L + (size_t)b * ncap * ncap;
+    for (int idx = tid; idx < ncap * ncap; idx += T) {
+      const int i = idx / ncap, k = idx - i * ncap;
+      Lo[idx] = (i < n && k <= i) ? A[(size_t)i * lda + k] : 0.0;
+    }
+  }
+  if (a.Kinv) {
+    double* Ko = a.Kinv + (size_t)b * ncap * ncap;
+    for (int idx = tid; idx < ncap * ncap; idx += T) {
+      const int i = idx / ncap, j = idx - i * ncap;
+      double v = 0.0;
+      if (i < n && j < n) {
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        const double* rh = A + (size_t)hi * lda;
+        const double* rl = A + (size_t)lo * lda;
+        v = S.dinv[hi] * (hi == lo ? S.dinv[hi] : rl[hi]);
+        for (int k = hi + 1; k < n; k++) v += rh[k] * rl[k];
+      }
+      Ko[idx] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct NllArgs {
+  const double* X; const double* y; const int32_t* n;
+  int B, ncap, d;
+  SpaceDesc sp;
+  const double* theta; double* nll; double* grad; int32_t* status;
+  double* panels; size_t panel_stride;
+};
+
+template <int DMAX>
+__global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int b = blockIdx.x;
+  const int n = a.n[b], d = a.d, H = d + 2;
+  const int tid = threadIdx.x;
+  __shared__ double th[TLBO_HMAX];
+  __shared__ double fg[1 + TLBO_HMAX];
+  FitWs S;
+  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, a.ncap, d);
+  load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
+  if (tid < H) th[tid] = a.theta[(size_t)b * H + tid];
+  __syncthreads();
+  const bool ok = nll_eval<DMAX>(S, a.sp, th, fg);
+  if (tid == 0) { a.nll[b] = fg[0]; a.status[b] = ok ? 0 : 1; }
+  if (tid < H) a.grad[(size_t)b * H + tid] = fg[1 + tid];
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+static const size_t kSmemLimit = 227 * 1024;
+
+struct WorkLayout {
+  bool global_panels;
+  size_t smem_fit, smem_fac;
+  size_t panel_stride;   // doubles
+};
+
+static WorkLayout plan(int ncap, int d) {
+  WorkLayout w;
+  const size_t small = fit_small_bytes(ncap, d);
+  const size_t panel = fit_panel_bytes(ncap);
+  const size_t st = ((sizeof(LbfgsbState) + 15) / 16) * 16;
+  w.global_panels = (st + small + panel + 1024) > kSmemLimit;
+  w.smem_fit = st + small + (w.global_panels ? 0 : panel);
+  w.smem_fac = small + (w.global_panels ? 0 : panel);
+  w.panel_stride = panel / sizeof(double);
+  return w;
+}
+
+extern "C" int64_t tlbo_gp_fit_workspace_bytes(int B, int R, int ncap, int d) {
+  // restart buffers + (possibly) global panels + device copies of ymean/ystd
+  const int H = d + 2;
+  size_t bytes = 0;
+  bytes += (size_t)B * R * H * 8 + (size_t)B * R * 8 + (size_t)B * R * 16 + 2 * (size_t)B * 8 + 256;
+  WorkLayout w = plan(ncap, d);
+  if (w.global_panels) bytes += (size_t)B * R * w.panel_stride * 8;
+  return (int64_t)bytes;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { tlbo_set_error(cudaGetErrorString(e)); return (int)e; }
+  }
+  return 0;
+}
+
+static int launch_factorize(const double* d_X, const double* d_y, const int32_t* d_n, int B, int R, int ncap,
+                            int d, const SpaceDesc& sp, const double* theta_in, const double* f_in,
+                            const double* d_ymean, const double* d_ystd, const tlbo_pack* pack, int slot0,
+                            double* d_L, double* d_Kinv, int32_t* d_status, double* panels,
+                            const WorkLayout& w, cudaStream_t s) {
+  FacArgs fa;
+  fa.X = d_X; fa.y = d_y; fa.n = d_n; fa.B = B; fa.R = R; fa.ncap = ncap; fa.d = d; fa.sp = sp;
+  fa.theta_in = theta_in; fa.f_in = f_in; fa.ymean = d_ymean; fa.ystd = d_ystd;
+  fa.pack = *pack; fa.slot0 = slot0; fa.L = d_L; fa.Kinv = d_Kinv; fa.status = d_status;
+  fa.panels = w.global_panels ? panels : nullptr; fa.panel_stride = w.panel_stride;
+  int rc = set_smem(gp_factorize_kernel, w.smem_fac);
+  if (rc) return rc;
+  gp_factorize_kernel<<<B, FIT_THREADS, w.smem_fac, s>>>(fa);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static int check_common(int B, int ncap, int d, const tlbo_pack* pack, int slot0) {
+  if (B <= 0 || ncap <= 0 || d <= 0 || d > TLBO_MAX_D) { tlbo_set_error("bad B/ncap/d"); return TLBO_E_BADARG; }
+  if (pack) {
+    if (pack->d != d || pack->ncap < ncap || slot0 < 0 || slot0 + B > pack->M) {
+      tlbo_set_error("pack does not match the batch (d / ncap / slots)");
+      return TLBO_E_BADARG;
+    }
+  }
+  return 0;
+}
+
+extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const int32_t* d_n, int B, int ncap,
+                                   int d, const int32_t* h_types, const double* d_p0, int R,
+                                   const double* d_lo, const double* d_hi, const double* h_ymean,
+                                   const double* h_ystd, int do_optimize, const tlbo_pack* pack, int slot0,
+                                   double* d_restart_theta, double* d_restart_f, int32_t* d_restart_info,
+                                   int32_t* d_status, void* d_work, void* stream) {
+  int rc = check_common(B, ncap, d, pack, slot0);
+  if (rc) return rc;
+  if (R <= 0 || !pack || !d_status || !d_work) { tlbo_set_error("bad R / NULL pack, status or work"); return TLBO_E_BADARG; }
+  SpaceDesc sp;
+  rc = tlbo_make_space(d, h_types, &sp);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = d + 2;
+  if (!do_optimize) R = 1;
+  WorkLayout w = plan(ncap, d);
+  // carve the workspace
+  unsigned char* wp = (unsigned char*)d_work;
+  double* w_theta = (double*)wp; wp += (size_t)B * R * H * 8;
+  double* w_f = (double*)wp; wp += (size_t)B * R * 8;
+  int32_t* w_info = (int32_t*)wp; wp += (size_t)B * R * 16;
+  double* w_ymean = (double*)wp; wp += (size_t)B * 8;
+  double* w_ystd = (double*)wp; wp += (size_t)B * 8;
+  wp = (unsigned char*)(((uintptr_t)wp + 255) & ~(uintptr_t)255);
+  double* panels = (double*)wp;
+  TLBO_CUDA_CHECK(cudaMemcpyAsync(w_ymean, h_ymean, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  TLBO_CUDA_CHECK(cudaMemcpyAsync(w_ystd, h_ystd, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  double* rt = d_restart_theta ? d_restart_theta : w_theta;
+  double* rf = d_restart_f ? d_restart_f : w_f;
+  int32_t* ri = d_restart_info ? d_restart_info : w_info;
+
+  FitArgs a;
+  a.X = d_X; a.y = d_y; a.n = d_n; a.B = B; a.R = R; a.ncap = ncap; a.d = d; a.sp = sp;
+  a.p0 = d_p0; a.lo = d_lo; a.hi = d_hi; a.do_optimize = do_optimize;
+  a.restart_theta = rt; a.restart_f = rf; a.restart_info = ri;
+  a.panels = w.global_panels ? panels : nullptr; a.panel_stride = w.panel_stride;
+  if (d <= 12) {
+    rc = set_smem(gp_fit_kernel<12>, w.smem_fit);
+    if (rc) return rc;
+    gp_fit_kernel<12><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);
+  } else {
+    rc = set_smem(gp_fit_kernel<24>, w.smem_fit);
+    if (rc) return rc;
+    gp_fit_kernel<24><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);
+  }
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return launch_factorize(d_X, d_y, d_n, B, R, ncap, d, sp, rt, rf, w_ymean, w_ystd, pack, slot0, nullptr,
+                          nullptr, d_status, panels, w, s);
+}
+
+extern "C" int tlbo_gp_factorize_batched(const double* d_X, const double* d_y, const int32_t* d_n, int B,
+                                         int ncap, int d, const int32_t* h_types, const double* d_theta,
+                                         const double* h_ymean, const double* h_ystd, const tlbo_pack* pack,
+                                         int slot0, double* d_L, double* d_Kinv, int32_t* d_status,
+                                         void* d_work, void* stream) {
+  int rc = check_common(B, ncap, d, pack, slot0);
+  if (rc) return rc;
+  if (!pack || !d_status || !d_work) { tlbo_set_error("NULL pack, status or work"); return TLBO_E_BADARG; }
+  SpaceDesc sp;
+  rc = tlbo_make_space(d, h_types, &sp);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  WorkLayout w = plan(ncap, d);
+  unsigned char* wp = (unsigned char*)d_work;
+  double* w_ymean = (double*)wp; wp += (size_t)B * 8;
+  double* w_ystd = (double*)wp; wp += (size_t)B * 8;
+  wp = (unsigned char*)(((uintptr_t)wp + 255) & ~(uintptr_t)255);
+  double* panels = (double*)wp;
+  TLBO_CUDA_CHECK(cudaMemcpyAsync(w_ymean, h_ymean, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  TLBO_CUDA_CHECK(cudaMemcpyAsync(w_ystd, h_ystd, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  return launch_factorize(d_X, d_y, d_n, B, 1, ncap, d, sp, d_theta, nullptr, w_ymean, w_ystd, pack, slot0,
+                          d_L, d_Kinv, d_status, panels, w, s);
+}
+
+extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, const int32_t* d_n, int B,
+                                        int ncap, int d, const int32_t* h_types, const double* d_theta,
+                                        double* d_nll, double* d_grad, int32_t* d_status, void* d_work,
+                                        void* stream) {
+  int rc = check_common(B, ncap, d, nullptr, 0);
+  if (rc) return rc;
+  SpaceDesc sp;
+  rc = tlbo_make_space(d, h_types, &sp);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  WorkLayout w = plan(ncap, d);
+  NllArgs a;
+  a.X = d_X; a.y = d_y; a.n = d_n; a.B = B; a.ncap = ncap; a.d = d; a.sp = sp;
+  a.theta = d_theta; a.nll = d_nll; a.grad = d_grad; a.status = d_status;
+  a.panels = w.global_panels ? (double*)d_work : nullptr; a.panel_stride = w.panel_stride;
+  if (w.global_panels && !d_work) { tlbo_set_error("workspace required for this ncap"); return TLBO_E_BADARG; }
+  if (d <= 12) {
+    rc = set_smem(gp_nll_grad_kernel<12>, w.smem_fac);
+    if (rc) return rc;
+    gp_nll_grad_kernel<12><<<B, FIT_THREADS, w.smem_fac, s>>>(a);
+  } else {
+    rc = set_smem(gp_nll_grad_kernel<24>, w.smem_fac);
+    if (rc) return rc;
+    gp_nll_grad_kernel<24><<<B, FIT_THREADS, w.smem_fac, s>>>(a);
+  }
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

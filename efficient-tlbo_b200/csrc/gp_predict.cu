@@ -1,0 +1,458 @@
+// Posterior mean / variance kernels and the fused ensemble predict + EI + arg-max.
+//
+// Replaces reference tlbo/model/gp.py:250-305 (GaussianProcess._predict over skopt's
+// GaussianProcessRegressor.predict(return_std=True)), tlbo/facade/rgpe.py:141-153 /
+// base_facade.py:145-183 (ensemble combination), base_facade.py:110-143 (variance floor),
+// tlbo/acquisition_function/acquisition.py:130-177 (EI) and
+// tlbo/optimizer/ei_optimization.py:106-132 + tlbo/framework/smbo_offline.py:261-263
+// (ordering and first-unevaluated selection).
+//
+// Variance form: the reference evaluates diag - k^T K_inv k with K_inv = L^-T L^-1; here the
+// same quantity is evaluated as diag - |L^-1 k|^2 (triangular form, n^2 + 2n flops per
+// surrogate and candidate by SURVEY 8d's convention), which is the sum of squares the
+// reference's einsum expands to and cannot go negative by cancellation inside the sum.
+//
+// Fused kernel structure (per CTA: 8 warps, each owning NW tiles of 8 candidates):
+//   for each surrogate m (accumulation order):
+//     stage Xs_m, alpha_m, hyp_m in shared memory
+//     K* phase : lane (g = lane>>2, t = lane&3) computes k(x_cand[g], x_train[4*js + t]) for
+//                every j-step js -- exactly the B fragment (k = t, n = g) of an FP64
+//                mma.m8n8k4 -- parks it in a lane-private shared-memory slot, and
+//                accumulates k * alpha for the mean
+//     V phase  : L^-1 streamed through shared memory in row chunks; per pair of 8-row blocks
+//                acc[8 x 8] += Linv[8 x 4] * Kstar[4 x 8] on the FP64 tensor pipe (DMMA),
+//                lower-triangular blocks only; |v|^2 accumulated from the C fragments
+//     combine  : per candidate un-standardise, clip, weight, accumulate mu / var
+//   EI, NaN rule, exclusion of evaluated rows, lexicographic (ei, key, idx) arg-max.
+#include "tlbo_common.cuh"
+#include <float.h>
+
+#define PRED_THREADS 256
+#define PRED_WARPS 8
+
+// ---------------------------------------------------------------------------------------
+// Small-query predict: one warp per (query row, surrogate).
+struct PredSmallArgs {
+  tlbo_pack pack;
+  SpaceDesc sp;
+  const double* Xq; int Nq;
+  double* mu; double* var;
+};
+
+__global__ void __launch_bounds__(256) gp_predict_small_kernel(PredSmallArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncap = a.pack.ncap, d = a.pack.d, dc = a.sp.d_cont, ldl = TLBO_LDL(ncap);
+  double* kbuf = reinterpret_cast<double*>(smem) + (size_t)wid * (ncap + TLBO_HMAX);
+  double* xq = kbuf + ncap;
+  const long long total = (long long)a.Nq * a.pack.M;
+  for (long long item = (long long)blockIdx.x * warps + wid; item < total; item += (long long)gridDim.x * warps) {
+    const int m = (int)(item / a.Nq), q = (int)(item - (long long)m * a.Nq);
+    const int n = a.pack.d_n[m];
+    const double* hyp = a.pack.d_hyp + (size_t)m * TLBO_HYP_STRIDE;
+    const double* Xs = a.pack.d_Xs + (size_t)m * ncap * d;
+    const double* al = a.pack.d_alpha + (size_t)m * ncap;
+    const double* Li = a.pack.d_Linv + (size_t)m * ncap * ldl;
+    const double c = hyp[0], ymean = hyp[2], ystd = hyp[3], diag = hyp[4];
+    __syncwarp();
+    if (lane < d) {
+      double v = a.Xq[(size_t)q * d + a.sp.perm[lane]];
+      if (lane < dc) v *= hyp[8 + lane];
+      xq[lane] = v;
+    }
+    __syncwarp();
+    double mpart = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      const double* xj = Xs + (size_t)j * d;
+      double s = 0.0, hs = 0.0;
+      for (int p = 0; p < dc; p++) { const double df = xq[p] - xj[p]; s += df * df; }
+      for (int p = dc; p < d; p++) if (xq[p] != xj[p]) hs += hyp[8 + p];
+      const double k = matern_hamming(c, s, hs);
+      kbuf[j] = k;
+      mpart += k * al[j];
+    }
+    __syncwarp();
+    double qpart = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double* row = Li + (size_t)i * ldl;
+      double v = 0.0;
+      for (int j = 0; j <= i; j++) v += row[j] * kbuf[j];
+      qpart += v * v;
+    }
+    const double mean = warp_sum(mpart);
+    const double qq = warp_sum(qpart);
+    if (lane == 0) {
+      double yv = diag - qq;
+      if (yv < 0.0) yv = 0.0;
+      const double sd = sqrt(yv);
+      double var = sd * sd;
+      if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;   // np.clip keeps NaN
+      a.mu[(size_t)m * a.Nq + q] = mean * ystd + ymean;
+      a.var[(size_t)m * a.Nq + q] = var * (ystd * ystd);
+    }
+  }
+}
+
+extern "C" int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, const double* d_Xq, int Nq,
+                               double* d_mu, double* d_var, void* stream) {
+  if (!pack || Nq <= 0) { tlbo_set_error("bad pack / Nq"); return TLBO_E_BADARG; }
+  PredSmallArgs a;
+  a.pack = *pack;
+  int rc = tlbo_make_space(pack->d, h_types, &a.sp);
+  if (rc) return rc;
+  a.Xq = d_Xq; a.Nq = Nq; a.mu = d_mu; a.var = d_var;
+  const int warps = 8;
+  const size_t smem = (size_t)warps * (pack->ncap + TLBO_HMAX) * sizeof(double);
+  if (smem > 200 * 1024) { tlbo_set_error("ncap too large for predict_small"); return TLBO_E_TOOLARGE; }
+  if (smem > 48 * 1024)
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(gp_predict_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long items = (long long)Nq * pack->M;
+  int grid = (int)((items + warps - 1) / warps);
+  if (grid > 148 * 8) grid = 148 * 8;
+  gp_predict_small_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(a);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused predict + EI + arg-max.
+struct Best { double ei; double key; long long idx; };
+
+__device__ __forceinline__ bool better(const Best& a, const Best& b) {
+  // lexsort((key, ei))[::-1] order: larger ei first, then larger key, then larger index
+  if (a.ei != b.ei) return a.ei > b.ei;
+  if (a.key != b.key) return a.key > b.key;
+  return a.idx > b.idx;
+}
+
+__device__ __forceinline__ Best warp_best(Best v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best w;
+    w.ei = __shfl_xor_sync(0xffffffffu, v.ei, o);
+    w.key = __shfl_xor_sync(0xffffffffu, v.key, o);
+    w.idx = __shfl_xor_sync(0xffffffffu, v.idx, o);
+    if (better(w, v)) v = w;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct FusedArgs {
+  tlbo_pack pack;
+  SpaceDesc sp;
+  const double* w; const int32_t* skip; int mode;
+  const double* cand; long long N;
+  double eta, par, var_floor;
+  const double* keys; const long long* excluded; int n_excl; long long idx_offset;
+  double* mu; double* var; double* ei;
+  double* partial;       // [grid, 4]
+  int rc_rows;           // Linv rows per shared-memory chunk (multiple of 16)
+  int njmax;             // ncap / 4
+};
+
+// shared-memory plan (doubles): cand [TILE * d] | Xs [ncap * d] | alpha [ncap] | hyp [32] |
+//   Linv chunk [rc_rows * ldl] | spill [8 warps][njmax][NW][32] | comb [8 warps][NW*8][2]
+template <int NW>
+__global__ void __launch_bounds__(PRED_THREADS, 1) predict_ei_fused_kernel(FusedArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int ncap = a.pack.ncap, d = a.pack.d, dc = a.sp.d_cont, ldl = TLBO_LDL(ncap);
+  constexpr int WC = NW * 8;                 // candidates per warp
+  constexpr int TILE = PRED_WARPS * WC;      // candidates per CTA iteration
+  double* s_cand = reinterpret_cast<double*>(smem);
+  double* s_Xs = s_cand + (size_t)TILE * d;
+  double* s_alpha = s_Xs + (size_t)ncap * d;
+  double* s_hyp = s_alpha + ncap;
+  double* s_Linv = s_hyp + TLBO_HYP_STRIDE;
+  double* s_spill = s_Linv + (size_t)a.rc_rows * ldl;
+  double* s_comb = s_spill + (size_t)PRED_WARPS * a.njmax * NW * 32;
+  double* my_spill = s_spill + (size_t)wid * a.njmax * NW * 32;
+  double* my_comb = s_comb + (size_t)wid * WC * 2;
+
+  Best best; best.ei = -INFINITY; best.key = -INFINITY; best.idx = -1;
+  double negcount = 0.0;
+  const long long ntiles = (a.N + TILE - 1) / TILE;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TILE;
+    __syncthreads();
+    // stage the candidate tile (coalesced, permuted columns)
+    {
+      const long long lim = (a.N - row0 < TILE ? a.N - row0 : TILE) * d;
+      const double* src = a.cand + (size_t)row0 * d;
+      for (int idx = tid; idx < TILE * d; idx += PRED_THREADS) {
+        const int r = idx / d, p = idx - r * d;
+        const long long sidx = (long long)r * d + a.sp.perm[p];
+        s_cand[idx] = (sidx < lim) ? src[sidx] : 0.0;
+      }
+    }
+    // per-lane ensemble accumulators: lane owns candidate (lane) of this warp when WC == 32,
+    // in general candidate index cl = lane (valid if lane < WC)
+    double acc_mu = 0.0, acc_var = 0.0, wsum = 0.0;
+    for (int m = 0; m < a.pack.M; m++) {
+      const double wm = a.w[m];
+      if (a.skip && a.skip[m]) continue;
+      const int n = a.pack.d_n[m];
+      if (n <= 0) continue;
+      __syncthreads();
+      {
+        const double* gX = a.pack.d_Xs + (size_t)m * ncap * d;
+        for (int idx = tid; idx < n * d; idx += PRED_THREADS) s_Xs[idx] = gX[idx];
+        const double* gA = a.pack.d_alpha + (size_t)m * ncap;
+        for (int idx = tid; idx < ncap; idx += PRED_THREADS) s_alpha[idx] = gA[idx];
+        if (tid < TLBO_HYP_STRIDE) s_hyp[tid] = a.pack.d_hyp[(size_t)m * TLBO_HYP_STRIDE + tid];
+      }
+      __syncthreads();
+      const double c = s_hyp[0], ymean = s_hyp[2], ystd = s_hyp[3], diag = s_hyp[4];
+      const int nj = (n + 3) >> 2;            // j-steps of 4 training rows
+      // ---- K* phase
+      double mpart[NW];
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        mpart[w] = 0.0;
+        const double* xc = s_cand + (size_t)(wid * WC + w * 8 + g) * d;
+        double xs[TLBO_MAX_D];
+#pragma unroll
+        for (int p = 0; p < TLBO_MAX_D; p++)
+          if (p < d) xs[p] = (p < dc) ? xc[p] * s_hyp[8 + p] : xc[p];
+        for (int js = 0; js < nj; js++) {
+          const int j = 4 * js + t;
+          double k = 0.0;
+          if (j < n) {
+            const double* xj = s_Xs + (size_t)j * d;
+            double s = 0.0, hs = 0.0;
+#pragma unroll
+            for (int p = 0; p < TLBO_MAX_D; p++) {
+              if (p < dc) { const double df = xs[p] - xj[p]; s += df * df; }
+              else if (p < d) { if (xs[p] != xj[p]) hs += s_hyp[8 + p]; }
+            }
+            k = matern_hamming(c, s, hs);
+            mpart[w] += k * s_alpha[j];
+          }
+          my_spill[((size_t)js * NW + w) * 32 + lane] = k;
+        }
+      }
+      // ---- V phase: q = |Linv k|^2 via DMMA, Linv streamed in row chunks
+      double qpart[NW][2];
+#pragma unroll
+      for (int w = 0; w < NW; w++) { qpart[w][0] = 0.0; qpart[w][1] = 0.0; }
+      const int nib = (n + 7) >> 3;           // 8-row blocks
+      const double* gL = a.pack.d_Linv + (size_t)m * ncap * ldl;
+      for (int r0 = 0; r0 < nib * 8; r0 += a.rc_rows) {
+        const int rows = (nib * 8 - r0 < a.rc_rows) ? nib * 8 - r0 : a.rc_rows;
+        __syncthreads();
+        {
+          // only columns < r0 + rows are ever read (lower triangular)
+          const double* src = gL + (size_t)r0 * ldl;
+          const int cnt = rows * ldl;
+          for (int idx = tid; idx < cnt; idx += PRED_THREADS) s_Linv[idx] = src[idx];
+        }
+        __syncthreads();
+        for (int ib = 0; ib * 8 < rows; ib += 2) {
+          const bool two = (ib + 1) * 8 < rows;
+          const int ig = (r0 >> 3) + ib;      // global 8-row block index of the first block
+          const int jend = two ? 2 * (ig + 2) : 2 * (ig + 1);
+          double acc0[NW][2], acc1[NW][2];
+#pragma unroll
+          for (int w = 0; w < NW; w++) { acc0[w][0] = acc0[w][1] = 0.0; acc1[w][0] = acc1[w][1] = 0.0; }
+          const double* rowA0 = s_Linv + (size_t)(ib * 8 + g) * ldl + t;
+          const double* rowA1 = rowA0 + (size_t)8 * ldl;
+          const int jlim = jend < nj ? jend : nj;
+          for (int js = 0; js < jlim; js++) {
+            const double a0 = rowA0[4 * js];
+            const double a1 = two ? rowA1[4 * js] : 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+              const double b = my_spill[((size_t)js * NW + w) * 32 + lane];
+              dmma8x8x4(acc0[w][0], acc0[w][1], a0, b);
+              if (two) dmma8x8x4(acc1[w][0], acc1[w][1], a1, b);
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < NW; w++) {
+            qpart[w][0] += acc0[w][0] * acc0[w][0] + acc1[w][0] * acc1[w][0];
+            qpart[w][1] += acc0[w][1] * acc0[w][1] + acc1[w][1] * acc1[w][1];
+          }
+        }
+      }
+      // ---- reduce: mean over the 4 lanes of a group, q over the 8 groups
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        double mv = mpart[w];
+        mv += __shfl_xor_sync(0xffffffffu, mv, 1);
+        mv += __shfl_xor_sync(0xffffffffu, mv, 2);
+        double q0 = qpart[w][0], q1 = qpart[w][1];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        }
+        if (t == 0) my_comb[(w * 8 + g) * 2 + 0] = mv;                 // mean of candidate g
+        if (g == 0) { my_comb[(w * 8 + 2 * t) * 2 + 1] = q0; my_comb[(w * 8 + 2 * t + 1) * 2 + 1] = q1; }
+      }
+      __syncwarp();
+      if (lane < WC) {
+        const double mean = my_comb[lane * 2 + 0], qq = my_comb[lane * 2 + 1];
+        double yv = diag - qq;
+        if (yv < 0.0) yv = 0.0;
+        const double sd = sqrt(yv);
+        double var = sd * sd;
+        if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;
+        const double mu_m = mean * ystd + ymean;
+        const double var_m = var * (ystd * ystd);
+        if (a.mode == 0) {
+          acc_mu += wm * mu_m;
+          acc_var += wm * wm * var_m;
+        } else {
+          if (m == 0) { acc_mu = mu_m; acc_var = var_m; }
+          else { acc_mu += wm * mu_m; wsum += wm; }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- EI + selection
+    if (lane < WC) {
+      const long long row = row0 + wid * WC + lane;
+      if (row < a.N) {
+        double mu = acc_mu, var = acc_var;
+        if (a.mode == 1) mu = mu / (0.75 + wsum);
+        if (var < a.var_floor) var = a.var_floor;
+        if (var != var) var = a.var_floor;
+        const double s = sqrt(var);
+        double f;
+        if (s == 0.0) f = 0.0;
+        else {
+          const double dm = a.eta - mu - a.par;
+          const double z = dm / s;
+          const double cdf = 0.5 * erfc(-z * 0.7071067811865476);
+          const double pdf = exp(-0.5 * z * z) * 0.3989422804014327;
+          f = dm * cdf + s * pdf;
+        }
+        if (f < 0.0) negcount += 1.0;
+        if (f != f) f = -DBL_MAX;
+        if (a.mu) a.mu[row] = mu;
+        if (a.var) a.var[row] = var;
+        if (a.ei) a.ei[row] = f;
+        const long long gidx = a.idx_offset + row;
+        bool excl = false;
+        int lo = 0, hi = a.n_excl - 1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          const long long v = a.excluded[mid];
+          if (v == gidx) { excl = true; break; }
+          if (v < gidx) lo = mid + 1; else hi = mid - 1;
+        }
+        if (!excl) {
+          Best cnd; cnd.ei = f; cnd.key = a.keys ? a.keys[row] : 0.0; cnd.idx = gidx;
+          if (best.idx < 0 || better(cnd, best)) best = cnd;
+        }
+      }
+    }
+  }
+  // ---- block arg-max
+  __shared__ Best s_best[PRED_WARPS];
+  __shared__ double s_neg[PRED_WARPS];
+  Best wb = best;
+  if (wb.idx < 0) { wb.ei = -INFINITY; wb.key = -INFINITY; }
+  wb = warp_best(wb);
+  const double wn = warp_sum(negcount);
+  __syncthreads();
+  if (lane == 0) { s_best[wid] = wb; s_neg[wid] = wn; }
+  __syncthreads();
+  if (tid == 0) {
+    Best bb = s_best[0];
+    double nn = s_neg[0];
+    for (int w = 1; w < PRED_WARPS; w++) { if (better(s_best[w], bb)) bb = s_best[w]; nn += s_neg[w]; }
+    double* o = a.partial + (size_t)blockIdx.x * 4;
+    o[0] = bb.ei; o[1] = bb.key; o[2] = (double)bb.idx; o[3] = nn;
+  }
+}
+
+__global__ void argmax_final_kernel(const double* partial, int nparts, double* out) {
+  // single warp
+  Best b; b.ei = -INFINITY; b.key = -INFINITY; b.idx = -1;
+  double nn = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 32) {
+    Best c; c.ei = partial[i * 4]; c.key = partial[i * 4 + 1]; c.idx = (long long)partial[i * 4 + 2];
+    nn += partial[i * 4 + 3];
+    if (c.idx >= 0 && (b.idx < 0 || better(c, b))) b = c;
+  }
+  if (b.idx < 0) { b.ei = -INFINITY; b.key = -INFINITY; }
+  b = warp_best(b);
+  nn = warp_sum(nn);
+  if (threadIdx.x == 0) { out[0] = b.ei; out[1] = b.key; out[2] = (double)b.idx; out[3] = nn; }
+}
+
+struct FusedPlan { int nw; int rc_rows; size_t smem; int grid; };
+
+static bool fused_plan(int ncap, int d, long long N, FusedPlan* pl) {
+  const int ldl = TLBO_LDL(ncap);
+  const int njmax = ncap / 4;
+  const size_t limit = 227 * 1024 - 2048;
+  for (int nw = 4; nw >= 1; nw >>= 1) {
+    const size_t tile = (size_t)PRED_WARPS * nw * 8;
+    const size_t fixed = sizeof(double) * (tile * d + (size_t)ncap * d + ncap + TLBO_HYP_STRIDE +
+                                           (size_t)PRED_WARPS * njmax * nw * 32 + (size_t)PRED_WARPS * nw * 8 * 2);
+    if (fixed + sizeof(double) * 16 * ldl > limit) continue;
+    size_t rows = (limit - fixed) / (sizeof(double) * ldl);
+    rows = (rows / 16) * 16;
+    if (rows > (size_t)((ncap + 15) / 16) * 16) rows = (size_t)((ncap + 15) / 16) * 16;
+    if (rows < 16) continue;
+    pl->nw = nw;
+    pl->rc_rows = (int)rows;
+    pl->smem = fixed + sizeof(double) * rows * ldl;
+    const long long ntiles = (N + (long long)tile - 1) / (long long)tile;
+    long long grid = ntiles < 148 ? ntiles : 148;
+    // several waves of tiles per CTA keep the tail short; one CTA per SM (smem-bound occupancy)
+    pl->grid = (int)(grid < 1 ? 1 : grid);
+    return true;
+  }
+  return false;
+}
+
+extern "C" int64_t tlbo_predict_ei_workspace_bytes(int64_t N) {
+  (void)N;
+  return (int64_t)(148 * 4 * sizeof(double) + 256);
+}
+
+extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
+                                     const int32_t* d_skip, int mode, const double* d_cand, int64_t N,
+                                     double eta, double par, double var_floor, const double* d_keys,
+                                     const int64_t* d_excluded, int n_excl, int64_t idx_offset, double* d_best,
+                                     double* d_mu, double* d_var, double* d_ei, void* d_work, void* stream) {
+  if (!pack || N <= 0 || !d_w || !d_cand || !d_best || !d_work) { tlbo_set_error("bad arguments"); return TLBO_E_BADARG; }
+  if (pack->ncap % 8 != 0) { tlbo_set_error("pack ncap must be a multiple of 8"); return TLBO_E_BADARG; }
+  FusedArgs a;
+  a.pack = *pack;
+  int rc = tlbo_make_space(pack->d, h_types, &a.sp);
+  if (rc) return rc;
+  FusedPlan pl;
+  if (!fused_plan(pack->ncap, pack->d, N, &pl)) { tlbo_set_error("surrogates too large for the fused kernel"); return TLBO_E_TOOLARGE; }
+  a.w = d_w; a.skip = d_skip; a.mode = mode; a.cand = d_cand; a.N = N;
+  a.eta = eta; a.par = par; a.var_floor = var_floor;
+  a.keys = d_keys; a.excluded = (const long long*)d_excluded; a.n_excl = d_excluded ? n_excl : 0;
+  a.idx_offset = idx_offset; a.mu = d_mu; a.var = d_var; a.ei = d_ei;
+  a.partial = (double*)d_work; a.rc_rows = pl.rc_rows; a.njmax = pack->ncap / 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pl.nw == 4) {
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(predict_ei_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    predict_ei_fused_kernel<4><<<pl.grid, PRED_THREADS, pl.smem, s>>>(a);
+  } else if (pl.nw == 2) {
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(predict_ei_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    predict_ei_fused_kernel<2><<<pl.grid, PRED_THREADS, pl.smem, s>>>(a);
+  } else {
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(predict_ei_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    predict_ei_fused_kernel<1><<<pl.grid, PRED_THREADS, pl.smem, s>>>(a);
+  }
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  argmax_final_kernel<<<1, 32, 0, s>>>(a.partial, pl.grid, d_best);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -50,6 +50,7 @@ struct LbfgsbState {
   double d[LB_NMAX], z[LB_NMAX];
   double S[LB_M][LB_NMAX], Y[LB_M][LB_NMAX];
   double B[LB_NMAX][LB_NMAX];
+  double Wk[LB_NMAX][LB_NMAX];   // scratch for the reduced Cholesky (kept off the stack)
   double theta;
   int col;
   int iwhere[LB_NMAX];
@@ -207,8 +208,8 @@ TLBO_HD void cauchy(LbfgsbState& s) {
 }
 
 // Dense Cholesky solve of the free-variable block.  Returns false if not PD.
-TLBO_HD bool solve_free(const LbfgsbState& s, const int* ind, int nsub, const double* rhs, double* out) {
-  double A[LB_NMAX][LB_NMAX];
+TLBO_HD bool solve_free(LbfgsbState& s, const int* ind, int nsub, const double* rhs, double* out) {
+  double (*A)[LB_NMAX] = s.Wk;
   for (int a = 0; a < nsub; a++)
     for (int b = 0; b <= a; b++) A[a][b] = s.B[ind[a]][ind[b]];
   for (int k = 0; k < nsub; k++) {
@@ -516,6 +517,10 @@ TLBO_HD void lbfgsb_init(LbfgsbState& s, int n, const double* x0, const double* 
   s.factr = 1.0e7; s.pgtol = 1.0e-5; s.maxiter = 15000; s.maxfun = 15000; s.maxls = 20;
   s.col = 0; s.theta = 1.0;
   s.iter = 0; s.nfgv = 0; s.nskip = 0; s.phase = 0; s.status = LB_ERROR;
+  s.ls_brackt = 0; s.ls_stage = 1;
+  s.ls_ginit = s.ls_gtest = s.ls_gx = s.ls_gy = s.ls_finit = s.ls_fx = s.ls_fy = 0.0;
+  s.ls_stx = s.ls_sty = s.ls_stmin = s.ls_stmax = s.ls_width = s.ls_width1 = 0.0;
+  s.stp = 1.0; s.stpmx = 1.0; s.gd = s.gdold = 0.0; s.f = s.fold = s.f_last = 0.0;
   lb::rebuild_B(s);
 }
 

@@ -1,0 +1,124 @@
+// Ensemble-weighting kernels.
+//
+//  * rank_loss_counts: bit-exact integer mis-ranked-pair counts -- replaces the pure-Python
+//    O(S * (K+1) * n^2) loops of RGPE.train / TransBO_RGPE.train
+//    (reference tlbo/facade/rgpe.py:74-104, tlbo/facade/topo.py:72-104) and the discordant
+//    pair count of TST.train (tlbo/facade/tst.py:37-43).  The normal draws themselves are
+//    produced on the host by legacy np.random in the reference's draw order and uploaded;
+//    the kernel only compares and counts.
+//  * pairwise_logistic_loss_grad: Loss_func / Loss_der with func_id = 3
+//    (reference tlbo/utils/scipy_solver.py:6-78) evaluated once per SLSQP callback.
+#include "tlbo_common.cuh"
+
+#define RL_THREADS 128
+
+__global__ void __launch_bounds__(RL_THREADS) rank_loss_kernel(const double* __restrict__ y,
+                                                               const double* __restrict__ ys, int n, int Mr,
+                                                               const int32_t* __restrict__ row_lo,
+                                                               const int32_t* __restrict__ row_hi, int upper_only,
+                                                               long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* sy = reinterpret_cast<double*>(smem);
+  double* ss = sy + n;
+  __shared__ unsigned long long total;
+  const int item = blockIdx.x;           // s * Mr + m
+  const int m = item % Mr;
+  const double* src = ys + (size_t)item * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { sy[i] = y[i]; ss[i] = src[i]; }
+  if (threadIdx.x == 0) total = 0ull;
+  __syncthreads();
+  const int lo = row_lo[m], hi = row_hi[m];
+  unsigned int cnt = 0;
+  // work item = (i, j-chunk of 32): lanes take consecutive j, warps take rows
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = lo + wid; i < hi; i += nw) {
+    const double yi = sy[i], si = ss[i];
+    const int j0 = upper_only ? i + 1 : 0;
+    for (int j = j0 + lane; j < n; j += 32) {
+      const bool a = yi < sy[j];
+      const bool b = si < ss[j];
+      cnt += (a != b) ? 1u : 0u;
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) atomicAdd(&total, (unsigned long long)cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[item] = (long long)total;
+}
+
+extern "C" int tlbo_rank_loss_counts(const double* d_y, const double* d_ys, int n, int S, int Mr,
+                                     const int32_t* d_row_lo, const int32_t* d_row_hi, int upper_only,
+                                     int64_t* d_counts, void* stream) {
+  if (n <= 0 || S <= 0 || Mr <= 0) { tlbo_set_error("bad n/S/Mr"); return TLBO_E_BADARG; }
+  const size_t smem = 2 * (size_t)n * sizeof(double);
+  if (smem > 200 * 1024) { tlbo_set_error("n too large for rank_loss_counts"); return TLBO_E_TOOLARGE; }
+  if (smem > 48 * 1024)
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(rank_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rank_loss_kernel<<<S * Mr, RL_THREADS, smem, (cudaStream_t)stream>>>(d_y, d_ys, n, Mr, d_row_lo, d_row_hi,
+                                                                        upper_only, (long long*)d_counts);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+#define PL_THREADS 256
+
+__global__ void __launch_bounds__(PL_THREADS) pair_logistic_kernel(const double* __restrict__ A,
+                                                                   const double* __restrict__ y,
+                                                                   const double* __restrict__ w, int n, int m,
+                                                                   double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* sp = reinterpret_cast<double*>(smem);   // predictions [n]
+  double* sy = sp + n;                            // [n]
+  double* sc = sy + n;                            // per-row gradient coefficient [n]
+  double* red = sc + n;                           // [32]
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int i = tid; i < n; i += T) {
+    double p = 0.0;
+    for (int k = 0; k < m; k++) p += A[(size_t)i * m + k] * w[k];
+    sp[i] = p;
+    sy[i] = y[i];
+  }
+  __syncthreads();
+  // Row r owns the pairs in which it is the LOWER-y member (reference pair (i, j) with
+  // y_i > y_j has j = r): loss term log(1 + exp(p_r - p_i)), coefficient +s on row r, -s on row i.
+  double loss = 0.0, npairs = 0.0;
+  for (int r = tid; r < n; r += T) {
+    const double yr = sy[r], pr = sp[r];
+    double coef = 0.0;
+    for (int q = 0; q < n; q++) {
+      const double yq = sy[q];
+      if (yq > yr) {
+        const double ez = exp(pr - sp[q]);
+        loss += log(1.0 + ez);
+        npairs += 1.0;
+        coef += ez / (1.0 + ez);
+      } else if (yq < yr) {
+        const double ez = exp(sp[q] - pr);
+        coef -= ez / (1.0 + ez);
+      }
+    }
+    sc[r] = coef;
+  }
+  const double tl = block_sum(loss, red);
+  const double tp = block_sum(npairs, red);
+  __syncthreads();
+  if (tid == 0) { out[0] = (tp > 0.0) ? tl / tp : 0.0; out[1] = tp; }
+  for (int k = tid; k < m; k += T) {
+    double gk = 0.0;
+    for (int r = 0; r < n; r++) gk += sc[r] * A[(size_t)r * m + k];
+    out[2 + k] = (tp > 0.0) ? gk / tp : 0.0;
+  }
+}
+
+extern "C" int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const double* d_w, int n,
+                                                int m, double* d_out, void* stream) {
+  if (n <= 0 || m <= 0) { tlbo_set_error("bad n/m"); return TLBO_E_BADARG; }
+  const size_t smem = (3 * (size_t)n + 32) * sizeof(double);
+  if (smem > 200 * 1024) { tlbo_set_error("n too large for pairwise_logistic"); return TLBO_E_TOOLARGE; }
+  if (smem > 48 * 1024)
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(pair_logistic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_logistic_kernel<<<1, PL_THREADS, smem, (cudaStream_t)stream>>>(d_A, d_y, d_w, n, m, d_out);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,165 @@
+/* tlbo_b200 -- C ABI of the B200-native surrogate-and-acquisition hot path.
+ *
+ * The reference (thomas-young-2013/efficient-tlbo) is pure Python and has no
+ * FFI; its boundary for this path is the duck-typed Python surrogate / facade /
+ * acquisition interface.  This header declares the C entry
+ * points that the Python mirror of that interface (efficient-tlbo_b200/tlbo_b200)
+ * binds with ctypes, each citing the reference call site(s) it replaces.
+ * INTEGRATION.md shows the ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array is dense row-major float64 unless
+ *    stated; pointers named d_* are DEVICE pointers (current CUDA device), pointers
+ *    named h_* are HOST pointers.
+ *  - `stream` is a cudaStream_t passed as void*; every entry point only enqueues
+ *    work on that stream (no implicit synchronisation) unless stated.
+ *  - return value: 0 on success, a positive cudaError_t, or a negative TLBO_E_*.
+ *    tlbo_last_error() returns a static message for the calling thread.
+ *  - input columns follow the reference's encoding
+ *    (tlbo/config_space/util.py:11-30): `h_types[d]` is the vector produced by
+ *    get_types (tlbo/model/util_funcs.py:14-55): 0 = continuous / integer /
+ *    constant column, >0 = categorical with that many choices.
+ *  - theta layout (log space) = the reference kernel tree's
+ *    (tlbo/model/model_builder.py:28-72): [log c, log l_cont.., log l_cat.., log s2],
+ *    H = d + 2.
+ */
+#ifndef TLBO_B200_H
+#define TLBO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLBO_MAX_D 22          /* H = d + 2 <= 24 */
+#define TLBO_E_BADARG (-1)
+#define TLBO_E_TOOLARGE (-2)
+
+const char* tlbo_last_error(void);
+int tlbo_version(void);
+
+/* A batch ("pack") of fitted GP surrogates laid out for the predict kernels.
+ * All arrays are device memory owned by the caller; per-model arrays are strided by
+ * `ncap` rows (ncap >= max n, multiple of 8).  Columns of Xs are PERMUTED: the
+ * continuous columns first (scaled by 1/l), then the categorical ones (raw codes).
+ *   hyp row (TLBO_HYP_STRIDE doubles): [c, s2, y_mean, y_std, c+s2, 0,0,0,
+ *        then per permuted column p: cont -> 1/l_p, cat -> 1/(2 l_p^2)]
+ *   Linv rows are strided by TLBO_LDL(ncap) = ncap + 4 doubles (bank-conflict-free
+ *   fragment loads for the FP64 mma in the fused predict kernel).                  */
+#define TLBO_HYP_STRIDE 32
+#define TLBO_LDL(ncap) ((ncap) + 4)
+typedef struct tlbo_pack {
+  int32_t M;            /* number of surrogates                                   */
+  int32_t ncap;         /* row capacity / stride                                  */
+  int32_t d;            /* input columns                                          */
+  int32_t reserved;
+  int32_t* d_n;         /* [M]            observations per surrogate              */
+  double* d_Xs;         /* [M, ncap, d]   permuted + scaled training inputs       */
+  double* d_hyp;        /* [M, TLBO_HYP_STRIDE]                                   */
+  double* d_alpha;      /* [M, ncap]      K^-1 y                                  */
+  double* d_Linv;       /* [M, ncap, TLBO_LDL(ncap)] row-major lower-triangular L^-1 */
+  double* d_theta;      /* [M, d+2]       fitted log hyper-parameters             */
+} tlbo_pack;
+
+/* Batched MAP fit of B independent GP surrogates -- replaces
+ * GaussianProcess._train/_nll/_optimize (tlbo/model/gp.py:98-248) and the skopt /
+ * sklearn GaussianProcessRegressor.fit + log_marginal_likelihood they call, for every
+ * surrogate of build_source_surrogates / build_single_surrogate
+ * (tlbo/facade/base_facade.py:58-108) at once.
+ *   d_X   [B, ncap, d]  raw inputs, reference column order (non-finite already -> -1)
+ *   d_y   [B, ncap]     targets AFTER the reference's y normalisation
+ *   d_n   [B]           rows in use
+ *   d_p0  [R, H]        L-BFGS-B start points (row 0 = kernel default theta; rows 1..
+ *                       = the sampled restarts of gp.py:211-239), shared by all B
+ *   d_lo, d_hi [H]      log-space bounds
+ *   h_ymean, h_ystd [B] BaseGP._normalize_y statistics (base_gp.py:48-64), stored in the pack
+ *   do_optimize         0 -> keep p0 row 0 (gp.py do_optimize=False)
+ * Outputs: pack slots slot0 .. slot0+B-1 are filled (n, Xs, hyp, alpha, Linv, theta);
+ *   d_restart_theta [B, R, H], d_restart_f [B, R], d_restart_info [B, R, 4] int32
+ *   (nfev, nit, status, noise bumps) and d_status [B] int32 (0 ok, 1 final Cholesky
+ *   failed -> the reference would raise LinAlgError, 2 no finite optimum) may be NULL
+ *   except d_status.  d_work: scratch of tlbo_gp_fit_workspace_bytes() bytes.       */
+int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const int32_t* d_n, int B, int ncap, int d,
+                        const int32_t* h_types, const double* d_p0, int R, const double* d_lo,
+                        const double* d_hi, const double* h_ymean, const double* h_ystd, int do_optimize,
+                        const tlbo_pack* pack, int slot0, double* d_restart_theta, double* d_restart_f,
+                        int32_t* d_restart_info, int32_t* d_status, void* d_work, void* stream);
+int64_t tlbo_gp_fit_workspace_bytes(int B, int R, int ncap, int d);
+
+/* Factorise B surrogates at GIVEN theta (skopt GaussianProcessRegressor.fit with
+ * optimizer=None: L = chol(K), alpha_ = K^-1 y, K_inv_ = L^-T L^-1) and fill pack slots.
+ * Optional dense outputs for parity checks: d_L [B, ncap, ncap], d_Kinv [B, ncap, ncap]. */
+int tlbo_gp_factorize_batched(const double* d_X, const double* d_y, const int32_t* d_n, int B, int ncap,
+                              int d, const int32_t* h_types, const double* d_theta, const double* h_ymean,
+                              const double* h_ystd, const tlbo_pack* pack, int slot0, double* d_L,
+                              double* d_Kinv, int32_t* d_status, void* d_work, void* stream);
+
+/* NLL (+ log-priors) and gradient at given theta for B surrogates -- one evaluation of
+ * GaussianProcess._nll (tlbo/model/gp.py:164-197).  d_nll [B], d_grad [B, H],
+ * d_status [B] (1 = Cholesky failed -> nll 1e25, grad 0 as the reference returns).    */
+int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, const int32_t* d_n, int B, int ncap, int d,
+                             const int32_t* h_types, const double* d_theta, double* d_nll, double* d_grad,
+                             int32_t* d_status, void* d_work, void* stream);
+
+/* Per-surrogate posterior mean / variance at a SMALL query set -- replaces
+ * GaussianProcess._predict (tlbo/model/gp.py:250-305) + skopt predict(return_std=True)
+ * for the K source predicts at the n target points (tlbo/facade/rgpe.py:27-30,
+ * topo_variant1.py:27-35) and the CV-fold predicts (rgpe.py:56-70).
+ * d_Xq [Nq, d] reference column order; outputs d_mu, d_var [M, Nq] un-standardised,
+ * variance clipped at 1e-10 before un-standardising as gp.py:297-300 does.            */
+int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, const double* d_Xq, int Nq, double* d_mu,
+                    double* d_var, void* stream);
+
+/* Fused ensemble predict + EI + arg-max over a candidate pool -- replaces, in one pass,
+ * (K+1) x GaussianProcess.predict, RGPE.predict / combine_predictions
+ * (tlbo/facade/rgpe.py:141-153, base_facade.py:145-183), the facade variance floor
+ * (base_facade.py:140-141), EI._compute (tlbo/acquisition_function/acquisition.py:130-177),
+ * the NaN rule of __call__ (:73-76), lexsort((rand, ei))[::-1]
+ * (tlbo/optimizer/ei_optimization.py:126-132) and the first-unevaluated scan
+ * (tlbo/framework/smbo_offline.py:261-263).
+ *   d_w [M]           ensemble weights in ACCUMULATION order (w == 0 and skip -> model skipped)
+ *   d_skip [M] int32  1 = leave the surrogate out (RGPE ignored_flag), may be NULL
+ *   mode              0: mu = sum w mu_m, var = sum w^2 var_m   (RGPE / 'idp_lc')
+ *                     1: TST: mu = (mu_0 + sum_{m>0} w_m mu_m) / (0.75 + sum w), var = var_0
+ *   d_cand [N, d]     candidate rows, reference column order
+ *   eta, par          EI incumbent and xi
+ *   var_floor         facade / model variance threshold (1e-10 or 1e-5)
+ *   d_keys [N]        tie-break keys rng.rand(N); NULL -> ties resolved by larger index
+ *   d_excluded [n_excl] int64 SORTED global row ids already evaluated (may be NULL)
+ *   idx_offset        global row id of d_cand row 0 (candidate-pool sharding)
+ * Outputs: d_best [4] doubles = (ei, key, global idx as double, #EI<0) of the best
+ *   non-excluded row; optional per-row d_mu, d_var, d_ei [N] (after floor / NaN rule).
+ *   d_work: scratch of tlbo_predict_ei_workspace_bytes(N) bytes.                       */
+int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
+                          const int32_t* d_skip, int mode, const double* d_cand, int64_t N, double eta,
+                          double par, double var_floor, const double* d_keys, const int64_t* d_excluded,
+                          int n_excl, int64_t idx_offset, double* d_best, double* d_mu, double* d_var,
+                          double* d_ei, void* d_work, void* stream);
+int64_t tlbo_predict_ei_workspace_bytes(int64_t N);
+
+/* Integer mis-ranked-pair counts -- replaces the pure-Python loops of RGPE.train /
+ * TransBO_RGPE.train (tlbo/facade/rgpe.py:74-104, topo.py:72-104) and TST.train
+ * (tlbo/facade/tst.py:37-43).
+ *   d_y [n]; d_ys [S, Mr, n] sampled (or predicted) values;
+ *   d_row_lo, d_row_hi [Mr] int32 row range of i; j runs over 0..n-1, or over i+1..n-1
+ *   when upper_only != 0 (TST).  d_counts [S, Mr] int64 =
+ *   #{(i, j): (y_i < y_j) xor (ys_i < ys_j)}.  Bit-exact.                              */
+int tlbo_rank_loss_counts(const double* d_y, const double* d_ys, int n, int S, int Mr, const int32_t* d_row_lo,
+                          const int32_t* d_row_hi, int upper_only, int64_t* d_counts, void* stream);
+
+/* Pairwise logistic ranking loss and gradient -- replaces Loss_func / Loss_der with
+ * func_id = 3 (tlbo/utils/scipy_solver.py:6-78) inside the SLSQP loop of scipy_solve.
+ *   d_A [n, m] predictions, d_y [n], d_w [m];  d_out [2 + m] = (loss, #pairs, grad[m]). */
+int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const double* d_w, int n, int m,
+                                     double* d_out, void* stream);
+
+/* Device-rate probes used by bench.py for the roofline denominators (FP64 FMA pipe and
+ * FP64 mma.sync rate are not in MEASURED_PEAKS.json).  Returns achieved TFLOP/s in
+ * h_out[0] (DFMA) and h_out[1] (DMMA m8n8k4); synchronous.                             */
+int tlbo_fp64_peak_probe(double* h_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
