@@ -1,0 +1,272 @@
+"""Thin, typed wrappers over the C ABI (one function per entry point of
+``include/tlbo_b200.h``).  torch is used for device memory and streams only."""
+import ctypes
+
+import numpy as np
+import torch
+
+from tlbo_b200 import _cabi
+from tlbo_b200._cabi import HYP_STRIDE, TlboPack, check, ldl, lib, ptr
+
+F64 = torch.float64
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError('tlbo_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback.')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _types_arr(types):
+    t = np.ascontiguousarray(np.asarray(types, dtype=np.int32))
+    return t
+
+
+def round_up(n, m):
+    return ((int(n) + m - 1) // m) * m
+
+
+class SurrogatePack(object):
+    """Device-resident batch of fitted GP surrogates (``struct tlbo_pack``)."""
+
+    def __init__(self, M, ncap, d):
+        dev = _dev()
+        ncap = round_up(max(ncap, 8), 8)
+        self.M, self.ncap, self.d = int(M), int(ncap), int(d)
+        self.n = torch.zeros(M, dtype=torch.int32, device=dev)
+        self.Xs = torch.zeros(M, ncap, d, dtype=F64, device=dev)
+        self.hyp = torch.zeros(M, HYP_STRIDE, dtype=F64, device=dev)
+        self.alpha = torch.zeros(M, ncap, dtype=F64, device=dev)
+        self.Linv = torch.zeros(M, ncap, ldl(ncap), dtype=F64, device=dev)
+        self.theta = torch.zeros(M, d + 2, dtype=F64, device=dev)
+        self.c = TlboPack(self.M, self.ncap, self.d, 0, self.n.data_ptr(), self.Xs.data_ptr(),
+                          self.hyp.data_ptr(), self.alpha.data_ptr(), self.Linv.data_ptr(),
+                          self.theta.data_ptr())
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+    def copy_slot_from(self, dst_slot, other, src_slot):
+        """Copy one fitted surrogate from another pack (other.ncap <= self.ncap)."""
+        assert other.d == self.d and other.ncap <= self.ncap
+        nc = other.ncap
+        self.n[dst_slot] = other.n[src_slot]
+        self.Xs[dst_slot].zero_()
+        self.Xs[dst_slot, :nc] = other.Xs[src_slot]
+        self.hyp[dst_slot] = other.hyp[src_slot]
+        self.alpha[dst_slot].zero_()
+        self.alpha[dst_slot, :nc] = other.alpha[src_slot]
+        self.Linv[dst_slot].zero_()
+        self.Linv[dst_slot, :nc, :nc] = other.Linv[src_slot, :, :nc]
+        self.theta[dst_slot] = other.theta[src_slot]
+
+
+def _pad_batch(X_list, y_list, ncap, d):
+    """Host-side batch assembly -> pinned staging -> device."""
+    B = len(X_list)
+    Xh = np.zeros((B, ncap, d), dtype=np.float64)
+    yh = np.zeros((B, ncap), dtype=np.float64)
+    nh = np.zeros(B, dtype=np.int32)
+    for b, (X, y) in enumerate(zip(X_list, y_list)):
+        n = X.shape[0]
+        Xh[b, :n] = X
+        yh[b, :n] = y
+        nh[b] = n
+    dev = _dev()
+    return (torch.from_numpy(Xh).to(dev), torch.from_numpy(yh).to(dev), torch.from_numpy(nh).to(dev))
+
+
+def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0, do_optimize=True,
+                   return_restarts=False):
+    """``tlbo_gp_fit_batched``.  X_list/y_list: per-surrogate host arrays (y already
+    normalised); p0 [R, H] start points; returns status int32[B] (host) and optionally
+    the per-restart results."""
+    B = len(X_list)
+    d = int(X_list[0].shape[1])
+    H = d + 2
+    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    if ncap > pack.ncap:
+        raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
+    dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
+    dev = dX.device
+    p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, H))
+    R = p0.shape[0]
+    dp0 = torch.from_numpy(p0).to(dev)
+    dlo = torch.from_numpy(np.ascontiguousarray(lo, dtype=np.float64)).to(dev)
+    dhi = torch.from_numpy(np.ascontiguousarray(hi, dtype=np.float64)).to(dev)
+    hym = np.ascontiguousarray(ymean, dtype=np.float64)
+    hys = np.ascontiguousarray(ystd, dtype=np.float64)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, R, ncap, d))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    rt = torch.zeros(B, R, H, dtype=F64, device=dev)
+    rf = torch.zeros(B, R, dtype=F64, device=dev)
+    ri = torch.zeros(B, R, 4, dtype=torch.int32, device=dev)
+    t = _types_arr(types)
+    check(lib.tlbo_gp_fit_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dp0), R, ptr(dlo), ptr(dhi),
+                                  ptr(hym), ptr(hys), 1 if do_optimize else 0, pack.ref(), slot0, ptr(rt), ptr(rf),
+                                  ptr(ri), ptr(status), ptr(work), _stream()))
+    st = status.cpu().numpy()          # synchronises; keeps host staging alive until done
+    if return_restarts:
+        return st, rt.cpu().numpy(), rf.cpu().numpy(), ri.cpu().numpy()
+    return st
+
+
+def gp_factorize_batched(X_list, y_list, types, thetas, ymean, ystd, pack, slot0=0, want_dense=False):
+    """``tlbo_gp_factorize_batched``: factorise at given theta and fill pack slots."""
+    B = len(X_list)
+    d = int(X_list[0].shape[1])
+    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    if ncap > pack.ncap:
+        raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
+    dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
+    dev = dX.device
+    dth = torch.from_numpy(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, d + 2))).to(dev)
+    hym = np.ascontiguousarray(ymean, dtype=np.float64)
+    hys = np.ascontiguousarray(ystd, dtype=np.float64)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, 1, ncap, d))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    dL = torch.zeros(B, ncap, ncap, dtype=F64, device=dev) if want_dense else None
+    dK = torch.zeros(B, ncap, ncap, dtype=F64, device=dev) if want_dense else None
+    t = _types_arr(types)
+    check(lib.tlbo_gp_factorize_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dth), ptr(hym), ptr(hys),
+                                        pack.ref(), slot0, ptr(dL), ptr(dK), ptr(status), ptr(work), _stream()))
+    st = status.cpu().numpy()
+    if want_dense:
+        return st, dL.cpu().numpy(), dK.cpu().numpy()
+    return st
+
+
+def gp_nll_grad_batched(X_list, y_list, types, thetas):
+    """``tlbo_gp_nll_grad_batched``: one ``GaussianProcess._nll`` evaluation per surrogate."""
+    B = len(X_list)
+    d = int(X_list[0].shape[1])
+    H = d + 2
+    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
+    dev = dX.device
+    dth = torch.from_numpy(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, H))).to(dev)
+    nll = torch.zeros(B, dtype=F64, device=dev)
+    grad = torch.zeros(B, H, dtype=F64, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, 1, ncap, d))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    t = _types_arr(types)
+    check(lib.tlbo_gp_nll_grad_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dth), ptr(nll), ptr(grad),
+                                       ptr(status), ptr(work), _stream()))
+    return nll.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy()
+
+
+def gp_predict(pack, types, Xq):
+    """``tlbo_gp_predict``: per-surrogate mean / variance at a small query set.
+    Xq: device tensor or host array [Nq, d].  Returns device tensors mu, var [M, Nq]."""
+    dev = _dev()
+    if not torch.is_tensor(Xq):
+        Xq = torch.from_numpy(np.ascontiguousarray(Xq, dtype=np.float64)).to(dev)
+    Nq = int(Xq.shape[0])
+    mu = torch.empty(pack.M, Nq, dtype=F64, device=dev)
+    var = torch.empty(pack.M, Nq, dtype=F64, device=dev)
+    if Nq == 0:
+        return mu, var
+    t = _types_arr(types)
+    check(lib.tlbo_gp_predict(pack.ref(), ptr(t), ptr(Xq), Nq, ptr(mu), ptr(var), _stream()))
+    return mu, var
+
+
+class FusedWorkspace(object):
+    """Reusable scratch + result buffers of ``tlbo_predict_ei_fused``."""
+
+    def __init__(self):
+        dev = _dev()
+        self.work = torch.empty(int(lib.tlbo_predict_ei_workspace_bytes(0)), dtype=torch.uint8, device=dev)
+        self.best = torch.zeros(4, dtype=F64, device=dev)
+
+
+def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, keys=None, excluded=None,
+                     idx_offset=0, mode=0, want_rows=False, ws=None, sync=True):
+    """``tlbo_predict_ei_fused``.  All array arguments are DEVICE tensors (cand [N, d],
+    w [M], skip int32[M] or None, keys [N] or None, excluded sorted int64 or None).
+    Returns (ei, key, idx, n_negative) of the best non-excluded row (host floats when
+    ``sync``), plus device mu/var/ei [N] when ``want_rows``."""
+    dev = cand.device
+    N = int(cand.shape[0])
+    ws = ws or FusedWorkspace()
+    mu = var = ei = None
+    if want_rows:
+        mu = torch.empty(N, dtype=F64, device=dev)
+        var = torch.empty(N, dtype=F64, device=dev)
+        ei = torch.empty(N, dtype=F64, device=dev)
+    n_excl = 0 if excluded is None else int(excluded.numel())
+    t = _types_arr(types)
+    check(lib.tlbo_predict_ei_fused(pack.ref(), ptr(t), ptr(w), ptr(skip), int(mode), ptr(cand), N, float(eta),
+                                    float(par), float(var_floor), ptr(keys), ptr(excluded) if n_excl else None,
+                                    n_excl, int(idx_offset), ptr(ws.best), ptr(mu), ptr(var), ptr(ei),
+                                    ptr(ws.work), _stream()))
+    if not sync:
+        return ws.best, mu, var, ei
+    b = ws.best.cpu().numpy()
+    res = (float(b[0]), float(b[1]), int(b[2]), int(b[3]))
+    if want_rows:
+        return res, mu, var, ei
+    return res
+
+
+def rank_loss_counts(y, ys, row_lo, row_hi, upper_only=False):
+    """``tlbo_rank_loss_counts``.  y [n], ys [S, Mr, n] host arrays or device tensors;
+    returns int64[S, Mr] on the host."""
+    dev = _dev()
+
+    def up(a, dt):
+        if torch.is_tensor(a):
+            return a.to(device=dev, dtype=dt).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    dy = up(y, F64)
+    dys = up(ys, F64)
+    S, Mr, n = dys.shape
+    dlo = up(np.asarray(row_lo, dtype=np.int32), torch.int32)
+    dhi = up(np.asarray(row_hi, dtype=np.int32), torch.int32)
+    counts = torch.zeros(S, Mr, dtype=torch.int64, device=dev)
+    check(lib.tlbo_rank_loss_counts(ptr(dy), ptr(dys), int(n), int(S), int(Mr), ptr(dlo), ptr(dhi),
+                                    1 if upper_only else 0, ptr(counts), _stream()))
+    return counts.cpu().numpy()
+
+
+class PairLogistic(object):
+    """``tlbo_pairwise_logistic_loss_grad`` with A and y resident on the device across
+    the SLSQP callbacks of one ``scipy_solve``."""
+
+    def __init__(self, A, y):
+        dev = _dev()
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        self.n, self.m = A.shape
+        self.dA = torch.from_numpy(A).to(dev)
+        self.dy = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))).to(dev)
+        self.dw = torch.zeros(self.m, dtype=F64, device=dev)
+        self.out = torch.zeros(2 + self.m, dtype=F64, device=dev)
+        self._cache_w = None
+        self._cache = None
+
+    def __call__(self, w):
+        w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
+        if self._cache_w is not None and np.array_equal(w, self._cache_w):
+            return self._cache
+        self.dw.copy_(torch.from_numpy(w))
+        check(lib.tlbo_pairwise_logistic_loss_grad(ptr(self.dA), ptr(self.dy), ptr(self.dw), self.n, self.m,
+                                                   ptr(self.out), _stream()))
+        o = self.out.cpu().numpy()
+        self._cache_w = w.copy()
+        self._cache = (float(o[0]), int(o[1]), o[2:].copy())
+        return self._cache
+
+
+def fp64_peak_probe():
+    """(DFMA TFLOP/s, DMMA TFLOP/s) measured on the current device."""
+    _dev()
+    out = (ctypes.c_double * 2)()
+    check(lib.tlbo_fp64_peak_probe(ctypes.cast(out, ctypes.c_void_p), _stream()))
+    return float(out[0]), float(out[1])

@@ -1,0 +1,86 @@
+"""GPU parity of the batched MAP fit (on-device L-BFGS-B, 11 restarts) against the oracle's
+scipy.optimize.fmin_l_bfgs_b runs of GaussianProcess._optimize (reference gp.py:199-248).
+
+L-BFGS-B trajectories are chaotic in the last bits, so parity is layered:
+per-restart optimum values agree for the large majority of restarts, the selected optimum's
+NLL is no worse than the oracle's beyond tolerance, and downstream predictions agree."""
+import numpy as np
+import pytest
+
+from oracle import gp as ogp
+
+pytestmark = pytest.mark.gpu
+
+RF_TYPES = np.array([2, 2, 0, 0, 0, 0, 0, 0, 0])
+
+
+def _data(rng, n, types):
+    d = len(types)
+    X = rng.rand(n, d)
+    for j in range(d):
+        if types[j] > 0:
+            X[:, j] = rng.randint(0, types[j], size=n)
+    if d == 9:
+        X[:, [2, 4, 5, 8]] = 0.0
+    y = np.sin(3 * X[:, 3 % d]) + 0.5 * X[:, 6 % d] ** 2 + 0.3 * X[:, 0] + 0.05 * rng.randn(n)
+    return X, y
+
+
+@pytest.mark.parametrize('n,types,seed', [(20, RF_TYPES, 4465), (50, RF_TYPES, 3822), (30, np.zeros(5, int), 1)])
+def test_fit_restarts_track_scipy(n, types, seed):
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(n)
+    spec = ogp.KernelSpec(types)
+    B = 3
+    Xs, ys, yms, yss, ogs = [], [], [], [], []
+    for b in range(B):
+        X, y = _data(rng, n, types)
+        g = ogp.OracleGP(types, seed)
+        g.train(X, y)
+        Xs.append(X); ys.append(g.y); yms.append(g.mean_y); yss.append(g.std_y); ogs.append(g)
+    p0 = np.vstack([spec.default_theta()[None, :], ogp.restart_points(spec, seed)])
+    lb = spec.log_bounds()
+    pack = ops.SurrogatePack(B, n, len(types))
+    st, rt, rf, ri = ops.gp_fit_batched(Xs, ys, types, p0, lb[:, 0], lb[:, 1], yms, yss, pack, return_restarts=True)
+    assert not st.any()
+    R = p0.shape[0]
+    Xq, _ = _data(rng, 64, types)
+    mu, var = ops.gp_predict(pack, types, Xq)
+    mu, var = mu.cpu().numpy(), var.cpu().numpy()
+    for b in range(B):
+        fo = np.array([r[1] for r in ogs[b].restart_results])
+        close = np.abs(rf[b] - fo) <= 1e-5 * np.maximum(1.0, np.abs(fo))
+        assert close.sum() >= R - 3, (rf[b], fo)
+        # every reported f is the NLL at the reported theta
+        for r in range(R):
+            f_chk, _ = ogp.nll(rt[b, r], spec, Xs[b], ys[b])
+            assert abs(f_chk - rf[b, r]) <= 1e-8 * max(1.0, abs(f_chk))
+            assert (rt[b, r] >= lb[:, 0] - 1e-12).all() and (rt[b, r] <= lb[:, 1] + 1e-12).all()
+        # selected optimum no worse than scipy's
+        assert rf[b].min() <= fo.min() + 1e-5 * max(1.0, abs(fo.min()))
+        if abs(rf[b].min() - fo.min()) <= 1e-7 * max(1.0, abs(fo.min())) and np.argmin(rf[b]) == np.argmin(fo):
+            th = pack.theta[b].cpu().numpy()
+            if np.abs(th - ogs[b].hypers).max() < 1e-3:
+                mo, vo = ogs[b].predict(Xq)
+                np.testing.assert_allclose(mu[b], mo.ravel(), rtol=1e-2, atol=1e-3)
+
+
+def test_fit_without_optimize_keeps_default_theta():
+    from tlbo_b200 import ops
+    types = RF_TYPES
+    rng = np.random.RandomState(0)
+    spec = ogp.KernelSpec(types)
+    X, y = _data(rng, 25, types)
+    g = ogp.OracleGP(types, 1)
+    g.train(X, y, do_optimize=False)
+    pack = ops.SurrogatePack(1, 25, 9)
+    lb = spec.log_bounds()
+    st = ops.gp_fit_batched([X], [g.y], types, spec.default_theta()[None, :], lb[:, 0], lb[:, 1], [g.mean_y],
+                            [g.std_y], pack, do_optimize=False)
+    assert not st.any()
+    np.testing.assert_allclose(pack.theta[0].cpu().numpy(), spec.default_theta())
+    Xq, _ = _data(rng, 10, types)
+    mu, var = ops.gp_predict(pack, types, Xq)
+    mo, vo = g.predict(Xq)
+    np.testing.assert_allclose(mu[0].cpu().numpy(), mo.ravel(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var[0].cpu().numpy(), vo.ravel(), rtol=1e-6, atol=1e-12)

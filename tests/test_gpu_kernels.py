@@ -1,0 +1,311 @@
+"""GPU parity tests of the CUDA kernels (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): mean / variance / EI within 1e-6 relative in FP64;
+ranking-loss counts and selected candidate indices bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import gp as ogp
+from oracle.acquisition import OracleEI, first_unevaluated, sort_by_acq_value
+from oracle.facade import loss_der3, loss_func3, rank_loss_vectorised
+
+pytestmark = pytest.mark.gpu
+
+RF_TYPES = np.array([2, 2, 0, 0, 0, 0, 0, 0, 0])
+RTOL = 1e-6
+
+
+def _data(rng, n, types, const_cols=(2, 4, 5, 8)):
+    d = len(types)
+    X = rng.rand(n, d)
+    for j in range(d):
+        if types[j] > 0:
+            X[:, j] = rng.randint(0, types[j], size=n)
+    if len(types) == 9:
+        X[:, list(const_cols)] = 0.0
+    y = np.sin(3 * X[:, 3 % d]) + 0.5 * X[:, 6 % d] ** 2 + 0.3 * X[:, 0] + 0.05 * rng.randn(n)
+    return X, y
+
+
+def _norm(y):
+    m, s = np.mean(y), np.std(y)
+    if s == 0:
+        s = 1
+    return (y - m) / s, m, s
+
+
+def _theta(rng, spec):
+    lb = spec.log_bounds()
+    th = np.array([rng.uniform(-1, 1.5)] + list(rng.uniform(-2.0, 0.08, size=spec.H - 2)) + [rng.uniform(-12, -3)])
+    return np.clip(th, lb[:, 0], lb[:, 1])
+
+
+@pytest.mark.parametrize('n,types', [(5, RF_TYPES), (50, RF_TYPES), (75, RF_TYPES), (33, np.zeros(5, int)),
+                                     (100, np.zeros(20, int)), (200, np.zeros(5, int))])
+def test_nll_grad_matches_oracle(n, types):
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(n)
+    spec = ogp.KernelSpec(types)
+    Xs, ys, ths = [], [], []
+    for b in range(4):
+        X, y = _data(rng, n, types)
+        yn, _, _ = _norm(y)
+        Xs.append(X); ys.append(yn); ths.append(_theta(rng, spec))
+    ths[0] = spec.default_theta()
+    f, g, st = ops.gp_nll_grad_batched(Xs, ys, types, ths)
+    for b in range(4):
+        fo, go = ogp.nll(ths[b], spec, Xs[b], ys[b])
+        if fo >= 1e25:
+            assert f[b] == 1e25 and not g[b].any()
+            continue
+        assert st[b] == 0
+        assert abs(f[b] - fo) <= 1e-8 * max(1.0, abs(fo)), (b, f[b], fo)
+        np.testing.assert_allclose(g[b], go, rtol=1e-6, atol=1e-7 * max(1.0, np.abs(go).max()))
+
+
+def test_nll_cholesky_failure_returns_1e25():
+    """gp.py:183-186: LinAlgError -> (1e25, zeros).  Duplicate rows + minimal noise."""
+    from tlbo_b200 import ops
+    types = np.zeros(3, int)
+    rng = np.random.RandomState(0)
+    X = np.repeat(rng.rand(4, 3), 5, axis=0)
+    y = rng.randn(20)
+    spec = ogp.KernelSpec(types)
+    th = np.array([2.0, 0.08, 0.08, 0.08, -25.0])
+    fo, go = ogp.nll(th, spec, X, y)
+    f, g, st = ops.gp_nll_grad_batched([X], [y], types, [th])
+    assert (fo >= 1e25) == (f[0] >= 1e25)
+
+
+@pytest.mark.parametrize('n,types', [(3, RF_TYPES), (50, RF_TYPES), (75, RF_TYPES), (200, np.zeros(5, int))])
+def test_factorize_matches_oracle(n, types):
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(n + 1)
+    spec = ogp.KernelSpec(types)
+    B = 3
+    Xs, ys, ths, yms, yss, ogs = [], [], [], [], [], []
+    for b in range(B):
+        X, y = _data(rng, n, types)
+        g = ogp.OracleGP(types, 1)
+        th = _theta(rng, spec)
+        g.train(X, y, do_optimize=False, theta=th)
+        Xs.append(X); ys.append(g.y); ths.append(th); yms.append(g.mean_y); yss.append(g.std_y); ogs.append(g)
+    pack = ops.SurrogatePack(B, n, len(types))
+    st, L, Kinv = ops.gp_factorize_batched(Xs, ys, types, ths, yms, yss, pack, want_dense=True)
+    assert not st.any()
+    for b in range(B):
+        np.testing.assert_allclose(L[b, :n, :n], ogs[b].L, rtol=1e-9, atol=1e-12)
+        scale = np.abs(ogs[b].K_inv).max()
+        np.testing.assert_allclose(Kinv[b, :n, :n], ogs[b].K_inv, rtol=1e-6, atol=1e-9 * scale)
+        al = pack.alpha[b, :n].cpu().numpy()
+        np.testing.assert_allclose(al, ogs[b].alpha, rtol=1e-6, atol=1e-9 * np.abs(ogs[b].alpha).max())
+    # small-query predict
+    Xq, _ = _data(rng, 37, types)
+    mu, var = ops.gp_predict(pack, types, Xq)
+    mu, var = mu.cpu().numpy(), var.cpu().numpy()
+    for b in range(B):
+        mo, vo = ogs[b].predict(Xq)
+        np.testing.assert_allclose(mu[b], mo.ravel(), rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(var[b], vo.ravel(), rtol=RTOL, atol=1e-12)
+
+
+def _fitted_pack(rng, types, ns, ncap=None):
+    from tlbo_b200 import ops
+    spec = ogp.KernelSpec(types)
+    Xs, ys, ths, yms, yss, ogs = [], [], [], [], [], []
+    for n in ns:
+        X, y = _data(rng, n, types)
+        g = ogp.OracleGP(types, 1)
+        th = _theta(rng, spec)
+        g.train(X, y, do_optimize=False, theta=th)
+        Xs.append(X); ys.append(g.y); ths.append(th); yms.append(g.mean_y); yss.append(g.std_y); ogs.append(g)
+    M = len(ns)
+    pack = ops.SurrogatePack(M, ncap or max(ns), len(types))
+    # surrogates of different sizes: factorise size groups separately into their slots
+    for m in range(M):
+        st = ops.gp_factorize_batched([Xs[m]], [ys[m]], types, [ths[m]], [yms[m]], [yss[m]], pack, slot0=m)
+        assert not st.any()
+    return pack, ogs
+
+
+def _oracle_ensemble(ogs, w, skip, Xc, mode=0):
+    if mode == 0:
+        mu = np.zeros((Xc.shape[0], 1)); var = np.zeros((Xc.shape[0], 1))
+        # accumulation order of the kernel = pack order
+        for m, g in enumerate(ogs):
+            if skip is not None and skip[m]:
+                continue
+            a, b = g.predict(Xc)
+            mu += w[m] * a
+            var += w[m] * w[m] * b
+        return mu, var
+    mu, var = ogs[0].predict(Xc)
+    den = 0.75
+    for m in range(1, len(ogs)):
+        a, _ = ogs[m].predict(Xc)
+        mu += w[m] * a
+        den += w[m]
+    return mu / den, var
+
+
+class _Ens(object):
+    def __init__(self, ogs, w, skip, mode, floor):
+        self.ogs, self.w, self.skip, self.mode, self.floor = ogs, w, skip, mode, floor
+
+    def predict_marginalized_over_instances(self, X):
+        mu, var = _oracle_ensemble(self.ogs, self.w, self.skip, X, self.mode)
+        var[var < self.floor] = self.floor
+        var[np.isnan(var)] = self.floor
+        return mu, var
+
+
+@pytest.mark.parametrize('types,ns,N,mode', [
+    (RF_TYPES, [50] * 5 + [20], 3000, 0),
+    (RF_TYPES, [50] * 29 + [75], 20000, 0),
+    (RF_TYPES, [7, 50, 50, 50], 1000, 1),
+    (np.zeros(5, int), [100] * 3, 4099, 0),
+    (np.zeros(20, int), [200, 50], 2500, 0),
+    (RF_TYPES, [3, 50], 17, 0),
+])
+def test_fused_predict_ei_argmax(types, ns, N, mode):
+    import torch
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(len(ns) * 1000 + N)
+    pack, ogs = _fitted_pack(rng, types, ns)
+    M = len(ns)
+    w = rng.rand(M)
+    w[rng.rand(M) < 0.3] = 0.0
+    w[-1] = max(w[-1], 0.2)
+    w = w / w.sum() if mode == 0 else w
+    skip = (rng.rand(M) < 0.2).astype(np.int32)
+    skip[-1] = 0
+    if mode == 1:
+        skip[:] = 0
+    Xc, _ = _data(rng, N, types)
+    # some candidates coincide with training rows (variance cancellation path)
+    Xc[:min(ns[-1], N)] = ogs[-1].X[:min(ns[-1], N)]
+    eta = float(np.min(ogs[-1].y)) * ogs[-1].std_y + ogs[-1].mean_y
+    ens = _Ens(ogs, w, skip, mode, 1e-10)
+    ei_o = OracleEI(ens)
+    ei_o.update(eta=eta)
+    acq = ei_o(Xc)
+    rs = np.random.RandomState(7)
+    order, keys = sort_by_acq_value(acq, rs)
+    evaluated = list(order[:3]) + [int(order[10 % N])]
+    want = first_unevaluated(order, evaluated)
+
+    dev = torch.device('cuda')
+    res, mu, var, ei = ops.predict_ei_fused(
+        pack, types, torch.from_numpy(w).to(dev), torch.from_numpy(skip).to(dev), torch.from_numpy(Xc).to(dev),
+        eta, keys=torch.from_numpy(keys).to(dev),
+        excluded=torch.from_numpy(np.sort(np.array(evaluated, dtype=np.int64))).to(dev), mode=mode, want_rows=True)
+    mo, vo = ens.predict_marginalized_over_instances(Xc)
+    np.testing.assert_allclose(mu.cpu().numpy(), mo.ravel(), rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(var.cpu().numpy(), vo.ravel(), rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(ei.cpu().numpy(), acq.ravel(), rtol=RTOL, atol=1e-12 + 1e-6 * acq.max())
+    assert res[3] == 0
+    # selected index: bit-exact whenever the oracle's own winner is separated from the
+    # runner-up by more than the FP64 parity tolerance; otherwise the GPU pick must be
+    # within tolerance of the best EI.
+    eo = acq.ravel().copy()
+    eo[evaluated] = -np.inf
+    top2 = np.sort(eo)[-2:]
+    if top2[1] - top2[0] > 1e-9 * max(top2[1], 1e-300):
+        assert res[2] == want
+    else:
+        assert eo[res[2]] >= top2[1] * (1 - 1e-6)
+    assert abs(res[0] - eo[res[2]]) <= 1e-6 * max(eo[res[2]], 1e-12) + 1e-12
+    assert res[1] == keys[res[2]]
+
+
+def test_fused_argmax_bit_exact_given_identical_ei():
+    """Index selection given the GPU's own EI column: lexsort((key, ei))[::-1] + first
+    unevaluated, bit-exact (ties on EI broken by the larger key)."""
+    import torch
+    from tlbo_b200 import ops
+    types = RF_TYPES
+    rng = np.random.RandomState(3)
+    pack, ogs = _fitted_pack(rng, types, [50, 50, 30])
+    N = 50000
+    Xc, _ = _data(rng, N, types)
+    # duplicate rows -> exact EI ties
+    Xc[N // 2:] = Xc[:N - N // 2]
+    w = np.array([0.3, 0.2, 0.5])
+    dev = torch.device('cuda')
+    keys = np.random.RandomState(11).rand(N)
+    eta = float(np.min(ogs[-1].y)) * ogs[-1].std_y + ogs[-1].mean_y
+    for n_ex in (0, 1, 40):
+        res0, mu, var, ei = ops.predict_ei_fused(pack, types, torch.from_numpy(w).to(dev), None,
+                                                 torch.from_numpy(Xc).to(dev), eta,
+                                                 keys=torch.from_numpy(keys).to(dev), want_rows=True)
+        e = ei.cpu().numpy()
+        order = np.lexsort((keys, e))[::-1]
+        ex = sorted(int(i) for i in order[:n_ex])
+        res = ops.predict_ei_fused(pack, types, torch.from_numpy(w).to(dev), None, torch.from_numpy(Xc).to(dev), eta,
+                                   keys=torch.from_numpy(keys).to(dev),
+                                   excluded=torch.tensor(ex, dtype=torch.int64, device=dev) if ex else None)
+        assert res[2] == first_unevaluated(order, ex)
+        assert res[0] == e[res[2]]
+
+
+def test_fused_sharded_offsets_agree_with_single_call():
+    import torch
+    from tlbo_b200 import ops
+    types = np.zeros(5, int)
+    rng = np.random.RandomState(5)
+    pack, ogs = _fitted_pack(rng, types, [40, 60])
+    N = 10007
+    Xc, _ = _data(rng, N, types)
+    dev = torch.device('cuda')
+    w = torch.tensor([0.4, 0.6], dtype=torch.float64, device=dev)
+    keys = torch.from_numpy(np.random.RandomState(1).rand(N)).to(dev)
+    X = torch.from_numpy(Xc).to(dev)
+    full = ops.predict_ei_fused(pack, types, w, None, X, 0.1, keys=keys)
+    parts = []
+    bounds = [0, 2500, 5000, 7500, N]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        parts.append(ops.predict_ei_fused(pack, types, w, None, X[a:b].contiguous(), 0.1,
+                                          keys=keys[a:b].contiguous(), idx_offset=a))
+    best = max(parts, key=lambda r: (r[0], r[1], r[2]))
+    assert best[:3] == full[:3]
+
+
+@pytest.mark.parametrize('n,S,Mr', [(5, 30, 6), (75, 30, 35), (200, 30, 8), (1, 2, 2)])
+def test_rank_loss_counts_bit_exact(n, S, Mr):
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(n)
+    y = rng.randn(n)
+    y[rng.rand(n) < 0.2] = y[0]          # ties in y
+    ys = rng.randn(S, Mr, n)
+    ys[:, :, ::3] = np.round(ys[:, :, ::3], 1)   # ties in the samples
+    lo = rng.randint(0, n, size=Mr)
+    hi = np.minimum(lo + rng.randint(0, n + 1, size=Mr), n)
+    lo[0], hi[0] = 0, n
+    got = ops.rank_loss_counts(y, ys, lo, hi)
+    for s in range(S):
+        for m in range(Mr):
+            assert got[s, m] == rank_loss_vectorised(y, ys[s, m], lo[m], hi[m])
+    got_u = ops.rank_loss_counts(y, ys[:1], np.zeros(Mr, int), np.full(Mr, n), upper_only=True)
+    iu = np.triu_indices(n, 1)
+    for m in range(Mr):
+        a = (y[:, None] < y[None, :])[iu]
+        b = (ys[0, m][:, None] < ys[0, m][None, :])[iu]
+        assert got_u[0, m] == np.count_nonzero(a ^ b)
+
+
+@pytest.mark.parametrize('n,m', [(3, 5), (20, 29), (75, 30), (200, 30)])
+def test_pairwise_logistic_loss_grad(n, m):
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(n * m)
+    A = rng.randn(n, m)
+    y = rng.rand(n)
+    y[1] = y[0]
+    pl = ops.PairLogistic(A, y)
+    for _ in range(3):
+        w = rng.rand(m)
+        w /= w.sum()
+        loss, npairs, grad = pl(w)
+        lo = loss_func3(y, A.dot(w))
+        go = loss_der3(y, A, w)
+        assert abs(loss - lo) <= 1e-10 * max(1, abs(lo))
+        np.testing.assert_allclose(grad, go, rtol=1e-8, atol=1e-12)
