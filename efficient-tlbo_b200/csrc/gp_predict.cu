@@ -146,7 +146,7 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 struct FusedArgs {
   tlbo_pack pack;
   SpaceDesc sp;
-  const double* w; const int32_t* skip; int mode;
+  const double* w; const int32_t* skip; const int32_t* order; int mode;
   const double* cand; long long N;
   double eta, par, var_floor;
   const double* keys; const long long* excluded; int n_excl; long long idx_offset;
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) predict_ei_fused_kernel(Fused
     // per-lane ensemble accumulators: lane owns candidate (lane) of this warp when WC == 32,
     // in general candidate index cl = lane (valid if lane < WC)
     double acc_mu = 0.0, acc_var = 0.0, wsum = 0.0;
-    for (int m = 0; m < a.pack.M; m++) {
+    for (int mi = 0; mi < a.pack.M; mi++) {
+      const int m = a.order ? a.order[mi] : mi;
       const double wm = a.w[m];
       if (a.skip && a.skip[m]) continue;
       const int n = a.pack.d_n[m];
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) predict_ei_fused_kernel(Fused
           acc_mu += wm * mu_m;
           acc_var += wm * wm * var_m;
         } else {
-          if (m == 0) { acc_mu = mu_m; acc_var = var_m; }
+          if (mi == 0) { acc_mu = mu_m; acc_var = var_m; }
           else { acc_mu += wm * mu_m; wsum += wm; }
         }
       }
@@ -423,7 +424,8 @@ extern "C" int64_t tlbo_predict_ei_workspace_bytes(int64_t N) {
 }
 
 extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
-                                     const int32_t* d_skip, int mode, const double* d_cand, int64_t N,
+                                     const int32_t* d_skip, const int32_t* d_order, int mode,
+                                     const double* d_cand, int64_t N,
                                      double eta, double par, double var_floor, const double* d_keys,
                                      const int64_t* d_excluded, int n_excl, int64_t idx_offset, double* d_best,
                                      double* d_mu, double* d_var, double* d_ei, void* d_work, void* stream) {
@@ -435,7 +437,7 @@ extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_typ
   if (rc) return rc;
   FusedPlan pl;
   if (!fused_plan(pack->ncap, pack->d, N, &pl)) { tlbo_set_error("surrogates too large for the fused kernel"); return TLBO_E_TOOLARGE; }
-  a.w = d_w; a.skip = d_skip; a.mode = mode; a.cand = d_cand; a.N = N;
+  a.w = d_w; a.skip = d_skip; a.order = d_order; a.mode = mode; a.cand = d_cand; a.N = N;
   a.eta = eta; a.par = par; a.var_floor = var_floor;
   a.keys = d_keys; a.excluded = (const long long*)d_excluded; a.n_excl = d_excluded ? n_excl : 0;
   a.idx_offset = idx_offset; a.mu = d_mu; a.var = d_var; a.ei = d_ei;

@@ -41,7 +41,7 @@ SYMBOLS = {
                                           c_int, _P, _P, _P, _P, _P]),
     'tlbo_gp_nll_grad_batched': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     'tlbo_gp_predict': (c_int, [POINTER(TlboPack), _P, _P, c_int, _P, _P, _P]),
-    'tlbo_predict_ei_fused': (c_int, [POINTER(TlboPack), _P, _P, _P, c_int, _P, c_int64, c_double, c_double,
+    'tlbo_predict_ei_fused': (c_int, [POINTER(TlboPack), _P, _P, _P, _P, c_int, _P, c_int64, c_double, c_double,
                                       c_double, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
     'tlbo_predict_ei_workspace_bytes': (c_int64, [c_int64]),
     'tlbo_rank_loss_counts': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),

@@ -1,0 +1,198 @@
+"""Ensemble-facade base (reference tlbo/facade/base_facade.py:15-208) on the device path.
+
+All K source surrogates, the target surrogate and the (up to 5) cross-validation surrogates
+of one facade share ONE device-resident ``SurrogatePack``:
+    slots [0, K)      source surrogates (fitted once, in one batched launch)
+    slot  K           target surrogate
+    slots (K, K + 5]  cross-validation surrogates of the current iteration
+so that an iteration costs one batched fit launch, one small-query predict launch and one
+fused predict + EI + arg-max launch."""
+import abc
+
+import numpy as np
+
+from tlbo_b200.config_space import convert_configurations_to_array, get_types
+from tlbo_b200.model.gp import fit_models
+from tlbo_b200.model.model_builder import build_model
+from tlbo_b200.utils.constants import VERY_SMALL_NUMBER
+from tlbo_b200.utils.normalization import zero_mean_unit_var_normalization, zero_one_normalization
+
+N_CV_SLOTS = 5
+
+
+def _history_to_arrays(hist):
+    """One source history: an ``OrderedDict{Configuration -> perf}`` (the reference's
+    pickle format) or an ``(X, y)`` pair of arrays."""
+    if isinstance(hist, (tuple, list)) and len(hist) == 2 and isinstance(hist[0], np.ndarray):
+        return np.asarray(hist[0], dtype=np.float64), np.array(hist[1], dtype=np.float64)
+    _X, _y = list(), list()
+    for _config, _perf in hist.items():
+        _X.append(_config)
+        _y.append(_perf)
+    return convert_configurations_to_array(_X), np.array(_y, dtype=np.float64)
+
+
+class BaseFacade(object, metaclass=abc.ABCMeta):
+    def __init__(self, config_space, source_hpo_data, seed, target_hp_configs=None,
+                 history_dataset_features=None, num_src_hpo_trial=50, surrogate_type='gp', max_target_rows=96):
+        self.method_id = None
+        self.config_space = config_space
+        self.random_seed = seed
+        self.K = len(source_hpo_data)
+        self.num_src_hpo_trial = num_src_hpo_trial
+        self.source_hpo_data = source_hpo_data
+        self.target_hp_configs = target_hp_configs
+        self.source_surrogates = None
+        self.target_surrogate = None
+        self.history_dataset_features = history_dataset_features
+        if history_dataset_features is not None:
+            assert len(history_dataset_features) == self.K
+        if surrogate_type not in ('gp', 'gp_b200'):
+            raise ValueError("surrogate_type %r is not part of the B200 hot path (use 'gp')" % surrogate_type)
+        self.surrogate_type = surrogate_type
+        self.types, self.bounds = get_types(config_space)
+        self.instance_features = None
+        self.var_threshold = VERY_SMALL_NUMBER
+        self.w = None
+        self.eta_list = list()
+        self.target_weight = []
+        self._pack = None
+        self._cap_hint = max_target_rows
+        # accumulation order of the fused ensemble predict (pack slot ids) and TST mode flag
+        self._fused_mode = 0
+
+    # ---- device pack ------------------------------------------------------------------
+    def _ensure_pack(self, rows):
+        from tlbo_b200 import ops
+        need = ops.round_up(max(rows, self.num_src_hpo_trial, 8), 8)
+        if self._pack is not None and self._pack.ncap >= need:
+            return self._pack
+        cap = ops.round_up(max(need, self._cap_hint), 8)
+        if self._pack is not None:
+            cap = max(cap, ops.round_up(int(self._pack.ncap * 1.5), 8))
+        new = ops.SurrogatePack(self.K + 1 + N_CV_SLOTS, cap, len(self.types))
+        if self._pack is not None:
+            for s in range(self._pack.M):
+                new.copy_slot_from(s, self._pack, s)
+            for mdl in (self.source_surrogates or []):
+                mdl.bind(new, mdl._slot)
+        self._pack = new
+        return new
+
+    @abc.abstractmethod
+    def train(self, X, y):
+        pass
+
+    @abc.abstractmethod
+    def predict(self, X):
+        pass
+
+    # ---- surrogate construction ---------------------------------------------------------
+    def build_source_surrogates(self, normalize):
+        """base_facade.py:58-91 -- the K source fits run as ONE batched launch."""
+        self.source_surrogates = list()
+        pack = self._ensure_pack(self.num_src_hpo_trial)
+        Xs, ys = [], []
+        for k, hist in enumerate(self.source_hpo_data):
+            model = build_model(self.surrogate_type, self.config_space, np.random.RandomState(self.random_seed))
+            X, y = _history_to_arrays(hist)
+            X = X[:self.num_src_hpo_trial]
+            y = y[:self.num_src_hpo_trial]
+            if normalize == 'standardize':
+                if (y == y[0]).all():
+                    y[0] += 1e-4
+                y, _, _ = zero_mean_unit_var_normalization(y)
+            elif normalize == 'scale':
+                if (y == y[0]).all():
+                    y[0] += 1e-4
+                y, _, _ = zero_one_normalization(y)
+                y = 2 * y - 1.
+            else:
+                raise ValueError('Invalid parameter in norm.')
+            self.eta_list.append(np.min(y))
+            model.bind(pack, k)
+            Xs.append(X)
+            ys.append(y)
+            self.source_surrogates.append(model)
+        if self.K:
+            fit_models(self.source_surrogates, Xs, ys)
+
+    def _prepare_single_surrogate(self, X, y, normalize, slot):
+        """The host half of ``build_single_surrogate`` (base_facade.py:93-108): build the
+        model, apply the all-equal guard (mutating the caller's ``y``) and the facade-level
+        normalisation.  Returns ``(model, X, y_normalised)`` for a later batched fit."""
+        assert normalize in ['standardize', 'scale', 'none']
+        model = build_model(self.surrogate_type, self.config_space, np.random.RandomState(self.random_seed))
+        if normalize == 'standardize':
+            if (y == y[0]).all():
+                y[0] += 1e-4
+            y, _, _ = zero_mean_unit_var_normalization(y)
+        elif normalize == 'scale':
+            if (y == y[0]).all():
+                y[0] += 1e-4
+            y, _, _ = zero_one_normalization(y)
+        model.bind(self._ensure_pack(X.shape[0]), slot)
+        return model, X, y
+
+    def build_single_surrogate(self, X, y, normalize, slot=None):
+        job = self._prepare_single_surrogate(X, y, normalize, self.K if slot is None else slot)
+        fit_models([job[0]], [job[1]], [job[2]])
+        return job[0]
+
+    # ---- prediction -----------------------------------------------------------------------
+    def _ensemble_args(self):
+        """(w[M], skip[M] or None, order[M] or None) over pack slots 0..K for the fused
+        kernel; subclasses override."""
+        return np.asarray(self.w, dtype=np.float64), None, None
+
+    def _fused(self, X_dev, eta=0.0, par=0.0, var_floor=0.0, keys=None, excluded=None, idx_offset=0,
+               want_rows=False, ws=None, sync=True):
+        from tlbo_b200 import ops
+        w, skip, order = self._ensemble_args()
+        view = ops.pack_view(self._pack, 0, self.K + 1)
+        dw = ops.h2d(np.ascontiguousarray(w, dtype=np.float64))
+        dskip = None if skip is None else ops.h2d(np.ascontiguousarray(skip, dtype=np.int32))
+        dorder = None if order is None else ops.h2d(np.ascontiguousarray(order, dtype=np.int32))
+        return ops.predict_ei_fused(view, self.types, dw, dskip, X_dev, eta, par=par, var_floor=var_floor,
+                                    keys=keys, excluded=excluded, idx_offset=idx_offset, mode=self._fused_mode,
+                                    order=dorder, want_rows=want_rows, ws=ws, sync=sync)
+
+    def _to_device(self, X):
+        import torch
+        from tlbo_b200 import ops
+        if torch.is_tensor(X):
+            return X
+        X = np.array(X, dtype=np.float64)
+        X[~np.isfinite(X)] = -1
+        return ops.h2d(X)
+
+    def _predict_rows(self, X, var_floor):
+        if len(X.shape) != 2:
+            raise ValueError('Expected 2d array, got %dd array!' % len(X.shape))
+        if X.shape[1] != len(self.types):
+            raise ValueError('Rows in X should have %d entries but have %d!' % (len(self.types), X.shape[1]))
+        if self.target_surrogate is None:
+            raise ValueError('Target surrogate is none.')
+        from tlbo_b200 import ops
+        _, mu, var, _ = self._fused(self._to_device(X), var_floor=var_floor, want_rows=True)
+        return ops.d2h(mu).reshape((-1, 1)), ops.d2h(var).reshape((-1, 1))
+
+    def predict_marginalized_over_instances(self, X):
+        """base_facade.py:110-143: ensemble predict with the 1e-10 variance floor."""
+        return self._predict_rows(X, self.var_threshold)
+
+    def combine_predictions(self, X, combination_method='idp_lc'):
+        """base_facade.py:145-183.  Only 'idp_lc' (independent linear combination) is on
+        the benchmark path; it is what the fused kernel's mode 0 evaluates."""
+        if combination_method != 'idp_lc':
+            raise ValueError('Invalid combination method %s.' % combination_method)
+        return self._predict_rows(X, 0.0)
+
+    def _source_predictions(self, X, n_extra=0):
+        """mu, var [K + 1 + n_extra, n] of every pack slot at the target points -- the K
+        source predicts of rgpe.py:27-30 / topo_variant1.py:27-35 plus the CV surrogates,
+        in ONE launch."""
+        from tlbo_b200 import ops
+        view = ops.pack_view(self._pack, 0, self.K + 1 + n_extra)
+        mu, var = ops.gp_predict(view, self.types, self._to_device(X))
+        return ops.d2h(mu), ops.d2h(var)

@@ -1,0 +1,160 @@
+"""RGPE and TransBO_RGPE ensemble facades on the device path
+(reference tlbo/facade/rgpe.py:5-156, tlbo/facade/topo.py:5-162).
+
+Per ``train`` call: the target + 5 cross-validation GPs are fitted in ONE batched launch,
+all K + 6 surrogates are evaluated at the target points in ONE launch, the 30 x (K + 5)
+bootstrap draws come from the host's GLOBAL legacy ``np.random`` stream in the reference's
+draw order (one vectorised call, stream-identical to the reference's loop), and the
+mis-ranked-pair counts come from the integer pair-count kernel (bit-exact)."""
+import numpy as np
+
+from tlbo_b200.facade.base_facade import BaseFacade, N_CV_SLOTS
+from tlbo_b200.model.gp import fit_models
+
+
+class _BootstrapRankingFacade(BaseFacade):
+    k_fold_num = 5
+
+    def _init_common(self, only_source):
+        self.only_source = only_source
+        self.build_source_surrogates(normalize='standardize')
+        self.scale = True
+        self.num_sample = 30
+        self.ignored_flag = [False] * self.K
+        self.hist_ws = list()
+        self.iteration_id = 0
+        self.last_losses = None
+
+    def _ranking_losses(self, X, y):
+        """Everything of rgpe.py:24-109 up to (and including) the loss table
+        ``int64[num_sample, K + 1]`` and the arg-min histogram."""
+        from tlbo_b200 import ops
+        K = self.K
+        instance_num = len(y)
+        skip_target_surrogate = instance_num < self.k_fold_num
+
+        # host half of build_single_surrogate for the target and the CV folds, in the
+        # reference's order (the all-equal guards mutate ``y`` in place as they go)
+        jobs = [self._prepare_single_surrogate(X, y, 'standardize', K)]
+        n_folds = 0
+        if not skip_target_surrogate:
+            fold_num = instance_num // self.k_fold_num
+            for i in range(self.k_fold_num):
+                row_indexs = list(range(instance_num))
+                bound = (instance_num - i * fold_num) if i == (self.k_fold_num - 1) else fold_num
+                del row_indexs[i * fold_num:i * fold_num + bound]
+                if (y[row_indexs] == y[row_indexs[0]]).all():
+                    y[row_indexs[0]] += 1e-4
+                jobs.append(self._prepare_single_surrogate(X[row_indexs, :], y[row_indexs], 'standardize',
+                                                           K + 1 + i))
+            n_folds = self.k_fold_num
+        # a pack regrow inside _prepare_single_surrogate rebinds nothing for fresh models: rebind all
+        for j, job in enumerate(jobs):
+            job[0].bind(self._pack, K + j)
+        fit_models([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+        self.target_surrogate = jobs[0][0]
+
+        # K source predicts + fold predicts at the target points: one launch
+        mu, var = self._source_predictions(X, n_extra=n_folds)
+        rows = list(range(K)) + list(range(K + 1, K + 1 + n_folds))
+        loc, scale = mu[rows], var[rows]                     # [K + n_folds, n]; scale = VARIANCE (rgpe.py:77)
+
+        # draws: sample-major, then source 0..K-1, then fold 0..4, n normals each -- the
+        # order in which the reference's loops consume the global stream
+        S = self.num_sample
+        ys = np.random.normal(np.broadcast_to(loc, (S,) + loc.shape), np.broadcast_to(scale, (S,) + scale.shape))
+        row_lo = [0] * K
+        row_hi = [instance_num] * K
+        if n_folds:
+            fold_num = instance_num // self.k_fold_num
+            for fold in range(self.k_fold_num):
+                row_lo.append(fold_num * fold)
+                row_hi.append(instance_num if fold == self.k_fold_num - 1 else (fold + 1) * fold_num)
+        counts = ops.rank_loss_counts(np.asarray(y, dtype=np.float64), ys, row_lo, row_hi)
+        losses = np.empty((S, K + 1), dtype=np.int64)
+        losses[:, :K] = counts[:, :K]
+        losses[:, K] = counts[:, K:].sum(axis=1) if n_folds else instance_num * instance_num
+        argmin_list = np.bincount(np.argmin(losses, axis=1), minlength=K + 1)
+        self.last_losses = losses
+        return losses, argmin_list, instance_num
+
+    def _dilution_flags(self, losses):
+        """rgpe.py:116-120."""
+        threshold = sorted(losses[:, -1])[int(self.num_sample * 0.95)]
+        for id in range(self.K):
+            median = sorted(losses[:, id])[int(self.num_sample * 0.5)]
+            self.ignored_flag[id] = bool(median > threshold)
+
+    def _log_weights(self):
+        w = np.array(self.w, dtype=np.float64).copy()
+        for id in range(self.K):
+            if self.ignored_flag[id]:
+                w[id] = 0.
+        self.target_weight.append(w[-1])
+        self.hist_ws.append(w)
+        self.iteration_id += 1
+
+    def _ensemble_args(self):
+        # rgpe.py:141-153: target first, then the non-ignored sources in order
+        skip = np.array(list(self.ignored_flag) + [False], dtype=np.int32)
+        order = np.array([self.K] + list(range(self.K)), dtype=np.int32)
+        return np.asarray(self.w, dtype=np.float64), skip, order
+
+    def predict(self, X):
+        return self._predict_rows(X, 0.0)
+
+    def get_weights(self):
+        return self.w
+
+
+class RGPE(_BootstrapRankingFacade):
+    def __init__(self, config_space, source_hpo_data, target_hp_configs, seed, surrogate_type='gp',
+                 num_src_hpo_trial=50, only_source=False, **kw):
+        super().__init__(config_space, source_hpo_data, seed, target_hp_configs, surrogate_type=surrogate_type,
+                         num_src_hpo_trial=num_src_hpo_trial, **kw)
+        self.method_id = 'rgpe'
+        self._init_common(only_source)
+        self.w = [1. / self.K] * self.K + [0.]
+
+    def train(self, X, y):
+        losses, argmin_list, _ = self._ranking_losses(X, y)
+        for id in range(self.K + 1):
+            self.w[id] = argmin_list[id] / self.num_sample
+        self._dilution_flags(losses)
+        if self.only_source:
+            self.w[-1] = 0.
+            if np.sum(self.w) == 0:
+                self.w = [1. / self.K] * self.K + [0.]
+            else:
+                self.w[:-1] = np.array(self.w[:-1]) / np.sum(self.w[:-1])
+        self._log_weights()
+
+
+class TransBO_RGPE(_BootstrapRankingFacade):
+    """reference tlbo/facade/topo.py: the RGPE ranking loss with target-weight monotonicity
+    and exponential smoothing (rho = 0.7) of the weights."""
+
+    def __init__(self, config_space, source_hpo_data, target_hp_configs, seed, surrogate_type='gp',
+                 num_src_hpo_trial=50, only_source=False, **kw):
+        super().__init__(config_space, source_hpo_data, seed, target_hp_configs, surrogate_type=surrogate_type,
+                         num_src_hpo_trial=num_src_hpo_trial, **kw)
+        self.method_id = 'trans_rgpe'
+        self._init_common(only_source)
+        self.w = np.array([1. / self.K] * self.K + [0.])
+
+    def train(self, X, y):
+        losses, argmin_list, instance_num = self._ranking_losses(X, y)
+        new_weights = argmin_list / self.num_sample
+        self._dilution_flags(losses)
+        min_num_y = 5
+        w_target = new_weights[-1]
+        w_source = np.array(new_weights[:-1])
+        if instance_num >= min_num_y:
+            if instance_num >= 2 * min_num_y:
+                w_target = np.max([w_target, self.w[-1]])
+            if np.sum(w_source) > 0:
+                w_source = w_source / np.sum(w_source) * (1 - w_target)
+        w_new = np.array(list(w_source) + [w_target])
+        rho = 0.7
+        self.w = rho * w_new + (1 - rho) * self.w
+        self._log_weights()

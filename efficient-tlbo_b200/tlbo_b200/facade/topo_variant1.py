@@ -1,0 +1,101 @@
+"""OBTLV -- what ``--methods topo`` runs (reference tlbo/facade/topo_variant1.py:9-106,
+tools/offline_benchmark.py:310-311): two-phase simplex-constrained minimisation of a
+pairwise logistic ranking loss (sources, then sources + cross-validated target)."""
+import numpy as np
+
+from tlbo_b200.facade.base_facade import BaseFacade
+from tlbo_b200.model.gp import fit_models
+from tlbo_b200.utils.scipy_solver import scipy_solve
+
+_scale_method = 'standardize'
+
+
+def _kfold_val_slices(n, n_splits=5):
+    """Validation ranges of sklearn ``KFold(n_splits)`` without shuffling: the first
+    ``n % n_splits`` folds hold one extra row."""
+    sizes = np.full(n_splits, n // n_splits, dtype=int)
+    sizes[:n % n_splits] += 1
+    out, cur = [], 0
+    for s in sizes:
+        out.append((cur, cur + int(s)))
+        cur += int(s)
+    return out
+
+
+class OBTLV(BaseFacade):
+    def __init__(self, config_space, source_hpo_data, target_hp_configs, seed, surrogate_type='gp',
+                 num_src_hpo_trial=50, fusion_method='idp_lc', only_source=False, **kw):
+        super().__init__(config_space, source_hpo_data, seed, target_hp_configs, surrogate_type=surrogate_type,
+                         num_src_hpo_trial=num_src_hpo_trial, **kw)
+        self.method_id = 'topo_v1'
+        self.fusion_method = fusion_method
+        self.build_source_surrogates(normalize=_scale_method)
+        self.only_source = only_source
+        self.w = np.array([1. / self.K] * self.K + [0.])
+        self.min_num_y = 5
+        self.hist_ws = list()
+        self.iteration_id = 0
+        self.target_y_range = None
+
+    def batch_predict(self, X):
+        """topo_variant1.py:27-35: [n, K] source means at X."""
+        mu, _ = self._source_predictions(X)
+        return np.ascontiguousarray(mu[:self.K].T)
+
+    def train(self, X, y):
+        K = self.K
+        instance_num = X.shape[0]
+        do_cv = (not self.only_source) and instance_num >= self.min_num_y
+        # host halves of every build_single_surrogate of this call, then ONE batched fit
+        jobs = [self._prepare_single_surrogate(X, y, _scale_method, K)]
+        folds = _kfold_val_slices(instance_num, 5) if do_cv else []
+        for i, (lo, hi) in enumerate(folds):
+            train_idx = np.concatenate([np.arange(0, lo), np.arange(hi, instance_num)])
+            jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
+        for j, job in enumerate(jobs):
+            job[0].bind(self._pack, K + j)
+        fit_models([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+        self.target_surrogate = jobs[0][0]
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+
+        mu, _ = self._source_predictions(X, n_extra=len(folds))
+        pred_y = np.ascontiguousarray(mu[:K].T)
+
+        self.learn_source_weights(pred_y, y)
+        w_source = self.w[:K]               # a view: the in-place scaling below is the reference's
+        w_target = 0.
+        if do_cv:
+            _t_pred_y = np.empty(instance_num)
+            for i, (lo, hi) in enumerate(folds):
+                _t_pred_y[lo:hi] = mu[K + 1 + i, lo:hi]
+            _pred_y = np.c_[pred_y, _t_pred_y.reshape((-1, 1))]
+            w_target = self.compute_target_weight(_pred_y, y)
+            if instance_num >= 2 * self.min_num_y:
+                w_target = np.max([w_target, self.w[-1]])
+            w_source *= (1 - w_target)
+        w_new = np.asarray(list(w_source) + [w_target])
+        rho = 0.6
+        self.w = rho * w_new + (1 - rho) * self.w
+        w = self.w.copy()
+        self.target_weight.append(w[-1])
+        self.hist_ws.append(w)
+        self.iteration_id += 1
+
+    def learn_source_weights(self, pred_y, true_y):
+        x, status = scipy_solve(pred_y, true_y, 3)
+        if status:
+            x[x < 1e-3] = 0.
+            self.w[:self.K] = x
+
+    def compute_target_weight(self, pred_y, true_y):
+        x, status = scipy_solve(pred_y, true_y, 3)
+        if status:
+            x[x < 1e-3] = 0.
+            return x[-1]
+        return self.w[-1]
+
+    def predict(self, X):
+        return self.combine_predictions(X, self.fusion_method)
+
+    def get_weights(self):
+        return self.w

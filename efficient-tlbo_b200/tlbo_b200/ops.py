@@ -30,6 +30,76 @@ def round_up(n, m):
     return ((int(n) + m - 1) // m) * m
 
 
+class _Stats(object):
+    """Launch / transfer accounting for bench.py: how many of OUR kernels were launched,
+    how many bytes crossed PCIe, and (when ``timing``) a CUDA-event pair around every
+    C-ABI call on the launching stream."""
+
+    def __init__(self):
+        self.timing = False
+        self.reset()
+
+    def reset(self):
+        self.launches = {}
+        self.h2d = 0
+        self.d2h = 0
+        self.events = []
+
+    def total_launches(self):
+        return sum(self.launches.values())
+
+    def kernel_ms(self):
+        """name -> (calls, total ms) from the recorded event pairs (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.events:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+STATS = _Stats()
+
+
+class _call(object):
+    def __init__(self, name, kernels):
+        self.name, self.kernels = name, kernels
+
+    def __enter__(self):
+        STATS.launches[self.name] = STATS.launches.get(self.name, 0) + self.kernels
+        if STATS.timing:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STATS.timing:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            STATS.events.append((self.name, self.e0, e1))
+        return False
+
+
+def h2d(a, dtype=None):
+    """Host array -> device tensor (counted)."""
+    if torch.is_tensor(a):
+        if a.is_cuda:
+            return a if dtype is None else a.to(dtype)
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    STATS.h2d += t.numel() * t.element_size()
+    return t.to(_dev())
+
+
+def d2h(t):
+    """Device tensor -> numpy (counted; synchronises)."""
+    STATS.d2h += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
 class SurrogatePack(object):
     """Device-resident batch of fitted GP surrogates (``struct tlbo_pack``)."""
 
@@ -65,6 +135,30 @@ class SurrogatePack(object):
         self.theta[dst_slot] = other.theta[src_slot]
 
 
+class PackView(object):
+    """``M`` consecutive slots of a pack, starting at ``slot0`` (no copy)."""
+
+    def __init__(self, pack, slot0, M):
+        assert 0 <= slot0 and slot0 + M <= pack.M
+        self.base, self.slot0 = pack, int(slot0)
+        self.M, self.ncap, self.d = int(M), pack.ncap, pack.d
+        s = self.slot0
+        self.n, self.Xs, self.hyp = pack.n[s:s + M], pack.Xs[s:s + M], pack.hyp[s:s + M]
+        self.alpha, self.Linv, self.theta = pack.alpha[s:s + M], pack.Linv[s:s + M], pack.theta[s:s + M]
+        self.c = TlboPack(self.M, self.ncap, self.d, 0, self.n.data_ptr(), self.Xs.data_ptr(),
+                          self.hyp.data_ptr(), self.alpha.data_ptr(), self.Linv.data_ptr(),
+                          self.theta.data_ptr())
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+
+def pack_view(pack, slot0, M):
+    if slot0 == 0 and M == pack.M:
+        return pack
+    return PackView(pack, slot0, M)
+
+
 def _pad_batch(X_list, y_list, ncap, d):
     """Host-side batch assembly -> pinned staging -> device."""
     B = len(X_list)
@@ -76,8 +170,7 @@ def _pad_batch(X_list, y_list, ncap, d):
         Xh[b, :n] = X
         yh[b, :n] = y
         nh[b] = n
-    dev = _dev()
-    return (torch.from_numpy(Xh).to(dev), torch.from_numpy(yh).to(dev), torch.from_numpy(nh).to(dev))
+    return h2d(Xh), h2d(yh), h2d(nh)
 
 
 def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0, do_optimize=True,
@@ -95,11 +188,12 @@ def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0
     dev = dX.device
     p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, H))
     R = p0.shape[0]
-    dp0 = torch.from_numpy(p0).to(dev)
-    dlo = torch.from_numpy(np.ascontiguousarray(lo, dtype=np.float64)).to(dev)
-    dhi = torch.from_numpy(np.ascontiguousarray(hi, dtype=np.float64)).to(dev)
+    dp0 = h2d(p0)
+    dlo = h2d(np.ascontiguousarray(lo, dtype=np.float64))
+    dhi = h2d(np.ascontiguousarray(hi, dtype=np.float64))
     hym = np.ascontiguousarray(ymean, dtype=np.float64)
     hys = np.ascontiguousarray(ystd, dtype=np.float64)
+    STATS.h2d += hym.nbytes + hys.nbytes
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, R, ncap, d))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
@@ -107,12 +201,13 @@ def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0
     rf = torch.zeros(B, R, dtype=F64, device=dev)
     ri = torch.zeros(B, R, 4, dtype=torch.int32, device=dev)
     t = _types_arr(types)
-    check(lib.tlbo_gp_fit_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dp0), R, ptr(dlo), ptr(dhi),
-                                  ptr(hym), ptr(hys), 1 if do_optimize else 0, pack.ref(), slot0, ptr(rt), ptr(rf),
-                                  ptr(ri), ptr(status), ptr(work), _stream()))
-    st = status.cpu().numpy()          # synchronises; keeps host staging alive until done
+    with _call('gp_fit', 2):            # gp_fit_kernel + gp_factorize_kernel
+        check(lib.tlbo_gp_fit_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dp0), R, ptr(dlo),
+                                      ptr(dhi), ptr(hym), ptr(hys), 1 if do_optimize else 0, pack.ref(), slot0,
+                                      ptr(rt), ptr(rf), ptr(ri), ptr(status), ptr(work), _stream()))
+    st = d2h(status)                   # synchronises; keeps host staging alive until done
     if return_restarts:
-        return st, rt.cpu().numpy(), rf.cpu().numpy(), ri.cpu().numpy()
+        return st, d2h(rt), d2h(rf), d2h(ri)
     return st
 
 
@@ -125,7 +220,7 @@ def gp_factorize_batched(X_list, y_list, types, thetas, ymean, ystd, pack, slot0
         raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
     dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
     dev = dX.device
-    dth = torch.from_numpy(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, d + 2))).to(dev)
+    dth = h2d(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, d + 2)))
     hym = np.ascontiguousarray(ymean, dtype=np.float64)
     hys = np.ascontiguousarray(ystd, dtype=np.float64)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -134,11 +229,13 @@ def gp_factorize_batched(X_list, y_list, types, thetas, ymean, ystd, pack, slot0
     dL = torch.zeros(B, ncap, ncap, dtype=F64, device=dev) if want_dense else None
     dK = torch.zeros(B, ncap, ncap, dtype=F64, device=dev) if want_dense else None
     t = _types_arr(types)
-    check(lib.tlbo_gp_factorize_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dth), ptr(hym), ptr(hys),
-                                        pack.ref(), slot0, ptr(dL), ptr(dK), ptr(status), ptr(work), _stream()))
-    st = status.cpu().numpy()
+    with _call('gp_factorize', 1):
+        check(lib.tlbo_gp_factorize_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dth), ptr(hym),
+                                            ptr(hys), pack.ref(), slot0, ptr(dL), ptr(dK), ptr(status), ptr(work),
+                                            _stream()))
+    st = d2h(status)
     if want_dense:
-        return st, dL.cpu().numpy(), dK.cpu().numpy()
+        return st, d2h(dL), d2h(dK)
     return st
 
 
@@ -150,16 +247,17 @@ def gp_nll_grad_batched(X_list, y_list, types, thetas):
     ncap = round_up(max(x.shape[0] for x in X_list), 8)
     dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
     dev = dX.device
-    dth = torch.from_numpy(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, H))).to(dev)
+    dth = h2d(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, H)))
     nll = torch.zeros(B, dtype=F64, device=dev)
     grad = torch.zeros(B, H, dtype=F64, device=dev)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, 1, ncap, d))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     t = _types_arr(types)
-    check(lib.tlbo_gp_nll_grad_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dth), ptr(nll), ptr(grad),
-                                       ptr(status), ptr(work), _stream()))
-    return nll.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy()
+    with _call('gp_nll_grad', 1):
+        check(lib.tlbo_gp_nll_grad_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dth), ptr(nll),
+                                           ptr(grad), ptr(status), ptr(work), _stream()))
+    return d2h(nll), d2h(grad), d2h(status)
 
 
 def gp_predict(pack, types, Xq):
@@ -167,14 +265,15 @@ def gp_predict(pack, types, Xq):
     Xq: device tensor or host array [Nq, d].  Returns device tensors mu, var [M, Nq]."""
     dev = _dev()
     if not torch.is_tensor(Xq):
-        Xq = torch.from_numpy(np.ascontiguousarray(Xq, dtype=np.float64)).to(dev)
+        Xq = h2d(np.ascontiguousarray(Xq, dtype=np.float64))
     Nq = int(Xq.shape[0])
     mu = torch.empty(pack.M, Nq, dtype=F64, device=dev)
     var = torch.empty(pack.M, Nq, dtype=F64, device=dev)
     if Nq == 0:
         return mu, var
     t = _types_arr(types)
-    check(lib.tlbo_gp_predict(pack.ref(), ptr(t), ptr(Xq), Nq, ptr(mu), ptr(var), _stream()))
+    with _call('gp_predict_small', 1):
+        check(lib.tlbo_gp_predict(pack.ref(), ptr(t), ptr(Xq), Nq, ptr(mu), ptr(var), _stream()))
     return mu, var
 
 
@@ -188,7 +287,7 @@ class FusedWorkspace(object):
 
 
 def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, keys=None, excluded=None,
-                     idx_offset=0, mode=0, want_rows=False, ws=None, sync=True):
+                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True):
     """``tlbo_predict_ei_fused``.  All array arguments are DEVICE tensors (cand [N, d],
     w [M], skip int32[M] or None, keys [N] or None, excluded sorted int64 or None).
     Returns (ei, key, idx, n_negative) of the best non-excluded row (host floats when
@@ -203,13 +302,14 @@ def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, 
         ei = torch.empty(N, dtype=F64, device=dev)
     n_excl = 0 if excluded is None else int(excluded.numel())
     t = _types_arr(types)
-    check(lib.tlbo_predict_ei_fused(pack.ref(), ptr(t), ptr(w), ptr(skip), int(mode), ptr(cand), N, float(eta),
-                                    float(par), float(var_floor), ptr(keys), ptr(excluded) if n_excl else None,
-                                    n_excl, int(idx_offset), ptr(ws.best), ptr(mu), ptr(var), ptr(ei),
-                                    ptr(ws.work), _stream()))
+    with _call('predict_ei_fused', 2):    # predict_ei_fused_kernel + argmax_final_kernel
+        check(lib.tlbo_predict_ei_fused(pack.ref(), ptr(t), ptr(w), ptr(skip), ptr(order), int(mode), ptr(cand), N,
+                                        float(eta), float(par), float(var_floor), ptr(keys),
+                                        ptr(excluded) if n_excl else None, n_excl, int(idx_offset), ptr(ws.best),
+                                        ptr(mu), ptr(var), ptr(ei), ptr(ws.work), _stream()))
     if not sync:
         return ws.best, mu, var, ei
-    b = ws.best.cpu().numpy()
+    b = d2h(ws.best)
     res = (float(b[0]), float(b[1]), int(b[2]), int(b[3]))
     if want_rows:
         return res, mu, var, ei
@@ -222,18 +322,19 @@ def rank_loss_counts(y, ys, row_lo, row_hi, upper_only=False):
     dev = _dev()
 
     def up(a, dt):
-        if torch.is_tensor(a):
-            return a.to(device=dev, dtype=dt).contiguous()
-        return torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+        if torch.is_tensor(a) and a.is_cuda:
+            return a.to(dtype=dt).contiguous()
+        return h2d(a, dt)
     dy = up(y, F64)
     dys = up(ys, F64)
     S, Mr, n = dys.shape
     dlo = up(np.asarray(row_lo, dtype=np.int32), torch.int32)
     dhi = up(np.asarray(row_hi, dtype=np.int32), torch.int32)
     counts = torch.zeros(S, Mr, dtype=torch.int64, device=dev)
-    check(lib.tlbo_rank_loss_counts(ptr(dy), ptr(dys), int(n), int(S), int(Mr), ptr(dlo), ptr(dhi),
-                                    1 if upper_only else 0, ptr(counts), _stream()))
-    return counts.cpu().numpy()
+    with _call('rank_loss_counts', 1):
+        check(lib.tlbo_rank_loss_counts(ptr(dy), ptr(dys), int(n), int(S), int(Mr), ptr(dlo), ptr(dhi),
+                                        1 if upper_only else 0, ptr(counts), _stream()))
+    return d2h(counts)
 
 
 class PairLogistic(object):
@@ -244,8 +345,8 @@ class PairLogistic(object):
         dev = _dev()
         A = np.ascontiguousarray(A, dtype=np.float64)
         self.n, self.m = A.shape
-        self.dA = torch.from_numpy(A).to(dev)
-        self.dy = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))).to(dev)
+        self.dA = h2d(A)
+        self.dy = h2d(np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1)))
         self.dw = torch.zeros(self.m, dtype=F64, device=dev)
         self.out = torch.zeros(2 + self.m, dtype=F64, device=dev)
         self._cache_w = None
@@ -256,9 +357,11 @@ class PairLogistic(object):
         if self._cache_w is not None and np.array_equal(w, self._cache_w):
             return self._cache
         self.dw.copy_(torch.from_numpy(w))
-        check(lib.tlbo_pairwise_logistic_loss_grad(ptr(self.dA), ptr(self.dy), ptr(self.dw), self.n, self.m,
-                                                   ptr(self.out), _stream()))
-        o = self.out.cpu().numpy()
+        STATS.h2d += w.nbytes
+        with _call('pairwise_logistic', 1):
+            check(lib.tlbo_pairwise_logistic_loss_grad(ptr(self.dA), ptr(self.dy), ptr(self.dw), self.n, self.m,
+                                                       ptr(self.out), _stream()))
+        o = d2h(self.out)
         self._cache_w = w.copy()
         self._cache = (float(o[0]), int(o[1]), o[2:].copy())
         return self._cache

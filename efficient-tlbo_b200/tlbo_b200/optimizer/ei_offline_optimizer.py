@@ -1,0 +1,99 @@
+"""Acquisition maximiser over a fixed candidate table
+(reference tlbo/optimizer/ei_offline_optimizer.py:10-29 ``OfflineSearch``,
+tlbo/optimizer/ei_optimization.py:50-132).
+
+The table is uploaded once and stays resident in HBM.  ``maximize`` consumes one
+``rng.rand(N)`` per call exactly like ``_sort_configs_by_acq_value`` and returns the
+candidates best-first; by default only the head of that order is materialised (the caller
+-- smbo_offline.py:261-263 -- takes the first unevaluated entry), via the fused arg-max."""
+import numpy as np
+
+from tlbo_b200.config_space import Configuration, convert_configurations_to_array
+
+
+class AcquisitionFunctionMaximizer(object):
+    def __init__(self, acquisition_function, config_space, rng=None):
+        self.acquisition_function = acquisition_function
+        self.config_space = config_space
+        if rng is None:
+            self.rng = np.random.RandomState(seed=1)
+        else:
+            self.rng = rng
+
+    def maximize(self, runhistory, num_points, **kwargs):
+        return [t[1] for t in self._maximize(runhistory, num_points, **kwargs)]
+
+
+class OfflineSearch(AcquisitionFunctionMaximizer):
+    def __init__(self, configuration_list, acquisition_function, config_space, rng=None, shard=None):
+        super().__init__(acquisition_function, config_space, rng)
+        import torch
+        from tlbo_b200 import ops
+        if isinstance(configuration_list, np.ndarray):
+            self.X_table = np.ascontiguousarray(configuration_list, dtype=np.float64)
+            self.configuration_list = None
+        else:
+            self.configuration_list = configuration_list
+            self.X_table = convert_configurations_to_array(configuration_list)
+        X = self.X_table.copy()
+        X[~np.isfinite(X)] = -1
+        self.N = X.shape[0]
+        # candidate-pool sharding (tlbo_b200.distributed.PoolShard): this rank's row range
+        self.shard = shard
+        lo, hi = (0, self.N) if shard is None else shard.row_range(self.N)
+        self.lo, self.hi = lo, hi
+        ops._dev()        # no CPU fallback: raises without a CUDA device
+        self._host_rows = torch.from_numpy(X[lo:hi]).pin_memory()
+        self.X_dev = self._host_rows.to('cuda', non_blocking=True)
+        self._ws = ops.FusedWorkspace()
+        self._keys_host = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+        self._keys_dev = torch.empty(hi - lo, dtype=torch.float64, device='cuda')
+        self.last_best = None
+
+    def reupload(self):
+        """Host -> device copy of the candidate rows (the end-to-end benchmark path, where
+        the caller hands host configurations on every call like the reference does)."""
+        from tlbo_b200 import ops
+        self.X_dev.copy_(self._host_rows, non_blocking=True)
+        ops.STATS.h2d += self._host_rows.numel() * 8
+
+    def _config(self, idx):
+        if self.configuration_list is not None:
+            return self.configuration_list[idx]
+        return Configuration(self.config_space, self.X_table[idx], idx)
+
+    def best_unevaluated(self, evaluated_rows):
+        """Row index the reference's loop would return: first entry of the descending
+        (EI, random key) order that is not in ``evaluated_rows``."""
+        import torch
+        from tlbo_b200 import ops
+        keys = self.rng.rand(self.N)
+        self._keys_host.copy_(torch.from_numpy(keys[self.lo:self.hi]))
+        self._keys_dev.copy_(self._keys_host, non_blocking=True)
+        ops.STATS.h2d += self._keys_host.numel() * 8
+        ex = None
+        if len(evaluated_rows):
+            ex = ops.h2d(np.sort(np.asarray(evaluated_rows, dtype=np.int64)))
+        if self.shard is None:
+            res = self.acquisition_function.best_unevaluated(self.X_dev, keys=self._keys_dev, excluded=ex,
+                                                             ws=self._ws)
+        else:
+            best_dev = self.acquisition_function.best_unevaluated(self.X_dev, keys=self._keys_dev, excluded=ex,
+                                                                  idx_offset=self.lo, ws=self._ws, sync=False)[0]
+            res = self.shard.reduce_best(best_dev)
+            if res[3] > 0:
+                raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")
+        self.last_best = res
+        if res[2] < 0:
+            raise ValueError('The configuration in the SET (%d) is over' % self.N)
+        return res[2]
+
+    def _maximize(self, runhistory, num_points, evaluated_rows=(), full_order=False, **kwargs):
+        if not full_order:
+            idx = self.best_unevaluated(evaluated_rows)
+            return [(self.last_best[0], self._config(idx))]
+        # full descending order (reference semantics, O(N log N) on the host)
+        acq = self.acquisition_function(self.X_table)
+        random = self.rng.rand(self.N)
+        indices = np.lexsort((random.flatten(), acq.flatten()))
+        return [(acq[ind][0], self._config(ind)) for ind in indices[::-1]]

@@ -118,10 +118,14 @@ int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, const double*
  * the NaN rule of __call__ (:73-76), lexsort((rand, ei))[::-1]
  * (tlbo/optimizer/ei_optimization.py:126-132) and the first-unevaluated scan
  * (tlbo/framework/smbo_offline.py:261-263).
- *   d_w [M]           ensemble weights in ACCUMULATION order (w == 0 and skip -> model skipped)
+ *   d_w [M]           ensemble weight of every pack slot
  *   d_skip [M] int32  1 = leave the surrogate out (RGPE ignored_flag), may be NULL
+ *   d_order [M] int32 pack slots in ACCUMULATION order (floating-point sums follow the
+ *                     reference's loop order: RGPE adds the target first, rgpe.py:142-152;
+ *                     combine_predictions adds it last, base_facade.py:152-160); NULL = 0..M-1
  *   mode              0: mu = sum w mu_m, var = sum w^2 var_m   (RGPE / 'idp_lc')
- *                     1: TST: mu = (mu_0 + sum_{m>0} w_m mu_m) / (0.75 + sum w), var = var_0
+ *                     1: TST (tst.py:64-73): first slot in order = target t,
+ *                        mu = (mu_t + sum_{m != t} w_m mu_m) / (0.75 + sum_{m != t} w_m), var = var_t
  *   d_cand [N, d]     candidate rows, reference column order
  *   eta, par          EI incumbent and xi
  *   var_floor         facade / model variance threshold (1e-10 or 1e-5)
@@ -132,7 +136,8 @@ int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, const double*
  *   non-excluded row; optional per-row d_mu, d_var, d_ei [N] (after floor / NaN rule).
  *   d_work: scratch of tlbo_predict_ei_workspace_bytes(N) bytes.                       */
 int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
-                          const int32_t* d_skip, int mode, const double* d_cand, int64_t N, double eta,
+                          const int32_t* d_skip, const int32_t* d_order, int mode, const double* d_cand,
+                          int64_t N, double eta,
                           double par, double var_floor, const double* d_keys, const int64_t* d_excluded,
                           int n_excl, int64_t idx_offset, double* d_best, double* d_mu, double* d_var,
                           double* d_ei, void* d_work, void* stream);

@@ -1,0 +1,193 @@
+"""End-to-end parity of the drop-in (facade + EI + maximiser + offline loop on the GPU)
+against the oracle's restatement of the reference loop, iteration by iteration.
+
+Hyper-parameter optimisation is checked separately (tests/test_gpu_fit.py); here the
+oracle's GPs are teacher-forced with the hyper-parameters the device fit selected, so that
+everything downstream -- source / CV predictions, the bootstrap draws taken from the global
+np.random stream, the integer ranking losses, weights, dilution flags, EI, tie-broken
+ordering and the selected row -- must agree: counts and indices bit-exact, floats to 1e-6."""
+import numpy as np
+import pytest
+
+import oracle.facade as ofacade
+from oracle.acquisition import OracleSMBOOffline
+from oracle.gp import OracleGP
+
+pytestmark = pytest.mark.gpu
+
+
+class ForcedGP(OracleGP):
+    queue = []
+
+    def train(self, X, Y, do_optimize=True, theta=None):
+        th = ForcedGP.queue.pop(0)
+        return super().train(X, Y, do_optimize=False, theta=th)
+
+
+@pytest.fixture
+def forced(monkeypatch):
+    monkeypatch.setattr(ofacade, 'OracleGP', ForcedGP)
+    ForcedGP.queue = []
+    yield ForcedGP
+    ForcedGP.queue = []
+
+
+def _bench(K, N, seed, kind='rf', d=None):
+    from tlbo_b200 import synthetic
+    b = synthetic.make_benchmark(n_tasks=K + 1, T=N, kind=kind, d=d, seed=seed)
+    sources, _ = synthetic.leave_one_out_sources(b['tables'], 0, K, seed)
+    return b['types'], sources, b['tables'][0]
+
+
+def _make(method, types, sources, seed):
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.notl import NoTL
+    from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
+    from tlbo_b200.facade.topo_variant1 import OBTLV
+    from tlbo_b200.facade.tst import TST
+    cs = TableSpace(types)
+    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, tst=TST, notl=NoTL)[method]
+    prod = cls(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+    return cs, prod
+
+
+def _make_oracle(method, types, sources, seed, prod, forced):
+    K = len(sources)
+    if method != 'notl':
+        forced.queue = [prod._pack.theta[k].cpu().numpy() for k in range(K)]
+    if method == 'rgpe':
+        return ofacade.OracleRGPE(types, sources, seed)
+    if method == 'trans_rgpe':
+        return ofacade.OracleRGPE(types, sources, seed, smooth=0.7)
+    if method == 'topo':
+        return ofacade.OracleOBTLV(types, sources, seed)
+    if method == 'tst':
+        return ofacade.OracleTST(types, sources, seed)
+    return ofacade.OracleNoTL(types, sources, seed)
+
+
+@pytest.mark.parametrize('method,K,N,iters,kind,d', [
+    ('rgpe', 4, 3000, 16, 'rf', None),
+    ('trans_rgpe', 3, 2000, 14, 'rf', None),
+    ('topo', 4, 3000, 14, 'rf', None),
+    ('tst', 3, 2000, 9, 'rf', None),
+    ('notl', 2, 2000, 8, 'cont', 5),
+])
+def test_offline_loop_matches_oracle(method, K, N, iters, kind, d, forced):
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    seed = 4465
+    types, sources, (Xt, yt) = _bench(K, N, seed, kind, d)
+    cs, prod = _make(method, types, sources, seed)
+    ora = _make_oracle(method, types, sources, seed, prod, forced)
+    assert not forced.queue
+    smbo = SMBO_OFFLINE((Xt, yt), cs, prod, random_seed=seed, max_runs=iters)      # seeds np.random
+    state = np.random.get_state()
+    osmbo = OracleSMBOOffline(Xt, yt, ora, seed, max_runs=iters)
+    np.random.set_state(state)
+    if method in ('rgpe', 'trans_rgpe', 'topo'):
+        for k in range(K):
+            assert abs(prod.eta_list[k] - ora.eta_list[k]) < 1e-12
+    for it in range(iters):
+        s0 = np.random.get_state()
+        cfg, st, perf, _ = smbo.iterate()
+        s1 = np.random.get_state()
+        n_prev = len(osmbo.evaluated)
+        if n_prev >= 3:
+            n_fit = 1
+            if method in ('rgpe', 'trans_rgpe', 'topo') and n_prev >= 5:
+                n_fit = 6
+            forced.queue = [prod._pack.theta[K + j].cpu().numpy() for j in range(n_fit)]
+        np.random.set_state(s0)
+        idx = osmbo.iterate()
+        s2 = np.random.get_state()
+        assert not forced.queue
+        # identical consumption of the global stream
+        assert s1[2] == s2[2] and (s1[1] == s2[1]).all() and s1[3] == s2[3] and s1[4] == s2[4]
+        assert cfg.index == idx, (it, cfg.index, idx)
+        assert smbo.configurations == osmbo.evaluated
+        if n_prev >= 3 and method != 'notl':
+            np.testing.assert_allclose(np.asarray(prod.w, float), np.asarray(ora.w, float), rtol=0, atol=2e-5)
+            np.testing.assert_allclose(prod.target_weight[-1], ora.target_weight[-1], rtol=0, atol=2e-5)
+        if n_prev >= 3 and method in ('rgpe', 'trans_rgpe'):
+            assert (prod.last_losses == ora.last_losses).all()
+            assert list(prod.ignored_flag) == list(ora.ignored_flag)
+        if n_prev >= 3 and osmbo.last_acq is not None:
+            ei_o = float(osmbo.last_acq[idx, 0])
+            ei_p = smbo.acq_optimizer.last_best[0]
+            assert abs(ei_p - ei_o) <= 1e-6 * max(abs(ei_o), 1e-12) + 1e-13
+    assert abs(smbo.get_adtm() - osmbo.get_adtm()) < 1e-15
+
+
+def test_facade_predict_and_ei_call_interface(forced):
+    """predict / predict_marginalized_over_instances / EI.__call__ shapes, floors, errors."""
+    from tlbo_b200.acquisition_function.acquisition import EI
+    from tlbo_b200.config_space import table_to_configurations
+    seed = 3822
+    types, sources, (Xt, yt) = _bench(3, 500, seed)
+    cs, prod = _make('rgpe', types, sources, seed)
+    ora = _make_oracle('rgpe', types, sources, seed, prod, forced)
+    X, y = Xt[:12].copy(), yt[:12].copy()
+    np.random.seed(1)
+    prod.train(X, y.copy())
+    forced.queue = [prod._pack.theta[3 + j].cpu().numpy() for j in range(6)]
+    np.random.seed(1)
+    ora.train(X, y.copy())
+    Xq = Xt[100:400]
+    mu, var = prod.predict(Xq)
+    mo, vo = ora.predict(Xq)
+    assert mu.shape == (300, 1) and var.shape == (300, 1)
+    np.testing.assert_allclose(mu, mo, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, vo, rtol=1e-6, atol=1e-13)
+    m2, v2 = prod.predict_marginalized_over_instances(Xq)
+    assert (v2 >= 1e-10).all()
+    with pytest.raises(ValueError):
+        prod.predict_marginalized_over_instances(Xq[:, :3])
+    with pytest.raises(ValueError):
+        prod.predict_marginalized_over_instances(Xq[0])
+    ei = EI(prod)
+    with pytest.raises(ValueError):
+        ei(table_to_configurations(cs, Xq[:4]))
+    ei.update(model=prod, eta=float(np.min((y - y.mean()) / y.std())), num_data=12)
+    acq = ei(table_to_configurations(cs, Xq))
+    assert acq.shape == (300, 1) and (acq >= 0).all()
+    from oracle.acquisition import OracleEI
+    oe = OracleEI(ora)
+    oe.update(eta=ei.eta)
+    np.testing.assert_allclose(acq, oe(Xq), rtol=1e-6, atol=1e-12)
+    # a single surrogate behind the same interface (plain SMBO: 1e-5 floor)
+    gp = prod.source_surrogates[0]
+    m, v = gp.predict_marginalized_over_instances(Xq)
+    og = ora.source_surrogates[0]
+    mo, vo = og.predict_marginalized_over_instances(Xq)
+    np.testing.assert_allclose(m, mo, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(v, vo, rtol=1e-6, atol=1e-13)
+    e1 = EI(gp)
+    e1.update(eta=-0.5)
+    o1 = OracleEI(og)
+    o1.update(eta=-0.5)
+    np.testing.assert_allclose(e1._compute(Xq), o1._compute(Xq), rtol=1e-6, atol=1e-12)
+
+
+def test_gp_train_validation_errors():
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.model.model_builder import build_model
+    cs = TableSpace([2, 0, 0])
+    m = build_model('gp', cs, np.random.RandomState(1))
+    X = np.random.RandomState(0).rand(10, 3)
+    X[:, 0] = np.round(X[:, 0])
+    y = X[:, 1] * 2
+    with pytest.raises(ValueError):
+        m.train(X[:, :2], y)
+    with pytest.raises(ValueError):
+        m.train(X, y[:5])
+    with pytest.raises(ValueError):
+        m.train(X[0], y)
+    with pytest.raises(Exception):
+        m.predict(X)
+    with pytest.raises(ValueError):
+        build_model('rf', cs, np.random.RandomState(1))
+    m.train(X, y)
+    assert m.is_trained and m.hypers.shape == (5,)
+    mu, var = m.predict(X)
+    assert mu.shape == (10, 1) and var.shape == (10, 1)
+    assert np.abs(mu.ravel() - y).max() < 0.05
