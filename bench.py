@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""Headline benchmark of the surrogate-and-acquisition hot path.
+
+Metric (BASELINE.json): BO iterations / second, one iteration = fit (target + 5 CV GPs, 11
+L-BFGS-B restarts each) + ensemble weights (RGPE bootstrap ranking loss or TOPO SLSQP) +
+fused predict / EI / arg-max over the whole candidate pool, at 29 source surrogates.
+Workload = BASELINE.json configs[1]: 29 source GPs (50 observations each), 10^5-candidate
+pool, random_forest-shaped space (d = 9), synthetic histories.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+Prints ONE JSON line (rank 0).  N > 1: one process per GPU (torchrun); ranks run independent
+BO trials (different target task / seed) -- the path shards by trial with no data-path
+collective ("weak" scaling); a pool-sharded run of ONE trial (tiny NCCL all-gather of the
+per-rank arg-max) is reported beside it under "pool_sharded".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+if 'reference' in sys.argv:
+    # the reference pins every BLAS/OpenMP pool to one thread (tools/offline_benchmark.py:3-8);
+    # must happen before numpy is imported
+    for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'VECLIB_MAXIMUM_THREADS',
+               'NUMEXPR_NUM_THREADS'):
+        os.environ[_v] = '1'
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'efficient-tlbo_b200')
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'BO iters/sec (fit+weights+EI) at 29 sources'
+UNIT = 'iters/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--method', default='rgpe', choices=['rgpe', 'topo', 'trans_rgpe', 'tst'])
+    ap.add_argument('--pool', type=int, default=100000)
+    ap.add_argument('--sources', type=int, default=29)
+    ap.add_argument('--n0', type=int, default=40, help='target observations before the first step')
+    ap.add_argument('--cpu-sample-rows', type=int, default=10000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-pool-sharded', action='store_true')
+    ap.add_argument('--ref-procs', type=int, default=0, help='reference arm: worker processes (0 = all cores)')
+    ap.add_argument('--pair-loops', default='literal', choices=['literal', 'vectorised'],
+                    help='reference arm: literal Python pair loops (as the reference) or numpy broadcasting')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+def build_workload(task, seed, pool, K, n0, n_tasks=30):
+    """Synthetic histories shaped like the reference's pickles: 30 tasks,
+    RF-shaped space; the K sources contribute their first 50 rows, the target a pool table."""
+    from tlbo_b200 import synthetic
+    types, const = synthetic.space_types('rf')
+    fam = synthetic.TaskFamily(types, const, n_tasks=n_tasks, seed=4466)
+    ids = [i for i in range(n_tasks) if i != task]
+    np.random.RandomState(seed).shuffle(ids)
+    ids = ids[:K]
+    sources = []
+    for k in ids:
+        rng = np.random.RandomState(1000 + k)
+        X = synthetic.sample_table(rng, 50, types, const)
+        sources.append((X, fam.evaluate(k, X, rng)))
+    rng = np.random.RandomState(2000 + task)
+    Xt = synthetic.sample_table(rng, pool, types, const)
+    yt = fam.evaluate(task, Xt, rng)
+    rows0 = [0] + list(np.random.RandomState(seed + 1).choice(np.arange(1, pool), size=n0 - 1, replace=False))
+    return dict(types=types, sources=sources, Xt=Xt, yt=yt, rows0=[int(r) for r in rows0], seed=seed)
+
+
+def fused_flops_per_candidate(n_list, d_cont, d_cat):
+    """SURVEY.md 8(d) algorithmic flops of one candidate through the surrogates actually
+    evaluated (triangular L^-1 form: n^2 + 2n for the quadratic form)."""
+    f = 30.0
+    for n in n_list:
+        f += n * (3 * d_cont + 2 * d_cat + 12) + 2 * n + n * n + 2 * n
+    return f
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (numpy/scipy restatement of the reference path), reference-faithful
+# variant (literal Python pair loops as in tlbo/facade/rgpe.py:74-109).
+def _oracle_facade(method, types, sources, seed, literal):
+    import oracle.facade as of
+    if method == 'rgpe':
+        return of.OracleRGPE(types, sources, seed, literal_loops=literal)
+    if method == 'trans_rgpe':
+        return of.OracleRGPE(types, sources, seed, smooth=0.7, literal_loops=literal)
+    if method == 'topo':
+        return of.OracleOBTLV(types, sources, seed, literal_loops=literal)
+    return of.OracleTST(types, sources, seed, literal_loops=literal)
+
+
+def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, literal=True, quiet=True):
+    """Runs warmup + steps BO iterations of the oracle.  Per step: the full fit + weights
+    (timed), and EI + ordering over the first ``sample_rows`` pool rows (timed, then scaled
+    by pool / sample_rows: the work is exactly linear in the number of candidates).
+    Returns (train_s[], maximize_s_scaled[], setup_s)."""
+    from oracle.acquisition import OracleEI, first_unevaluated, sort_by_acq_value
+    from oracle.facade import zero_mean_unit_var_normalization, zero_one_normalization
+    wl = build_workload(task, seed, pool, K, n0)
+    t0 = time.perf_counter()
+    fac = _oracle_facade(method, wl['types'], wl['sources'], seed, literal)
+    setup = time.perf_counter() - t0
+    np.random.seed(seed)
+    acq_rng = np.random.RandomState(seed)
+    ei = OracleEI(fac)
+    Xs = wl['Xt'][:sample_rows]
+    evaluated = list(wl['rows0'])
+    scale = float(pool) / float(sample_rows)
+    tr, mx = [], []
+    for it in range(warmup + steps):
+        X = wl['Xt'][evaluated]
+        Y = wl['yt'][evaluated].copy()
+        a = time.perf_counter()
+        fac.train(X, Y)
+        b = time.perf_counter()
+        y_ = (zero_one_normalization(Y) if fac.method_id in ['tst', 'tstm'] else zero_mean_unit_var_normalization(Y))[0]
+        ei.update(model=fac, eta=np.min(y_), num_data=len(evaluated))
+        acq = ei(Xs)
+        order, _ = sort_by_acq_value(acq, acq_rng)
+        idx = first_unevaluated(order, evaluated)
+        c = time.perf_counter()
+        evaluated.append(idx)
+        if it >= warmup:
+            tr.append(b - a)
+            mx.append((c - b) * scale)
+    return tr, mx, setup
+
+
+def _oracle_worker(args):
+    return oracle_trial(*args)
+
+
+def cpu_baseline_sample(args, n_start):
+    """One reference-faithful oracle iteration on this box's host (1 core, BLAS pinned to one
+    thread as the reference mandates), bounded sample.  Runs in a child process so the thread
+    pins take effect before numpy loads."""
+    def child(loops):
+        cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--ref-procs', '1', '--steps', '1',
+               '--warmup', '0', '--n0', str(n_start), '--method', args.method, '--pool', str(args.pool),
+               '--sources', str(args.sources), '--cpu-sample-rows', str(args.cpu_sample_rows),
+               '--pair-loops', loops]
+        env = dict(os.environ)
+        for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+            env.pop(k, None)
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1200)
+        if out.returncode != 0:
+            raise RuntimeError('cpu baseline child failed: ' + out.stderr[-2000:])
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    lit = child('literal')
+    vec = child('vectorised')
+    tr, mx = [lit['train_s_per_step']], [lit['maximize_s_per_step_scaled']]
+    t = tr[0] + mx[0]
+    tv = vec['train_s_per_step'] + vec['maximize_s_per_step_scaled']
+    return dict(value=1.0 / t, unit=UNIT, cores=1, kind='port',
+                sample=('1 BO iteration of the numpy/scipy oracle at target n=%d, K=%d: fit+weights at full size '
+                        '(literal Python pair loops as the reference), EI+sort on the first %d of %d pool rows '
+                        'scaled x%.0f' % (n_start, args.sources, args.cpu_sample_rows, args.pool,
+                                          args.pool / args.cpu_sample_rows)),
+                train_s=tr[0], maximize_s_scaled=mx[0],
+                value_vectorised_pair_count=1.0 / tv, host_cores_available=os.cpu_count())
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    P = args.ref_procs or (os.cpu_count() or 1)
+    n_start = args.n0
+    jobs = [(args.method, t % 30, 4465 + t, args.pool, args.sources, n_start, args.steps, args.warmup,
+             args.cpu_sample_rows, args.pair_loops == 'literal') for t in range(P)]
+    t0 = time.perf_counter()
+    if P == 1:
+        res = [_oracle_worker(jobs[0])]
+    else:
+        with mp.get_context('fork').Pool(P) as pool:
+            res = pool.map(_oracle_worker, jobs)
+    wall = time.perf_counter() - t0
+    per_proc = [sum(r[0]) + sum(r[1]) for r in res]
+    total = max(per_proc)
+    value = P * args.steps / total
+    sample = ('%d parallel single-thread processes (one independent BO trial each, as the reference pins BLAS to 1 '
+              'thread); per step: fit+weights at full size (PAIRLOOPS pair loops), EI+sort on the first %d of '
+              '%d pool rows scaled x%.0f; target n=%d..%d'
+              % (P, args.cpu_sample_rows, args.pool, args.pool / args.cpu_sample_rows, n_start + args.warmup,
+                 n_start + args.warmup + args.steps - 1)).replace('PAIRLOOPS', args.pair_loops)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, 'cpu'),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': P, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': wall,
+        'per_trial_ms_per_step': 1e3 * float(np.mean(per_proc)) / args.steps,
+        'train_s_per_step': float(np.mean([np.mean(r[0]) for r in res])),
+        'maximize_s_per_step_scaled': float(np.mean([np.mean(r[1]) for r in res])),
+        'pair_loops': args.pair_loops,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, where):
+    return {
+        'workload': '%s offline BO, %d source GPs x 50 obs, %d-candidate EI pool, d=9 random_forest space, '
+                    'target n=%d..%d' % (args.method, args.sources, args.pool, args.n0 + args.warmup,
+                                         args.n0 + args.warmup + args.steps - 1),
+        'method': args.method, 'sources': args.sources, 'pool': args.pool, 'd': 9,
+        'restarts_per_fit': 11, 'fits_per_iter': 6,
+        'l2': ('flushed before every step (256 MiB device memset inside the timed region)' if where == 'gpu'
+               else 'n/a (host)'),
+        'multi_gpu': 'independent BO trials per rank (no data-path collective)',
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def make_product(args, wl, shard=None):
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
+    from tlbo_b200.facade.topo_variant1 import OBTLV
+    from tlbo_b200.facade.tst import TST
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, tst=TST)[args.method]
+    cs = TableSpace(wl['types'])
+    fac = cls(cs, wl['sources'], None, wl['seed'], surrogate_type='gp', num_src_hpo_trial=50)
+    smbo = SMBO_OFFLINE((wl['Xt'], wl['yt']), cs, fac, random_seed=wl['seed'], max_runs=10 ** 9, shard=shard)
+    smbo.configurations = list(wl['rows0'])
+    smbo.perfs = [float(wl['yt'][r]) for r in wl['rows0']]
+    return fac, smbo
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tlbo_b200 import ops
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py (impl=ours) needs a CUDA device; there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = build_workload(rank % 30, 4465 + rank, args.pool, args.sources, args.n0)
+    fac, smbo = make_product(args, wl)
+    d_cont = int((wl['types'] == 0).sum())
+    d_cat = int((wl['types'] != 0).sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dmma_tf = ops.fp64_peak_probe()
+    K, W = args.steps, args.warmup
+
+    def step(e2e):
+        flush.zero_()
+        if e2e:
+            smbo.acq_optimizer.reupload()
+        cfg, _, _, _ = smbo.iterate()
+        return cfg.index
+
+    # ---- warm-up
+    for _ in range(W):
+        step(False)
+    snap = (list(smbo.configurations), list(smbo.perfs))
+
+    def timed(e2e, record_flops):
+        smbo.configurations, smbo.perfs = list(snap[0]), list(snap[1])
+        ops.STATS.reset()
+        ops.STATS.timing = record_flops
+        flops = 0.0
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            step(e2e)
+            if record_flops:
+                n_t = len(smbo.configurations) - 1
+                skip = list(getattr(fac, 'ignored_flag', [False] * fac.K))
+                ns = [50 for k in range(fac.K) if not skip[k]] + [n_t]
+                flops += fused_flops_per_candidate(ns, d_cont, d_cat) * args.pool
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        ops.STATS.timing = False
+        return ms, wall, flops
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, wall_res, flops = timed(False, True)
+    kms = ops.STATS.kernel_ms()
+    launches = ops.STATS.total_launches()
+    launch_detail = dict(ops.STATS.launches)
+    clocks = sampler.stop()
+    ms_e2e, wall_e2e, _ = timed(True, False)
+    h2d_step = ops.STATS.h2d / float(K)
+    d2h_step = ops.STATS.d2h / float(K)
+
+    # ---- pool-sharded variant of ONE trial (all ranks fit redundantly, each scores a row
+    # range, NCCL all-gather of the per-rank arg-max)
+    pool_sharded = None
+    if world > 1 and not args.no_pool_sharded:
+        from tlbo_b200.distributed import PoolShard
+        wl0 = build_workload(0, 4465, args.pool * world, args.sources, args.n0)
+        shard = PoolShard()
+        fac_s, smbo_s = make_product(args, wl0, shard=shard)
+        for _ in range(W):
+            smbo_s.iterate()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            smbo_s.iterate()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms_s = max_over_ranks(e0.elapsed_time(e1))
+        pool_sharded = {'value': K / (ms_s * 1e-3), 'unit': UNIT, 'pool_rows_total': args.pool * world,
+                        'collective': 'all_gather of 4 doubles per rank (NCCL)', 'ms_per_step': ms_s / K,
+                        'rows_selected': smbo_s.configurations[-3:]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused predict + EI + arg-max kernel
+    fused_calls, fused_ms = kms.get('predict_ei_fused', (0, 0.0))
+    peaks = {}
+    pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            peaks = json.load(f)
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    hbm_src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    traffic = None
+    tr_path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tr_path):
+        with open(tr_path) as f:
+            traffic = json.load(f).get('predict_ei_fused_dram_bytes_per_launch')
+    ach_tf = flops / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else 0.0
+    alg_bytes = args.pool * (8.0 * 9 + 8.0)
+    ach_gbs = alg_bytes * fused_calls / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
+    roofline = {
+        'kernel': 'predict_ei_fused_kernel', 'bound': 'tensor', 'achieved': ach_tf, 'peak': dmma_tf[1],
+        'unit': 'TFLOP/s', 'frac': ach_tf / dmma_tf[1] if dmma_tf[1] else None, 'traffic': traffic,
+        'peak_source': 'FP64 DMMA (mma.m8n8k4.f64) rate measured by tlbo_fp64_peak_probe in this run; '
+                       'MEASURED_PEAKS.json carries no FP64 figure. FP64 FMA-pipe rate: %.2f TFLOP/s' % dmma_tf[0],
+        'algorithmic_flops_per_launch': flops / max(fused_calls, 1),
+        'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': fused_ms / max(fused_calls, 1),
+        'hbm_achieved_gbs': ach_gbs, 'hbm_peak_gbs': hbm_peak, 'hbm_frac': ach_gbs / hbm_peak,
+        'hbm_peak_source': hbm_src,
+        'note': 'FP64-compute-bound kernel (arithmetic intensity ~%.0f flop/B); flops by SURVEY.md 8(d), '
+                'triangular L^-1 form, over the surrogates actually evaluated' % (
+                    flops / max(fused_calls, 1) / alg_bytes),
+    }
+    step_ms = ms_res / K
+    breakdown = {k: {'calls_per_step': c / float(K), 'ms_per_step': t / K, 'share_of_step': t / ms_res}
+                 for k, (c, t) in kms.items()}
+    line = {
+        'metric': METRIC, 'value': world * K / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, 'gpu'),
+        'e2e': {'value': world * K / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_step,
+                'd2h_bytes_per_step': d2h_step, 'ms_per_step': ms_e2e / K,
+                'api': 'SMBO_OFFLINE.iterate() with the candidate table re-uploaded from pinned host memory '
+                       'every step and the selected row read back'},
+        'gpu_launches': launches, 'gpu_launch_detail': launch_detail,
+        'clocks': clocks, 'roofline': roofline, 'step_breakdown': breakdown,
+        'predict_candidates_per_s': args.pool * fused_calls / (fused_ms * 1e-3) if fused_ms > 0 else None,
+        'host_wall_ms_per_step': 1e3 * wall_res / K,
+    }
+    if pool_sharded is not None:
+        line['pool_sharded'] = pool_sharded
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline_sample(args, args.n0 + W)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

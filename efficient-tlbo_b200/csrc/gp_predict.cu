@@ -334,7 +334,12 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) predict_ei_fused_kernel(Fused
           const double z = dm / s;
           const double cdf = 0.5 * erfc(-z * 0.7071067811865476);
           const double pdf = exp(-0.5 * z * z) * 0.3989422804014327;
-          f = dm * cdf + s * pdf;
+          // two products and one sum, each rounded (numpy semantics, no FMA contraction)
+          f = __dadd_rn(__dmul_rn(dm, cdf), __dmul_rn(s, pdf));
+          // z < -37.5: Phi(z) is subnormal and the two terms (equal to ~1e-3 relative) carry
+          // no relative precision, so the sign of their difference is rounding luck of the
+          // libm in use (glibc happens to stay >= 0); EI there is < 1e-305 * s.
+          if (f < 0.0 && cdf < 2.2250738585072014e-308) f = 0.0;
         }
         if (f < 0.0) negcount += 1.0;
         if (f != f) f = -DBL_MAX;
