@@ -17,6 +17,7 @@
 //   5. + log-priors (lognormal on c, horseshoe on s2) and their gradients.
 #include "tlbo_common.cuh"
 #include "lbfgsb_dense.cuh"
+#include "lbfgsb_warp.cuh"
 
 #define FIT_THREADS 256
 
@@ -293,17 +294,26 @@ struct FitArgs {
   size_t panel_stride;   // doubles
 };
 
-template <int DMAX>
+// Optimiser state size in shared memory (either variant).
+__host__ __device__ inline size_t fit_state_bytes() {
+  const size_t a = sizeof(LbfgsbState), b = sizeof(LbwState);
+  return (((a > b ? a : b) + 15) / 16) * 16;
+}
+
+// WARP_OPT = true: warp-cooperative optimiser (lbfgsb_warp.cuh, default);
+//            false: single-thread reference statement of the same optimiser (lbfgsb_dense.cuh).
+template <int DMAX, bool WARP_OPT>
 __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x / a.R, r = blockIdx.x - b * a.R;
   const int n = a.n[b], d = a.d, H = d + 2;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   __shared__ double th[TLBO_HMAX];
   __shared__ double fg[1 + TLBO_HMAX];
   __shared__ int act;
   LbfgsbState* st = reinterpret_cast<LbfgsbState*>(smem);
-  unsigned char* rest = smem + ((sizeof(LbfgsbState) + 15) / 16) * 16;
+  LbwState* sw = reinterpret_cast<LbwState*>(smem);
+  unsigned char* rest = smem + fit_state_bytes();
   FitWs S;
   carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
@@ -332,22 +342,31 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
     }
     return;
   }
-  if (tid == 0) lbfgsb_init(*st, H, th, a.lo, a.hi);
+  if (WARP_OPT) { if (wid == 0) lbw_init(*sw, H, th, a.lo, a.hi, lane); }
+  else { if (tid == 0) lbfgsb_init(*st, H, th, a.lo, a.hi); }
   __syncthreads();
   for (;;) {
-    if (tid < H) th[tid] = st->x[tid];
+    if (tid < H) th[tid] = WARP_OPT ? sw->x[tid] : st->x[tid];
     __syncthreads();
     nll_eval<DMAX>(S, a.sp, th, fg);
     nfev++;
-    if (tid == 0) act = lbfgsb_feed(*st, fg[0], fg + 1);
+    if (WARP_OPT) {
+      if (wid == 0) {
+        const int rc = lbw_feed(*sw, fg[0], fg + 1, lane);
+        if (lane == 0) act = rc;
+      }
+    } else {
+      if (tid == 0) act = lbfgsb_feed(*st, fg[0], fg + 1);
+    }
     __syncthreads();
     if (act == LB_DONE) break;
   }
-  if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = st->x[tid];
+  if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = WARP_OPT ? sw->x[tid] : st->x[tid];
   if (tid == 0) {
-    a.restart_f[(size_t)b * a.R + r] = st->f_last;
+    a.restart_f[(size_t)b * a.R + r] = WARP_OPT ? sw->f_last : st->f_last;
     int32_t* info = a.restart_info + ((size_t)b * a.R + r) * 4;
-    info[0] = nfev; info[1] = st->iter; info[2] = st->status; info[3] = bumps;
+    info[0] = nfev; info[1] = WARP_OPT ? sw->iter : st->iter; info[2] = WARP_OPT ? sw->status : st->status;
+    info[3] = bumps;
   }
 }
 
@@ -484,6 +503,13 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) 
 // ---------------------------------------------------------------------------------------
 // host side
 static const size_t kSmemLimit = 227 * 1024;
+static int g_fit_variant = 1;   // 1 = warp-cooperative optimiser, 0 = single-thread statement
+
+extern "C" int tlbo_set_fit_variant(int variant) {
+  const int old = g_fit_variant;
+  g_fit_variant = variant ? 1 : 0;
+  return old;
+}
 
 struct WorkLayout {
   bool global_panels;
@@ -495,7 +521,7 @@ static WorkLayout plan(int ncap, int d) {
   WorkLayout w;
   const size_t small = fit_small_bytes(ncap, d);
   const size_t panel = fit_panel_bytes(ncap);
-  const size_t st = ((sizeof(LbfgsbState) + 15) / 16) * 16;
+  const size_t st = fit_state_bytes();
   w.global_panels = (st + small + panel + 1024) > kSmemLimit;
   w.smem_fit = st + small + (w.global_panels ? 0 : panel);
   w.smem_fac = small + (w.global_panels ? 0 : panel);
@@ -586,15 +612,18 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
   a.p0 = d_p0; a.lo = d_lo; a.hi = d_hi; a.do_optimize = do_optimize;
   a.restart_theta = rt; a.restart_f = rf; a.restart_info = ri;
   a.panels = w.global_panels ? panels : nullptr; a.panel_stride = w.panel_stride;
-  if (d <= 12) {
-    rc = set_smem(gp_fit_kernel<12>, w.smem_fit);
-    if (rc) return rc;
-    gp_fit_kernel<12><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);
+#define TLBO_LAUNCH_FIT(DM, WO)                                              \
+  do {                                                                       \
+    rc = set_smem(gp_fit_kernel<DM, WO>, w.smem_fit);                        \
+    if (rc) return rc;                                                       \
+    gp_fit_kernel<DM, WO><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);         \
+  } while (0)
+  if (g_fit_variant != 0) {
+    if (d <= 12) TLBO_LAUNCH_FIT(12, true); else TLBO_LAUNCH_FIT(24, true);
   } else {
-    rc = set_smem(gp_fit_kernel<24>, w.smem_fit);
-    if (rc) return rc;
-    gp_fit_kernel<24><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);
+    if (d <= 12) TLBO_LAUNCH_FIT(12, false); else TLBO_LAUNCH_FIT(24, false);
   }
+#undef TLBO_LAUNCH_FIT
   TLBO_CUDA_CHECK(cudaGetLastError());
   return launch_factorize(d_X, d_y, d_n, B, R, ncap, d, sp, rt, rf, w_ymean, w_ystd, pack, slot0, nullptr,
                           nullptr, d_status, panels, w, s);

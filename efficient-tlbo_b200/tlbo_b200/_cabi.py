@@ -37,6 +37,7 @@ SYMBOLS = {
     'tlbo_gp_fit_batched': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, c_int,
                                     POINTER(TlboPack), c_int, _P, _P, _P, _P, _P, _P]),
     'tlbo_gp_fit_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int]),
+    'tlbo_set_fit_variant': (c_int, [c_int]),
     'tlbo_gp_factorize_batched': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, POINTER(TlboPack),
                                           c_int, _P, _P, _P, _P, _P]),
     'tlbo_gp_nll_grad_batched': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),

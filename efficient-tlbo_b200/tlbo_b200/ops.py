@@ -373,3 +373,9 @@ def fp64_peak_probe():
     out = (ctypes.c_double * 2)()
     check(lib.tlbo_fp64_peak_probe(ctypes.cast(out, ctypes.c_void_p), _stream()))
     return float(out[0]), float(out[1])
+
+
+def set_fit_variant(variant):
+    """``tlbo_set_fit_variant``: 1 = warp-cooperative L-BFGS-B (default), 0 = single-thread
+    statement of the same optimiser.  Returns the previous value."""
+    return int(lib.tlbo_set_fit_variant(int(variant)))

@@ -86,6 +86,11 @@ int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const int32_t* d_n
                         const tlbo_pack* pack, int slot0, double* d_restart_theta, double* d_restart_f,
                         int32_t* d_restart_info, int32_t* d_status, void* d_work, void* stream);
 int64_t tlbo_gp_fit_workspace_bytes(int B, int R, int ncap, int d);
+/* Selects the L-BFGS-B implementation used by tlbo_gp_fit_batched: 1 (default) = warp-cooperative
+ * (csrc/lbfgsb_warp.cuh), 0 = the single-thread statement of the same algorithm
+ * (csrc/lbfgsb_dense.cuh, the one cross-checked against scipy on the host).  Returns the
+ * previous value.  Both follow scipy.optimize.fmin_l_bfgs_b (reference gp.py:241-248).     */
+int tlbo_set_fit_variant(int variant);
 
 /* Factorise B surrogates at GIVEN theta (skopt GaussianProcessRegressor.fit with
  * optimizer=None: L = chol(K), alpha_ = K^-1 y, K_inv_ = L^-T L^-1) and fill pack slots.
