@@ -31,6 +31,7 @@ struct FitWs {
   double* alpha;   // [n]
   double* red;     // [8 * 32] reduction scratch
   double* hyp;     // [2 * TLBO_HMAX] per permuted column: l (cont) or 1/(2 l^2) (cat); then 1/l^3 (cat)
+  double* colbuf;  // [2 * 128] double-buffered pivot-column broadcast of the register-panel elimination
   int n, lda, d;
 };
 
@@ -38,7 +39,7 @@ __host__ __device__ inline int fit_lda(int n) { return (n & 1) ? n : n + 1; }
 
 __host__ inline size_t fit_small_bytes(int ncap, int d) {
   // Xr, Xs, y, piv, dinv, alpha, red, hyp
-  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 8);
+  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * 128 + 8);
 }
 __host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
 
@@ -54,6 +55,7 @@ __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* 
   S.alpha = p; p += ncap;
   S.red = p; p += 8 * 32;
   S.hyp = p; p += 2 * TLBO_HMAX;
+  S.colbuf = p; p += 2 * 128;
   S.A = panel_global ? panel_global : p;
 }
 
@@ -152,6 +154,316 @@ __device__ bool build_and_eliminate(const FitWs& S, const SpaceDesc& sp, const d
   return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// Register-resident variant of steps 1-2 for n + 1 <= 16 * T.  The (n+1) x n panel lives in
+// registers, 2-D cyclically distributed over the 16 x 16 thread grid (thread (ty, tx) owns
+// rows ty + 16a, columns tx + 16b); per elimination step only the pivot column crosses
+// shared memory (double-buffered, ONE __syncthreads per column).  Element-wise the
+// arithmetic is identical to build_and_eliminate.  ncu on the shared-memory version showed
+// ~1.8k cycles per column of exposed LDS latency in the per-thread row loop.
+// On success the shared panel holds, scaled: A[i][k] (i < k) = (L^-1)_ki, A[n][k] = (L^-1 y)_k
+// and -- scale_lower: A[i][k] (i >= k) = L_ik;  else: A[k][k] = 1/L_kk, A[i][k] (i > k) = 0
+// (so that row i of the panel is column i of L^-1, zero-padded: what nll_eval_reg contracts).
+template <int T>
+__device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                        bool scale_lower) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  double* A = S.A;
+  __syncthreads();
+  if (tid < d) {
+    const double l = exp(theta[1 + tid]);
+    if (tid < dc) { S.hyp[tid] = l; }
+    else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+  }
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  __syncthreads();
+  for (int idx = tid; idx < n * d; idx += NT) {
+    const int p = idx % d;
+    double v = S.Xr[idx];
+    if (p < dc) v = v / S.hyp[p];
+    S.Xs[idx] = v;
+  }
+  __syncthreads();
+  // kernel matrix (lower triangle, diagonal, y row) through shared memory: ONE copy of the
+  // exp / sqrt code, then every thread picks up its register tile
+  for (int idx = tid; idx < (n + 1) * n; idx += NT) {
+    const int i = idx / n, j = idx - i * n;
+    if (i < j) continue;
+    double v;
+    if (i == n) v = S.y[j];
+    else if (i == j) v = c + noise;
+    else {
+      const double* xi = S.Xs + (size_t)i * d;
+      const double* xj = S.Xs + (size_t)j * d;
+      double s = 0.0, hs = 0.0;
+      for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+      for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+      v = matern_hamming(c, s, hs);
+    }
+    A[(size_t)i * lda + j] = v;
+  }
+  __syncthreads();
+  double a[T][T];
+#pragma unroll
+  for (int ia = 0; ia < T; ia++) {
+    const int i = ty + 16 * ia;
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+      const int j = tx + 16 * jb;
+      a[ia][jb] = (i <= n && j < n && i >= j) ? A[(size_t)i * lda + j] : 0.0;
+    }
+  }
+  // Tile (ia, jb) holds lower-part elements (i >= j, incl. the y row) when ia > jb, upper-part
+  // (inverse) elements when ia < jb; on diagonal tiles the class is fixed per thread.  All
+  // k-dependent masking is folded into the multipliers (f = 0 for inactive columns, ck_up = 0
+  // for not-yet-active inverse rows), so the tile update is T*T unpredicated FMAs.
+  const bool diag_lower = ty >= tx;
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    double* buf = S.colbuf + (k & 1) * 128;
+    const int kb = k >> 4;
+    if (tx == (k & 15)) {
+#pragma unroll
+      for (int jb = 0; jb < T; jb++)
+        if (jb == kb) {
+#pragma unroll
+          for (int ia = 0; ia < T; ia++) buf[ty + 16 * ia] = a[ia][jb];
+        }
+    }
+    __syncthreads();
+    const double piv = buf[k];
+    if (!(piv > 0.0)) { ok = false; break; }
+    const double ip = 1.0 / piv;
+    if (tid == 0) S.piv[k] = piv;
+    double ck_lo[T], ck_up[T];
+#pragma unroll
+    for (int ia = 0; ia < T; ia++) {
+      const int i = ty + 16 * ia;
+      ck_lo[ia] = buf[i];
+      ck_up[ia] = (i < k) ? ck_lo[ia] : ((i == k) ? 1.0 : 0.0);
+    }
+    const int jb0 = (k + 1) >> 4;      // column blocks below hold only j <= k
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+      if (jb >= jb0) {
+        const int j = tx + 16 * jb;
+        const double f = (j > k && j < n) ? buf[j] * ip : 0.0;
+#pragma unroll
+        for (int ia = 0; ia < T; ia++) {
+          const double ck = (ia > jb) ? ck_lo[ia] : ((ia < jb) ? ck_up[ia] : (diag_lower ? ck_lo[ia] : ck_up[ia]));
+          a[ia][jb] -= ck * f;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!ok) return false;
+  for (int k = tid; k < n; k += NT) S.dinv[k] = 1.0 / sqrt(S.piv[k]);
+  __syncthreads();
+#pragma unroll
+  for (int jb = 0; jb < T; jb++) {
+    const int k = tx + 16 * jb;
+    if (k < n) {
+      const double dk = S.dinv[k];
+#pragma unroll
+      for (int ia = 0; ia < T; ia++) {
+        const int i = ty + 16 * ia;
+        if (i <= n) {
+          double v;
+          if (i < k || i == n) v = a[ia][jb] * dk;
+          else if (scale_lower) v = (i == k) ? sqrt(S.piv[k]) : a[ia][jb] * dk;
+          else v = (i == k) ? dk : 0.0;
+          A[(size_t)i * lda + k] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // alpha_i = sum_{k>=i} (L^-1)_ki z_k
+  for (int i = tid; i < n; i += NT) {
+    const double* ri = A + (size_t)i * lda;
+    const double* z = A + (size_t)n * lda;
+    double al = S.dinv[i] * z[i];
+    for (int k = i + 1; k < n; k++) al += ri[k] * z[k];
+    S.alpha[i] = al;
+  }
+  __syncthreads();
+  return true;
+}
+
+// log-priors of GaussianProcess._nll and the final sign / finiteness rules (thread 0).
+__device__ __forceinline__ void nll_finish(const double* theta, int H, int n, double nll_data, double* out) {
+  double lml = -nll_data - 0.5 * (double)n * LOG_2PI;
+  // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
+  const double v0 = exp(theta[0]);
+  double lp0, gp0;
+  if (v0 <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
+  else {
+    const double lv = log(v0);
+    lp0 = -(lv * lv) / 2.0 - log(2.5066282746310002 * v0);
+    gp0 = -(1.0 + lv) / v0 * v0;
+  }
+  // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
+  const double vn = exp(theta[H - 1]);
+  const double s2 = 0.1 * 0.1;
+  double lpn, gpn;
+  if (vn == 0.0) { lpn = INFINITY; gpn = INFINITY; }
+  else {
+    const double a = log(1.0 + 3.0 * (s2 / (vn * vn)));
+    lpn = log(a + VERY_SMALL_NUMBER);
+    double b = 3.0 * s2 + vn * vn;
+    b *= log(3.0 * s2 * (1.0 / (vn * vn)) + 1.0);
+    b = fmax(b, 1e-14);
+    gpn = -(6.0 * s2) / b;
+  }
+  lml += lp0 + lpn;
+  out[1] += gp0;
+  out[H] += gpn;
+  bool fin = isfinite(lml);
+  for (int h = 0; h < H; h++) fin = fin && isfinite(out[1 + h]);
+  if (!fin) {
+    out[0] = 1e25;
+    for (int h = 0; h < H; h++) out[1 + h] = 0.0;
+  } else {
+    out[0] = -lml;
+    for (int h = 0; h < H; h++) out[1 + h] = -out[1 + h];
+  }
+}
+
+// nll_eval on the register-panel path: the gradient contraction uses the same 2-D cyclic
+// tiling -- K^-1_ij = sum_k U[i][k] U[j][k] over the zero-padded rows of the panel, T x T
+// outer products per k (2T shared loads per T^2 FMAs instead of 2 per FMA).
+template <int T, int DMAX>
+__device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool ok = build_and_eliminate_reg<T>(S, sp, theta, false);
+  if (!ok) {
+    if (tid == 0) out[0] = 1e25;
+    if (tid < H) out[1 + tid] = 0.0;
+    __syncthreads();
+    return false;
+  }
+  const double* A = S.A;
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  double part = 0.0;
+  for (int k = tid; k < n; k += NT) {
+    const double z = A[(size_t)n * lda + k];
+    part += 0.5 * z * z + 0.5 * log(S.piv[k]);
+  }
+  const double nll_data = block_sum(part, S.red);
+
+  double kin[T][T];
+#pragma unroll
+  for (int ia = 0; ia < T; ia++)
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) kin[ia][jb] = 0.0;
+  // only tiles with i > j (or the diagonal) matter; rows of U are zero left of the diagonal,
+  // so the sum may start at the thread's smallest row index
+  {
+    const double* ui_p[T];
+    const double* uj_p[T];
+#pragma unroll
+    for (int q = 0; q < T; q++) {
+      const int i = ty + 16 * q, j = tx + 16 * q;
+      ui_p[q] = A + (size_t)(i < n ? i : 0) * lda;
+      uj_p[q] = A + (size_t)(j < n ? j : 0) * lda;
+    }
+    for (int k = ty; k < n; k++) {
+      double ui[T], uj[T];
+#pragma unroll
+      for (int q = 0; q < T; q++) {
+        ui[q] = (ty + 16 * q < n) ? ui_p[q][k] : 0.0;
+        uj[q] = (tx + 16 * q < n) ? uj_p[q][k] : 0.0;
+      }
+#pragma unroll
+      for (int ia = 0; ia < T; ia++)
+#pragma unroll
+        for (int jb = 0; jb < T; jb++) kin[ia][jb] += ui[ia] * uj[jb];
+    }
+  }
+  // publish W = alpha alpha^T - K^-1 (strict lower part into the panel, diagonal into piv[]:
+  // both are dead by now) and contract it with dK/dtheta in ONE linear pair loop
+  __syncthreads();
+  {
+    double* Aw = S.A;
+#pragma unroll
+    for (int ia = 0; ia < T; ia++) {
+      const int i = ty + 16 * ia;
+#pragma unroll
+      for (int jb = 0; jb < T; jb++) {
+        const int j = tx + 16 * jb;
+        if (i < n && j < i) Aw[(size_t)i * lda + j] = S.alpha[i] * S.alpha[j] - kin[ia][jb];
+        else if (i < n && j == i) S.piv[i] = S.alpha[i] * S.alpha[i] - kin[ia][jb];
+      }
+    }
+  }
+  __syncthreads();
+  double g0 = 0.0, gn = 0.0;
+  double gacc[DMAX];
+#pragma unroll
+  for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
+  const int npairs = n * (n - 1) / 2;
+  for (int q = tid; q < npairs; q += NT) {
+    int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+    while (i * (i - 1) / 2 > q) i--;
+    while ((i + 1) * i / 2 <= q) i++;
+    const int j = q - i * (i - 1) / 2;   // j < i
+    const double W = A[(size_t)i * lda + j];
+    const double* xi = S.Xs + (size_t)i * d;
+    const double* xj = S.Xs + (size_t)j * d;
+    double s = 0.0, hs = 0.0;
+    for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+    for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+    const double t = sqrt(s) * SQRT5;
+    const double e = exp(-t), eh = exp(-hs);
+    const double Kc = c * ((1.0 + t + t * t / 3.0) * e) * eh;
+    const double WK = W * Kc;
+    g0 += WK;
+    const double coef = W * c * eh * (5.0 / 3.0) * (t + 1.0) * e;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < dc) { const double df = xi[p] - xj[p]; gacc[p] += coef * (df * df); }
+      else if (p < d) { if (xi[p] != xj[p]) gacc[p] += WK * S.hyp[TLBO_HMAX + p]; }
+    }
+  }
+  for (int i = tid; i < n; i += NT) {
+    const double W = S.piv[i];
+    g0 += 0.5 * W * c;
+    gn += 0.5 * W * noise;
+  }
+  const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
+  __syncthreads();
+  {
+    double v = warp_sum(g0);
+    if (lane == 0) S.red[wid * 32 + 0] = v;
+    v = warp_sum(gn);
+    if (lane == 0) S.red[wid * 32 + (d + 1)] = v;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < d) {
+        v = warp_sum(gacc[p]);
+        if (lane == 0) S.red[wid * 32 + 1 + p] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < H) {
+    double v = 0.0;
+    for (int w = 0; w < nw; w++) v += S.red[w * 32 + tid];
+    out[1 + tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) nll_finish(theta, H, n, nll_data, out);
+  __syncthreads();
+  return true;
+}
+
 // One evaluation of GaussianProcess._nll (gp.py:164-197).  Result: out[0] = f, out[1..H] = g
 // (shared memory), visible to all threads on return.  Returns Cholesky success.
 template <int DMAX>
@@ -241,45 +553,28 @@ __device__ bool nll_eval(const FitWs& S, const SpaceDesc& sp, const double* thet
     out[1 + tid] = v;       // d LML / d theta_h (without priors)
   }
   __syncthreads();
-  if (tid == 0) {
-    double lml = -nll_data - 0.5 * (double)n * LOG_2PI;
-    // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
-    const double v0 = exp(theta[0]);
-    double lp0, gp0;
-    if (v0 <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
-    else {
-      const double lv = log(v0);
-      lp0 = -(lv * lv) / 2.0 - log(2.5066282746310002 * v0);
-      gp0 = -(1.0 + lv) / v0 * v0;
-    }
-    // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
-    const double vn = exp(theta[H - 1]);
-    const double s2 = 0.1 * 0.1;
-    double lpn, gpn;
-    if (vn == 0.0) { lpn = INFINITY; gpn = INFINITY; }
-    else {
-      const double a = log(1.0 + 3.0 * (s2 / (vn * vn)));
-      lpn = log(a + VERY_SMALL_NUMBER);
-      double b = 3.0 * s2 + vn * vn;
-      b *= log(3.0 * s2 * (1.0 / (vn * vn)) + 1.0);
-      b = fmax(b, 1e-14);
-      gpn = -(6.0 * s2) / b;
-    }
-    lml += lp0 + lpn;
-    out[1] += gp0;
-    out[H] += gpn;
-    bool fin = isfinite(lml);
-    for (int h = 0; h < H; h++) fin = fin && isfinite(out[1 + h]);
-    if (!fin) {
-      out[0] = 1e25;
-      for (int h = 0; h < H; h++) out[1 + h] = 0.0;
-    } else {
-      out[0] = -lml;
-      for (int h = 0; h < H; h++) out[1 + h] = -out[1 + h];
-    }
-  }
+  if (tid == 0) nll_finish(theta, H, n, nll_data, out);
   __syncthreads();
   return true;
+}
+
+// T = 0: shared-memory panel (any n that fits); T > 0: register panel, n + 1 <= 16 T.
+template <int T>
+__device__ __forceinline__ bool build_and_eliminate_any(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                                        bool scale_lower) {
+  if constexpr (T == 0) return build_and_eliminate(S, sp, theta, scale_lower);
+  else return build_and_eliminate_reg<T>(S, sp, theta, scale_lower);
+}
+template <int T, int DMAX>
+__device__ __forceinline__ bool nll_eval_any(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
+  if constexpr (T == 0) return nll_eval<DMAX>(S, sp, theta, out);
+  else return nll_eval_reg<T, DMAX>(S, sp, theta, out);
+}
+__host__ inline int panel_tile_for(int ncap) {
+  if (ncap + 1 <= 64) return 4;
+  if (ncap + 1 <= 80) return 5;
+  if (ncap + 1 <= 128) return 8;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -302,7 +597,7 @@ __host__ __device__ inline size_t fit_state_bytes() {
 
 // WARP_OPT = true: warp-cooperative optimiser (lbfgsb_warp.cuh, default);
 //            false: single-thread reference statement of the same optimiser (lbfgsb_dense.cuh).
-template <int DMAX, bool WARP_OPT>
+template <int DMAX, bool WARP_OPT, int T>
 __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x / a.R, r = blockIdx.x - b * a.R;
@@ -324,7 +619,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
     // gp.py:127-140: the initial GaussianProcessRegressor.fit at the default theta retries
     // with noise += 1 on LinAlgError; the bumped theta then becomes start point 0.
     for (int tries = 0; tries < 10; tries++) {
-      if (build_and_eliminate(S, a.sp, th, false)) break;
+      if (build_and_eliminate_any<T>(S, a.sp, th, false)) break;
       if (tid == 0) th[H - 1] = log(exp(th[H - 1]) + 1.0);
       bumps++;
       __syncthreads();
@@ -332,7 +627,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   }
   int nfev = 0;
   if (!a.do_optimize) {
-    nll_eval<DMAX>(S, a.sp, th, fg);
+    nll_eval_any<T, DMAX>(S, a.sp, th, fg);
     nfev = 1;
     if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = th[tid];
     if (tid == 0) {
@@ -348,7 +643,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   for (;;) {
     if (tid < H) th[tid] = WARP_OPT ? sw->x[tid] : st->x[tid];
     __syncthreads();
-    nll_eval<DMAX>(S, a.sp, th, fg);
+    nll_eval_any<T, DMAX>(S, a.sp, th, fg);
     nfev++;
     if (WARP_OPT) {
       if (wid == 0) {
@@ -482,7 +777,7 @@ struct NllArgs {
   double* panels; size_t panel_stride;
 };
 
-template <int DMAX>
+template <int DMAX, int T>
 __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x;
@@ -495,7 +790,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) 
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.theta[(size_t)b * H + tid];
   __syncthreads();
-  const bool ok = nll_eval<DMAX>(S, a.sp, th, fg);
+  const bool ok = nll_eval_any<T, DMAX>(S, a.sp, th, fg);
   if (tid == 0) { a.nll[b] = fg[0]; a.status[b] = ok ? 0 : 1; }
   if (tid < H) a.grad[(size_t)b * H + tid] = fg[1 + tid];
 }
@@ -612,17 +907,28 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
   a.p0 = d_p0; a.lo = d_lo; a.hi = d_hi; a.do_optimize = do_optimize;
   a.restart_theta = rt; a.restart_f = rf; a.restart_info = ri;
   a.panels = w.global_panels ? panels : nullptr; a.panel_stride = w.panel_stride;
-#define TLBO_LAUNCH_FIT(DM, WO)                                              \
+#define TLBO_LAUNCH_FIT(DM, WO, TT)                                          \
   do {                                                                       \
-    rc = set_smem(gp_fit_kernel<DM, WO>, w.smem_fit);                        \
+    rc = set_smem(gp_fit_kernel<DM, WO, TT>, w.smem_fit);                    \
     if (rc) return rc;                                                       \
-    gp_fit_kernel<DM, WO><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);         \
+    gp_fit_kernel<DM, WO, TT><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);     \
   } while (0)
+#define TLBO_LAUNCH_FIT_T(DM)                                                \
+  do {                                                                       \
+    switch (tile) {                                                          \
+      case 4: TLBO_LAUNCH_FIT(DM, true, 4); break;                           \
+      case 5: TLBO_LAUNCH_FIT(DM, true, 5); break;                           \
+      case 8: TLBO_LAUNCH_FIT(DM, true, 8); break;                           \
+      default: TLBO_LAUNCH_FIT(DM, true, 0); break;                          \
+    }                                                                        \
+  } while (0)
+  const int tile = (g_fit_variant != 0 && !w.global_panels) ? panel_tile_for(ncap) : 0;
   if (g_fit_variant != 0) {
-    if (d <= 12) TLBO_LAUNCH_FIT(12, true); else TLBO_LAUNCH_FIT(24, true);
+    if (d <= 12) TLBO_LAUNCH_FIT_T(12); else TLBO_LAUNCH_FIT_T(24);
   } else {
-    if (d <= 12) TLBO_LAUNCH_FIT(12, false); else TLBO_LAUNCH_FIT(24, false);
+    if (d <= 12) TLBO_LAUNCH_FIT(12, false, 0); else TLBO_LAUNCH_FIT(24, false, 0);
   }
+#undef TLBO_LAUNCH_FIT_T
 #undef TLBO_LAUNCH_FIT
   TLBO_CUDA_CHECK(cudaGetLastError());
   return launch_factorize(d_X, d_y, d_n, B, R, ncap, d, sp, rt, rf, w_ymean, w_ystd, pack, slot0, nullptr,
@@ -669,15 +975,25 @@ extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, co
   a.theta = d_theta; a.nll = d_nll; a.grad = d_grad; a.status = d_status;
   a.panels = w.global_panels ? (double*)d_work : nullptr; a.panel_stride = w.panel_stride;
   if (w.global_panels && !d_work) { tlbo_set_error("workspace required for this ncap"); return TLBO_E_BADARG; }
-  if (d <= 12) {
-    rc = set_smem(gp_nll_grad_kernel<12>, w.smem_fac);
-    if (rc) return rc;
-    gp_nll_grad_kernel<12><<<B, FIT_THREADS, w.smem_fac, s>>>(a);
-  } else {
-    rc = set_smem(gp_nll_grad_kernel<24>, w.smem_fac);
-    if (rc) return rc;
-    gp_nll_grad_kernel<24><<<B, FIT_THREADS, w.smem_fac, s>>>(a);
-  }
+#define TLBO_LAUNCH_NLL(DM, TT)                                              \
+  do {                                                                       \
+    rc = set_smem(gp_nll_grad_kernel<DM, TT>, w.smem_fac);                   \
+    if (rc) return rc;                                                       \
+    gp_nll_grad_kernel<DM, TT><<<B, FIT_THREADS, w.smem_fac, s>>>(a);        \
+  } while (0)
+#define TLBO_LAUNCH_NLL_T(DM)                                                \
+  do {                                                                       \
+    switch (tile) {                                                          \
+      case 4: TLBO_LAUNCH_NLL(DM, 4); break;                                 \
+      case 5: TLBO_LAUNCH_NLL(DM, 5); break;                                 \
+      case 8: TLBO_LAUNCH_NLL(DM, 8); break;                                 \
+      default: TLBO_LAUNCH_NLL(DM, 0); break;                                \
+    }                                                                        \
+  } while (0)
+  const int tile = (g_fit_variant != 0 && !w.global_panels) ? panel_tile_for(ncap) : 0;
+  if (d <= 12) TLBO_LAUNCH_NLL_T(12); else TLBO_LAUNCH_NLL_T(24);
+#undef TLBO_LAUNCH_NLL_T
+#undef TLBO_LAUNCH_NLL
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

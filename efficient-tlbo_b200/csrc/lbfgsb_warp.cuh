@@ -82,24 +82,39 @@ __device__ __forceinline__ double projgr(const LbwState& s, int lane) {
   return wmax(v);
 }
 
+// Column `lane` of B stays in registers across the col rank-2 updates (no shared-memory
+// round trip per pair); written back once.
 __device__ void rebuild_B(LbwState& s, int lane) {
   const int n = s.n;
-  if (lane < n)
-    for (int j = 0; j < n; j++) s.B[j][lane] = (j == lane) ? s.theta : 0.0;
-  __syncwarp();
+  const bool act = lane < n;
+  double Bc[LB_NMAX];
+#pragma unroll
+  for (int j = 0; j < LB_NMAX; j++) Bc[j] = (j == lane) ? s.theta : 0.0;
   for (int k = 0; k < s.col; k++) {
     const double* sk = s.S[k];
     const double* yk = s.Y[k];
-    const double a = matvec_row(s, sk, lane);           // (B s_k)_lane
-    const double skl = lane < n ? sk[lane] : 0.0, ykl = lane < n ? yk[lane] : 0.0;
+    double a = 0.0;                                       // (B s_k)_lane
+#pragma unroll
+    for (int j = 0; j < LB_NMAX; j++)
+      if (j < n) a += Bc[j] * sk[j];
+    if (!act) a = 0.0;
+    const double skl = act ? sk[lane] : 0.0, ykl = act ? yk[lane] : 0.0;
     const double sBs = wsum(skl * a), ys = wsum(ykl * skl);
-    if (lane < n) s.rr[lane] = a;                        // Bs, shared with the other lanes
+    __syncwarp();
+    if (act) s.rr[lane] = a;                              // Bs, shared with the other lanes
     __syncwarp();
     const double i1 = 1.0 / sBs, i2 = 1.0 / ys;
-    if (lane < n)
-      for (int j = 0; j < n; j++) s.B[j][lane] += yk[j] * ykl * i2 - s.rr[j] * a * i1;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < LB_NMAX; j++)
+      if (j < n) Bc[j] += yk[j] * ykl * i2 - s.rr[j] * a * i1;
   }
+  __syncwarp();
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < LB_NMAX; j++)
+      if (j < n) s.B[j][lane] = Bc[j];
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void reset_memory(LbwState& s, int lane) {
@@ -208,7 +223,7 @@ __device__ bool solve_free(LbwState& s, int nsub, int lane) {
     const double pk = __shfl_sync(0xffffffffu, v, k);
     if (!(pk > 0.0)) { ok = false; break; }
     const double p = sqrt(pk);
-    if (act && lane == k) s.Wk[k][k] = p;
+    if (act && lane == k) { s.Wk[k][k] = p; s.xp[k] = 1.0 / p; }
     else if (act && lane > k) s.Wk[lane][k] = v / p;
     __syncwarp();
   }
@@ -217,7 +232,7 @@ __device__ bool solve_free(LbwState& s, int nsub, int lane) {
   double v = act ? s.rr[lane] : 0.0;
   for (int q = 0; q < nsub; q++) {
     double o = 0.0;
-    if (lane == q) o = v / s.Wk[q][q];
+    if (lane == q) o = v * s.xp[q];
     o = __shfl_sync(0xffffffffu, o, q);
     if (lane == q) v = o;
     else if (act && lane > q) v -= s.Wk[lane][q] * o;
@@ -225,7 +240,7 @@ __device__ bool solve_free(LbwState& s, int nsub, int lane) {
   // back substitution with L^T
   for (int i = nsub - 1; i >= 0; i--) {
     double o = 0.0;
-    if (lane == i) o = v / s.Wk[i][i];
+    if (lane == i) o = v * s.xp[i];
     o = __shfl_sync(0xffffffffu, o, i);
     if (lane == i) v = o;
     else if (act && lane < i) v -= s.Wk[i][lane] * o;
