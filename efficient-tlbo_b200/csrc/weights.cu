@@ -16,6 +16,9 @@ __global__ void __launch_bounds__(RL_THREADS) rank_loss_kernel(const double* __r
                                                                const double* __restrict__ ys, int n, int Mr,
                                                                const int32_t* __restrict__ row_lo,
                                                                const int32_t* __restrict__ row_hi, int upper_only,
+                                                               const double* __restrict__ loc,
+                                                               const double* __restrict__ scale,
+                                                               const int32_t* __restrict__ src,
                                                                long long* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* sy = reinterpret_cast<double*>(smem);
@@ -23,8 +26,19 @@ __global__ void __launch_bounds__(RL_THREADS) rank_loss_kernel(const double* __r
   __shared__ unsigned long long total;
   const int item = blockIdx.x;           // s * Mr + m
   const int m = item % Mr;
-  const double* src = ys + (size_t)item * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { sy[i] = y[i]; ss[i] = src[i]; }
+  const double* zs = ys + (size_t)item * n;
+  if (loc) {
+    // ys holds standard-normal draws z: sample = loc + scale * z with a rounded product and a
+    // rounded sum -- the arithmetic of numpy's legacy normal(loc, scale) (no FMA contraction)
+    const double* lo_ = loc + (size_t)src[m] * n;
+    const double* sc_ = scale + (size_t)src[m] * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      sy[i] = y[i];
+      ss[i] = __dadd_rn(lo_[i], __dmul_rn(sc_[i], zs[i]));
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { sy[i] = y[i]; ss[i] = zs[i]; }
+  }
   if (threadIdx.x == 0) total = 0ull;
   __syncthreads();
   const int lo = row_lo[m], hi = row_hi[m];
@@ -46,18 +60,34 @@ __global__ void __launch_bounds__(RL_THREADS) rank_loss_kernel(const double* __r
   if (threadIdx.x == 0) counts[item] = (long long)total;
 }
 
-extern "C" int tlbo_rank_loss_counts(const double* d_y, const double* d_ys, int n, int S, int Mr,
-                                     const int32_t* d_row_lo, const int32_t* d_row_hi, int upper_only,
-                                     int64_t* d_counts, void* stream) {
+static int rank_loss_launch(const double* d_y, const double* d_ys, int n, int S, int Mr, const int32_t* d_row_lo,
+                            const int32_t* d_row_hi, int upper_only, const double* d_loc, const double* d_scale,
+                            const int32_t* d_src, int64_t* d_counts, void* stream) {
   if (n <= 0 || S <= 0 || Mr <= 0) { tlbo_set_error("bad n/S/Mr"); return TLBO_E_BADARG; }
   const size_t smem = 2 * (size_t)n * sizeof(double);
   if (smem > 200 * 1024) { tlbo_set_error("n too large for rank_loss_counts"); return TLBO_E_TOOLARGE; }
   if (smem > 48 * 1024)
     TLBO_CUDA_CHECK(cudaFuncSetAttribute(rank_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rank_loss_kernel<<<S * Mr, RL_THREADS, smem, (cudaStream_t)stream>>>(d_y, d_ys, n, Mr, d_row_lo, d_row_hi,
-                                                                        upper_only, (long long*)d_counts);
+                                                                        upper_only, d_loc, d_scale, d_src,
+                                                                        (long long*)d_counts);
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int tlbo_rank_loss_counts(const double* d_y, const double* d_ys, int n, int S, int Mr,
+                                     const int32_t* d_row_lo, const int32_t* d_row_hi, int upper_only,
+                                     int64_t* d_counts, void* stream) {
+  return rank_loss_launch(d_y, d_ys, n, S, Mr, d_row_lo, d_row_hi, upper_only, nullptr, nullptr, nullptr, d_counts,
+                          stream);
+}
+
+extern "C" int tlbo_rank_loss_counts_normal(const double* d_y, const double* d_z, const double* d_loc,
+                                            const double* d_scale, const int32_t* d_src, int n, int S, int Mr,
+                                            const int32_t* d_row_lo, const int32_t* d_row_hi, int64_t* d_counts,
+                                            void* stream) {
+  if (!d_loc || !d_scale || !d_src) { tlbo_set_error("NULL loc/scale/src"); return TLBO_E_BADARG; }
+  return rank_loss_launch(d_y, d_z, n, S, Mr, d_row_lo, d_row_hi, 0, d_loc, d_scale, d_src, d_counts, stream);
 }
 
 // ---------------------------------------------------------------------------------------

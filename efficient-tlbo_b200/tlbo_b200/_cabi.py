@@ -46,6 +46,7 @@ SYMBOLS = {
                                       c_double, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
     'tlbo_predict_ei_workspace_bytes': (c_int64, [c_int64]),
     'tlbo_rank_loss_counts': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
+    'tlbo_rank_loss_counts_normal': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     'tlbo_pairwise_logistic_loss_grad': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     'tlbo_fp64_peak_probe': (c_int, [_P, _P]),
 }

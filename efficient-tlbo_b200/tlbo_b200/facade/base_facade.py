@@ -12,7 +12,7 @@ import abc
 import numpy as np
 
 from tlbo_b200.config_space import convert_configurations_to_array, get_types
-from tlbo_b200.model.gp import fit_models
+from tlbo_b200.model.gp import fit_models, fit_models_async
 from tlbo_b200.model.model_builder import build_model
 from tlbo_b200.utils.constants import VERY_SMALL_NUMBER
 from tlbo_b200.utils.normalization import zero_mean_unit_var_normalization, zero_one_normalization
@@ -60,6 +60,9 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self._cap_hint = max_target_rows
         # accumulation order of the fused ensemble predict (pack slot ids) and TST mode flag
         self._fused_mode = 0
+        self._stage = None            # pinned staging buffers (created with the pack)
+        self._overlap_hook = None     # host callback run while the batched fit is in flight
+        self._p0_cache = None         # restart start points shared by every model of this facade
 
     # ---- device pack ------------------------------------------------------------------
     def _ensure_pack(self, rows):
@@ -70,6 +73,8 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         cap = ops.round_up(max(need, self._cap_hint), 8)
         if self._pack is not None:
             cap = max(cap, ops.round_up(int(self._pack.ncap * 1.5), 8))
+        if self._stage is None:
+            self._stage = ops.PinnedStage()
         new = ops.SurrogatePack(self.K + 1 + N_CV_SLOTS, cap, len(self.types))
         if self._pack is not None:
             for s in range(self._pack.M):
@@ -110,12 +115,21 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             else:
                 raise ValueError('Invalid parameter in norm.')
             self.eta_list.append(np.min(y))
+            self._share_start_points(model)
             model.bind(pack, k)
             Xs.append(X)
             ys.append(y)
             self.source_surrogates.append(model)
         if self.K:
             fit_models(self.source_surrogates, Xs, ys)
+
+    def _share_start_points(self, model):
+        """Every model of a facade is built from a fresh ``RandomState(self.random_seed)``
+        (base_facade.py:64-65,95), so the 10 sampled L-BFGS-B start points are identical:
+        draw them once and share the array (also lets the batched fit see one ``p0``)."""
+        if self._p0_cache is None:
+            self._p0_cache = model._start_points()
+        model._p0_override = self._p0_cache
 
     def _prepare_single_surrogate(self, X, y, normalize, slot):
         """The host half of ``build_single_surrogate`` (base_facade.py:93-108): build the
@@ -131,12 +145,16 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             if (y == y[0]).all():
                 y[0] += 1e-4
             y, _, _ = zero_one_normalization(y)
+        self._share_start_points(model)
         model.bind(self._ensure_pack(X.shape[0]), slot)
         return model, X, y
 
     def build_single_surrogate(self, X, y, normalize, slot=None):
         job = self._prepare_single_surrogate(X, y, normalize, self.K if slot is None else slot)
-        fit_models([job[0]], [job[1]], [job[2]])
+        finish = fit_models_async([job[0]], [job[1]], [job[2]])
+        if self._overlap_hook is not None:
+            self._overlap_hook()
+        finish()
         return job[0]
 
     # ---- prediction -----------------------------------------------------------------------

@@ -9,7 +9,7 @@ mis-ranked-pair counts come from the integer pair-count kernel (bit-exact)."""
 import numpy as np
 
 from tlbo_b200.facade.base_facade import BaseFacade, N_CV_SLOTS
-from tlbo_b200.model.gp import fit_models
+from tlbo_b200.model.gp import fit_models_async
 
 
 class _BootstrapRankingFacade(BaseFacade):
@@ -51,18 +51,10 @@ class _BootstrapRankingFacade(BaseFacade):
         # a pack regrow inside _prepare_single_surrogate rebinds nothing for fresh models: rebind all
         for j, job in enumerate(jobs):
             job[0].bind(self._pack, K + j)
-        fit_models([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
-        self.target_surrogate = jobs[0][0]
-
-        # K source predicts + fold predicts at the target points: one launch
-        mu, var = self._source_predictions(X, n_extra=n_folds)
-        rows = list(range(K)) + list(range(K + 1, K + 1 + n_folds))
-        loc, scale = mu[rows], var[rows]                     # [K + n_folds, n]; scale = VARIANCE (rgpe.py:77)
-
-        # draws: sample-major, then source 0..K-1, then fold 0..4, n normals each -- the
-        # order in which the reference's loops consume the global stream
+        # inputs of the post-fit kernels go up BEFORE the fit is enqueued (pageable copies
+        # would otherwise wait for it)
         S = self.num_sample
-        ys = np.random.normal(np.broadcast_to(loc, (S,) + loc.shape), np.broadcast_to(scale, (S,) + scale.shape))
+        rows = list(range(K)) + list(range(K + 1, K + 1 + n_folds))
         row_lo = [0] * K
         row_hi = [instance_num] * K
         if n_folds:
@@ -70,7 +62,30 @@ class _BootstrapRankingFacade(BaseFacade):
             for fold in range(self.k_fold_num):
                 row_lo.append(fold_num * fold)
                 row_hi.append(instance_num if fold == self.k_fold_num - 1 else (fold + 1) * fold_num)
-        counts = ops.rank_loss_counts(np.asarray(y, dtype=np.float64), ys, row_lo, row_hi)
+        X_dev = self._to_device(X)
+        y_dev = ops.h2d(np.asarray(y, dtype=np.float64))
+        src_dev = ops.h2d(np.asarray(rows, dtype=np.int32))
+        lo_dev = ops.h2d(np.asarray(row_lo, dtype=np.int32))
+        hi_dev = ops.h2d(np.asarray(row_hi, dtype=np.int32))
+        finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+        self.target_surrogate = jobs[0][0]
+
+        # ---- host work overlapped with the device fit
+        # bootstrap draws: sample-major, then source 0..K-1, then fold 0..4, n normals each --
+        # the order in which the reference's loops consume the GLOBAL legacy stream.
+        # np.random.normal(loc, scale) == loc + scale * standard_normal() draw for draw, so
+        # the draws are taken now and the affine map runs on the device (rank-loss kernel).
+        z = np.random.standard_normal((S, len(rows), instance_num))
+        z_dev = self._stage.upload('z', z)
+        if self._overlap_hook is not None:
+            self._overlap_hook()
+
+        # K source predicts + fold predicts at the target points (one launch), pair counts
+        view = ops.pack_view(self._pack, 0, K + 1 + n_folds)
+        mu_dev, var_dev = ops.gp_predict(view, self.types, X_dev)
+        counts_dev = ops.rank_loss_counts_normal(y_dev, z_dev, mu_dev, var_dev, src_dev, lo_dev, hi_dev, sync=False)
+        finish_fit()                                   # first synchronisation of the iteration
+        counts = ops.d2h(counts_dev)
         losses = np.empty((S, K + 1), dtype=np.int64)
         losses[:, :K] = counts[:, :K]
         losses[:, K] = counts[:, K:].sum(axis=1) if n_folds else instance_num * instance_num

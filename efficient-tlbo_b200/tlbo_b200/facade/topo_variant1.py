@@ -4,7 +4,7 @@ pairwise logistic ranking loss (sources, then sources + cross-validated target).
 import numpy as np
 
 from tlbo_b200.facade.base_facade import BaseFacade
-from tlbo_b200.model.gp import fit_models
+from tlbo_b200.model.gp import fit_models_async
 from tlbo_b200.utils.scipy_solver import scipy_solve
 
 _scale_method = 'standardize'
@@ -54,11 +54,17 @@ class OBTLV(BaseFacade):
             jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
         for j, job in enumerate(jobs):
             job[0].bind(self._pack, K + j)
-        fit_models([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+        from tlbo_b200 import ops
+        X_dev = self._to_device(X)                       # before the fit is enqueued
+        finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
         self.target_surrogate = jobs[0][0]
         self.target_y_range = 0.5 * (np.max(y) - np.min(y))
-
-        mu, _ = self._source_predictions(X, n_extra=len(folds))
+        if self._overlap_hook is not None:
+            self._overlap_hook()                         # host work overlapped with the device fit
+        view = ops.pack_view(self._pack, 0, K + 1 + len(folds))
+        mu_dev, _ = ops.gp_predict(view, self.types, X_dev)
+        finish_fit()
+        mu = ops.d2h(mu_dev)
         pred_y = np.ascontiguousarray(mu[:K].T)
 
         self.learn_source_weights(pred_y, y)

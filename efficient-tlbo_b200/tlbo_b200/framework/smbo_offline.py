@@ -155,7 +155,13 @@ class SMBO_OFFLINE(object):
                 self.model.target_weight.append(self.model.target_weight[-1])
             return row
 
-        self.model.train(X, Y)
+        # tie-break keys / evaluated-row list are staged while the facade's fit kernel runs
+        evaluated = self.configurations + self.failed_configurations
+        self.model._overlap_hook = lambda: self.acq_optimizer.prepare(evaluated)
+        try:
+            self.model.train(X, Y)
+        finally:
+            self.model._overlap_hook = None
         if self.model.method_id in ['tst', 'tstm']:
             y_, _, _ = zero_one_normalization(Y)
         else:
@@ -163,4 +169,4 @@ class SMBO_OFFLINE(object):
         incumbent_value = np.min(y_)
         self.incumbent_value = incumbent_value
         self.acquisition_function.update(model=self.model, eta=incumbent_value, num_data=len(self.configurations))
-        return self.acq_optimizer.best_unevaluated(self.configurations + self.failed_configurations)
+        return self.acq_optimizer.best_unevaluated(evaluated)

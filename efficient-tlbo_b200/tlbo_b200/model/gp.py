@@ -72,6 +72,7 @@ class GaussianProcess(object):
         self.fit_info_ = None
         self._pack = None
         self._slot = 0
+        self._p0_override = None     # facades share one set of start points (same seed -> same draws)
 
     # ---- pack placement ------------------------------------------------------------
     def bind(self, pack, slot):
@@ -122,6 +123,8 @@ class GaussianProcess(object):
         """Default theta + ``n_opt_restarts`` samples: lognormal prior on the amplitude,
         uniform in the log bounds for length scales (model rng), horseshoe on the noise
         (both priors draw from the rng shared at construction)."""
+        if self._p0_override is not None:
+            return self._p0_override
         p0 = [self.kernel.theta.copy()]
         R = self.n_opt_restarts
         if R > 0:
@@ -153,7 +156,14 @@ def _check_train_args(model, X, Y):
 
 
 def fit_models(models, Xs, Ys, do_optimize=True):
-    """Train several ``GaussianProcess`` objects in one batched device launch.
+    """Train several ``GaussianProcess`` objects in one batched device launch (see
+    ``fit_models_async``)."""
+    return fit_models_async(models, Xs, Ys, do_optimize)()
+
+
+def fit_models_async(models, Xs, Ys, do_optimize=True):
+    """Enqueue the batched fit and return ``finish()``; host work done between the two
+    overlaps the device fit.
 
     Models bound to consecutive slots of one pack are fitted in place; unbound models get a
     private one-slot pack.  Models whose restart start points differ are launched in
@@ -187,28 +197,36 @@ def fit_models(models, Xs, Ys, do_optimize=True):
             g = groups[-1]
             last = g[-1][0]
             if (last._pack is mdl._pack and mdl._slot == last._slot + 1 and p0.shape == g[0][3].shape
-                    and np.array_equal(p0, g[0][3]) and np.array_equal(mdl.types, g[0][0].types)):
+                    and (p0 is g[0][3] or np.array_equal(p0, g[0][3])) and np.array_equal(mdl.types, g[0][0].types)):
                 g.append(job)
                 continue
         groups.append([job])
 
+    handles = []
     for g in groups:
         m0 = g[0][0]
         lb = m0.kernel.bounds
-        st, rt, rf, ri = ops.gp_fit_batched(
+        handles.append(ops.gp_fit_batched(
             [j[1] for j in g], [j[2] for j in g], m0.types, g[0][3], lb[:, 0], lb[:, 1],
             [j[0].mean_y_ for j in g], [j[0].std_y_ for j in g], m0._pack, slot0=m0._slot,
-            do_optimize=do_optimize, return_restarts=True)
-        thetas = ops.d2h(m0._pack.theta[m0._slot:m0._slot + len(g)])
-        for b, (mdl, X, y, p0) in enumerate(g):
-            if st[b] == 1:
-                # the reference's final GaussianProcessRegressor.fit raises (gp.py:146)
-                raise np.linalg.LinAlgError('Cholesky of the kernel matrix failed at the selected hyper-parameters')
-            if st[b] != 0:
-                raise RuntimeError('GP fit failed: no finite optimum (status %d)' % st[b])
-            mdl.hypers = thetas[b].copy()
-            mdl.kernel.theta = thetas[b].copy()
-            mdl.is_trained = True
-            mdl.n_train_ = X.shape[0]
-            mdl.fit_info_ = dict(restart_theta=rt[b], restart_f=rf[b], restart_info=ri[b])
-    return models
+            do_optimize=do_optimize, sync=False))
+
+    def finish():
+        for g, h in zip(groups, handles):
+            m0 = g[0][0]
+            st, rt, rf, ri = h.finish(return_restarts=True)
+            thetas = ops.d2h(m0._pack.theta[m0._slot:m0._slot + len(g)])
+            for b, (mdl, X, y, p0) in enumerate(g):
+                if st[b] == 1:
+                    # the reference's final GaussianProcessRegressor.fit raises (gp.py:146)
+                    raise np.linalg.LinAlgError(
+                        'Cholesky of the kernel matrix failed at the selected hyper-parameters')
+                if st[b] != 0:
+                    raise RuntimeError('GP fit failed: no finite optimum (status %d)' % st[b])
+                mdl.hypers = thetas[b].copy()
+                mdl.kernel.theta = thetas[b].copy()
+                mdl.is_trained = True
+                mdl.n_train_ = X.shape[0]
+                mdl.fit_info_ = dict(restart_theta=rt[b], restart_f=rf[b], restart_info=ri[b])
+        return models
+    return finish

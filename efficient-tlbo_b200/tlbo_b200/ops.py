@@ -94,6 +94,28 @@ def h2d(a, dtype=None):
     return t.to(_dev())
 
 
+class PinnedStage(object):
+    """Reusable pinned staging buffers for uploads that must not block the host while a
+    kernel is in flight (pageable copies synchronise).  One buffer per tag; a tag may be
+    reused once the consumer of the previous upload has been synchronised."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def upload(self, tag, arr):
+        arr = np.ascontiguousarray(arr)
+        nbytes = max(arr.nbytes, 8)
+        buf = self.bufs.get(tag)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(round_up(nbytes, 4096), dtype=torch.uint8).pin_memory()
+            self.bufs[tag] = buf
+        src = torch.from_numpy(arr)
+        view = buf[:arr.nbytes].view(src.dtype).reshape(src.shape) if arr.nbytes else src
+        view.copy_(src)
+        STATS.h2d += arr.nbytes
+        return view.to(_dev(), non_blocking=True)
+
+
 def d2h(t):
     """Device tensor -> numpy (counted; synchronises)."""
     STATS.d2h += t.numel() * t.element_size()
@@ -173,11 +195,43 @@ def _pad_batch(X_list, y_list, ncap, d):
     return h2d(Xh), h2d(yh), h2d(nh)
 
 
+class FitHandle(object):
+    """Result buffers of an enqueued ``tlbo_gp_fit_batched``; ``finish`` reads them back
+    (one synchronisation)."""
+
+    def __init__(self, status, rt, rf, ri, keep):
+        self.status, self.rt, self.rf, self.ri, self._keep = status, rt, rf, ri, keep
+
+    def finish(self, return_restarts=False):
+        st = d2h(self.status)
+        self._keep = None
+        if return_restarts:
+            return st, d2h(self.rt), d2h(self.rf), d2h(self.ri)
+        return st
+
+
+_CONST_CACHE = {}
+
+
+def _cached_const(a):
+    """Small read-only device constants (start points, bounds): uploaded once per value."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    key = (a.shape, a.tobytes(), torch.cuda.current_device())
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) > 256:
+            _CONST_CACHE.clear()
+        t = h2d(a)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0, do_optimize=True,
-                   return_restarts=False):
+                   return_restarts=False, sync=True):
     """``tlbo_gp_fit_batched``.  X_list/y_list: per-surrogate host arrays (y already
     normalised); p0 [R, H] start points; returns status int32[B] (host) and optionally
-    the per-restart results."""
+    the per-restart results -- or, with ``sync=False``, a ``FitHandle`` right after the
+    launch so that host work can overlap the fit."""
     B = len(X_list)
     d = int(X_list[0].shape[1])
     H = d + 2
@@ -188,27 +242,27 @@ def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0
     dev = dX.device
     p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, H))
     R = p0.shape[0]
-    dp0 = h2d(p0)
-    dlo = h2d(np.ascontiguousarray(lo, dtype=np.float64))
-    dhi = h2d(np.ascontiguousarray(hi, dtype=np.float64))
+    dp0 = _cached_const(p0)
+    dlo = _cached_const(lo)
+    dhi = _cached_const(hi)
     hym = np.ascontiguousarray(ymean, dtype=np.float64)
     hys = np.ascontiguousarray(ystd, dtype=np.float64)
     STATS.h2d += hym.nbytes + hys.nbytes
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, R, ncap, d))
     work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    rt = torch.zeros(B, R, H, dtype=F64, device=dev)
-    rf = torch.zeros(B, R, dtype=F64, device=dev)
-    ri = torch.zeros(B, R, 4, dtype=torch.int32, device=dev)
+    rt = torch.empty(B, R, H, dtype=F64, device=dev)
+    rf = torch.empty(B, R, dtype=F64, device=dev)
+    ri = torch.empty(B, R, 4, dtype=torch.int32, device=dev)
     t = _types_arr(types)
     with _call('gp_fit', 2):            # gp_fit_kernel + gp_factorize_kernel
         check(lib.tlbo_gp_fit_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dp0), R, ptr(dlo),
                                       ptr(dhi), ptr(hym), ptr(hys), 1 if do_optimize else 0, pack.ref(), slot0,
                                       ptr(rt), ptr(rf), ptr(ri), ptr(status), ptr(work), _stream()))
-    st = d2h(status)                   # synchronises; keeps host staging alive until done
-    if return_restarts:
-        return st, d2h(rt), d2h(rf), d2h(ri)
-    return st
+    h = FitHandle(status, rt, rf, ri, (dX, dy, dn, work, hym, hys))
+    if not sync:
+        return h
+    return h.finish(return_restarts)
 
 
 def gp_factorize_batched(X_list, y_list, types, thetas, ymean, ystd, pack, slot0=0, want_dense=False):
@@ -334,6 +388,32 @@ def rank_loss_counts(y, ys, row_lo, row_hi, upper_only=False):
     with _call('rank_loss_counts', 1):
         check(lib.tlbo_rank_loss_counts(ptr(dy), ptr(dys), int(n), int(S), int(Mr), ptr(dlo), ptr(dhi),
                                         1 if upper_only else 0, ptr(counts), _stream()))
+    return d2h(counts)
+
+
+def rank_loss_counts_normal(y, z, loc, scale, src, row_lo, row_hi, sync=True):
+    """``tlbo_rank_loss_counts_normal``: z [S, Mr, n] standard-normal draws (host), loc / scale
+    device tensors [*, n] (outputs of ``gp_predict``), src[Mr] their row per column.  Returns
+    int64[S, Mr] on the host, or the device tensor when ``sync`` is False."""
+    dev = _dev()
+
+    def up(a, dt):
+        if torch.is_tensor(a) and a.is_cuda:
+            return a
+        return h2d(np.ascontiguousarray(a, dtype=dt))
+    dy = up(y, np.float64)
+    dz = up(z, np.float64)
+    S, Mr, n = dz.shape
+    dsrc = up(src, np.int32)
+    dlo = up(row_lo, np.int32)
+    dhi = up(row_hi, np.int32)
+    assert loc.is_contiguous() and scale.is_contiguous() and loc.shape[1] == n
+    counts = torch.zeros(S, Mr, dtype=torch.int64, device=dev)
+    with _call('rank_loss_counts', 1):
+        check(lib.tlbo_rank_loss_counts_normal(ptr(dy), ptr(dz), ptr(loc), ptr(scale), ptr(dsrc), int(n), int(S),
+                                               int(Mr), ptr(dlo), ptr(dhi), ptr(counts), _stream()))
+    if not sync:
+        return counts
     return d2h(counts)
 
 

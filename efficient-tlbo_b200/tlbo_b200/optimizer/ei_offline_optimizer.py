@@ -49,6 +49,8 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         self._keys_host = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
         self._keys_dev = torch.empty(hi - lo, dtype=torch.float64, device='cuda')
         self.last_best = None
+        self._prepared = None
+        self._stage = ops.PinnedStage()
 
     def reupload(self):
         """Host -> device copy of the candidate rows (the end-to-end benchmark path, where
@@ -62,9 +64,11 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
             return self.configuration_list[idx]
         return Configuration(self.config_space, self.X_table[idx], idx)
 
-    def best_unevaluated(self, evaluated_rows):
-        """Row index the reference's loop would return: first entry of the descending
-        (EI, random key) order that is not in ``evaluated_rows``."""
+    def prepare(self, evaluated_rows):
+        """Host half of one maximisation -- the ``rng.rand(N)`` tie-break keys of
+        ``_sort_configs_by_acq_value`` and the sorted evaluated-row list -- staged through
+        pinned memory with asynchronous uploads, so that it can run while the facade's fit
+        kernel is in flight."""
         import torch
         from tlbo_b200 import ops
         keys = self.rng.rand(self.N)
@@ -73,7 +77,16 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         ops.STATS.h2d += self._keys_host.numel() * 8
         ex = None
         if len(evaluated_rows):
-            ex = ops.h2d(np.sort(np.asarray(evaluated_rows, dtype=np.int64)))
+            ex = self._stage.upload('excluded', np.sort(np.asarray(evaluated_rows, dtype=np.int64)))
+        self._prepared = (ex,)
+
+    def best_unevaluated(self, evaluated_rows):
+        """Row index the reference's loop would return: first entry of the descending
+        (EI, random key) order that is not in ``evaluated_rows``."""
+        if self._prepared is None:
+            self.prepare(evaluated_rows)
+        ex, = self._prepared
+        self._prepared = None
         if self.shard is None:
             res = self.acquisition_function.best_unevaluated(self.X_dev, keys=self._keys_dev, excluded=ex,
                                                              ws=self._ws)

@@ -158,6 +158,16 @@ int64_t tlbo_predict_ei_workspace_bytes(int64_t N);
 int tlbo_rank_loss_counts(const double* d_y, const double* d_ys, int n, int S, int Mr, const int32_t* d_row_lo,
                           const int32_t* d_row_hi, int upper_only, int64_t* d_counts, void* stream);
 
+/* Same counts with the bootstrap draws formed on the device: d_z [S, Mr, n] are STANDARD normal
+ * draws (host, legacy np.random stream, reference draw order); the sampled values of
+ * rgpe.py:77,97  np.random.normal(mu, var)  are loc + scale * z with loc = d_loc[d_src[m]],
+ * scale = d_scale[d_src[m]] (rows of the [*, n] outputs of tlbo_gp_predict), evaluated as a
+ * rounded product plus a rounded sum exactly like numpy's legacy normal().  Saves the
+ * device -> host -> device round trip of the predictions inside RGPE.train.                 */
+int tlbo_rank_loss_counts_normal(const double* d_y, const double* d_z, const double* d_loc, const double* d_scale,
+                                 const int32_t* d_src, int n, int S, int Mr, const int32_t* d_row_lo,
+                                 const int32_t* d_row_hi, int64_t* d_counts, void* stream);
+
 /* Pairwise logistic ranking loss and gradient -- replaces Loss_func / Loss_der with
  * func_id = 3 (tlbo/utils/scipy_solver.py:6-78) inside the SLSQP loop of scipy_solve.
  *   d_A [n, m] predictions, d_y [n], d_w [m];  d_out [2 + m] = (loss, #pairs, grad[m]). */

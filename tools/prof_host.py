@@ -1,0 +1,18 @@
+import sys, os, cProfile, pstats, io
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'efficient-tlbo_b200'))
+import numpy as np, torch, time
+import bench
+class A: pass
+args = A(); args.method = sys.argv[1] if len(sys.argv) > 1 else 'rgpe'; args.pool = 100000; args.sources = 29; args.n0 = 40
+wl = bench.build_workload(0, 4465, args.pool, args.sources, args.n0)
+fac, smbo = bench.make_product(args, wl)
+for _ in range(3): smbo.iterate()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+pr = cProfile.Profile(); pr.enable()
+for _ in range(20): smbo.iterate()
+torch.cuda.synchronize()
+pr.disable()
+print('ms/step', (time.perf_counter() - t0) / 20 * 1e3)
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats('tottime').print_stats(28); print(s.getvalue()[:6000])
