@@ -16,10 +16,36 @@
 //      from rows of L^-T and dK/dtheta recomputed per pair -- never materialised (n^2 H).
 //   5. + log-priors (lognormal on c, horseshoe on s2) and their gradients.
 #include "tlbo_common.cuh"
-#include "lbfgsb_dense.cuh"
-#include "lbfgsb_warp.cuh"
 
 #define FIT_THREADS 256
+// Optional phase timing (compile with -DTLBO_PHASE_TIMING): CTA 0 accumulates clock64() deltas
+// per phase of the NLL evaluation / optimiser step; read back with tlbo_debug_phase_cycles().
+#ifdef TLBO_PHASE_TIMING
+__device__ long long g_phase_cycles[16];
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_MARK(idx)                                                        \
+  do {                                                                         \
+    const long long _now = clock64();                                          \
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_cycles[idx] += _now - _pt; \
+    _pt = _now;                                                                \
+  } while (0)
+#define PHASE_LOCALS() long long _pl[4] = {0, 0, 0, 0}
+#define PHASE_LMARK(q) do { const long long _now = clock64(); _pl[q] += _now - _pt; _pt = _now; } while (0)
+#define PHASE_LFLUSH(base)                                                     \
+  do {                                                                         \
+    if (threadIdx.x == 0 && blockIdx.x == 0)                                   \
+      for (int _q = 0; _q < 4; _q++) g_phase_cycles[base + _q] += _pl[_q];     \
+  } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_MARK(idx) do {} while (0)
+#define PHASE_LOCALS() do {} while (0)
+#define PHASE_LMARK(q) do {} while (0)
+#define PHASE_LFLUSH(base) do {} while (0)
+#endif
+#include "lbfgsb_dense.cuh"
+#include "lbfgsb_warp.cuh"
+#define FIT_COLBUF 392   // raw / inverse-masked / lower-masked copies of the pivot column + pivot, 1/pivot
 
 struct FitWs {
   double* A;       // [(n+1) * lda]  elimination panel
@@ -31,20 +57,31 @@ struct FitWs {
   double* alpha;   // [n]
   double* red;     // [8 * 32] reduction scratch
   double* hyp;     // [2 * TLBO_HMAX] per permuted column: l (cont) or 1/(2 l^2) (cat); then 1/l^3 (cat)
-  double* colbuf;  // [2 * 128] double-buffered pivot-column broadcast of the register-panel elimination
-  int n, lda, d;
+  double* colbuf;  // [2 * FIT_COLBUF] double-buffered pivot-column broadcast of the register-panel elimination
+  int* pairs;      // [n (n-1) / 2] packed (i << 16 | j), i > j: built once per kernel (register-panel path)
+  double* Kc;      // [npairs] kernel value per pair        } written by the kernel-matrix build, reused by
+  double* Cg;      // [npairs] c e^{-t-hs} 5/3 (1 + t)      } the gradient contraction (NULL: recompute)
+  int n, lda, d, npairs;
 };
 
 __host__ __device__ inline int fit_lda(int n) { return (n & 1) ? n : n + 1; }
 
-__host__ inline size_t fit_small_bytes(int ncap, int d) {
-  // Xr, Xs, y, piv, dinv, alpha, red, hyp
-  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * 128 + 8);
+// pair tables of the register-panel path: index table always (tile > 0), value caches when
+// they fit beside the panel (tile <= 5, i.e. n <= 79)
+__host__ __device__ inline size_t fit_pair_bytes(int ncap, int tile) {
+  if (tile <= 0) return 0;
+  const size_t np = (size_t)ncap * (ncap - 1) / 2 + 2;
+  return ((np * 4 + 15) / 16) * 16 + (tile <= 5 ? 2 * np * sizeof(double) : 0);
+}
+__host__ inline size_t fit_small_bytes(int ncap, int d, int tile) {
+  // Xr, Xs, y, piv, dinv, alpha, red, hyp, colbuf, pair tables
+  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8) +
+         fit_pair_bytes(ncap, tile);
 }
 __host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
 
 __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* panel_global, int n, int ncap,
-                                         int d) {
+                                         int d, int tile) {
   double* p = reinterpret_cast<double*>(smem);
   S.n = n; S.d = d; S.lda = fit_lda(n);
   S.Xr = p; p += (size_t)ncap * d;
@@ -55,7 +92,15 @@ __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* 
   S.alpha = p; p += ncap;
   S.red = p; p += 8 * 32;
   S.hyp = p; p += 2 * TLBO_HMAX;
-  S.colbuf = p; p += 2 * 128;
+  S.colbuf = p; p += 2 * FIT_COLBUF;
+  S.npairs = n * (n - 1) / 2;
+  S.pairs = nullptr; S.Kc = nullptr; S.Cg = nullptr;
+  if (tile > 0) {
+    const size_t np = (size_t)ncap * (ncap - 1) / 2 + 2;
+    if (tile <= 5) { S.Kc = p; p += np; S.Cg = p; p += np; }
+    S.pairs = reinterpret_cast<int*>(p);
+    p += ((np * 4 + 15) / 16) * 2;
+  }
   S.A = panel_global ? panel_global : p;
 }
 
@@ -67,6 +112,14 @@ __device__ __forceinline__ void load_problem(const FitWs& S, const SpaceDesc& sp
     S.Xr[idx] = X[(size_t)i * d + sp.perm[p]];
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) S.y[i] = y[i];
+  if (S.pairs) {
+    for (int q = threadIdx.x; q < S.npairs; q += blockDim.x) {
+      int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+      while (i * (i - 1) / 2 > q) i--;
+      while ((i + 1) * i / 2 <= q) i++;
+      S.pairs[q] = (i << 16) | (q - i * (i - 1) / 2);
+    }
+  }
   (void)ncap;
 }
 
@@ -154,6 +207,96 @@ __device__ bool build_and_eliminate(const FitWs& S, const SpaceDesc& sp, const d
   return true;
 }
 
+// 1/x from the hardware reciprocal seed (rcp.approx.ftz.f64, ~20 bits) and two Newton steps:
+// ~52 cycles of dependent latency against ~112 for the IEEE division (tools/ubench/lat.cu),
+// result within 1 ulp -- it sits on the critical path of every elimination step.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// One block of 16 elimination steps with the pivot-column block index KB a compile-time
+// constant (the outer loop over KB is unrolled by template recursion): tile indexing, most of
+// the activity masks and the skipping of already-eliminated column blocks resolve statically,
+// so a step is: 2-3 128-bit stores by the 16 owners of the pivot column (one warp), ONE
+// __syncthreads, five 128-bit loads, a handful of selects and the tile FMAs -- no uniform
+// branches and no data-dependent branch (a non-positive pivot only raises a flag).
+// Developed against tools/ubench/elim*.cu: 820 -> 503 cycles per step on B200.
+struct ElimCtx {
+  double* colbuf; double* pivs; int n; int tx, ty; bool diag_lower, own_diag; double ip_next; bool bad;
+};
+
+template <int T, int KB>
+__device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
+  constexpr int TP = (T + 1) & ~1;             // packed per-lane stride (128-bit chunks)
+  const int n = c.n, tx = c.tx, ty = c.ty;
+  const int kend = (n - 16 * KB) < 16 ? (n - 16 * KB) : 16;
+  for (int kt = 0; kt < kend; kt++) {
+    const int k = 16 * KB + kt;
+    double* buf = c.colbuf + (kt & 1) * FIT_COLBUF;
+    if (tx == kt) {
+      double2* b2 = reinterpret_cast<double2*>(buf + ty * TP);
+#pragma unroll
+      for (int q = 0; q < TP; q += 2)
+        b2[q >> 1] = make_double2(a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0);
+      if (ty == kt) {
+        *reinterpret_cast<double2*>(buf + 384) = make_double2(a[KB][KB], c.ip_next);
+        c.pivs[k] = a[KB][KB];
+      }
+    }
+    const bool row_lt = ty < kt, row_eq = ty == kt, col_gt = tx > kt;
+    __syncthreads();
+    const double2 pp = *reinterpret_cast<const double2*>(buf + 384);
+    c.bad = c.bad || !(pp.x > 0.0);
+    const double ip = pp.y;
+    double ck_lo[TP], fr[TP];
+    {
+      const double2* c2 = reinterpret_cast<const double2*>(buf + ty * TP);
+      const double2* f2 = reinterpret_cast<const double2*>(buf + tx * TP);
+#pragma unroll
+      for (int q = 0; q < TP; q += 2) {
+        const double2 v = c2[q >> 1], w = f2[q >> 1];
+        ck_lo[q] = v.x; ck_lo[q + 1] = v.y; fr[q] = w.x; fr[q + 1] = w.y;
+      }
+    }
+    // inverse-part multiplier of row block KB (rows i < k are active, the pivot row enters with 1);
+    // row blocks below KB are fully active, those above not yet
+    const double ck_up_kb = row_lt ? ck_lo[KB] : (row_eq ? 1.0 : 0.0);
+#pragma unroll
+    for (int jb = KB; jb < T; jb++) {
+      double f = (tx + 16 * jb < n) ? fr[jb] * ip : 0.0;
+      if (jb == KB) f = col_gt ? f : 0.0;
+#pragma unroll
+      for (int ia = 0; ia < T; ia++) {
+        if (ia > jb) a[ia][jb] -= ck_lo[ia] * f;                        // lower part (and the y row)
+        else if (ia < jb) {                                             // inverse part
+          if (ia < KB) a[ia][jb] -= ck_lo[ia] * f;
+          else if (ia == KB) a[ia][jb] -= ck_up_kb * f;
+        } else {                                                        // diagonal tile
+          const double cu = (ia < KB) ? ck_lo[ia] : ((ia == KB) ? ck_up_kb : 0.0);
+          a[ia][jb] -= (c.diag_lower ? ck_lo[ia] : cu) * f;
+        }
+      }
+    }
+    // the owner of the next pivot prepares its reciprocal
+    if (c.own_diag) {
+      if (kt < 15) { if (tx == kt + 1) c.ip_next = fast_rcp(a[KB][KB]); }
+      else if (KB + 1 < T) { if (tx == 0) c.ip_next = fast_rcp(a[(KB + 1 < T) ? KB + 1 : KB][(KB + 1 < T) ? KB + 1 : KB]); }
+    }
+  }
+}
+
+template <int T, int KB>
+__device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
+  if (16 * KB < c.n) elim_block<T, KB>(a, c);
+  if constexpr (KB + 1 < T) elim_all<T, KB + 1>(a, c);
+}
+
 // ---------------------------------------------------------------------------------------
 // Register-resident variant of steps 1-2 for n + 1 <= 16 * T.  The (n+1) x n panel lives in
 // registers, 2-D cyclically distributed over the 16 x 16 thread grid (thread (ty, tx) owns
@@ -169,8 +312,11 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
                                         bool scale_lower) {
   const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
   const int tid = threadIdx.x, NT = blockDim.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  // ty = fast index: the 16 owners of a pivot column (fixed tx) sit in ONE warp, so the other
+  // seven warps skip the publish code with a uniform branch
+  const int tx = tid >> 4, ty = tid & 15;
   double* A = S.A;
+  PHASE_T0();
   __syncthreads();
   if (tid < d) {
     const double l = exp(theta[1 + tid]);
@@ -187,23 +333,25 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
     S.Xs[idx] = v;
   }
   __syncthreads();
+  PHASE_MARK(0);
   // kernel matrix (lower triangle, diagonal, y row) through shared memory: ONE copy of the
-  // exp / sqrt code, then every thread picks up its register tile
-  for (int idx = tid; idx < (n + 1) * n; idx += NT) {
-    const int i = idx / n, j = idx - i * n;
-    if (i < j) continue;
-    double v;
-    if (i == n) v = S.y[j];
-    else if (i == j) v = c + noise;
-    else {
-      const double* xi = S.Xs + (size_t)i * d;
-      const double* xj = S.Xs + (size_t)j * d;
-      double s = 0.0, hs = 0.0;
-      for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
-      for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
-      v = matern_hamming(c, s, hs);
-    }
+  // exp / sqrt code over the pair table, then every thread picks up its register tile
+  for (int q = tid; q < S.npairs; q += NT) {
+    const int ij = S.pairs[q], i = ij >> 16, j = ij & 0xffff;
+    const double* xi = S.Xs + (size_t)i * d;
+    const double* xj = S.Xs + (size_t)j * d;
+    double s = 0.0, hs = 0.0;
+    for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+    for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+    const double t = sqrt(s) * SQRT5;
+    const double ce = c * exp(-t - hs);
+    const double v = ce * (1.0 + t + t * t / 3.0);
     A[(size_t)i * lda + j] = v;
+    if (S.Kc) { S.Kc[q] = v; S.Cg[q] = ce * (5.0 / 3.0) * (t + 1.0); }
+  }
+  for (int j = tid; j < n; j += NT) {
+    A[(size_t)j * lda + j] = c + noise;
+    A[(size_t)n * lda + j] = S.y[j];
   }
   __syncthreads();
   double a[T][T];
@@ -216,50 +364,20 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
       a[ia][jb] = (i <= n && j < n && i >= j) ? A[(size_t)i * lda + j] : 0.0;
     }
   }
+  PHASE_MARK(1);
   // Tile (ia, jb) holds lower-part elements (i >= j, incl. the y row) when ia > jb, upper-part
-  // (inverse) elements when ia < jb; on diagonal tiles the class is fixed per thread.  All
-  // k-dependent masking is folded into the multipliers (f = 0 for inactive columns, ck_up = 0
-  // for not-yet-active inverse rows), so the tile update is T*T unpredicated FMAs.
-  const bool diag_lower = ty >= tx;
-  bool ok = true;
-  for (int k = 0; k < n; k++) {
-    double* buf = S.colbuf + (k & 1) * 128;
-    const int kb = k >> 4;
-    if (tx == (k & 15)) {
-#pragma unroll
-      for (int jb = 0; jb < T; jb++)
-        if (jb == kb) {
-#pragma unroll
-          for (int ia = 0; ia < T; ia++) buf[ty + 16 * ia] = a[ia][jb];
-        }
-    }
-    __syncthreads();
-    const double piv = buf[k];
-    if (!(piv > 0.0)) { ok = false; break; }
-    const double ip = 1.0 / piv;
-    if (tid == 0) S.piv[k] = piv;
-    double ck_lo[T], ck_up[T];
-#pragma unroll
-    for (int ia = 0; ia < T; ia++) {
-      const int i = ty + 16 * ia;
-      ck_lo[ia] = buf[i];
-      ck_up[ia] = (i < k) ? ck_lo[ia] : ((i == k) ? 1.0 : 0.0);
-    }
-    const int jb0 = (k + 1) >> 4;      // column blocks below hold only j <= k
-#pragma unroll
-    for (int jb = 0; jb < T; jb++) {
-      if (jb >= jb0) {
-        const int j = tx + 16 * jb;
-        const double f = (j > k && j < n) ? buf[j] * ip : 0.0;
-#pragma unroll
-        for (int ia = 0; ia < T; ia++) {
-          const double ck = (ia > jb) ? ck_lo[ia] : ((ia < jb) ? ck_up[ia] : (diag_lower ? ck_lo[ia] : ck_up[ia]));
-          a[ia][jb] -= ck * f;
-        }
-      }
-    }
-  }
-  __syncthreads();
+  // (inverse) elements when ia < jb; on diagonal tiles the class is fixed per thread.  The 16
+  // owners of pivot column k publish it three ways -- raw (multiplier of lower-part rows),
+  // masked to the active inverse rows (i < k, 1 at i == k), masked to the rows j > k that
+  // still get eliminated -- and the owner of the pivot publishes 1/pivot, so the consumers'
+  // tile update is T*T unpredicated FMAs with no per-step division, select or compare.
+  ElimCtx ec;
+  ec.colbuf = S.colbuf; ec.pivs = S.piv; ec.n = n; ec.tx = tx; ec.ty = ty;
+  ec.diag_lower = ty >= tx; ec.own_diag = ty == tx; ec.ip_next = 0.0; ec.bad = false;
+  if (tid == 0) ec.ip_next = fast_rcp(a[0][0]);
+  elim_all<T, 0>(a, ec);
+  const bool ok = !__syncthreads_or(ec.bad ? 1 : 0);
+  PHASE_MARK(2);
   if (!ok) return false;
   for (int k = tid; k < n; k += NT) S.dinv[k] = 1.0 / sqrt(S.piv[k]);
   __syncthreads();
@@ -291,6 +409,7 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
     S.alpha[i] = al;
   }
   __syncthreads();
+  PHASE_MARK(3);
   return true;
 }
 
@@ -333,6 +452,28 @@ __device__ __forceinline__ void nll_finish(const double* theta, int H, int n, do
   }
 }
 
+// K^-1_ij = sum_k U[i][k] U[j][k] over the zero-padded rows of the panel (row i of U is zero
+// left of column i), for the lower-triangle tiles only.  With the column block KB static, row
+// blocks above KB are skipped at compile time and so are the tiles right of the diagonal.
+template <int T, int KB>
+__device__ __forceinline__ void kin_all(double (&kin)[T][T], const double* A, int lda, int n, int ty, int tx) {
+  const int k1 = (16 * KB + 16 < n) ? 16 * KB + 16 : n;
+  for (int k = 16 * KB; k < k1; k++) {
+    double ui[KB + 1], uj[KB + 1];
+#pragma unroll
+    for (int q = 0; q <= KB; q++) {
+      const int i = ty + 16 * q, j = tx + 16 * q;
+      ui[q] = (i < n) ? A[(size_t)i * lda + k] : 0.0;
+      uj[q] = (j < n) ? A[(size_t)j * lda + k] : 0.0;
+    }
+#pragma unroll
+    for (int ia = 0; ia <= KB; ia++)
+#pragma unroll
+      for (int jb = 0; jb <= ia; jb++) kin[ia][jb] += ui[ia] * uj[jb];
+  }
+  if constexpr (KB + 1 < T) kin_all<T, KB + 1>(kin, A, lda, n, ty, tx);
+}
+
 // nll_eval on the register-panel path: the gradient contraction uses the same 2-D cyclic
 // tiling -- K^-1_ij = sum_k U[i][k] U[j][k] over the zero-padded rows of the panel, T x T
 // outer products per k (2T shared loads per T^2 FMAs instead of 2 per FMA).
@@ -340,7 +481,7 @@ template <int T, int DMAX>
 __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
   const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
   const int tid = threadIdx.x, NT = blockDim.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid >> 4, ty = tid & 15;
   const bool ok = build_and_eliminate_reg<T>(S, sp, theta, false);
   if (!ok) {
     if (tid == 0) out[0] = 1e25;
@@ -356,40 +497,20 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     const double z = A[(size_t)n * lda + k];
     part += 0.5 * z * z + 0.5 * log(S.piv[k]);
   }
+  PHASE_T0();
   const double nll_data = block_sum(part, S.red);
+  PHASE_MARK(4);
 
   double kin[T][T];
 #pragma unroll
   for (int ia = 0; ia < T; ia++)
 #pragma unroll
     for (int jb = 0; jb < T; jb++) kin[ia][jb] = 0.0;
-  // only tiles with i > j (or the diagonal) matter; rows of U are zero left of the diagonal,
-  // so the sum may start at the thread's smallest row index
-  {
-    const double* ui_p[T];
-    const double* uj_p[T];
-#pragma unroll
-    for (int q = 0; q < T; q++) {
-      const int i = ty + 16 * q, j = tx + 16 * q;
-      ui_p[q] = A + (size_t)(i < n ? i : 0) * lda;
-      uj_p[q] = A + (size_t)(j < n ? j : 0) * lda;
-    }
-    for (int k = ty; k < n; k++) {
-      double ui[T], uj[T];
-#pragma unroll
-      for (int q = 0; q < T; q++) {
-        ui[q] = (ty + 16 * q < n) ? ui_p[q][k] : 0.0;
-        uj[q] = (tx + 16 * q < n) ? uj_p[q][k] : 0.0;
-      }
-#pragma unroll
-      for (int ia = 0; ia < T; ia++)
-#pragma unroll
-        for (int jb = 0; jb < T; jb++) kin[ia][jb] += ui[ia] * uj[jb];
-    }
-  }
+  kin_all<T, 0>(kin, A, lda, n, ty, tx);
   // publish W = alpha alpha^T - K^-1 (strict lower part into the panel, diagonal into piv[]:
   // both are dead by now) and contract it with dK/dtheta in ONE linear pair loop
   __syncthreads();
+  PHASE_MARK(5);
   {
     double* Aw = S.A;
 #pragma unroll
@@ -404,28 +525,30 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     }
   }
   __syncthreads();
+  PHASE_MARK(6);
   double g0 = 0.0, gn = 0.0;
   double gacc[DMAX];
 #pragma unroll
   for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
-  const int npairs = n * (n - 1) / 2;
-  for (int q = tid; q < npairs; q += NT) {
-    int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
-    while (i * (i - 1) / 2 > q) i--;
-    while ((i + 1) * i / 2 <= q) i++;
-    const int j = q - i * (i - 1) / 2;   // j < i
+  for (int q = tid; q < S.npairs; q += NT) {
+    const int ij = S.pairs[q], i = ij >> 16, j = ij & 0xffff;
     const double W = A[(size_t)i * lda + j];
     const double* xi = S.Xs + (size_t)i * d;
     const double* xj = S.Xs + (size_t)j * d;
-    double s = 0.0, hs = 0.0;
-    for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
-    for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
-    const double t = sqrt(s) * SQRT5;
-    const double e = exp(-t), eh = exp(-hs);
-    const double Kc = c * ((1.0 + t + t * t / 3.0) * e) * eh;
-    const double WK = W * Kc;
+    double WK, coef;
+    if (S.Kc) {
+      WK = W * S.Kc[q];
+      coef = W * S.Cg[q];
+    } else {
+      double s = 0.0, hs = 0.0;
+      for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+      for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+      const double t = sqrt(s) * SQRT5;
+      const double ce = c * exp(-t - hs);
+      WK = W * (ce * (1.0 + t + t * t / 3.0));
+      coef = W * (ce * (5.0 / 3.0) * (t + 1.0));
+    }
     g0 += WK;
-    const double coef = W * c * eh * (5.0 / 3.0) * (t + 1.0) * e;
 #pragma unroll
     for (int p = 0; p < DMAX; p++) {
       if (p < dc) { const double df = xi[p] - xj[p]; gacc[p] += coef * (df * df); }
@@ -437,6 +560,7 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     g0 += 0.5 * W * c;
     gn += 0.5 * W * noise;
   }
+  PHASE_MARK(7);
   const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
   __syncthreads();
   {
@@ -461,6 +585,7 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   __syncthreads();
   if (tid == 0) nll_finish(theta, H, n, nll_data, out);
   __syncthreads();
+  PHASE_MARK(8);
   return true;
 }
 
@@ -610,7 +735,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   LbwState* sw = reinterpret_cast<LbwState*>(smem);
   unsigned char* rest = smem + fit_state_bytes();
   FitWs S;
-  carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d);
+  carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d, T);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.p0[(size_t)r * H + tid];
   __syncthreads();
@@ -645,6 +770,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
     __syncthreads();
     nll_eval_any<T, DMAX>(S, a.sp, th, fg);
     nfev++;
+    PHASE_T0();
     if (WARP_OPT) {
       if (wid == 0) {
         const int rc = lbw_feed(*sw, fg[0], fg + 1, lane);
@@ -654,6 +780,10 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
       if (tid == 0) act = lbfgsb_feed(*st, fg[0], fg + 1);
     }
     __syncthreads();
+    PHASE_MARK(9);
+#ifdef TLBO_PHASE_TIMING
+    if (tid == 0 && blockIdx.x == 0) g_phase_cycles[15] += 1;
+#endif
     if (act == LB_DONE) break;
   }
   if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = WARP_OPT ? sw->x[tid] : st->x[tid];
@@ -686,7 +816,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_factorize_kernel(FacArgs a)
   __shared__ double th[TLBO_HMAX];
   __shared__ int best;
   FitWs S;
-  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, ncap, d);
+  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, ncap, d, 0);
   load_problem(S, a.sp, a.X + (size_t)b * ncap * d, a.y + (size_t)b * ncap, ncap);
   if (tid == 0) {
     // gp.py:241-248: first strict improvement wins
@@ -786,7 +916,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) 
   __shared__ double th[TLBO_HMAX];
   __shared__ double fg[1 + TLBO_HMAX];
   FitWs S;
-  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, a.ncap, d);
+  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, a.ncap, d, T);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.theta[(size_t)b * H + tid];
   __syncthreads();
@@ -798,7 +928,20 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) 
 // ---------------------------------------------------------------------------------------
 // host side
 static const size_t kSmemLimit = 227 * 1024;
-static int g_fit_variant = 1;   // 1 = warp-cooperative optimiser, 0 = single-thread statement
+static int g_fit_variant = 1;   // 1 = warp-cooperative optimiser + register panel, 0 = single-thread statement
+
+#ifdef TLBO_PHASE_TIMING
+extern "C" int tlbo_debug_phase_cycles(long long* h_out, int reset) {
+  cudaMemcpyFromSymbol(h_out, g_phase_cycles, sizeof(long long) * 16);
+  cudaMemcpyFromSymbol(h_out + 16, g_feed_cycles, sizeof(long long) * 8);
+  if (reset) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+    cudaMemcpyToSymbol(g_feed_cycles, z, sizeof(long long) * 8);
+  }
+  return 0;
+}
+#endif
 
 extern "C" int tlbo_set_fit_variant(int variant) {
   const int old = g_fit_variant;
@@ -807,6 +950,7 @@ extern "C" int tlbo_set_fit_variant(int variant) {
 }
 
 struct WorkLayout {
+  int tile;              // register-panel tile (0 = shared-memory panel path)
   bool global_panels;
   size_t smem_fit, smem_fac;
   size_t panel_stride;   // doubles
@@ -814,9 +958,12 @@ struct WorkLayout {
 
 static WorkLayout plan(int ncap, int d) {
   WorkLayout w;
-  const size_t small = fit_small_bytes(ncap, d);
   const size_t panel = fit_panel_bytes(ncap);
   const size_t st = fit_state_bytes();
+  int tile = g_fit_variant != 0 ? panel_tile_for(ncap) : 0;
+  size_t small = fit_small_bytes(ncap, d, tile);
+  if (tile > 0 && st + small + panel + 1024 > kSmemLimit) { tile = 0; small = fit_small_bytes(ncap, d, 0); }
+  w.tile = tile;
   w.global_panels = (st + small + panel + 1024) > kSmemLimit;
   w.smem_fit = st + small + (w.global_panels ? 0 : panel);
   w.smem_fac = small + (w.global_panels ? 0 : panel);
@@ -922,7 +1069,7 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
       default: TLBO_LAUNCH_FIT(DM, true, 0); break;                          \
     }                                                                        \
   } while (0)
-  const int tile = (g_fit_variant != 0 && !w.global_panels) ? panel_tile_for(ncap) : 0;
+  const int tile = w.tile;
   if (g_fit_variant != 0) {
     if (d <= 12) TLBO_LAUNCH_FIT_T(12); else TLBO_LAUNCH_FIT_T(24);
   } else {
@@ -990,7 +1137,7 @@ extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, co
       default: TLBO_LAUNCH_NLL(DM, 0); break;                                \
     }                                                                        \
   } while (0)
-  const int tile = (g_fit_variant != 0 && !w.global_panels) ? panel_tile_for(ncap) : 0;
+  const int tile = w.tile;
   if (d <= 12) TLBO_LAUNCH_NLL_T(12); else TLBO_LAUNCH_NLL_T(24);
 #undef TLBO_LAUNCH_NLL_T
 #undef TLBO_LAUNCH_NLL

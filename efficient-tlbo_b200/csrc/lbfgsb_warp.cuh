@@ -43,6 +43,15 @@ struct LbwState {
   int flag;                             // lane-0 -> warp broadcast slot
 };
 
+#ifdef TLBO_PHASE_TIMING
+#define LBW_T0() long long _lt = clock64()
+#define LBW_MARK(idx) do { const long long _n = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) g_feed_cycles[idx] += _n - _lt; _lt = _n; } while (0)
+__device__ long long g_feed_cycles[8];
+#else
+#define LBW_T0() do {} while (0)
+#define LBW_MARK(idx) do {} while (0)
+#endif
+
 namespace lbw {
 
 __device__ __forceinline__ double wsum(double v) {
@@ -387,10 +396,13 @@ __device__ __noinline__ int new_iteration(LbwState& s, int lane) {
   const int n = s.n;
   const bool act = lane < n;
   for (int guard = 0; guard < 4; guard++) {
+    LBW_T0();
     cauchy(s, lane);
+    LBW_MARK(1);
     const int nfree = __popc(__ballot_sync(0xffffffffu, act && s.iwhere[lane] <= 0));
     bool ok = true;
     if (nfree > 0 && s.col > 0) ok = subsm(s, lane);
+    LBW_MARK(2);
     if (!ok) { reset_memory(s, lane); continue; }
     const double dl = act ? s.z[lane] - s.x[lane] : 0.0;
     const double gl = act ? s.g[lane] : 0.0;
@@ -446,6 +458,7 @@ __device__ __noinline__ int new_iteration(LbwState& s, int lane) {
       }
     }
     code = bcast_flag(s, lane, code);
+    LBW_MARK(3);
     if (code == 1) return LB_DONE;
     if (code == 2) { reset_memory(s, lane); continue; }
     if (act) {
@@ -490,6 +503,7 @@ __device__ inline void lbw_init(LbwState& s, int n, const double* x0, const doub
 __device__ __noinline__ int lbw_feed(LbwState& s, double f, const double* g, int lane) {
   const int n = s.n;
   const bool act = lane < n;
+  LBW_T0();
   if (lane == 0) { s.f = f; s.f_last = f; }
   if (act) s.g[lane] = g[lane];
   __syncwarp();
@@ -579,7 +593,9 @@ __device__ __noinline__ int lbw_feed(LbwState& s, double f, const double* g, int
     __syncwarp();
     if (lane == 0) s.col += 1;
     __syncwarp();
+    LBW_MARK(4);
     lbw::rebuild_B(s, lane);
+    LBW_MARK(0);
   } else {
     __syncwarp();
   }

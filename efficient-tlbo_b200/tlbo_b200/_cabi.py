@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libtlbo_b200.so')
+LIB_PATH = os.environ.get('TLBO_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libtlbo_b200.so')
 
 HYP_STRIDE = 32
 MAX_D = 22
