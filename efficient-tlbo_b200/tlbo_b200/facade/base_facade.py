@@ -63,6 +63,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self._stage = None            # pinned staging buffers (created with the pack)
         self._overlap_hook = None     # host callback run while the batched fit is in flight
         self._p0_cache = None         # restart start points shared by every model of this facade
+        self._proto = None            # prototype of a freshly built target-side surrogate
 
     # ---- device pack ------------------------------------------------------------------
     def _ensure_pack(self, rows):
@@ -136,7 +137,12 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         model, apply the all-equal guard (mutating the caller's ``y``) and the facade-level
         normalisation.  Returns ``(model, X, y_normalised)`` for a later batched fit."""
         assert normalize in ['standardize', 'scale', 'none']
-        model = build_model(self.surrogate_type, self.config_space, np.random.RandomState(self.random_seed))
+        if self._proto is None:
+            self._proto = build_model(self.surrogate_type, self.config_space,
+                                      np.random.RandomState(self.random_seed))
+            self._share_start_points(self._proto)
+        # every build_model(type, cs, RandomState(seed)) call yields the same fresh model
+        model = self._proto.fresh_copy()
         if normalize == 'standardize':
             if (y == y[0]).all():
                 y[0] += 1e-4
@@ -145,7 +151,6 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             if (y == y[0]).all():
                 y[0] += 1e-4
             y, _, _ = zero_one_normalization(y)
-        self._share_start_points(model)
         model.bind(self._ensure_pack(X.shape[0]), slot)
         return model, X, y
 

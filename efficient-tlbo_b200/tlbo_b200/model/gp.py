@@ -58,12 +58,13 @@ class GaussianProcess(object):
         self.types = np.asarray(types)
         self.bounds = bounds
         self.kernel = kernel if kernel is not None else KernelInfo(self.types)
+        self._theta0 = self.kernel.theta.copy()
         self.alpha = alpha
         self.normalize_y = normalize_y
         self.n_opt_restarts = n_opt_restarts
         self.seed = seed
-        self.rng = np.random.RandomState(seed)
-        self.prior_rng = prior_rng if prior_rng is not None else np.random.RandomState(seed)
+        self._rng = None                      # created on first use (only the start-point draws need it)
+        self._prior_rng = prior_rng
         self.var_threshold = 10 ** -5          # base_model.py:86
         self.hypers = np.empty((0,))
         self.is_trained = False
@@ -73,6 +74,33 @@ class GaussianProcess(object):
         self._pack = None
         self._slot = 0
         self._p0_override = None     # facades share one set of start points (same seed -> same draws)
+
+    @property
+    def rng(self):
+        if self._rng is None:
+            self._rng = np.random.RandomState(self.seed)
+        return self._rng
+
+    @property
+    def prior_rng(self):
+        if self._prior_rng is None:
+            self._prior_rng = np.random.RandomState(self.seed)
+        return self._prior_rng
+
+    def fresh_copy(self):
+        """An untrained surrogate identical to a newly built one (default theta, same seed
+        and shared start points) without re-running the factory: what a facade needs six
+        times per iteration."""
+        import copy
+        m = copy.copy(self)
+        m.kernel = copy.copy(self.kernel)
+        m.kernel.theta = self._theta0.copy()
+        m.hypers = np.empty((0,))
+        m.is_trained = False
+        m.fit_info_ = None
+        m._pack, m._slot = None, 0
+        m._rng = None
+        return m
 
     # ---- pack placement ------------------------------------------------------------
     def bind(self, pack, slot):

@@ -182,17 +182,20 @@ def pack_view(pack, slot0, M):
 
 
 def _pad_batch(X_list, y_list, ncap, d):
-    """Host-side batch assembly -> pinned staging -> device."""
+    """Host-side batch assembly; ONE upload ([X | y | n] in a single float64 buffer)."""
     B = len(X_list)
-    Xh = np.zeros((B, ncap, d), dtype=np.float64)
-    yh = np.zeros((B, ncap), dtype=np.float64)
-    nh = np.zeros(B, dtype=np.int32)
+    nx, ny = B * ncap * d, B * ncap
+    buf = np.zeros(nx + ny + (B + 1) // 2 + 1, dtype=np.float64)
+    Xh = buf[:nx].reshape(B, ncap, d)
+    yh = buf[nx:nx + ny].reshape(B, ncap)
+    nh = buf[nx + ny:].view(np.int32)
     for b, (X, y) in enumerate(zip(X_list, y_list)):
         n = X.shape[0]
         Xh[b, :n] = X
         yh[b, :n] = y
         nh[b] = n
-    return h2d(Xh), h2d(yh), h2d(nh)
+    dbuf = h2d(buf)
+    return dbuf[:nx].view(B, ncap, d), dbuf[nx:nx + ny].view(B, ncap), dbuf[nx + ny:].view(torch.int32)[:B]
 
 
 class FitHandle(object):
