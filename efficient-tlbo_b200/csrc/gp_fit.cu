@@ -227,6 +227,18 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // __syncthreads, five 128-bit loads, a handful of selects and the tile FMAs -- no uniform
 // branches and no data-dependent branch (a non-positive pivot only raises a flag).
 // Developed against tools/ubench/elim*.cu: 820 -> 503 cycles per step on B200.
+__device__ __forceinline__ void sts2_if(double* p, double x, double y, bool pred) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.shared.v2.f64 [%0], {%1, %2}; }" ::"r"(addr), "d"(x), "d"(y),
+               "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void sts1_if(double* p, double x, bool pred) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(addr), "d"(x), "r"((int)pred)
+               : "memory");
+}
+
 struct ElimCtx {
   double* colbuf; double* pivs; int n; int tx, ty; bool diag_lower, own_diag; double ip_next; bool bad;
 };
@@ -239,15 +251,15 @@ __device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
   for (int kt = 0; kt < kend; kt++) {
     const int k = 16 * KB + kt;
     double* buf = c.colbuf + (kt & 1) * FIT_COLBUF;
-    if (tx == kt) {
-      double2* b2 = reinterpret_cast<double2*>(buf + ty * TP);
+    {
+      // branch-free publish (divergent branches on this path cost ~100 cycles per step):
+      // predicated 128-bit stores by the 16 owners of the pivot column, pivot + 1/pivot by its owner
+      const bool pub = (tx == kt), own = pub && (ty == kt);
 #pragma unroll
       for (int q = 0; q < TP; q += 2)
-        b2[q >> 1] = make_double2(a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0);
-      if (ty == kt) {
-        *reinterpret_cast<double2*>(buf + 384) = make_double2(a[KB][KB], c.ip_next);
-        c.pivs[k] = a[KB][KB];
-      }
+        sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, pub);
+      sts2_if(buf + 384, a[KB][KB], c.ip_next, own);
+      sts1_if(c.pivs + k, a[KB][KB], own);
     }
     const bool row_lt = ty < kt, row_eq = ty == kt, col_gt = tx > kt;
     __syncthreads();
@@ -283,10 +295,12 @@ __device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
         }
       }
     }
-    // the owner of the next pivot prepares its reciprocal
-    if (c.own_diag) {
-      if (kt < 15) { if (tx == kt + 1) c.ip_next = fast_rcp(a[KB][KB]); }
-      else if (KB + 1 < T) { if (tx == 0) c.ip_next = fast_rcp(a[(KB + 1 < T) ? KB + 1 : KB][(KB + 1 < T) ? KB + 1 : KB]); }
+    {
+      // speculative and branch-free: every thread inverts its own candidate for the next pivot
+      // (only the owner's value is ever published)
+      constexpr int KN = (KB + 1 < T) ? KB + 1 : KB;
+      const double pv = (kt < 15) ? a[KB][KB] : a[KN][KN];
+      c.ip_next = fast_rcp(pv);
     }
   }
 }
@@ -374,7 +388,7 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
   ElimCtx ec;
   ec.colbuf = S.colbuf; ec.pivs = S.piv; ec.n = n; ec.tx = tx; ec.ty = ty;
   ec.diag_lower = ty >= tx; ec.own_diag = ty == tx; ec.ip_next = 0.0; ec.bad = false;
-  if (tid == 0) ec.ip_next = fast_rcp(a[0][0]);
+  ec.ip_next = fast_rcp(a[0][0]);
   elim_all<T, 0>(a, ec);
   const bool ok = !__syncthreads_or(ec.bad ? 1 : 0);
   PHASE_MARK(2);

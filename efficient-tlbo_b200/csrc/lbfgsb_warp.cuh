@@ -92,38 +92,55 @@ __device__ __forceinline__ double projgr(const LbwState& s, int lane) {
 }
 
 // Column `lane` of B stays in registers across the col rank-2 updates (no shared-memory
-// round trip per pair); written back once.
-__device__ void rebuild_B(LbwState& s, int lane) {
+// round trip per pair); written back once.  NMAX (12 or 24) bounds the unrolled loops.
+template <int NMAX>
+__device__ void rebuild_B_t(LbwState& s, int lane) {
   const int n = s.n;
   const bool act = lane < n;
-  double Bc[LB_NMAX];
+  double Bc[NMAX];
 #pragma unroll
-  for (int j = 0; j < LB_NMAX; j++) Bc[j] = (j == lane) ? s.theta : 0.0;
+  for (int j = 0; j < NMAX; j++) Bc[j] = (j == lane) ? s.theta : 0.0;
   for (int k = 0; k < s.col; k++) {
     const double* sk = s.S[k];
     const double* yk = s.Y[k];
-    double a = 0.0;                                       // (B s_k)_lane
+    double skv[NMAX];
 #pragma unroll
-    for (int j = 0; j < LB_NMAX; j++)
-      if (j < n) a += Bc[j] * sk[j];
+    for (int j = 0; j < NMAX; j++) skv[j] = (j < n) ? sk[j] : 0.0;
+    // (B s_k)_lane, summed in the order of the single-thread statement
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) a += Bc[j] * skv[j];
     if (!act) a = 0.0;
     const double skl = act ? sk[lane] : 0.0, ykl = act ? yk[lane] : 0.0;
-    const double sBs = wsum(skl * a), ys = wsum(ykl * skl);
-    __syncwarp();
-    if (act) s.rr[lane] = a;                              // Bs, shared with the other lanes
-    __syncwarp();
-    const double i1 = 1.0 / sBs, i2 = 1.0 / ys;
+    double p1 = skl * a, p2 = ykl * skl;
 #pragma unroll
-    for (int j = 0; j < LB_NMAX; j++)
-      if (j < n) Bc[j] += yk[j] * ykl * i2 - s.rr[j] * a * i1;
+    for (int o = 16; o > 0; o >>= 1) {
+      p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+      p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+    }
+    const double i1 = 1.0 / p1, i2 = 1.0 / p2;            // 1 / s'Bs, 1 / y's
+    const double c1 = ykl * i2, c2 = a * i1;
+    // entry (j, lane) += y_j y_lane / y's - (Bs)_j (Bs)_lane / s'Bs ; (Bs)_j from lane j
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) {
+      const double bsj = __shfl_sync(0xffffffffu, a, j);
+      const double ykj = (j < n) ? yk[j] : 0.0;
+      Bc[j] += ykj * ykl * i2 - bsj * a * i1;
+    }
+    (void)c1; (void)c2;
   }
   __syncwarp();
   if (act) {
 #pragma unroll
-    for (int j = 0; j < LB_NMAX; j++)
+    for (int j = 0; j < NMAX; j++)
       if (j < n) s.B[j][lane] = Bc[j];
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ void rebuild_B(LbwState& s, int lane) {
+  if (s.n <= 12) rebuild_B_t<12>(s, lane);
+  else rebuild_B_t<LB_NMAX>(s, lane);
 }
 
 __device__ __forceinline__ void reset_memory(LbwState& s, int lane) {
@@ -231,9 +248,9 @@ __device__ bool solve_free(LbwState& s, int nsub, int lane) {
     }
     const double pk = __shfl_sync(0xffffffffu, v, k);
     if (!(pk > 0.0)) { ok = false; break; }
-    const double p = sqrt(pk);
-    if (act && lane == k) { s.Wk[k][k] = p; s.xp[k] = 1.0 / p; }
-    else if (act && lane > k) s.Wk[lane][k] = v / p;
+    const double rp = rsqrt(pk);                 // 1 / L_kk
+    if (act && lane == k) { s.Wk[k][k] = pk * rp; s.xp[k] = rp; }
+    else if (act && lane > k) s.Wk[lane][k] = v * rp;
     __syncwarp();
   }
   if (!ok) return false;
@@ -279,47 +296,54 @@ __device__ bool subsm(LbwState& s, int lane) {
   }
   __syncwarp();
   if (!solve_free(s, nsub, lane)) return false;
-  // projection step: scalar bookkeeping on lane 0 (cheap, rarely more than the clamp)
+  // projection step: every free lane clamps its own variable; the rare back-tracking branch
+  // (a clamp was active AND the projected direction is not a descent direction) keeps the
+  // exact sequential rule on lane 0
+  const double zl = act ? s.z[lane] : 0.0;
+  double znew = zl;
+  bool hit = false;
+  if (freev) {
+    double xk = lb::dmax(s.l[lane], zl + s.dsub[pos]);
+    xk = lb::dmin(s.u[lane], xk);
+    znew = xk;
+    hit = (xk == s.l[lane] || xk == s.u[lane]);
+  }
+  if (__ballot_sync(0xffffffffu, hit) == 0u) {
+    if (freev) s.z[lane] = znew;
+    __syncwarp();
+    return true;
+  }
+  const double dd_p = wsum(act ? (znew - s.x[lane]) * s.g[lane] : 0.0);
+  if (!(dd_p > 0.0)) {
+    if (freev) s.z[lane] = znew;
+    __syncwarp();
+    return true;
+  }
   if (lane == 0) {
-    int iword = 0;
-    for (int i = 0; i < n; i++) s.xp[i] = s.z[i];
+    // z still holds the Cauchy point here
+    double alpha = 1.0, temp1 = 1.0;
+    int ibd = -1;
     for (int a = 0; a < nsub; a++) {
       const int k = s.ind[a];
-      double xk = lb::dmax(s.l[k], s.z[k] + s.dsub[a]);
-      xk = lb::dmin(s.u[k], xk);
-      s.z[k] = xk;
-      if (xk == s.l[k] || xk == s.u[k]) iword = 1;
-    }
-    if (iword != 0) {
-      double dd_p = 0.0;
-      for (int i = 0; i < n; i++) dd_p += (s.z[i] - s.x[i]) * s.g[i];
-      if (dd_p > 0.0) {
-        for (int i = 0; i < n; i++) s.z[i] = s.xp[i];
-        double alpha = 1.0, temp1 = 1.0;
-        int ibd = -1;
-        for (int a = 0; a < nsub; a++) {
-          const int k = s.ind[a];
-          const double dk = s.dsub[a];
-          if (dk < 0.0) {
-            const double temp2 = s.l[k] - s.z[k];
-            if (temp2 >= 0.0) temp1 = 0.0;
-            else if (dk * alpha < temp2) temp1 = temp2 / dk;
-          } else if (dk > 0.0) {
-            const double temp2 = s.u[k] - s.z[k];
-            if (temp2 <= 0.0) temp1 = 0.0;
-            else if (dk * alpha > temp2) temp1 = temp2 / dk;
-          }
-          if (temp1 < alpha) { alpha = temp1; ibd = a; }
-        }
-        if (alpha < 1.0) {
-          const double dk = s.dsub[ibd];
-          const int k = s.ind[ibd];
-          if (dk > 0.0) { s.z[k] = s.u[k]; s.dsub[ibd] = 0.0; }
-          else if (dk < 0.0) { s.z[k] = s.l[k]; s.dsub[ibd] = 0.0; }
-        }
-        for (int a = 0; a < nsub; a++) s.z[s.ind[a]] += alpha * s.dsub[a];
+      const double dk = s.dsub[a];
+      if (dk < 0.0) {
+        const double temp2 = s.l[k] - s.z[k];
+        if (temp2 >= 0.0) temp1 = 0.0;
+        else if (dk * alpha < temp2) temp1 = temp2 / dk;
+      } else if (dk > 0.0) {
+        const double temp2 = s.u[k] - s.z[k];
+        if (temp2 <= 0.0) temp1 = 0.0;
+        else if (dk * alpha > temp2) temp1 = temp2 / dk;
       }
+      if (temp1 < alpha) { alpha = temp1; ibd = a; }
     }
+    if (alpha < 1.0) {
+      const double dk = s.dsub[ibd];
+      const int k = s.ind[ibd];
+      if (dk > 0.0) { s.z[k] = s.u[k]; s.dsub[ibd] = 0.0; }
+      else if (dk < 0.0) { s.z[k] = s.l[k]; s.dsub[ibd] = 0.0; }
+    }
+    for (int a = 0; a < nsub; a++) s.z[s.ind[a]] += alpha * s.dsub[a];
   }
   __syncwarp();
   return true;
