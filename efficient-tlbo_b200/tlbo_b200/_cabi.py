@@ -23,7 +23,7 @@ def ldl(ncap):
 class TlboPack(ctypes.Structure):
     """``struct tlbo_pack`` (include/tlbo_b200.h)."""
     _fields_ = [
-        ('M', c_int32), ('ncap', c_int32), ('d', c_int32), ('reserved', c_int32),
+        ('M', c_int32), ('ncap', c_int32), ('d', c_int32), ('nmax', c_int32),
         ('d_n', c_void_p), ('d_Xs', c_void_p), ('d_hyp', c_void_p), ('d_alpha', c_void_p),
         ('d_Linv', c_void_p), ('d_theta', c_void_p),
     ]

@@ -67,7 +67,7 @@ class EI(AbstractAcquisitionFunction):
             raise Exception('Model has to be trained first!')
         w = torch.ones(1, dtype=torch.float64, device=X_dev.device)
         return ops.predict_ei_fused(model._view(), model.types, w, None, X_dev, self.eta, par=self.par,
-                                    var_floor=self._var_floor(), **kw)
+                                    var_floor=self._var_floor(), nmax=model.n_train_, **kw)
 
     def _to_device(self, X):
         import torch

@@ -176,9 +176,11 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         dw = ops.h2d(np.ascontiguousarray(w, dtype=np.float64))
         dskip = None if skip is None else ops.h2d(np.ascontiguousarray(skip, dtype=np.int32))
         dorder = None if order is None else ops.h2d(np.ascontiguousarray(order, dtype=np.int32))
+        nmax = max([self.num_src_hpo_trial if self.K else 0, getattr(self.target_surrogate, 'n_train_', 0)] +
+                   [m.n_train_ for m in (self.source_surrogates or [])])
         return ops.predict_ei_fused(view, self.types, dw, dskip, X_dev, eta, par=par, var_floor=var_floor,
                                     keys=keys, excluded=excluded, idx_offset=idx_offset, mode=self._fused_mode,
-                                    order=dorder, want_rows=want_rows, ws=ws, sync=sync)
+                                    order=dorder, want_rows=want_rows, ws=ws, sync=sync, nmax=nmax)
 
     def _to_device(self, X):
         import torch

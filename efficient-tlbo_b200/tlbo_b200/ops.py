@@ -344,7 +344,7 @@ class FusedWorkspace(object):
 
 
 def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, keys=None, excluded=None,
-                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True):
+                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True, nmax=0):
     """``tlbo_predict_ei_fused``.  All array arguments are DEVICE tensors (cand [N, d],
     w [M], skip int32[M] or None, keys [N] or None, excluded sorted int64 or None).
     Returns (ei, key, idx, n_negative) of the best non-excluded row (host floats when
@@ -359,6 +359,7 @@ def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, 
         ei = torch.empty(N, dtype=F64, device=dev)
     n_excl = 0 if excluded is None else int(excluded.numel())
     t = _types_arr(types)
+    pack.c.nmax = int(nmax) if nmax and nmax > 0 else 0
     with _call('predict_ei_fused', 2):    # predict_ei_fused_kernel + argmax_final_kernel
         check(lib.tlbo_predict_ei_fused(pack.ref(), ptr(t), ptr(w), ptr(skip), ptr(order), int(mode), ptr(cand), N,
                                         float(eta), float(par), float(var_floor), ptr(keys),

@@ -53,7 +53,8 @@ typedef struct tlbo_pack {
   int32_t M;            /* number of surrogates                                   */
   int32_t ncap;         /* row capacity / stride                                  */
   int32_t d;            /* input columns                                          */
-  int32_t reserved;
+  int32_t nmax;         /* hint: largest n among the slots in use (0 = unknown -> ncap);
+                           sizes the shared-memory plan of the fused predict kernel        */
   int32_t* d_n;         /* [M]            observations per surrogate              */
   double* d_Xs;         /* [M, ncap, d]   permuted + scaled training inputs       */
   double* d_hyp;        /* [M, TLBO_HYP_STRIDE]                                   */
