@@ -92,43 +92,64 @@ extern "C" int tlbo_rank_loss_counts_normal(const double* d_y, const double* d_z
 
 // ---------------------------------------------------------------------------------------
 #define PL_THREADS 256
+#define PL_MAXM 64
 
+struct PlWeights { double w[PL_MAXM]; };
+
+// One CTA.  Phase 1: p = A w.  Phase 2: all n^2 ordered pairs spread over the 256 threads
+// (thread (r, c): row r, partners q = c, c + 4, ...), each pair with y_q > y_r contributes
+// log(1 + e^{p_r - p_q}) to the loss and +-sigma(p_r - p_q) to the per-row coefficients.
+// Phase 3: grad = A^T coef / #pairs.  hw != NULL: weights arrive as a kernel argument (no copy).
 __global__ void __launch_bounds__(PL_THREADS) pair_logistic_kernel(const double* __restrict__ A,
                                                                    const double* __restrict__ y,
-                                                                   const double* __restrict__ w, int n, int m,
+                                                                   const double* __restrict__ w, PlWeights hw,
+                                                                   int use_hw, int n, int m,
                                                                    double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* sp = reinterpret_cast<double*>(smem);   // predictions [n]
   double* sy = sp + n;                            // [n]
   double* sc = sy + n;                            // per-row gradient coefficient [n]
   double* red = sc + n;                           // [32]
+  double* sw = red + 32;                          // [m]
   const int tid = threadIdx.x, T = blockDim.x;
+  for (int k = tid; k < m; k += T) sw[k] = use_hw ? hw.w[k] : w[k];
+  __syncthreads();
   for (int i = tid; i < n; i += T) {
     double p = 0.0;
-    for (int k = 0; k < m; k++) p += A[(size_t)i * m + k] * w[k];
+    for (int k = 0; k < m; k++) p += A[(size_t)i * m + k] * sw[k];
     sp[i] = p;
     sy[i] = y[i];
+    sc[i] = 0.0;
   }
   __syncthreads();
   // Row r owns the pairs in which it is the LOWER-y member (reference pair (i, j) with
   // y_i > y_j has j = r): loss term log(1 + exp(p_r - p_i)), coefficient +s on row r, -s on row i.
   double loss = 0.0, npairs = 0.0;
-  for (int r = tid; r < n; r += T) {
-    const double yr = sy[r], pr = sp[r];
+  const int lanes_per_row = 4;
+  const int c = tid & (lanes_per_row - 1);
+  const int rows_per_pass = T / lanes_per_row;
+  for (int r0 = 0; r0 < n; r0 += rows_per_pass) {          // uniform trip count: shuffles below
+    const int r = r0 + tid / lanes_per_row;
+    const bool valid = r < n;
+    const double yr = valid ? sy[r] : 0.0, pr = valid ? sp[r] : 0.0;
     double coef = 0.0;
-    for (int q = 0; q < n; q++) {
-      const double yq = sy[q];
-      if (yq > yr) {
-        const double ez = exp(pr - sp[q]);
-        loss += log(1.0 + ez);
-        npairs += 1.0;
-        coef += ez / (1.0 + ez);
-      } else if (yq < yr) {
-        const double ez = exp(sp[q] - pr);
-        coef -= ez / (1.0 + ez);
+    if (valid) {
+      for (int q = c; q < n; q += lanes_per_row) {
+        const double yq = sy[q];
+        if (yq > yr) {
+          const double ez = exp(pr - sp[q]);
+          loss += log(1.0 + ez);
+          npairs += 1.0;
+          coef += ez / (1.0 + ez);
+        } else if (yq < yr) {
+          const double ez = exp(sp[q] - pr);
+          coef -= ez / (1.0 + ez);
+        }
       }
     }
-    sc[r] = coef;
+    coef += __shfl_xor_sync(0xffffffffu, coef, 1);
+    coef += __shfl_xor_sync(0xffffffffu, coef, 2);
+    if (valid && c == 0) sc[r] = coef;
   }
   const double tl = block_sum(loss, red);
   const double tp = block_sum(npairs, red);
@@ -141,14 +162,28 @@ __global__ void __launch_bounds__(PL_THREADS) pair_logistic_kernel(const double*
   }
 }
 
-extern "C" int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const double* d_w, int n,
-                                                int m, double* d_out, void* stream) {
+static int pair_logistic_launch(const double* d_A, const double* d_y, const double* d_w, const double* h_w, int n,
+                                int m, double* d_out, void* stream) {
   if (n <= 0 || m <= 0) { tlbo_set_error("bad n/m"); return TLBO_E_BADARG; }
-  const size_t smem = (3 * (size_t)n + 32) * sizeof(double);
+  if (h_w && m > PL_MAXM) { tlbo_set_error("m too large for host-side weights"); return TLBO_E_TOOLARGE; }
+  const size_t smem = (3 * (size_t)n + 32 + m) * sizeof(double);
   if (smem > 200 * 1024) { tlbo_set_error("n too large for pairwise_logistic"); return TLBO_E_TOOLARGE; }
   if (smem > 48 * 1024)
     TLBO_CUDA_CHECK(cudaFuncSetAttribute(pair_logistic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pair_logistic_kernel<<<1, PL_THREADS, smem, (cudaStream_t)stream>>>(d_A, d_y, d_w, n, m, d_out);
+  PlWeights hw;
+  if (h_w) for (int k = 0; k < m; k++) hw.w[k] = h_w[k];
+  pair_logistic_kernel<<<1, PL_THREADS, smem, (cudaStream_t)stream>>>(d_A, d_y, d_w, hw, h_w ? 1 : 0, n, m, d_out);
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const double* d_w, int n,
+                                                int m, double* d_out, void* stream) {
+  return pair_logistic_launch(d_A, d_y, d_w, nullptr, n, m, d_out, stream);
+}
+
+extern "C" int tlbo_pairwise_logistic_loss_grad_hw(const double* d_A, const double* d_y, const double* h_w, int n,
+                                                   int m, double* d_out, void* stream) {
+  if (!h_w) { tlbo_set_error("NULL h_w"); return TLBO_E_BADARG; }
+  return pair_logistic_launch(d_A, d_y, nullptr, h_w, n, m, d_out, stream);
 }

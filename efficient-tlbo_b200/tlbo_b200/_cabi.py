@@ -48,6 +48,7 @@ SYMBOLS = {
     'tlbo_rank_loss_counts': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
     'tlbo_rank_loss_counts_normal': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     'tlbo_pairwise_logistic_loss_grad': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
+    'tlbo_pairwise_logistic_loss_grad_hw': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     'tlbo_fp64_peak_probe': (c_int, [_P, _P]),
 }
 

@@ -36,6 +36,7 @@ class OBTLV(BaseFacade):
         self.hist_ws = list()
         self.iteration_id = 0
         self.target_y_range = None
+        self._side = None             # CUDA stream of the phase-1 weight solve
 
     def batch_predict(self, X):
         """topo_variant1.py:27-35: [n, K] source means at X."""
@@ -54,26 +55,39 @@ class OBTLV(BaseFacade):
             jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
         for j, job in enumerate(jobs):
             job[0].bind(self._pack, K + j)
+        import torch
         from tlbo_b200 import ops
         X_dev = self._to_device(X)                       # before the fit is enqueued
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)                     # X_dev and the source slots are ready
         finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
         self.target_surrogate = jobs[0][0]
         self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        # Phase 1 (source weights) depends only on the SOURCE surrogates: it runs on a side
+        # stream -- source predictions at X plus the SLSQP callbacks -- while the batched fit of
+        # the target + CV surrogates occupies the main stream.
         if self._overlap_hook is not None:
-            self._overlap_hook()                         # host work overlapped with the device fit
-        view = ops.pack_view(self._pack, 0, K + 1 + len(folds))
-        mu_dev, _ = ops.gp_predict(view, self.types, X_dev)
+            self._overlap_hook()                         # tie keys etc., overlapped with the fit
+        with torch.cuda.stream(self._side):
+            mu_src_dev, _ = ops.gp_predict(ops.pack_view(self._pack, 0, K), self.types, X_dev)
+            pred_y = np.ascontiguousarray(ops.d2h(mu_src_dev).T)
+            self.learn_source_weights(pred_y, y)
+        main.wait_stream(self._side)
+        mu = None
+        if len(folds):
+            view = ops.pack_view(self._pack, K + 1, len(folds))
+            mu_cv_dev, _ = ops.gp_predict(view, self.types, X_dev)
         finish_fit()
-        mu = ops.d2h(mu_dev)
-        pred_y = np.ascontiguousarray(mu[:K].T)
-
-        self.learn_source_weights(pred_y, y)
+        if len(folds):
+            mu = ops.d2h(mu_cv_dev)
         w_source = self.w[:K]               # a view: the in-place scaling below is the reference's
         w_target = 0.
         if do_cv:
             _t_pred_y = np.empty(instance_num)
             for i, (lo, hi) in enumerate(folds):
-                _t_pred_y[lo:hi] = mu[K + 1 + i, lo:hi]
+                _t_pred_y[lo:hi] = mu[i, lo:hi]
             _pred_y = np.c_[pred_y, _t_pred_y.reshape((-1, 1))]
             w_target = self.compute_target_weight(_pred_y, y)
             if instance_num >= 2 * self.min_num_y:

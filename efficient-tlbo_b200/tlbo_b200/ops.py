@@ -110,8 +110,10 @@ class PinnedStage(object):
             buf = torch.empty(round_up(nbytes, 4096), dtype=torch.uint8).pin_memory()
             self.bufs[tag] = buf
         src = torch.from_numpy(arr)
-        view = buf[:arr.nbytes].view(src.dtype).reshape(src.shape) if arr.nbytes else src
-        view.copy_(src)
+        if not arr.nbytes:
+            return src.to(_dev())
+        view = buf[:arr.nbytes].view(src.dtype).reshape(src.shape)
+        view.numpy()[...] = arr                      # plain memcpy (see OfflineSearch.prepare)
         STATS.h2d += arr.nbytes
         return view.to(_dev(), non_blocking=True)
 
@@ -422,17 +424,21 @@ def rank_loss_counts_normal(y, z, loc, scale, src, row_lo, row_hi, sync=True):
 
 
 class PairLogistic(object):
-    """``tlbo_pairwise_logistic_loss_grad`` with A and y resident on the device across
-    the SLSQP callbacks of one ``scipy_solve``."""
+    """Pairwise logistic ranking loss + gradient with A and y resident on the device across
+    the SLSQP callbacks of one ``scipy_solve``.  Per callback: ONE launch with the weights as
+    a kernel argument, the result written straight into mapped pinned host memory, one stream
+    synchronisation (no host<->device memcpy)."""
 
     def __init__(self, A, y):
-        dev = _dev()
+        _dev()
         A = np.ascontiguousarray(A, dtype=np.float64)
         self.n, self.m = A.shape
         self.dA = h2d(A)
         self.dy = h2d(np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1)))
-        self.dw = torch.zeros(self.m, dtype=F64, device=dev)
-        self.out = torch.zeros(2 + self.m, dtype=F64, device=dev)
+        self.host_w = self.m <= 64
+        self.dw = None if self.host_w else torch.zeros(self.m, dtype=F64, device=self.dA.device)
+        self.out = torch.zeros(2 + self.m, dtype=F64).pin_memory()      # device-visible (UVA)
+        self.out_np = self.out.numpy()
         self._cache_w = None
         self._cache = None
 
@@ -440,12 +446,20 @@ class PairLogistic(object):
         w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
         if self._cache_w is not None and np.array_equal(w, self._cache_w):
             return self._cache
-        self.dw.copy_(torch.from_numpy(w))
-        STATS.h2d += w.nbytes
+        stream = torch.cuda.current_stream()
+        sptr = ctypes.c_void_p(stream.cuda_stream)
         with _call('pairwise_logistic', 1):
-            check(lib.tlbo_pairwise_logistic_loss_grad(ptr(self.dA), ptr(self.dy), ptr(self.dw), self.n, self.m,
-                                                       ptr(self.out), _stream()))
-        o = d2h(self.out)
+            if self.host_w:
+                check(lib.tlbo_pairwise_logistic_loss_grad_hw(ptr(self.dA), ptr(self.dy), ptr(w), self.n, self.m,
+                                                              ptr(self.out), sptr))
+            else:
+                self.dw.copy_(torch.from_numpy(w))
+                check(lib.tlbo_pairwise_logistic_loss_grad(ptr(self.dA), ptr(self.dy), ptr(self.dw), self.n, self.m,
+                                                           ptr(self.out), sptr))
+        STATS.h2d += w.nbytes
+        stream.synchronize()
+        STATS.d2h += self.out_np.nbytes
+        o = self.out_np
         self._cache_w = w.copy()
         self._cache = (float(o[0]), int(o[1]), o[2:].copy())
         return self._cache

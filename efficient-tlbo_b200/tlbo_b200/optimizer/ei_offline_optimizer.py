@@ -47,6 +47,7 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         self.X_dev = self._host_rows.to('cuda', non_blocking=True)
         self._ws = ops.FusedWorkspace()
         self._keys_host = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+        self._keys_host_np = self._keys_host.numpy()     # same memory; filled with a plain memcpy
         self._keys_dev = torch.empty(hi - lo, dtype=torch.float64, device='cuda')
         self.last_best = None
         self._prepared = None
@@ -72,7 +73,9 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         import torch
         from tlbo_b200 import ops
         keys = self.rng.rand(self.N)
-        self._keys_host.copy_(torch.from_numpy(keys[self.lo:self.hi]))
+        # numpy memcpy into the pinned buffer: torch's multi-threaded CPU copy_ stalls for
+        # milliseconds when it contends with the BLAS threads of scipy's SLSQP
+        self._keys_host_np[:] = keys[self.lo:self.hi]
         self._keys_dev.copy_(self._keys_host, non_blocking=True)
         ops.STATS.h2d += self._keys_host.numel() * 8
         ex = None

@@ -174,6 +174,11 @@ int tlbo_rank_loss_counts_normal(const double* d_y, const double* d_z, const dou
  *   d_A [n, m] predictions, d_y [n], d_w [m];  d_out [2 + m] = (loss, #pairs, grad[m]). */
 int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const double* d_w, int n, int m,
                                      double* d_out, void* stream);
+/* Same, with the weight vector taken from HOST memory (m <= 64) and passed as a kernel argument:
+ * one SLSQP callback = one launch, no host -> device copy.  d_out may be mapped pinned host
+ * memory (unified addressing), so the callback only has to synchronise the stream.           */
+int tlbo_pairwise_logistic_loss_grad_hw(const double* d_A, const double* d_y, const double* h_w, int n, int m,
+                                        double* d_out, void* stream);
 
 /* Device-rate probes used by bench.py for the roofline denominators (FP64 FMA pipe and
  * FP64 mma.sync rate are not in MEASURED_PEAKS.json).  Returns achieved TFLOP/s in
