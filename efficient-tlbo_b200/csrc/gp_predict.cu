@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
                 h1 += (xs[p + 1] != u1.y) ? hk[(p + 1 - DCP) < DKP ? (p + 1 - DCP) : 0] : 0.0;
               }
             }
-            double k0 = matern_hamming(c, s0, h0), k1 = matern_hamming(c, s1, h1);
+            double k0 = matern_hamming_fast(c, s0, h0), k1 = matern_hamming_fast(c, s1, h1);
             k0 = (j0 < n) ? k0 : 0.0;
             k1 = (j1 < n) ? k1 : 0.0;
             mpart[w] += k0 * s_alpha[j0];
@@ -334,10 +334,17 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
         const int rows = (nib * 8 - r0 < a.rc_rows) ? nib * 8 - r0 : a.rc_rows;
         __syncthreads();
         {
-          // only columns < r0 + rows are ever read (lower triangular)
+          // only columns < r0 + rows are ever read (lower triangular): copy that many, not ldl
           const double* src = gL + (size_t)r0 * ldl;
-          const int cnt = rows * ldl;
-          for (int idx = tid; idx < cnt; idx += PRED_THREADS) s_Linv[idx] = src[idx];
+          const int ncol = (r0 + rows + 3) & ~3;
+          const int c4 = ncol >> 2;                       // 4-column groups per row
+          for (int idx = tid; idx < rows * c4; idx += PRED_THREADS) {
+            const int rr = idx / c4, cc = (idx - rr * c4) << 2;
+            const double2 v0 = *reinterpret_cast<const double2*>(src + (size_t)rr * ldl + cc);
+            const double2 v1 = *reinterpret_cast<const double2*>(src + (size_t)rr * ldl + cc + 2);
+            *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc) = v0;
+            *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc + 2) = v1;
+          }
         }
         __syncthreads();
         for (int ib = 0; ib * 8 < rows; ib += 2) {
