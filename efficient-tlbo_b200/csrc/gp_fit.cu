@@ -67,21 +67,21 @@ struct FitWs {
 __host__ __device__ inline int fit_lda(int n) { return (n & 1) ? n : n + 1; }
 
 // pair tables of the register-panel path: index table always (tile > 0), value caches when
-// they fit beside the panel (tile <= 5, i.e. n <= 79)
-__host__ __device__ inline size_t fit_pair_bytes(int ncap, int tile) {
+// they fit beside the panel (decided by the host plan)
+__host__ __device__ inline size_t fit_pair_bytes(int ncap, int tile, int cache) {
   if (tile <= 0) return 0;
   const size_t np = (size_t)ncap * (ncap - 1) / 2 + 2;
-  return ((np * 4 + 15) / 16) * 16 + (tile <= 5 ? 2 * np * sizeof(double) : 0);
+  return ((np * 4 + 15) / 16) * 16 + (cache ? 2 * np * sizeof(double) : 0);
 }
-__host__ inline size_t fit_small_bytes(int ncap, int d, int tile) {
+__host__ inline size_t fit_small_bytes(int ncap, int d, int tile, int cache) {
   // Xr, Xs, y, piv, dinv, alpha, red, hyp, colbuf, pair tables
   return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8) +
-         fit_pair_bytes(ncap, tile);
+         fit_pair_bytes(ncap, tile, cache);
 }
 __host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
 
 __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* panel_global, int n, int ncap,
-                                         int d, int tile) {
+                                         int d, int tile, int cache) {
   double* p = reinterpret_cast<double*>(smem);
   S.n = n; S.d = d; S.lda = fit_lda(n);
   S.Xr = p; p += (size_t)ncap * d;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* 
   S.pairs = nullptr; S.Kc = nullptr; S.Cg = nullptr;
   if (tile > 0) {
     const size_t np = (size_t)ncap * (ncap - 1) / 2 + 2;
-    if (tile <= 5) { S.Kc = p; p += np; S.Cg = p; p += np; }
+    if (cache) { S.Kc = p; p += np; S.Cg = p; p += np; }
     S.pairs = reinterpret_cast<int*>(p);
     p += ((np * 4 + 15) / 16) * 2;
   }
@@ -712,6 +712,8 @@ __device__ __forceinline__ bool nll_eval_any(const FitWs& S, const SpaceDesc& sp
 __host__ inline int panel_tile_for(int ncap) {
   if (ncap + 1 <= 64) return 4;
   if (ncap + 1 <= 80) return 5;
+  if (ncap + 1 <= 96) return 6;
+  if (ncap + 1 <= 112) return 7;
   if (ncap + 1 <= 128) return 8;
   return 0;
 }
@@ -726,6 +728,7 @@ struct FitArgs {
   double* restart_theta; double* restart_f; int32_t* restart_info;
   double* panels;        // global panels (NULL -> shared memory)
   size_t panel_stride;   // doubles
+  int cache;             // pair-value caches present in the shared-memory plan
 };
 
 // Optimiser state size in shared memory (either variant).
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   LbwState* sw = reinterpret_cast<LbwState*>(smem);
   unsigned char* rest = smem + fit_state_bytes();
   FitWs S;
-  carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d, T);
+  carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d, T, a.cache);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.p0[(size_t)r * H + tid];
   __syncthreads();
@@ -830,7 +833,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_factorize_kernel(FacArgs a)
   __shared__ double th[TLBO_HMAX];
   __shared__ int best;
   FitWs S;
-  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, ncap, d, 0);
+  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, ncap, d, 0, 0);
   load_problem(S, a.sp, a.X + (size_t)b * ncap * d, a.y + (size_t)b * ncap, ncap);
   if (tid == 0) {
     // gp.py:241-248: first strict improvement wins
@@ -919,6 +922,7 @@ struct NllArgs {
   SpaceDesc sp;
   const double* theta; double* nll; double* grad; int32_t* status;
   double* panels; size_t panel_stride;
+  int cache;
 };
 
 template <int DMAX, int T>
@@ -930,7 +934,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) 
   __shared__ double th[TLBO_HMAX];
   __shared__ double fg[1 + TLBO_HMAX];
   FitWs S;
-  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, a.ncap, d, T);
+  carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, a.ncap, d, T, a.cache);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.theta[(size_t)b * H + tid];
   __syncthreads();
@@ -965,6 +969,7 @@ extern "C" int tlbo_set_fit_variant(int variant) {
 
 struct WorkLayout {
   int tile;              // register-panel tile (0 = shared-memory panel path)
+  int cache;             // pair-value caches (Kc, Cg) fit in shared memory
   bool global_panels;
   size_t smem_fit, smem_fac;
   size_t panel_stride;   // doubles
@@ -975,9 +980,12 @@ static WorkLayout plan(int ncap, int d) {
   const size_t panel = fit_panel_bytes(ncap);
   const size_t st = fit_state_bytes();
   int tile = g_fit_variant != 0 ? panel_tile_for(ncap) : 0;
-  size_t small = fit_small_bytes(ncap, d, tile);
-  if (tile > 0 && st + small + panel + 1024 > kSmemLimit) { tile = 0; small = fit_small_bytes(ncap, d, 0); }
+  int cache = tile > 0 ? 1 : 0;
+  size_t small = fit_small_bytes(ncap, d, tile, cache);
+  if (tile > 0 && st + small + panel + 1024 > kSmemLimit) { cache = 0; small = fit_small_bytes(ncap, d, tile, 0); }
+  if (tile > 0 && st + small + panel + 1024 > kSmemLimit) { tile = 0; small = fit_small_bytes(ncap, d, 0, 0); }
   w.tile = tile;
+  w.cache = cache;
   w.global_panels = (st + small + panel + 1024) > kSmemLimit;
   w.smem_fit = st + small + (w.global_panels ? 0 : panel);
   w.smem_fac = small + (w.global_panels ? 0 : panel);
@@ -1068,6 +1076,7 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
   a.p0 = d_p0; a.lo = d_lo; a.hi = d_hi; a.do_optimize = do_optimize;
   a.restart_theta = rt; a.restart_f = rf; a.restart_info = ri;
   a.panels = w.global_panels ? panels : nullptr; a.panel_stride = w.panel_stride;
+  a.cache = w.cache;
 #define TLBO_LAUNCH_FIT(DM, WO, TT)                                          \
   do {                                                                       \
     rc = set_smem(gp_fit_kernel<DM, WO, TT>, w.smem_fit);                    \
@@ -1079,6 +1088,8 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
     switch (tile) {                                                          \
       case 4: TLBO_LAUNCH_FIT(DM, true, 4); break;                           \
       case 5: TLBO_LAUNCH_FIT(DM, true, 5); break;                           \
+      case 6: TLBO_LAUNCH_FIT(DM, true, 6); break;                           \
+      case 7: TLBO_LAUNCH_FIT(DM, true, 7); break;                           \
       case 8: TLBO_LAUNCH_FIT(DM, true, 8); break;                           \
       default: TLBO_LAUNCH_FIT(DM, true, 0); break;                          \
     }                                                                        \
@@ -1135,6 +1146,7 @@ extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, co
   a.X = d_X; a.y = d_y; a.n = d_n; a.B = B; a.ncap = ncap; a.d = d; a.sp = sp;
   a.theta = d_theta; a.nll = d_nll; a.grad = d_grad; a.status = d_status;
   a.panels = w.global_panels ? (double*)d_work : nullptr; a.panel_stride = w.panel_stride;
+  a.cache = w.cache;
   if (w.global_panels && !d_work) { tlbo_set_error("workspace required for this ncap"); return TLBO_E_BADARG; }
 #define TLBO_LAUNCH_NLL(DM, TT)                                              \
   do {                                                                       \
@@ -1147,6 +1159,8 @@ extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, co
     switch (tile) {                                                          \
       case 4: TLBO_LAUNCH_NLL(DM, 4); break;                                 \
       case 5: TLBO_LAUNCH_NLL(DM, 5); break;                                 \
+      case 6: TLBO_LAUNCH_NLL(DM, 6); break;                                 \
+      case 7: TLBO_LAUNCH_NLL(DM, 7); break;                                 \
       case 8: TLBO_LAUNCH_NLL(DM, 8); break;                                 \
       default: TLBO_LAUNCH_NLL(DM, 0); break;                                \
     }                                                                        \

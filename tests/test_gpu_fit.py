@@ -86,7 +86,7 @@ def test_fit_without_optimize_keeps_default_theta():
     np.testing.assert_allclose(var[0].cpu().numpy(), vo.ravel(), rtol=1e-6, atol=1e-12)
 
 
-@pytest.mark.parametrize('n,types', [(40, RF_TYPES), (60, np.zeros(5, int))])
+@pytest.mark.parametrize('n,types', [(40, RF_TYPES), (60, np.zeros(5, int)), (72, RF_TYPES), (100, np.zeros(5, int))])
 def test_warp_optimiser_tracks_single_thread_statement(n, types):
     """The warp-cooperative L-BFGS-B (default) against the single-thread statement of the same
     algorithm (the one cross-checked against scipy on the host): same optimum per restart up
