@@ -84,6 +84,22 @@ def build_workload(task, seed, pool, K, n0, n_tasks=30):
     return dict(types=types, sources=sources, Xt=Xt, yt=yt, rows0=[int(r) for r in rows0], seed=seed)
 
 
+def fit_flops(models, d_cont, d_cat):
+    """SURVEY.md 8(d) algorithmic flops of the NLL + gradient evaluations one batched fit
+    actually performed (sum over surrogates and restarts of nfev)."""
+    H = d_cont + d_cat + 2
+    f, evals = 0.0, 0
+    for m in models:
+        info = m.fit_info_
+        if info is None:
+            continue
+        n = m.n_train_
+        nfev = int(info['restart_info'][:, 0].sum())
+        evals += nfev
+        f += nfev * (n * n * (3 * d_cont + 2 * d_cat + 12) + n ** 3 / 3.0 + 2.0 * n ** 3 + 2.0 * n * n * H)
+    return f, evals
+
+
 def fused_flops_per_candidate(n_list, d_cont, d_cat):
     """SURVEY.md 8(d) algorithmic flops of one candidate through the surrogates actually
     evaluated (triangular L^-1 form: n^2 + 2n for the quadratic form)."""
@@ -353,6 +369,7 @@ def run_ours(args):
         ops.STATS.reset()
         ops.STATS.timing = record_flops
         flops = 0.0
+        fitfl, fitev = 0.0, 0
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -365,17 +382,20 @@ def run_ours(args):
                 skip = list(getattr(fac, 'ignored_flag', [False] * fac.K))
                 ns = [50 for k in range(fac.K) if not skip[k]] + [n_t]
                 flops += fused_flops_per_candidate(ns, d_cont, d_cat) * args.pool
+                ff, fe = fit_flops(getattr(fac, 'last_fit_models', []), d_cont, d_cat)
+                fitfl += ff
+                fitev += fe
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
         ops.STATS.timing = False
-        return ms, wall, flops
+        return ms, wall, (flops, fitfl, fitev)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_res, wall_res, flops = timed(False, True)
+    ms_res, wall_res, (flops, fitfl, fitev) = timed(False, True)
     kms = ops.STATS.kernel_ms()
     launches = ops.STATS.total_launches()
     launch_detail = dict(ops.STATS.launches)
@@ -443,6 +463,17 @@ def run_ours(args):
                 'triangular L^-1 form, over the surrogates actually evaluated' % (
                     flops / max(fused_calls, 1) / alg_bytes),
     }
+    fit_calls, fit_ms = kms.get('gp_fit', (0, 0.0))
+    dominant = max(kms.items(), key=lambda kv: kv[1][1])[0] if kms else None
+    roofline_fit = {
+        'kernel': 'gp_fit_kernel (+ gp_factorize_kernel)', 'bound': 'latency',
+        'achieved': fitfl / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else 0.0, 'peak': dmma_tf[0], 'unit': 'TFLOP/s',
+        'frac': (fitfl / (fit_ms * 1e-3) / 1e12 / dmma_tf[0]) if fit_ms > 0 else None,
+        'nll_evaluations_per_launch': fitev / max(fit_calls, 1), 'avg_launch_ms': fit_ms / max(fit_calls, 1),
+        'us_per_sequential_evaluation_note': 'one CTA per (surrogate, restart) runs its L-BFGS-B evaluations '
+        'back to back; the launch lasts as long as the slowest restart (see DESIGN.md 3.1, tools/phase_fit.py)',
+        'peak_source': 'FP64 FMA-pipe rate measured by tlbo_fp64_peak_probe in this run',
+    }
     step_ms = ms_res / K
     breakdown = {k: {'calls_per_step': c / float(K), 'ms_per_step': t / K, 'share_of_step': t / ms_res}
                  for k, (c, t) in kms.items()}
@@ -455,7 +486,8 @@ def run_ours(args):
                 'api': 'SMBO_OFFLINE.iterate() with the candidate table re-uploaded from pinned host memory '
                        'every step and the selected row read back'},
         'gpu_launches': launches, 'gpu_launch_detail': launch_detail,
-        'clocks': clocks, 'roofline': roofline, 'step_breakdown': breakdown,
+        'clocks': clocks, 'roofline': roofline, 'roofline_fit': roofline_fit, 'dominant_kernel': dominant,
+        'step_breakdown': breakdown,
         'predict_candidates_per_s': args.pool * fused_calls / (fused_ms * 1e-3) if fused_ms > 0 else None,
         'host_wall_ms_per_step': 1e3 * wall_res / K,
     }

@@ -332,36 +332,55 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
   double* A = S.A;
   PHASE_T0();
   __syncthreads();
-  if (tid < d) {
-    const double l = exp(theta[1 + tid]);
-    if (tid < dc) { S.hyp[tid] = l; }
-    else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+  // every thread needs the scale of "its" column (p = tid & 31 < d <= 22): one exp per thread,
+  // no shared-memory round trip before the scaling pass
+  const int pcol = tid & 31;
+  double myscale = 1.0;
+  if (pcol < d) {
+    const double l = exp(theta[1 + pcol]);
+    myscale = (pcol < dc) ? 1.0 / l : 1.0;
+    if (tid < d) {
+      if (tid < dc) { S.hyp[tid] = l; }
+      else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+    }
   }
   const double c = exp(theta[0]);
   const double noise = exp(theta[d + 1]);
-  __syncthreads();
-  for (int idx = tid; idx < n * d; idx += NT) {
-    const int p = idx % d;
-    double v = S.Xr[idx];
-    if (p < dc) v = v / S.hyp[p];
-    S.Xs[idx] = v;
-  }
+  if (pcol < d)
+    for (int i = tid >> 5; i < n; i += NT >> 5) S.Xs[(size_t)i * d + pcol] = S.Xr[(size_t)i * d + pcol] * myscale;
   __syncthreads();
   PHASE_MARK(0);
   // kernel matrix (lower triangle, diagonal, y row) through shared memory: ONE copy of the
   // exp / sqrt code over the pair table, then every thread picks up its register tile
-  for (int q = tid; q < S.npairs; q += NT) {
-    const int ij = S.pairs[q], i = ij >> 16, j = ij & 0xffff;
-    const double* xi = S.Xs + (size_t)i * d;
-    const double* xj = S.Xs + (size_t)j * d;
-    double s = 0.0, hs = 0.0;
-    for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
-    for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
-    const double t = sqrt(s) * SQRT5;
-    const double ce = c * exp(-t - hs);
-    const double v = ce * (1.0 + t + t * t / 3.0);
-    A[(size_t)i * lda + j] = v;
-    if (S.Kc) { S.Kc[q] = v; S.Cg[q] = ce * (5.0 / 3.0) * (t + 1.0); }
+  // two pairs in flight per thread (independent sqrt / exp chains)
+  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
+    const int q1 = q0 + NT;
+    const bool has1 = q1 < S.npairs;
+    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
+    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
+    const double* xi0 = S.Xs + (size_t)i0 * d;
+    const double* xj0 = S.Xs + (size_t)j0 * d;
+    const double* xi1 = S.Xs + (size_t)i1 * d;
+    const double* xj1 = S.Xs + (size_t)j1 * d;
+    double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+    for (int p = 0; p < dc; p++) {
+      const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+      s0 += e0 * e0; s1 += e1 * e1;
+    }
+    for (int p = dc; p < d; p++) {
+      const double hp = S.hyp[p];
+      h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
+      h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
+    }
+    const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
+    const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
+    const double v0 = ce0 * (1.0 + t0 + t0 * t0 / 3.0), v1 = ce1 * (1.0 + t1 + t1 * t1 / 3.0);
+    A[(size_t)i0 * lda + j0] = v0;
+    if (S.Kc) { S.Kc[q0] = v0; S.Cg[q0] = ce0 * (5.0 / 3.0) * (t0 + 1.0); }
+    if (has1) {
+      A[(size_t)i1 * lda + j1] = v1;
+      if (S.Kc) { S.Kc[q1] = v1; S.Cg[q1] = ce1 * (5.0 / 3.0) * (t1 + 1.0); }
+    }
   }
   for (int j = tid; j < n; j += NT) {
     A[(size_t)j * lda + j] = c + noise;
@@ -544,29 +563,50 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   double gacc[DMAX];
 #pragma unroll
   for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
-  for (int q = tid; q < S.npairs; q += NT) {
-    const int ij = S.pairs[q], i = ij >> 16, j = ij & 0xffff;
-    const double W = A[(size_t)i * lda + j];
-    const double* xi = S.Xs + (size_t)i * d;
-    const double* xj = S.Xs + (size_t)j * d;
-    double WK, coef;
+  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
+    const int q1 = q0 + NT;
+    const bool has1 = q1 < S.npairs;
+    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
+    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
+    const double W0 = A[(size_t)i0 * lda + j0];
+    const double W1 = has1 ? A[(size_t)i1 * lda + j1] : 0.0;        // a masked second pair adds zeros
+    const double* xi0 = S.Xs + (size_t)i0 * d;
+    const double* xj0 = S.Xs + (size_t)j0 * d;
+    const double* xi1 = S.Xs + (size_t)i1 * d;
+    const double* xj1 = S.Xs + (size_t)j1 * d;
+    double WK0, WK1, cf0, cf1;
     if (S.Kc) {
-      WK = W * S.Kc[q];
-      coef = W * S.Cg[q];
+      WK0 = W0 * S.Kc[q0]; cf0 = W0 * S.Cg[q0];
+      WK1 = W1 * S.Kc[has1 ? q1 : q0]; cf1 = W1 * S.Cg[has1 ? q1 : q0];
     } else {
-      double s = 0.0, hs = 0.0;
-      for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
-      for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
-      const double t = sqrt(s) * SQRT5;
-      const double ce = c * exp(-t - hs);
-      WK = W * (ce * (1.0 + t + t * t / 3.0));
-      coef = W * (ce * (5.0 / 3.0) * (t + 1.0));
+      double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+      for (int p = 0; p < dc; p++) {
+        const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+        s0 += e0 * e0; s1 += e1 * e1;
+      }
+      for (int p = dc; p < d; p++) {
+        const double hp = S.hyp[p];
+        h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
+        h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
+      }
+      const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
+      const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
+      WK0 = W0 * (ce0 * (1.0 + t0 + t0 * t0 / 3.0)); cf0 = W0 * (ce0 * (5.0 / 3.0) * (t0 + 1.0));
+      WK1 = W1 * (ce1 * (1.0 + t1 + t1 * t1 / 3.0)); cf1 = W1 * (ce1 * (5.0 / 3.0) * (t1 + 1.0));
     }
-    g0 += WK;
+    g0 += WK0;
+    g0 += WK1;
 #pragma unroll
     for (int p = 0; p < DMAX; p++) {
-      if (p < dc) { const double df = xi[p] - xj[p]; gacc[p] += coef * (df * df); }
-      else if (p < d) { if (xi[p] != xj[p]) gacc[p] += WK * S.hyp[TLBO_HMAX + p]; }
+      if (p < dc) {
+        const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+        gacc[p] += cf0 * (e0 * e0);
+        gacc[p] += cf1 * (e1 * e1);
+      } else if (p < d) {
+        const double h3 = S.hyp[TLBO_HMAX + p];
+        gacc[p] += (xi0[p] != xj0[p]) ? WK0 * h3 : 0.0;
+        gacc[p] += (xi1[p] != xj1[p]) ? WK1 * h3 : 0.0;
+      }
     }
   }
   for (int i = tid; i < n; i += NT) {
@@ -578,16 +618,20 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
   __syncthreads();
   {
-    double v = warp_sum(g0);
-    if (lane == 0) S.red[wid * 32 + 0] = v;
-    v = warp_sum(gn);
-    if (lane == 0) S.red[wid * 32 + (d + 1)] = v;
+    // one interleaved butterfly over all H slots (independent shuffles pipeline)
 #pragma unroll
-    for (int p = 0; p < DMAX; p++) {
-      if (p < d) {
-        v = warp_sum(gacc[p]);
-        if (lane == 0) S.red[wid * 32 + 1 + p] = v;
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+      gn += __shfl_xor_sync(0xffffffffu, gn, o);
+#pragma unroll
+      for (int p = 0; p < DMAX; p++) gacc[p] += __shfl_xor_sync(0xffffffffu, gacc[p], o);
+    }
+    if (lane == 0) {
+      S.red[wid * 32 + 0] = g0;
+      S.red[wid * 32 + (d + 1)] = gn;
+#pragma unroll
+      for (int p = 0; p < DMAX; p++)
+        if (p < d) S.red[wid * 32 + 1 + p] = gacc[p];
     }
   }
   __syncthreads();

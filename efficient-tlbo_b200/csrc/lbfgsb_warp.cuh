@@ -436,21 +436,25 @@ __device__ __noinline__ int new_iteration(LbwState& s, int lane) {
     double stpmx = 1.0e10;
     if (s.iter == 0) stpmx = 1.0;
     else {
-      // lane 0 keeps the exact sequential update (the comparison uses the running value)
-      if (act) s.d[lane] = dl;
+      // every lane forms its bound ratio (the divisions run in parallel); lane 0 then applies the
+      // exact sequential rule of lnsrlb (the comparison uses the running value)
+      double a2 = 0.0, ratio = 0.0;
+      if (act) {
+        a2 = (dl < 0.0) ? s.l[lane] - s.x[lane] : s.u[lane] - s.x[lane];
+        ratio = (dl != 0.0) ? a2 / dl : 0.0;
+        s.d[lane] = dl; s.dd[lane] = a2; s.tb[lane] = ratio;
+      }
       __syncwarp();
       if (lane == 0) {
         double m = 1.0e10;
         for (int i = 0; i < n; i++) {
-          const double a1 = s.d[i];
+          const double a1 = s.d[i], b2 = s.dd[i];
           if (a1 < 0.0) {
-            const double a2 = s.l[i] - s.x[i];
-            if (a2 >= 0.0) m = 0.0;
-            else if (a1 * m < a2) m = a2 / a1;
+            if (b2 >= 0.0) m = 0.0;
+            else if (a1 * m < b2) m = s.tb[i];
           } else if (a1 > 0.0) {
-            const double a2 = s.u[i] - s.x[i];
-            if (a2 <= 0.0) m = 0.0;
-            else if (a1 * m > a2) m = a2 / a1;
+            if (b2 <= 0.0) m = 0.0;
+            else if (a1 * m > b2) m = s.tb[i];
           }
         }
         s.stpmx = m;

@@ -28,6 +28,7 @@ class _BootstrapRankingFacade(BaseFacade):
     def _ranking_losses(self, X, y):
         """Everything of rgpe.py:24-109 up to (and including) the loss table
         ``int64[num_sample, K + 1]`` and the arg-min histogram."""
+        import torch
         from tlbo_b200 import ops
         K = self.K
         instance_num = len(y)
@@ -62,13 +63,26 @@ class _BootstrapRankingFacade(BaseFacade):
             for fold in range(self.k_fold_num):
                 row_lo.append(fold_num * fold)
                 row_hi.append(instance_num if fold == self.k_fold_num - 1 else (fold + 1) * fold_num)
-        X_dev = self._to_device(X)
-        y_dev = ops.h2d(np.asarray(y, dtype=np.float64))
-        src_dev = ops.h2d(np.asarray(rows, dtype=np.int32))
-        lo_dev = ops.h2d(np.asarray(row_lo, dtype=np.int32))
-        hi_dev = ops.h2d(np.asarray(row_hi, dtype=np.int32))
+        # one upload: [X | y | src, lo, hi (int32 pairs)] in a single float64 buffer
+        Xh = np.array(X, dtype=np.float64)
+        Xh[~np.isfinite(Xh)] = -1
+        nx, nr = Xh.size, len(rows)
+        hb = np.empty(nx + instance_num + 3 * ((nr + 1) // 2), dtype=np.float64)
+        hb[:nx] = Xh.ravel()
+        hb[nx:nx + instance_num] = y
+        ib = hb[nx + instance_num:].view(np.int32)
+        nr2 = 2 * ((nr + 1) // 2)
+        ib[0:nr] = rows
+        ib[nr2:nr2 + nr] = row_lo
+        ib[2 * nr2:2 * nr2 + nr] = row_hi
+        db = ops.h2d(hb)
+        X_dev = db[:nx].view(instance_num, Xh.shape[1])
+        y_dev = db[nx:nx + instance_num]
+        dib = db[nx + instance_num:].view(torch.int32)
+        src_dev, lo_dev, hi_dev = dib[0:nr], dib[nr2:nr2 + nr], dib[2 * nr2:2 * nr2 + nr]
         finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
         self.target_surrogate = jobs[0][0]
+        self.last_fit_models = [j[0] for j in jobs]
 
         # ---- host work overlapped with the device fit
         # bootstrap draws: sample-major, then source 0..K-1, then fold 0..4, n normals each --

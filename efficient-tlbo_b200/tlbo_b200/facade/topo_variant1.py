@@ -64,6 +64,7 @@ class OBTLV(BaseFacade):
         self._side.wait_stream(main)                     # X_dev and the source slots are ready
         finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
         self.target_surrogate = jobs[0][0]
+        self.last_fit_models = [j[0] for j in jobs]
         self.target_y_range = 0.5 * (np.max(y) - np.min(y))
         # Phase 1 (source weights) depends only on the SOURCE surrogates: it runs on a side
         # stream -- source predictions at X plus the SLSQP callbacks -- while the batched fit of

@@ -183,6 +183,30 @@ def _check_train_args(model, X, Y):
         raise ValueError('X.shape[0] (%s) != y.shape[0] (%s)' % (X.shape[0], Y.shape[0]))
 
 
+class _LazyFitInfo(object):
+    """Per-restart results of a batched fit, read back from the device on first access only."""
+
+    def __init__(self, handle):
+        self._dev = {'restart_theta': handle.rt, 'restart_f': handle.rf, 'restart_info': handle.ri}
+        self._host = {}
+
+    def host(self, key):
+        if key not in self._host:
+            from tlbo_b200 import ops
+            self._host[key] = ops.d2h(self._dev[key])
+        return self._host[key]
+
+
+class _FitInfoView(object):
+    """``fit_info_`` of one surrogate: ``['restart_theta' | 'restart_f' | 'restart_info']``."""
+
+    def __init__(self, lazy, b):
+        self._lazy, self._b = lazy, b
+
+    def __getitem__(self, key):
+        return self._lazy.host(key)[self._b]
+
+
 def fit_models(models, Xs, Ys, do_optimize=True):
     """Train several ``GaussianProcess`` objects in one batched device launch (see
     ``fit_models_async``)."""
@@ -242,8 +266,9 @@ def fit_models_async(models, Xs, Ys, do_optimize=True):
     def finish():
         for g, h in zip(groups, handles):
             m0 = g[0][0]
-            st, rt, rf, ri = h.finish(return_restarts=True)
+            st = h.finish()
             thetas = ops.d2h(m0._pack.theta[m0._slot:m0._slot + len(g)])
+            lazy = _LazyFitInfo(h)
             for b, (mdl, X, y, p0) in enumerate(g):
                 if st[b] == 1:
                     # the reference's final GaussianProcessRegressor.fit raises (gp.py:146)
@@ -255,6 +280,6 @@ def fit_models_async(models, Xs, Ys, do_optimize=True):
                 mdl.kernel.theta = thetas[b].copy()
                 mdl.is_trained = True
                 mdl.n_train_ = X.shape[0]
-                mdl.fit_info_ = dict(restart_theta=rt[b], restart_f=rf[b], restart_info=ri[b])
+                mdl.fit_info_ = _FitInfoView(lazy, b)
         return models
     return finish
