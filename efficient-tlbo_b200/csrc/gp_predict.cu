@@ -152,6 +152,8 @@ struct FusedArgs {
   const double* keys; const long long* excluded; int n_excl; long long idx_offset;
   double* mu; double* var; double* ei;
   double* partial;       // [grid, 4]
+  const double* cmu; const double* cvar; int ncached;   // resident per-surrogate posteriors [ncached, N]
+  double* pm_mu; double* pm_var;                        // optional per-surrogate outputs [M, N]
   int rc_rows;           // Linv rows per shared-memory chunk (multiple of 16)
   int njmax;             // j-steps (of 4 training rows) the shared-memory plan provides for
 };
@@ -215,6 +217,24 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
       if (a.skip && a.skip[m]) continue;
       const int n = a.pack.d_n[m];
       if (n <= 0) continue;
+      if (a.cmu && m < a.ncached) {
+        // this surrogate's posterior over the pool is resident in HBM (it does not depend on
+        // the target observations): two coalesced 8-byte reads per candidate instead of n
+        // kernel evaluations and an n x n contraction
+        if (lane < WC) {
+          const long long row = row0 + wid * WC + lane;
+          const double mu_m = (row < a.N) ? a.cmu[(size_t)m * a.N + row] : 0.0;
+          const double var_m = (row < a.N) ? a.cvar[(size_t)m * a.N + row] : 0.0;
+          if (a.mode == 0) {
+            acc_mu += wm * mu_m;
+            acc_var += wm * wm * var_m;
+          } else {
+            if (mi == 0) { acc_mu = mu_m; acc_var = var_m; }
+            else { acc_mu += wm * mu_m; wsum += wm; }
+          }
+        }
+        continue;
+      }
       __syncthreads();
       {
         const double* gX = a.pack.d_Xs + (size_t)m * ncap * d;
@@ -400,6 +420,10 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
         if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;
         const double mu_m = mean * ystd + ymean;
         const double var_m = var * (ystd * ystd);
+        if (a.pm_mu) {
+          const long long prow = row0 + wid * WC + lane;
+          if (prow < a.N) { a.pm_mu[(size_t)m * a.N + prow] = mu_m; a.pm_var[(size_t)m * a.N + prow] = var_m; }
+        }
         if (a.mode == 0) {
           acc_mu += wm * mu_m;
           acc_var += wm * wm * var_m;
@@ -552,7 +576,7 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, F
 
 extern "C" int64_t tlbo_predict_ei_workspace_bytes(int64_t N) {
   (void)N;
-  return (int64_t)(296 * 4 * sizeof(double) + 256);
+  return (int64_t)((296 * 4 + 8 + 256 + 8) * sizeof(double) + 256);
 }
 
 template <int NW, int DCP, int DKP, int MINB>
@@ -564,12 +588,12 @@ static int fused_launch(const FusedArgs& a, const FusedPlan& pl, cudaStream_t s)
   return 0;
 }
 
-extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
-                                     const int32_t* d_skip, const int32_t* d_order, int mode,
-                                     const double* d_cand, int64_t N,
-                                     double eta, double par, double var_floor, const double* d_keys,
-                                     const int64_t* d_excluded, int n_excl, int64_t idx_offset, double* d_best,
-                                     double* d_mu, double* d_var, double* d_ei, void* d_work, void* stream) {
+static int fused_entry(const tlbo_pack* pack, const int32_t* h_types, const double* d_w, const int32_t* d_skip,
+                       const int32_t* d_order, int mode, const double* d_cand, int64_t N, double eta, double par,
+                       double var_floor, const double* d_keys, const int64_t* d_excluded, int n_excl,
+                       int64_t idx_offset, double* d_best, double* d_mu, double* d_var, double* d_ei,
+                       const double* d_cache_mu, const double* d_cache_var, int n_cached, double* d_model_mu,
+                       double* d_model_var, void* d_work, void* stream) {
   if (!pack || N <= 0 || !d_w || !d_cand || !d_best || !d_work) { tlbo_set_error("bad arguments"); return TLBO_E_BADARG; }
   if (pack->ncap % 8 != 0) { tlbo_set_error("pack ncap must be a multiple of 8"); return TLBO_E_BADARG; }
   FusedArgs a;
@@ -585,6 +609,9 @@ extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_typ
   a.eta = eta; a.par = par; a.var_floor = var_floor;
   a.keys = d_keys; a.excluded = (const long long*)d_excluded; a.n_excl = d_excluded ? n_excl : 0;
   a.idx_offset = idx_offset; a.mu = d_mu; a.var = d_var; a.ei = d_ei;
+  a.cmu = (d_cache_mu && d_cache_var && n_cached > 0) ? d_cache_mu : nullptr;
+  a.cvar = d_cache_var; a.ncached = n_cached;
+  a.pm_mu = (d_model_mu && d_model_var) ? d_model_mu : nullptr; a.pm_var = d_model_var;
   a.partial = (double*)d_work; a.rc_rows = pl.rc_rows; a.njmax = pl.njmax;
   cudaStream_t s = (cudaStream_t)stream;
   if (pl.dcp == 8 && pl.dkp == 2) rc = (pl.nw == 2) ? fused_launch<2, 8, 2, 2>(a, pl, s) : fused_launch<4, 8, 2, 1>(a, pl, s);
@@ -597,4 +624,42 @@ extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_typ
   argmax_final_kernel<<<1, 32, 0, s>>>(a.partial, pl.grid, d_best);
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
+                                     const int32_t* d_skip, const int32_t* d_order, int mode,
+                                     const double* d_cand, int64_t N,
+                                     double eta, double par, double var_floor, const double* d_keys,
+                                     const int64_t* d_excluded, int n_excl, int64_t idx_offset, double* d_best,
+                                     double* d_mu, double* d_var, double* d_ei, void* d_work, void* stream) {
+  return fused_entry(pack, h_types, d_w, d_skip, d_order, mode, d_cand, N, eta, par, var_floor, d_keys, d_excluded,
+                     n_excl, idx_offset, d_best, d_mu, d_var, d_ei, nullptr, nullptr, 0, nullptr, nullptr, d_work,
+                     stream);
+}
+
+extern "C" int tlbo_predict_ei_fused_cached(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
+                                            const int32_t* d_skip, const int32_t* d_order, int mode,
+                                            const double* d_cand, int64_t N, double eta, double par,
+                                            double var_floor, const double* d_keys, const int64_t* d_excluded,
+                                            int n_excl, int64_t idx_offset, double* d_best, double* d_mu,
+                                            double* d_var, double* d_ei, const double* d_cache_mu,
+                                            const double* d_cache_var, int n_cached, void* d_work, void* stream) {
+  return fused_entry(pack, h_types, d_w, d_skip, d_order, mode, d_cand, N, eta, par, var_floor, d_keys, d_excluded,
+                     n_excl, idx_offset, d_best, d_mu, d_var, d_ei, d_cache_mu, d_cache_var, n_cached, nullptr,
+                     nullptr, d_work, stream);
+}
+
+extern "C" int tlbo_predict_pool_posteriors(const tlbo_pack* pack, const int32_t* h_types, const double* d_cand,
+                                            int64_t N, double* d_model_mu, double* d_model_var, void* d_work,
+                                            void* stream) {
+  if (!pack || !d_model_mu || !d_model_var || !d_work) { tlbo_set_error("bad arguments"); return TLBO_E_BADARG; }
+  // ensemble outputs are not wanted: unit weights, no exclusion; the arg-max result lands in the
+  // tail of the workspace and is ignored
+  double* scratch = (double*)d_work;
+  double* d_w = scratch + 296 * 4 + 8;
+  double* d_best = d_w + 256;
+  if (pack->M > 256) { tlbo_set_error("too many surrogates for tlbo_predict_pool_posteriors"); return TLBO_E_TOOLARGE; }
+  TLBO_CUDA_CHECK(cudaMemsetAsync(d_w, 0, sizeof(double) * 256, (cudaStream_t)stream));
+  return fused_entry(pack, h_types, d_w, nullptr, nullptr, 0, d_cand, N, 0.0, 0.0, 0.0, nullptr, nullptr, 0, 0, d_best,
+                     nullptr, nullptr, nullptr, nullptr, nullptr, 0, d_model_mu, d_model_var, d_work, stream);
 }

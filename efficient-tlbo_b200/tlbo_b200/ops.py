@@ -346,7 +346,7 @@ class FusedWorkspace(object):
 
 
 def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, keys=None, excluded=None,
-                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True, nmax=0):
+                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True, nmax=0, cache=None):
     """``tlbo_predict_ei_fused``.  All array arguments are DEVICE tensors (cand [N, d],
     w [M], skip int32[M] or None, keys [N] or None, excluded sorted int64 or None).
     Returns (ei, key, idx, n_negative) of the best non-excluded row (host floats when
@@ -363,10 +363,19 @@ def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, 
     t = _types_arr(types)
     pack.c.nmax = int(nmax) if nmax and nmax > 0 else 0
     with _call('predict_ei_fused', 2):    # predict_ei_fused_kernel + argmax_final_kernel
-        check(lib.tlbo_predict_ei_fused(pack.ref(), ptr(t), ptr(w), ptr(skip), ptr(order), int(mode), ptr(cand), N,
-                                        float(eta), float(par), float(var_floor), ptr(keys),
-                                        ptr(excluded) if n_excl else None, n_excl, int(idx_offset), ptr(ws.best),
-                                        ptr(mu), ptr(var), ptr(ei), ptr(ws.work), _stream()))
+        if cache is None:
+            check(lib.tlbo_predict_ei_fused(pack.ref(), ptr(t), ptr(w), ptr(skip), ptr(order), int(mode), ptr(cand), N,
+                                            float(eta), float(par), float(var_floor), ptr(keys),
+                                            ptr(excluded) if n_excl else None, n_excl, int(idx_offset), ptr(ws.best),
+                                            ptr(mu), ptr(var), ptr(ei), ptr(ws.work), _stream()))
+        else:
+            cmu, cvar = cache
+            assert cmu.shape[1] == N and cvar.shape == cmu.shape and cmu.is_contiguous() and cvar.is_contiguous()
+            check(lib.tlbo_predict_ei_fused_cached(pack.ref(), ptr(t), ptr(w), ptr(skip), ptr(order), int(mode),
+                                                   ptr(cand), N, float(eta), float(par), float(var_floor), ptr(keys),
+                                                   ptr(excluded) if n_excl else None, n_excl, int(idx_offset),
+                                                   ptr(ws.best), ptr(mu), ptr(var), ptr(ei), ptr(cmu), ptr(cvar),
+                                                   int(cmu.shape[0]), ptr(ws.work), _stream()))
     if not sync:
         return ws.best, mu, var, ei
     b = d2h(ws.best)
@@ -374,6 +383,22 @@ def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, 
     if want_rows:
         return res, mu, var, ei
     return res
+
+
+def predict_pool_posteriors(pack, types, cand, nmax=0, ws=None):
+    """``tlbo_predict_pool_posteriors``: per-surrogate posterior mean / variance of every slot of
+    ``pack`` over a resident candidate pool; returns device tensors ``mu, var [M, N]``."""
+    dev = cand.device
+    N = int(cand.shape[0])
+    ws = ws or FusedWorkspace()
+    mu = torch.empty(pack.M, N, dtype=F64, device=dev)
+    var = torch.empty(pack.M, N, dtype=F64, device=dev)
+    t = _types_arr(types)
+    pack.c.nmax = int(nmax) if nmax and nmax > 0 else 0
+    with _call('predict_pool_posteriors', 2):
+        check(lib.tlbo_predict_pool_posteriors(pack.ref(), ptr(t), ptr(cand), N, ptr(mu), ptr(var), ptr(ws.work),
+                                               _stream()))
+    return mu, var
 
 
 def rank_loss_counts(y, ys, row_lo, row_hi, upper_only=False):

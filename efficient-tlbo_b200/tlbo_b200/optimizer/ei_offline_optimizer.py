@@ -49,6 +49,11 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         self._keys_host = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
         self._keys_host_np = self._keys_host.numpy()     # same memory; filled with a plain memcpy
         self._keys_dev = torch.empty(hi - lo, dtype=torch.float64, device='cuda')
+        # the table is fixed for the lifetime of this maximiser: let an ensemble facade keep its
+        # source surrogates' posteriors over it resident
+        model = getattr(acquisition_function, 'model', None)
+        if hasattr(model, 'register_static_pool'):
+            model.register_static_pool(self.X_dev)
         self.last_best = None
         self._prepared = None
         self._stage = ops.PinnedStage()

@@ -149,6 +149,25 @@ int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const d
                           double* d_ei, void* d_work, void* stream);
 int64_t tlbo_predict_ei_workspace_bytes(int64_t N);
 
+/* Resident per-surrogate posteriors.  The source surrogates of a facade never change after
+ * build_source_surrogates (tlbo/facade/base_facade.py:58-91) and OfflineSearch scores the SAME
+ * candidate table every iteration (tlbo/optimizer/ei_offline_optimizer.py:20-29), so their
+ * posterior mean / variance over the pool -- which the reference recomputes in every
+ * RGPE.predict / combine_predictions call -- is computed ONCE and kept in HBM:
+ *   tlbo_predict_pool_posteriors fills d_model_mu / d_model_var [M, N] (un-standardised, GP-level
+ *   1e-10 clip applied) for every slot of `pack`;
+ *   tlbo_predict_ei_fused_cached is tlbo_predict_ei_fused with slots m < n_cached read from
+ *   d_cache_mu / d_cache_var [n_cached, N] instead of being evaluated.  Results are bit-identical
+ *   to the uncached call (same values, same accumulation order).                               */
+int tlbo_predict_pool_posteriors(const tlbo_pack* pack, const int32_t* h_types, const double* d_cand, int64_t N,
+                                 double* d_model_mu, double* d_model_var, void* d_work, void* stream);
+int tlbo_predict_ei_fused_cached(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
+                                 const int32_t* d_skip, const int32_t* d_order, int mode, const double* d_cand,
+                                 int64_t N, double eta, double par, double var_floor, const double* d_keys,
+                                 const int64_t* d_excluded, int n_excl, int64_t idx_offset, double* d_best,
+                                 double* d_mu, double* d_var, double* d_ei, const double* d_cache_mu,
+                                 const double* d_cache_var, int n_cached, void* d_work, void* stream);
+
 /* Integer mis-ranked-pair counts -- replaces the pure-Python loops of RGPE.train /
  * TransBO_RGPE.train (tlbo/facade/rgpe.py:74-104, topo.py:72-104) and TST.train
  * (tlbo/facade/tst.py:37-43).

@@ -191,3 +191,30 @@ def test_gp_train_validation_errors():
     mu, var = m.predict(X)
     assert mu.shape == (10, 1) and var.shape == (10, 1)
     assert np.abs(mu.ravel() - y).max() < 0.05
+
+
+def test_resident_pool_posteriors_are_bit_identical(forced):
+    """The fused call with the source surrogates' posteriors read from the HBM-resident cache
+    returns exactly the bits of the uncached call (per-row mu / var / EI and the selected row)."""
+    import torch
+    seed = 2854
+    types, sources, (Xt, yt) = _bench(5, 4000, seed)
+    cs, prod = _make('topo', types, sources, seed)
+    X, y = Xt[:15].copy(), yt[:15].copy()
+    prod.train(X, y.copy())
+    from tlbo_b200 import ops
+    Xd = ops.h2d(Xt)
+    keys = ops.h2d(np.random.RandomState(3).rand(Xt.shape[0]))
+    ex = ops.h2d(np.arange(15, dtype=np.int64))
+    eta = float(np.min((y - y.mean()) / y.std()))
+    r0, m0, v0, e0 = prod._fused(Xd, eta=eta, var_floor=1e-10, keys=keys, excluded=ex, want_rows=True)
+    prod.register_static_pool(Xd)
+    assert prod._pool_cache
+    r1, m1, v1, e1 = prod._fused(Xd, eta=eta, var_floor=1e-10, keys=keys, excluded=ex, want_rows=True)
+    assert r0 == r1
+    assert torch.equal(m0, m1) and torch.equal(v0, v1) and torch.equal(e0, e1)
+    # cached values are the per-surrogate predictions
+    cmu, cvar = list(prod._pool_cache.values())[0]
+    mo, vo = prod.source_surrogates[2].predict(Xt[:300])
+    np.testing.assert_allclose(cmu[2, :300].cpu().numpy(), mo.ravel(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(cvar[2, :300].cpu().numpy(), vo.ravel(), rtol=1e-10, atol=1e-16)
