@@ -107,7 +107,9 @@ class PinnedStage(object):
         nbytes = max(arr.nbytes, 8)
         buf = self.bufs.get(tag)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(round_up(nbytes, 4096), dtype=torch.uint8).pin_memory()
+            # geometric growth: pinning is a ~0.3 ms driver call, and e.g. the bootstrap-draw
+            # buffer grows by a few KB every BO iteration
+            buf = torch.empty(round_up(max(2 * nbytes, 1 << 16), 4096), dtype=torch.uint8).pin_memory()
             self.bufs[tag] = buf
         src = torch.from_numpy(arr)
         if not arr.nbytes:

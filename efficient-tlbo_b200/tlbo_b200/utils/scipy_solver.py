@@ -15,8 +15,10 @@ def scipy_solve(A, b, loss_type=3, debug=False):
     n, m = A.shape
     dev_loss = ops.PairLogistic(A, b)
 
-    ineq_cons = {'type': 'ineq', 'fun': lambda x: np.array(x), 'jac': lambda x: np.eye(len(x))}
-    eq_cons = {'type': 'eq', 'fun': lambda x: np.array([sum(x) - 1]), 'jac': lambda x: np.array([1.] * len(x))}
+    # same constraint functions as the reference; the constant Jacobians are built once
+    eye_m, ones_m = np.eye(m), np.array([1.] * m)
+    ineq_cons = {'type': 'ineq', 'fun': lambda x: np.array(x), 'jac': lambda x: eye_m}
+    eq_cons = {'type': 'eq', 'fun': lambda x: np.array([sum(x) - 1]), 'jac': lambda x: ones_m}
     x0 = np.array([1. / m] * m)
 
     def f(x):
