@@ -64,7 +64,8 @@ class SMBO_OFFLINE(object):
         self.acquisition_function = EI(self.model)
         table = self.X_table if self.configuration_list is None else self.configuration_list
         self.acq_optimizer = OfflineSearch(table, self.acquisition_function, config_space,
-                                           rng=np.random.RandomState(self.random_seed), shard=shard)
+                                           rng=np.random.RandomState(self.random_seed), shard=shard,
+                                           prefetch_keys=True)
         self.random_configuration_chooser = ChooserProb(prob=0.001, rng=np.random.RandomState(self.random_seed))
         self.incumbent_value = None
         self.timing = dict(train=0.0, maximize=0.0)

@@ -25,7 +25,8 @@ class AcquisitionFunctionMaximizer(object):
 
 
 class OfflineSearch(AcquisitionFunctionMaximizer):
-    def __init__(self, configuration_list, acquisition_function, config_space, rng=None, shard=None):
+    def __init__(self, configuration_list, acquisition_function, config_space, rng=None, shard=None,
+                 prefetch_keys=False):
         super().__init__(acquisition_function, config_space, rng)
         import torch
         from tlbo_b200 import ops
@@ -46,8 +47,16 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         self._host_rows = torch.from_numpy(X[lo:hi]).pin_memory()
         self.X_dev = self._host_rows.to('cuda', non_blocking=True)
         self._ws = ops.FusedWorkspace()
-        self._keys_host = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
-        self._keys_host_np = self._keys_host.numpy()     # same memory; filled with a plain memcpy
+        # two pinned staging buffers for the tie-break keys (same memory as numpy views)
+        self._keys_host = [torch.empty(hi - lo, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self._keys_host_np = [t.numpy() for t in self._keys_host]
+        self._keys_flip = 0
+        # prefetch_keys: the keys of the NEXT maximisation -- rng.rand(N), independent of the BO
+        # state -- are drawn by a worker thread (numpy releases the GIL) while the current
+        # iteration runs.  Only valid when `rng` is owned by this maximiser (SMBO_OFFLINE's is).
+        self._prefetch = bool(prefetch_keys)
+        self._pool = None
+        self._future = None
         self._keys_dev = torch.empty(hi - lo, dtype=torch.float64, device='cuda')
         # the table is fixed for the lifetime of this maximiser: let an ensemble facade keep its
         # source surrogates' posteriors over it resident
@@ -77,16 +86,28 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         kernel is in flight."""
         import torch
         from tlbo_b200 import ops
-        keys = self.rng.rand(self.N)
-        # numpy memcpy into the pinned buffer: torch's multi-threaded CPU copy_ stalls for
-        # milliseconds when it contends with the BLAS threads of scipy's SLSQP
-        self._keys_host_np[:] = keys[self.lo:self.hi]
-        self._keys_dev.copy_(self._keys_host, non_blocking=True)
-        ops.STATS.h2d += self._keys_host.numel() * 8
+        slot = self._draw_keys() if self._future is None else self._future.result()
+        self._future = None
+        self._keys_dev.copy_(self._keys_host[slot], non_blocking=True)
+        ops.STATS.h2d += self._keys_host[slot].numel() * 8
+        if self._prefetch:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=1)
+            self._future = self._pool.submit(self._draw_keys)
         ex = None
         if len(evaluated_rows):
             ex = self._stage.upload('excluded', np.sort(np.asarray(evaluated_rows, dtype=np.int64)))
         self._prepared = (ex,)
+
+    def _draw_keys(self):
+        """One ``rng.rand(N)`` (the reference's tie-break draw) into the next pinned buffer.
+        numpy memcpy, not torch copy_: torch's multi-threaded CPU copy stalls for milliseconds
+        when it contends with the BLAS threads of scipy's SLSQP."""
+        keys = self.rng.rand(self.N)
+        self._keys_flip ^= 1
+        self._keys_host_np[self._keys_flip][:] = keys[self.lo:self.hi]
+        return self._keys_flip
 
     def best_unevaluated(self, evaluated_rows):
         """Row index the reference's loop would return: first entry of the descending
