@@ -39,7 +39,7 @@ def _bench(K, N, seed, kind='rf', d=None):
     return b['types'], sources, b['tables'][0]
 
 
-def _make(method, types, sources, seed):
+def _make(method, types, sources, seed, **kw):
     from tlbo_b200.config_space import TableSpace
     from tlbo_b200.facade.notl import NoTL
     from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
@@ -47,7 +47,7 @@ def _make(method, types, sources, seed):
     from tlbo_b200.facade.tst import TST
     cs = TableSpace(types)
     cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, tst=TST, notl=NoTL)[method]
-    prod = cls(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+    prod = cls(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50, **kw)
     return cs, prod
 
 
@@ -68,6 +68,7 @@ def _make_oracle(method, types, sources, seed, prod, forced):
 
 @pytest.mark.parametrize('method,K,N,iters,kind,d', [
     ('rgpe', 4, 3000, 16, 'rf', None),
+    ('rgpe_regrow', 3, 1500, 70, 'rf', None),
     ('trans_rgpe', 3, 2000, 14, 'rf', None),
     ('topo', 4, 3000, 14, 'rf', None),
     ('tst', 3, 2000, 9, 'rf', None),
@@ -77,7 +78,12 @@ def test_offline_loop_matches_oracle(method, K, N, iters, kind, d, forced):
     from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
     seed = 4465
     types, sources, (Xt, yt) = _bench(K, N, seed, kind, d)
-    cs, prod = _make(method, types, sources, seed)
+    kw = {}
+    if method == 'rgpe_regrow':
+        # long run from a deliberately small pack: exercises pack growth (sources copied to the new
+        # pack while their pool posteriors stay resident) and the larger panel tiles of the fit
+        method, kw = 'rgpe', dict(max_target_rows=8)
+    cs, prod = _make(method, types, sources, seed, **kw)
     ora = _make_oracle(method, types, sources, seed, prod, forced)
     assert not forced.queue
     smbo = SMBO_OFFLINE((Xt, yt), cs, prod, random_seed=seed, max_runs=iters)      # seeds np.random
