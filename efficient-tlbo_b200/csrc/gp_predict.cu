@@ -143,6 +143,33 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                : "d"(a), "d"(b));
 }
 
+// ---- TMA (bulk async copy) staging of the candidate tile -------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                            unsigned long long* bar) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(gmem_src), "r"(bytes), "r"(mb)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (int spin = 0; spin < (1 << 26); spin++) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    if (done) return;
+  }
+  asm volatile("trap;");       // never hang the device on a lost transaction
+}
+
 struct FusedArgs {
   tlbo_pack pack;
   SpaceDesc sp;
@@ -186,17 +213,39 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
   double* s_comb = s_spill + (size_t)PRED_WARPS * a.njmax * NW * 32;
   double* my_spill = s_spill + (size_t)wid * a.njmax * NW * 32;
   double* my_comb = s_comb + (size_t)wid * WC * 2;
+  double* s_raw = s_comb + (size_t)PRED_WARPS * WC * 2;     // TMA landing buffer: TILE * d raw candidate rows
+  __shared__ __align__(8) unsigned long long s_mbar;
+  if (tid == 0) mbar_init(&s_mbar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned tma_phase = 0;
 
   Best best; best.ei = -INFINITY; best.key = -INFINITY; best.idx = -1;
   double negcount = 0.0;
   const long long ntiles = (a.N + TILE - 1) / TILE;
+  // A tile's rows are contiguous in the pool: one 1-D bulk copy (TMA) lands them in shared memory
+  // while the previous tile is still being scored; tiles whose byte count or address is not a
+  // multiple of 16 (an odd tail) take the plain coalesced-load path.
+  auto tma_bytes = [&](long long t) -> unsigned {
+    const long long r0 = t * TILE;
+    const long long rows = (a.N - r0 < TILE) ? a.N - r0 : TILE;
+    const unsigned long long bytes = (unsigned long long)rows * d * sizeof(double);
+    const unsigned long long addr = (unsigned long long)(a.cand + (size_t)r0 * d);
+    return ((bytes & 15ull) == 0 && (addr & 15ull) == 0) ? (unsigned)bytes : 0u;
+  };
+  if (blockIdx.x < ntiles && tid == 0) {
+    const unsigned b0 = tma_bytes(blockIdx.x);
+    if (b0) tma_load_1d(s_raw, a.cand + (size_t)blockIdx.x * TILE * d, b0, &s_mbar);
+  }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TILE;
     __syncthreads();
-    // stage the candidate tile (coalesced reads, permuted [and padded] columns)
+    // stage the candidate tile (permuted [and padded] columns)
     {
       const long long lim = (a.N - row0 < TILE ? a.N - row0 : TILE) * d;
-      const double* src = a.cand + (size_t)row0 * d;
+      const bool via_tma = tma_bytes(tile) != 0;            // uniform
+      const double* src = via_tma ? s_raw : a.cand + (size_t)row0 * d;
+      if (via_tma) { mbar_wait(&s_mbar, tma_phase); tma_phase ^= 1; }
       if (FAST) {
         for (int idx = tid; idx < TILE * DP; idx += PRED_THREADS) s_cand[idx] = 0.0;
         __syncthreads();
@@ -206,6 +255,12 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
         const long long sidx = (long long)r * d + a.sp.perm[p];
         const int pp = FAST ? ((p < dc) ? p : DCP + (p - dc)) : p;
         s_cand[r * DP + pp] = (sidx < lim) ? src[sidx] : 0.0;
+      }
+      __syncthreads();                                      // s_raw is free again
+      const long long nxt = tile + gridDim.x;
+      if (nxt < ntiles && tid == 0) {
+        const unsigned bn = tma_bytes(nxt);
+        if (bn) tma_load_1d(s_raw, a.cand + (size_t)nxt * TILE * d, bn, &s_mbar);
       }
     }
     // per-lane ensemble accumulators: lane owns candidate (lane) of this warp when WC == 32,
@@ -522,11 +577,12 @@ static void fused_pick_layout(int dc, int dk, int* dcp, int* dkp) {
   else { *dcp = 0; *dkp = 0; }
 }
 
-static size_t fused_fixed_bytes(int nw, int njmax, int dp) {
+static size_t fused_fixed_bytes(int nw, int njmax, int dp, int d) {
   const size_t tile = (size_t)PRED_WARPS * nw * 8;
   const size_t nrows = 4 * (size_t)njmax + 4;
   return sizeof(double) * (tile * dp + nrows * dp + nrows + 2 * TLBO_HYP_STRIDE +
-                           (size_t)PRED_WARPS * njmax * nw * 32 + (size_t)PRED_WARPS * nw * 8 * 2);
+                           (size_t)PRED_WARPS * njmax * nw * 32 + (size_t)PRED_WARPS * nw * 8 * 2 +
+                           tile * d /* TMA landing buffer */ + 2);
 }
 
 static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, FusedPlan* pl) {
@@ -540,7 +596,7 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, F
   const size_t limit1 = 227 * 1024 - 2048, limit2 = (227 * 1024) / 2 - 2048;
   // preferred: two CTAs per SM (16 warps hide the sqrt / exp latency chains) with NW = 2
   if (pl->dcp > 0) {
-    const size_t fixed = fused_fixed_bytes(2, njmax, dp);
+    const size_t fixed = fused_fixed_bytes(2, njmax, dp, d);
     if (fixed + sizeof(double) * 16 * ldl <= limit2) {
       size_t rows = ((limit2 - fixed) / (sizeof(double) * ldl) / 16) * 16;
       if (rows > (size_t)nb16) rows = nb16;
@@ -554,7 +610,7 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, F
   for (int nw = 4; nw >= 1; nw >>= 1) {
     if (pl->dcp > 0 && nw == 1) break;
     const size_t tile = (size_t)PRED_WARPS * nw * 8;
-    const size_t fixed = fused_fixed_bytes(nw, njmax, dp);
+    const size_t fixed = fused_fixed_bytes(nw, njmax, dp, d);
     if (fixed + sizeof(double) * 16 * ldl > limit1) continue;
     size_t rows = ((limit1 - fixed) / (sizeof(double) * ldl) / 16) * 16;
     if (rows > (size_t)nb16) rows = nb16;
