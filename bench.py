@@ -49,6 +49,13 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--method', default='rgpe', choices=['rgpe', 'topo', 'trans_rgpe', 'tst'])
+    ap.add_argument('--surrogate', default='gp', choices=['gp', 'gp_mcmc'],
+                    help="'gp_mcmc': MCMC-marginalised GP hyper-parameters (BASELINE configs[4])")
+    ap.add_argument('--mcmc-steps', type=int, nargs=2, default=[250, 250], metavar=('BURNIN', 'CHAIN'),
+                    help='emcee burn-in / chain steps per fit (reference: 250 250, model_builder.py:74-89)')
+    ap.add_argument('--cpu-mcmc-steps', type=int, default=5,
+                    help='reference arm with gp_mcmc: burn-in = chain = this many steps, fit time scaled to the '
+                         'full chain length (the sampler cost is linear in the number of steps)')
     ap.add_argument('--pool', type=int, default=100000)
     ap.add_argument('--sources', type=int, default=29)
     ap.add_argument('--n0', type=int, default=40, help='target observations before the first step')
@@ -90,7 +97,7 @@ def fit_flops(models, d_cont, d_cat):
     H = d_cont + d_cat + 2
     f, evals = 0.0, 0
     for m in models:
-        info = m.fit_info_
+        info = getattr(m, 'fit_info_', None)
         if info is None:
             continue
         n = m.n_train_
@@ -166,18 +173,17 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy/scipy restatement of the reference path), reference-faithful
 # variant (literal Python pair loops as in tlbo/facade/rgpe.py:74-109).
-def _oracle_facade(method, types, sources, seed, literal):
+def _oracle_facade(method, types, sources, seed, literal, surrogate='gp', mcmc_steps=None):
     import oracle.facade as of
-    if method == 'rgpe':
-        return of.OracleRGPE(types, sources, seed, literal_loops=literal)
-    if method == 'trans_rgpe':
-        return of.OracleRGPE(types, sources, seed, smooth=0.7, literal_loops=literal)
-    if method == 'topo':
-        return of.OracleOBTLV(types, sources, seed, literal_loops=literal)
-    return of.OracleTST(types, sources, seed, literal_loops=literal)
+    base, kw = {'rgpe': (of.OracleRGPE, {}), 'trans_rgpe': (of.OracleRGPE, {'smooth': 0.7}),
+                'topo': (of.OracleOBTLV, {}), 'tst': (of.OracleTST, {})}[method]
+    if surrogate == 'gp_mcmc':
+        base = type('Mcmc' + base.__name__, (base,), dict(surrogate_type='gp_mcmc', mcmc_steps=tuple(mcmc_steps)))
+    return base(types, sources, seed, literal_loops=literal, **kw)
 
 
-def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, literal=True, quiet=True):
+def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, literal=True, surrogate='gp',
+                 mcmc_steps=None, mcmc_full=None):
     """Runs warmup + steps BO iterations of the oracle.  Per step: the full fit + weights
     (timed), and EI + ordering over the first ``sample_rows`` pool rows (timed, then scaled
     by pool / sample_rows: the work is exactly linear in the number of candidates).
@@ -186,8 +192,13 @@ def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, li
     from oracle.facade import zero_mean_unit_var_normalization, zero_one_normalization
     wl = build_workload(task, seed, pool, K, n0)
     t0 = time.perf_counter()
-    fac = _oracle_facade(method, wl['types'], wl['sources'], seed, literal)
+    fac = _oracle_facade(method, wl['types'], wl['sources'], seed, literal, surrogate, mcmc_steps)
     setup = time.perf_counter() - t0
+    # gp_mcmc: the chains run `mcmc_steps` steps and the fit time is scaled to the full length
+    # (log-probability evaluations: W * (steps + 2) per fit, the rest of train() is negligible)
+    fit_scale = 1.0
+    if surrogate == 'gp_mcmc':
+        fit_scale = (sum(mcmc_full) + 2.0) / (sum(mcmc_steps) + 2.0)
     np.random.seed(seed)
     acq_rng = np.random.RandomState(seed)
     ei = OracleEI(fac)
@@ -209,7 +220,7 @@ def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, li
         c = time.perf_counter()
         evaluated.append(idx)
         if it >= warmup:
-            tr.append(b - a)
+            tr.append((b - a) * fit_scale)
             mx.append((c - b) * scale)
     return tr, mx, setup
 
@@ -226,7 +237,8 @@ def cpu_baseline_sample(args, n_start):
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--ref-procs', '1', '--steps', '1',
                '--warmup', '0', '--n0', str(n_start), '--method', args.method, '--pool', str(args.pool),
                '--sources', str(args.sources), '--cpu-sample-rows', str(args.cpu_sample_rows),
-               '--pair-loops', loops]
+               '--pair-loops', loops, '--surrogate', args.surrogate, '--mcmc-steps', str(args.mcmc_steps[0]),
+               str(args.mcmc_steps[1]), '--cpu-mcmc-steps', str(args.cpu_mcmc_steps)]
         env = dict(os.environ)
         for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
             env.pop(k, None)
@@ -243,9 +255,17 @@ def cpu_baseline_sample(args, n_start):
                 sample=('1 BO iteration of the numpy/scipy oracle at target n=%d, K=%d: fit+weights at full size '
                         '(literal Python pair loops as the reference), EI+sort on the first %d of %d pool rows '
                         'scaled x%.0f' % (n_start, args.sources, args.cpu_sample_rows, args.pool,
-                                          args.pool / args.cpu_sample_rows)),
+                                          args.pool / args.cpu_sample_rows)) + _mcmc_sample_note(args),
                 train_s=tr[0], maximize_s_scaled=mx[0],
                 value_vectorised_pair_count=1.0 / tv, host_cores_available=os.cpu_count())
+
+
+def _mcmc_sample_note(args):
+    if args.surrogate != 'gp_mcmc':
+        return ''
+    return ('; gp_mcmc: chains of %d+%d emcee steps timed, fit time scaled to %d+%d steps (linear in the number '
+            'of log-probability evaluations)' % (args.cpu_mcmc_steps, args.cpu_mcmc_steps, args.mcmc_steps[0],
+                                                 args.mcmc_steps[1]))
 
 
 def run_reference_arm(args):
@@ -256,7 +276,8 @@ def run_reference_arm(args):
     P = args.ref_procs or (os.cpu_count() or 1)
     n_start = args.n0
     jobs = [(args.method, t % 30, 4465 + t, args.pool, args.sources, n_start, args.steps, args.warmup,
-             args.cpu_sample_rows, args.pair_loops == 'literal') for t in range(P)]
+             args.cpu_sample_rows, args.pair_loops == 'literal', args.surrogate,
+             (args.cpu_mcmc_steps, args.cpu_mcmc_steps), tuple(args.mcmc_steps)) for t in range(P)]
     t0 = time.perf_counter()
     if P == 1:
         res = [_oracle_worker(jobs[0])]
@@ -272,6 +293,7 @@ def run_reference_arm(args):
               '%d pool rows scaled x%.0f; target n=%d..%d'
               % (P, args.cpu_sample_rows, args.pool, args.pool / args.cpu_sample_rows, n_start + args.warmup,
                  n_start + args.warmup + args.steps - 1)).replace('PAIRLOOPS', args.pair_loops)
+    sample += _mcmc_sample_note(args)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
@@ -290,11 +312,16 @@ def run_reference_arm(args):
 
 def workload_config(args, where):
     return {
-        'workload': '%s offline BO, %d source GPs x 50 obs, %d-candidate EI pool, d=9 random_forest space, '
-                    'target n=%d..%d' % (args.method, args.sources, args.pool, args.n0 + args.warmup,
-                                         args.n0 + args.warmup + args.steps - 1),
+        'workload': '%s offline BO, %d source %s x 50 obs, %d-candidate EI pool, d=9 random_forest space, '
+                    'target n=%d..%d' % (args.method, args.sources,
+                                         'GPs' if args.surrogate == 'gp' else 'MCMC-marginalised GPs (34 walkers)',
+                                         args.pool, args.n0 + args.warmup, args.n0 + args.warmup + args.steps - 1),
         'method': args.method, 'sources': args.sources, 'pool': args.pool, 'd': 9,
-        'restarts_per_fit': 11, 'fits_per_iter': 6,
+        'surrogate': args.surrogate,
+        'restarts_per_fit': 11 if args.surrogate == 'gp' else None, 'fits_per_iter': 6,
+        'mcmc': (None if args.surrogate == 'gp' else
+                 {'walkers': 34, 'burnin_steps': args.mcmc_steps[0], 'chain_steps': args.mcmc_steps[1],
+                  'log_prob_evals_per_fit': 34 * (sum(args.mcmc_steps) + 2)}),
         'l2': ('flushed before every step (256 MiB device memset inside the timed region)' if where == 'gpu'
                else 'n/a (host)'),
         'multi_gpu': 'independent BO trials per rank (no data-path collective)',
@@ -311,7 +338,10 @@ def make_product(args, wl, shard=None):
     from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
     cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, tst=TST)[args.method]
     cs = TableSpace(wl['types'])
-    fac = cls(cs, wl['sources'], None, wl['seed'], surrogate_type='gp', num_src_hpo_trial=50)
+    kw = {}
+    if args.surrogate == 'gp_mcmc':
+        kw['mcmc_steps'] = tuple(args.mcmc_steps)
+    fac = cls(cs, wl['sources'], None, wl['seed'], surrogate_type=args.surrogate, num_src_hpo_trial=50, **kw)
     smbo = SMBO_OFFLINE((wl['Xt'], wl['yt']), cs, fac, random_seed=wl['seed'], max_runs=10 ** 9, shard=shard)
     smbo.configurations = list(wl['rows0'])
     smbo.perfs = [float(wl['yt'][r]) for r in wl['rows0']]
@@ -387,6 +417,8 @@ def run_ours(args):
                 n_src_used = sum(1 for k in range(fac.K) if not skip[k])
                 cached = bool(getattr(fac, '_pool_cache', None))
                 ns = ([] if cached else [50] * n_src_used) + [n_t]
+                if args.surrogate == 'gp_mcmc':
+                    ns = [n_t] * fac._G          # the target's walker GPs (tlbo_predict_pool_posteriors)
                 flops += fused_flops_per_candidate(ns, d_cont, d_cat) * args.pool
                 cached_reads += (16.0 * n_src_used * args.pool) if cached else 0.0
                 ff, fe = fit_flops(getattr(fac, 'last_fit_models', []), d_cont, d_cat)
@@ -442,7 +474,8 @@ def run_ours(args):
         return
 
     # ---- roofline of the fused predict + EI + arg-max kernel
-    fused_calls, fused_ms = kms.get('predict_ei_fused', (0, 0.0))
+    fused_name = 'predict_ei_fused' if args.surrogate == 'gp' else 'predict_pool_posteriors'
+    fused_calls, fused_ms = kms.get(fused_name, (0, 0.0))
     peaks = {}
     pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(pk_path):
@@ -485,6 +518,19 @@ def run_ours(args):
         'back to back; the launch lasts as long as the slowest restart (see DESIGN.md 3.1, tools/phase_fit.py)',
         'peak_source': 'FP64 FMA-pipe rate measured by tlbo_fp64_peak_probe in this run',
     }
+    roofline_mcmc = None
+    if args.surrogate == 'gp_mcmc':
+        ch_calls, ch_ms = kms.get('gp_mcmc_chain', (0, 0.0))
+        half = 2 * sum(args.mcmc_steps) + 2
+        roofline_mcmc = {
+            'kernel': 'gp_mcmc_kernel (persistent cooperative launch, one CTA per (surrogate, active walker))',
+            'bound': 'latency', 'avg_launch_ms': ch_ms / max(ch_calls, 1),
+            'sequential_log_prob_evaluations_per_launch': half,
+            'us_per_half_step': 1e3 * ch_ms / max(ch_calls, 1) / half,
+            'log_prob_evaluations_per_launch': 6 * fac._G * (sum(args.mcmc_steps) + 2),
+            'note': 'one half-step = one kernel-matrix build + register-panel Cholesky + barrier among the '
+                    'W/2 CTAs of a surrogate; SURVEY 8(d): latency-bound, report time not a roofline fraction',
+        }
     step_ms = ms_res / K
     breakdown = {k: {'calls_per_step': c / float(K), 'ms_per_step': t / K, 'share_of_step': t / ms_ins}
                  for k, (c, t) in kms.items()}
@@ -502,6 +548,9 @@ def run_ours(args):
         'predict_candidates_per_s': args.pool * fused_calls / (fused_ms * 1e-3) if fused_ms > 0 else None,
         'host_wall_ms_per_step': 1e3 * wall_res / K, 'instrumented_ms_per_step': ms_ins / K,
     }
+    if roofline_mcmc is not None:
+        line['roofline_mcmc'] = roofline_mcmc
+        line['roofline']['kernel'] = 'predict_ei_fused_kernel (per-walker posterior mode: tlbo_predict_pool_posteriors)'
     if pool_sharded is not None:
         line['pool_sharded'] = pool_sharded
     if world == 1 and not args.no_cpu_baseline:

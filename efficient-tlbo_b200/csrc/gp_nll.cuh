@@ -1,0 +1,749 @@
+// Device-side GP negative log marginal likelihood machinery shared by the batched MAP fit
+// (gp_fit.cu) and the MCMC hyper-parameter sampler (gp_mcmc.cu): shared-memory workspace,
+// kernel-matrix build, square-root-free panel elimination (shared-memory and register-resident
+// variants), NLL + gradient evaluation.  See gp_fit.cu for the algorithm notes.
+#pragma once
+#include "tlbo_common.cuh"
+
+#define FIT_THREADS 256
+// Optional phase timing (compile with -DTLBO_PHASE_TIMING): CTA 0 accumulates clock64() deltas
+// per phase of the NLL evaluation / optimiser step; read back with tlbo_debug_phase_cycles().
+#ifdef TLBO_PHASE_TIMING
+__device__ long long g_phase_cycles[16];
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_MARK(idx)                                                        \
+  do {                                                                         \
+    const long long _now = clock64();                                          \
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_cycles[idx] += _now - _pt; \
+    _pt = _now;                                                                \
+  } while (0)
+#define PHASE_LOCALS() long long _pl[4] = {0, 0, 0, 0}
+#define PHASE_LMARK(q) do { const long long _now = clock64(); _pl[q] += _now - _pt; _pt = _now; } while (0)
+#define PHASE_LFLUSH(base)                                                     \
+  do {                                                                         \
+    if (threadIdx.x == 0 && blockIdx.x == 0)                                   \
+      for (int _q = 0; _q < 4; _q++) g_phase_cycles[base + _q] += _pl[_q];     \
+  } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_MARK(idx) do {} while (0)
+#define PHASE_LOCALS() do {} while (0)
+#define PHASE_LMARK(q) do {} while (0)
+#define PHASE_LFLUSH(base) do {} while (0)
+#endif
+#define FIT_COLBUF 392   // raw / inverse-masked / lower-masked copies of the pivot column + pivot, 1/pivot
+
+struct FitWs {
+  double* A;       // [(n+1) * lda]  elimination panel
+  double* Xr;      // [n * d]  raw inputs, permuted columns
+  double* Xs;      // [n * d]  cont columns / l, cat columns raw
+  double* y;       // [n]
+  double* piv;     // [n]
+  double* dinv;    // [n]  1/sqrt(piv)
+  double* alpha;   // [n]
+  double* red;     // [8 * 32] reduction scratch
+  double* hyp;     // [2 * TLBO_HMAX] per permuted column: l (cont) or 1/(2 l^2) (cat); then 1/l^3 (cat)
+  double* colbuf;  // [2 * FIT_COLBUF] double-buffered pivot-column broadcast of the register-panel elimination
+  int* pairs;      // [n (n-1) / 2] packed (i << 16 | j), i > j: built once per kernel (register-panel path)
+  double* Kc;      // [npairs] kernel value per pair        } written by the kernel-matrix build, reused by
+  double* Cg;      // [npairs] c e^{-t-hs} 5/3 (1 + t)      } the gradient contraction (NULL: recompute)
+  int n, lda, d, npairs;
+};
+
+__host__ __device__ inline int fit_lda(int n) { return (n & 1) ? n : n + 1; }
+
+// pair tables of the register-panel path: index table always (tile > 0), value caches when
+// they fit beside the panel (decided by the host plan)
+__host__ __device__ inline size_t fit_pair_bytes(int ncap, int tile, int cache) {
+  if (tile <= 0) return 0;
+  const size_t np = (size_t)ncap * (ncap - 1) / 2 + 2;
+  return ((np * 4 + 15) / 16) * 16 + (cache ? 2 * np * sizeof(double) : 0);
+}
+__host__ inline size_t fit_small_bytes(int ncap, int d, int tile, int cache) {
+  // Xr, Xs, y, piv, dinv, alpha, red, hyp, colbuf, pair tables
+  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8) +
+         fit_pair_bytes(ncap, tile, cache);
+}
+__host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
+
+__device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* panel_global, int n, int ncap,
+                                         int d, int tile, int cache) {
+  double* p = reinterpret_cast<double*>(smem);
+  S.n = n; S.d = d; S.lda = fit_lda(n);
+  S.Xr = p; p += (size_t)ncap * d;
+  S.Xs = p; p += (size_t)ncap * d;
+  S.y = p; p += ncap;
+  S.piv = p; p += ncap;
+  S.dinv = p; p += ncap;
+  S.alpha = p; p += ncap;
+  S.red = p; p += 8 * 32;
+  S.hyp = p; p += 2 * TLBO_HMAX;
+  S.colbuf = p; p += 2 * FIT_COLBUF;
+  S.npairs = n * (n - 1) / 2;
+  S.pairs = nullptr; S.Kc = nullptr; S.Cg = nullptr;
+  if (tile > 0) {
+    const size_t np = (size_t)ncap * (ncap - 1) / 2 + 2;
+    if (cache) { S.Kc = p; p += np; S.Cg = p; p += np; }
+    S.pairs = reinterpret_cast<int*>(p);
+    p += ((np * 4 + 15) / 16) * 2;
+  }
+  S.A = panel_global ? panel_global : p;
+}
+
+__device__ __forceinline__ void load_problem(const FitWs& S, const SpaceDesc& sp, const double* X,
+                                             const double* y, int ncap) {
+  const int n = S.n, d = S.d;
+  for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
+    const int i = idx / d, p = idx - i * d;
+    S.Xr[idx] = X[(size_t)i * d + sp.perm[p]];
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) S.y[i] = y[i];
+  if (S.pairs) {
+    for (int q = threadIdx.x; q < S.npairs; q += blockDim.x) {
+      int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+      while (i * (i - 1) / 2 > q) i--;
+      while ((i + 1) * i / 2 <= q) i++;
+      S.pairs[q] = (i << 16) | (q - i * (i - 1) / 2);
+    }
+  }
+  (void)ncap;
+}
+
+// Steps 1-2.  Returns false (uniformly) if a pivot is not positive (Cholesky would fail).
+// On success: A[i][k] i>k = L_ik*sqrt(piv_k) (unscaled), piv[], dinv[], and -- scaled --
+// A[i][k] i<k = (L^-1)_ki,  A[n][k] = (L^-1 y)_k.   If scale_lower, A[i][k] i>=k = L_ik.
+static __device__ bool build_and_eliminate(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                    bool scale_lower) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double* A = S.A;
+  __syncthreads();
+  if (tid < d) {
+    const double l = exp(theta[1 + tid]);
+    if (tid < dc) { S.hyp[tid] = l; }
+    else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+  }
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  __syncthreads();
+  for (int idx = tid; idx < n * d; idx += T) {
+    const int p = idx % d;
+    double v = S.Xr[idx];
+    if (p < dc) v = v / S.hyp[p];
+    S.Xs[idx] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (n + 1) * n; idx += T) {
+    const int i = idx / n, j = idx - i * n;
+    double v;
+    if (i == n) v = S.y[j];
+    else if (i < j) v = 0.0;
+    else if (i == j) v = c + noise;
+    else {
+      const double* xi = S.Xs + (size_t)i * d;
+      const double* xj = S.Xs + (size_t)j * d;
+      double s = 0.0, hs = 0.0;
+      for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+      for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+      v = matern_hamming(c, s, hs);
+    }
+    A[(size_t)i * lda + j] = v;
+  }
+  bool ok = true;
+  const int tx = tid & 15, ty = tid >> 4, TY = T >> 4;
+  for (int k = 0; k < n; k++) {
+    __syncthreads();
+    const double piv = A[(size_t)k * lda + k];
+    if (!(piv > 0.0)) { ok = false; break; }
+    const double ip = 1.0 / piv;
+    if (tid == 0) S.piv[k] = piv;
+    for (int j = k + 1 + tx; j < n; j += 16) {
+      const double fj = A[(size_t)j * lda + k] * ip;
+      for (int i = ty; i <= n; i += TY) {
+        double ck;
+        if (i >= j || i < k) ck = A[(size_t)i * lda + k];
+        else if (i == k) ck = 1.0;
+        else continue;
+        A[(size_t)i * lda + j] -= ck * fj;
+      }
+    }
+  }
+  __syncthreads();
+  if (!ok) return false;
+  for (int k = tid; k < n; k += T) S.dinv[k] = 1.0 / sqrt(S.piv[k]);
+  __syncthreads();
+  for (int idx = tid; idx < (n + 1) * n; idx += T) {
+    const int i = idx / n, k = idx - i * n;
+    if (i < k || i == n) A[(size_t)i * lda + k] *= S.dinv[k];
+    else if (scale_lower) {
+      if (i == k) A[(size_t)i * lda + k] = sqrt(S.piv[k]);
+      else A[(size_t)i * lda + k] *= S.dinv[k];
+    }
+  }
+  __syncthreads();
+  // alpha_i = sum_{k>=i} (L^-1)_ki z_k
+  for (int i = tid; i < n; i += T) {
+    const double* ri = A + (size_t)i * lda;
+    const double* z = A + (size_t)n * lda;
+    double a = S.dinv[i] * z[i];
+    for (int k = i + 1; k < n; k++) a += ri[k] * z[k];
+    S.alpha[i] = a;
+  }
+  __syncthreads();
+  return true;
+}
+
+// 1/x from the hardware reciprocal seed (rcp.approx.ftz.f64, ~20 bits) and two Newton steps:
+// ~52 cycles of dependent latency against ~112 for the IEEE division (tools/ubench/lat.cu),
+// result within 1 ulp -- it sits on the critical path of every elimination step.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// One block of 16 elimination steps with the pivot-column block index KB a compile-time
+// constant (the outer loop over KB is unrolled by template recursion): tile indexing, most of
+// the activity masks and the skipping of already-eliminated column blocks resolve statically,
+// so a step is: 2-3 128-bit stores by the 16 owners of the pivot column (one warp), ONE
+// __syncthreads, five 128-bit loads, a handful of selects and the tile FMAs -- no uniform
+// branches and no data-dependent branch (a non-positive pivot only raises a flag).
+// Developed against tools/ubench/elim*.cu: 820 -> 503 cycles per step on B200.
+__device__ __forceinline__ void sts2_if(double* p, double x, double y, bool pred) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.shared.v2.f64 [%0], {%1, %2}; }" ::"r"(addr), "d"(x), "d"(y),
+               "r"((int)pred)
+               : "memory");
+}
+__device__ __forceinline__ void sts1_if(double* p, double x, bool pred) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(addr), "d"(x), "r"((int)pred)
+               : "memory");
+}
+
+struct ElimCtx {
+  double* colbuf; double* pivs; int n; int tx, ty; bool diag_lower, own_diag; double ip_next; bool bad;
+};
+
+template <int T, int KB>
+__device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
+  constexpr int TP = (T + 1) & ~1;             // packed per-lane stride (128-bit chunks)
+  const int n = c.n, tx = c.tx, ty = c.ty;
+  const int kend = (n - 16 * KB) < 16 ? (n - 16 * KB) : 16;
+  for (int kt = 0; kt < kend; kt++) {
+    const int k = 16 * KB + kt;
+    double* buf = c.colbuf + (kt & 1) * FIT_COLBUF;
+    {
+      // branch-free publish (divergent branches on this path cost ~100 cycles per step):
+      // predicated 128-bit stores by the 16 owners of the pivot column, pivot + 1/pivot by its owner
+      const bool pub = (tx == kt), own = pub && (ty == kt);
+#pragma unroll
+      for (int q = 0; q < TP; q += 2)
+        sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, pub);
+      sts2_if(buf + 384, a[KB][KB], c.ip_next, own);
+      sts1_if(c.pivs + k, a[KB][KB], own);
+    }
+    const bool row_lt = ty < kt, row_eq = ty == kt, col_gt = tx > kt;
+    __syncthreads();
+    const double2 pp = *reinterpret_cast<const double2*>(buf + 384);
+    c.bad = c.bad || !(pp.x > 0.0);
+    const double ip = pp.y;
+    double ck_lo[TP], fr[TP];
+    {
+      const double2* c2 = reinterpret_cast<const double2*>(buf + ty * TP);
+      const double2* f2 = reinterpret_cast<const double2*>(buf + tx * TP);
+#pragma unroll
+      for (int q = 0; q < TP; q += 2) {
+        const double2 v = c2[q >> 1], w = f2[q >> 1];
+        ck_lo[q] = v.x; ck_lo[q + 1] = v.y; fr[q] = w.x; fr[q + 1] = w.y;
+      }
+    }
+    // inverse-part multiplier of row block KB (rows i < k are active, the pivot row enters with 1);
+    // row blocks below KB are fully active, those above not yet
+    const double ck_up_kb = row_lt ? ck_lo[KB] : (row_eq ? 1.0 : 0.0);
+#pragma unroll
+    for (int jb = KB; jb < T; jb++) {
+      double f = (tx + 16 * jb < n) ? fr[jb] * ip : 0.0;
+      if (jb == KB) f = col_gt ? f : 0.0;
+#pragma unroll
+      for (int ia = 0; ia < T; ia++) {
+        if (ia > jb) a[ia][jb] -= ck_lo[ia] * f;                        // lower part (and the y row)
+        else if (ia < jb) {                                             // inverse part
+          if (ia < KB) a[ia][jb] -= ck_lo[ia] * f;
+          else if (ia == KB) a[ia][jb] -= ck_up_kb * f;
+        } else {                                                        // diagonal tile
+          const double cu = (ia < KB) ? ck_lo[ia] : ((ia == KB) ? ck_up_kb : 0.0);
+          a[ia][jb] -= (c.diag_lower ? ck_lo[ia] : cu) * f;
+        }
+      }
+    }
+    {
+      // speculative and branch-free: every thread inverts its own candidate for the next pivot
+      // (only the owner's value is ever published)
+      constexpr int KN = (KB + 1 < T) ? KB + 1 : KB;
+      const double pv = (kt < 15) ? a[KB][KB] : a[KN][KN];
+      c.ip_next = fast_rcp(pv);
+    }
+  }
+}
+
+template <int T, int KB>
+__device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
+  if (16 * KB < c.n) elim_block<T, KB>(a, c);
+  if constexpr (KB + 1 < T) elim_all<T, KB + 1>(a, c);
+}
+
+// ---------------------------------------------------------------------------------------
+// Register-resident variant of steps 1-2 for n + 1 <= 16 * T.  The (n+1) x n panel lives in
+// registers, 2-D cyclically distributed over the 16 x 16 thread grid (thread (ty, tx) owns
+// rows ty + 16a, columns tx + 16b); per elimination step only the pivot column crosses
+// shared memory (double-buffered, ONE __syncthreads per column).  Element-wise the
+// arithmetic is identical to build_and_eliminate.  ncu on the shared-memory version showed
+// ~1.8k cycles per column of exposed LDS latency in the per-thread row loop.
+// On success the shared panel holds, scaled: A[i][k] (i < k) = (L^-1)_ki, A[n][k] = (L^-1 y)_k
+// and -- scale_lower: A[i][k] (i >= k) = L_ik;  else: A[k][k] = 1/L_kk, A[i][k] (i > k) = 0
+// (so that row i of the panel is column i of L^-1, zero-padded: what nll_eval_reg contracts).
+template <int T>
+__device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                        bool scale_lower) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  // ty = fast index: the 16 owners of a pivot column (fixed tx) sit in ONE warp, so the other
+  // seven warps skip the publish code with a uniform branch
+  const int tx = tid >> 4, ty = tid & 15;
+  double* A = S.A;
+  PHASE_T0();
+  __syncthreads();
+  // every thread needs the scale of "its" column (p = tid & 31 < d <= 22): one exp per thread,
+  // no shared-memory round trip before the scaling pass
+  const int pcol = tid & 31;
+  double myscale = 1.0;
+  if (pcol < d) {
+    const double l = exp(theta[1 + pcol]);
+    myscale = (pcol < dc) ? 1.0 / l : 1.0;
+    if (tid < d) {
+      if (tid < dc) { S.hyp[tid] = l; }
+      else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+    }
+  }
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  if (pcol < d)
+    for (int i = tid >> 5; i < n; i += NT >> 5) S.Xs[(size_t)i * d + pcol] = S.Xr[(size_t)i * d + pcol] * myscale;
+  __syncthreads();
+  PHASE_MARK(0);
+  // kernel matrix (lower triangle, diagonal, y row) through shared memory: ONE copy of the
+  // exp / sqrt code over the pair table, then every thread picks up its register tile
+  // two pairs in flight per thread (independent sqrt / exp chains)
+  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
+    const int q1 = q0 + NT;
+    const bool has1 = q1 < S.npairs;
+    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
+    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
+    const double* xi0 = S.Xs + (size_t)i0 * d;
+    const double* xj0 = S.Xs + (size_t)j0 * d;
+    const double* xi1 = S.Xs + (size_t)i1 * d;
+    const double* xj1 = S.Xs + (size_t)j1 * d;
+    double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+    for (int p = 0; p < dc; p++) {
+      const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+      s0 += e0 * e0; s1 += e1 * e1;
+    }
+    for (int p = dc; p < d; p++) {
+      const double hp = S.hyp[p];
+      h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
+      h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
+    }
+    const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
+    const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
+    const double v0 = ce0 * (1.0 + t0 + t0 * t0 / 3.0), v1 = ce1 * (1.0 + t1 + t1 * t1 / 3.0);
+    A[(size_t)i0 * lda + j0] = v0;
+    if (S.Kc) { S.Kc[q0] = v0; S.Cg[q0] = ce0 * (5.0 / 3.0) * (t0 + 1.0); }
+    if (has1) {
+      A[(size_t)i1 * lda + j1] = v1;
+      if (S.Kc) { S.Kc[q1] = v1; S.Cg[q1] = ce1 * (5.0 / 3.0) * (t1 + 1.0); }
+    }
+  }
+  for (int j = tid; j < n; j += NT) {
+    A[(size_t)j * lda + j] = c + noise;
+    A[(size_t)n * lda + j] = S.y[j];
+  }
+  __syncthreads();
+  double a[T][T];
+#pragma unroll
+  for (int ia = 0; ia < T; ia++) {
+    const int i = ty + 16 * ia;
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+      const int j = tx + 16 * jb;
+      a[ia][jb] = (i <= n && j < n && i >= j) ? A[(size_t)i * lda + j] : 0.0;
+    }
+  }
+  PHASE_MARK(1);
+  // Tile (ia, jb) holds lower-part elements (i >= j, incl. the y row) when ia > jb, upper-part
+  // (inverse) elements when ia < jb; on diagonal tiles the class is fixed per thread.  The 16
+  // owners of pivot column k publish it three ways -- raw (multiplier of lower-part rows),
+  // masked to the active inverse rows (i < k, 1 at i == k), masked to the rows j > k that
+  // still get eliminated -- and the owner of the pivot publishes 1/pivot, so the consumers'
+  // tile update is T*T unpredicated FMAs with no per-step division, select or compare.
+  ElimCtx ec;
+  ec.colbuf = S.colbuf; ec.pivs = S.piv; ec.n = n; ec.tx = tx; ec.ty = ty;
+  ec.diag_lower = ty >= tx; ec.own_diag = ty == tx; ec.ip_next = 0.0; ec.bad = false;
+  ec.ip_next = fast_rcp(a[0][0]);
+  elim_all<T, 0>(a, ec);
+  const bool ok = !__syncthreads_or(ec.bad ? 1 : 0);
+  PHASE_MARK(2);
+  if (!ok) return false;
+  for (int k = tid; k < n; k += NT) S.dinv[k] = 1.0 / sqrt(S.piv[k]);
+  __syncthreads();
+#pragma unroll
+  for (int jb = 0; jb < T; jb++) {
+    const int k = tx + 16 * jb;
+    if (k < n) {
+      const double dk = S.dinv[k];
+#pragma unroll
+      for (int ia = 0; ia < T; ia++) {
+        const int i = ty + 16 * ia;
+        if (i <= n) {
+          double v;
+          if (i < k || i == n) v = a[ia][jb] * dk;
+          else if (scale_lower) v = (i == k) ? sqrt(S.piv[k]) : a[ia][jb] * dk;
+          else v = (i == k) ? dk : 0.0;
+          A[(size_t)i * lda + k] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // alpha_i = sum_{k>=i} (L^-1)_ki z_k
+  for (int i = tid; i < n; i += NT) {
+    const double* ri = A + (size_t)i * lda;
+    const double* z = A + (size_t)n * lda;
+    double al = S.dinv[i] * z[i];
+    for (int k = i + 1; k < n; k++) al += ri[k] * z[k];
+    S.alpha[i] = al;
+  }
+  __syncthreads();
+  PHASE_MARK(3);
+  return true;
+}
+
+// log-priors of GaussianProcess._nll and the final sign / finiteness rules (thread 0).
+__device__ __forceinline__ void nll_finish(const double* theta, int H, int n, double nll_data, double* out) {
+  double lml = -nll_data - 0.5 * (double)n * LOG_2PI;
+  // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
+  const double v0 = exp(theta[0]);
+  double lp0, gp0;
+  if (v0 <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
+  else {
+    const double lv = log(v0);
+    lp0 = -(lv * lv) / 2.0 - log(2.5066282746310002 * v0);
+    gp0 = -(1.0 + lv) / v0 * v0;
+  }
+  // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
+  const double vn = exp(theta[H - 1]);
+  const double s2 = 0.1 * 0.1;
+  double lpn, gpn;
+  if (vn == 0.0) { lpn = INFINITY; gpn = INFINITY; }
+  else {
+    const double a = log(1.0 + 3.0 * (s2 / (vn * vn)));
+    lpn = log(a + VERY_SMALL_NUMBER);
+    double b = 3.0 * s2 + vn * vn;
+    b *= log(3.0 * s2 * (1.0 / (vn * vn)) + 1.0);
+    b = fmax(b, 1e-14);
+    gpn = -(6.0 * s2) / b;
+  }
+  lml += lp0 + lpn;
+  out[1] += gp0;
+  out[H] += gpn;
+  bool fin = isfinite(lml);
+  for (int h = 0; h < H; h++) fin = fin && isfinite(out[1 + h]);
+  if (!fin) {
+    out[0] = 1e25;
+    for (int h = 0; h < H; h++) out[1 + h] = 0.0;
+  } else {
+    out[0] = -lml;
+    for (int h = 0; h < H; h++) out[1 + h] = -out[1 + h];
+  }
+}
+
+// K^-1_ij = sum_k U[i][k] U[j][k] over the zero-padded rows of the panel (row i of U is zero
+// left of column i), for the lower-triangle tiles only.  With the column block KB static, row
+// blocks above KB are skipped at compile time and so are the tiles right of the diagonal.
+template <int T, int KB>
+__device__ __forceinline__ void kin_all(double (&kin)[T][T], const double* A, int lda, int n, int ty, int tx) {
+  const int k1 = (16 * KB + 16 < n) ? 16 * KB + 16 : n;
+  for (int k = 16 * KB; k < k1; k++) {
+    double ui[KB + 1], uj[KB + 1];
+#pragma unroll
+    for (int q = 0; q <= KB; q++) {
+      const int i = ty + 16 * q, j = tx + 16 * q;
+      ui[q] = (i < n) ? A[(size_t)i * lda + k] : 0.0;
+      uj[q] = (j < n) ? A[(size_t)j * lda + k] : 0.0;
+    }
+#pragma unroll
+    for (int ia = 0; ia <= KB; ia++)
+#pragma unroll
+      for (int jb = 0; jb <= ia; jb++) kin[ia][jb] += ui[ia] * uj[jb];
+  }
+  if constexpr (KB + 1 < T) kin_all<T, KB + 1>(kin, A, lda, n, ty, tx);
+}
+
+// nll_eval on the register-panel path: the gradient contraction uses the same 2-D cyclic
+// tiling -- K^-1_ij = sum_k U[i][k] U[j][k] over the zero-padded rows of the panel, T x T
+// outer products per k (2T shared loads per T^2 FMAs instead of 2 per FMA).
+template <int T, int DMAX>
+__device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int tx = tid >> 4, ty = tid & 15;
+  const bool ok = build_and_eliminate_reg<T>(S, sp, theta, false);
+  if (!ok) {
+    if (tid == 0) out[0] = 1e25;
+    if (tid < H) out[1 + tid] = 0.0;
+    __syncthreads();
+    return false;
+  }
+  const double* A = S.A;
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  double part = 0.0;
+  for (int k = tid; k < n; k += NT) {
+    const double z = A[(size_t)n * lda + k];
+    part += 0.5 * z * z + 0.5 * log(S.piv[k]);
+  }
+  PHASE_T0();
+  const double nll_data = block_sum(part, S.red);
+  PHASE_MARK(4);
+
+  double kin[T][T];
+#pragma unroll
+  for (int ia = 0; ia < T; ia++)
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) kin[ia][jb] = 0.0;
+  kin_all<T, 0>(kin, A, lda, n, ty, tx);
+  // publish W = alpha alpha^T - K^-1 (strict lower part into the panel, diagonal into piv[]:
+  // both are dead by now) and contract it with dK/dtheta in ONE linear pair loop
+  __syncthreads();
+  PHASE_MARK(5);
+  {
+    double* Aw = S.A;
+#pragma unroll
+    for (int ia = 0; ia < T; ia++) {
+      const int i = ty + 16 * ia;
+#pragma unroll
+      for (int jb = 0; jb < T; jb++) {
+        const int j = tx + 16 * jb;
+        if (i < n && j < i) Aw[(size_t)i * lda + j] = S.alpha[i] * S.alpha[j] - kin[ia][jb];
+        else if (i < n && j == i) S.piv[i] = S.alpha[i] * S.alpha[i] - kin[ia][jb];
+      }
+    }
+  }
+  __syncthreads();
+  PHASE_MARK(6);
+  double g0 = 0.0, gn = 0.0;
+  double gacc[DMAX];
+#pragma unroll
+  for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
+  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
+    const int q1 = q0 + NT;
+    const bool has1 = q1 < S.npairs;
+    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
+    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
+    const double W0 = A[(size_t)i0 * lda + j0];
+    const double W1 = has1 ? A[(size_t)i1 * lda + j1] : 0.0;        // a masked second pair adds zeros
+    const double* xi0 = S.Xs + (size_t)i0 * d;
+    const double* xj0 = S.Xs + (size_t)j0 * d;
+    const double* xi1 = S.Xs + (size_t)i1 * d;
+    const double* xj1 = S.Xs + (size_t)j1 * d;
+    double WK0, WK1, cf0, cf1;
+    if (S.Kc) {
+      WK0 = W0 * S.Kc[q0]; cf0 = W0 * S.Cg[q0];
+      WK1 = W1 * S.Kc[has1 ? q1 : q0]; cf1 = W1 * S.Cg[has1 ? q1 : q0];
+    } else {
+      double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+      for (int p = 0; p < dc; p++) {
+        const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+        s0 += e0 * e0; s1 += e1 * e1;
+      }
+      for (int p = dc; p < d; p++) {
+        const double hp = S.hyp[p];
+        h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
+        h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
+      }
+      const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
+      const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
+      WK0 = W0 * (ce0 * (1.0 + t0 + t0 * t0 / 3.0)); cf0 = W0 * (ce0 * (5.0 / 3.0) * (t0 + 1.0));
+      WK1 = W1 * (ce1 * (1.0 + t1 + t1 * t1 / 3.0)); cf1 = W1 * (ce1 * (5.0 / 3.0) * (t1 + 1.0));
+    }
+    g0 += WK0;
+    g0 += WK1;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < dc) {
+        const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+        gacc[p] += cf0 * (e0 * e0);
+        gacc[p] += cf1 * (e1 * e1);
+      } else if (p < d) {
+        const double h3 = S.hyp[TLBO_HMAX + p];
+        gacc[p] += (xi0[p] != xj0[p]) ? WK0 * h3 : 0.0;
+        gacc[p] += (xi1[p] != xj1[p]) ? WK1 * h3 : 0.0;
+      }
+    }
+  }
+  for (int i = tid; i < n; i += NT) {
+    const double W = S.piv[i];
+    g0 += 0.5 * W * c;
+    gn += 0.5 * W * noise;
+  }
+  PHASE_MARK(7);
+  const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
+  __syncthreads();
+  {
+    // one interleaved butterfly over all H slots (independent shuffles pipeline)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+      gn += __shfl_xor_sync(0xffffffffu, gn, o);
+#pragma unroll
+      for (int p = 0; p < DMAX; p++) gacc[p] += __shfl_xor_sync(0xffffffffu, gacc[p], o);
+    }
+    if (lane == 0) {
+      S.red[wid * 32 + 0] = g0;
+      S.red[wid * 32 + (d + 1)] = gn;
+#pragma unroll
+      for (int p = 0; p < DMAX; p++)
+        if (p < d) S.red[wid * 32 + 1 + p] = gacc[p];
+    }
+  }
+  __syncthreads();
+  if (tid < H) {
+    double v = 0.0;
+    for (int w = 0; w < nw; w++) v += S.red[w * 32 + tid];
+    out[1 + tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) nll_finish(theta, H, n, nll_data, out);
+  __syncthreads();
+  PHASE_MARK(8);
+  return true;
+}
+
+// One evaluation of GaussianProcess._nll (gp.py:164-197).  Result: out[0] = f, out[1..H] = g
+// (shared memory), visible to all threads on return.  Returns Cholesky success.
+template <int DMAX>
+__device__ bool nll_eval(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const bool ok = build_and_eliminate(S, sp, theta, false);
+  if (!ok) {
+    if (tid == 0) out[0] = 1e25;
+    if (tid < H) out[1 + tid] = 0.0;
+    __syncthreads();
+    return false;
+  }
+  const double* A = S.A;
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  // data fit and log-determinant
+  double part = 0.0;
+  for (int k = tid; k < n; k += T) {
+    const double z = A[(size_t)n * lda + k];
+    part += 0.5 * z * z + 0.5 * log(S.piv[k]);
+  }
+  const double nll_data = block_sum(part, S.red);
+
+  // gradient accumulators: g0 (log c), gacc[p] (length scales, permuted order), gn (log s2)
+  double g0 = 0.0, gn = 0.0;
+  double gacc[DMAX];
+#pragma unroll
+  for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
+
+  const int npairs = n * (n - 1) / 2;
+  for (int q = tid; q < npairs; q += T) {
+    int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+    while (i * (i - 1) / 2 > q) i--;
+    while ((i + 1) * i / 2 <= q) i++;
+    const int j = q - i * (i - 1) / 2;   // j < i
+    const double* ri = A + (size_t)i * lda;
+    const double* rj = A + (size_t)j * lda;
+    double kin = S.dinv[i] * rj[i];
+    for (int k = i + 1; k < n; k++) kin += ri[k] * rj[k];
+    const double W = S.alpha[i] * S.alpha[j] - kin;
+    const double* xi = S.Xs + (size_t)i * d;
+    const double* xj = S.Xs + (size_t)j * d;
+    double s = 0.0, hs = 0.0;
+    for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
+    for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
+    const double t = sqrt(s) * SQRT5;
+    const double e = exp(-t), eh = exp(-hs);
+    const double Kc = c * ((1.0 + t + t * t / 3.0) * e) * eh;
+    const double WK = W * Kc;
+    g0 += WK;
+    const double coef = W * c * eh * (5.0 / 3.0) * (t + 1.0) * e;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < dc) { const double df = xi[p] - xj[p]; gacc[p] += coef * (df * df); }
+      else if (p < d) { if (xi[p] != xj[p]) gacc[p] += WK * S.hyp[TLBO_HMAX + p]; }
+    }
+  }
+  for (int i = tid; i < n; i += T) {
+    const double* ri = A + (size_t)i * lda;
+    double kin = S.dinv[i] * S.dinv[i];
+    for (int k = i + 1; k < n; k++) kin += ri[k] * ri[k];
+    const double W = S.alpha[i] * S.alpha[i] - kin;
+    g0 += 0.5 * W * c;
+    gn += 0.5 * W * noise;
+  }
+  // reduce H values across the block
+  const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  __syncthreads();
+  {
+    double v = warp_sum(g0);
+    if (lane == 0) S.red[wid * 32 + 0] = v;
+    v = warp_sum(gn);
+    if (lane == 0) S.red[wid * 32 + (d + 1)] = v;
+#pragma unroll
+    for (int p = 0; p < DMAX; p++) {
+      if (p < d) {
+        v = warp_sum(gacc[p]);
+        if (lane == 0) S.red[wid * 32 + 1 + p] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < H) {
+    double v = 0.0;
+    for (int w = 0; w < nw; w++) v += S.red[w * 32 + tid];
+    out[1 + tid] = v;       // d LML / d theta_h (without priors)
+  }
+  __syncthreads();
+  if (tid == 0) nll_finish(theta, H, n, nll_data, out);
+  __syncthreads();
+  return true;
+}
+
+// T = 0: shared-memory panel (any n that fits); T > 0: register panel, n + 1 <= 16 T.
+template <int T>
+__device__ __forceinline__ bool build_and_eliminate_any(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                                        bool scale_lower) {
+  if constexpr (T == 0) return build_and_eliminate(S, sp, theta, scale_lower);
+  else return build_and_eliminate_reg<T>(S, sp, theta, scale_lower);
+}
+template <int T, int DMAX>
+__device__ __forceinline__ bool nll_eval_any(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
+  if constexpr (T == 0) return nll_eval<DMAX>(S, sp, theta, out);
+  else return nll_eval_reg<T, DMAX>(S, sp, theta, out);
+}
+__host__ inline int panel_tile_for(int ncap) {
+  if (ncap + 1 <= 64) return 4;
+  if (ncap + 1 <= 80) return 5;
+  if (ncap + 1 <= 96) return 6;
+  if (ncap + 1 <= 112) return 7;
+  if (ncap + 1 <= 128) return 8;
+  return 0;
+}

@@ -6,13 +6,19 @@ of one facade share ONE device-resident ``SurrogatePack``:
     slot  K           target surrogate
     slots (K, K + 5]  cross-validation surrogates of the current iteration
 so that an iteration costs one batched fit launch, one small-query predict launch and one
-fused predict + EI + arg-max launch."""
+fused predict + EI + arg-max launch.
+
+With ``surrogate_type='gp_mcmc'`` (BASELINE config 5) every surrogate is a GROUP of W walker GPs
+(``GaussianProcessMCMC``): logical slot j occupies pack slots ``[j * W, (j + 1) * W)``, per-walker
+posteriors are marginalised on the device (``tlbo_mcmc_marginalize``) and the ensemble
+combination + EI + arg-max run over the marginalised per-surrogate posteriors."""
 import abc
 
 import numpy as np
 
 from tlbo_b200.config_space import convert_configurations_to_array, get_types
-from tlbo_b200.model.gp import fit_models, fit_models_async
+from tlbo_b200.model.gp import fit_models_async
+from tlbo_b200.model.gp_mcmc import fit_mcmc_models_async
 from tlbo_b200.model.model_builder import build_model
 from tlbo_b200.utils.constants import VERY_SMALL_NUMBER
 from tlbo_b200.utils.normalization import zero_mean_unit_var_normalization, zero_one_normalization
@@ -34,7 +40,8 @@ def _history_to_arrays(hist):
 
 class BaseFacade(object, metaclass=abc.ABCMeta):
     def __init__(self, config_space, source_hpo_data, seed, target_hp_configs=None,
-                 history_dataset_features=None, num_src_hpo_trial=50, surrogate_type='gp', max_target_rows=96):
+                 history_dataset_features=None, num_src_hpo_trial=50, surrogate_type='gp', max_target_rows=96,
+                 mcmc_steps=None):
         self.method_id = None
         self.config_space = config_space
         self.random_seed = seed
@@ -47,10 +54,19 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self.history_dataset_features = history_dataset_features
         if history_dataset_features is not None:
             assert len(history_dataset_features) == self.K
-        if surrogate_type not in ('gp', 'gp_b200'):
-            raise ValueError("surrogate_type %r is not part of the B200 hot path (use 'gp')" % surrogate_type)
+        if surrogate_type not in ('gp', 'gp_b200', 'gp_mcmc'):
+            raise ValueError("surrogate_type %r is not part of the B200 hot path (use 'gp' or 'gp_mcmc')"
+                             % surrogate_type)
         self.surrogate_type = surrogate_type
         self.types, self.bounds = get_types(config_space)
+        # walker GPs per surrogate (1 for the MAP GP): model_builder.py:74-77
+        self._G = 1
+        if surrogate_type == 'gp_mcmc':
+            self._G = 3 * (len(self.types) + 2)
+            self._G += self._G % 2
+        self._mcmc_steps = mcmc_steps       # (burn-in, chain) override of the reference's (250, 250)
+        self._mcmc_shared = {}              # initial ensemble + random tables shared by identically seeded models
+        self._logical_pack = None           # K + 1 placeholder slots for the all-resident fused call
         self.instance_features = None
         self.var_threshold = VERY_SMALL_NUMBER
         self.w = None
@@ -77,7 +93,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             cap = max(cap, ops.round_up(int(self._pack.ncap * 1.5), 8))
         if self._stage is None:
             self._stage = ops.PinnedStage()
-        new = ops.SurrogatePack(self.K + 1 + N_CV_SLOTS, cap, len(self.types))
+        new = ops.SurrogatePack((self.K + 1 + N_CV_SLOTS) * self._G, cap, len(self.types))
         if self._pack is not None:
             for s in range(self._pack.M):
                 new.copy_slot_from(s, self._pack, s)
@@ -95,13 +111,28 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         pass
 
     # ---- surrogate construction ---------------------------------------------------------
+    def _new_model(self):
+        """``build_model(surrogate_type, config_space, RandomState(seed))`` (base_facade.py:64-65,95)."""
+        model = build_model(self.surrogate_type, self.config_space, np.random.RandomState(self.random_seed))
+        if self._G > 1:
+            assert model.group_size == self._G
+            if self._mcmc_steps is not None:
+                model.burnin_steps, model.chain_length = int(self._mcmc_steps[0]), int(self._mcmc_steps[1])
+        return model
+
+    def _fit_async(self, models, Xs, ys):
+        """One batched device fit of ``models`` (MAP restarts or MCMC chains); returns ``finish``."""
+        if self._G > 1:
+            return fit_mcmc_models_async(models, Xs, ys)
+        return fit_models_async(models, Xs, ys)
+
     def build_source_surrogates(self, normalize):
         """base_facade.py:58-91 -- the K source fits run as ONE batched launch."""
         self.source_surrogates = list()
         pack = self._ensure_pack(self.num_src_hpo_trial)
         Xs, ys = [], []
         for k, hist in enumerate(self.source_hpo_data):
-            model = build_model(self.surrogate_type, self.config_space, np.random.RandomState(self.random_seed))
+            model = self._new_model()
             X, y = _history_to_arrays(hist)
             X = X[:self.num_src_hpo_trial]
             y = y[:self.num_src_hpo_trial]
@@ -123,12 +154,15 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             ys.append(y)
             self.source_surrogates.append(model)
         if self.K:
-            fit_models(self.source_surrogates, Xs, ys)
+            self._fit_async(self.source_surrogates, Xs, ys)()
 
     def _share_start_points(self, model):
         """Every model of a facade is built from a fresh ``RandomState(self.random_seed)``
         (base_facade.py:64-65,95), so the 10 sampled L-BFGS-B start points are identical:
         draw them once and share the array (also lets the batched fit see one ``p0``)."""
+        if self._G > 1:
+            model._shared = self._mcmc_shared        # same seeds -> same initial ensemble and random tables
+            return
         if self._p0_cache is None:
             self._p0_cache = model._start_points()
         model._p0_override = self._p0_cache
@@ -139,8 +173,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         normalisation.  Returns ``(model, X, y_normalised)`` for a later batched fit."""
         assert normalize in ['standardize', 'scale', 'none']
         if self._proto is None:
-            self._proto = build_model(self.surrogate_type, self.config_space,
-                                      np.random.RandomState(self.random_seed))
+            self._proto = self._new_model()
             self._share_start_points(self._proto)
         # every build_model(type, cs, RandomState(seed)) call yields the same fresh model
         model = self._proto.fresh_copy()
@@ -157,7 +190,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
 
     def build_single_surrogate(self, X, y, normalize, slot=None):
         job = self._prepare_single_surrogate(X, y, normalize, self.K if slot is None else slot)
-        finish = fit_models_async([job[0]], [job[1]], [job[2]])
+        finish = self._fit_async([job[0]], [job[1]], [job[2]])
         if self._overlap_hook is not None:
             self._overlap_hook()
         finish()
@@ -173,16 +206,72 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
                want_rows=False, ws=None, sync=True):
         from tlbo_b200 import ops
         w, skip, order = self._ensemble_args()
-        view = ops.pack_view(self._pack, 0, self.K + 1)
         dw = ops.h2d(np.ascontiguousarray(w, dtype=np.float64))
         dskip = None if skip is None else ops.h2d(np.ascontiguousarray(skip, dtype=np.int32))
         dorder = None if order is None else ops.h2d(np.ascontiguousarray(order, dtype=np.int32))
+        if self._G > 1:
+            # marginalised per-surrogate posteriors, all resident: sources from the pool cache (or
+            # computed now for an ad-hoc query), the target's W walker GPs evaluated and
+            # marginalised into row K; the fused kernel then only combines, scores and reduces
+            cmu, cvar = self._group_posteriors(X_dev)
+            return ops.predict_ei_fused(self._logical(), self.types, dw, dskip, X_dev, eta, par=par,
+                                        var_floor=var_floor, keys=keys, excluded=excluded, idx_offset=idx_offset,
+                                        mode=self._fused_mode, order=dorder, want_rows=want_rows, ws=ws, sync=sync,
+                                        nmax=8, cache=(cmu, cvar))
+        view = ops.pack_view(self._pack, 0, self.K + 1)
         nmax = max([self.num_src_hpo_trial if self.K else 0, getattr(self.target_surrogate, 'n_train_', 0)] +
                    [m.n_train_ for m in (self.source_surrogates or [])])
         cache = self._pool_cache.get((X_dev.data_ptr(), int(X_dev.shape[0])))
         return ops.predict_ei_fused(view, self.types, dw, dskip, X_dev, eta, par=par, var_floor=var_floor,
                                     keys=keys, excluded=excluded, idx_offset=idx_offset, mode=self._fused_mode,
                                     order=dorder, want_rows=want_rows, ws=ws, sync=sync, nmax=nmax, cache=cache)
+
+    # ---- MCMC-marginalised surrogates: group-level posteriors ----------------------------------
+    def _logical(self):
+        """K + 1 placeholder slots (n = 1) standing for the marginalised surrogates in the fused
+        kernel's all-resident mode (it only reads their posteriors from HBM)."""
+        from tlbo_b200 import ops
+        if self._logical_pack is None:
+            self._logical_pack = ops.SurrogatePack(self.K + 1, 8, len(self.types))
+            self._logical_pack.n.fill_(1)
+        return self._logical_pack
+
+    def _walker_posteriors_into(self, slot, X_dev, out_mu, out_var):
+        """Marginalised posterior of logical surrogate ``slot`` over ``X_dev`` into row ``slot`` of
+        ``out_mu / out_var`` (gp_mcmc.py:418-440): W walker posteriors, then one reduction."""
+        from tlbo_b200 import ops
+        G = self._G
+        view = ops.pack_view(self._pack, slot * G, G)
+        mdl = self.target_surrogate if slot == self.K else self.source_surrogates[slot]
+        mu_w, var_w = ops.predict_pool_posteriors(view, self.types, X_dev, nmax=mdl.n_train_)
+        ops.mcmc_marginalize(mu_w, var_w, 1, G, out=(out_mu[slot:slot + 1], out_var[slot:slot + 1]))
+
+    def _group_posteriors(self, X_dev):
+        import torch
+        key = (X_dev.data_ptr(), int(X_dev.shape[0]))
+        hit = self._pool_cache.get(key)
+        if hit is None:
+            N = int(X_dev.shape[0])
+            cmu = torch.zeros(self.K + 1, N, dtype=torch.float64, device=X_dev.device)
+            cvar = torch.zeros(self.K + 1, N, dtype=torch.float64, device=X_dev.device)
+            # facades without source surrogates (NoTL) skip those slots in the combination
+            for k in range(self.K if self.source_surrogates is not None else 0):
+                self._walker_posteriors_into(k, X_dev, cmu, cvar)
+        else:
+            cmu, cvar = hit
+        self._walker_posteriors_into(self.K, X_dev, cmu, cvar)
+        return cmu, cvar
+
+    def _predict_slots(self, slot0, M, X_dev):
+        """Device ``mu, var [M, n]`` of logical surrogates ``slot0 .. slot0 + M - 1`` at a small
+        query set: ONE predict launch (+ one marginalisation for walker groups)."""
+        from tlbo_b200 import ops
+        G = self._G
+        view = ops.pack_view(self._pack, slot0 * G, M * G)
+        mu, var = ops.gp_predict(view, self.types, X_dev)
+        if G > 1:
+            mu, var = ops.mcmc_marginalize(mu, var, M, G)
+        return mu, var
 
     def register_static_pool(self, X_dev):
         """Declare ``X_dev`` (device tensor [N, d]) an immutable candidate pool: the source
@@ -195,6 +284,15 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             return
         key = (X_dev.data_ptr(), int(X_dev.shape[0]))
         if key in self._pool_cache:
+            return
+        if self._G > 1:
+            import torch
+            N = int(X_dev.shape[0])
+            cmu = torch.empty(self.K + 1, N, dtype=torch.float64, device=X_dev.device)
+            cvar = torch.empty(self.K + 1, N, dtype=torch.float64, device=X_dev.device)
+            for k in range(self.K):            # row K is the target's, refreshed by every fused call
+                self._walker_posteriors_into(k, X_dev, cmu, cvar)
+            self._pool_cache = {key: (cmu, cvar)}
             return
         view = ops.pack_view(self._pack, 0, self.K)
         nmax = max(m.n_train_ for m in self.source_surrogates)
@@ -236,6 +334,5 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         source predicts of rgpe.py:27-30 / topo_variant1.py:27-35 plus the CV surrogates,
         in ONE launch."""
         from tlbo_b200 import ops
-        view = ops.pack_view(self._pack, 0, self.K + 1 + n_extra)
-        mu, var = ops.gp_predict(view, self.types, self._to_device(X))
+        mu, var = self._predict_slots(0, self.K + 1 + n_extra, self._to_device(X))
         return ops.d2h(mu), ops.d2h(var)

@@ -9,7 +9,6 @@ mis-ranked-pair counts come from the integer pair-count kernel (bit-exact)."""
 import numpy as np
 
 from tlbo_b200.facade.base_facade import BaseFacade, N_CV_SLOTS
-from tlbo_b200.model.gp import fit_models_async
 
 
 class _BootstrapRankingFacade(BaseFacade):
@@ -80,7 +79,7 @@ class _BootstrapRankingFacade(BaseFacade):
         y_dev = db[nx:nx + instance_num]
         dib = db[nx + instance_num:].view(torch.int32)
         src_dev, lo_dev, hi_dev = dib[0:nr], dib[nr2:nr2 + nr], dib[2 * nr2:2 * nr2 + nr]
-        finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+        finish_fit = self._fit_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
         self.target_surrogate = jobs[0][0]
         self.last_fit_models = [j[0] for j in jobs]
 
@@ -95,8 +94,7 @@ class _BootstrapRankingFacade(BaseFacade):
             self._overlap_hook()
 
         # K source predicts + fold predicts at the target points (one launch), pair counts
-        view = ops.pack_view(self._pack, 0, K + 1 + n_folds)
-        mu_dev, var_dev = ops.gp_predict(view, self.types, X_dev)
+        mu_dev, var_dev = self._predict_slots(0, K + 1 + n_folds, X_dev)
         counts_dev = ops.rank_loss_counts_normal(y_dev, z_dev, mu_dev, var_dev, src_dev, lo_dev, hi_dev, sync=False)
         finish_fit()                                   # first synchronisation of the iteration
         counts = ops.d2h(counts_dev)

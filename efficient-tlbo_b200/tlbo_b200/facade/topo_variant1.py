@@ -4,7 +4,6 @@ pairwise logistic ranking loss (sources, then sources + cross-validated target).
 import numpy as np
 
 from tlbo_b200.facade.base_facade import BaseFacade
-from tlbo_b200.model.gp import fit_models_async
 from tlbo_b200.utils.scipy_solver import scipy_solve
 
 _scale_method = 'standardize'
@@ -62,7 +61,7 @@ class OBTLV(BaseFacade):
         if self._side is None:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(main)                     # X_dev and the source slots are ready
-        finish_fit = fit_models_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+        finish_fit = self._fit_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
         self.target_surrogate = jobs[0][0]
         self.last_fit_models = [j[0] for j in jobs]
         self.target_y_range = 0.5 * (np.max(y) - np.min(y))
@@ -72,14 +71,13 @@ class OBTLV(BaseFacade):
         if self._overlap_hook is not None:
             self._overlap_hook()                         # tie keys etc., overlapped with the fit
         with torch.cuda.stream(self._side):
-            mu_src_dev, _ = ops.gp_predict(ops.pack_view(self._pack, 0, K), self.types, X_dev)
+            mu_src_dev, _ = self._predict_slots(0, K, X_dev)
             pred_y = np.ascontiguousarray(ops.d2h(mu_src_dev).T)
             self.learn_source_weights(pred_y, y)
         main.wait_stream(self._side)
         mu = None
         if len(folds):
-            view = ops.pack_view(self._pack, K + 1, len(folds))
-            mu_cv_dev, _ = ops.gp_predict(view, self.types, X_dev)
+            mu_cv_dev, _ = self._predict_slots(K + 1, len(folds), X_dev)
         finish_fit()
         if len(folds):
             mu = ops.d2h(mu_cv_dev)

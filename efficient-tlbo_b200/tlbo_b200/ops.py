@@ -492,6 +492,125 @@ class PairLogistic(object):
         return self._cache
 
 
+# ---- MCMC-marginalised GP (BASELINE config 5) -------------------------------------------
+
+class McmcTables(object):
+    """Device copy of the stretch-move random tables (``stretch_move_tables``) of one or more
+    samplers, stacked ``[n_tables, 2 * nsteps, W / 2]``.  Uploads are cached by identity of
+    the host tables: every model a facade builds shares one table."""
+    _cache = {}
+
+    def __init__(self, tables):
+        key = tuple(id(t) for t in tables) + (torch.cuda.current_device(),)
+        hit = McmcTables._cache.get(key)
+        if hit is None:
+            if len(McmcTables._cache) > 16:
+                McmcTables._cache.clear()
+            dev = [h2d(np.ascontiguousarray(np.stack([t[i] for t in tables]))) for i in range(5)]
+            hit = (list(tables), dev)          # the host tables stay alive, so the ids stay unique
+            McmcTables._cache[key] = hit
+        self.sidx, self.cidx, self.zz, self.fac, self.logu = hit[1]
+        self.n_tables = len(tables)
+        self.nhalf, self.Ns = int(self.sidx.shape[1]), int(self.sidx.shape[2])
+
+
+class McmcHandle(object):
+    """Buffers of an enqueued ``tlbo_gp_mcmc_chain``; ``finish`` reads them back."""
+
+    def __init__(self, pos, lp, naccept, status, batch, keep):
+        self.pos, self.lp, self.naccept, self.status, self.batch, self._keep = pos, lp, naccept, status, batch, keep
+
+    def finish(self):
+        st = d2h(self.status)
+        self._keep = None
+        return st, d2h(self.pos), d2h(self.lp), d2h(self.naccept)
+
+
+def upload_batch(X_list, y_list):
+    """Padded device batch ``(dX [B, ncap, d], dy [B, ncap], dn [B], ncap)`` (one upload)."""
+    d = int(X_list[0].shape[1])
+    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
+    return dX, dy, dn, ncap
+
+
+def gp_mcmc_chain(batch, types, W, nsteps, pos0, tables, table_of, prior_bounds_raw, theta0):
+    """``tlbo_gp_mcmc_chain``: ``nsteps`` emcee stretch-move steps of ``W`` walkers for each of
+    the B surrogates of ``batch`` (``upload_batch``) in one persistent launch (per group of
+    co-resident surrogates).  ``pos0`` host ``[B, W, H]`` initial ensembles; ``tables`` a
+    ``McmcTables`` (or None when ``nsteps == 0``: one batched evaluation of ``_ll``).
+    Returns a ``McmcHandle`` right after the launch."""
+    dX, dy, dn, ncap = batch
+    B, d = int(dX.shape[0]), int(dX.shape[2])
+    H = d + 2
+    dev = dX.device
+    pos = h2d(np.ascontiguousarray(np.asarray(pos0, dtype=np.float64).reshape(B, W, H)))
+    lp = torch.empty(B, W, dtype=F64, device=dev)
+    nacc = torch.zeros(B, W, dtype=torch.int32, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    pb = np.asarray(prior_bounds_raw, dtype=np.float64).reshape(H, 2)
+    dlo = _cached_const(pb[:, 0])
+    dhi = _cached_const(pb[:, 1])
+    dth0 = None if theta0 is None else _cached_const(theta0)
+    dtab = None
+    if nsteps > 0:
+        assert tables is not None and tables.nhalf == 2 * nsteps and tables.Ns == W // 2
+        if table_of is not None and tables.n_tables > 1:
+            dtab = h2d(np.ascontiguousarray(table_of, dtype=np.int32))
+    work = torch.empty(int(lib.tlbo_gp_mcmc_workspace_bytes(B, W, ncap, d)), dtype=torch.uint8, device=dev)
+    t = _types_arr(types)
+    tb = tables
+    with _call('gp_mcmc_chain', 1):
+        check(lib.tlbo_gp_mcmc_chain(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), int(W), int(nsteps), ptr(pos),
+                                     ptr(lp), ptr(tb.sidx) if nsteps else None, ptr(tb.cidx) if nsteps else None,
+                                     ptr(tb.zz) if nsteps else None, ptr(tb.fac) if nsteps else None,
+                                     ptr(tb.logu) if nsteps else None, ptr(dtab), ptr(dlo), ptr(dhi), ptr(dth0),
+                                     ptr(nacc), ptr(status), ptr(work), _stream()))
+    return McmcHandle(pos, lp, nacc, status, batch, (work, dtab, tb))
+
+
+def gp_factorize_walkers(batch, types, theta_dev, ymean, ystd, pack, slot0, W):
+    """Factorise ``W`` walker GPs per surrogate of ``batch`` at the DEVICE thetas
+    ``theta_dev [B * W, H]`` into pack slots ``slot0 ...`` (``tlbo_gp_factorize_batched`` over
+    the replicated batch).  Returns the device status tensor ``int32[B * W]`` (no sync)."""
+    dX, dy, dn, ncap = batch
+    B, d = int(dX.shape[0]), int(dX.shape[2])
+    if ncap > pack.ncap:
+        raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
+    rX = dX.repeat_interleave(W, dim=0).contiguous()
+    ry = dy.repeat_interleave(W, dim=0).contiguous()
+    rn = dn.repeat_interleave(W, dim=0).contiguous()
+    hym = np.ascontiguousarray(np.repeat(np.asarray(ymean, dtype=np.float64), W))
+    hys = np.ascontiguousarray(np.repeat(np.asarray(ystd, dtype=np.float64), W))
+    status = torch.zeros(B * W, dtype=torch.int32, device=dX.device)
+    work = torch.empty(int(lib.tlbo_gp_fit_workspace_bytes(B * W, 1, ncap, d)), dtype=torch.uint8, device=dX.device)
+    t = _types_arr(types)
+    theta_dev = theta_dev.contiguous()
+    with _call('gp_factorize', 1):
+        check(lib.tlbo_gp_factorize_batched(ptr(rX), ptr(ry), ptr(rn), B * W, ncap, d, ptr(t), ptr(theta_dev), ptr(hym),
+                                            ptr(hys), pack.ref(), int(slot0), None, None, ptr(status), ptr(work),
+                                            _stream()))
+    status._keep = (rX, ry, rn, work, hym, hys, theta_dev)
+    return status
+
+
+def mcmc_marginalize(mu, var, G, W, out=None):
+    """``tlbo_mcmc_marginalize``: device ``mu, var [G * W, N]`` -> ``gmu, gvar [G, N]`` (written
+    into ``out = (gmu, gvar)`` when given)."""
+    assert mu.shape == var.shape and mu.shape[0] == G * W and mu.is_contiguous() and var.is_contiguous()
+    N = int(mu.shape[1])
+    if out is not None:
+        gmu, gvar = out
+        assert gmu.shape == (G, N) and gvar.shape == (G, N) and gmu.is_contiguous() and gvar.is_contiguous()
+    else:
+        gmu = torch.empty(G, N, dtype=F64, device=mu.device)
+        gvar = torch.empty(G, N, dtype=F64, device=mu.device)
+    if N:
+        with _call('mcmc_marginalize', 1):
+            check(lib.tlbo_mcmc_marginalize(ptr(mu), ptr(var), int(G), int(W), N, ptr(gmu), ptr(gvar), _stream()))
+    return gmu, gvar
+
+
 def fp64_peak_probe():
     """(DFMA TFLOP/s, DMMA TFLOP/s) measured on the current device."""
     _dev()

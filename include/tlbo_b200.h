@@ -199,6 +199,49 @@ int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const
 int tlbo_pairwise_logistic_loss_grad_hw(const double* d_A, const double* d_y, const double* h_w, int n, int m,
                                         double* d_out, void* stream);
 
+/* MCMC marginalisation of the GP hyper-parameters (BASELINE config 5) -- replaces
+ * GaussianProcessMCMC._train / _ll (tlbo/model/gp_mcmc.py:116-282,294-332): the
+ * emcee.EnsembleSampler chain over the kernel hyper-parameters (emcee 3.x stretch move, a = 2,
+ * two randomly split halves per step; un-vendored dependency, requirements.txt:16) with
+ * log-probability = sklearn GaussianProcessRegressor.log_marginal_likelihood(theta) + lognormal
+ * prior on c + horseshoe(0.1) prior on s2 + Tophat bound priors on every dimension
+ * (tlbo/model/base_gp.py:92-132, gp_base_prior.py:155-240), -inf on a failed Cholesky or a
+ * non-finite value.  B surrogates x W walkers (W even) advance `nsteps` steps in ONE persistent
+ * cooperative launch per group of co-resident surrogates; no host round trips.
+ *   d_X, d_y, d_n        as tlbo_gp_fit_batched (y after BaseGP._normalize_y)
+ *   d_pos [B, W, H]      in: initial ensemble (prior samples, gp_mcmc.py:153-171 or the previous
+ *                        chain's p0); out: final positions (sampler.get_chain()[-1])
+ *   d_lp  [B, W]         out: log-probability of the final positions (nsteps = 0: of d_pos, i.e. one
+ *                        batched evaluation of _ll)
+ *   random tables, host-drawn from the sampler's legacy MT19937 stream in emcee's order, shape
+ *   [n_tables, 2 * nsteps, W/2], half-step h = 2 * step + split:
+ *     d_sidx   int32  walker ids of the active half (ascending)
+ *     d_cidx   int32  partner walker id (complementary half) of each active walker
+ *     d_zz            stretch factors ((a - 1) u + 1)^2 / a
+ *     d_factors       (H - 1) * log(zz)
+ *     d_logu          log of the acceptance uniforms
+ *   d_table_of [B] int32 table used by surrogate b (NULL: table 0 for all)
+ *   d_prior_lo, d_prior_hi [H]  Tophat bounds in the ORIGINAL scale
+ *   d_theta0 [H]         kernel default theta for the initial GaussianProcessRegressor.fit of
+ *                        gp_mcmc.py:141 (d_status[b] = 1 if its Cholesky fails); may be NULL
+ *   d_naccept [B, W] int32  accepted proposals per walker (accumulated, caller zeroes)
+ *   d_work               scratch of tlbo_gp_mcmc_workspace_bytes() bytes                         */
+int tlbo_gp_mcmc_chain(const double* d_X, const double* d_y, const int32_t* d_n, int B, int ncap, int d,
+                       const int32_t* h_types, int W, int nsteps, double* d_pos, double* d_lp,
+                       const int32_t* d_sidx, const int32_t* d_cidx, const double* d_zz, const double* d_factors,
+                       const double* d_logu, const int32_t* d_table_of, const double* d_prior_lo,
+                       const double* d_prior_hi, const double* d_theta0, int32_t* d_naccept, int32_t* d_status,
+                       void* d_work, void* stream);
+int64_t tlbo_gp_mcmc_workspace_bytes(int B, int W, int ncap, int d);
+
+/* Hyper-parameter-marginalised posterior -- replaces GaussianProcessMCMC._predict
+ * (tlbo/model/gp_mcmc.py:418-440): for each of G surrogates with W walker GPs each,
+ *   m = mean_w mu_w,  v = var_w(mu_w) + mean_w(var_w),  v clipped at DBL_EPSILON.
+ * d_mu, d_var [G * W, N] per-walker posteriors (outputs of tlbo_gp_predict /
+ * tlbo_predict_pool_posteriors); d_gmu, d_gvar [G, N].                                            */
+int tlbo_mcmc_marginalize(const double* d_mu, const double* d_var, int G, int W, int64_t N, double* d_gmu,
+                          double* d_gvar, void* stream);
+
 /* Device-rate probes used by bench.py for the roofline denominators (FP64 FMA pipe and
  * FP64 mma.sync rate are not in MEASURED_PEAKS.json).  Returns achieved TFLOP/s in
  * h_out[0] (DFMA) and h_out[1] (DMMA m8n8k4); synchronous.                             */

@@ -56,7 +56,21 @@ def rank_loss_vectorised(y, sampled_y, row_lo, row_hi):
 
 
 class OracleFacade(object):
-    """``BaseFacade`` (tlbo/facade/base_facade.py:15-183)."""
+    """``BaseFacade`` (tlbo/facade/base_facade.py:15-183).
+
+    ``surrogate_type`` / ``mcmc_steps`` are class attributes (subclass to change them):
+    ``'gp'`` builds ``OracleGP``, ``'gp_mcmc'`` the MCMC-marginalised ``OracleGPMCMC`` with
+    ``mcmc_steps = (burn-in, chain)`` (reference: 250, 250 -- model_builder.py:74-89)."""
+    surrogate_type = 'gp'
+    mcmc_steps = None
+
+    def _new_model(self):
+        """``build_model(surrogate_type, config_space, RandomState(seed))``: base_facade.py:64-65,95."""
+        if self.surrogate_type == 'gp_mcmc':
+            from oracle.gp_mcmc import OracleGPMCMC
+            burn, chain = self.mcmc_steps if self.mcmc_steps is not None else (250, 250)
+            return OracleGPMCMC(self.types, self.random_seed, chain_length=chain, burnin_steps=burn)
+        return OracleGP(self.types, self.random_seed)
 
     def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, literal_loops=False):
         self.method_id = None
@@ -78,7 +92,7 @@ class OracleFacade(object):
         """base_facade.py:58-91."""
         self.source_surrogates = list()
         for X, y in self.source_hpo_data:
-            model = OracleGP(self.types, self.random_seed)
+            model = self._new_model()
             X = np.asarray(X, dtype=np.float64)[:self.num_src_hpo_trial]
             y = np.array(y, dtype=np.float64)[:self.num_src_hpo_trial]
             if normalize == 'standardize':
@@ -99,7 +113,7 @@ class OracleFacade(object):
     def build_single_surrogate(self, X, y, normalize):
         """base_facade.py:93-108 (mutates the caller's ``y`` in the all-equal case)."""
         assert normalize in ['standardize', 'scale', 'none']
-        model = OracleGP(self.types, self.random_seed)
+        model = self._new_model()
         if normalize == 'standardize':
             if (y == y[0]).all():
                 y[0] += 1e-4
