@@ -74,14 +74,18 @@ __device__ double mcmc_logprob(const FitWs& S, const SpaceDesc& sp, double* th, 
     inside = !(v < lo_raw[tid] || v > hi_raw[tid]) && (t == t);
   }
   if (!__syncthreads_and(inside ? 1 : 0)) return -INFINITY;
-  const bool ok = build_and_eliminate_any<T>(S, sp, th, false);
-  if (!ok) return -INFINITY;                     // sklearn: LinAlgError -> -inf
-  double part = 0.0;
-  for (int k = tid; k < n; k += blockDim.x) {
-    const double z = S.A[(size_t)n * S.lda + k];
-    part += 0.5 * z * z + 0.5 * log(S.piv[k]);
+  double nll_data;
+  if constexpr (T > 0) {
+    if (!lml_eliminate_reg<T>(S, sp, th, &nll_data)) return -INFINITY;      // sklearn: LinAlgError -> -inf
+  } else {
+    if (!build_and_eliminate(S, sp, th, false)) return -INFINITY;
+    double part = 0.0;
+    for (int k = tid; k < n; k += blockDim.x) {
+      const double z = S.A[(size_t)n * S.lda + k];
+      part += 0.5 * z * z + 0.5 * log(S.piv[k]);
+    }
+    nll_data = block_sum(part, S.red);
   }
-  const double nll_data = block_sum(part, S.red);
   double lml = -nll_data - 0.5 * (double)n * LOG_2PI;
   // priors in the reference's order: [lognormal, tophat] on c, [tophat] per length scale,
   // [horseshoe(0.1), tophat] on the noise (base_gp.py:92-132); the tophats contribute 0 here
@@ -200,9 +204,8 @@ static McmcLayout plan_mcmc(int ncap, int d) {
   McmcLayout w;
   const size_t panel = fit_panel_bytes(ncap);
   int tile = panel_tile_for(ncap);
-  int cache = tile > 0 ? 1 : 0;
+  int cache = 0;                       // no gradient: the pair-value caches are not needed
   size_t small = fit_small_bytes(ncap, d, tile, cache);
-  if (tile > 0 && small + panel + 1024 > kSmemLimitMcmc) { cache = 0; small = fit_small_bytes(ncap, d, tile, 0); }
   if (tile > 0 && small + panel + 1024 > kSmemLimitMcmc) { tile = 0; small = fit_small_bytes(ncap, d, 0, 0); }
   w.tile = tile; w.cache = cache;
   w.global_panels = (small + panel + 1024) > kSmemLimitMcmc;

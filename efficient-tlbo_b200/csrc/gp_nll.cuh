@@ -229,7 +229,10 @@ struct ElimCtx {
   double* colbuf; double* pivs; int n; int tx, ty; bool diag_lower, own_diag; double ip_next; bool bad;
 };
 
-template <int T, int KB>
+// LOWER_ONLY: only the lower part (Cholesky factor and the y row) is eliminated -- what the
+// gradient-free log-likelihood of the MCMC sampler needs; the inverse-part tiles are skipped (the
+// upper-part threads of diagonal tiles compute values nobody reads).
+template <int T, int KB, bool LOWER_ONLY = false>
 __device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
   constexpr int TP = (T + 1) & ~1;             // packed per-lane stride (128-bit chunks)
   const int n = c.n, tx = c.tx, ty = c.ty;
@@ -273,8 +276,12 @@ __device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
       for (int ia = 0; ia < T; ia++) {
         if (ia > jb) a[ia][jb] -= ck_lo[ia] * f;                        // lower part (and the y row)
         else if (ia < jb) {                                             // inverse part
-          if (ia < KB) a[ia][jb] -= ck_lo[ia] * f;
-          else if (ia == KB) a[ia][jb] -= ck_up_kb * f;
+          if constexpr (!LOWER_ONLY) {
+            if (ia < KB) a[ia][jb] -= ck_lo[ia] * f;
+            else if (ia == KB) a[ia][jb] -= ck_up_kb * f;
+          }
+        } else if constexpr (LOWER_ONLY) {                              // diagonal tile, lower threads matter
+          a[ia][jb] -= ck_lo[ia] * f;
         } else {                                                        // diagonal tile
           const double cu = (ia < KB) ? ck_lo[ia] : ((ia == KB) ? ck_up_kb : 0.0);
           a[ia][jb] -= (c.diag_lower ? ck_lo[ia] : cu) * f;
@@ -291,10 +298,10 @@ __device__ __forceinline__ void elim_block(double (&a)[T][T], ElimCtx& c) {
   }
 }
 
-template <int T, int KB>
+template <int T, int KB, bool LOWER_ONLY = false>
 __device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
-  if (16 * KB < c.n) elim_block<T, KB>(a, c);
-  if constexpr (KB + 1 < T) elim_all<T, KB + 1>(a, c);
+  if (16 * KB < c.n) elim_block<T, KB, LOWER_ONLY>(a, c);
+  if constexpr (KB + 1 < T) elim_all<T, KB + 1, LOWER_ONLY>(a, c);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -429,6 +436,93 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
   }
   __syncthreads();
   PHASE_MARK(3);
+  return true;
+}
+
+// Gradient-free variant for the MCMC sampler (gp_mcmc.cu): kernel matrix + LOWER_ONLY elimination,
+// then  sum_k [ z_k^2 / 2 + log(piv_k) / 2 ]  (z = L^-1 y) straight from the register tiles -- no
+// panel write-back, no alpha, no pair-value caches.  Returns false (uniformly) on a non-positive
+// pivot; *nll_data is uniform on return.
+template <int T>
+__device__ bool lml_eliminate_reg(const FitWs& S, const SpaceDesc& sp, const double* theta, double* nll_data) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int tx = tid >> 4, ty = tid & 15;
+  double* A = S.A;
+  __syncthreads();
+  const int pcol = tid & 31;
+  double myscale = 1.0;
+  if (pcol < d) {
+    const double l = exp(theta[1 + pcol]);
+    myscale = (pcol < dc) ? 1.0 / l : 1.0;
+    if (tid < d && tid >= dc) S.hyp[tid] = 1.0 / (2.0 * l * l);
+  }
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  if (pcol < d)
+    for (int i = tid >> 5; i < n; i += NT >> 5) S.Xs[(size_t)i * d + pcol] = S.Xr[(size_t)i * d + pcol] * myscale;
+  __syncthreads();
+  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
+    const int q1 = q0 + NT;
+    const bool has1 = q1 < S.npairs;
+    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
+    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
+    const double* xi0 = S.Xs + (size_t)i0 * d;
+    const double* xj0 = S.Xs + (size_t)j0 * d;
+    const double* xi1 = S.Xs + (size_t)i1 * d;
+    const double* xj1 = S.Xs + (size_t)j1 * d;
+    double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+    for (int p = 0; p < dc; p++) {
+      const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
+      s0 += e0 * e0; s1 += e1 * e1;
+    }
+    for (int p = dc; p < d; p++) {
+      const double hp = S.hyp[p];
+      h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
+      h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
+    }
+    const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
+    const double v0 = c * exp_nonpos(-t0 - h0) * (1.0 + t0 + t0 * t0 / 3.0);
+    const double v1 = c * exp_nonpos(-t1 - h1) * (1.0 + t1 + t1 * t1 / 3.0);
+    A[(size_t)i0 * lda + j0] = v0;
+    if (has1) A[(size_t)i1 * lda + j1] = v1;
+  }
+  for (int j = tid; j < n; j += NT) {
+    A[(size_t)j * lda + j] = c + noise;
+    A[(size_t)n * lda + j] = S.y[j];
+  }
+  __syncthreads();
+  double a[T][T];
+#pragma unroll
+  for (int ia = 0; ia < T; ia++) {
+    const int i = ty + 16 * ia;
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+      const int j = tx + 16 * jb;
+      a[ia][jb] = (i <= n && j < n && i >= j) ? A[(size_t)i * lda + j] : 0.0;
+    }
+  }
+  ElimCtx ec;
+  ec.colbuf = S.colbuf; ec.pivs = S.piv; ec.n = n; ec.tx = tx; ec.ty = ty;
+  ec.diag_lower = ty >= tx; ec.own_diag = ty == tx; ec.ip_next = 0.0; ec.bad = false;
+  ec.ip_next = fast_rcp(a[0][0]);
+  elim_all<T, 0, true>(a, ec);
+  const bool ok = !__syncthreads_or(ec.bad ? 1 : 0);      // also orders the pivots in S.piv
+  if (!ok) return false;
+  // the owner of (row n, column k) holds z_k sqrt(piv_k); pivots come from shared memory
+  double part = 0.0;
+#pragma unroll
+  for (int ia = 0; ia < T; ia++) {
+    if (ty + 16 * ia == n) {
+#pragma unroll
+      for (int jb = 0; jb < T; jb++) {
+        const int k = tx + 16 * jb;
+        if (k < n) { const double v = a[ia][jb]; part += 0.5 * (v * v) / S.piv[k]; }
+      }
+    }
+  }
+  for (int k = tid; k < n; k += NT) part += 0.5 * log(S.piv[k]);
+  *nll_data = block_sum(part, S.red);
   return true;
 }
 

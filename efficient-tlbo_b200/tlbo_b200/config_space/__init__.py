@@ -12,9 +12,13 @@ class TableSpace(object):
     """Search-space descriptor: ``types[d]`` (0 = continuous / integer / constant,
     k > 0 = categorical with k choices) and per-column bounds as ``get_types`` returns."""
 
-    def __init__(self, types, bounds=None, default=None):
+    def __init__(self, types, bounds=None, default=None, const_mask=None):
         self.types = np.asarray(types, dtype=np.uint)
         d = len(self.types)
+        # columns holding a Constant hyper-parameter (encoded 0, no neighbours, never sampled)
+        self.const_mask = (np.zeros(d, dtype=bool) if const_mask is None
+                           else np.asarray(const_mask, dtype=bool).reshape(d))
+        self._rng = np.random.RandomState()
         if bounds is None:
             bounds = [(float(t), np.nan) if t > 0 else (0.0, 1.0) for t in self.types]
         self.bounds = np.array(bounds, dtype=object)
@@ -22,7 +26,30 @@ class TableSpace(object):
         self._seed = None
 
     def seed(self, seed):
+        """``ConfigurationSpace.seed``: re-seeds the sampler behind ``sample_configuration``."""
         self._seed = seed
+        self._rng = np.random.RandomState(seed)
+
+    def sample_array(self, size):
+        """``size`` configurations in the reference's array encoding: unit-interval floats for
+        numerical columns, choice indices for categorical ones, 0 for constants (column by
+        column from the space's own RandomState, like ConfigSpace's vectorised sampler)."""
+        d = len(self.types)
+        X = np.zeros((int(size), d), dtype=np.float64)
+        for j in range(d):
+            if self.types[j] > 0:
+                X[:, j] = self._rng.randint(0, int(self.types[j]), size=int(size))
+            elif not self.const_mask[j]:
+                X[:, j] = self._rng.uniform(0.0, 1.0, size=int(size))
+        return X
+
+    def sample_configuration(self, size=1):
+        """``ConfigurationSpace.sample_configuration``: one Configuration for ``size == 1``, a
+        list otherwise."""
+        X = self.sample_array(size)
+        if size == 1:
+            return Configuration(self, X[0], -1)
+        return [Configuration(self, X[i], -1) for i in range(X.shape[0])]
 
     def get_types(self):
         return self.types.copy(), self.bounds.copy()
@@ -82,3 +109,68 @@ def convert_configurations_to_array(configs):
 
 def table_to_configurations(space, X):
     return [Configuration(space, X[i], i) for i in range(X.shape[0])]
+
+
+def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=4, stdev=0.2):
+    """The complete one-exchange neighbourhood of ``config`` as an array ``[m, d]``, in the order
+    ConfigSpace 0.4.x's lazy generator ``util.get_one_exchange_neighbourhood(configuration,
+    seed)`` would yield it (the reference calls it at tlbo/optimizer/ei_optimization.py:266-267;
+    ConfigSpace itself is an un-vendored dependency, restated from its published algorithm):
+
+    a private ``RandomState(seed)`` repeatedly picks a hyper-parameter index; a numerical column
+    yields ONE neighbour per pick -- ``normal(value, stdev)`` redrawn until it falls in [0, 1] --
+    up to ``num_neighbors`` picks; a categorical column's other choices are shuffled once on its
+    first pick and popped one per pick; constants have no neighbours.  Because the generator's
+    random stream is private, materialising the whole (finite) neighbourhood up front yields the
+    same sequence the lazy consumer would have seen -- which is what lets the local search score
+    a full neighbourhood in one device launch."""
+    space = config.space
+    array = config.get_array()
+    d = len(array)
+    random = np.random.RandomState(seed)
+    types = space.types
+    remaining = np.zeros(d, dtype=np.int64)
+    for j in range(d):
+        if types[j] > 0:
+            remaining[j] = int(types[j]) - 1
+        elif not space.const_mask[j]:
+            remaining[j] = num_neighbors
+    usable = int(np.sum(np.isfinite(array)))
+    used = int(np.sum((remaining == 0) & np.isfinite(array)))
+    stacks = {}
+    out = []
+    while used < usable:
+        index = int(random.randint(d))
+        if remaining[index] == 0 or not np.isfinite(array[index]):
+            continue
+        value = array[index]
+        if types[index] > 0:
+            if index not in stacks:
+                neighbors = [float(c) for c in range(int(types[index])) if c != int(value)]
+                random.shuffle(neighbors)
+                stacks[index] = neighbors
+            neighbor = stacks[index].pop()
+        else:
+            neighbor = None
+            for _ in range(101):                       # "no infinite loops" guard of the generator
+                cand = random.normal(value, stdev)
+                if 0.0 <= cand <= 1.0:
+                    neighbor = cand
+                    break
+            if neighbor is None:
+                remaining[index] = 0
+                used += 1
+                continue
+        new_array = array.copy()
+        new_array[index] = neighbor
+        out.append(new_array)
+        remaining[index] -= 1
+        if remaining[index] == 0:
+            used += 1
+    return np.array(out, dtype=np.float64).reshape(-1, d)
+
+
+def get_one_exchange_neighbourhood(config, seed, num_neighbors=4, stdev=0.2):
+    """Generator form (the reference's call signature, tlbo/config_space/__init__.py:10)."""
+    for row in one_exchange_neighbourhood_arrays(config, seed, num_neighbors, stdev):
+        yield Configuration(config.space, row, -1)
