@@ -1,0 +1,180 @@
+"""Acquisition maximisers of the ONLINE scenario on the device path
+(reference tlbo/optimizer/ei_optimization.py: ``LocalSearch`` :135-294, ``RandomSearch``
+:297-357, ``InterleavedLocalAndRandomSearch`` :360-475, ``ChallengerList`` :478-524;
+wired in by tlbo/framework/online/smbo_online.py:18-26).
+
+The reference scores ONE neighbour per acquisition call inside each hill-climb
+(``_one_iter``, :270-281): ~10^2 sequential calls per maximisation, each a Python loop over
+K + 1 GP predicts.  Here a hill-climb step scores the incumbent's WHOLE one-exchange
+neighbourhood in one fused ensemble-predict + EI launch and then takes the first improving
+neighbour -- exactly the neighbour the reference's early ``break`` would have stopped at,
+because the neighbourhood generator draws from a private ``RandomState(seed)`` (so
+materialising it eagerly changes no stream) and the acquisition is deterministic.  The ten
+start points are scored in one launch, the ~4990 random configurations in another.  Every
+draw from the shared ``rng`` (ordering keys, per-step generator seeds, the tie-break shuffle,
+the interleaving chooser) happens in the reference's order."""
+import logging
+
+import numpy as np
+
+from tlbo_b200.config_space import Configuration, convert_configurations_to_array, one_exchange_neighbourhood_arrays
+from tlbo_b200.optimizer.ei_offline_optimizer import AcquisitionFunctionMaximizer
+from tlbo_b200.optimizer.random_configuration_chooser import ChooserProb
+
+
+class _SortMixin(object):
+    def _sort_configs_by_acq_value(self, configs):
+        """ei_optimization.py:106-132: descending by acquisition value, ties by a fresh
+        ``rng.rand(N)`` key."""
+        acq_values = self.acquisition_function(configs)
+        random = self.rng.rand(len(acq_values))
+        indices = np.lexsort((random.flatten(), acq_values.flatten()))
+        return [(acq_values[ind][0], configs[ind]) for ind in indices[::-1]]
+
+
+class LocalSearch(_SortMixin, AcquisitionFunctionMaximizer):
+    def __init__(self, acquisition_function, config_space, rng=None, max_steps=None, n_steps_plateau_walk=10):
+        super().__init__(acquisition_function, config_space, rng)
+        self.max_steps = max_steps
+        self.n_steps_plateau_walk = n_steps_plateau_walk
+        self.logger = logging.getLogger(self.__module__ + '.' + self.__class__.__name__)
+        self.last_stats = None
+
+    def _maximize(self, runhistory, num_points, **kwargs):
+        init_points = self._get_initial_points(num_points, runhistory)
+        # the incumbents' own acquisition values do not depend on any random draw: one launch
+        start_acq = self.acquisition_function(init_points) if len(init_points) else np.zeros((0, 1))
+        configs_acq = []
+        stats = dict(steps=0, neighbours=0, launches=1)
+        for i, start_point in enumerate(init_points):
+            acq_val, configuration = self._one_iter(start_point, start_acq[i], stats)
+            configuration.origin = 'Local Search'
+            configs_acq.append((acq_val, configuration))
+        self.last_stats = stats
+        self.rng.shuffle(configs_acq)                       # random tie-break
+        configs_acq.sort(reverse=True, key=lambda x: x[0])
+        return configs_acq
+
+    def _get_initial_points(self, num_points, runhistory):
+        if runhistory.empty():
+            init_points = self.config_space.sample_configuration(size=num_points)
+        else:
+            configs_previous_runs = runhistory.get_all_configs()
+            configs_previous_runs_sorted = self._sort_configs_by_acq_value(configs_previous_runs)
+            num_configs_local_search = int(min(len(configs_previous_runs_sorted), num_points))
+            init_points = list(map(lambda x: x[1], configs_previous_runs_sorted[:num_configs_local_search]))
+        return init_points
+
+    def _one_iter(self, start_point, acq_val_incumbent, stats):
+        """ei_optimization.py:239-294 with the neighbourhood of each step scored in one launch."""
+        incumbent = start_point
+        local_search_steps = 0
+        while True:
+            local_search_steps += 1
+            if local_search_steps % 1000 == 0:
+                self.logger.warning('Local search took already %d iterations. Is it maybe stuck in a infinite loop?',
+                                    local_search_steps)
+            changed_inc = False
+            neighbours = one_exchange_neighbourhood_arrays(incumbent, seed=self.rng.randint(0, 10000))
+            if len(neighbours):
+                acq = self.acquisition_function(neighbours)
+                stats['launches'] += 1
+                better = np.nonzero(acq[:, 0] > acq_val_incumbent[0])[0]
+                # the reference evaluates lazily and stops at the first improvement
+                stats['neighbours'] += int(better[0]) + 1 if len(better) else len(neighbours)
+                if len(better):
+                    j = int(better[0])
+                    incumbent = Configuration(incumbent.space, neighbours[j], -1)
+                    acq_val_incumbent = acq[j]
+                    changed_inc = True
+            stats['steps'] += 1
+            if (not changed_inc) or (self.max_steps is not None and local_search_steps == self.max_steps):
+                break
+        return acq_val_incumbent, incumbent
+
+
+class RandomSearch(_SortMixin, AcquisitionFunctionMaximizer):
+    def _maximize(self, runhistory, num_points, _sorted=False, **kwargs):
+        if num_points > 1:
+            rand_configs = self.config_space.sample_configuration(size=num_points)
+        else:
+            rand_configs = [self.config_space.sample_configuration(size=1)]
+        if _sorted:
+            for c in rand_configs:
+                c.origin = 'Random Search (sorted)'
+            return self._sort_configs_by_acq_value(rand_configs)
+        for c in rand_configs:
+            c.origin = 'Random Search'
+        return [(0, c) for c in rand_configs]
+
+
+class InterleavedLocalAndRandomSearch(AcquisitionFunctionMaximizer):
+    def __init__(self, acquisition_function, config_space, rng=None, max_steps=None, n_steps_plateau_walk=10,
+                 n_sls_iterations=10, rand_prob=0.1):
+        super().__init__(acquisition_function, config_space, rng)
+        # the reference hands the SAME rng object to all three helpers (ei_optimization.py:391-404)
+        self.random_search = RandomSearch(acquisition_function=acquisition_function, config_space=config_space,
+                                          rng=rng)
+        self.local_search = LocalSearch(acquisition_function=acquisition_function, config_space=config_space,
+                                        rng=rng, max_steps=max_steps, n_steps_plateau_walk=n_steps_plateau_walk)
+        self.n_sls_iterations = n_sls_iterations
+        self.random_chooser = ChooserProb(prob=rand_prob, rng=rng if rng is not None else self.rng)
+
+    def maximize(self, runhistory, num_points, random_configuration_chooser=None, **kwargs):
+        if random_configuration_chooser is None:
+            random_configuration_chooser = self.random_chooser
+        next_configs_by_local_search = self.local_search._maximize(runhistory, self.n_sls_iterations, **kwargs)
+        next_configs_by_random_search_sorted = self.random_search._maximize(
+            runhistory, num_points - len(next_configs_by_local_search), _sorted=True)
+        next_configs_by_acq_value = next_configs_by_random_search_sorted + next_configs_by_local_search
+        next_configs_by_acq_value.sort(reverse=True, key=lambda x: x[0])
+        next_configs_by_acq_value = [_[1] for _ in next_configs_by_acq_value]
+        challengers = ChallengerList(next_configs_by_acq_value, self.config_space, random_configuration_chooser)
+        random_configuration_chooser.next_smbo_iteration()
+        return challengers
+
+    def _maximize(self, runhistory, num_points, **kwargs):
+        raise NotImplementedError()
+
+
+class ChallengerList(object):
+    """ei_optimization.py:478-524: interleaves freshly sampled random configurations by the
+    chooser's rule while iterating over the sorted challengers."""
+
+    def __init__(self, challengers, configuration_space, random_configuration_chooser):
+        self.challengers = challengers
+        self.configuration_space = configuration_space
+        self._index = 0
+        self._iteration = 1
+        self.random_configuration_chooser = random_configuration_chooser
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._index == len(self.challengers):
+            raise StopIteration
+        if self.random_configuration_chooser.check(self._iteration):
+            config = self.configuration_space.sample_configuration()
+            config.origin = 'Random Search'
+        else:
+            config = self.challengers[self._index]
+            self._index += 1
+        self._iteration += 1
+        return config
+
+
+class HistoryContainer(object):
+    """The two methods of tlbo/utils/history_container.py the maximisers use."""
+
+    def __init__(self):
+        self.data = dict()
+
+    def add(self, config, perf):
+        self.data[config] = perf
+
+    def empty(self):
+        return len(self.data) == 0
+
+    def get_all_configs(self):
+        return list(self.data.keys())

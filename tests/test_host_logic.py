@@ -67,9 +67,11 @@ def test_unsupported_surrogates_raise():
     from tlbo_b200.facade.rgpe import RGPE
     from tlbo_b200.model.model_builder import build_model
     cs = TableSpace([0, 0])
-    for kind in ('rf', 'gp_mcmc', 'gp_rbf'):
+    for kind in ('rf', 'gp_rbf'):
         with pytest.raises(ValueError):
             build_model(kind, cs, np.random.RandomState(0))
+    m = build_model('gp_mcmc', cs, np.random.RandomState(0))       # model_builder.py:74-89
+    assert (m.n_mcmc_walkers, m.burnin_steps, m.chain_length) == (12, 250, 250)
     with pytest.raises(ValueError):
         build_model('nonsense', cs, np.random.RandomState(0))
     with pytest.raises(ValueError):
