@@ -167,14 +167,50 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_mcmc_kernel(McmcArgs a) {
 // gp_mcmc.py:418-440: m = mean_w mu_w, v = var_w(mu_w) + mean_w(var_w), clipped at machine eps.
 // Sums run over the walkers in order with separately rounded operations, as numpy's
 // add.reduce over axis 0 does.
-__global__ void mcmc_marginalize_kernel(const double* __restrict__ mu, const double* __restrict__ var, int G, int W,
-                                        long long N, double* __restrict__ gmu, double* __restrict__ gvar) {
+template <int WC>
+__device__ __forceinline__ void marginalize_one(const double* __restrict__ pm, const double* __restrict__ pv, int W,
+                                                long long N, double* gm, double* gv) {
+  // the walkers' values stay in registers between the mean pass and the deviation pass when
+  // W <= WC (34 for the reference's spaces with d = 9), so HBM is read exactly once
+  double vals[WC];
+  double sm = 0.0, sv = 0.0;
+#pragma unroll
+  for (int w = 0; w < WC; w++) {
+    if (w < W) {
+      const double x = pm[(size_t)w * N], y = pv[(size_t)w * N];
+      vals[w] = x;
+      sm = (w == 0) ? x : __dadd_rn(sm, x);
+      sv = (w == 0) ? y : __dadd_rn(sv, y);
+    }
+  }
+  const double m = sm / (double)W;
+  double ss = 0.0;
+#pragma unroll
+  for (int w = 0; w < WC; w++) {
+    if (w < W) {
+      const double dw = __dsub_rn(vals[w], m);
+      const double sq = __dmul_rn(dw, dw);
+      ss = (w == 0) ? sq : __dadd_rn(ss, sq);
+    }
+  }
+  double v = __dadd_rn(ss / (double)W, sv / (double)W);
+  const double eps = 2.220446049250313e-16;
+  if (v < eps) v = eps;            // np.clip(v, eps, inf); nan stays nan
+  *gm = m;
+  *gv = v;
+}
+
+__global__ void __launch_bounds__(256) mcmc_marginalize_kernel(const double* __restrict__ mu,
+                                                               const double* __restrict__ var, int G, int W,
+                                                               long long N, double* __restrict__ gmu,
+                                                               double* __restrict__ gvar) {
   const long long total = (long long)G * N;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long g = idx / N, j = idx - g * N;
     const double* pm = mu + (size_t)g * W * N + j;
     const double* pv = var + (size_t)g * W * N + j;
+    if (W <= 48) { marginalize_one<48>(pm, pv, W, N, gmu + idx, gvar + idx); continue; }
     double sm = pm[0], sv = pv[0];
     for (int w = 1; w < W; w++) {
       sm = __dadd_rn(sm, pm[(size_t)w * N]);
@@ -189,7 +225,7 @@ __global__ void mcmc_marginalize_kernel(const double* __restrict__ mu, const dou
     }
     double v = __dadd_rn(ss / (double)W, sv / (double)W);
     const double eps = 2.220446049250313e-16;
-    if (v < eps) v = eps;            // np.clip(v, eps, inf); nan stays nan
+    if (v < eps) v = eps;
     gmu[idx] = m;
     gvar[idx] = v;
   }
@@ -309,7 +345,7 @@ extern "C" int tlbo_mcmc_marginalize(const double* d_mu, const double* d_var, in
   if (N == 0) return 0;
   const long long total = (long long)G * N;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   mcmc_marginalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_mu, d_var, G, W, (long long)N, d_gmu,
                                                                                d_gvar);
   TLBO_CUDA_CHECK(cudaGetLastError());

@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
           if (a.mode == 0) {
             acc_mu += wm * mu_m;
             acc_var += wm * wm * var_m;
+          } else if (a.mode == 2) {
+            const double iv = 1.0 / var_m;
+            acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
+            acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
           } else {
             if (mi == 0) { acc_mu = mu_m; acc_var = var_m; }
             else { acc_mu += wm * mu_m; wsum += wm; }
@@ -482,6 +486,10 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
         if (a.mode == 0) {
           acc_mu += wm * mu_m;
           acc_var += wm * wm * var_m;
+        } else if (a.mode == 2) {
+          const double iv = 1.0 / var_m;
+          acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
+          acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
         } else {
           if (mi == 0) { acc_mu = mu_m; acc_var = var_m; }
           else { acc_mu += wm * mu_m; wsum += wm; }
@@ -495,6 +503,13 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
       if (row < a.N) {
         double mu = acc_mu, var = acc_var;
         if (a.mode == 1) mu = mu / (0.75 + wsum);
+        if (a.mode == 2) {
+          // POGPE (pogpe.py:57-60): precision-weighted product of experts
+          double tmp = acc_var;
+          if (tmp == 0.0) tmp = 1e-5;
+          var = 1.0 / tmp;
+          mu = __dmul_rn(acc_mu, var);
+        }
         if (var < a.var_floor) var = a.var_floor;
         if (var != var) var = a.var_floor;
         const double s = sqrt(var);

@@ -83,6 +83,13 @@ class EI(AbstractAcquisitionFunction):
         if len(X.shape) == 1:
             X = X[:, np.newaxis]
         self._require_eta()
+        if hasattr(self.model, 'acq_small') and not hasattr(X, 'is_cuda'):
+            # small host query sets (online local search): mapped pinned buffers, one synchronisation
+            fast = self.model.acq_small(X, self.eta, self.par, self._var_floor())
+            if fast is not None:
+                if fast[1] > 0:
+                    raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")
+                return fast[0].reshape((-1, 1))
         res, mu, var, ei = self._fused(self._to_device(X), want_rows=True)
         if res[3] > 0:
             raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")

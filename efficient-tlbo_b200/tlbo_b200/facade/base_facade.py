@@ -24,6 +24,7 @@ from tlbo_b200.utils.constants import VERY_SMALL_NUMBER
 from tlbo_b200.utils.normalization import zero_mean_unit_var_normalization, zero_one_normalization
 
 N_CV_SLOTS = 5
+SMALL_QUERY_ROWS = 2048      # at or below: per-(row, surrogate) warps instead of the pool-tile kernel
 
 
 def _history_to_arrays(hist):
@@ -67,6 +68,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self._mcmc_steps = mcmc_steps       # (burn-in, chain) override of the reference's (250, 250)
         self._mcmc_shared = {}              # initial ensemble + random tables shared by identically seeded models
         self._logical_pack = None           # K + 1 placeholder slots for the all-resident fused call
+        self._small = None                  # pinned buffers of the small-query acquisition path
         self.instance_features = None
         self.var_threshold = VERY_SMALL_NUMBER
         self.w = None
@@ -206,9 +208,21 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
                want_rows=False, ws=None, sync=True):
         from tlbo_b200 import ops
         w, skip, order = self._ensemble_args()
-        dw = ops.h2d(np.ascontiguousarray(w, dtype=np.float64))
-        dskip = None if skip is None else ops.h2d(np.ascontiguousarray(skip, dtype=np.int32))
-        dorder = None if order is None else ops.h2d(np.ascontiguousarray(order, dtype=np.int32))
+        dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
+        dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
+        dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+        N = int(X_dev.shape[0])
+        if N <= SMALL_QUERY_ROWS and (X_dev.data_ptr(), N) not in self._pool_cache:
+            # small ad-hoc query sets (the online scenario's neighbourhoods and sampled configurations):
+            # a pool tile is scored by ONE CTA walking the surrogates in turn, which leaves the device
+            # idle here -- instead one warp per (row, surrogate) evaluates every posterior in parallel
+            # (tlbo_gp_predict [+ tlbo_mcmc_marginalize]) and the fused kernel only combines, scores
+            # and reduces the resident posteriors
+            mu, var = self._predict_slots(0, self.K + 1, X_dev)
+            return ops.predict_ei_fused(self._logical(), self.types, dw, dskip, X_dev, eta, par=par,
+                                        var_floor=var_floor, keys=keys, excluded=excluded, idx_offset=idx_offset,
+                                        mode=self._fused_mode, order=dorder, want_rows=want_rows, ws=ws, sync=sync,
+                                        nmax=8, cache=(mu, var))
         if self._G > 1:
             # marginalised per-surrogate posteriors, all resident: sources from the pool cache (or
             # computed now for an ad-hoc query), the target's W walker GPs evaluated and
@@ -225,6 +239,38 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         return ops.predict_ei_fused(view, self.types, dw, dskip, X_dev, eta, par=par, var_floor=var_floor,
                                     keys=keys, excluded=excluded, idx_offset=idx_offset, mode=self._fused_mode,
                                     order=dorder, want_rows=want_rows, ws=ws, sync=sync, nmax=nmax, cache=cache)
+
+    def acq_small(self, X, eta, par, var_floor):
+        """EI of a small host query set ``X [N, d]`` (N <= SMALL_QUERY_ROWS) through mapped pinned
+        buffers: returns ``(ei float64[N], n_negative)``, or None when this facade has no fast path
+        (walker groups).  Same kernels, same values as ``_fused(want_rows=True)``."""
+        import torch
+        from tlbo_b200 import ops
+        N = int(X.shape[0])
+        if self._G > 1 or N == 0 or N > SMALL_QUERY_ROWS:
+            return None
+        if self.target_surrogate is None:
+            raise ValueError('Target surrogate is none.')
+        sq = self._small
+        if sq is None or sq.cap < N:
+            sq = self._small = ops.SmallQuery(max(256, 2 * N), len(self.types), self.K + 1)
+        Xp = sq.X_np[:N]
+        Xp[...] = X
+        Xp[~np.isfinite(Xp)] = -1
+        w, skip, order = self._ensemble_args()
+        dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
+        dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
+        dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+        Xq = sq.Xd[:N]
+        Xq.copy_(sq.X[:N], non_blocking=True)
+        mu, var = ops.gp_predict(ops.pack_view(self._pack, 0, self.K + 1), self.types, Xq, out=(sq.mu, sq.var))
+        ops.predict_ei_fused(self._logical(), self.types, dw, dskip, Xq, eta, par=par, var_floor=var_floor,
+                             mode=self._fused_mode, order=dorder, ws=sq.ws, sync=False, nmax=8, cache=(mu, var),
+                             rows=(sq.mu_rows, sq.var_rows, sq.ei))
+        torch.cuda.current_stream().synchronize()
+        ops.STATS.h2d += N * len(self.types) * 8
+        ops.STATS.d2h += N * 8 + 32
+        return sq.ei_np[:N].copy(), int(sq.best_np[3])
 
     # ---- MCMC-marginalised surrogates: group-level posteriors ----------------------------------
     def _logical(self):

@@ -233,6 +233,20 @@ def _cached_const(a):
     return t
 
 
+def cached_upload(a):
+    """Small host arrays that repeat from call to call (ensemble weights / skip flags / slot order
+    within one maximisation): uploaded once per distinct value."""
+    a = np.ascontiguousarray(a)
+    key = (a.dtype.str, a.shape, a.tobytes(), torch.cuda.current_device())
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) > 256:
+            _CONST_CACHE.clear()
+        t = h2d(a)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0, do_optimize=True,
                    return_restarts=False, sync=True):
     """``tlbo_gp_fit_batched``.  X_list/y_list: per-surrogate host arrays (y already
@@ -321,15 +335,20 @@ def gp_nll_grad_batched(X_list, y_list, types, thetas):
     return d2h(nll), d2h(grad), d2h(status)
 
 
-def gp_predict(pack, types, Xq):
+def gp_predict(pack, types, Xq, out=None):
     """``tlbo_gp_predict``: per-surrogate mean / variance at a small query set.
-    Xq: device tensor or host array [Nq, d].  Returns device tensors mu, var [M, Nq]."""
+    Xq: device tensor (or pinned host tensor, read over UVA) or host array [Nq, d].  Returns device
+    tensors mu, var [M, Nq] (``out`` = preallocated contiguous buffers with at least that many elements)."""
     dev = _dev()
     if not torch.is_tensor(Xq):
         Xq = h2d(np.ascontiguousarray(Xq, dtype=np.float64))
     Nq = int(Xq.shape[0])
-    mu = torch.empty(pack.M, Nq, dtype=F64, device=dev)
-    var = torch.empty(pack.M, Nq, dtype=F64, device=dev)
+    if out is not None:
+        mu = out[0].view(-1)[:pack.M * Nq].view(pack.M, Nq)
+        var = out[1].view(-1)[:pack.M * Nq].view(pack.M, Nq)
+    else:
+        mu = torch.empty(pack.M, Nq, dtype=F64, device=dev)
+        var = torch.empty(pack.M, Nq, dtype=F64, device=dev)
     if Nq == 0:
         return mu, var
     t = _types_arr(types)
@@ -339,16 +358,40 @@ def gp_predict(pack, types, Xq):
 
 
 class FusedWorkspace(object):
-    """Reusable scratch + result buffers of ``tlbo_predict_ei_fused``."""
+    """Reusable scratch + result buffers of ``tlbo_predict_ei_fused`` (``pinned_best``: the 4-double
+    result lands in mapped pinned host memory, readable after a stream synchronisation)."""
 
-    def __init__(self):
+    def __init__(self, pinned_best=False):
         dev = _dev()
         self.work = torch.empty(int(lib.tlbo_predict_ei_workspace_bytes(0)), dtype=torch.uint8, device=dev)
-        self.best = torch.zeros(4, dtype=F64, device=dev)
+        self.best = torch.zeros(4, dtype=F64).pin_memory() if pinned_best else torch.zeros(4, dtype=F64, device=dev)
+
+
+class SmallQuery(object):
+    """Buffers of the low-overhead acquisition call on a small ad-hoc query set (the online
+    scenario's neighbourhoods): the rows go up with one asynchronous copy from a pinned staging
+    buffer and EI comes back through mapped pinned host memory (UVA stores), so one call is two
+    launches and ONE stream synchronisation -- no blocking memcpy, no allocation."""
+
+    def __init__(self, cap, d, M):
+        dev = _dev()
+        self.cap = int(cap)
+        self.X = torch.zeros(self.cap, d, dtype=F64).pin_memory()
+        self.X_np = self.X.numpy()
+        self.Xd = torch.zeros(self.cap, d, dtype=F64, device=dev)
+        self.ei = torch.zeros(self.cap, dtype=F64).pin_memory()
+        self.ei_np = self.ei.numpy()
+        self.mu_rows = torch.zeros(self.cap, dtype=F64, device=dev)
+        self.var_rows = torch.zeros(self.cap, dtype=F64, device=dev)
+        self.mu = torch.zeros(M * self.cap, dtype=F64, device=dev)
+        self.var = torch.zeros(M * self.cap, dtype=F64, device=dev)
+        self.ws = FusedWorkspace(pinned_best=True)
+        self.best_np = self.ws.best.numpy()
 
 
 def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, keys=None, excluded=None,
-                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True, nmax=0, cache=None):
+                     idx_offset=0, mode=0, order=None, want_rows=False, ws=None, sync=True, nmax=0, cache=None,
+                     rows=None):
     """``tlbo_predict_ei_fused``.  All array arguments are DEVICE tensors (cand [N, d],
     w [M], skip int32[M] or None, keys [N] or None, excluded sorted int64 or None).
     Returns (ei, key, idx, n_negative) of the best non-excluded row (host floats when
@@ -357,7 +400,9 @@ def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, 
     N = int(cand.shape[0])
     ws = ws or FusedWorkspace()
     mu = var = ei = None
-    if want_rows:
+    if rows is not None:
+        mu, var, ei = rows            # caller-provided per-row outputs (device or pinned host, >= N elements)
+    elif want_rows:
         mu = torch.empty(N, dtype=F64, device=dev)
         var = torch.empty(N, dtype=F64, device=dev)
         ei = torch.empty(N, dtype=F64, device=dev)
@@ -382,7 +427,7 @@ def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, 
         return ws.best, mu, var, ei
     b = d2h(ws.best)
     res = (float(b[0]), float(b[1]), int(b[2]), int(b[3]))
-    if want_rows:
+    if want_rows or rows is not None:
         return res, mu, var, ei
     return res
 

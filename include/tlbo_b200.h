@@ -132,6 +132,8 @@ int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, const double*
  *   mode              0: mu = sum w mu_m, var = sum w^2 var_m   (RGPE / 'idp_lc')
  *                     1: TST (tst.py:64-73): first slot in order = target t,
  *                        mu = (mu_t + sum_{m != t} w_m mu_m) / (0.75 + sum_{m != t} w_m), var = var_t
+ *                     2: POGPE / "gogpe" (pogpe.py:36-60): product of experts,
+ *                        var = 1 / sum_m (w_m / var_m) (a zero sum -> 1e-5), mu = var * sum_m (w_m mu_m / var_m)
  *   d_cand [N, d]     candidate rows, reference column order
  *   eta, par          EI incumbent and xi
  *   var_floor         facade / model variance threshold (1e-10 or 1e-5)
