@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 OBJ_DIR = os.path.join(PKG, 'build')
 LIB = os.path.join(LIB_DIR, 'libtlbo_b200.so')
-SOURCES = ['c_api.cu', 'gp_fit.cu', 'gp_mcmc.cu', 'gp_predict.cu', 'weights.cu']
+SOURCES = ['c_api.cu', 'gp_fit.cu', 'gp_mcmc.cu', 'gp_predict.cu', 'host_search.cu', 'weights.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-diag-suppress', '550']
 

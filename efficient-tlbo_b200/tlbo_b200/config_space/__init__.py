@@ -67,19 +67,25 @@ class Configuration(object):
 
     def __init__(self, space, array, index=-1):
         self.space = space
-        self.array = np.asarray(array, dtype=np.float64)
+        self.array = array if (type(array) is np.ndarray and array.dtype == np.float64) else np.asarray(
+            array, dtype=np.float64)
         self.index = int(index)
         self.origin = None
-        self._key = self.array.tobytes()
+        self._key = None                 # value key, built on first comparison / hash
 
     def get_array(self):
         return self.array
 
+    def key(self):
+        if self._key is None:
+            self._key = self.array.tobytes()
+        return self._key
+
     def __eq__(self, other):
-        return isinstance(other, Configuration) and self._key == other._key
+        return isinstance(other, Configuration) and self.key() == other.key()
 
     def __hash__(self):
-        return hash(self._key)
+        return hash(self.key())
 
     def __repr__(self):
         return 'Configuration(index=%d, %s)' % (self.index, np.array2string(self.array, precision=4))
@@ -111,8 +117,11 @@ def table_to_configurations(space, X):
     return [Configuration(space, X[i], i) for i in range(X.shape[0])]
 
 
-def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=4, stdev=0.2):
-    """The complete one-exchange neighbourhood of ``config`` as an array ``[m, d]``, in the order
+def one_exchange_neighbourhood_arrays_py(config, seed, num_neighbors=4, stdev=0.2):
+    """Readable Python statement of ``one_exchange_neighbourhood_arrays`` (the product calls the
+    native ``tlbo_one_exchange_neighbourhood``; tests check the two draw for draw).
+
+    The complete one-exchange neighbourhood of ``config`` as an array ``[m, d]``, in the order
     ConfigSpace 0.4.x's lazy generator ``util.get_one_exchange_neighbourhood(configuration,
     seed)`` would yield it (the reference calls it at tlbo/optimizer/ei_optimization.py:266-267;
     ConfigSpace itself is an un-vendored dependency, restated from its published algorithm):
@@ -168,6 +177,27 @@ def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=4, stdev=0.2):
         if remaining[index] == 0:
             used += 1
     return np.array(out, dtype=np.float64).reshape(-1, d)
+
+
+def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=4, stdev=0.2):
+    """The complete one-exchange neighbourhood of ``config`` as an array ``[m, d]`` (see
+    ``one_exchange_neighbourhood_arrays_py`` for the algorithm), generated by the native helper
+    ``tlbo_one_exchange_neighbourhood`` of the C ABI: the Python loop costs more than the device
+    work of a hill-climb step."""
+    import ctypes
+    from tlbo_b200._cabi import check, lib, ptr
+    space = config.space
+    array = np.ascontiguousarray(config.get_array(), dtype=np.float64)
+    d = len(array)
+    types = np.ascontiguousarray(space.types, dtype=np.int32)
+    cmask = np.ascontiguousarray(space.const_mask, dtype=np.uint8)
+    max_rows = int(np.sum(np.where(types > 0, types - 1, num_neighbors))) + 1
+    out = np.empty((max_rows, d), dtype=np.float64)
+    n = ctypes.c_int32(0)
+    check(lib.tlbo_one_exchange_neighbourhood(ptr(array), d, ptr(types), ptr(cmask), int(seed) & 0xffffffff,
+                                              int(num_neighbors), float(stdev), ptr(out), max_rows,
+                                              ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
+    return out[:n.value]
 
 
 def get_one_exchange_neighbourhood(config, seed, num_neighbors=4, stdev=0.2):

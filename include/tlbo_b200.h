@@ -244,6 +244,20 @@ int64_t tlbo_gp_mcmc_workspace_bytes(int B, int W, int ncap, int d);
 int tlbo_mcmc_marginalize(const double* d_mu, const double* d_var, int G, int W, int64_t N, double* d_gmu,
                           double* d_gvar, void* stream);
 
+/* Host-side helper of the online scenario's local search (no device work): the complete
+ * one-exchange neighbourhood of a configuration in the order ConfigSpace's lazy generator
+ * get_one_exchange_neighbourhood(configuration, seed) yields it -- the call the reference makes once
+ * per hill-climb step (tlbo/optimizer/ei_optimization.py:266-267, tlbo/config_space/__init__.py:10).
+ * Reproduces the generator's private numpy RandomState(seed) stream (legacy MT19937, masked-rejection
+ * randint / shuffle, polar-method normal).
+ *   h_array [d]        the configuration (reference encoding; non-finite = inactive)
+ *   h_types [d]        get_types vector; h_const_mask [d] 1 = Constant hyper-parameter (may be NULL)
+ *   num_neighbors, stdev   ConfigSpace defaults 4 and 0.2
+ *   h_out [max_rows, d], *h_n_rows   neighbours, one changed column per row                      */
+int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t* h_types,
+                                    const uint8_t* h_const_mask, uint32_t seed, int num_neighbors, double stdev,
+                                    double* h_out, int max_rows, int32_t* h_n_rows);
+
 /* Device-rate probes used by bench.py for the roofline denominators (FP64 FMA pipe and
  * FP64 mma.sync rate are not in MEASURED_PEAKS.json).  Returns achieved TFLOP/s in
  * h_out[0] (DFMA) and h_out[1] (DMMA m8n8k4); synchronous.                             */

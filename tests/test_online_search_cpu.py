@@ -41,7 +41,8 @@ class FakeAcq(object):
 
 @pytest.mark.parametrize('types,const', SPACES)
 def test_sampling_and_neighbourhood_match_the_oracle(types, const):
-    from tlbo_b200.config_space import get_one_exchange_neighbourhood, one_exchange_neighbourhood_arrays
+    from tlbo_b200.config_space import (get_one_exchange_neighbourhood, one_exchange_neighbourhood_arrays,
+                                        one_exchange_neighbourhood_arrays_py)
     sp, osp = _spaces(types, const)
     sp.seed(11)
     osp.seed(11)
@@ -57,6 +58,7 @@ def test_sampling_and_neighbourhood_match_the_oracle(types, const):
         got = one_exchange_neighbourhood_arrays(c, seed=100 + i)
         want = list(osp.neighbourhood(c.get_array(), seed=100 + i))
         assert got.shape == (n_expected, len(types))
+        assert np.array_equal(got, one_exchange_neighbourhood_arrays_py(c, seed=100 + i))    # native == Python
         assert np.array_equal(got, np.array(want).reshape(-1, len(types)))
         assert np.all((got != c.get_array()).sum(axis=1) == 1)          # one-exchange
         gen = list(get_one_exchange_neighbourhood(c, seed=100 + i))
@@ -120,3 +122,31 @@ def test_challenger_list_interleaves_random_configurations():
     kept = [c for c in out if any(c is b for b in base)]
     assert kept == list(base) and len(out) > 20
     assert all(c.origin == 'Random Search' for c in out if not any(c is b for b in base))
+
+
+def test_native_neighbourhood_reproduces_numpys_legacy_stream():
+    """Many seeds / spaces: the C helper (own MT19937, masked-rejection randint / shuffle, polar normal)
+    must equal the numpy-driven Python statement bit for bit, including values at the borders of the
+    unit interval (many rejected normal draws) and wide categoricals (long shuffles)."""
+    from tlbo_b200.config_space import (Configuration, TableSpace, one_exchange_neighbourhood_arrays,
+                                        one_exchange_neighbourhood_arrays_py)
+    rng = np.random.RandomState(0)
+    spaces = [TableSpace(RF_TYPES, const_mask=RF_CONST), TableSpace(np.array([7, 0, 0, 13, 2, 0])),
+              TableSpace(np.zeros(12, dtype=int)), TableSpace(np.array([40, 3]))]
+    for sp in spaces:
+        sp.seed(4)
+        X = sp.sample_array(25)
+        cont = np.nonzero((sp.types == 0) & ~sp.const_mask)[0]
+        if len(cont):
+            X[:5, cont[0]] = [0.0, 1.0, 1e-9, 0.999999, 0.5]
+        for i in range(25):
+            c = Configuration(sp, X[i], -1)
+            for seed in (0, 1, int(rng.randint(0, 10000)), 9999, 2 ** 31 + 5):
+                a = one_exchange_neighbourhood_arrays(c, seed)
+                b = one_exchange_neighbourhood_arrays_py(c, seed)
+                assert a.shape == b.shape and np.array_equal(a, b), (sp.types, i, seed)
+    # inactive (non-finite) columns are never exchanged
+    sp = TableSpace(np.array([0, 0, 3]))
+    c = Configuration(sp, np.array([0.3, np.nan, 1.0]), -1)
+    a, b = one_exchange_neighbourhood_arrays(c, 5), one_exchange_neighbourhood_arrays_py(c, 5)
+    assert a.shape == (6, 3) and np.array_equal(a, b, equal_nan=True)
