@@ -23,12 +23,13 @@ import sys
 import threading
 import time
 
-if 'reference' in sys.argv:
-    # the reference pins every BLAS/OpenMP pool to one thread (tools/offline_benchmark.py:3-8);
-    # must happen before numpy is imported
-    for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'VECLIB_MAXIMUM_THREADS',
-               'NUMEXPR_NUM_THREADS'):
-        os.environ[_v] = '1'
+# The reference's driver pins every BLAS/OpenMP pool to one thread (tools/offline_benchmark.py:3-8); must
+# happen before numpy is imported.  Both arms run that way: the CPU arm because the reference mandates it,
+# the CUDA arm because its only host numerics are scipy's SLSQP iterations on 30-variable problems, where a
+# multi-threaded BLAS pool costs far more in wake-ups than it saves.
+for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'VECLIB_MAXIMUM_THREADS',
+           'NUMEXPR_NUM_THREADS'):
+    os.environ[_v] = '1'
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, 'efficient-tlbo_b200')

@@ -13,6 +13,8 @@ import os
 import sys
 import time
 
+for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):      # as tools/online_benchmark.py:3-8 does
+    os.environ[_v] = '1'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'efficient-tlbo_b200')):
     if p not in sys.path:
