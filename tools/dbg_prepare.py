@@ -5,7 +5,7 @@ import numpy as np, torch
 import bench
 from tlbo_b200.optimizer import ei_offline_optimizer as eo
 class A: pass
-args = A(); args.method = 'topo'; args.pool = 100000; args.sources = 29; args.n0 = 40
+args = A(); args.method = 'topo'; args.pool = 100000; args.sources = 29; args.n0 = 40; args.surrogate = 'gp'; args.mcmc_steps = [250, 250]
 wl = bench.build_workload(0, 4465, args.pool, args.sources, args.n0)
 fac, smbo = bench.make_product(args, wl)
 orig = eo.OfflineSearch.prepare

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 import numpy as np, torch, time
 import bench
 class A: pass
-args = A(); args.method = sys.argv[1] if len(sys.argv) > 1 else 'rgpe'; args.pool = 100000; args.sources = 29; args.n0 = 40
+args = A(); args.method = sys.argv[1] if len(sys.argv) > 1 else 'rgpe'; args.pool = 100000; args.sources = 29; args.n0 = 40; args.surrogate = 'gp'; args.mcmc_steps = [250, 250]
 wl = bench.build_workload(0, 4465, args.pool, args.sources, args.n0)
 fac, smbo = bench.make_product(args, wl)
 for _ in range(3): smbo.iterate()

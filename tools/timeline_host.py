@@ -8,7 +8,7 @@ from tlbo_b200 import ops
 import tlbo_b200.facade.rgpe as R
 import tlbo_b200.model.gp as G
 class A: pass
-args = A(); args.method = 'rgpe'; args.pool = 100000; args.sources = 29; args.n0 = 40
+args = A(); args.method = 'rgpe'; args.pool = 100000; args.sources = 29; args.n0 = 40; args.surrogate = 'gp'; args.mcmc_steps = [250, 250]
 wl = bench.build_workload(0, 4465, args.pool, args.sources, args.n0)
 fac, smbo = bench.make_product(args, wl)
 for _ in range(5): smbo.iterate()
@@ -30,7 +30,8 @@ wrap(ops, 'predict_ei_fused', 'fused call (launch+sync)')
 wrap(fac, '_ranking_losses', '_ranking_losses total')
 wrap(fac, 'train', 'train total')
 wrap(smbo, 'choose_next', 'choose_next total')
-R.fit_models_async = G.fit_models_async
+import tlbo_b200.facade.base_facade as BF
+BF.fit_models_async = G.fit_models_async
 torch.cuda.synchronize(); t0 = time.perf_counter()
 N = 20
 for _ in range(N): smbo.iterate()
