@@ -34,7 +34,7 @@ def _bounds_raw(spec):
 
 
 @pytest.mark.parametrize('n,types', [(6, RF_TYPES), (50, RF_TYPES), (75, RF_TYPES), (40, np.zeros(5, int)),
-                                     (150, np.zeros(5, int))])
+                                     (150, np.zeros(5, int)), (200, np.zeros(5, int)), (100, np.zeros(20, int))])
 def test_log_probability_matches_oracle(n, types):
     from tlbo_b200 import ops
     rng = np.random.RandomState(n)
@@ -104,7 +104,8 @@ def _run_both(types, n, W, nsteps, seed, B=2):
 
 
 @pytest.mark.parametrize('types,n,W,nsteps', [(RF_TYPES, 30, 34, 25), (np.zeros(5, int), 50, 22, 25),
-                                              (np.zeros(3, int), 140, 16, 6)])
+                                              (np.zeros(3, int), 140, 16, 6), (np.zeros(3, int), 200, 16, 4),
+                                              (np.zeros(20, int), 60, 66, 5)])
 def test_chain_makes_the_oracles_decisions(types, n, W, nsteps):
     nacc = _run_both(types, n, W, nsteps, seed=n + W)
     assert nacc.sum() > 0
