@@ -132,7 +132,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -378,6 +378,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    per_rank = []
     wl = build_workload(rank % 30, 4465 + rank, args.pool, args.sources, args.n0)
     fac, smbo = make_product(args, wl)
     d_cont = int((wl['types'] == 0).sum())
@@ -394,8 +403,11 @@ def run_ours(args):
         return cfg.index
 
     # ---- warm-up (the clock sampler runs from here to the end of the last timed region)
+    # one sampler for the whole job (rank 0's GPU): eight nvidia-smi pollers contend for the driver
+    # lock with the ranks' own launches and synchronisations
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         step(False)
     snap = (list(smbo.configurations), list(smbo.perfs))
@@ -431,7 +443,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
+        mine = e0.elapsed_time(e1)
+        ms = max_over_ranks(mine)
+        per_rank.append(all_ranks(mine))
         ops.STATS.timing = False
         return ms, wall, (flops, fitfl, fitev, cached_reads)
 
@@ -550,6 +564,7 @@ def run_ours(args):
         'step_breakdown': breakdown,
         'predict_candidates_per_s': args.pool * fused_calls / (fused_ms * 1e-3) if fused_ms > 0 else None,
         'host_wall_ms_per_step': 1e3 * wall_res / K, 'instrumented_ms_per_step': ms_ins / K,
+        'per_rank_ms_per_step': [round(v / K, 4) for v in per_rank[0]],
     }
     if roofline_mcmc is not None:
         line['roofline_mcmc'] = roofline_mcmc
