@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument('--cpu-sample-rows', type=int, default=10000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pool-sharded', action='store_true')
+    ap.add_argument('--distinct-trials', action='store_true',
+                    help='N > 1: give every rank its own target task / seed instead of a replica of trial 0')
     ap.add_argument('--ref-procs', type=int, default=0, help='reference arm: worker processes (0 = all cores)')
     ap.add_argument('--pair-loops', default='literal', choices=['literal', 'vectorised'],
                     help='reference arm: literal Python pair loops (as the reference) or numpy broadcasting')
@@ -326,7 +328,9 @@ def workload_config(args, where):
                   'log_prob_evals_per_fit': 34 * (sum(args.mcmc_steps) + 2)}),
         'l2': ('flushed before every step (256 MiB device memset inside the timed region)' if where == 'gpu'
                else 'n/a (host)'),
-        'multi_gpu': 'independent BO trials per rank (no data-path collective)',
+        'multi_gpu': ('independent BO trials per rank, no data-path collective; ' +
+                      ('distinct target task / seed per rank' if getattr(args, 'distinct_trials', False)
+                       else 'every rank runs a replica of trial 0 (identical per-GPU work)')),
         'resident': 'candidate pool, fitted surrogates and the source surrogates\' pool posteriors stay in HBM',
     }
 
@@ -387,7 +391,12 @@ def run_ours(args):
         return [float(v) for v in t.tolist()]
 
     per_rank = []
-    wl = build_workload(rank % 30, 4465 + rank, args.pool, args.sources, args.n0)
+    # N > 1: independent BO trials, one per rank, no data-path collective.  By default every rank runs a
+    # replica of trial 0 so that the per-GPU work is IDENTICAL to the N = 1 run (weak scaling then
+    # measures the system, not the trial-to-trial spread of L-BFGS-B / SLSQP iteration counts, which is
+    # +-15 % and would be charged to the slowest rank); --distinct-trials gives each rank its own task/seed.
+    trial = rank if args.distinct_trials else 0
+    wl = build_workload(trial % 30, 4465 + trial, args.pool, args.sources, args.n0)
     fac, smbo = make_product(args, wl)
     d_cont = int((wl['types'] == 0).sum())
     d_cat = int((wl['types'] != 0).sum())
