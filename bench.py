@@ -278,7 +278,9 @@ def run_reference_arm(args):
     import multiprocessing as mp
     P = args.ref_procs or (os.cpu_count() or 1)
     n_start = args.n0
-    jobs = [(args.method, t % 30, 4465 + t, args.pool, args.sources, n_start, args.steps, args.warmup,
+    # same trial selection as the CUDA arm: replicas of trial 0 unless --distinct-trials
+    tid = (lambda t: t) if args.distinct_trials else (lambda t: 0)
+    jobs = [(args.method, tid(t) % 30, 4465 + tid(t), args.pool, args.sources, n_start, args.steps, args.warmup,
              args.cpu_sample_rows, args.pair_loops == 'literal', args.surrogate,
              (args.cpu_mcmc_steps, args.cpu_mcmc_steps), tuple(args.mcmc_steps)) for t in range(P)]
     t0 = time.perf_counter()
@@ -291,11 +293,12 @@ def run_reference_arm(args):
     per_proc = [sum(r[0]) + sum(r[1]) for r in res]
     total = max(per_proc)
     value = P * args.steps / total
-    sample = ('%d parallel single-thread processes (one independent BO trial each, as the reference pins BLAS to 1 '
+    sample = ('%d parallel single-thread processes (one BO trial each: -- TRIALS --; as the reference pins BLAS to 1 '
               'thread); per step: fit+weights at full size (PAIRLOOPS pair loops), EI+sort on the first %d of '
               '%d pool rows scaled x%.0f; target n=%d..%d'
               % (P, args.cpu_sample_rows, args.pool, args.pool / args.cpu_sample_rows, n_start + args.warmup,
                  n_start + args.warmup + args.steps - 1)).replace('PAIRLOOPS', args.pair_loops)
+    sample = sample.replace('-- TRIALS --', 'distinct tasks / seeds' if args.distinct_trials else 'replicas of trial 0')
     sample += _mcmc_sample_note(args)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
