@@ -9,7 +9,9 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 no CPU fallback and never imports ``oracle``.
 
 What it is: a numpy/scipy restatement of the reference's algorithm for the hot
-path named in SURVEY.md section 8 (rows a1-a9), with a plain ``float64[N, d]`` +
+path named in SURVEY.md section 8 (rows a1-a10 and f-1: ``gp.py``, ``facade.py``, ``acquisition.py``,
+``gp_mcmc.py`` -- GaussianProcessMCMC + emcee's stretch move --, ``ei_optimization.py`` -- the online
+scenario's maximisers --), with a plain ``float64[N, d]`` +
 ``types[d]`` input contract instead of ConfigSpace objects.  Every function
 cites the reference ``file:line`` it follows (paths relative to
 ``/root/reference``).
@@ -34,5 +36,7 @@ kernel stack (``tests/test_oracle_sklearn.py``), finite differences for the
 Hamming part, and first-principles identities.  Against the *reference's own*
 outputs parity is therefore UNPINNED (stated again in DESIGN.md).  Golden
 vectors under ``tests/golden/`` are minted from this oracle with fixed seeds by
-``tests/golden/make_golden.py``.
+``tests/golden/make_golden.py`` / ``make_golden_mcmc.py``.  The same holds for the two further un-vendored
+dependencies restated for rows a10 / f-1 -- ``emcee`` (sampler) and ``ConfigSpace`` (neighbourhood /
+sampling streams): parity UNPINNED, see the headers of ``gp_mcmc.py`` and ``ei_optimization.py``.
 """
