@@ -239,6 +239,20 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
   }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TILE;
+    if (a.cmu && lane < WC) {
+      // resident posteriors of this tile: pull them towards L2 now, while the candidate tile is
+      // staged -- the combination loop below reads them one surrogate at a time (accumulation order
+      // is fixed), which would otherwise expose one HBM latency per surrogate
+      const long long prow = row0 + wid * WC + lane;
+      if (prow < a.N) {
+        for (int mi = 0; mi < a.pack.M; mi++) {
+          const int m = a.order ? a.order[mi] : mi;
+          if (m >= a.ncached || (a.skip && a.skip[m])) continue;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cmu + (size_t)m * a.N + prow));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cvar + (size_t)m * a.N + prow));
+        }
+      }
+    }
     __syncthreads();
     // stage the candidate tile (permuted [and padded] columns)
     {
