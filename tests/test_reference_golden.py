@@ -1,0 +1,166 @@
+"""The oracle pinned against the REFERENCE'S OWN outputs (tests/golden/reference_v1.npz).
+
+The fixture was produced by tests/golden/make_reference_golden.py, which imports the unmodified
+reference from /root/reference in the build container and runs its kernels, ``GaussianProcess``,
+``EI``, ``scipy_solve``, facades and ``SMBO_OFFLINE`` loop (absent third-party imports stood in for by
+tests/golden/refshims/).  These tests run everywhere (no /root/reference needed): the numpy/scipy
+oracle must reproduce the reference's numbers -- kernels / likelihood / posterior to rounding,
+integer ranking losses, weights, selected rows and the global np.random stream state exactly."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle.facade as ofacade
+from oracle import gp as ogp
+from oracle.acquisition import OracleEI, OracleSMBOOffline
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+R = np.load(os.path.join(HERE, 'golden', 'reference_v1.npz'))
+TAGS = ['rf', 'c5']
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_kernel_matches_reference(tag):
+    """gp_kernels.py Matern / Hamming / Constant / White / Product / Sum ``_call`` bodies."""
+    types, X, Xq, theta = R['kern_%s_types' % tag], R['kern_%s_X' % tag], R['kern_%s_Xq' % tag], R['kern_%s_thetas' % tag][0]
+    spec = ogp.KernelSpec(types)
+    K, dK = ogp.kernel(theta, spec, X, eval_gradient=True)
+    np.testing.assert_allclose(K, R['kern_%s_K' % tag], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(dK, R['kern_%s_dK' % tag], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(ogp.kernel(theta, spec, Xq, X), R['kern_%s_Ks' % tag], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(ogp.kernel_diag(theta, spec, Xq), R['kern_%s_diag' % tag], rtol=1e-14)
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_nll_matches_reference(tag):
+    """GaussianProcess._nll: sklearn LML + lognormal / horseshoe priors, value and gradient."""
+    types, X = R['kern_%s_types' % tag], R['kern_%s_X' % tag]
+    spec = ogp.KernelSpec(types)
+    g = ogp.OracleGP(types, 7)
+    g.train(X, R['kern_%s_y' % tag].copy(), do_optimize=False, theta=spec.default_theta())
+    np.testing.assert_allclose(g.y, R['nll_%s_ynorm' % tag], rtol=1e-14, atol=1e-15)
+    for i, theta in enumerate(R['kern_%s_thetas' % tag]):
+        f, grad = ogp.nll(theta, spec, X, g.y)
+        assert abs(f - R['nll_%s_f' % tag][i]) <= 1e-10 * abs(R['nll_%s_f' % tag][i])
+        np.testing.assert_allclose(grad, R['nll_%s_g' % tag][i], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_fit_matches_reference(tag):
+    """GaussianProcess._optimize: identical start points (prior / uniform draws of the shared and the
+    model's own RandomState), the same optimum restart by restart, the same theta*."""
+    types, X = R['kern_%s_types' % tag], R['kern_%s_X' % tag]
+    spec = ogp.KernelSpec(types)
+    p0 = R['fit_%s_p0' % tag]
+    np.testing.assert_array_equal(p0[0], spec.default_theta())
+    np.testing.assert_allclose(ogp.restart_points(spec, 7), p0[1:], rtol=1e-15, atol=0)
+    g = ogp.OracleGP(types, 7)
+    g.train(X, R['kern_%s_y' % tag].copy())
+    f_ref = R['fit_%s_f' % tag]
+    f_got = np.array([r[1] for r in g.restart_results])
+    np.testing.assert_allclose(f_got, f_ref, rtol=1e-6, atol=1e-6)
+    assert int(np.argmin(f_got)) == int(np.argmin(f_ref))
+    np.testing.assert_allclose(g.hypers, R['fit_%s_theta_star' % tag], rtol=1e-4, atol=1e-4)
+    # posterior of the fully trained model (each side with its own optimiser run)
+    mu, var = g.predict(R['kern_%s_Xq' % tag])
+    np.testing.assert_allclose(mu, R['pred_%s_mu' % tag], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(var, R['pred_%s_var' % tag], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_predict_and_ei_match_reference(tag):
+    """GaussianProcess.predict at a fixed theta (the regressor's K_inv_ variance form), the 1e-5 floor of
+    predict_marginalized_over_instances, EI._compute and EI.__call__."""
+    types, X, Xq = R['kern_%s_types' % tag], R['kern_%s_X' % tag], R['kern_%s_Xq' % tag]
+    g = ogp.OracleGP(types, 7)
+    g.train(X, R['kern_%s_y' % tag].copy(), do_optimize=False, theta=R['kern_%s_thetas' % tag][1])
+    np.testing.assert_allclose(g.L, R['pred_%s_fixed_L' % tag], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(g.alpha, R['pred_%s_fixed_alpha' % tag], rtol=1e-7, atol=1e-9)
+    scale = np.abs(R['pred_%s_fixed_Kinv' % tag]).max()
+    np.testing.assert_allclose(g.K_inv, R['pred_%s_fixed_Kinv' % tag], rtol=1e-7, atol=1e-10 * scale)
+    mu, var = g.predict(Xq)
+    np.testing.assert_allclose(mu, R['pred_%s_fixed_mu' % tag], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, R['pred_%s_fixed_var' % tag], rtol=1e-6, atol=1e-13)
+    # trained model: teacher-forced to the reference's theta*
+    g = ogp.OracleGP(types, 7)
+    g.train(X, R['kern_%s_y' % tag].copy(), do_optimize=False, theta=R['fit_%s_theta_star' % tag])
+    mu, var = g.predict(Xq)
+    np.testing.assert_allclose(mu, R['pred_%s_mu' % tag], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, R['pred_%s_var' % tag], rtol=1e-6, atol=1e-13)
+    mu2, var2 = g.predict_marginalized_over_instances(Xq)
+    np.testing.assert_allclose(var2, R['pred_%s_marg_var' % tag], rtol=1e-6, atol=1e-13)
+    ei = OracleEI(g)
+    ei.update(model=g, eta=float(R['ei_%s_eta' % tag]), num_data=X.shape[0])
+    np.testing.assert_allclose(ei._compute(Xq), R['ei_%s_acq' % tag], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(ei(Xq), R['ei_%s_acq_call' % tag], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_slsqp_weights_match_reference(tag):
+    """utils/scipy_solver.py scipy_solve with loss_type=3 (pairwise logistic)."""
+    w, status = ofacade.scipy_solve(R['slsqp_%s_A' % tag], R['slsqp_%s_y' % tag])
+    assert bool(status) == bool(R['slsqp_%s_status' % tag])
+    np.testing.assert_allclose(w, R['slsqp_%s_w' % tag], rtol=1e-7, atol=1e-9)
+
+
+class _ForcedGP(ogp.OracleGP):
+    """Teacher-forced to the reference's fitted hyper-parameters, in the reference's fit order."""
+    queue = []
+
+    def train(self, X, Y, do_optimize=True, theta=None):
+        return super().train(X, Y, do_optimize=False, theta=_ForcedGP.queue.pop(0))
+
+
+def _state_vec():
+    st = np.random.get_state()
+    return np.concatenate([st[1].astype(np.int64), [st[2], st[3]], [np.float64(st[4]).view(np.int64)]])
+
+
+LOOPS = {'rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, literal_loops=True),
+         'trans_rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, smooth=0.7),
+         'topo': lambda t, s, seed: ofacade.OracleOBTLV(t, s, seed),
+         'tst': lambda t, s, seed: ofacade.OracleTST(t, s, seed),
+         'pogpe': lambda t, s, seed: ofacade.OraclePOGPE(t, s, seed)}
+
+
+@pytest.mark.parametrize('method', sorted(LOOPS))
+def test_offline_loop_matches_reference(method, monkeypatch):
+    """SMBO_OFFLINE + facade + EI + OfflineSearch, iteration by iteration, against the reference's own
+    run: selected rows, weights, dilution flags, integer ranking-loss tables and the global np.random
+    stream state are EXACT; the oracle's GPs take the reference's fitted theta (the optimiser itself is
+    covered by test_fit_matches_reference)."""
+    monkeypatch.setattr(ofacade, 'OracleGP', _ForcedGP)
+    K, seed, types = int(R['loop_K']), int(R['loop_seed']), R['loop_types']
+    p = 'loop_%s_' % method
+    tables = [(R['loop_task%d_X' % t], R['loop_task%d_y' % t]) for t in range(K + 1)]
+    thetas = [th for th in R[p + 'thetas']]
+    nsrc = int(R[p + 'n_source_fits'])
+    _ForcedGP.queue = thetas[:nsrc]
+    fac = LOOPS[method](types, [(X.copy(), y.copy()) for X, y in tables[1:]], seed)
+    assert not _ForcedGP.queue
+    np.testing.assert_allclose(fac.eta_list, R[p + 'eta_list'], rtol=1e-13)
+    smbo = OracleSMBOOffline(tables[0][0], tables[0][1], fac, seed, initial_runs=3)
+    used, loss_rows = nsrc, 0
+    ref_losses = R[p + 'losses']
+    for it, row in enumerate(R[p + 'rows']):
+        nfit = int(R[p + 'fits_per_iter'][it])
+        _ForcedGP.queue = thetas[used:used + nfit]
+        used += nfit
+        got = smbo.iterate()
+        assert not _ForcedGP.queue, 'iteration %d: the oracle fitted fewer GPs than the reference' % it
+        assert got == int(row), 'iteration %d: oracle picked row %d, reference %d' % (it, got, row)
+        np.testing.assert_array_equal(_state_vec(), R[p + 'np_random_state'][it], err_msg='np.random stream, it %d' % it)
+        if fac.w is not None:
+            np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), R[p + 'w'][it], rtol=1e-6,
+                                       atol=1e-8, err_msg='weights, iteration %d' % it)
+        if method in ('rgpe', 'trans_rgpe') and nfit:
+            np.testing.assert_array_equal(np.asarray(fac.ignored_flag, dtype=bool), R[p + 'ignored'][it])
+            if nfit == 6:
+                np.testing.assert_array_equal(fac.last_losses, ref_losses[loss_rows:loss_rows + 30])
+            loss_rows += 30
+    np.testing.assert_allclose(smbo.perfs, R[p + 'perfs'], rtol=0, atol=0)
+    np.testing.assert_allclose(fac.target_weight, R[p + 'target_weight'], rtol=1e-6, atol=1e-8)
+    if p + 'hist_ws' in R.files and len(R[p + 'hist_ws']):
+        np.testing.assert_allclose(np.array([np.asarray(w, dtype=np.float64) for w in fac.hist_ws]), R[p + 'hist_ws'],
+                                   rtol=1e-6, atol=1e-8)
