@@ -214,10 +214,48 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
   double* my_spill = s_spill + (size_t)wid * a.njmax * NW * 32;
   double* my_comb = s_comb + (size_t)wid * WC * 2;
   double* s_raw = s_comb + (size_t)PRED_WARPS * WC * 2;     // TMA landing buffer: TILE * d raw candidate rows
+  // active-surrogate list (accumulation order, skipped / empty slots dropped): weight, slot, n, flags
+  double* s_lw = s_raw + (size_t)TILE * d;
+  int* s_lm = reinterpret_cast<int*>(s_lw + a.pack.M);
+  int* s_ln = s_lm + a.pack.M;
+  int* s_lf = s_ln + a.pack.M;            // bit 0: first entry of the order (mode 1 initialiser); bits 8..: cached run length
   __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ int s_L, s_neval, s_evali;
   if (tid == 0) mbar_init(&s_mbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (wid == 0) {
+    // order-preserving compaction by warp 0: the per-tile loops below then touch no global metadata
+    int count = 0, neval = 0, evali = -1;
+    for (int base = 0; base < a.pack.M; base += 32) {
+      const int mi = base + lane;
+      int m = 0, n = 0; bool keep = false;
+      if (mi < a.pack.M) {
+        m = a.order ? a.order[mi] : mi;
+        n = a.pack.d_n[m];
+        keep = !(a.skip && a.skip[m]) && n > 0;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      const int pos = count + __popc(mask & ((1u << lane) - 1u));
+      const bool cached = keep && a.cmu && m < a.ncached;
+      if (keep) { s_lw[pos] = a.w[m]; s_lm[pos] = m; s_ln[pos] = n; s_lf[pos] = (mi == 0) ? 1 : 0; }
+      const unsigned emask = __ballot_sync(0xffffffffu, keep && !cached);
+      if (emask) { neval += __popc(emask); evali = count + __popc(mask & ((1u << (31 - __clz(emask))) - 1u)); }
+      count += __popc(mask);
+    }
+    __syncwarp();
+    // run lengths of consecutive resident (cached) entries, from the back
+    if (lane == 0) {
+      int run = 0;
+      for (int i = count - 1; i >= 0; i--) {
+        const bool cached = a.cmu && s_lm[i] < a.ncached;
+        run = cached ? run + 1 : 0;
+        s_lf[i] |= run << 8;
+      }
+      s_L = count; s_neval = neval; s_evali = evali;
+    }
+  }
   __syncthreads();
+  const int L = s_L;
   unsigned tma_phase = 0;
 
   Best best; best.ei = -INFINITY; best.key = -INFINITY; best.idx = -1;
@@ -237,103 +275,155 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
     const unsigned b0 = tma_bytes(blockIdx.x);
     if (b0) tma_load_1d(s_raw, a.cand + (size_t)blockIdx.x * TILE * d, b0, &s_mbar);
   }
+  // ---- staging helpers (all threads; the callers place the barriers)
+  auto stage_model = [&](int m, int n) {
+    const double* gX = a.pack.d_Xs + (size_t)m * ncap * d;
+    const double* gA = a.pack.d_alpha + (size_t)m * ncap;
+    const double* gH = a.pack.d_hyp + (size_t)m * TLBO_HYP_STRIDE;
+    if (FAST) {
+      for (int idx = tid; idx < nrows * DP; idx += PRED_THREADS) {
+        const int j = idx / DP, pp = idx - j * DP;
+        const int p = (pp < DCP) ? pp : dc + (pp - DCP);
+        const bool ok = (j < n) && ((pp < DCP) ? (pp < dc) : (p < d));
+        s_Xs[idx] = ok ? gX[(size_t)j * d + p] : 0.0;
+      }
+      for (int idx = tid; idx < nrows; idx += PRED_THREADS) s_alpha[idx] = (idx < n) ? gA[idx] : 0.0;
+      if (tid < TLBO_HYP_STRIDE) {
+        s_hyp[tid] = gH[tid];
+        const int p = (tid < DCP) ? tid : dc + (tid - DCP);
+        const bool ok = (tid < DCP) ? (tid < dc) : (tid < DCP + DKP && p < d);
+        s_hypp[tid] = ok ? gH[8 + p] : 0.0;
+      }
+    } else {
+      for (int idx = tid; idx < n * d; idx += PRED_THREADS) s_Xs[idx] = gX[idx];
+      for (int idx = tid; idx < nrows; idx += PRED_THREADS) s_alpha[idx] = (idx < n) ? gA[idx] : 0.0;
+      if (tid < TLBO_HYP_STRIDE) s_hyp[tid] = gH[tid];
+    }
+  };
+  auto stage_linv = [&](int m, int r0, int rows) {
+    // only columns < r0 + rows are ever read (lower triangular): copy that many, not ldl
+    const double* src = a.pack.d_Linv + (size_t)m * ncap * ldl + (size_t)r0 * ldl;
+    const int ncol = (r0 + rows + 3) & ~3;
+    const int c4 = ncol >> 2;                       // 4-column groups per row
+    for (int idx = tid; idx < rows * c4; idx += PRED_THREADS) {
+      const int rr = idx / c4, cc = (idx - rr * c4) << 2;
+      const double2 v0 = *reinterpret_cast<const double2*>(src + (size_t)rr * ldl + cc);
+      const double2 v1 = *reinterpret_cast<const double2*>(src + (size_t)rr * ldl + cc + 2);
+      *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc) = v0;
+      *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc + 2) = v1;
+    }
+  };
+  // Exactly one surrogate is evaluated per tile (the usual per-iteration launch: the target, all
+  // sources resident) and its L^-1 fits one chunk: stage it ONCE per CTA, not once per tile.
+  bool persist = false;
+  if (s_neval == 1) {
+    const int n1 = s_ln[s_evali];
+    if (((n1 + 7) >> 3) * 8 <= a.rc_rows) {
+      persist = true;
+      stage_model(s_lm[s_evali], n1);
+      stage_linv(s_lm[s_evali], 0, ((n1 + 7) >> 3) * 8);
+    }
+  }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * TILE;
     if (a.cmu && lane < WC) {
       // resident posteriors of this tile: pull them towards L2 now, while the candidate tile is
-      // staged -- the combination loop below reads them one surrogate at a time (accumulation order
-      // is fixed), which would otherwise expose one HBM latency per surrogate
+      // staged -- the combination loop below reads them in accumulation order
       const long long prow = row0 + wid * WC + lane;
       if (prow < a.N) {
-        for (int mi = 0; mi < a.pack.M; mi++) {
-          const int m = a.order ? a.order[mi] : mi;
-          if (m >= a.ncached || (a.skip && a.skip[m])) continue;
+        for (int i = 0; i < L; i++) {
+          const int m = s_lm[i];
+          if (m >= a.ncached) continue;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cmu + (size_t)m * a.N + prow));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cvar + (size_t)m * a.N + prow));
         }
       }
     }
-    __syncthreads();
-    // stage the candidate tile (permuted [and padded] columns)
+    __syncthreads();                                        // previous tile's readers of s_cand are done
+    // stage the candidate tile (permuted [and padded] columns) in ONE pass
     {
       const long long lim = (a.N - row0 < TILE ? a.N - row0 : TILE) * d;
       const bool via_tma = tma_bytes(tile) != 0;            // uniform
       const double* src = via_tma ? s_raw : a.cand + (size_t)row0 * d;
       if (via_tma) { mbar_wait(&s_mbar, tma_phase); tma_phase ^= 1; }
       if (FAST) {
-        for (int idx = tid; idx < TILE * DP; idx += PRED_THREADS) s_cand[idx] = 0.0;
-        __syncthreads();
+        for (int idx = tid; idx < TILE * DP; idx += PRED_THREADS) {
+          const int r = idx / DP, pp = idx - r * DP;
+          const int p = (pp < DCP) ? ((pp < dc) ? pp : -1) : ((dc + pp - DCP < d) ? dc + pp - DCP : -1);
+          double v = 0.0;
+          if (p >= 0) {
+            const long long sidx = (long long)r * d + a.sp.perm[p];
+            if (sidx < lim) v = src[sidx];
+          }
+          s_cand[idx] = v;
+        }
+      } else {
+        for (int idx = tid; idx < TILE * d; idx += PRED_THREADS) {
+          const int r = idx / d, p = idx - r * d;
+          const long long sidx = (long long)r * d + a.sp.perm[p];
+          s_cand[idx] = (sidx < lim) ? src[sidx] : 0.0;
+        }
       }
-      for (int idx = tid; idx < TILE * d; idx += PRED_THREADS) {
-        const int r = idx / d, p = idx - r * d;
-        const long long sidx = (long long)r * d + a.sp.perm[p];
-        const int pp = FAST ? ((p < dc) ? p : DCP + (p - dc)) : p;
-        s_cand[r * DP + pp] = (sidx < lim) ? src[sidx] : 0.0;
-      }
-      __syncthreads();                                      // s_raw is free again
+      __syncthreads();                                      // s_cand complete, s_raw free again
       const long long nxt = tile + gridDim.x;
       if (nxt < ntiles && tid == 0) {
         const unsigned bn = tma_bytes(nxt);
         if (bn) tma_load_1d(s_raw, a.cand + (size_t)nxt * TILE * d, bn, &s_mbar);
       }
     }
-    // per-lane ensemble accumulators: lane owns candidate (lane) of this warp when WC == 32,
-    // in general candidate index cl = lane (valid if lane < WC)
+    // per-lane ensemble accumulators: lane cl < WC owns candidate cl of this warp
     double acc_mu = 0.0, acc_var = 0.0, wsum = 0.0;
-    for (int mi = 0; mi < a.pack.M; mi++) {
-      const int m = a.order ? a.order[mi] : mi;
-      const double wm = a.w[m];
-      if (a.skip && a.skip[m]) continue;
-      const int n = a.pack.d_n[m];
-      if (n <= 0) continue;
-      if (a.cmu && m < a.ncached) {
-        // this surrogate's posterior over the pool is resident in HBM (it does not depend on
-        // the target observations): two coalesced 8-byte reads per candidate instead of n
-        // kernel evaluations and an n x n contraction
-        if (lane < WC) {
-          const long long row = row0 + wid * WC + lane;
-          const double mu_m = (row < a.N) ? a.cmu[(size_t)m * a.N + row] : 0.0;
-          const double var_m = (row < a.N) ? a.cvar[(size_t)m * a.N + row] : 0.0;
-          if (a.mode == 0) {
-            acc_mu += wm * mu_m;
-            acc_var += wm * wm * var_m;
-          } else if (a.mode == 2) {
-            const double iv = 1.0 / var_m;
-            acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
-            acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
-          } else {
-            if (mi == 0) { acc_mu = mu_m; acc_var = var_m; }
-            else { acc_mu += wm * mu_m; wsum += wm; }
+    const long long myrow = row0 + wid * WC + lane;
+    const bool myok = lane < WC && myrow < a.N;
+    auto combine = [&](bool first, double wm, double mu_m, double var_m) {
+      if (a.mode == 0) {
+        acc_mu += wm * mu_m;
+        acc_var += wm * wm * var_m;
+      } else if (a.mode == 2) {
+        const double iv = 1.0 / var_m;
+        acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
+        acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
+      } else {
+        if (first) { acc_mu = mu_m; acc_var = var_m; }
+        else { acc_mu += wm * mu_m; wsum += wm; }
+      }
+    };
+    int li = 0;
+    while (li < L) {
+      const int run = s_lf[li] >> 8;
+      if (run > 0) {
+        // resident posteriors (they do not depend on the target observations): two coalesced 8-byte
+        // reads per candidate and surrogate.  Up to CB surrogates' loads are issued back to back,
+        // then accumulated in the fixed order -- one memory latency per batch, not per surrogate.
+        constexpr int CB = 8;
+        const int r = run < CB ? run : CB;
+        double cm[CB], cv[CB];
+#pragma unroll
+        for (int b = 0; b < CB; b++) {
+          cm[b] = 0.0; cv[b] = 0.0;
+          if (b < r && myok) {
+            const size_t off = (size_t)s_lm[li + b] * a.N + myrow;
+            cm[b] = __ldg(a.cmu + off);
+            cv[b] = __ldg(a.cvar + off);
           }
         }
+        if (lane < WC) {
+#pragma unroll
+          for (int b = 0; b < CB; b++)
+            if (b < r) combine((s_lf[li + b] & 1) != 0, s_lw[li + b], cm[b], cv[b]);
+        }
+        li += r;
         continue;
       }
-      __syncthreads();
-      {
-        const double* gX = a.pack.d_Xs + (size_t)m * ncap * d;
-        const double* gA = a.pack.d_alpha + (size_t)m * ncap;
-        const double* gH = a.pack.d_hyp + (size_t)m * TLBO_HYP_STRIDE;
-        if (FAST) {
-          for (int idx = tid; idx < nrows * DP; idx += PRED_THREADS) {
-            const int j = idx / DP, pp = idx - j * DP;
-            const int p = (pp < DCP) ? pp : dc + (pp - DCP);
-            const bool ok = (j < n) && ((pp < DCP) ? (pp < dc) : (p < d));
-            s_Xs[idx] = ok ? gX[(size_t)j * d + p] : 0.0;
-          }
-          for (int idx = tid; idx < nrows; idx += PRED_THREADS) s_alpha[idx] = (idx < n) ? gA[idx] : 0.0;
-          if (tid < TLBO_HYP_STRIDE) {
-            s_hyp[tid] = gH[tid];
-            const int p = (tid < DCP) ? tid : dc + (tid - DCP);
-            const bool ok = (tid < DCP) ? (tid < dc) : (tid < DCP + DKP && p < d);
-            s_hypp[tid] = ok ? gH[8 + p] : 0.0;
-          }
-        } else {
-          for (int idx = tid; idx < n * d; idx += PRED_THREADS) s_Xs[idx] = gX[idx];
-          for (int idx = tid; idx < nrows; idx += PRED_THREADS) s_alpha[idx] = (idx < n) ? gA[idx] : 0.0;
-          if (tid < TLBO_HYP_STRIDE) s_hyp[tid] = gH[tid];
-        }
+      const int m = s_lm[li], n = s_ln[li];
+      const double wm = s_lw[li];
+      const bool first = (s_lf[li] & 1) != 0;
+      li++;
+      if (!persist) {
+        __syncthreads();
+        stage_model(m, n);
+        __syncthreads();
       }
-      __syncthreads();
       const double c = s_hyp[0], ymean = s_hyp[2], ystd = s_hyp[3], diag = s_hyp[4];
       const int nj = (n + 3) >> 2;            // j-steps of 4 training rows
       // ---- K* phase
@@ -417,29 +507,18 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
           }
         }
       }
-      // ---- V phase: q = |Linv k|^2 via DMMA, Linv streamed in row chunks
+      // ---- V phase: q = |Linv k|^2 via DMMA, Linv streamed in row chunks (resident when `persist`)
       double qpart[NW][2];
 #pragma unroll
       for (int w = 0; w < NW; w++) { qpart[w][0] = 0.0; qpart[w][1] = 0.0; }
       const int nib = (n + 7) >> 3;           // 8-row blocks
-      const double* gL = a.pack.d_Linv + (size_t)m * ncap * ldl;
       for (int r0 = 0; r0 < nib * 8; r0 += a.rc_rows) {
         const int rows = (nib * 8 - r0 < a.rc_rows) ? nib * 8 - r0 : a.rc_rows;
-        __syncthreads();
-        {
-          // only columns < r0 + rows are ever read (lower triangular): copy that many, not ldl
-          const double* src = gL + (size_t)r0 * ldl;
-          const int ncol = (r0 + rows + 3) & ~3;
-          const int c4 = ncol >> 2;                       // 4-column groups per row
-          for (int idx = tid; idx < rows * c4; idx += PRED_THREADS) {
-            const int rr = idx / c4, cc = (idx - rr * c4) << 2;
-            const double2 v0 = *reinterpret_cast<const double2*>(src + (size_t)rr * ldl + cc);
-            const double2 v1 = *reinterpret_cast<const double2*>(src + (size_t)rr * ldl + cc + 2);
-            *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc) = v0;
-            *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc + 2) = v1;
-          }
+        if (!persist) {
+          __syncthreads();
+          stage_linv(m, r0, rows);
+          __syncthreads();
         }
-        __syncthreads();
         for (int ib = 0; ib * 8 < rows; ib += 2) {
           const bool two = (ib + 1) * 8 < rows;
           const int ig = (r0 >> 3) + ib;      // global 8-row block index of the first block
@@ -493,21 +572,8 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
         if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;
         const double mu_m = mean * ystd + ymean;
         const double var_m = var * (ystd * ystd);
-        if (a.pm_mu) {
-          const long long prow = row0 + wid * WC + lane;
-          if (prow < a.N) { a.pm_mu[(size_t)m * a.N + prow] = mu_m; a.pm_var[(size_t)m * a.N + prow] = var_m; }
-        }
-        if (a.mode == 0) {
-          acc_mu += wm * mu_m;
-          acc_var += wm * wm * var_m;
-        } else if (a.mode == 2) {
-          const double iv = 1.0 / var_m;
-          acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
-          acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
-        } else {
-          if (mi == 0) { acc_mu = mu_m; acc_var = var_m; }
-          else { acc_mu += wm * mu_m; wsum += wm; }
-        }
+        if (a.pm_mu && myok) { a.pm_mu[(size_t)m * a.N + myrow] = mu_m; a.pm_var[(size_t)m * a.N + myrow] = var_m; }
+        combine(first, wm, mu_m, var_m);
       }
       __syncwarp();
     }
@@ -581,19 +647,35 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
   }
 }
 
-__global__ void argmax_final_kernel(const double* partial, int nparts, double* out) {
-  // single warp
+#define ARGMAX_FINAL_THREADS 320
+__global__ void __launch_bounds__(ARGMAX_FINAL_THREADS) argmax_final_kernel(const double* partial, int nparts, double* out) {
+  // one partial per thread (<= 296 CTAs), warp arg-max, then warp 0 merges the warp results
+  __shared__ Best s_b[ARGMAX_FINAL_THREADS / 32];
+  __shared__ double s_n[ARGMAX_FINAL_THREADS / 32];
   Best b; b.ei = -INFINITY; b.key = -INFINITY; b.idx = -1;
   double nn = 0.0;
-  for (int i = threadIdx.x; i < nparts; i += 32) {
-    Best c; c.ei = partial[i * 4]; c.key = partial[i * 4 + 1]; c.idx = (long long)partial[i * 4 + 2];
-    nn += partial[i * 4 + 3];
+  for (int i = threadIdx.x; i < nparts; i += ARGMAX_FINAL_THREADS) {
+    const double2 p0 = *reinterpret_cast<const double2*>(partial + (size_t)i * 4);
+    const double2 p1 = *reinterpret_cast<const double2*>(partial + (size_t)i * 4 + 2);
+    Best c; c.ei = p0.x; c.key = p0.y; c.idx = (long long)p1.x;
+    nn += p1.y;
     if (c.idx >= 0 && (b.idx < 0 || better(c, b))) b = c;
   }
   if (b.idx < 0) { b.ei = -INFINITY; b.key = -INFINITY; }
   b = warp_best(b);
   nn = warp_sum(nn);
-  if (threadIdx.x == 0) { out[0] = b.ei; out[1] = b.key; out[2] = (double)b.idx; out[3] = nn; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_b[wid] = b; s_n[wid] = nn; }
+  __syncthreads();
+  if (wid == 0) {
+    Best c; c.ei = -INFINITY; c.key = -INFINITY; c.idx = -1;
+    double n2 = 0.0;
+    if (lane < ARGMAX_FINAL_THREADS / 32) { c = s_b[lane]; n2 = s_n[lane]; }
+    if (c.idx < 0) { c.ei = -INFINITY; c.key = -INFINITY; }
+    c = warp_best(c);
+    n2 = warp_sum(n2);
+    if (lane == 0) { out[0] = c.ei; out[1] = c.key; out[2] = (double)c.idx; out[3] = n2; }
+  }
 }
 
 struct FusedPlan { int nw; int rc_rows; size_t smem; int grid; int njmax; int dcp, dkp; int minb; };
@@ -606,15 +688,16 @@ static void fused_pick_layout(int dc, int dk, int* dcp, int* dkp) {
   else { *dcp = 0; *dkp = 0; }
 }
 
-static size_t fused_fixed_bytes(int nw, int njmax, int dp, int d) {
+static size_t fused_fixed_bytes(int nw, int njmax, int dp, int d, int M) {
   const size_t tile = (size_t)PRED_WARPS * nw * 8;
   const size_t nrows = 4 * (size_t)njmax + 4;
   return sizeof(double) * (tile * dp + nrows * dp + nrows + 2 * TLBO_HYP_STRIDE +
                            (size_t)PRED_WARPS * njmax * nw * 32 + (size_t)PRED_WARPS * nw * 8 * 2 +
-                           tile * d /* TMA landing buffer */ + 2);
+                           tile * d /* TMA landing buffer */ + 2) +
+         (size_t)M * (sizeof(double) + 3 * sizeof(int)) /* active-surrogate list */ + 16;
 }
 
-static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, FusedPlan* pl) {
+static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, int M, FusedPlan* pl) {
   const int ldl = TLBO_LDL(ncap);
   if (nmax <= 0 || nmax > ncap) nmax = ncap;
   const int njmax = (nmax + 3) / 4;
@@ -625,7 +708,7 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, F
   const size_t limit1 = 227 * 1024 - 2048, limit2 = (227 * 1024) / 2 - 2048;
   // preferred: two CTAs per SM (16 warps hide the sqrt / exp latency chains) with NW = 2
   if (pl->dcp > 0) {
-    const size_t fixed = fused_fixed_bytes(2, njmax, dp, d);
+    const size_t fixed = fused_fixed_bytes(2, njmax, dp, d, M);
     if (fixed + sizeof(double) * 16 * ldl <= limit2) {
       size_t rows = ((limit2 - fixed) / (sizeof(double) * ldl) / 16) * 16;
       if (rows > (size_t)nb16) rows = nb16;
@@ -639,7 +722,7 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, F
   for (int nw = 4; nw >= 1; nw >>= 1) {
     if (pl->dcp > 0 && nw == 1) break;
     const size_t tile = (size_t)PRED_WARPS * nw * 8;
-    const size_t fixed = fused_fixed_bytes(nw, njmax, dp, d);
+    const size_t fixed = fused_fixed_bytes(nw, njmax, dp, d, M);
     if (fixed + sizeof(double) * 16 * ldl > limit1) continue;
     size_t rows = ((limit1 - fixed) / (sizeof(double) * ldl) / 16) * 16;
     if (rows > (size_t)nb16) rows = nb16;
@@ -654,7 +737,7 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, F
   }
   if (pl->dcp > 0) {           // specialised layout does not fit: fall back to the generic one
     pl->dcp = pl->dkp = 0;
-    return fused_plan(ncap, nmax, d, -1, -1, N, pl);
+    return fused_plan(ncap, nmax, d, -1, -1, N, M, pl);
   }
   return false;
 }
@@ -686,7 +769,8 @@ static int fused_entry(const tlbo_pack* pack, const int32_t* h_types, const doub
   int rc = tlbo_make_space(pack->d, h_types, &a.sp);
   if (rc) return rc;
   FusedPlan pl;
-  if (!fused_plan(pack->ncap, pack->nmax, pack->d, a.sp.d_cont, a.sp.d_cat, N, &pl)) {
+  if (pack->M <= 0 || pack->M > 4096) { tlbo_set_error("pack M out of range for the fused kernel"); return TLBO_E_TOOLARGE; }
+  if (!fused_plan(pack->ncap, pack->nmax, pack->d, a.sp.d_cont, a.sp.d_cat, N, pack->M, &pl)) {
     tlbo_set_error("surrogates too large for the fused kernel");
     return TLBO_E_TOOLARGE;
   }
@@ -706,7 +790,7 @@ static int fused_entry(const tlbo_pack* pack, const int32_t* h_types, const doub
   else if (pl.nw == 2) rc = fused_launch<2, 0, 0, 1>(a, pl, s);
   else rc = fused_launch<1, 0, 0, 1>(a, pl, s);
   if (rc) return rc;
-  argmax_final_kernel<<<1, 32, 0, s>>>(a.partial, pl.grid, d_best);
+  argmax_final_kernel<<<1, ARGMAX_FINAL_THREADS, 0, s>>>(a.partial, pl.grid, d_best);
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

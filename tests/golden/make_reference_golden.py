@@ -18,6 +18,10 @@ restored.  Everything recorded below is computed by reference code:
   pred_*   GaussianProcess.predict / predict_marginalized_over_instances at theta*
   ei_*     acquisition.EI over those predictions
   slsqp_*  utils/scipy_solver.scipy_solve inputs / weights
+  mcmc_*   model/gp_mcmc.GaussianProcessMCMC: _ll (Tophat bound priors, -inf outside the box), the initial
+           ensemble drawn from the priors, the walkers' positions after short chains (two consecutive
+           train calls: with and without burn-in), marginalised prediction.  The stretch-move sampler
+           itself comes from the emcee stand-in (= the oracle's restatement): sampler NOT pinned
   loop_*   framework/smbo_offline.SMBO_OFFLINE driving facade/rgpe.RGPE, facade/topo.TransBO_RGPE,
            facade/topo_variant1.OBTLV, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
            dilution flags, the bootstrap ranking-loss tables (captured from the np.argmin calls of
@@ -166,6 +170,37 @@ def gp_level(out):
         out['ei_%s_acq_call' % tag] = ei([Configuration(cs, vector=x) for x in Xq])
 
 
+def mcmc_level(out):
+    rng = np.random.RandomState(20261021)
+    for tag, cs, types, n in (('rf', rf_space(), RF_TYPES, 20), ('c4', cont_space(4), np.zeros(4, int), 16)):
+        X, y = data(rng, n, types)
+        Xq, _ = data(rng, 48, types)
+        Xq[:4] = X[:4]
+        model = build_model('gp_mcmc', cs, np.random.RandomState(11))
+        model.burnin_steps, model.chain_length = 12, 12
+        H = len(model.kernel.theta)
+        out.update({'mcmc_%s_types' % tag: types, 'mcmc_%s_X' % tag: X, 'mcmc_%s_y' % tag: y, 'mcmc_%s_Xq' % tag: Xq,
+                    'mcmc_%s_walkers' % tag: model.n_mcmc_walkers})
+        quiet(model.train, X, y.copy())
+        out['mcmc_%s_hypers1' % tag] = np.array(model.hypers)
+        mu, var = model.predict(Xq)
+        out['mcmc_%s_mu1' % tag], out['mcmc_%s_var1' % tag] = mu, var
+        # _ll at in-box, out-of-box and clipped points (the model is trained: self.gp / priors exist)
+        thetas = np.array([np.concatenate([[rng.uniform(-0.5, 1.0)], rng.uniform(-1.5, 0.05, H - 2),
+                                           [rng.uniform(-9, -4)]]) for _ in range(4)])
+        thetas[2, 1] = 0.5          # length scale above its bound -> -inf
+        thetas[3, -1] = -60.0       # clipped to -50, still below the noise bound -> -inf
+        out['mcmc_%s_ll_thetas' % tag] = thetas
+        out['mcmc_%s_ll' % tag] = np.array([model._ll(th.copy()) for th in thetas], dtype=np.float64)
+        # second train on more data: no burn-in, the ensemble continues from p0
+        X2, y2 = data(rng, n + 3, types)
+        quiet(model.train, X2, y2.copy())
+        out['mcmc_%s_X2' % tag], out['mcmc_%s_y2' % tag] = X2, y2
+        out['mcmc_%s_hypers2' % tag] = np.array(model.hypers)
+        mu, var = model.predict_marginalized_over_instances(Xq)
+        out['mcmc_%s_mu2' % tag], out['mcmc_%s_var2' % tag] = mu, var
+
+
 def slsqp_level(out):
     rng = np.random.RandomState(11)
     for tag, n, m in (('a', 12, 4), ('b', 30, 6)):
@@ -248,6 +283,7 @@ def loop_level(out):
 def main():
     out = {}
     gp_level(out)
+    mcmc_level(out)
     slsqp_level(out)
     loop_level(out)
     path = os.path.join(HERE, 'reference_v1.npz')
