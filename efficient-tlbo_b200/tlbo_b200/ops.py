@@ -513,13 +513,16 @@ class PairLogistic(object):
         self.out_np = self.out.numpy()
         self._cache_w = None
         self._cache = None
+        # the launching stream is fixed for the lifetime of one scipy_solve (looking it up costs
+        # ~20 us per SLSQP callback)
+        self._stream = torch.cuda.current_stream()
+        self._sptr = ctypes.c_void_p(self._stream.cuda_stream)
 
     def __call__(self, w):
         w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
         if self._cache_w is not None and np.array_equal(w, self._cache_w):
             return self._cache
-        stream = torch.cuda.current_stream()
-        sptr = ctypes.c_void_p(stream.cuda_stream)
+        stream, sptr = self._stream, self._sptr
         with _call('pairwise_logistic', 1):
             if self.host_w:
                 check(lib.tlbo_pairwise_logistic_loss_grad_hw(ptr(self.dA), ptr(self.dy), ptr(w), self.n, self.m,

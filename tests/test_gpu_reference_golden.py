@@ -190,3 +190,25 @@ def test_cuda_loop_with_device_fit_tracks_reference(method):
     assert same >= 5                      # 3 initial rows + at least the first two model-based picks
     span = tables[0][1].max() - tables[0][1].min()
     assert min(smbo.perfs) <= R[p + 'perfs'].min() + 0.05 * span
+
+
+@pytest.mark.parametrize('tag', ['rf', 'c4'])
+def test_cuda_gp_mcmc_matches_reference(tag):
+    """The device chain + walker GPs + marginalisation against the reference's own GaussianProcessMCMC run
+    (short chains; sampler = the restated stretch move on both sides, see tests/golden/refshims/emcee.py)."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.model.model_builder import build_model
+    types, X, y, Xq = (R['mcmc_%s_%s' % (tag, k)] for k in ('types', 'X', 'y', 'Xq'))
+    m = build_model('gp_mcmc', TableSpace(types), np.random.RandomState(11))
+    assert m.n_mcmc_walkers == int(R['mcmc_%s_walkers' % tag])
+    m.burnin_steps, m.chain_length = 12, 12
+    m.train(X, y.copy())
+    np.testing.assert_allclose(np.array(m.hypers), R['mcmc_%s_hypers1' % tag], rtol=1e-8, atol=1e-10)
+    mu, var = m.predict(Xq)
+    np.testing.assert_allclose(mu, R['mcmc_%s_mu1' % tag], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, R['mcmc_%s_var1' % tag], rtol=1e-6, atol=1e-12)
+    m.train(R['mcmc_%s_X2' % tag], R['mcmc_%s_y2' % tag].copy())
+    np.testing.assert_allclose(np.array(m.hypers), R['mcmc_%s_hypers2' % tag], rtol=1e-8, atol=1e-10)
+    mu, var = m.predict_marginalized_over_instances(Xq)
+    np.testing.assert_allclose(mu, R['mcmc_%s_mu2' % tag], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, R['mcmc_%s_var2' % tag], rtol=1e-6, atol=1e-12)

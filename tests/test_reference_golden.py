@@ -164,3 +164,30 @@ def test_offline_loop_matches_reference(method, monkeypatch):
     if p + 'hist_ws' in R.files and len(R[p + 'hist_ws']):
         np.testing.assert_allclose(np.array([np.asarray(w, dtype=np.float64) for w in fac.hist_ws]), R[p + 'hist_ws'],
                                    rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize('tag', ['rf', 'c4'])
+def test_gp_mcmc_matches_reference(tag):
+    """model/gp_mcmc.py GaussianProcessMCMC as run by the reference itself (short chains; the stretch-move
+    sampler on both sides is the restated one -- see tests/golden/refshims/emcee.py -- so this pins _ll with
+    its Tophat bound priors, the prior-sampled initial ensemble, the burn-in / no-burn-in flow, the walker
+    models and the marginalised prediction, not emcee)."""
+    from oracle import gp_mcmc as omc
+    types, X, y, Xq = (R['mcmc_%s_%s' % (tag, k)] for k in ('types', 'X', 'y', 'Xq'))
+    g = omc.OracleGPMCMC(types, 11, chain_length=12, burnin_steps=12)
+    assert g.n_mcmc_walkers == int(R['mcmc_%s_walkers' % tag])
+    g.train(X, y.copy())
+    np.testing.assert_allclose(np.array(g.hypers), R['mcmc_%s_hypers1' % tag], rtol=1e-9, atol=1e-11)
+    mu, var = g.predict(Xq)
+    np.testing.assert_allclose(mu, R['mcmc_%s_mu1' % tag], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, R['mcmc_%s_var1' % tag], rtol=1e-6, atol=1e-13)
+    want = R['mcmc_%s_ll' % tag]
+    got = np.array([omc.ll(th.copy(), g.spec, g.X, g.y) for th in R['mcmc_%s_ll_thetas' % tag]], dtype=np.float64)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin) and fin.any() and (~fin).any()
+    np.testing.assert_allclose(got[fin], want[fin], rtol=1e-10)
+    g.train(R['mcmc_%s_X2' % tag], R['mcmc_%s_y2' % tag].copy())
+    np.testing.assert_allclose(np.array(g.hypers), R['mcmc_%s_hypers2' % tag], rtol=1e-9, atol=1e-11)
+    mu, var = g.predict_marginalized_over_instances(Xq)
+    np.testing.assert_allclose(mu, R['mcmc_%s_mu2' % tag], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, R['mcmc_%s_var2' % tag], rtol=1e-6, atol=1e-13)
