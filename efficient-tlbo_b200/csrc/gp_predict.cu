@@ -313,6 +313,18 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
       *reinterpret_cast<double2*>(s_Linv + (size_t)rr * ldl + cc + 2) = v1;
     }
   };
+  // Same copy with 16-byte asynchronous copies (LDGSTS): issued before the K* phase, awaited after it
+  auto stage_linv_async = [&](int m, int r0, int rows) {
+    const double* src = a.pack.d_Linv + (size_t)m * ncap * ldl + (size_t)r0 * ldl;
+    const int ncol = (r0 + rows + 3) & ~3;
+    const int c2 = ncol >> 1;                       // 2-column (16-byte) groups per row
+    for (int idx = tid; idx < rows * c2; idx += PRED_THREADS) {
+      const int rr = idx / c2, cc = (idx - rr * c2) << 1;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(s_Linv + (size_t)rr * ldl + cc);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)rr * ldl + cc) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   // Exactly one surrogate is evaluated per tile (the usual per-iteration launch: the target, all
   // sources resident) and its L^-1 fits one chunk: stage it ONCE per CTA, not once per tile.
   bool persist = false;
@@ -419,9 +431,12 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
       const double wm = s_lw[li];
       const bool first = (s_lf[li] & 1) != 0;
       li++;
+      const int nib = (n + 7) >> 3;           // 8-row blocks
       if (!persist) {
-        __syncthreads();
+        __syncthreads();                      // previous surrogate's readers of s_Xs / s_Linv are done
         stage_model(m, n);
+        // first L^-1 chunk: in flight while the K* phase below runs
+        stage_linv_async(m, 0, (nib * 8 < a.rc_rows) ? nib * 8 : a.rc_rows);
         __syncthreads();
       }
       const double c = s_hyp[0], ymean = s_hyp[2], ystd = s_hyp[3], diag = s_hyp[4];
@@ -511,13 +526,17 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
       double qpart[NW][2];
 #pragma unroll
       for (int w = 0; w < NW; w++) { qpart[w][0] = 0.0; qpart[w][1] = 0.0; }
-      const int nib = (n + 7) >> 3;           // 8-row blocks
       for (int r0 = 0; r0 < nib * 8; r0 += a.rc_rows) {
         const int rows = (nib * 8 - r0 < a.rc_rows) ? nib * 8 - r0 : a.rc_rows;
         if (!persist) {
-          __syncthreads();
-          stage_linv(m, r0, rows);
-          __syncthreads();
+          if (r0 == 0) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+          } else {
+            __syncthreads();
+            stage_linv(m, r0, rows);
+            __syncthreads();
+          }
         }
         for (int ib = 0; ib * 8 < rows; ib += 2) {
           const bool two = (ib + 1) * 8 < rows;
@@ -705,7 +724,8 @@ static bool fused_plan(int ncap, int nmax, int d, int dc, int dk, long long N, i
   fused_pick_layout(dc, dk, &pl->dcp, &pl->dkp);
   const int dp = pl->dcp > 0 ? pl->dcp + pl->dkp : d;
   pl->njmax = njmax;
-  const size_t limit1 = 227 * 1024 - 2048, limit2 = (227 * 1024) / 2 - 2048;
+  // one CTA: 227 KB minus slack; two CTAs per SM: 2 x (dynamic + static (~300 B) + 1 KB reserved) <= 228 KB
+  const size_t limit1 = 227 * 1024 - 2048, limit2 = (228 * 1024) / 2 - 1024 - 512;
   // preferred: two CTAs per SM (16 warps hide the sqrt / exp latency chains) with NW = 2
   if (pl->dcp > 0) {
     const size_t fixed = fused_fixed_bytes(2, njmax, dp, d, M);

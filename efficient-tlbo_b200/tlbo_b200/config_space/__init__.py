@@ -117,7 +117,12 @@ def table_to_configurations(space, X):
     return [Configuration(space, X[i], i) for i in range(X.shape[0])]
 
 
-def one_exchange_neighbourhood_arrays_py(config, seed, num_neighbors=4, stdev=0.2):
+# The reference binds these two at tlbo/config_space/__init__.py:10
+# (``partial(get_one_exchange_neighbourhood, stdev=0.05, num_neighbors=8)``) -- not ConfigSpace's own defaults.
+NUM_NEIGHBORS, NEIGHBOUR_STDEV = 8, 0.05
+
+
+def one_exchange_neighbourhood_arrays_py(config, seed, num_neighbors=NUM_NEIGHBORS, stdev=NEIGHBOUR_STDEV):
     """Readable Python statement of ``one_exchange_neighbourhood_arrays`` (the product calls the
     native ``tlbo_one_exchange_neighbourhood``; tests check the two draw for draw).
 
@@ -179,7 +184,7 @@ def one_exchange_neighbourhood_arrays_py(config, seed, num_neighbors=4, stdev=0.
     return np.array(out, dtype=np.float64).reshape(-1, d)
 
 
-def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=4, stdev=0.2):
+def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=NUM_NEIGHBORS, stdev=NEIGHBOUR_STDEV):
     """The complete one-exchange neighbourhood of ``config`` as an array ``[m, d]`` (see
     ``one_exchange_neighbourhood_arrays_py`` for the algorithm), generated by the native helper
     ``tlbo_one_exchange_neighbourhood`` of the C ABI: the Python loop costs more than the device
@@ -200,7 +205,7 @@ def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=4, stdev=0.2):
     return out[:n.value]
 
 
-def get_one_exchange_neighbourhood(config, seed, num_neighbors=4, stdev=0.2):
+def get_one_exchange_neighbourhood(config, seed, num_neighbors=NUM_NEIGHBORS, stdev=NEIGHBOUR_STDEV):
     """Generator form (the reference's call signature, tlbo/config_space/__init__.py:10)."""
     for row in one_exchange_neighbourhood_arrays(config, seed, num_neighbors, stdev):
         yield Configuration(config.space, row, -1)

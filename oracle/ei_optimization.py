@@ -15,7 +15,8 @@ published algorithm as recalled and are NOT pinned against it (parity unpinned f
 neighbourhood / sampling streams; everything downstream of them is exact):
   * ``sample``: column-wise draws from the space's own RandomState;
   * ``neighbourhood``: the lazy generator ``ConfigSpace.util.get_one_exchange_neighbourhood
-    (configuration, seed, num_neighbors=4, stdev=0.2)``.
+    (configuration, seed, num_neighbors=8, stdev=0.05)`` -- the two keyword values are what the
+    reference binds at ``tlbo/config_space/__init__.py:10``, not ConfigSpace's own defaults.
 """
 import numpy as np
 
@@ -42,7 +43,7 @@ class OracleSpace(object):
                 X[:, j] = self.rng.uniform(0.0, 1.0, size=size)
         return X
 
-    def neighbourhood(self, array, seed, num_neighbors=4, stdev=0.2):
+    def neighbourhood(self, array, seed, num_neighbors=8, stdev=0.05):
         """Lazy generator: one neighbour per ``next``."""
         random = np.random.RandomState(seed)
         d = len(array)

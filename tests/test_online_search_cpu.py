@@ -52,7 +52,7 @@ def test_sampling_and_neighbourhood_match_the_oracle(types, const):
     assert np.array_equal(np.array([c.get_array() for c in cfgs]), osp.sample(5))
     one = sp.sample_configuration()
     assert np.array_equal(one.get_array(), osp.sample(1)[0])
-    n_expected = sum((int(t) - 1) if t > 0 else (0 if (const is not None and const[j]) else 4)
+    n_expected = sum((int(t) - 1) if t > 0 else (0 if (const is not None and const[j]) else 8)   # num_neighbors=8: tlbo/config_space/__init__.py:10
                      for j, t in enumerate(types))
     for i, c in enumerate(cfgs):
         got = one_exchange_neighbourhood_arrays(c, seed=100 + i)
@@ -149,4 +149,4 @@ def test_native_neighbourhood_reproduces_numpys_legacy_stream():
     sp = TableSpace(np.array([0, 0, 3]))
     c = Configuration(sp, np.array([0.3, np.nan, 1.0]), -1)
     a, b = one_exchange_neighbourhood_arrays(c, 5), one_exchange_neighbourhood_arrays_py(c, 5)
-    assert a.shape == (6, 3) and np.array_equal(a, b, equal_nan=True)
+    assert a.shape == (10, 3) and np.array_equal(a, b, equal_nan=True)   # 8 numerical + 2 categorical
