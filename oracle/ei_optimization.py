@@ -172,8 +172,12 @@ def interleaved_maximize(acq_fn, space, rng, evaluated_configs, num_points, n_sl
 class OracleSMBOOnline(object):
     """``SMBO_ONLINE`` (smbo_online.py) with ``evaluate`` = ``objective_function(config)``."""
 
-    def __init__(self, objective_function, space, surrogate_model, random_seed, initial_runs=3, num_points=5000):
+    def __init__(self, objective_function, space, surrogate_model, random_seed, initial_runs=3, num_points=5000,
+                 first_config=None):
         from oracle.acquisition import OracleEI
+        # smbo_offline.py:211-217: the default configuration, or -- when it is not a key of the target
+        # table -- ``configuration_list[0]``, is proposed while it is unevaluated
+        self.first_config = None if first_config is None else np.asarray(first_config, dtype=np.float64)
         self.objective_function = objective_function
         self.space = space
         self.random_seed = random_seed
@@ -208,7 +212,9 @@ class OracleSMBOOnline(object):
 
     def choose_next(self, X, Y):
         if X.shape[0] < self.init_num:
-            return self.sample_random_config()            # no default configuration in an OracleSpace
+            if self.first_config is not None and not self._seen(self.first_config):
+                return self.first_config
+            return self.sample_random_config()
         if self.chooser_rng.rand() < 0.001:
             config = self.sample_random_config()
             tw = self.model.target_weight

@@ -22,6 +22,10 @@ restored.  Everything recorded below is computed by reference code:
            ensemble drawn from the priors, the walkers' positions after short chains (two consecutive
            train calls: with and without burn-in), marginalised prediction.  The stretch-move sampler
            itself comes from the emcee stand-in (= the oracle's restatement): sampler NOT pinned
+  online_* framework/online/smbo_online.SMBO_ONLINE + optimizer/ei_optimization.InterleavedLocalAndRandomSearch
+           (LocalSearch, RandomSearch, ChallengerList) over RGPE / OBTLV: picked configurations, perfs, weights,
+           fitted theta, np.random states.  ConfigSpace's sampling / neighbourhood streams come from the
+           stand-in (= the oracle's restatement): those two streams NOT pinned
   loop_*   framework/smbo_offline.SMBO_OFFLINE driving facade/rgpe.RGPE, facade/topo.TransBO_RGPE,
            facade/topo_variant1.OBTLV, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
            dilution flags, the bootstrap ranking-loss tables (captured from the np.argmin calls of
@@ -57,6 +61,7 @@ from tlbo.facade.rgpe import RGPE                                           # no
 from tlbo.facade.topo import TransBO_RGPE                                   # noqa: E402
 from tlbo.facade.topo_variant1 import OBTLV                                 # noqa: E402
 from tlbo.facade.tst import TST                                             # noqa: E402
+from tlbo.framework.online.smbo_online import SMBO_ONLINE                   # noqa: E402
 from tlbo.framework.smbo_offline import SMBO_OFFLINE                        # noqa: E402
 import tlbo.model.gp as ref_gp                                              # noqa: E402
 from tlbo.model.model_builder import build_model                            # noqa: E402
@@ -280,12 +285,69 @@ def loop_level(out):
         print(method, 'rows', rows, 'fits', n_source_fits, fits_per_iter, 'loss rows', len(losses))
 
 
+def online_objective(x):
+    return float(np.sin(3 * x[3]) + 0.5 * x[6] ** 2 + 0.3 * x[0] + 0.2 * np.cos(5 * x[7]) * x[1])
+
+
+def online_level(out):
+    """SMBO_ONLINE + InterleavedLocalAndRandomSearch (LocalSearch one neighbour per acquisition call,
+    sorted RandomSearch, ChallengerList) over RGPE and OBTLV.  The objective returns ``(perf, test_perf)``
+    because ``SMBO_ONLINE.evaluate`` hands its value to an ``iterate`` that unpacks two
+    (smbo_online.py:28-39 / smbo_offline.py:162).  num_points is the reference's hard-coded 5000."""
+    types = RF_TYPES
+    K, n_src, seed, iters = 3, 50, 3822, 8
+    tables = [(out['loop_task%d_X' % t], out['loop_task%d_y' % t]) for t in range(1, K + 1)]
+    first = np.array([1., 0., 0., 0.25, 0., 0., 0.75, 0.5, 0.])
+    out['online_first'], out['online_seed'] = first, seed
+    for method, cls in (('rgpe', RGPE), ('topo', OBTLV)):
+        cs = rf_space()
+        sources = [collections.OrderedDict((Configuration(cs, vector=x), float(v)) for x, v in zip(X, y))
+                   for X, y in tables]
+        c0 = Configuration(cs, vector=first)
+        target = collections.OrderedDict([(c0, (online_objective(first), -1))])
+        thetas = []
+        orig_train = ref_gp.GaussianProcess._train
+
+        def spy_train(self, X, y, do_optimize=True):
+            r = orig_train(self, X, y, do_optimize)
+            thetas.append(np.array(self.hypers, dtype=np.float64))
+            return r
+        ref_gp.GaussianProcess._train = spy_train
+        try:
+            fac = quiet(cls, cs, sources, list(target.keys()), seed, surrogate_type='gp', num_src_hpo_trial=n_src)
+            n_source_fits = len(thetas)
+            smbo = quiet(SMBO_ONLINE, lambda c: (online_objective(c.get_array()), -1), target, cs, fac,
+                         random_seed=seed, max_runs=iters, source_hpo_data=sources, num_src_hpo_trial=n_src,
+                         surrogate_type='gp', initial_runs=3, logging_dir='/tmp/tlbo_ref_logs')
+            picks, states, fits_per_iter, w_hist = [], [], [], []
+            for _ in range(iters):
+                before = len(thetas)
+                cfg, _, _, _ = quiet(smbo.iterate)
+                picks.append(np.array(cfg.get_array(), dtype=np.float64))
+                fits_per_iter.append(len(thetas) - before)
+                st = np.random.get_state()
+                states.append(np.concatenate([st[1].astype(np.int64), [st[2], st[3]], [np.float64(st[4]).view(np.int64)]]))
+                w_hist.append(np.array(fac.w, dtype=np.float64).ravel())
+        finally:
+            ref_gp.GaussianProcess._train = orig_train
+        p = 'online_%s_' % method
+        out[p + 'picks'] = np.array(picks)
+        out[p + 'perfs'] = np.array(smbo.perfs, dtype=np.float64)
+        out[p + 'thetas'] = np.array(thetas)
+        out[p + 'n_source_fits'] = n_source_fits
+        out[p + 'fits_per_iter'] = np.array(fits_per_iter)
+        out[p + 'np_random_state'] = np.array(states)
+        out[p + 'w'] = np.array(w_hist)
+        print('online', method, 'fits', fits_per_iter, 'perfs', np.round(smbo.perfs, 4))
+
+
 def main():
     out = {}
     gp_level(out)
     mcmc_level(out)
     slsqp_level(out)
     loop_level(out)
+    online_level(out)
     path = os.path.join(HERE, 'reference_v1.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes,', len(out), 'arrays')

@@ -1,5 +1,15 @@
-"""Stand-in for ConfigSpace (see ../README.md): value classes with the attributes the reference reads."""
+"""Stand-in for ConfigSpace (see ../README.md): value classes with the attributes the reference reads.
+``sample_configuration`` and ``util.get_one_exchange_neighbourhood`` run the sampling / neighbourhood
+streams as RESTATED in oracle/ei_optimization.py ``OracleSpace`` (ConfigSpace itself is not on this
+machine: fixtures made through them pin the reference's own maximisers, not ConfigSpace's streams)."""
+import os
+import sys
+
 import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
 
 from ConfigSpace.hyperparameters import (CategoricalHyperparameter, Constant, OrdinalHyperparameter,  # noqa
                                          UniformFloatHyperparameter, UniformIntegerHyperparameter)
@@ -32,6 +42,20 @@ class ConfigurationSpace(object):
 
     def get_conditions(self):
         return []
+
+    def _oracle_space(self):
+        from oracle.ei_optimization import OracleSpace
+        types = [len(hp.choices) if isinstance(hp, CategoricalHyperparameter) else 0 for hp in self._hps]
+        const = [isinstance(hp, Constant) for hp in self._hps]
+        sp = OracleSpace(types, const)
+        sp.rng = self.random                      # one stream: the space's own RandomState
+        return sp
+
+    def sample_configuration(self, size=1):
+        X = self._oracle_space().sample(size)
+        if size == 1:
+            return Configuration(self, vector=X[0])
+        return [Configuration(self, vector=x) for x in X]
 
     def get_forbiddens(self):
         return []

@@ -212,3 +212,41 @@ def test_cuda_gp_mcmc_matches_reference(tag):
     mu, var = m.predict_marginalized_over_instances(Xq)
     np.testing.assert_allclose(mu, R['mcmc_%s_mu2' % tag], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(var, R['mcmc_%s_var2' % tag], rtol=1e-6, atol=1e-12)
+
+
+def _online_objective(c):
+    x = c.get_array()
+    return float(np.sin(3 * x[3]) + 0.5 * x[6] ** 2 + 0.3 * x[0] + 0.2 * np.cos(5 * x[7]) * x[1])
+
+
+@pytest.mark.parametrize('method', ['rgpe', 'topo'])
+def test_cuda_online_loop_matches_reference(method, monkeypatch):
+    """The drop-in SMBO_ONLINE (batched one-exchange local search, ONE acquisition call per hill-climb
+    step) against the reference's own SMBO_ONLINE + InterleavedLocalAndRandomSearch run (one call per
+    neighbour): same configurations, same np.random stream, device GPs at the reference's theta."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.rgpe import RGPE
+    from tlbo_b200.facade.topo_variant1 import OBTLV
+    from tlbo_b200.framework.smbo_online import SMBO_ONLINE
+    forced = _ForcedFits(monkeypatch)
+    K, types, seed = int(R['loop_K']), R['loop_types'], int(R['online_seed'])
+    p = 'online_%s_' % method
+    const = np.array([0, 0, 1, 0, 1, 1, 0, 0, 1], dtype=bool)
+    sources = [(R['loop_task%d_X' % t].copy(), R['loop_task%d_y' % t].copy()) for t in range(1, K + 1)]
+    thetas = [th for th in R[p + 'thetas']]
+    nsrc = int(R[p + 'n_source_fits'])
+    forced.queue = thetas[:nsrc]
+    cs = TableSpace(types, const_mask=const, default=R['online_first'])
+    fac = dict(rgpe=RGPE, topo=OBTLV)[method](cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+    smbo = SMBO_ONLINE(_online_objective, cs, fac, initial_runs=3, random_seed=seed, max_runs=100)
+    used = nsrc
+    for it, pick in enumerate(R[p + 'picks']):
+        nfit = int(R[p + 'fits_per_iter'][it])
+        forced.queue = thetas[used:used + nfit]
+        used += nfit
+        cfg, _, perf, _ = smbo.iterate()
+        assert not forced.queue
+        np.testing.assert_array_equal(cfg.get_array(), pick, err_msg='iteration %d' % it)
+        np.testing.assert_array_equal(_state_vec(), R[p + 'np_random_state'][it], err_msg='np.random stream, it %d' % it)
+        np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), R[p + 'w'][it], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(np.asarray(smbo.perfs), R[p + 'perfs'])

@@ -191,3 +191,40 @@ def test_gp_mcmc_matches_reference(tag):
     mu, var = g.predict_marginalized_over_instances(Xq)
     np.testing.assert_allclose(mu, R['mcmc_%s_mu2' % tag], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(var, R['mcmc_%s_var2' % tag], rtol=1e-6, atol=1e-13)
+
+
+def _online_objective(x):
+    return float(np.sin(3 * x[3]) + 0.5 * x[6] ** 2 + 0.3 * x[0] + 0.2 * np.cos(5 * x[7]) * x[1])
+
+
+RF_CONST = np.array([0, 0, 1, 0, 1, 1, 0, 0, 1], dtype=bool)
+
+
+@pytest.mark.parametrize('method', ['rgpe', 'topo'])
+def test_online_loop_matches_reference(method, monkeypatch):
+    """SMBO_ONLINE + InterleavedLocalAndRandomSearch (LocalSearch scoring ONE neighbour per acquisition
+    call, sorted RandomSearch over ~4990 configurations, ChallengerList) as run by the reference itself:
+    the oracle picks the same configurations with the same np.random stream consumption.  (The space's
+    sampling / neighbourhood streams are the restated ones on both sides: tests/golden/refshims/ConfigSpace.)"""
+    from oracle.ei_optimization import OracleSMBOOnline, OracleSpace
+    monkeypatch.setattr(ofacade, 'OracleGP', _ForcedGP)
+    K, types, seed = int(R['loop_K']), R['loop_types'], int(R['online_seed'])
+    p = 'online_%s_' % method
+    sources = [(R['loop_task%d_X' % t].copy(), R['loop_task%d_y' % t].copy()) for t in range(1, K + 1)]
+    thetas = [th for th in R[p + 'thetas']]
+    nsrc = int(R[p + 'n_source_fits'])
+    _ForcedGP.queue = thetas[:nsrc]
+    fac = LOOPS[method](types, sources, seed)
+    smbo = OracleSMBOOnline(_online_objective, OracleSpace(types, RF_CONST), fac, seed, initial_runs=3,
+                            first_config=R['online_first'])
+    used = nsrc
+    for it, pick in enumerate(R[p + 'picks']):
+        nfit = int(R[p + 'fits_per_iter'][it])
+        _ForcedGP.queue = thetas[used:used + nfit]
+        used += nfit
+        got = smbo.iterate()
+        assert not _ForcedGP.queue
+        np.testing.assert_array_equal(got, pick, err_msg='iteration %d' % it)
+        np.testing.assert_array_equal(_state_vec(), R[p + 'np_random_state'][it], err_msg='np.random stream, it %d' % it)
+        np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), R[p + 'w'][it], rtol=1e-6, atol=1e-8)
+    np.testing.assert_array_equal(np.asarray(smbo.perfs), R[p + 'perfs'])
