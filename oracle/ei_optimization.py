@@ -12,7 +12,12 @@ Configurations are plain ``float64[d]`` arrays in the reference's encoding.  The
 (``OracleSpace``) restates the two ConfigSpace services the maximisers use -- ConfigSpace 0.4.12
 is an UN-VENDORED dependency absent from this image (``requirements.txt``), so these follow its
 published algorithm as recalled and are NOT pinned against it (parity unpinned for the
-neighbourhood / sampling streams; everything downstream of them is exact):
+neighbourhood / sampling streams).  Everything downstream of them IS pinned against the reference's
+own ``SMBO_ONLINE`` + ``InterleavedLocalAndRandomSearch`` / ``LocalSearch`` / ``RandomSearch`` /
+``ChallengerList`` code, run unmodified in the build container over a ConfigSpace stand-in that wraps
+``OracleSpace`` (``tests/golden/make_reference_golden.py`` -> ``reference_v1.npz`` ``online_*``; checked by
+``tests/test_reference_golden.py::test_online_loop_matches_reference``: same picked configurations, same
+``np.random`` stream states, same weights):
   * ``sample``: column-wise draws from the space's own RandomState;
   * ``neighbourhood``: the lazy generator ``ConfigSpace.util.get_one_exchange_neighbourhood
     (configuration, seed, num_neighbors=8, stdev=0.05)`` -- the two keyword values are what the

@@ -17,9 +17,14 @@ algorithm is restated here from the emcee 3.x sources as recalled (``ensemble.py
 ``moves/stretch.py`` ``StretchMove.get_proposal``, ``ensemble.py`` ``walkers_independent``):
 the affine-invariant stretch move of Goodman & Weare (2010) with a = 2, two randomly split
 halves per step, every random number drawn from ``sampler._random`` (a legacy
-``RandomState``).  PARITY UNPINNED for the sampler: no golden vector of the reference or of
-emcee exists here; ``tests/test_oracle_mcmc.py`` pins it against first principles (detailed
-balance on a known Gaussian target, stream-consumption invariants).
+``RandomState``).  PARITY UNPINNED for the sampler: no golden vector of emcee exists here;
+``tests/test_oracle_mcmc.py`` pins it against first principles (detailed balance on a known
+Gaussian target, stream-consumption invariants).  Everything AROUND the sampler is pinned against
+the reference's own ``GaussianProcessMCMC`` code, run unmodified in the build container over an
+``emcee.EnsembleSampler`` stand-in that wraps ``emcee_run`` below
+(``tests/golden/make_reference_golden.py`` -> ``reference_v1.npz`` ``mcmc_*``: ``_ll`` with its Tophat
+bound priors, the prior-sampled initial ensemble, burn-in / continuation flow, walker models,
+marginalised prediction; checked by ``tests/test_reference_golden.py::test_gp_mcmc_matches_reference``).
 """
 import numpy as np
 import scipy.linalg
