@@ -153,3 +153,123 @@ extern "C" int tlbo_one_exchange_neighbourhood(const double* h_array, int d, con
   *h_n_rows = rows;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Host half of `build_single_surrogate` + `GaussianProcess._train` for a batch of cross-validation jobs
+// (reference tlbo/facade/base_facade.py:93-108, tlbo/facade/rgpe.py:55-70, tlbo/facade/topo_variant1.py,
+// tlbo/model/gp.py:115-122, tlbo/model/base_gp.py:48-64,148-151, tlbo/utils/normalization.py:4-28).
+//
+// Per BO iteration the facades build 1 + 5 training sets from the same (X, y): all rows, and all rows
+// except one contiguous validation range.  Each set gets the all-equal guard(s), the facade-level
+// normalisation, the inactive-value imputation and the GP-level standardisation -- a few dozen numpy
+// calls on 50-element arrays per set, ~0.09 ms each in the interpreter, on the critical path in front of
+// the device fit.  This helper writes all of them straight into the padded upload buffer.
+//
+// Every floating-point result is bit-identical to numpy's: `np.mean` / `np.std` reduce with numpy's
+// pairwise summation (8 interleaved partial sums up to 128 elements, recursive halving above), the
+// variance is mean(|x - mean|^2) with the mean divided first, and each elementwise operation is a single
+// IEEE operation (this file is compiled for the host without FMA contraction).
+// tests/test_host_logic.py checks it against the numpy statement on thousands of random cases.
+namespace {
+
+double np_pairwise_sum(const double* a, long n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (long i = 0; i < n; i++) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    long i;
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+  }
+  long n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+inline double np_sum(const double* a, long n) { return 0.0 + np_pairwise_sum(a, n); }   // add.reduce starts from the identity
+inline double np_mean(const double* a, long n) { return np_sum(a, n) / (double)n; }
+double np_std(const double* a, long n, double* tmp) {
+  const double m = np_sum(a, n) / (double)n;
+  for (long i = 0; i < n; i++) { const double x = a[i] - m; tmp[i] = x * x; }
+  return sqrt(np_sum(tmp, n) / (double)n);
+}
+
+}  // namespace
+
+extern "C" int tlbo_host_prepare_jobs(const double* h_X, double* h_y_inout, int n, int d, int n_jobs,
+                                      const int32_t* h_skip_lo, const int32_t* h_skip_hi,
+                                      const int32_t* h_outer_guard, int normalize, int normalize_y, int ncap,
+                                      double* h_Xout, double* h_yout, int32_t* h_nout, double* h_ymean,
+                                      double* h_ystd) {
+  if (!h_X || !h_y_inout || !h_skip_lo || !h_skip_hi || !h_Xout || !h_yout || !h_nout || !h_ymean || !h_ystd ||
+      n <= 0 || d <= 0 || n_jobs <= 0 || ncap < n || normalize < 0 || normalize > 2) {
+    tlbo_set_error("tlbo_host_prepare_jobs: bad arguments");
+    return TLBO_E_BADARG;
+  }
+  double* tmp = new double[2 * (size_t)n];
+  double* yc = tmp + n;
+  for (int b = 0; b < n_jobs; b++) {
+    const int lo = h_skip_lo[b], hi = h_skip_hi[b];
+    if (lo < 0 || hi < lo || hi > n || (hi - lo) >= n) {
+      delete[] tmp;
+      tlbo_set_error("tlbo_host_prepare_jobs: bad validation range");
+      return TLBO_E_BADARG;
+    }
+    const int m = n - (hi - lo);
+    auto src = [&](int i) { return i < lo ? i : i + (hi - lo); };      // kept row i -> row of (X, y)
+    // caller-side guard on the ORIGINAL y (rgpe.py:62-63): y[rows] all equal -> y[rows[0]] += 1e-4
+    if (h_outer_guard && h_outer_guard[b]) {
+      bool alleq = true;
+      const double y0 = h_y_inout[src(0)];
+      for (int i = 1; i < m && alleq; i++) alleq = (h_y_inout[src(i)] == y0);
+      if (alleq) h_y_inout[src(0)] += 1e-4;
+    }
+    const bool whole = (hi == lo);             // the job's y IS the caller's array (no fancy-index copy)
+    for (int i = 0; i < m; i++) yc[i] = h_y_inout[src(i)];
+    // build_single_surrogate (base_facade.py:96-104)
+    if (normalize == 1 || normalize == 2) {
+      bool alleq = true;
+      for (int i = 1; i < m && alleq; i++) alleq = (yc[i] == yc[0]);
+      if (alleq) {
+        yc[0] += 1e-4;
+        if (whole) h_y_inout[0] += 1e-4;       // in-place on the caller's array
+      }
+      if (normalize == 1) {
+        const double mean = np_mean(yc, m), sd = np_std(yc, m, tmp);
+        for (int i = 0; i < m; i++) yc[i] = (yc[i] - mean) / sd;
+      } else {
+        double mn = yc[0], mx = yc[0];
+        for (int i = 1; i < m; i++) { mn = yc[i] < mn ? yc[i] : mn; mx = yc[i] > mx ? yc[i] : mx; }
+        for (int i = 0; i < m; i++) yc[i] = (yc[i] - mn) / (mx - mn);
+      }
+    }
+    // GaussianProcess._train: standardise again (base_gp.py:48-64); std == 0 -> 1
+    double ym = 0.0, ys = 1.0;
+    if (normalize_y) {
+      ym = np_mean(yc, m);
+      ys = np_std(yc, m, tmp);
+      if (ys == 0.0) ys = 1.0;
+      for (int i = 0; i < m; i++) yc[i] = (yc[i] - ym) / ys;
+    }
+    h_ymean[b] = ym; h_ystd[b] = ys; h_nout[b] = m;
+    double* yo = h_yout + (size_t)b * ncap;
+    double* Xo = h_Xout + (size_t)b * ncap * d;
+    for (int i = 0; i < m; i++) {
+      yo[i] = yc[i];
+      const double* xr = h_X + (size_t)src(i) * d;
+      for (int p = 0; p < d; p++) { const double v = xr[p]; Xo[(size_t)i * d + p] = isfinite(v) ? v : -1.0; }
+    }
+    for (int i = m; i < ncap; i++) {
+      yo[i] = 0.0;
+      for (int p = 0; p < d; p++) Xo[(size_t)i * d + p] = 0.0;
+    }
+  }
+  delete[] tmp;
+  return 0;
+}

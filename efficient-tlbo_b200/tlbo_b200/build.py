@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(PKG, 'build')
 LIB = os.path.join(LIB_DIR, 'libtlbo_b200.so')
 SOURCES = ['c_api.cu', 'gp_fit.cu', 'gp_mcmc.cu', 'gp_predict.cu', 'host_search.cu', 'weights.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-diag-suppress', '550']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-diag-suppress', '550']
 
 
 def _nvcc():

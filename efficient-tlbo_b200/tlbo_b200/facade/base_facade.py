@@ -17,7 +17,7 @@ import abc
 import numpy as np
 
 from tlbo_b200.config_space import convert_configurations_to_array, get_types
-from tlbo_b200.model.gp import fit_models_async
+from tlbo_b200.model.gp import fit_models_async, fit_prepared_async
 from tlbo_b200.model.gp_mcmc import fit_mcmc_models_async
 from tlbo_b200.model.model_builder import build_model
 from tlbo_b200.utils.constants import VERY_SMALL_NUMBER
@@ -189,6 +189,26 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             y, _, _ = zero_one_normalization(y)
         model.bind(self._ensure_pack(X.shape[0]), slot)
         return model, X, y
+
+    def _native_prep_ok(self, X, y):
+        """The native host-prep path covers MAP GPs fed with a plain float64 vector."""
+        return (self._G == 1 and isinstance(y, np.ndarray) and y.dtype == np.float64 and y.ndim == 1
+                and y.flags.c_contiguous and isinstance(X, np.ndarray) and X.ndim == 2 and X.shape[0] == y.shape[0])
+
+    def _prepare_cv_jobs(self, X, y, ranges, outer_guard, normalize):
+        """``[_prepare_single_surrogate(X minus ranges[j], ...) for j]`` with the host half (guards, the two
+        normalisations, imputation, padding) done by ONE native call (``tlbo_host_prepare_jobs``,
+        bit-identical to the numpy statement above; ``y`` is mutated in place where the reference mutates
+        it).  Job j goes to slot ``K + j``.  Returns ``(models, launch)``; ``launch()`` enqueues the batched
+        fit and returns its ``finish``."""
+        from tlbo_b200 import ops
+        if self._proto is None:
+            self._proto = self._new_model()
+            self._share_start_points(self._proto)
+        pack = self._ensure_pack(X.shape[0])
+        prep = ops.prepare_jobs(X, y, ranges, outer_guard, normalize)
+        models = [self._proto.fresh_copy().bind(pack, self.K + j) for j in range(len(ranges))]
+        return models, (lambda: fit_prepared_async(models, prep))
 
     def build_single_surrogate(self, X, y, normalize, slot=None):
         job = self._prepare_single_surrogate(X, y, normalize, self.K if slot is None else slot)

@@ -47,13 +47,20 @@ class OBTLV(BaseFacade):
         instance_num = X.shape[0]
         do_cv = (not self.only_source) and instance_num >= self.min_num_y
         # host halves of every build_single_surrogate of this call, then ONE batched fit
-        jobs = [self._prepare_single_surrogate(X, y, _scale_method, K)]
         folds = _kfold_val_slices(instance_num, 5) if do_cv else []
-        for i, (lo, hi) in enumerate(folds):
-            train_idx = np.concatenate([np.arange(0, lo), np.arange(hi, instance_num)])
-            jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
-        for j, job in enumerate(jobs):
-            job[0].bind(self._pack, K + j)
+        if self._native_prep_ok(X, y):
+            # one native call for the host half of all 1 + 5 training sets (see BaseFacade._prepare_cv_jobs)
+            fit_models, launch_fit = self._prepare_cv_jobs(X, y, [(0, 0)] + list(folds), [0] * (1 + len(folds)),
+                                                           _scale_method)
+        else:
+            jobs = [self._prepare_single_surrogate(X, y, _scale_method, K)]
+            for i, (lo, hi) in enumerate(folds):
+                train_idx = np.concatenate([np.arange(0, lo), np.arange(hi, instance_num)])
+                jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
+            for j, job in enumerate(jobs):
+                job[0].bind(self._pack, K + j)
+            fit_models = [j[0] for j in jobs]
+            launch_fit = lambda: self._fit_async(fit_models, [j[1] for j in jobs], [j[2] for j in jobs])
         import torch
         from tlbo_b200 import ops
         X_dev = self._to_device(X)                       # before the fit is enqueued
@@ -61,9 +68,9 @@ class OBTLV(BaseFacade):
         if self._side is None:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(main)                     # X_dev and the source slots are ready
-        finish_fit = self._fit_async([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
-        self.target_surrogate = jobs[0][0]
-        self.last_fit_models = [j[0] for j in jobs]
+        finish_fit = launch_fit()
+        self.target_surrogate = fit_models[0]
+        self.last_fit_models = fit_models
         self.target_y_range = 0.5 * (np.max(y) - np.min(y))
         # Phase 1 (source weights) depends only on the SOURCE surrogates: it runs on a side
         # stream -- source predictions at X plus the SLSQP callbacks -- while the batched fit of

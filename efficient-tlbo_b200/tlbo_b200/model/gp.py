@@ -213,6 +213,39 @@ def fit_models(models, Xs, Ys, do_optimize=True):
     return fit_models_async(models, Xs, Ys, do_optimize)()
 
 
+def fit_prepared_async(models, prep):
+    """``fit_models_async`` for a batch whose host half was done by ``ops.prepare_jobs`` (one native call
+    instead of a few dozen numpy calls per surrogate): ``models`` are fresh surrogates bound to consecutive
+    slots of one pack and sharing their start points; returns ``finish()``."""
+    from tlbo_b200 import ops
+    m0 = models[0]
+    p0 = m0._start_points()
+    for b, mdl in enumerate(models):
+        assert mdl._pack is m0._pack and mdl._slot == m0._slot + b and mdl.normalize_y
+        assert mdl._start_points() is p0 or np.array_equal(mdl._start_points(), p0)
+        mdl.mean_y_, mdl.std_y_ = float(prep.ymean[b]), float(prep.ystd[b])
+    lb = m0.kernel.bounds
+    h = ops.gp_fit_batched(None, None, m0.types, p0, lb[:, 0], lb[:, 1], None, None, m0._pack, slot0=m0._slot,
+                           sync=False, prepared=prep)
+
+    def finish():
+        st = h.finish()
+        thetas = ops.d2h(m0._pack.theta[m0._slot:m0._slot + len(models)])
+        lazy = _LazyFitInfo(h)
+        for b, mdl in enumerate(models):
+            if st[b] == 1:
+                raise np.linalg.LinAlgError('Cholesky of the kernel matrix failed at the selected hyper-parameters')
+            if st[b] != 0:
+                raise RuntimeError('GP fit failed: no finite optimum (status %d)' % st[b])
+            mdl.hypers = thetas[b].copy()
+            mdl.kernel.theta = thetas[b].copy()
+            mdl.is_trained = True
+            mdl.n_train_ = int(prep.n[b])
+            mdl.fit_info_ = _FitInfoView(lazy, b)
+        return models
+    return finish
+
+
 def fit_models_async(models, Xs, Ys, do_optimize=True):
     """Enqueue the batched fit and return ``finish()``; host work done between the two
     overlaps the device fit.

@@ -202,6 +202,40 @@ def _pad_batch(X_list, y_list, ncap, d):
     return dbuf[:nx].view(B, ncap, d), dbuf[nx:nx + ny].view(B, ncap), dbuf[nx + ny:].view(torch.int32)[:B]
 
 
+class PreparedBatch(object):
+    """Padded upload buffer of a batched fit, filled by the native ``tlbo_host_prepare_jobs`` (the host half
+    of ``build_single_surrogate`` + ``GaussianProcess._train`` for the 1 + 5 training sets of an iteration,
+    bit-identical to the numpy statement in ``facade/base_facade.py`` / ``model/gp.py``)."""
+
+    def __init__(self, buf, B, ncap, d, n, ymean, ystd):
+        self.buf, self.B, self.ncap, self.d = buf, B, ncap, d
+        self.n, self.ymean, self.ystd = n, ymean, ystd
+
+
+def prepare_jobs(X, y, ranges, outer_guard, normalize, normalize_y=True):
+    """``tlbo_host_prepare_jobs``: job b trains on every row of (X, y) except ``ranges[b] = (lo, hi)``.
+    ``y`` (float64, contiguous) is mutated in place exactly where the reference mutates the caller's array
+    (the all-equal guards).  ``normalize``: 'none' | 'standardize' | 'scale'."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    assert y.dtype == np.float64 and y.flags.c_contiguous and y.ndim == 1
+    n, d = X.shape
+    B = len(ranges)
+    ncap = round_up(n, 8)
+    nx, ny = B * ncap * d, B * ncap
+    buf = np.empty(nx + ny + (B + 1) // 2 + 1, dtype=np.float64)
+    nh = buf[nx + ny:].view(np.int32)
+    nh[:] = 0
+    lo = np.array([r[0] for r in ranges], dtype=np.int32)
+    hi = np.array([r[1] for r in ranges], dtype=np.int32)
+    og = np.array(outer_guard, dtype=np.int32)
+    ym = np.empty(B, dtype=np.float64)
+    ys = np.empty(B, dtype=np.float64)
+    check(lib.tlbo_host_prepare_jobs(ptr(X), ptr(y), n, d, B, ptr(lo), ptr(hi), ptr(og),
+                                     {'none': 0, 'standardize': 1, 'scale': 2}[normalize], 1 if normalize_y else 0,
+                                     ncap, ptr(buf), ptr(buf[nx:]), ptr(nh), ptr(ym), ptr(ys)))
+    return PreparedBatch(buf, B, ncap, d, nh[:B].copy(), ym, ys)
+
+
 class FitHandle(object):
     """Result buffers of an enqueued ``tlbo_gp_fit_batched``; ``finish`` reads them back
     (one synchronisation)."""
@@ -248,18 +282,28 @@ def cached_upload(a):
 
 
 def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0, do_optimize=True,
-                   return_restarts=False, sync=True):
+                   return_restarts=False, sync=True, prepared=None):
     """``tlbo_gp_fit_batched``.  X_list/y_list: per-surrogate host arrays (y already
     normalised); p0 [R, H] start points; returns status int32[B] (host) and optionally
     the per-restart results -- or, with ``sync=False``, a ``FitHandle`` right after the
-    launch so that host work can overlap the fit."""
-    B = len(X_list)
-    d = int(X_list[0].shape[1])
+    launch so that host work can overlap the fit.  ``prepared``: a ``PreparedBatch`` (then
+    X_list / y_list / ymean / ystd are taken from it)."""
+    if prepared is not None:
+        B, d, ncap = prepared.B, prepared.d, prepared.ncap
+        ymean, ystd = prepared.ymean, prepared.ystd
+    else:
+        B = len(X_list)
+        d = int(X_list[0].shape[1])
+        ncap = round_up(max(x.shape[0] for x in X_list), 8)
     H = d + 2
-    ncap = round_up(max(x.shape[0] for x in X_list), 8)
     if ncap > pack.ncap:
         raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
-    dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
+    if prepared is not None:
+        nx, ny = B * ncap * d, B * ncap
+        dbuf = h2d(prepared.buf)
+        dX, dy, dn = dbuf[:nx].view(B, ncap, d), dbuf[nx:nx + ny].view(B, ncap), dbuf[nx + ny:].view(torch.int32)[:B]
+    else:
+        dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
     dev = dX.device
     p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, H))
     R = p0.shape[0]

@@ -258,6 +258,22 @@ int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t*
                                     const uint8_t* h_const_mask, uint32_t seed, int num_neighbors, double stdev,
                                     double* h_out, int max_rows, int32_t* h_n_rows);
 
+/* Host-side helper (no device work): the host half of build_single_surrogate + GaussianProcess._train for
+ * the 1 + 5 training sets a facade builds per BO iteration from the same (X, y) -- all rows, and all rows
+ * except one contiguous validation range (reference tlbo/facade/base_facade.py:93-108, rgpe.py:55-70,
+ * topo_variant1.py CV folds, tlbo/model/gp.py:115-122, base_gp.py:48-64,148-151, utils/normalization.py).
+ * Applies the all-equal guards (h_y_inout is mutated exactly where the reference mutates the caller's y),
+ * the facade-level normalisation (0 none, 1 standardize, 2 zero-one), the non-finite -> -1 imputation and
+ * the GP-level standardisation, bit-identical to the numpy statement (numpy's pairwise summation), and
+ * writes the zero-padded upload buffers of tlbo_gp_fit_batched.
+ *   h_X [n, d], h_y_inout [n]; job b keeps every row except [h_skip_lo[b], h_skip_hi[b])
+ *   h_outer_guard [n_jobs] (may be NULL): 1 = apply rgpe.py:62-63's guard on the original y first
+ *   h_Xout [n_jobs, ncap, d], h_yout [n_jobs, ncap], h_nout / h_ymean / h_ystd [n_jobs]                    */
+int tlbo_host_prepare_jobs(const double* h_X, double* h_y_inout, int n, int d, int n_jobs,
+                           const int32_t* h_skip_lo, const int32_t* h_skip_hi, const int32_t* h_outer_guard,
+                           int normalize, int normalize_y, int ncap, double* h_Xout, double* h_yout,
+                           int32_t* h_nout, double* h_ymean, double* h_ystd);
+
 /* Device-rate probes used by bench.py for the roofline denominators (FP64 FMA pipe and
  * FP64 mma.sync rate are not in MEASURED_PEAKS.json).  Returns achieved TFLOP/s in
  * h_out[0] (DFMA) and h_out[1] (DMMA m8n8k4); synchronous.                             */

@@ -149,3 +149,38 @@ def test_constant_targets_take_the_reference_guard():
     mo, vo = ora.predict(Xq)
     np.testing.assert_allclose(mu, mo, rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(var, vo, rtol=1e-6, atol=1e-13)
+
+
+@pytest.mark.parametrize('method', ['rgpe', 'topo'])
+def test_native_host_prep_equals_numpy_host_prep_on_device(method, monkeypatch):
+    """The same facade trained through ``tlbo_host_prepare_jobs`` and through the numpy statement of the host
+    half: identical fitted hyper-parameters, loss tables, weights and (mutated) targets, bit for bit --
+    including a target vector whose CV folds trigger the all-equal guards."""
+    import tlbo_b200.facade.base_facade as BF
+    from tlbo_b200 import synthetic
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.rgpe import RGPE
+    from tlbo_b200.facade.topo_variant1 import OBTLV
+    b = synthetic.make_benchmark(n_tasks=3, T=400, kind='rf', seed=5)
+    sources, _ = synthetic.leave_one_out_sources(b['tables'], 0, 2, 5)
+    Xt, yt = b['tables'][0]
+    cls = dict(rgpe=RGPE, topo=OBTLV)[method]
+    out = []
+    for native in (True, False):
+        if not native:
+            monkeypatch.setattr(BF.BaseFacade, '_native_prep_ok', lambda self, X, y: False)
+        fac = cls(TableSpace(b['types']), sources, None, 11, surrogate_type='gp', num_src_hpo_trial=50)
+        res = []
+        for n, flat in ((23, False), (12, True)):
+            X = np.ascontiguousarray(Xt[:n]); y = np.array(yt[:n], dtype=np.float64)
+            if flat:
+                y[2:] = 0.25              # every training set that drops rows 0-1 is all-equal
+            np.random.seed(3)
+            fac.train(X, y)
+            res.append((fac._pack.theta[fac.K:fac.K + 6].cpu().numpy().copy(), np.array(fac.w, dtype=np.float64).copy(),
+                        y.copy(), None if method != 'rgpe' else fac.last_losses.copy()))
+        out.append(res)
+    for (t1, w1, y1, l1), (t2, w2, y2, l2) in zip(*out):
+        assert np.array_equal(t1, t2) and np.array_equal(w1, w2) and np.array_equal(y1, y2)
+        if l1 is not None:
+            assert np.array_equal(l1, l2)

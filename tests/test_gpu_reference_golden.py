@@ -125,6 +125,11 @@ class _ForcedFits(object):
                 m.kernel.theta = np.array(self.queue.pop(0), dtype=np.float64)
             return orig(models, Xs, Ys, do_optimize=False)
         monkeypatch.setattr(BF, 'fit_models_async', forced)
+        # the native host-prep path launches through fit_prepared_async (one shared set of start points per
+        # batch, so it cannot place each GP at its own theta): route the forced loops through the numpy
+        # statement of the same host half (the two are bit-identical: tests/test_host_logic.py; the loops
+        # with the device's own fits below run the native path)
+        monkeypatch.setattr(BF.BaseFacade, '_native_prep_ok', lambda self, X, y: False)
 
 
 METHODS = ['rgpe', 'trans_rgpe', 'topo', 'tst', 'pogpe']

@@ -87,3 +87,104 @@ def test_synthetic_benchmark_shape():
     assert (y > 0).all() and (y < 1).all()
     src, ids = synthetic.leave_one_out_sources(b['tables'], 1, 2, 5)
     assert len(src) == 2 and 1 not in ids
+
+
+# ---- native host half of the per-iteration training sets (tlbo_host_prepare_jobs) ---------------------
+def _py_jobs(X, y, ranges, outer, normalize, normalize_y):
+    from tlbo_b200.utils.normalization import zero_mean_unit_var_normalization, zero_one_normalization
+    """numpy statement: what rgpe/_prepare_single_surrogate/fit_models_async do"""
+    y = y.copy(); outs = []
+    n = len(y)
+    for (lo, hi), og in zip(ranges, outer):
+        rows = [i for i in range(n) if not (lo <= i < hi)]
+        if og:
+            if (y[rows] == y[rows[0]]).all():
+                y[rows[0]] += 1e-4
+        if hi == lo:
+            yj = y          # the caller's array itself
+            Xj = X
+        else:
+            yj = y[rows]; Xj = X[rows, :]
+        if normalize == 1:
+            if (yj == yj[0]).all(): yj[0] += 1e-4
+            yj, _, _ = zero_mean_unit_var_normalization(yj)
+        elif normalize == 2:
+            if (yj == yj[0]).all(): yj[0] += 1e-4
+            yj, _, _ = zero_one_normalization(yj)
+        Xi = np.array(Xj, dtype=np.float64); Xi[~np.isfinite(Xi)] = -1
+        yy = np.asarray(yj, dtype=np.float64)
+        if normalize_y:
+            m = float(np.mean(yy)); s = float(np.std(yy))
+            if s == 0: s = 1
+            yy = (yy - m) / s
+        else:
+            m, s = 0.0, 1.0
+        outs.append((Xi, yy.flatten(), m, s))
+    return y, outs
+
+
+def _c_jobs(X, y, ranges, outer, normalize, normalize_y):
+    from tlbo_b200._cabi import check, lib, ptr
+    y = y.copy(); n, d = X.shape; B = len(ranges); ncap = ((n + 7)//8)*8
+    lo = np.array([r[0] for r in ranges], dtype=np.int32); hi = np.array([r[1] for r in ranges], dtype=np.int32)
+    og = np.array(outer, dtype=np.int32)
+    Xo = np.full((B, ncap, d), 7.0); yo = np.full((B, ncap), 7.0); no = np.zeros(B, np.int32); ym = np.zeros(B); ys = np.zeros(B)
+    check(lib.tlbo_host_prepare_jobs(ptr(np.ascontiguousarray(X)), ptr(y), n, d, B, ptr(lo), ptr(hi), ptr(og), normalize, normalize_y, ncap, ptr(Xo), ptr(yo), ptr(no), ptr(ym), ptr(ys)))
+    return y, [(Xo[b, :no[b]], yo[b, :no[b]], ym[b], ys[b]) for b in range(B)], Xo, yo, no
+
+
+
+def test_native_job_preparation_is_bit_identical_to_numpy():
+    """``tlbo_host_prepare_jobs`` against the numpy statement of build_single_surrogate + GaussianProcess._train's
+    host half (base_facade.py:93-108, rgpe.py:55-70, gp.py:115-122): guards (including the in-place mutation
+    of the caller's y), both normalisations with numpy's pairwise-summation mean / std, NaN imputation,
+    zero padding -- bit for bit, over RGPE folds and sklearn KFold ranges, n up to 210."""
+    rng = np.random.RandomState(0)
+    for trial in range(700):
+        n = int(rng.randint(5, 210)); d = int(rng.randint(1, 12))
+        X = rng.rand(n, d)
+        if trial % 7 == 0:
+            X[rng.rand(n, d) < 0.1] = np.nan
+        kind = trial % 5
+        if kind == 0:
+            y = rng.randn(n) * 10 ** rng.uniform(-4, 4)
+        elif kind == 1:
+            y = np.full(n, rng.randn())                      # all equal
+        elif kind == 2:
+            y = np.round(rng.rand(n), 1)                     # many ties
+        elif kind == 3:
+            y = np.full(n, 0.5); y[:n // 5] = rng.rand(n // 5)   # every fold but the first leaves all-equal rows
+        else:
+            y = rng.rand(n) + 1e6
+        if trial % 2 == 0:      # rgpe.py folds: n // 5 rows each, the last takes the remainder
+            f = n // 5
+            ranges = [(0, 0)] + [(i * f, n if i == 4 else (i + 1) * f) for i in range(5)]
+            outer = [0, 1, 1, 1, 1, 1]
+        else:                   # sklearn KFold(5)
+            sizes = np.full(5, n // 5); sizes[:n % 5] += 1
+            cur = 0; ranges = [(0, 0)]
+            for s in sizes:
+                ranges.append((cur, cur + int(s))); cur += int(s)
+            outer = [0] * 6
+        normalize = [1, 1, 2, 0][trial % 4]
+        y1, o1 = _py_jobs(X, y, ranges, outer, normalize, 1)
+        y2, o2, Xo, yo, no = _c_jobs(X, y, ranges, outer, normalize, 1)
+        assert np.array_equal(y1, y2), trial
+        for (a, b, m, s), (a2, b2, m2, s2) in zip(o1, o2):
+            assert np.array_equal(a, a2) and np.array_equal(b, b2, equal_nan=True), trial
+            assert (m == m2 or (m != m and m2 != m2)) and (s == s2 or (s != s and s2 != s2)), trial
+        for b in range(len(ranges)):
+            assert (Xo[b, no[b]:] == 0).all() and (yo[b, no[b]:] == 0).all()
+
+
+def test_prepare_jobs_wrapper_layout():
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(3)
+    X, y = rng.rand(23, 4), rng.rand(23)
+    prep = ops.prepare_jobs(X, y, [(0, 0), (0, 4), (20, 23)], [0, 1, 1], 'standardize')
+    assert (prep.B, prep.ncap, prep.d) == (3, 24, 4) and list(prep.n) == [23, 19, 20]
+    nx, ny = 3 * 24 * 4, 3 * 24
+    assert list(prep.buf[nx + ny:].view(np.int32)[:3]) == [23, 19, 20]
+    yj = prep.buf[nx:nx + ny].reshape(3, 24)
+    assert abs(yj[0, :23].mean()) < 1e-12 and abs(yj[0, :23].std() - 1) < 1e-12
+    assert np.array_equal(prep.buf[:nx].reshape(3, 24, 4)[1, :19], X[4:])
