@@ -125,3 +125,71 @@ class OBTLV(BaseFacade):
 
     def get_weights(self):
         return self.w
+
+
+class TOPO_V3(OBTLV):
+    """``--methods topo_v3`` (reference tlbo/facade/topo_variant3.py:9-109, tools/offline_benchmark.py:312-313):
+    ONE simplex-constrained solve over the K source columns plus the cross-validated target column (the
+    sources alone while there are fewer than 5 observations), the target weight floored at 0.3, no smoothing
+    (rho = 1) and no ``target_weight`` log.  Same kernels as ``OBTLV``."""
+
+    def __init__(self, config_space, source_hpo_data, target_hp_configs, seed, surrogate_type='gp',
+                 num_src_hpo_trial=50, fusion_method='idp_lc', **kw):
+        super().__init__(config_space, source_hpo_data, target_hp_configs, seed, surrogate_type=surrogate_type,
+                         num_src_hpo_trial=num_src_hpo_trial, fusion_method=fusion_method, **kw)
+        self.method_id = 'topo_v3'
+
+    def train(self, X, y):
+        from tlbo_b200 import ops
+        K = self.K
+        instance_num = X.shape[0]
+        do_cv = instance_num >= self.min_num_y
+        folds = _kfold_val_slices(instance_num, 5) if do_cv else []
+        if self._native_prep_ok(X, y):
+            fit_models, launch_fit = self._prepare_cv_jobs(X, y, [(0, 0)] + list(folds), [0] * (1 + len(folds)),
+                                                           _scale_method)
+        else:
+            jobs = [self._prepare_single_surrogate(X, y, _scale_method, K)]
+            for i, (lo, hi) in enumerate(folds):
+                train_idx = np.concatenate([np.arange(0, lo), np.arange(hi, instance_num)])
+                jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
+            for j, job in enumerate(jobs):
+                job[0].bind(self._pack, K + j)
+            fit_models = [j[0] for j in jobs]
+            launch_fit = lambda: self._fit_async(fit_models, [j[1] for j in jobs], [j[2] for j in jobs])
+        X_dev = self._to_device(X)                       # before the fit is enqueued
+        finish_fit = launch_fit()
+        self.target_surrogate = fit_models[0]
+        self.last_fit_models = fit_models
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        if self._overlap_hook is not None:
+            self._overlap_hook()
+        mu_dev, _ = self._predict_slots(0, K + 1 + len(folds), X_dev)     # sources, target, CV folds: one launch
+        finish_fit()
+        mu = ops.d2h(mu_dev)
+        pred_y = np.ascontiguousarray(mu[:K].T)
+        if not do_cv:
+            x, status = scipy_solve(pred_y, y, 3)         # learn_source_weights
+            if status:
+                x[x < 1e-3] = 0.
+                self.w[:K] = x
+        else:
+            _t_pred_y = np.empty(instance_num)
+            for i, (lo, hi) in enumerate(folds):
+                _t_pred_y[lo:hi] = mu[K + 1 + i, lo:hi]
+            x, status = scipy_solve(np.c_[pred_y, _t_pred_y.reshape((-1, 1))], y, 3)      # learn_weights
+            if status:
+                x[x < 1e-3] = 0.
+            else:
+                x = self.w.copy()
+            w_source, w_target = x[:-1], x[-1]
+            if status:
+                w_target = np.max([w_target, 0.3])
+                if instance_num >= 2 * self.min_num_y:
+                    w_target = np.max([w_target, self.w[-1]])
+                    w_source *= (1 - w_target)
+            w_new = np.asarray(list(w_source) + [w_target])
+            rho = 1.0
+            self.w = rho * w_new + (1 - rho) * self.w
+        self.hist_ws.append(self.w.copy())
+        self.iteration_id += 1

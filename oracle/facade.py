@@ -473,6 +473,47 @@ class OracleOBTLV(OracleFacade):
         return self.combine_predictions(X, self.fusion_method)
 
 
+class OracleTOPOV3(OracleOBTLV):
+    """tlbo/facade/topo_variant3.py (``--methods topo_v3``, tools/offline_benchmark.py:312-313): ONE
+    simplex-constrained solve over the K source columns plus the cross-validated target column, target
+    weight floored at 0.3, no smoothing (rho = 1), no ``target_weight`` log."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, fusion_method='idp_lc', literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, fusion_method, False, literal_loops)
+        self.method_id = 'topo_v3'
+
+    def train(self, X, y):
+        """topo_variant3.py:53-89."""
+        instance_num = X.shape[0]
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='standardize')
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        pred_y = self.batch_predict(X)
+        if instance_num < self.min_num_y:
+            x, status = self._solve(pred_y, y)            # learn_source_weights :91-95
+            if status:
+                x[x < 1e-3] = 0.
+                self.w[:self.K] = x
+        else:
+            _pred_y, _ = self.predict_target_surrogate_cv(X, y)
+            _pred_y = np.c_[pred_y, _pred_y.reshape((-1, 1))]
+            x, status = self._solve(_pred_y, y)           # learn_weights :97-103
+            if status:
+                x[x < 1e-3] = 0.
+            else:
+                x = self.w.copy()
+            w_source, w_target = x[:-1], x[-1]
+            if status:
+                w_target = np.max([w_target, 0.3])
+                if instance_num >= 2 * self.min_num_y:
+                    w_target = np.max([w_target, self.w[-1]])
+                    w_source *= (1 - w_target)
+            w_new = np.asarray(list(w_source) + [w_target])
+            rho = 1.0
+            self.w = rho * w_new + (1 - rho) * self.w
+        self.hist_ws.append(self.w.copy())
+        self.iteration_id += 1
+
+
 class OracleTST(OracleFacade):
     """tlbo/facade/tst.py (``use_metafeatures=False``)."""
 

@@ -27,7 +27,7 @@ restored.  Everything recorded below is computed by reference code:
            fitted theta, np.random states.  ConfigSpace's sampling / neighbourhood streams come from the
            stand-in (= the oracle's restatement): those two streams NOT pinned
   loop_*   framework/smbo_offline.SMBO_OFFLINE driving facade/rgpe.RGPE, facade/topo.TransBO_RGPE,
-           facade/topo_variant1.OBTLV, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
+           facade/topo_variant1.OBTLV, facade/topo_variant3.TOPO_V3, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
            dilution flags, the bootstrap ranking-loss tables (captured from the np.argmin calls of
            rgpe.py:108 / topo.py), every fitted theta in fit order, and the state of the global
            np.random stream after every iteration
@@ -60,6 +60,7 @@ from tlbo.facade.pogpe import POGPE                                         # no
 from tlbo.facade.rgpe import RGPE                                           # noqa: E402
 from tlbo.facade.topo import TransBO_RGPE                                   # noqa: E402
 from tlbo.facade.topo_variant1 import OBTLV                                 # noqa: E402
+from tlbo.facade.topo_variant3 import TOPO_V3                               # noqa: E402
 from tlbo.facade.tst import TST                                             # noqa: E402
 from tlbo.framework.online.smbo_online import SMBO_ONLINE                   # noqa: E402
 from tlbo.framework.smbo_offline import SMBO_OFFLINE                        # noqa: E402
@@ -226,7 +227,7 @@ def loop_level(out):
         out['loop_task%d_X' % t], out['loop_task%d_y' % t] = X, y
     out['loop_types'], out['loop_seed'], out['loop_K'] = types, seed, K
 
-    for method, cls, iters in (('rgpe', RGPE, 12), ('trans_rgpe', TransBO_RGPE, 12), ('topo', OBTLV, 10),
+    for method, cls, iters in (('rgpe', RGPE, 12), ('trans_rgpe', TransBO_RGPE, 12), ('topo', OBTLV, 10), ('topo_v3', TOPO_V3, 10),
                                ('tst', TST, 8), ('pogpe', POGPE, 8)):
         cs = rf_space()
         as_dict = lambda X, y: collections.OrderedDict((Configuration(cs, vector=x), float(v)) for x, v in zip(X, y))

@@ -120,6 +120,7 @@ def _state_vec():
 LOOPS = {'rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, literal_loops=True),
          'trans_rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, smooth=0.7),
          'topo': lambda t, s, seed: ofacade.OracleOBTLV(t, s, seed),
+         'topo_v3': lambda t, s, seed: ofacade.OracleTOPOV3(t, s, seed),
          'tst': lambda t, s, seed: ofacade.OracleTST(t, s, seed),
          'pogpe': lambda t, s, seed: ofacade.OraclePOGPE(t, s, seed)}
 
