@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--method', default='rgpe', choices=['rgpe', 'topo', 'topo_v3', 'trans_rgpe', 'tst', 'pogpe'])
+    ap.add_argument('--method', default='rgpe', choices=['rgpe', 'topo', 'topo_v3', 'obtl', 'trans_rgpe', 'tst', 'pogpe'])
     ap.add_argument('--surrogate', default='gp', choices=['gp', 'gp_mcmc'],
                     help="'gp_mcmc': MCMC-marginalised GP hyper-parameters (BASELINE configs[4])")
     ap.add_argument('--mcmc-steps', type=int, nargs=2, default=[250, 250], metavar=('BURNIN', 'CHAIN'),
@@ -179,7 +179,7 @@ class ClockSampler(object):
 def _oracle_facade(method, types, sources, seed, literal, surrogate='gp', mcmc_steps=None):
     import oracle.facade as of
     base, kw = {'rgpe': (of.OracleRGPE, {}), 'trans_rgpe': (of.OracleRGPE, {'smooth': 0.7}),
-                'topo': (of.OracleOBTLV, {}), 'topo_v3': (of.OracleTOPOV3, {}), 'tst': (of.OracleTST, {}), 'pogpe': (of.OraclePOGPE, {})}[method]
+                'topo': (of.OracleOBTLV, {}), 'topo_v3': (of.OracleTOPOV3, {}), 'obtl': (of.OracleOBTL, {}), 'tst': (of.OracleTST, {}), 'pogpe': (of.OraclePOGPE, {})}[method]
     if surrogate == 'gp_mcmc':
         base = type('Mcmc' + base.__name__, (base,), dict(surrogate_type='gp_mcmc', mcmc_steps=tuple(mcmc_steps)))
     return base(types, sources, seed, literal_loops=literal, **kw)
@@ -325,7 +325,7 @@ def workload_config(args, where):
         'method': args.method, 'sources': args.sources, 'pool': args.pool, 'd': 9,
         'surrogate': args.surrogate,
         'restarts_per_fit': 11 if args.surrogate == 'gp' else None,
-        'fits_per_iter': 6 if args.method in ('rgpe', 'trans_rgpe', 'topo', 'topo_v3') else 1,
+        'fits_per_iter': 6 if args.method in ('rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'obtl') else 1,
         'mcmc': (None if args.surrogate == 'gp' else
                  {'walkers': 34, 'burnin_steps': args.mcmc_steps[0], 'chain_steps': args.mcmc_steps[1],
                   'log_prob_evals_per_fit': 34 * (sum(args.mcmc_steps) + 2)}),
@@ -343,10 +343,10 @@ def make_product(args, wl, shard=None):
     from tlbo_b200.config_space import TableSpace
     from tlbo_b200.facade.pogpe import POGPE
     from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
-    from tlbo_b200.facade.topo_variant1 import OBTLV, TOPO_V3
+    from tlbo_b200.facade.topo_variant1 import OBTL, OBTLV, TOPO_V3
     from tlbo_b200.facade.tst import TST
     from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
-    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, tst=TST, pogpe=POGPE)[args.method]
+    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, obtl=OBTL, tst=TST, pogpe=POGPE)[args.method]
     cs = TableSpace(wl['types'])
     kw = {}
     if args.surrogate == 'gp_mcmc':

@@ -187,3 +187,59 @@ extern "C" int tlbo_pairwise_logistic_loss_grad_hw(const double* d_A, const doub
   if (!h_w) { tlbo_set_error("NULL h_w"); return TLBO_E_BADARG; }
   return pair_logistic_launch(d_A, d_y, nullptr, h_w, n, m, d_out, stream);
 }
+
+// ---------------------------------------------------------------------------------------
+// OBTL's sampled ranking loss (reference tlbo/facade/obtl.py:95-147): for every bootstrap sample s and
+// surrogate m, y_pred = normal(mu_m, var_m) (scale = the predictive VARIANCE, as written there) and
+//   loss = sum_{i<j} log(1 + exp(-10 z_ij)) / n^2,   z_ij = (y_i < y_j) ? y_pred_j - y_pred_i : y_pred_i - y_pred_j
+// -- the pure-Python double loop of calculate_ranking_loss, 50 x (K + 1) x n^2 / 2 penalty evaluations per BO
+// iteration.  One CTA per (sample, surrogate); the standard-normal draws come from the host's GLOBAL
+// legacy np.random stream in the reference's order and the affine map runs here with a rounded product
+// and a rounded sum (numpy's legacy normal).  A float loss: the sum order differs from the reference's
+// sequential loop (relative 1e-15); what the facade consumes is the arg-min over surrogates per sample.
+__global__ void __launch_bounds__(RL_THREADS) pair_penalty_kernel(const double* __restrict__ y,
+                                                                  const double* __restrict__ z, int n, int Mr,
+                                                                  const double* __restrict__ loc,
+                                                                  const double* __restrict__ scale,
+                                                                  double* __restrict__ loss) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* sy = reinterpret_cast<double*>(smem);
+  double* ss = sy + n;
+  __shared__ double red[32];
+  const int item = blockIdx.x;           // s * Mr + m
+  const int m = item % Mr;
+  const double* zs = z + (size_t)item * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sy[i] = y[i];
+    ss[i] = __dadd_rn(loc[(size_t)m * n + i], __dmul_rn(scale[(size_t)m * n + i], zs[i]));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double acc = 0.0;
+  for (int i = wid; i < n; i += nw) {
+    const double yi = sy[i], si = ss[i];
+    for (int j = i + 1 + lane; j < n; j += 32) {
+      double zz = (yi < sy[j]) ? (ss[j] - si) : (si - ss[j]);
+      zz *= 10.0;
+      acc += log(1.0 + exp(-zz));
+    }
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[item] = tot / ((double)n * (double)n);
+}
+
+extern "C" int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const double* d_loc,
+                                             const double* d_scale, int n, int S, int Mr, double* d_loss,
+                                             void* stream) {
+  if (!d_y || !d_z || !d_loc || !d_scale || !d_loss || n <= 0 || S <= 0 || Mr <= 0) {
+    tlbo_set_error("tlbo_pair_penalty_loss_normal: bad arguments");
+    return TLBO_E_BADARG;
+  }
+  const size_t smem = 2 * (size_t)n * sizeof(double);
+  if (smem > 200 * 1024) { tlbo_set_error("n too large for pair_penalty_loss"); return TLBO_E_TOOLARGE; }
+  if (smem > 48 * 1024)
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(pair_penalty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_penalty_kernel<<<S * Mr, RL_THREADS, smem, (cudaStream_t)stream>>>(d_y, d_z, n, Mr, d_loc, d_scale, d_loss);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

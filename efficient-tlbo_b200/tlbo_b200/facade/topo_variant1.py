@@ -193,3 +193,90 @@ class TOPO_V3(OBTLV):
             self.w = rho * w_new + (1 - rho) * self.w
         self.hist_ws.append(self.w.copy())
         self.iteration_id += 1
+
+
+class OBTL(OBTLV):
+    """``--methods obtl`` (reference tlbo/facade/obtl.py:9-150, tools/offline_benchmark.py:292-293): source weights
+    by the simplex-constrained pairwise-logistic solve (as ``OBTLV`` phase 1), target weight by SAMPLING -- 50
+    bootstrap draws ``normal(mu, var)`` of every source surrogate and of the cross-validated target surrogate,
+    each scored by the soft ranking loss ``sum_{i<j} log(1 + exp(-10 z_ij)) / n^2``; the target weight is the
+    share of samples in which the target wins the arg-min.  The reference's pure-Python pair loop
+    (``calculate_ranking_loss``) is the ``pair_penalty_kernel``; the draws come from the GLOBAL legacy
+    ``np.random`` stream in the reference's order (sample-major, surrogate 0..K, n normals each)."""
+    ensemble_size = 50
+
+    def __init__(self, config_space, source_hpo_data, target_hp_configs, seed, surrogate_type='gp',
+                 num_src_hpo_trial=50, fusion_method='idp_lc', **kw):
+        super().__init__(config_space, source_hpo_data, target_hp_configs, seed, surrogate_type=surrogate_type,
+                         num_src_hpo_trial=num_src_hpo_trial, fusion_method=fusion_method, **kw)
+        self.method_id = 'obtl'
+        self.last_sample_losses = None
+
+    def train(self, X, y):
+        import torch
+        from tlbo_b200 import ops
+        K = self.K
+        instance_num = X.shape[0]
+        do_cv = instance_num >= self.min_num_y
+        folds = _kfold_val_slices(instance_num, 5) if do_cv else []
+        if self._native_prep_ok(X, y):
+            fit_models, launch_fit = self._prepare_cv_jobs(X, y, [(0, 0)] + list(folds), [0] * (1 + len(folds)),
+                                                           _scale_method)
+        else:
+            jobs = [self._prepare_single_surrogate(X, y, _scale_method, K)]
+            for i, (lo, hi) in enumerate(folds):
+                train_idx = np.concatenate([np.arange(0, lo), np.arange(hi, instance_num)])
+                jobs.append(self._prepare_single_surrogate(X[train_idx, :], y[train_idx], _scale_method, K + 1 + i))
+            for j, job in enumerate(jobs):
+                job[0].bind(self._pack, K + j)
+            fit_models = [j[0] for j in jobs]
+            launch_fit = lambda: self._fit_async(fit_models, [j[1] for j in jobs], [j[2] for j in jobs])
+        X_dev = self._to_device(X)                       # before the fit is enqueued
+        y_dev = ops.h2d(np.ascontiguousarray(y, dtype=np.float64))
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        finish_fit = launch_fit()
+        self.target_surrogate = fit_models[0]
+        self.last_fit_models = fit_models
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        if self._overlap_hook is not None:
+            self._overlap_hook()
+        z_dev = None
+        if do_cv:
+            # obtl.py:111-117: ensemble_size x (K + 1) x n normals from the global stream (drawn while the
+            # fit runs: standard normals do not depend on the posteriors)
+            z_dev = self._stage.upload('z_obtl', np.random.standard_normal((self.ensemble_size, K + 1, instance_num)))
+        with torch.cuda.stream(self._side):              # source side: overlaps the fit
+            mu_src_dev, var_src_dev = self._predict_slots(0, K, X_dev)
+            pred_y = np.ascontiguousarray(ops.d2h(mu_src_dev).T)
+            self.learn_source_weights(pred_y, y)
+        main.wait_stream(self._side)
+        if do_cv:
+            mu_cv_dev, var_cv_dev = self._predict_slots(K + 1, len(folds), X_dev)
+        finish_fit()
+        w_source = self.w[:K]
+        w_target = 0.
+        if do_cv:
+            # cross-validated target posterior: fold i's model at its own validation rows (obtl.py:73-93)
+            loc = torch.empty(K + 1, instance_num, dtype=torch.float64, device=X_dev.device)
+            scale = torch.empty_like(loc)
+            loc[:K] = mu_src_dev
+            scale[:K] = var_src_dev
+            for i, (lo, hi) in enumerate(folds):
+                loc[K, lo:hi] = mu_cv_dev[i, lo:hi]
+                scale[K, lo:hi] = var_cv_dev[i, lo:hi]
+            losses = ops.pair_penalty_loss_normal(y_dev, z_dev, loc, scale)
+            self.last_sample_losses = losses
+            _w = np.bincount(np.argmin(losses, axis=1), minlength=K + 1).astype(np.float64)
+            _w = _w / np.sum(_w)
+            w_target = _w[-1]
+            if instance_num >= 2 * self.min_num_y:
+                w_target = np.max([w_target, self.w[-1]])
+            w_source *= (1 - w_target)
+        w_new = np.asarray(list(w_source) + [w_target])
+        rho = 0.6
+        self.w = rho * w_new + (1 - rho) * self.w
+        self.hist_ws.append(self.w.copy())
+        self.iteration_id += 1

@@ -539,6 +539,23 @@ def rank_loss_counts_normal(y, z, loc, scale, src, row_lo, row_hi, sync=True):
     return d2h(counts)
 
 
+def pair_penalty_loss_normal(y, z, loc, scale, sync=True):
+    """``tlbo_pair_penalty_loss_normal`` (OBTL's sampled ranking loss): y [n], z [S, Mr, n] device or host,
+    loc / scale [Mr, n] device -> loss float64[S, Mr]."""
+    dev = _dev()
+
+    def up(a):
+        return a if torch.is_tensor(a) and a.is_cuda else h2d(np.ascontiguousarray(a, dtype=np.float64))
+    y, z, loc, scale = up(y), up(z), up(loc), up(scale)
+    S, Mr, n = (int(v) for v in z.shape)
+    assert loc.shape == (Mr, n) and scale.shape == (Mr, n) and y.numel() == n
+    loss = torch.empty(S, Mr, dtype=F64, device=dev)
+    with _call('pair_penalty_loss', 1):
+        check(lib.tlbo_pair_penalty_loss_normal(ptr(y), ptr(z.contiguous()), ptr(loc.contiguous()),
+                                                ptr(scale.contiguous()), n, S, Mr, ptr(loss), _stream()))
+    return d2h(loss) if sync else loss
+
+
 class PairLogistic(object):
     """Pairwise logistic ranking loss + gradient with A and y resident on the device across
     the SLSQP callbacks of one ``scipy_solve``.  Per callback: ONE launch with the weights as

@@ -258,6 +258,15 @@ int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t*
                                     const uint8_t* h_const_mask, uint32_t seed, int num_neighbors, double stdev,
                                     double* h_out, int max_rows, int32_t* h_n_rows);
 
+/* OBTL's sampled ranking loss (reference tlbo/facade/obtl.py:95-147, calculate_weight_by_sampling +
+ * calculate_ranking_loss / penalty_func): loss[s, m] = sum_{i<j} log(1 + exp(-10 z_ij)) / n^2 with
+ * y_pred = loc[m] + scale[m] * z[s, m] (scale = the predictive variance, as the reference writes it) and
+ * z_ij = (y_i < y_j) ? y_pred_j - y_pred_i : y_pred_i - y_pred_j.
+ *   d_y [n]; d_z [S, Mr, n] standard-normal draws (host legacy np.random, reference draw order);
+ *   d_loc, d_scale [Mr, n]; d_loss [S, Mr]                                                               */
+int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const double* d_loc, const double* d_scale,
+                                  int n, int S, int Mr, double* d_loss, void* stream);
+
 /* Host-side helper (no device work): the host half of build_single_surrogate + GaussianProcess._train for
  * the 1 + 5 training sets a facade builds per BO iteration from the same (X, y) -- all rows, and all rows
  * except one contiguous validation range (reference tlbo/facade/base_facade.py:93-108, rgpe.py:55-70,

@@ -514,6 +514,78 @@ class OracleTOPOV3(OracleOBTLV):
         self.iteration_id += 1
 
 
+def obtl_ranking_loss(y_pred, y, literal=False):
+    """``OBTL.calculate_ranking_loss`` / ``penalty_func`` (tlbo/facade/obtl.py:124-139):
+    sum_{i<j} log(1 + exp(-10 z)) / n^2 with z = y_pred_j - y_pred_i if y_i < y_j else y_pred_i - y_pred_j."""
+    n = y_pred.shape[0]
+    if literal:
+        ranking_loss = 0.
+        for i in range(n):
+            for j in range(i + 1, n):
+                z = (y_pred[j] - y_pred[i]) if y[i] < y[j] else (y_pred[i] - y_pred[j])
+                z *= 10.
+                ranking_loss += np.log(1 + np.exp(-z))
+        return ranking_loss / (n * n)
+    iu, ju = np.triu_indices(n, 1)
+    z = np.where(y[iu] < y[ju], y_pred[ju] - y_pred[iu], y_pred[iu] - y_pred[ju]) * 10.
+    with np.errstate(over='ignore'):
+        return float(np.sum(np.log(1 + np.exp(-z)))) / (n * n)
+
+
+class OracleOBTL(OracleOBTLV):
+    """tlbo/facade/obtl.py (``--methods obtl``): source weights by the SLSQP solve, target weight by sampling
+    (``calculate_weight_by_sampling`` :95-122), rho = 0.6, no ``target_weight`` log."""
+    ensemble_size = 50
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, fusion_method='idp_lc', literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, fusion_method, False, literal_loops)
+        self.method_id = 'obtl'
+        self.last_sample_losses = None
+
+    def calculate_weight_by_sampling(self, X, y):
+        preds = []
+        for idx in range(self.K):
+            _mu, _var = self.source_surrogates[idx].predict(X)
+            preds.append((_mu.flatten(), _var.flatten()))
+        preds.append(self.predict_target_surrogate_cv(X, y))
+        _K = len(preds)
+        losses = np.zeros((self.ensemble_size, _K))
+        for s in range(self.ensemble_size):
+            for i in range(_K):
+                _mu, _var = preds[i]
+                y_pred = np.random.normal(_mu, _var)
+                losses[s, i] = obtl_ranking_loss(y_pred, y, self.literal_loops)
+        self.last_sample_losses = losses
+        _w = np.zeros(_K)
+        for idx in np.argmin(losses, axis=1):
+            _w[idx] += 1
+        _w = _w / np.sum(_w)
+        return _w[-1]
+
+    def train(self, X, y):
+        """obtl.py:37-63."""
+        instance_num = X.shape[0]
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='standardize')
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        pred_y = self.batch_predict(X)
+        x, status = self._solve(pred_y, y)            # learn_source_weights :65-69
+        if status:
+            x[x < 1e-3] = 0.
+            self.w[:self.K] = x
+        w_source = self.w[:self.K]
+        w_target = 0.
+        if instance_num >= self.min_num_y:
+            w_target = self.calculate_weight_by_sampling(X, y)
+            if instance_num >= 2 * self.min_num_y:
+                w_target = np.max([w_target, self.w[-1]])
+            w_source *= (1 - w_target)
+        w_new = np.asarray(list(w_source) + [w_target])
+        rho = 0.6
+        self.w = rho * w_new + (1 - rho) * self.w
+        self.hist_ws.append(self.w.copy())
+        self.iteration_id += 1
+
+
 class OracleTST(OracleFacade):
     """tlbo/facade/tst.py (``use_metafeatures=False``)."""
 

@@ -27,7 +27,7 @@ restored.  Everything recorded below is computed by reference code:
            fitted theta, np.random states.  ConfigSpace's sampling / neighbourhood streams come from the
            stand-in (= the oracle's restatement): those two streams NOT pinned
   loop_*   framework/smbo_offline.SMBO_OFFLINE driving facade/rgpe.RGPE, facade/topo.TransBO_RGPE,
-           facade/topo_variant1.OBTLV, facade/topo_variant3.TOPO_V3, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
+           facade/topo_variant1.OBTLV, facade/topo_variant3.TOPO_V3, facade/obtl.OBTL, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
            dilution flags, the bootstrap ranking-loss tables (captured from the np.argmin calls of
            rgpe.py:108 / topo.py), every fitted theta in fit order, and the state of the global
            np.random stream after every iteration
@@ -56,6 +56,7 @@ sys.path.insert(0, REFERENCE)
 from tlbo.acquisition_function.acquisition import EI                       # noqa: E402
 from tlbo.config_space import (CategoricalHyperparameter, Configuration, ConfigurationSpace, Constant,  # noqa: E402
                                UniformFloatHyperparameter, UniformIntegerHyperparameter)
+from tlbo.facade.obtl import OBTL                                           # noqa: E402
 from tlbo.facade.pogpe import POGPE                                         # noqa: E402
 from tlbo.facade.rgpe import RGPE                                           # noqa: E402
 from tlbo.facade.topo import TransBO_RGPE                                   # noqa: E402
@@ -227,7 +228,7 @@ def loop_level(out):
         out['loop_task%d_X' % t], out['loop_task%d_y' % t] = X, y
     out['loop_types'], out['loop_seed'], out['loop_K'] = types, seed, K
 
-    for method, cls, iters in (('rgpe', RGPE, 12), ('trans_rgpe', TransBO_RGPE, 12), ('topo', OBTLV, 10), ('topo_v3', TOPO_V3, 10),
+    for method, cls, iters in (('rgpe', RGPE, 12), ('trans_rgpe', TransBO_RGPE, 12), ('topo', OBTLV, 10), ('topo_v3', TOPO_V3, 10), ('obtl', OBTL, 10),
                                ('tst', TST, 8), ('pogpe', POGPE, 8)):
         cs = rf_space()
         as_dict = lambda X, y: collections.OrderedDict((Configuration(cs, vector=x), float(v)) for x, v in zip(X, y))
@@ -244,7 +245,7 @@ def loop_level(out):
 
         def spy_argmin(a, *args, **kw):
             if isinstance(a, list) and len(a) == K + 1 and not args and not kw:
-                losses.append([int(v) for v in a])
+                losses.append([float(v) for v in a])
             return orig_argmin(a, *args, **kw)
         ref_gp.GaussianProcess._train = spy_train
         np.argmin = spy_argmin
@@ -281,7 +282,7 @@ def loop_level(out):
         out[p + 'target_weight'] = np.array(fac.target_weight, dtype=np.float64)
         if hasattr(fac, 'hist_ws'):
             out[p + 'hist_ws'] = np.array([np.asarray(w, dtype=np.float64) for w in fac.hist_ws])
-        out[p + 'losses'] = np.array(losses, dtype=np.int64).reshape(-1, K + 1)
+        out[p + 'losses'] = np.array(losses, dtype=np.float64 if method == 'obtl' else np.int64).reshape(-1, K + 1)
         out[p + 'eta_list'] = np.array(fac.eta_list, dtype=np.float64)
         print(method, 'rows', rows, 'fits', n_source_fits, fits_per_iter, 'loss rows', len(losses))
 

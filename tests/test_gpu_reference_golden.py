@@ -98,9 +98,9 @@ def _product(method, types, sources, seed):
     from tlbo_b200.config_space import TableSpace
     from tlbo_b200.facade.pogpe import POGPE
     from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
-    from tlbo_b200.facade.topo_variant1 import OBTLV, TOPO_V3
+    from tlbo_b200.facade.topo_variant1 import OBTL, OBTLV, TOPO_V3
     from tlbo_b200.facade.tst import TST
-    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, tst=TST, pogpe=POGPE)[method]
+    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, obtl=OBTL, tst=TST, pogpe=POGPE)[method]
     cs = TableSpace(types)
     return cs, cls(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
 
@@ -132,7 +132,7 @@ class _ForcedFits(object):
         monkeypatch.setattr(BF.BaseFacade, '_native_prep_ok', lambda self, X, y: False)
 
 
-METHODS = ['rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'tst', 'pogpe']
+METHODS = ['rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'obtl', 'tst', 'pogpe']
 
 
 @pytest.mark.parametrize('method', METHODS)
@@ -168,6 +168,9 @@ def test_cuda_loop_matches_reference_given_theta(method, monkeypatch):
             if nfit == 6:
                 np.testing.assert_array_equal(fac.last_losses, R[p + 'losses'][loss_rows:loss_rows + 30])
             loss_rows += 30
+        if method == 'obtl' and nfit == 6:
+            np.testing.assert_allclose(fac.last_sample_losses, R[p + 'losses'][loss_rows:loss_rows + 50], rtol=1e-6)
+            loss_rows += 50
     np.testing.assert_array_equal(np.asarray(smbo.perfs), R[p + 'perfs'])
     np.testing.assert_allclose(fac.target_weight, R[p + 'target_weight'], rtol=1e-6, atol=1e-7)
 

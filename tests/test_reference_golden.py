@@ -121,6 +121,7 @@ LOOPS = {'rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, literal_loops
          'trans_rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, smooth=0.7),
          'topo': lambda t, s, seed: ofacade.OracleOBTLV(t, s, seed),
          'topo_v3': lambda t, s, seed: ofacade.OracleTOPOV3(t, s, seed),
+         'obtl': lambda t, s, seed: ofacade.OracleOBTL(t, s, seed, literal_loops=True),
          'tst': lambda t, s, seed: ofacade.OracleTST(t, s, seed),
          'pogpe': lambda t, s, seed: ofacade.OraclePOGPE(t, s, seed)}
 
@@ -160,6 +161,10 @@ def test_offline_loop_matches_reference(method, monkeypatch):
             if nfit == 6:
                 np.testing.assert_array_equal(fac.last_losses, ref_losses[loss_rows:loss_rows + 30])
             loss_rows += 30
+        if method == 'obtl' and nfit == 6:
+            # obtl.py:111-117: the 50 x (K + 1) sampled soft ranking losses (captured from the reference's np.argmin)
+            np.testing.assert_allclose(fac.last_sample_losses, ref_losses[loss_rows:loss_rows + 50], rtol=1e-9)
+            loss_rows += 50
     np.testing.assert_allclose(smbo.perfs, R[p + 'perfs'], rtol=0, atol=0)
     np.testing.assert_allclose(fac.target_weight, R[p + 'target_weight'], rtol=1e-6, atol=1e-8)
     if p + 'hist_ws' in R.files and len(R[p + 'hist_ws']):
