@@ -243,3 +243,95 @@ extern "C" int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Tie-break keys on the device: numpy's LEGACY `RandomState.random_sample` (MT19937, two 32-bit outputs
+// per double: (a >> 5) * 2^26 + (b >> 6)) / 2^53), bit for bit, with the generator state resident in HBM.
+//
+// `_sort_configs_by_acq_value` (reference tlbo/optimizer/ei_optimization.py:106-132) draws `rng.rand(N)`
+// over the WHOLE candidate table on every maximisation; at N = 1e6 that is ~5 ms of sequential host work and
+// an 8 MB upload per BO iteration -- more than everything else in the iteration.  MT19937 regenerates its
+// 624-word state in blocks; inside a block, word i depends on old words i, i + 1 and on word i + 397 (old for
+// i < 227, else the NEW word i - 227), so a block splits into three data-parallel phases (227 + 227 + 169
+// words) plus the last word.  One CTA walks the blocks (about 0.3 us each), tempers and converts 312 doubles
+// per block with coalesced stores; it runs on a side stream under the fit kernel, which leaves 82 SMs idle.
+// d_state: uint32[625] = key[624], pos -- numpy's `get_state()[1]`, `[2]`.
+#define MT_N 624
+#define MT_M 397
+#define MT_THREADS 256
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+  const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return far ^ (y >> 1) ^ ((uint32_t)(-(int32_t)(y & 1u)) & 0x9908b0dfu);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+__device__ __forceinline__ double mt_double(uint32_t w1, uint32_t w2) {
+  const double a = (double)(w1 >> 5), b = (double)(w2 >> 6);
+  return (a * 67108864.0 + b) / 9007199254740992.0;      // every step exact in binary64
+}
+
+__global__ void __launch_bounds__(MT_THREADS) mt19937_random_sample_kernel(uint32_t* __restrict__ state, long long N,
+                                                                           double* __restrict__ out) {
+  // two copies of the state: a block is twisted from `cur` into `nxt` (no read-after-write hazards inside a
+  // phase), so a block costs three barriers; the doubles are tempered and stored straight from `nxt`
+  __shared__ uint32_t keybuf[2][MT_N];
+  const int tid = threadIdx.x;
+  int cb = 0;
+  for (int i = tid; i < MT_N; i += MT_THREADS) keybuf[0][i] = state[i];
+  int pos = (int)state[MT_N];
+  __syncthreads();
+  long long produced = 0;
+  bool carry_valid = false;
+  uint32_t carry = 0;
+  while (produced < N) {                      // every control variable is uniform over the CTA
+    if (pos >= MT_N) {
+      const uint32_t* cur = keybuf[cb];
+      uint32_t* nxt = keybuf[cb ^ 1];
+      if (tid < 227) nxt[tid] = mt_twist(cur[tid], cur[tid + 1], cur[tid + MT_M]);
+      __syncthreads();
+      if (tid < 227) nxt[227 + tid] = mt_twist(cur[227 + tid], cur[228 + tid], nxt[tid]);
+      __syncthreads();
+      if (tid < 169) nxt[454 + tid] = mt_twist(cur[454 + tid], cur[455 + tid], nxt[227 + tid]);
+      else if (tid == 169) nxt[623] = mt_twist(cur[623], nxt[0], nxt[396]);
+      __syncthreads();
+      cb ^= 1;
+      pos = 0;
+    }
+    const uint32_t* key = keybuf[cb];
+    int start = pos;
+    if (carry_valid) {
+      if (tid == 0) out[produced] = mt_double(carry, mt_temper(key[start]));
+      produced++; start++; carry_valid = false;
+    }
+    const long long remain = N - produced;
+    long long pairs = (MT_N - start) / 2;
+    if (pairs > remain) pairs = remain;
+    for (int k = tid; k < (int)pairs; k += MT_THREADS)
+      out[produced + k] = mt_double(mt_temper(key[start + 2 * k]), mt_temper(key[start + 2 * k + 1]));
+    produced += pairs;
+    start += 2 * (int)pairs;
+    if (produced < N && start < MT_N) {       // an odd word closes the block: first half of the next double
+      carry = mt_temper(key[start]); carry_valid = true; start++;
+    }
+    pos = start;
+    // no barrier here: the next twist only READS this buffer and writes the other one, whose last readers
+    // (the previous twist's phases) are behind the barriers above
+  }
+  __syncthreads();
+  for (int i = tid; i < MT_N; i += MT_THREADS) state[i] = keybuf[cb][i];
+  if (tid == 0) state[MT_N] = (uint32_t)pos;
+}
+
+extern "C" int tlbo_mt19937_random_sample(uint32_t* d_state, int64_t N, double* d_out, void* stream) {
+  if (!d_state || !d_out || N < 0) { tlbo_set_error("tlbo_mt19937_random_sample: bad arguments"); return TLBO_E_BADARG; }
+  if (N == 0) return 0;
+  mt19937_random_sample_kernel<<<1, MT_THREADS, 0, (cudaStream_t)stream>>>(d_state, (long long)N, d_out);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -556,6 +556,36 @@ def pair_penalty_loss_normal(y, z, loc, scale, sync=True):
     return d2h(loss) if sync else loss
 
 
+class DeviceRandomState(object):
+    """A legacy ``np.random.RandomState`` whose MT19937 state lives on the device: ``rand_into(out)`` fills a
+    device tensor with the doubles ``rng.rand(out.numel())`` would return, bit for bit, and advances the
+    state (``tlbo_mt19937_random_sample``).  ``to_host(rng)`` / ``from_host(rng)`` move the state."""
+
+    def __init__(self, rng):
+        self.state = torch.empty(625, dtype=torch.int32, device=_dev())
+        self.from_host(rng)
+
+    def from_host(self, rng):
+        st = rng.get_state()
+        assert st[0] == 'MT19937'
+        h = np.empty(625, dtype=np.uint32)
+        h[:624] = st[1]
+        h[624] = st[2]
+        self.state.copy_(torch.from_numpy(h.view(np.int32)))
+        torch.cuda.current_stream().synchronize()      # the generator runs on a side stream
+        self._aux = (st[3], st[4])
+
+    def to_host(self, rng):
+        h = self.state.cpu().numpy().view(np.uint32)
+        rng.set_state(('MT19937', h[:624].copy(), int(h[624]), self._aux[0], self._aux[1]))
+
+    def rand_into(self, out):
+        assert out.is_cuda and out.dtype == F64 and out.is_contiguous()
+        with _call('mt19937_random_sample', 1):
+            check(lib.tlbo_mt19937_random_sample(ptr(self.state), int(out.numel()), ptr(out), _stream()))
+        return out
+
+
 class PairLogistic(object):
     """Pairwise logistic ranking loss + gradient with A and y resident on the device across
     the SLSQP callbacks of one ``scipy_solve``.  Per callback: ONE launch with the weights as

@@ -267,6 +267,13 @@ int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t*
 int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const double* d_loc, const double* d_scale,
                                   int n, int S, int Mr, double* d_loss, void* stream);
 
+/* numpy's LEGACY RandomState.random_sample on the device, bit for bit, with the MT19937 state resident in HBM:
+ * the `rng.rand(N)` tie-break keys that `_sort_configs_by_acq_value` (reference
+ * tlbo/optimizer/ei_optimization.py:106-132) draws over the whole candidate table on every maximisation.
+ *   d_state  uint32[625]: key[624] then pos, i.e. RandomState.get_state()[1] and [2]; advanced in place
+ *   d_out    double[N]                                                                                   */
+int tlbo_mt19937_random_sample(uint32_t* d_state, int64_t N, double* d_out, void* stream);
+
 /* Host-side helper (no device work): the host half of build_single_surrogate + GaussianProcess._train for
  * the 1 + 5 training sets a facade builds per BO iteration from the same (X, y) -- all rows, and all rows
  * except one contiguous validation range (reference tlbo/facade/base_facade.py:93-108, rgpe.py:55-70,

@@ -309,3 +309,27 @@ def test_pairwise_logistic_loss_grad(n, m):
         go = loss_der3(y, A, w)
         assert abs(loss - lo) <= 1e-10 * max(1, abs(lo))
         np.testing.assert_allclose(grad, go, rtol=1e-8, atol=1e-12)
+
+
+def test_device_mt19937_equals_numpy_legacy_random_sample():
+    """``tlbo_mt19937_random_sample``: the tie-break keys ``rng.rand(N)`` generated on the device with the MT19937
+    state resident in HBM -- bit-identical doubles, identical final state, across block boundaries, odd stream
+    positions (a double straddling two state blocks) and consecutive calls."""
+    import torch
+    from tlbo_b200 import ops
+    for seed, sizes, pre in ((4465, [5, 311, 312, 313, 1, 100000, 7], 0), (1, [624 * 3, 2, 999], 3), (2 ** 31 + 7, [10 ** 6], 1)):
+        ref = np.random.RandomState(seed)
+        for _ in range(pre):
+            ref.randint(0, 10000)            # odd / arbitrary stream position
+        dev = ops.DeviceRandomState(ref)
+        for n in sizes:
+            out = torch.empty(n, dtype=torch.float64, device='cuda')
+            dev.rand_into(out)
+            want = ref.rand(n)
+            assert np.array_equal(out.cpu().numpy(), want), (seed, n)
+        back = np.random.RandomState(0)
+        torch.cuda.synchronize()
+        dev.to_host(back)
+        a, b = back.get_state(), ref.get_state()
+        assert np.array_equal(a[1], b[1]) and a[2] == b[2]
+        assert back.rand() == ref.rand()
