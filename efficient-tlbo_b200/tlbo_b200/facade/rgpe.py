@@ -101,10 +101,10 @@ class _BootstrapRankingFacade(BaseFacade):
         # the order in which the reference's loops consume the GLOBAL legacy stream.
         # np.random.normal(loc, scale) == loc + scale * standard_normal() draw for draw, so
         # the draws are taken now and the affine map runs on the device (rank-loss kernel).
+        if self._overlap_hook is not None:
+            self._overlap_hook()        # first: the maximiser's device-side key generation starts under the fit
         z = np.random.standard_normal((S, len(rows), instance_num))
         z_dev = self._stage.upload('z', z)
-        if self._overlap_hook is not None:
-            self._overlap_hook()
 
         # K source predicts + fold predicts at the target points (one launch), pair counts
         mu_dev, var_dev = self._predict_slots(0, K + 1 + n_folds, X_dev)

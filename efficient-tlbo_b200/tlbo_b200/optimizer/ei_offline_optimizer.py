@@ -65,9 +65,14 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         if self._device_keys:
             self._prefetch = False
             self._dev_rng = ops.DeviceRandomState(self.rng)
-            self._keys_full = torch.empty(self.N, dtype=torch.float64, device='cuda')
-            self._keys_dev = self._keys_full[lo:hi]
+            # two key buffers: the keys of the NEXT maximisation (independent of the BO state) are generated
+            # right after the current one has been enqueued, so the generator never sits on the critical path
+            self._keys_full = [torch.empty(self.N, dtype=torch.float64, device='cuda') for _ in range(2)]
+            self._key_cur = 0
             self._key_stream = torch.cuda.Stream()
+            self._state_before = torch.empty_like(self._dev_rng.state)
+            self._generate_keys(0)
+            self._keys_dev = self._keys_full[0][lo:hi]
         # the table is fixed for the lifetime of this maximiser: let an ensemble facade keep its
         # source surrogates' posteriors over it resident
         model = getattr(acquisition_function, 'model', None)
@@ -97,12 +102,9 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         import torch
         from tlbo_b200 import ops
         if self._device_keys:
-            # the previous maximisation's kernel (the only reader of the key buffer) has completed: its
-            # result was read back.  The side stream does NOT wait for the main stream, where the fit of
-            # this iteration has just been enqueued; the main stream waits for the keys instead.
-            with torch.cuda.stream(self._key_stream):
-                self._dev_rng.rand_into(self._keys_full)
-            torch.cuda.current_stream().wait_stream(self._key_stream)
+            # the keys of this maximisation were generated ahead of time on the side stream
+            # (`_generate_keys`); the main stream waits for them right before the fused kernel
+            self._keys_dev = self._keys_full[self._key_cur][self.lo:self.hi]
             ex = None
             if len(evaluated_rows):
                 ex = self._stage.upload('excluded', np.sort(np.asarray(evaluated_rows, dtype=np.int64)))
@@ -122,6 +124,33 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
             ex = self._stage.upload('excluded', np.sort(np.asarray(evaluated_rows, dtype=np.int64)))
         self._prepared = (ex,)
 
+    def _generate_keys(self, buf):
+        """Enqueue ``rng.rand(N)`` into key buffer ``buf`` on the side stream.  The buffer's last reader (the
+        fused kernel of the maximisation before the previous one) completed long ago -- its result was read
+        back --, so the side stream never waits for the main stream (where a fit may be running)."""
+        import torch
+        with torch.cuda.stream(self._key_stream):
+            self._state_before.copy_(self._dev_rng.state)          # lets sync_host_rng() undo the look-ahead
+            self._dev_rng.rand_into(self._keys_full[buf])
+
+    def _consume_keys(self):
+        """Called once the current maximisation's kernel is enqueued: switch buffers and start generating the
+        next maximisation's keys."""
+        self._key_cur ^= 1
+        self._generate_keys(self._key_cur)
+
+    def sync_host_rng(self):
+        """Device-keys mode: bring the host ``rng`` object to the state the reference's maximiser would have
+        now (the device generator is one ``rand(N)`` ahead because of the look-ahead buffer)."""
+        import torch
+        if not self._device_keys:
+            return self.rng
+        self._key_stream.synchronize()
+        h = self._state_before.cpu().numpy().view(np.uint32)
+        st = self.rng.get_state()
+        self.rng.set_state(('MT19937', h[:624].copy(), int(h[624]), st[3], st[4]))
+        return self.rng
+
     def _draw_keys(self):
         """One ``rng.rand(N)`` (the reference's tie-break draw) into the next pinned buffer.
         numpy memcpy, not torch copy_: torch's multi-threaded CPU copy stalls for milliseconds
@@ -138,12 +167,24 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
             self.prepare(evaluated_rows)
         ex, = self._prepared
         self._prepared = None
+        if self._device_keys:
+            import torch
+            torch.cuda.current_stream().wait_stream(self._key_stream)
         if self.shard is None:
-            res = self.acquisition_function.best_unevaluated(self.X_dev, keys=self._keys_dev, excluded=ex,
-                                                             ws=self._ws)
+            best_dev = self.acquisition_function.best_unevaluated(self.X_dev, keys=self._keys_dev, excluded=ex,
+                                                                  ws=self._ws, sync=False)[0]
+            if self._device_keys:
+                self._consume_keys()              # next maximisation's keys: generated under everything that follows
+            from tlbo_b200 import ops
+            b = ops.d2h(best_dev)
+            res = (float(b[0]), float(b[1]), int(b[2]), int(b[3]))
+            if res[3] > 0:
+                raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")
         else:
             best_dev = self.acquisition_function.best_unevaluated(self.X_dev, keys=self._keys_dev, excluded=ex,
                                                                   idx_offset=self.lo, ws=self._ws, sync=False)[0]
+            if self._device_keys:
+                self._consume_keys()
             res = self.shard.reduce_best(best_dev)
             if res[3] > 0:
                 raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")
@@ -159,11 +200,11 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         # full descending order (reference semantics, O(N log N) on the host)
         acq = self.acquisition_function(self.X_table)
         if self._device_keys:
-            import torch
-            torch.cuda.synchronize()
-            self._dev_rng.to_host(self.rng)
-        random = self.rng.rand(self.N)
-        if self._device_keys:
-            self._dev_rng.from_host(self.rng)
+            # the look-ahead buffer already holds this call's rng.rand(N)
+            self._key_stream.synchronize()
+            random = self._keys_full[self._key_cur].cpu().numpy()
+            self._consume_keys()
+        else:
+            random = self.rng.rand(self.N)
         indices = np.lexsort((random.flatten(), acq.flatten()))
         return [(acq[ind][0], self._config(ind)) for ind in indices[::-1]]

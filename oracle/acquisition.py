@@ -99,6 +99,7 @@ class OracleSMBOOffline(object):
         self.chooser_rng = np.random.RandomState(random_seed)          # :85-88
         self.y_max, self.y_min = np.max(self.y_table), np.min(self.y_table)
         self.last_acq = None
+        self.last_keys = None
 
     def get_adtm(self):
         return (np.min(self.perfs) - self.y_min) / (self.y_max - self.y_min)
@@ -135,7 +136,7 @@ class OracleSMBOOffline(object):
         self.acquisition_function.update(model=self.model, eta=incumbent_value, num_data=len(self.evaluated))
         acq = self.acquisition_function(self.X_table)
         self.last_acq = acq
-        order, _ = sort_by_acq_value(acq, self.acq_rng)
+        order, self.last_keys = sort_by_acq_value(acq, self.acq_rng)
         return first_unevaluated(order, self.evaluated)
 
     def iterate(self):

@@ -126,7 +126,13 @@ def test_offline_loop_matches_oracle(method, K, N, iters, kind, d, forced):
             ei_o = float(osmbo.last_acq[idx, 0])
             ei_p = smbo.acq_optimizer.last_best[0]
             assert abs(ei_p - ei_o) <= 1e-6 * max(abs(ei_o), 1e-12) + 1e-13
+            # the tie-break key of the picked row: the device generator's rng.rand(N)[idx]
+            assert smbo.acq_optimizer.last_best[1] == osmbo.last_keys[idx]
     assert abs(smbo.get_adtm() - osmbo.get_adtm()) < 1e-15
+    # the maximiser's MT19937 state lives on the device (one look-ahead draw ahead): brought back to the host
+    # it equals the reference maximiser's rng after the same number of rng.rand(N) draws
+    a, b = smbo.acq_optimizer.sync_host_rng().get_state(), osmbo.acq_rng.get_state()
+    assert (a[1] == b[1]).all() and a[2] == b[2]
 
 
 def test_facade_predict_and_ei_call_interface(forced):
