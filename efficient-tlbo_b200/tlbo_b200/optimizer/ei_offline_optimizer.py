@@ -80,13 +80,23 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
             model.register_static_pool(self.X_dev)
         self.last_best = None
         self._prepared = None
+        self._copy_stream = None
+        self._copy_pending = False
         self._stage = ops.PinnedStage()
 
     def reupload(self):
         """Host -> device copy of the candidate rows (the end-to-end benchmark path, where
         the caller hands host configurations on every call like the reference does)."""
+        import torch
         from tlbo_b200 import ops
-        self.X_dev.copy_(self._host_rows, non_blocking=True)
+        # on a copy stream: the candidate rows are first read by the fused kernel at the END of the
+        # iteration, so the transfer runs under the fit kernel instead of in front of it (the previous
+        # reader of X_dev, the last maximisation's kernel, has completed -- its result was read back)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._copy_stream):
+            self.X_dev.copy_(self._host_rows, non_blocking=True)
+        self._copy_pending = True
         ops.STATS.h2d += self._host_rows.numel() * 8
 
     def _config(self, idx):
@@ -167,6 +177,10 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
             self.prepare(evaluated_rows)
         ex, = self._prepared
         self._prepared = None
+        if self._copy_pending:
+            import torch
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
+            self._copy_pending = False
         if self._device_keys:
             import torch
             torch.cuda.current_stream().wait_stream(self._key_stream)
