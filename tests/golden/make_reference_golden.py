@@ -27,7 +27,7 @@ restored.  Everything recorded below is computed by reference code:
            fitted theta, np.random states.  ConfigSpace's sampling / neighbourhood streams come from the
            stand-in (= the oracle's restatement): those two streams NOT pinned
   loop_*   framework/smbo_offline.SMBO_OFFLINE driving facade/rgpe.RGPE, facade/topo.TransBO_RGPE,
-           facade/topo_variant1.OBTLV, facade/topo_variant3.TOPO_V3, facade/obtl.OBTL, facade/tst.TST and facade/pogpe.POGPE: selected rows, weights,
+           facade/topo_variant1.OBTLV, facade/topo_variant3.TOPO_V3, facade/obtl.OBTL, facade/tst.TST, facade/pogpe.POGPE and facade/notl.NoTL: selected rows, weights,
            dilution flags, the bootstrap ranking-loss tables (captured from the np.argmin calls of
            rgpe.py:108 / topo.py), every fitted theta in fit order, and the state of the global
            np.random stream after every iteration
@@ -56,6 +56,7 @@ sys.path.insert(0, REFERENCE)
 from tlbo.acquisition_function.acquisition import EI                       # noqa: E402
 from tlbo.config_space import (CategoricalHyperparameter, Configuration, ConfigurationSpace, Constant,  # noqa: E402
                                UniformFloatHyperparameter, UniformIntegerHyperparameter)
+from tlbo.facade.notl import NoTL                                           # noqa: E402
 from tlbo.facade.obtl import OBTL                                           # noqa: E402
 from tlbo.facade.pogpe import POGPE                                         # noqa: E402
 from tlbo.facade.rgpe import RGPE                                           # noqa: E402
@@ -229,7 +230,7 @@ def loop_level(out):
     out['loop_types'], out['loop_seed'], out['loop_K'] = types, seed, K
 
     for method, cls, iters in (('rgpe', RGPE, 12), ('trans_rgpe', TransBO_RGPE, 12), ('topo', OBTLV, 10), ('topo_v3', TOPO_V3, 10), ('obtl', OBTL, 10),
-                               ('tst', TST, 8), ('pogpe', POGPE, 8)):
+                               ('tst', TST, 8), ('pogpe', POGPE, 8), ('notl', NoTL, 9)):
         cs = rf_space()
         as_dict = lambda X, y: collections.OrderedDict((Configuration(cs, vector=x), float(v)) for x, v in zip(X, y))
         sources = [as_dict(*tables[t]) for t in range(1, K + 1)]

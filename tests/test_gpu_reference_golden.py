@@ -96,11 +96,12 @@ def test_cuda_fit_matches_reference_restarts(tag):
 # ---- whole loops -------------------------------------------------------------------------------
 def _product(method, types, sources, seed):
     from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.notl import NoTL
     from tlbo_b200.facade.pogpe import POGPE
     from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
     from tlbo_b200.facade.topo_variant1 import OBTL, OBTLV, TOPO_V3
     from tlbo_b200.facade.tst import TST
-    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, obtl=OBTL, tst=TST, pogpe=POGPE)[method]
+    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, obtl=OBTL, tst=TST, pogpe=POGPE, notl=NoTL)[method]
     cs = TableSpace(types)
     return cs, cls(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
 
@@ -132,7 +133,7 @@ class _ForcedFits(object):
         monkeypatch.setattr(BF.BaseFacade, '_native_prep_ok', lambda self, X, y: False)
 
 
-METHODS = ['rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'obtl', 'tst', 'pogpe']
+METHODS = ['rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'obtl', 'tst', 'pogpe', 'notl']
 
 
 @pytest.mark.parametrize('method', METHODS)

@@ -123,7 +123,8 @@ LOOPS = {'rgpe': lambda t, s, seed: ofacade.OracleRGPE(t, s, seed, literal_loops
          'topo_v3': lambda t, s, seed: ofacade.OracleTOPOV3(t, s, seed),
          'obtl': lambda t, s, seed: ofacade.OracleOBTL(t, s, seed, literal_loops=True),
          'tst': lambda t, s, seed: ofacade.OracleTST(t, s, seed),
-         'pogpe': lambda t, s, seed: ofacade.OraclePOGPE(t, s, seed)}
+         'pogpe': lambda t, s, seed: ofacade.OraclePOGPE(t, s, seed),
+         'notl': lambda t, s, seed: ofacade.OracleNoTL(t, s, seed)}
 
 
 @pytest.mark.parametrize('method', sorted(LOOPS))
