@@ -258,7 +258,7 @@ extern "C" int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_
 // d_state: uint32[625] = key[624], pos -- numpy's `get_state()[1]`, `[2]`.
 #define MT_N 624
 #define MT_M 397
-#define MT_THREADS 256
+#define MT_THREADS 576
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
   const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
@@ -276,12 +276,17 @@ __device__ __forceinline__ double mt_double(uint32_t w1, uint32_t w2) {
   return (a * 67108864.0 + b) / 9007199254740992.0;      // every step exact in binary64
 }
 
+// Warps 0-7 twist block b + 1 (from `cur` into `nxt`, three phases, three barriers) while warps 8-17 temper,
+// convert and store the doubles of block b straight from `cur`: a block costs the three shared-memory hops of
+// the twist and nothing else.  The look-ahead twist is speculative -- if the stream ends inside block b, block
+// b + 1 is simply not committed, exactly as numpy leaves its key array untouched until the next draw.
+#define MT_TWIST_THREADS 256
+#define MT_WRITE_THREADS 320
 __global__ void __launch_bounds__(MT_THREADS) mt19937_random_sample_kernel(uint32_t* __restrict__ state, long long N,
                                                                            double* __restrict__ out) {
-  // two copies of the state: a block is twisted from `cur` into `nxt` (no read-after-write hazards inside a
-  // phase), so a block costs three barriers; the doubles are tempered and stored straight from `nxt`
   __shared__ uint32_t keybuf[2][MT_N];
   const int tid = threadIdx.x;
+  const int wtid = tid - MT_TWIST_THREADS;          // >= 0: writer thread
   int cb = 0;
   for (int i = tid; i < MT_N; i += MT_THREADS) keybuf[0][i] = state[i];
   int pos = (int)state[MT_N];
@@ -290,40 +295,43 @@ __global__ void __launch_bounds__(MT_THREADS) mt19937_random_sample_kernel(uint3
   bool carry_valid = false;
   uint32_t carry = 0;
   while (produced < N) {                      // every control variable is uniform over the CTA
-    if (pos >= MT_N) {
-      const uint32_t* cur = keybuf[cb];
-      uint32_t* nxt = keybuf[cb ^ 1];
-      if (tid < 227) nxt[tid] = mt_twist(cur[tid], cur[tid + 1], cur[tid + MT_M]);
-      __syncthreads();
-      if (tid < 227) nxt[227 + tid] = mt_twist(cur[227 + tid], cur[228 + tid], nxt[tid]);
-      __syncthreads();
-      if (tid < 169) nxt[454 + tid] = mt_twist(cur[454 + tid], cur[455 + tid], nxt[227 + tid]);
-      else if (tid == 169) nxt[623] = mt_twist(cur[623], nxt[0], nxt[396]);
-      __syncthreads();
-      cb ^= 1;
-      pos = 0;
-    }
-    const uint32_t* key = keybuf[cb];
+    const uint32_t* cur = keybuf[cb];
+    uint32_t* nxt = keybuf[cb ^ 1];
+    // ---- bookkeeping of what block `cur` still has to deliver (positions >= pos)
     int start = pos;
-    if (carry_valid) {
-      if (tid == 0) out[produced] = mt_double(carry, mt_temper(key[start]));
-      produced++; start++; carry_valid = false;
-    }
-    const long long remain = N - produced;
+    const long long base = produced;
+    const bool had_carry = carry_valid && start < MT_N;
+    if (had_carry) { produced++; start++; }
+    const int first = start;                  // first word of the first whole pair
     long long pairs = (MT_N - start) / 2;
+    if (pairs < 0) pairs = 0;
+    const long long remain = N - produced;
     if (pairs > remain) pairs = remain;
-    for (int k = tid; k < (int)pairs; k += MT_THREADS)
-      out[produced + k] = mt_double(mt_temper(key[start + 2 * k]), mt_temper(key[start + 2 * k + 1]));
     produced += pairs;
     start += 2 * (int)pairs;
-    if (produced < N && start < MT_N) {       // an odd word closes the block: first half of the next double
-      carry = mt_temper(key[start]); carry_valid = true; start++;
+    bool new_carry = false;
+    if (produced < N && start < MT_N) { new_carry = true; start++; }      // odd word: first half of the next double
+    // ---- writers: block `cur`;  twisters: phase 1 of the next block
+    if (wtid >= 0) {
+      if (had_carry && wtid == MT_WRITE_THREADS - 1) out[base] = mt_double(carry, mt_temper(cur[first - 1]));
+      const long long ob = base + (had_carry ? 1 : 0);
+      for (int k = wtid; k < (int)pairs; k += MT_WRITE_THREADS)
+        out[ob + k] = mt_double(mt_temper(cur[first + 2 * k]), mt_temper(cur[first + 2 * k + 1]));
+    } else if (tid < 227) {
+      nxt[tid] = mt_twist(cur[tid], cur[tid + 1], cur[tid + MT_M]);
     }
-    pos = start;
-    // no barrier here: the next twist only READS this buffer and writes the other one, whose last readers
-    // (the previous twist's phases) are behind the barriers above
+    const uint32_t next_carry = new_carry ? mt_temper(cur[start - 1]) : 0u;
+    __syncthreads();
+    if (tid < 227) nxt[227 + tid] = mt_twist(cur[227 + tid], cur[228 + tid], nxt[tid]);
+    __syncthreads();
+    if (tid < 169) nxt[454 + tid] = mt_twist(cur[454 + tid], cur[455 + tid], nxt[227 + tid]);
+    else if (tid == 169) nxt[623] = mt_twist(cur[623], nxt[0], nxt[396]);
+    __syncthreads();
+    carry_valid = new_carry;
+    carry = next_carry;
+    if (start >= MT_N && produced < N) { cb ^= 1; pos = 0; }     // commit the look-ahead block
+    else pos = start;
   }
-  __syncthreads();
   for (int i = tid; i < MT_N; i += MT_THREADS) state[i] = keybuf[cb][i];
   if (tid == 0) state[MT_N] = (uint32_t)pos;
 }
