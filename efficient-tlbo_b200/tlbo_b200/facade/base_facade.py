@@ -82,6 +82,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self._overlap_hook = None     # host callback run while the batched fit is in flight
         self._p0_cache = None         # restart start points shared by every model of this facade
         self._proto = None            # prototype of a freshly built target-side surrogate
+        self._ens_cache = None        # (pack, device weights / skip / order, pack view) of acq_small
         self._pool_cache = {}         # (data_ptr, N) -> resident source posteriors over a fixed pool
 
     # ---- device pack ------------------------------------------------------------------
@@ -124,6 +125,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
 
     def _fit_async(self, models, Xs, ys):
         """One batched device fit of ``models`` (MAP restarts or MCMC chains); returns ``finish``."""
+        self._ens_cache = None
         if self._G > 1:
             return fit_mcmc_models_async(models, Xs, ys)
         return fit_models_async(models, Xs, ys)
@@ -205,6 +207,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         if self._proto is None:
             self._proto = self._new_model()
             self._share_start_points(self._proto)
+        self._ens_cache = None
         pack = self._ensure_pack(X.shape[0])
         prep = ops.prepare_jobs(X, y, ranges, outer_guard, normalize)
         models = [self._proto.fresh_copy().bind(pack, self.K + j) for j in range(len(ranges))]
@@ -277,13 +280,19 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         Xp = sq.X_np[:N]
         Xp[...] = X
         Xp[~np.isfinite(Xp)] = -1
-        w, skip, order = self._ensemble_args()
-        dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
-        dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
-        dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+        # the ensemble weights / flags and the pack view only change with a fit: built once per training
+        # (this path runs a few hundred times per online BO iteration)
+        ens = self._ens_cache
+        if ens is None or ens[0] is not self._pack:
+            w, skip, order = self._ensemble_args()
+            dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
+            dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
+            dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+            ens = self._ens_cache = (self._pack, dw, dskip, dorder, ops.pack_view(self._pack, 0, self.K + 1))
+        _, dw, dskip, dorder, view = ens
         Xq = sq.Xd[:N]
         Xq.copy_(sq.X[:N], non_blocking=True)
-        mu, var = ops.gp_predict(ops.pack_view(self._pack, 0, self.K + 1), self.types, Xq, out=(sq.mu, sq.var))
+        mu, var = ops.gp_predict(view, self.types, Xq, out=(sq.mu, sq.var))
         ops.predict_ei_fused(self._logical(), self.types, dw, dskip, Xq, eta, par=par, var_floor=var_floor,
                              mode=self._fused_mode, order=dorder, ws=sq.ws, sync=False, nmax=8, cache=(mu, var),
                              rows=(sq.mu_rows, sq.var_rows, sq.ei))
