@@ -13,6 +13,11 @@ void tlbo_set_error(const char* msg) {
 extern "C" const char* tlbo_last_error(void) { return g_err; }
 extern "C" int tlbo_version(void) { return 100; }
 
+extern "C" int tlbo_stream_synchronize(void* stream) {
+  TLBO_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 // Column permutation: continuous columns (types == 0) first, categorical after, each group
 // in the reference's column order (model_builder.py:38-39: cont_dims / cat_dims).
 int tlbo_make_space(int d, const int32_t* h_types, SpaceDesc* sp) {

@@ -34,6 +34,7 @@ _P = c_void_p
 SYMBOLS = {
     'tlbo_last_error': (c_char_p, []),
     'tlbo_version': (c_int, []),
+    'tlbo_stream_synchronize': (c_int, [_P]),
     'tlbo_gp_fit_batched': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, c_int,
                                     POINTER(TlboPack), c_int, _P, _P, _P, _P, _P, _P]),
     'tlbo_gp_fit_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int]),

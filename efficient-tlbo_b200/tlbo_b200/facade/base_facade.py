@@ -296,7 +296,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         ops.predict_ei_fused(self._logical(), self.types, dw, dskip, Xq, eta, par=par, var_floor=var_floor,
                              mode=self._fused_mode, order=dorder, ws=sq.ws, sync=False, nmax=8, cache=(mu, var),
                              rows=(sq.mu_rows, sq.var_rows, sq.ei))
-        torch.cuda.current_stream().synchronize()
+        ops.stream_synchronize()
         ops.STATS.h2d += N * len(self.types) * 8
         ops.STATS.d2h += N * 8 + 32
         return sq.ei_np[:N].copy(), int(sq.best_np[3])

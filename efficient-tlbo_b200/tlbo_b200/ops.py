@@ -17,7 +17,20 @@ def _dev():
     return torch.device('cuda', torch.cuda.current_device())
 
 
+_RAW_STREAM = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
+def stream_synchronize():
+    """Wait for torch's current stream (``tlbo_stream_synchronize``)."""
+    check(lib.tlbo_stream_synchronize(_stream()))
+
+
 def _stream():
+    """The launching stream (torch's CURRENT stream, so ``with torch.cuda.stream(s)`` is honoured) as a raw
+    ``cudaStream_t``.  ``torch.cuda.current_stream()`` builds a Python Stream object (~15 us -- three of
+    them per acquisition call of the online local search); the raw query costs well under a microsecond."""
+    if _RAW_STREAM is not None:
+        return ctypes.c_void_p(_RAW_STREAM(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

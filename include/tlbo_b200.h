@@ -38,6 +38,9 @@ extern "C" {
 
 const char* tlbo_last_error(void);
 int tlbo_version(void);
+/* cudaStreamSynchronize(stream): lets a host binding wait for the stream it launched on without going through
+ * its framework's stream objects (the online local search waits a few hundred times per BO iteration). */
+int tlbo_stream_synchronize(void* stream);
 
 /* A batch ("pack") of fitted GP surrogates laid out for the predict kernels.
  * All arrays are device memory owned by the caller; per-model arrays are strided by
