@@ -537,7 +537,12 @@ def run_ours(args):
                     flops / max(fused_calls, 1) / alg_bytes),
     }
     fit_calls, fit_ms = kms.get('gp_fit', (0, 0.0))
-    dominant = max(kms.items(), key=lambda kv: kv[1][1])[0] if kms else None
+    # launches on side streams that run UNDER other kernels (the look-ahead tie-break key generator: one CTA,
+    # enqueued behind the previous fused kernel and finished long before the next one needs the keys) are
+    # reported but are not on the critical path of the step
+    overlapped = {'mt19937_random_sample'}
+    on_path = {k: v for k, v in kms.items() if k not in overlapped}
+    dominant = max(on_path.items(), key=lambda kv: kv[1][1])[0] if on_path else None
     roofline_fit = {
         'kernel': 'gp_fit_kernel (+ gp_factorize_kernel)', 'bound': 'latency',
         'achieved': fitfl / (fit_ms * 1e-3) / 1e12 if fit_ms > 0 else 0.0, 'peak': dmma_tf[0], 'unit': 'TFLOP/s',
@@ -563,6 +568,11 @@ def run_ours(args):
     step_ms = ms_res / K
     breakdown = {k: {'calls_per_step': c / float(K), 'ms_per_step': t / K, 'share_of_step': t / ms_ins}
                  for k, (c, t) in kms.items()}
+    for k in overlapped:
+        if k in breakdown:
+            breakdown[k]['overlapped'] = ('side stream, concurrent with the host post-processing and the next fit kernel; '
+                                          'the event pair also spans its wait for SM resources behind the previous '
+                                          'fused kernel -- not part of the critical path')
     line = {
         'metric': METRIC, 'value': world * K / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
