@@ -235,3 +235,48 @@ def test_resident_pool_posteriors_are_bit_identical(forced):
     mo, vo = prod.source_surrogates[2].predict(Xt[:300])
     np.testing.assert_allclose(cmu[2, :300].cpu().numpy(), mo.ravel(), rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(cvar[2, :300].cpu().numpy(), vo.ravel(), rtol=1e-10, atol=1e-16)
+
+
+def test_offline_search_full_order_and_head_share_one_key_stream(forced):
+    """``OfflineSearch.maximize``: the default head-only call and the reference-shaped ``full_order=True`` call
+    consume the SAME ``rng.rand(N)`` stream (device generator with a look-ahead buffer): a head call, a full
+    ordering and another head call equal the oracle's three consecutive ``_sort_configs_by_acq_value`` draws."""
+    from oracle.acquisition import OracleEI, sort_by_acq_value
+    from tlbo_b200.acquisition_function.acquisition import EI
+    from tlbo_b200.optimizer.ei_offline_optimizer import OfflineSearch
+    seed = 4465
+    types, sources, (Xt, yt) = _bench(2, 700, seed)
+    cs, prod = _make('rgpe', types, sources, seed)
+    ora = _make_oracle('rgpe', types, sources, seed, prod, forced)
+    X, y = Xt[:9].copy(), yt[:9].copy()
+    np.random.seed(2)
+    prod.train(X, y.copy())
+    forced.queue = [prod._pack.theta[2 + j].cpu().numpy() for j in range(6)]
+    np.random.seed(2)
+    ora.train(X, y.copy())
+    eta = float(np.min((y - y.mean()) / y.std()))
+    ei = EI(prod)
+    ei.update(model=prod, eta=eta, num_data=9)
+    oe = OracleEI(ora)
+    oe.update(eta=eta)
+    acq_o = oe(Xt)
+    search = OfflineSearch(Xt, ei, cs, rng=np.random.RandomState(seed), prefetch_keys=True)
+    orng = np.random.RandomState(seed)
+    # 1) head only
+    head = search.maximize(None, 5000)
+    order, keys = sort_by_acq_value(acq_o, orng)
+    assert head[0].index == int(order[0]) and search.last_best[1] == keys[order[0]]
+    # 2) full ordering (reference semantics)
+    full = search.maximize(None, 5000, full_order=True)
+    order, keys = sort_by_acq_value(acq_o, orng)
+    got = np.array([c.index for c in full])
+    top = 50                                    # beyond the head, EI ties at the 1e-6 level may swap neighbours
+    assert len(got) == len(order) and (got[:top] == order[:top]).all()
+    # 3) head again, with two evaluated rows excluded
+    ex = [int(order[0]), int(order[1])]
+    idx = search.best_unevaluated(ex)
+    order, keys = sort_by_acq_value(acq_o, orng)
+    want = [int(i) for i in order if int(i) not in ex][0]
+    assert idx == want and search.last_best[1] == keys[want]
+    a, b = search.sync_host_rng().get_state(), orng.get_state()
+    assert (a[1] == b[1]).all() and a[2] == b[2]
