@@ -194,15 +194,24 @@ def one_exchange_neighbourhood_arrays(config, seed, num_neighbors=NUM_NEIGHBORS,
     space = config.space
     array = np.ascontiguousarray(config.get_array(), dtype=np.float64)
     d = len(array)
-    types = np.ascontiguousarray(space.types, dtype=np.int32)
-    cmask = np.ascontiguousarray(space.const_mask, dtype=np.uint8)
-    max_rows = int(np.sum(np.where(types > 0, types - 1, num_neighbors))) + 1
+    # per-space constants of the call (this runs once per hill-climb step): converted once
+    cache = getattr(space, '_nbh_cache', None)
+    if cache is None or cache[0] != num_neighbors:
+        types = np.ascontiguousarray(space.types, dtype=np.int32)
+        cmask = np.ascontiguousarray(space.const_mask, dtype=np.uint8)
+        max_rows = int(np.sum(np.where(types > 0, types - 1, num_neighbors))) + 1
+        n_out = ctypes.c_int32(0)
+        cache = (num_neighbors, types, cmask, max_rows, n_out, ptr(types), ptr(cmask),
+                 ctypes.cast(ctypes.byref(n_out), ctypes.c_void_p))
+        try:
+            space._nbh_cache = cache
+        except AttributeError:
+            pass
+    _, types, cmask, max_rows, n_out, p_types, p_cmask, p_n = cache
     out = np.empty((max_rows, d), dtype=np.float64)
-    n = ctypes.c_int32(0)
-    check(lib.tlbo_one_exchange_neighbourhood(ptr(array), d, ptr(types), ptr(cmask), int(seed) & 0xffffffff,
-                                              int(num_neighbors), float(stdev), ptr(out), max_rows,
-                                              ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
-    return out[:n.value]
+    check(lib.tlbo_one_exchange_neighbourhood(ptr(array), d, p_types, p_cmask, int(seed) & 0xffffffff,
+                                              int(num_neighbors), float(stdev), ptr(out), max_rows, p_n))
+    return out[:n_out.value]
 
 
 def get_one_exchange_neighbourhood(config, seed, num_neighbors=NUM_NEIGHBORS, stdev=NEIGHBOUR_STDEV):
