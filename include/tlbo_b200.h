@@ -255,7 +255,8 @@ int tlbo_mcmc_marginalize(const double* d_mu, const double* d_var, int G, int W,
  * randint / shuffle, polar-method normal).
  *   h_array [d]        the configuration (reference encoding; non-finite = inactive)
  *   h_types [d]        get_types vector; h_const_mask [d] 1 = Constant hyper-parameter (may be NULL)
- *   num_neighbors, stdev   ConfigSpace defaults 4 and 0.2
+ *   num_neighbors, stdev   the reference binds 8 and 0.05 (tlbo/config_space/__init__.py:10); ConfigSpace's own
+ *                          defaults are 4 and 0.2
  *   h_out [max_rows, d], *h_n_rows   neighbours, one changed column per row                      */
 int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t* h_types,
                                     const uint8_t* h_const_mask, uint32_t seed, int num_neighbors, double stdev,
