@@ -58,41 +58,46 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.p0[(size_t)r * H + tid];
   __syncthreads();
-  int bumps = 0;
-  if (r == 0) {
-    // gp.py:127-140: the initial GaussianProcessRegressor.fit at the default theta retries
-    // with noise += 1 on LinAlgError; the bumped theta then becomes start point 0.
-    for (int tries = 0; tries < 10; tries++) {
-      if (build_and_eliminate_any<T>(S, a.sp, th, false)) break;
+  // ONE evaluation call site (the unrolled evaluation is ~100 KB of code; a second copy costs
+  // instruction-cache misses on the critical path): the evaluation at the start point doubles as
+  // the positive-definiteness probe of gp.py:127-140 -- the initial GaussianProcessRegressor.fit at
+  // the default theta retries with noise += 1 on LinAlgError (restart 0 only; bumped evaluations do
+  // not count as function evaluations), and the bumped theta then becomes start point 0.
+  int bumps = 0, nfev = 0;
+  if (a.do_optimize) {
+    if (WARP_OPT) { if (wid == 0) lbw_init(*sw, H, th, a.lo, a.hi, lane); }
+    else { if (tid == 0) lbfgsb_init(*st, H, th, a.lo, a.hi); }
+    __syncthreads();
+  }
+  for (;;) {
+    if (a.do_optimize && tid < H) th[tid] = WARP_OPT ? sw->x[tid] : st->x[tid];
+    __syncthreads();
+    const bool ok = nll_eval_any<T, DMAX>(S, a.sp, th, fg);
+    if (r == 0 && !ok && nfev == 0 && bumps < 10) {
       if (tid == 0) th[H - 1] = log(exp(th[H - 1]) + 1.0);
       bumps++;
       __syncthreads();
+      if (a.do_optimize) {
+        if (WARP_OPT) { if (wid == 0) lbw_init(*sw, H, th, a.lo, a.hi, lane); }
+        else { if (tid == 0) lbfgsb_init(*st, H, th, a.lo, a.hi); }
+        __syncthreads();
+      }
+      continue;
     }
-  }
-  int nfev = 0;
-  if (!a.do_optimize) {
-    nll_eval_any<T, DMAX>(S, a.sp, th, fg);
-    nfev = 1;
-    if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = th[tid];
-    if (tid == 0) {
-      a.restart_f[(size_t)b * a.R + r] = fg[0];
-      int32_t* info = a.restart_info + ((size_t)b * a.R + r) * 4;
-      info[0] = nfev; info[1] = 0; info[2] = -1; info[3] = bumps;
-    }
-    return;
-  }
-  if (WARP_OPT) { if (wid == 0) lbw_init(*sw, H, th, a.lo, a.hi, lane); }
-  else { if (tid == 0) lbfgsb_init(*st, H, th, a.lo, a.hi); }
-  __syncthreads();
-  for (;;) {
-    if (tid < H) th[tid] = WARP_OPT ? sw->x[tid] : st->x[tid];
-    __syncthreads();
-    nll_eval_any<T, DMAX>(S, a.sp, th, fg);
     nfev++;
+    if (!a.do_optimize) {
+      if (tid < H) a.restart_theta[((size_t)b * a.R + r) * H + tid] = th[tid];
+      if (tid == 0) {
+        a.restart_f[(size_t)b * a.R + r] = fg[0];
+        int32_t* info = a.restart_info + ((size_t)b * a.R + r) * 4;
+        info[0] = nfev; info[1] = 0; info[2] = -1; info[3] = bumps;
+      }
+      return;
+    }
     PHASE_T0();
     if (WARP_OPT) {
       if (wid == 0) {
-        const int rc = lbw_feed(*sw, fg[0], fg + 1, lane);
+        const int rc = lbw_feed<DMAX>(*sw, fg[0], fg + 1, lane);
         if (lane == 0) act = rc;
       }
     } else {
@@ -385,6 +390,13 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
     if (rc) return rc;                                                       \
     gp_fit_kernel<DM, WO, TT><<<B * R, FIT_THREADS, w.smem_fit, s>>>(a);     \
   } while (0)
+#ifdef TLBO_FIT_FEW_TILES   /* development builds: one register-panel instantiation (fast SASS inspection) */
+#define TLBO_LAUNCH_FIT_T(DM)                                                \
+  do {                                                                       \
+    if (tile == 4) TLBO_LAUNCH_FIT(DM, true, 4);                             \
+    else { tlbo_set_error("development build: tile 4 only"); return TLBO_E_BADARG; } \
+  } while (0)
+#else
 #define TLBO_LAUNCH_FIT_T(DM)                                                \
   do {                                                                       \
     switch (tile) {                                                          \
@@ -396,11 +408,13 @@ extern "C" int tlbo_gp_fit_batched(const double* d_X, const double* d_y, const i
       default: TLBO_LAUNCH_FIT(DM, true, 0); break;                          \
     }                                                                        \
   } while (0)
+#endif
   const int tile = w.tile;
+  // DMAX also sizes the unrolled loops of the warp optimiser: H = d + 2 <= DMAX
   if (g_fit_variant != 0) {
-    if (d <= 12) TLBO_LAUNCH_FIT_T(12); else TLBO_LAUNCH_FIT_T(24);
+    if (d <= 10) TLBO_LAUNCH_FIT_T(12); else TLBO_LAUNCH_FIT_T(24);
   } else {
-    if (d <= 12) TLBO_LAUNCH_FIT(12, false, 0); else TLBO_LAUNCH_FIT(24, false, 0);
+    if (d <= 10) TLBO_LAUNCH_FIT(12, false, 0); else TLBO_LAUNCH_FIT(24, false, 0);
   }
 #undef TLBO_LAUNCH_FIT_T
 #undef TLBO_LAUNCH_FIT
@@ -456,6 +470,13 @@ extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, co
     if (rc) return rc;                                                       \
     gp_nll_grad_kernel<DM, TT><<<B, FIT_THREADS, w.smem_fac, s>>>(a);        \
   } while (0)
+#ifdef TLBO_FIT_FEW_TILES
+#define TLBO_LAUNCH_NLL_T(DM)                                                \
+  do {                                                                       \
+    if (tile == 4) TLBO_LAUNCH_NLL(DM, 4);                                   \
+    else { tlbo_set_error("development build: tile 4 only"); return TLBO_E_BADARG; } \
+  } while (0)
+#else
 #define TLBO_LAUNCH_NLL_T(DM)                                                \
   do {                                                                       \
     switch (tile) {                                                          \
@@ -467,6 +488,7 @@ extern "C" int tlbo_gp_nll_grad_batched(const double* d_X, const double* d_y, co
       default: TLBO_LAUNCH_NLL(DM, 0); break;                                \
     }                                                                        \
   } while (0)
+#endif
   const int tile = w.tile;
   if (d <= 12) TLBO_LAUNCH_NLL_T(12); else TLBO_LAUNCH_NLL_T(24);
 #undef TLBO_LAUNCH_NLL_T

@@ -367,7 +367,9 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
     }
     const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
     const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
-    const double v0 = ce0 * (1.0 + t0 + t0 * t0 / 3.0), v1 = ce1 * (1.0 + t1 + t1 * t1 / 3.0);
+    // t^2 / 3 as a multiplication by the rounded 1/3 (<= 1 ulp from the IEEE quotient; the division is a
+    // ~25-instruction subroutine on the critical path of every pair)
+    const double v0 = ce0 * (1.0 + t0 + t0 * t0 * (1.0 / 3.0)), v1 = ce1 * (1.0 + t1 + t1 * t1 * (1.0 / 3.0));
     A[(size_t)i0 * lda + j0] = v0;
     if (S.Kc) { S.Kc[q0] = v0; S.Cg[q0] = ce0 * (5.0 / 3.0) * (t0 + 1.0); }
     if (has1) {
@@ -671,8 +673,8 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
       }
       const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
       const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
-      WK0 = W0 * (ce0 * (1.0 + t0 + t0 * t0 / 3.0)); cf0 = W0 * (ce0 * (5.0 / 3.0) * (t0 + 1.0));
-      WK1 = W1 * (ce1 * (1.0 + t1 + t1 * t1 / 3.0)); cf1 = W1 * (ce1 * (5.0 / 3.0) * (t1 + 1.0));
+      WK0 = W0 * (ce0 * (1.0 + t0 + t0 * t0 * (1.0 / 3.0))); cf0 = W0 * (ce0 * (5.0 / 3.0) * (t0 + 1.0));
+      WK1 = W1 * (ce1 * (1.0 + t1 + t1 * t1 * (1.0 / 3.0))); cf1 = W1 * (ce1 * (5.0 / 3.0) * (t1 + 1.0));
     }
     g0 += WK0;
     g0 += WK1;
@@ -696,9 +698,9 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   }
   PHASE_MARK(7);
   const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
-  __syncthreads();
   {
-    // one interleaved butterfly over all H slots (independent shuffles pipeline)
+    // one interleaved butterfly over all H slots (independent shuffles pipeline); S.red was last read
+    // before the barrier in front of the W publish, so no barrier is needed here
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       g0 += __shfl_xor_sync(0xffffffffu, g0, o);
@@ -715,13 +717,49 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     }
   }
   __syncthreads();
-  if (tid < H) {
-    double v = 0.0;
-    for (int w = 0; w < nw; w++) v += S.red[w * 32 + tid];
-    out[1 + tid] = v;
+  // warp 0 sums the per-warp partials while four lanes of warp 1 evaluate the log-priors of
+  // GaussianProcess._nll (the reference's formulas, operation for operation: nll_finish states them
+  // for one thread) with TWO lock-step log calls instead of seven sequential transcendental calls
+  double gsum = 0.0;
+  if (wid == 0) {
+    if (lane < H)
+      for (int w = 0; w < nw; w++) gsum += S.red[w * 32 + lane];       // d LML / d theta_h (without priors)
+  } else if (wid == 1 && lane < 4) {
+    const double s2 = 0.1 * 0.1, vn2 = noise * noise;
+    const double arg = (lane == 0) ? 1.0 + 3.0 * (s2 / vn2)
+                     : (lane == 1) ? 3.0 * s2 * (1.0 / vn2) + 1.0
+                     : (lane == 2) ? c : 2.5066282746310002 * c;
+    const double lg = log(arg);
+    const double lg_b = __shfl_sync(0xfu, lg, 1), lv = __shfl_sync(0xfu, lg, 2), l25 = __shfl_sync(0xfu, lg, 3);
+    if (lane == 0) {
+      // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
+      double lp0, gp0;
+      if (c <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
+      else { lp0 = -(lv * lv) / 2.0 - l25; gp0 = -(1.0 + lv) / c * c; }
+      // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
+      double lpn, gpn;
+      if (noise == 0.0) { lpn = INFINITY; gpn = INFINITY; }
+      else {
+        lpn = log(lg + VERY_SMALL_NUMBER);
+        double bq = (3.0 * s2 + vn2) * lg_b;
+        bq = fmax(bq, 1e-14);
+        gpn = -(6.0 * s2) / bq;
+      }
+      S.red[32 + 24] = lp0 + lpn;
+      S.red[32 + 25] = gp0;
+      S.red[32 + 26] = gpn;
+    }
   }
   __syncthreads();
-  if (tid == 0) nll_finish(theta, H, n, nll_data, out);
+  if (wid == 0) {
+    // final sign / finiteness rules of GaussianProcess._nll (gp.py:183-197)
+    const double lml = -nll_data - 0.5 * (double)n * LOG_2PI + S.red[32 + 24];
+    if (lane == 0) gsum += S.red[32 + 25];
+    if (lane == H - 1) gsum += S.red[32 + 26];
+    const bool fin = __all_sync(0xffffffffu, isfinite(lml) && (lane >= H || isfinite(gsum)));
+    if (lane == 0) out[0] = fin ? -lml : 1e25;
+    if (lane < H) out[1 + lane] = fin ? -gsum : 0.0;
+  }
   __syncthreads();
   PHASE_MARK(8);
   return true;

@@ -1,46 +1,44 @@
-// Warp-cooperative L-BFGS-B (device only): the same algorithm, state machine and
-// termination tests as lbfgsb_dense.cuh (which stays the host-testable statement of the
-// optimiser, checked against scipy in tests/test_lbfgsb_host.py), with the linear algebra
-// spread over the 32 lanes of one warp:
-//   * dense limited-memory matrix rebuild (m rank-2 updates)      lane = column of B
-//   * B*v products in the Cauchy search / subspace minimisation   lane = row, symmetric access
-//   * reduced Cholesky factorisation and the two triangular solves lane = row
-//   * all dot products                                             xor-butterfly (identical in every lane)
-// Scalar logic (line search dcsrch/dcstep, break-point bookkeeping, projection step) runs on
-// lane 0 over the shared-memory state and is published with __syncwarp().
+// Warp-resident L-BFGS-B (device only): the same algorithm, state machine and termination tests as
+// lbfgsb_dense.cuh (which stays the host-testable statement of the optimiser, checked against scipy in
+// tests/test_lbfgsb_host.py), organised for LATENCY: one step of the optimiser sits between two
+// dependent NLL evaluations of the fit kernel, with the other seven warps of the CTA parked at a barrier.
 //
-// ncu on the single-thread version showed 63% of the fit kernel's wall time inside this
-// state machine with 255 threads parked at the barrier (profiles/r1a_*); this version is
-// the remedy.  Replaces scipy.optimize.fmin_l_bfgs_b of reference tlbo/model/gp.py:241-248.
+// Round-1 version: 24 k cycles per step (rebuild_B 5.8 k, Cauchy 2.6 k, subspace step 8.3 k, line-search
+// bookkeeping 5.3 k; profiles/README.md).  What this version does differently:
+//   * the problem size is a template parameter (NMAX = 12 or 24): every loop over variables is unrolled,
+//     every vector a lane needs in full (s_k, y_k, B s, d, the pivot column ...) is read with 128-bit
+//     broadcast loads from shared memory into registers -- a "gather" is one store per lane, one
+//     __syncwarp and NMAX/2 loads, and cross-lane sums are a gather plus a local, fixed-order sum
+//     (identical in every lane) instead of five dependent shuffle levels;
+//   * lane i keeps row i of the dense limited-memory matrix B in registers from the rebuild through the
+//     Cauchy search to the subspace step (B is symmetric; it never touches shared memory);
+//   * scalar logic (dcsrch, break-point bookkeeping, stpmx, convergence tests) is executed redundantly by
+//     all lanes on identical data: no lane-0 sections, no flag broadcasts, no divergence;
+//   * the reduced Cholesky of the subspace step runs on the FULL matrix with identity rows / columns at
+//     the fixed variables (bit-identical arithmetic for the free block: the fixed rows contribute exact
+//     zeros), right-looking and register-resident with the forward substitution folded in;
+//   * the (s, y) pairs live in a ring buffer (no shifting), 1 / y's is stored with the pair, and the
+//     reciprocals on the rebuild's critical chain use the rcp.approx seed + 2 Newton steps (<= 1 ulp).
+//
+// Replaces scipy.optimize.fmin_l_bfgs_b of reference tlbo/model/gp.py:241-248.
 #pragma once
 #include "lbfgsb_dense.cuh"
 
-#define LW_LD (LB_NMAX + 1)
+#define LBW_SCR 4
 
-struct LbwState {
-  int n;
-  double x[LB_NMAX], l[LB_NMAX], u[LB_NMAX];
-  double f, g[LB_NMAX];
-  double t[LB_NMAX], r[LB_NMAX], fold;
-  double d[LB_NMAX], z[LB_NMAX];
-  double S[LB_M][LB_NMAX], Y[LB_M][LB_NMAX];
-  double B[LB_NMAX][LB_NMAX];          // symmetric; lanes read column `lane` (= row) conflict-free
-  double Wk[LB_NMAX][LW_LD];           // reduced Cholesky factor (lower)
-  // per-variable scratch of the Cauchy search / subspace step
-  double dd[LB_NMAX], tb[LB_NMAX], zfix[LB_NMAX], rr[LB_NMAX], dsub[LB_NMAX], xp[LB_NMAX];
-  int hasb[LB_NMAX], ind[LB_NMAX], iwhere[LB_NMAX];
-  double theta;
-  int col;
-  double stp, stpmx, gd, gdold, dnorm, dtd;
-  int ifun, iback;
-  int ls_brackt, ls_stage;
+struct __align__(16) LbwState {
+  // lane-indexed vectors, zero beyond n (all 16-byte aligned: read back with 128-bit loads)
+  double x[LB_NMAX], l[LB_NMAX], u[LB_NMAX], g[LB_NMAX];
+  double t[LB_NMAX], r[LB_NMAX], d[LB_NMAX], z[LB_NMAX];
+  double S[LB_M][LB_NMAX], Y[LB_M][LB_NMAX];     // ring buffer: pair k (oldest first) at (head + k) % LB_M
+  double scr[LBW_SCR][LB_NMAX];                   // rotating gather scratch
+  double ysinv[LB_M + 2];                         // 1 / y_k's_k
+  double L[LB_NMAX][LB_NMAX + 1];                 // reduced Cholesky factor (rows), for the back substitution
+  double theta, f, fold, f_last;
+  double stp, stpmx, gd, gdold, dnorm, dtd, sbgnrm;
   double ls_ginit, ls_gtest, ls_gx, ls_gy, ls_finit, ls_fx, ls_fy, ls_stx, ls_sty, ls_stmin, ls_stmax, ls_width,
       ls_width1;
-  int phase, iter, nfgv, nskip, status;
-  double sbgnrm, factr, pgtol;
-  int maxiter, maxfun, maxls;
-  double f_last;
-  int flag;                             // lane-0 -> warp broadcast slot
+  int n, col, head, ifun, iback, ls_brackt, ls_stage, phase, iter, nfgv, nskip, status;
 };
 
 #ifdef TLBO_PHASE_TIMING
@@ -54,450 +52,501 @@ __device__ long long g_feed_cycles[8];
 
 namespace lbw {
 
-__device__ __forceinline__ double wsum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// Scalars carried in registers during one call (identical in every lane); lane 0 writes them back.
+struct Regs {
+  double theta, f, fold, stp, stpmx, gd, gdold, dnorm, dtd, sbgnrm;
+  double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
+  int col, head, ifun, iback, brackt, stage, phase, iter, nfgv, nskip, status;
+};
+
+__device__ __forceinline__ void load_regs(const LbwState& s, Regs& R) {
+  R.theta = s.theta; R.f = s.f; R.fold = s.fold; R.stp = s.stp; R.stpmx = s.stpmx; R.gd = s.gd; R.gdold = s.gdold;
+  R.dnorm = s.dnorm; R.dtd = s.dtd; R.sbgnrm = s.sbgnrm;
+  R.ginit = s.ls_ginit; R.gtest = s.ls_gtest; R.gx = s.ls_gx; R.gy = s.ls_gy; R.finit = s.ls_finit; R.fx = s.ls_fx;
+  R.fy = s.ls_fy; R.stx = s.ls_stx; R.sty = s.ls_sty; R.stmin = s.ls_stmin; R.stmax = s.ls_stmax;
+  R.width = s.ls_width; R.width1 = s.ls_width1;
+  R.col = s.col; R.head = s.head; R.ifun = s.ifun; R.iback = s.iback; R.brackt = s.ls_brackt; R.stage = s.ls_stage;
+  R.phase = s.phase; R.iter = s.iter; R.nfgv = s.nfgv; R.nskip = s.nskip; R.status = s.status;
 }
-__device__ __forceinline__ double wmax(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+__device__ __forceinline__ void store_regs(LbwState& s, const Regs& R, int lane) {
+  if (lane == 0) {
+    s.theta = R.theta; s.f = R.f; s.fold = R.fold; s.stp = R.stp; s.stpmx = R.stpmx; s.gd = R.gd; s.gdold = R.gdold;
+    s.dnorm = R.dnorm; s.dtd = R.dtd; s.sbgnrm = R.sbgnrm;
+    s.ls_ginit = R.ginit; s.ls_gtest = R.gtest; s.ls_gx = R.gx; s.ls_gy = R.gy; s.ls_finit = R.finit; s.ls_fx = R.fx;
+    s.ls_fy = R.fy; s.ls_stx = R.stx; s.ls_sty = R.sty; s.ls_stmin = R.stmin; s.ls_stmax = R.stmax;
+    s.ls_width = R.width; s.ls_width1 = R.width1;
+    s.col = R.col; s.head = R.head; s.ifun = R.ifun; s.iback = R.iback; s.ls_brackt = R.brackt; s.ls_stage = R.stage;
+    s.phase = R.phase; s.iter = R.iter; s.nfgv = R.nfgv; s.nskip = R.nskip; s.status = R.status;
+  }
+  __syncwarp();
 }
-__device__ __forceinline__ int bcast_flag(LbwState& s, int lane, int v) {
-  if (lane == 0) s.flag = v;
-  __syncwarp();
-  const int r = s.flag;
-  __syncwarp();
+
+// 1/x from the hardware seed and two Newton steps (<= 1 ulp; ~56 cycles against ~112 for the IEEE division)
+__device__ __forceinline__ double rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
   return r;
 }
-
-// (B v)_lane with v in shared memory; B symmetric so column `lane` is read (conflict-free)
-__device__ __forceinline__ double matvec_row(const LbwState& s, const double* v, int lane) {
-  double a = 0.0;
-  if (lane < s.n)
-    for (int j = 0; j < s.n; j++) a += s.B[j][lane] * v[j];
-  return a;
+// 1/sqrt(x), x > 0: hardware seed and two coupled Newton steps
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double h = 0.5 * r, g = x * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  h = fma(h, e, h);
+  return 2.0 * h;
 }
 
-__device__ __forceinline__ double projgr(const LbwState& s, int lane) {
+template <int NMAX>
+__device__ __forceinline__ void ldvec(const double* p, double (&v)[NMAX]) {
+#pragma unroll
+  for (int j = 0; j < NMAX; j += 2) {
+    const double2 q = *reinterpret_cast<const double2*>(p + j);
+    v[j] = q.x; v[j + 1] = q.y;
+  }
+}
+// every lane's `v` (zero for lanes >= n) into registers of all lanes
+template <int NMAX>
+__device__ __forceinline__ void gather(LbwState& s, int& slot, int lane, double v, double (&out)[NMAX]) {
+  double* b = s.scr[slot];
+  slot = (slot + 1) & (LBW_SCR - 1);
+  if (lane < NMAX) b[lane] = v;
+  __syncwarp();
+  ldvec<NMAX>(b, out);
+}
+template <int NMAX>
+__device__ __forceinline__ double vsum(const double (&v)[NMAX]) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int j = 0; j < NMAX; j += 4) { a0 += v[j]; a1 += v[j + 1]; a2 += v[j + 2]; a3 += v[j + 3]; }
+  return (a0 + a1) + (a2 + a3);
+}
+template <int NMAX>
+__device__ __forceinline__ double vdot(const double (&a)[NMAX], const double (&b)[NMAX]) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int j = 0; j < NMAX; j += 4) {
+    a0 = fma(a[j], b[j], a0); a1 = fma(a[j + 1], b[j + 1], a1);
+    a2 = fma(a[j + 2], b[j + 2], a2); a3 = fma(a[j + 3], b[j + 3], a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+template <int NMAX>
+__device__ __forceinline__ double allsum(LbwState& s, int& slot, int lane, double v) {
+  double t[NMAX];
+  gather<NMAX>(s, slot, lane, v, t);
+  return vsum<NMAX>(t);
+}
+
+struct StepIO { double stx, fx, dx, sty, fy, dy, stp; int brackt; };
+__device__ __noinline__ StepIO dcstep_ni(StepIO io, double fp, double dp, double stpmin, double stpmax) {
+  lb::dcstep(io.stx, io.fx, io.dx, io.sty, io.fy, io.dy, io.stp, fp, dp, io.brackt, stpmin, stpmax);
+  return io;
+}
+
+// dcsrch over the register copy of the line-search state (every lane, identical data).
+__device__ __forceinline__ int dcsrch(Regs& R, double f, double g, int start) {
+  const double ftol = 1.0e-3, gtol = 0.9, xtol = 0.1, stpmin = 0.0, stpmax = R.stpmx;
+  const double xtrapl = 1.1, xtrapu = 4.0;
+  if (start) {
+    if (R.stp < stpmin) return 4;
+    if (R.stp > stpmax) return 4;
+    if (g >= 0.0) return 4;
+    R.brackt = 0;
+    R.stage = 1;
+    R.finit = f;
+    R.ginit = g;
+    R.gtest = ftol * g;
+    R.width = stpmax - stpmin;
+    R.width1 = R.width / 0.5;
+    R.stx = 0.0; R.fx = f; R.gx = g;
+    R.sty = 0.0; R.fy = f; R.gy = g;
+    R.stmin = 0.0;
+    R.stmax = R.stp + xtrapu * R.stp;
+    return 1;
+  }
+  const double ftest = R.finit + R.stp * R.gtest;
+  if (R.stage == 1 && f <= ftest && g >= 0.0) R.stage = 2;
+  int ret = 1;
+  if (R.brackt && (R.stp <= R.stmin || R.stp >= R.stmax)) ret = 3;
+  if (R.brackt && R.stmax - R.stmin <= xtol * R.stmax) ret = 3;
+  if (R.stp == stpmax && f <= ftest && g <= R.gtest) ret = 3;
+  if (R.stp == stpmin && (f > ftest || g >= R.gtest)) ret = 3;
+  if (f <= ftest && fabs(g) <= gtol * (-R.ginit)) ret = 2;
+  if (ret != 1) return ret;
+  {
+    // ONE out-of-line dcstep (a fifth of the optimiser's code; only line-search continuations get here):
+    // the modified-function variant of stage 1 differs in its arguments only
+    const bool modified = (R.stage == 1 && f <= R.fx && f > ftest);
+    StepIO io;
+    io.stx = R.stx; io.sty = R.sty; io.stp = R.stp; io.brackt = R.brackt;
+    io.fx = R.fx; io.dx = R.gx; io.fy = R.fy; io.dy = R.gy;
+    double fp = f, dp = g;
+    if (modified) {
+      fp = f - R.stp * R.gtest;
+      io.fx = R.fx - R.stx * R.gtest;
+      io.fy = R.fy - R.sty * R.gtest;
+      dp = g - R.gtest;
+      io.dx = R.gx - R.gtest;
+      io.dy = R.gy - R.gtest;
+    }
+    io = dcstep_ni(io, fp, dp, R.stmin, R.stmax);
+    R.stx = io.stx; R.sty = io.sty; R.stp = io.stp; R.brackt = io.brackt;
+    if (modified) {
+      R.fx = io.fx + R.stx * R.gtest;
+      R.fy = io.fy + R.sty * R.gtest;
+      R.gx = io.dx + R.gtest;
+      R.gy = io.dy + R.gtest;
+    } else {
+      R.fx = io.fx; R.fy = io.fy; R.gx = io.dx; R.gy = io.dy;
+    }
+  }
+  if (R.brackt) {
+    if (fabs(R.sty - R.stx) >= 0.66 * R.width1) R.stp = R.stx + 0.5 * (R.sty - R.stx);
+    R.width1 = R.width;
+    R.width = fabs(R.sty - R.stx);
+  }
+  if (R.brackt) {
+    R.stmin = lb::dmin(R.stx, R.sty);
+    R.stmax = lb::dmax(R.stx, R.sty);
+  } else {
+    R.stmin = R.stp + xtrapl * (R.stp - R.stx);
+    R.stmax = R.stp + xtrapu * (R.stp - R.stx);
+  }
+  R.stp = lb::dmax(R.stp, stpmin);
+  R.stp = lb::dmin(R.stp, stpmax);
+  if ((R.brackt && (R.stp <= R.stmin || R.stp >= R.stmax)) || (R.brackt && R.stmax - R.stmin <= xtol * R.stmax))
+    R.stp = R.stx;
+  return 1;
+}
+
+// infinity norm of the projected gradient (lane-owned x, g, l, u)
+template <int NMAX>
+__device__ __forceinline__ double projgr(LbwState& s, int& slot, int lane, bool act, double xl, double gl, double ll,
+                                         double ul) {
   double v = 0.0;
-  if (lane < s.n) {
-    double gi = s.g[lane];
-    if (gi < 0.0) gi = lb::dmax(s.x[lane] - s.u[lane], gi);
-    else gi = lb::dmin(s.x[lane] - s.l[lane], gi);
+  if (act) {
+    double gi = gl;
+    if (gi < 0.0) gi = lb::dmax(xl - ul, gi);
+    else gi = lb::dmin(xl - ll, gi);
     v = fabs(gi);
   }
-  return wmax(v);
+  double t[NMAX];
+  gather<NMAX>(s, slot, lane, v, t);
+  double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < NMAX; j += 2) { m0 = lb::dmax(m0, t[j]); m1 = lb::dmax(m1, t[j + 1]); }
+  return lb::dmax(m0, m1);
 }
 
-// Column `lane` of B stays in registers across the col rank-2 updates (no shared-memory
-// round trip per pair); written back once.  NMAX (12 or 24) bounds the unrolled loops.
+// Row `lane` of the dense limited-memory matrix: theta*I followed by the stored rank-2 updates, oldest first.
 template <int NMAX>
-__device__ void rebuild_B_t(LbwState& s, int lane) {
-  const int n = s.n;
-  const bool act = lane < n;
-  double Bc[NMAX];
+__device__ __forceinline__ void rebuild_B(LbwState& s, const Regs& R, int& slot, int lane, bool act,
+                                          double (&Bc)[NMAX]) {
 #pragma unroll
-  for (int j = 0; j < NMAX; j++) Bc[j] = (j == lane) ? s.theta : 0.0;
-  for (int k = 0; k < s.col; k++) {
-    const double* sk = s.S[k];
-    const double* yk = s.Y[k];
-    double skv[NMAX];
+  for (int j = 0; j < NMAX; j++) Bc[j] = (act && j == lane) ? R.theta : 0.0;
+  // software-pipelined: the (s, y) rows of pair k + 1 are loaded while the dependent chain of pair k
+  // (B s -> gather -> s'Bs -> reciprocal -> rank-2 update) runs
+  double sk[NMAX], yk[NMAX];
+  int p = R.head;
+  ldvec<NMAX>(s.S[p], sk);
+  ldvec<NMAX>(s.Y[p], yk);
+  double ykl = (lane < NMAX) ? s.Y[p][lane] : 0.0, yi = s.ysinv[p];
+#pragma unroll 1
+  for (int k = 0; k < R.col; k++) {
+    p = (p + 1 == LB_M) ? 0 : p + 1;
+    double skn[NMAX], ykn[NMAX], bs[NMAX];
+    ldvec<NMAX>(s.S[p], skn);
+    ldvec<NMAX>(s.Y[p], ykn);
+    const double ykln = (lane < NMAX) ? s.Y[p][lane] : 0.0, yin = s.ysinv[p];
+    const double c1 = ykl * yi;
+    const double a = vdot<NMAX>(Bc, sk);                 // (B s_k)_lane
+    gather<NMAX>(s, slot, lane, a, bs);
+    const double sBs = vdot<NMAX>(sk, bs);
+    const double c2 = a * rcp(sBs);
 #pragma unroll
-    for (int j = 0; j < NMAX; j++) skv[j] = (j < n) ? sk[j] : 0.0;
-    // (B s_k)_lane, summed in the order of the single-thread statement
-    double a = 0.0;
+    for (int j = 0; j < NMAX; j++) Bc[j] = fma(-bs[j], c2, fma(yk[j], c1, Bc[j]));
 #pragma unroll
-    for (int j = 0; j < NMAX; j++) a += Bc[j] * skv[j];
-    if (!act) a = 0.0;
-    const double skl = act ? sk[lane] : 0.0, ykl = act ? yk[lane] : 0.0;
-    double p1 = skl * a, p2 = ykl * skl;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-      p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-    }
-    const double i1 = 1.0 / p1, i2 = 1.0 / p2;            // 1 / s'Bs, 1 / y's
-    const double c1 = ykl * i2, c2 = a * i1;
-    // entry (j, lane) += y_j y_lane / y's - (Bs)_j (Bs)_lane / s'Bs ; (Bs)_j from lane j
-#pragma unroll
-    for (int j = 0; j < NMAX; j++) {
-      const double bsj = __shfl_sync(0xffffffffu, a, j);
-      const double ykj = (j < n) ? yk[j] : 0.0;
-      Bc[j] += ykj * ykl * i2 - bsj * a * i1;
-    }
-    (void)c1; (void)c2;
+    for (int j = 0; j < NMAX; j++) { sk[j] = skn[j]; yk[j] = ykn[j]; }
+    ykl = ykln; yi = yin;
   }
-  __syncwarp();
-  if (act) {
-#pragma unroll
-    for (int j = 0; j < NMAX; j++)
-      if (j < n) s.B[j][lane] = Bc[j];
-  }
-  __syncwarp();
 }
 
-__device__ __forceinline__ void rebuild_B(LbwState& s, int lane) {
-  if (s.n <= 12) rebuild_B_t<12>(s, lane);
-  else rebuild_B_t<LB_NMAX>(s, lane);
-}
-
-__device__ __forceinline__ void reset_memory(LbwState& s, int lane) {
-  if (lane == 0) { s.col = 0; s.theta = 1.0; }
-  __syncwarp();
-  rebuild_B(s, lane);
-}
-
-// Generalised Cauchy point; result in s.z, s.iwhere updated.
-__device__ void cauchy(LbwState& s, int lane) {
-  const int n = s.n;
-  const bool act = lane < n;
-  if (s.sbgnrm <= 0.0) {
-    if (act) s.z[lane] = s.x[lane];
-    __syncwarp();
-    return;
-  }
-  double dd = 0.0, tb = 0.0, zfix = 0.0;
-  bool hasb = false;
-  if (act) {
-    const double neggi = -s.g[lane];
-    const double tl = s.x[lane] - s.l[lane], tu = s.u[lane] - s.x[lane];
-    const bool xlower = tl <= 0.0, xupper = tu <= 0.0;
-    int iw = 0;
-    if (xlower) { if (neggi <= 0.0) iw = 1; }
-    else if (xupper) { if (neggi >= 0.0) iw = 2; }
-    else { if (fabs(neggi) <= 0.0) iw = -3; }
-    s.iwhere[lane] = iw;
-    if (iw == 0) {
-      dd = neggi;
-      if (neggi < 0.0) { tb = tl / (-neggi); hasb = true; }
-      else if (neggi > 0.0) { tb = tu / neggi; hasb = true; }
-    }
-    s.z[lane] = s.x[lane];
-    s.dd[lane] = dd;
-  }
-  __syncwarp();
-  const int nbreak0 = __popc(__ballot_sync(0xffffffffu, hasb));
-  if (__ballot_sync(0xffffffffu, dd != 0.0) == 0u) return;
-
-  double f1 = -wsum(dd * dd);
-  double Bd = matvec_row(s, s.dd, lane);
-  double f2 = wsum(dd * Bd);
-  const double f2_org = -s.theta * f1;
-  double dtm = -f1 / f2, tsum = 0.0, tj = 0.0;
-  int nleft = nbreak0;
-  bool vertex = false;
-  const double gl = act ? s.g[lane] : 0.0;
-  while (nleft > 0) {
-    // smallest remaining break point, lowest index on ties
-    double bt = hasb ? tb : INFINITY;
-    int bi = hasb ? lane : 64;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ot < bt || (ot == bt && oi < bi)) { bt = ot; bi = oi; }
-    }
-    const double tj0 = tj;
-    tj = bt;
-    const double dt = tj - tj0;
-    if (dtm < dt) break;
-    tsum += dt;
-    nleft--;
-    if (lane == bi) {
-      hasb = false;
-      const double dibp = dd;
-      dd = 0.0;
-      if (dibp > 0.0) { zfix = s.u[lane] - s.x[lane]; s.z[lane] = s.u[lane]; s.iwhere[lane] = 2; }
-      else { zfix = s.l[lane] - s.x[lane]; s.z[lane] = s.l[lane]; s.iwhere[lane] = 1; }
-      s.dd[lane] = 0.0;
-    }
-    __syncwarp();
-    if (nleft == 0 && nbreak0 == n) { dtm = dt; vertex = true; break; }
-    const double zc = (dd != 0.0) ? tsum * dd : zfix;
-    Bd = matvec_row(s, s.dd, lane);
-    f1 = wsum(gl * dd + zc * Bd);
-    f2 = wsum(dd * Bd);
-    f2 = lb::dmax(LB_EPSMCH * f2_org, f2);
-    if (nleft > 0) dtm = -f1 / f2;
-    else dtm = 0.0;
-  }
-  if (!vertex) {
-    if (dtm <= 0.0) dtm = 0.0;
-    tsum += dtm;
-    if (act) s.z[lane] += tsum * dd;
-  }
-  __syncwarp();
-}
-
-// Cholesky solve of the free-variable block (lane = row).  Returns false if not PD.
-__device__ bool solve_free(LbwState& s, int nsub, int lane) {
-  const bool act = lane < nsub;
-  if (act) {
-    const int ka = s.ind[lane];
-    for (int b = 0; b <= lane; b++) s.Wk[lane][b] = s.B[s.ind[b]][ka];
-  }
-  __syncwarp();
-  bool ok = true;
-  for (int k = 0; k < nsub; k++) {
-    double v = 0.0;
-    if (act && lane >= k) {
-      v = s.Wk[lane][k];
-      for (int q = 0; q < k; q++) v -= s.Wk[lane][q] * s.Wk[k][q];
-    }
-    const double pk = __shfl_sync(0xffffffffu, v, k);
-    if (!(pk > 0.0)) { ok = false; break; }
-    const double rp = rsqrt(pk);                 // 1 / L_kk
-    if (act && lane == k) { s.Wk[k][k] = pk * rp; s.xp[k] = rp; }
-    else if (act && lane > k) s.Wk[lane][k] = v * rp;
-    __syncwarp();
-  }
-  if (!ok) return false;
-  // forward substitution (column oriented; same subtraction order per row as the scalar code)
-  double v = act ? s.rr[lane] : 0.0;
-  for (int q = 0; q < nsub; q++) {
-    double o = 0.0;
-    if (lane == q) o = v * s.xp[q];
-    o = __shfl_sync(0xffffffffu, o, q);
-    if (lane == q) v = o;
-    else if (act && lane > q) v -= s.Wk[lane][q] * o;
-  }
-  // back substitution with L^T
-  for (int i = nsub - 1; i >= 0; i--) {
-    double o = 0.0;
-    if (lane == i) o = v * s.xp[i];
-    o = __shfl_sync(0xffffffffu, o, i);
-    if (lane == i) v = o;
-    else if (act && lane < i) v -= s.Wk[i][lane] * o;
-  }
-  if (act) s.dsub[lane] = v;
-  __syncwarp();
-  return true;
-}
-
-// Subspace minimisation with the v3.0 projection step.  s.z: Cauchy point in, minimiser out.
-__device__ bool subsm(LbwState& s, int lane) {
-  const int n = s.n;
-  const bool act = lane < n;
-  const bool freev = act && s.iwhere[lane] <= 0;
-  const unsigned fm = __ballot_sync(0xffffffffu, freev);
-  const int nsub = __popc(fm);
-  if (nsub == 0 || s.col == 0) return true;
-  const int pos = __popc(fm & ((1u << lane) - 1u));
-  if (freev) s.ind[pos] = lane;
-  if (act) s.xp[lane] = s.z[lane] - s.x[lane];       // zc
-  __syncwarp();
-  if (lane < nsub) {
-    const int k = s.ind[lane];
-    double v = 0.0;
-    for (int j = 0; j < n; j++) v += s.B[j][k] * s.xp[j];
-    s.rr[lane] = -(s.g[k] + v);
-  }
-  __syncwarp();
-  if (!solve_free(s, nsub, lane)) return false;
-  // projection step: every free lane clamps its own variable; the rare back-tracking branch
-  // (a clamp was active AND the projected direction is not a descent direction) keeps the
-  // exact sequential rule on lane 0
-  const double zl = act ? s.z[lane] : 0.0;
-  double znew = zl;
-  bool hit = false;
-  if (freev) {
-    double xk = lb::dmax(s.l[lane], zl + s.dsub[pos]);
-    xk = lb::dmin(s.u[lane], xk);
-    znew = xk;
-    hit = (xk == s.l[lane] || xk == s.u[lane]);
-  }
-  if (__ballot_sync(0xffffffffu, hit) == 0u) {
-    if (freev) s.z[lane] = znew;
-    __syncwarp();
-    return true;
-  }
-  const double dd_p = wsum(act ? (znew - s.x[lane]) * s.g[lane] : 0.0);
-  if (!(dd_p > 0.0)) {
-    if (freev) s.z[lane] = znew;
-    __syncwarp();
-    return true;
-  }
-  if (lane == 0) {
-    // z still holds the Cauchy point here
-    double alpha = 1.0, temp1 = 1.0;
-    int ibd = -1;
-    for (int a = 0; a < nsub; a++) {
-      const int k = s.ind[a];
-      const double dk = s.dsub[a];
+// Back-tracking branch of the v3.0 projection step (subsm): the sequential rule of the published code over
+// the free variables in index order, on shared-memory copies; identical in every lane.  Returns alpha.
+__device__ __noinline__ double project_backtrack(const LbwState& s, const double* dv, const double* zv, unsigned fm,
+                                                 int n, int* ibd_out) {
+  double alpha = 1.0, temp1 = 1.0;
+  int ibd = -1;
+  for (int a = 0; a < n; a++) {
+    if ((fm >> a) & 1u) {
+      const double dk = dv[a];
       if (dk < 0.0) {
-        const double temp2 = s.l[k] - s.z[k];
+        const double temp2 = s.l[a] - zv[a];
         if (temp2 >= 0.0) temp1 = 0.0;
         else if (dk * alpha < temp2) temp1 = temp2 / dk;
       } else if (dk > 0.0) {
-        const double temp2 = s.u[k] - s.z[k];
+        const double temp2 = s.u[a] - zv[a];
         if (temp2 <= 0.0) temp1 = 0.0;
         else if (dk * alpha > temp2) temp1 = temp2 / dk;
       }
       if (temp1 < alpha) { alpha = temp1; ibd = a; }
     }
-    if (alpha < 1.0) {
-      const double dk = s.dsub[ibd];
-      const int k = s.ind[ibd];
-      if (dk > 0.0) { s.z[k] = s.u[k]; s.dsub[ibd] = 0.0; }
-      else if (dk < 0.0) { s.z[k] = s.l[k]; s.dsub[ibd] = 0.0; }
-    }
-    for (int a = 0; a < nsub; a++) s.z[s.ind[a]] += alpha * s.dsub[a];
   }
-  __syncwarp();
-  return true;
+  *ibd_out = ibd;
+  return alpha;
 }
 
-// dcsrch on lane 0 over the shared state (same code path as the scalar optimiser).
-__device__ __forceinline__ int dcsrch_lane0(LbwState& s, double f, double g, int start) {
-  const double ftol = 1.0e-3, gtol = 0.9, xtol = 0.1, stpmin = 0.0, stpmax = s.stpmx;
-  const double xtrapl = 1.1, xtrapu = 4.0;
-  if (start) {
-    if (s.stp < stpmin) return 4;
-    if (s.stp > stpmax) return 4;
-    if (g >= 0.0) return 4;
-    s.ls_brackt = 0;
-    s.ls_stage = 1;
-    s.ls_finit = f;
-    s.ls_ginit = g;
-    s.ls_gtest = ftol * g;
-    s.ls_width = stpmax - stpmin;
-    s.ls_width1 = s.ls_width / 0.5;
-    s.ls_stx = 0.0; s.ls_fx = f; s.ls_gx = g;
-    s.ls_sty = 0.0; s.ls_fy = f; s.ls_gy = g;
-    s.ls_stmin = 0.0;
-    s.ls_stmax = s.stp + xtrapu * s.stp;
-    return 1;
-  }
-  const double ftest = s.ls_finit + s.stp * s.ls_gtest;
-  if (s.ls_stage == 1 && f <= ftest && g >= 0.0) s.ls_stage = 2;
-  int ret = 1;
-  if (s.ls_brackt && (s.stp <= s.ls_stmin || s.stp >= s.ls_stmax)) ret = 3;
-  if (s.ls_brackt && s.ls_stmax - s.ls_stmin <= xtol * s.ls_stmax) ret = 3;
-  if (s.stp == stpmax && f <= ftest && g <= s.ls_gtest) ret = 3;
-  if (s.stp == stpmin && (f > ftest || g >= s.ls_gtest)) ret = 3;
-  if (f <= ftest && fabs(g) <= gtol * (-s.ls_ginit)) ret = 2;
-  if (ret != 1) return ret;
-  if (s.ls_stage == 1 && f <= s.ls_fx && f > ftest) {
-    const double fm = f - s.stp * s.ls_gtest;
-    double fxm = s.ls_fx - s.ls_stx * s.ls_gtest;
-    double fym = s.ls_fy - s.ls_sty * s.ls_gtest;
-    const double gm = g - s.ls_gtest;
-    double gxm = s.ls_gx - s.ls_gtest;
-    double gym = s.ls_gy - s.ls_gtest;
-    lb::dcstep(s.ls_stx, fxm, gxm, s.ls_sty, fym, gym, s.stp, fm, gm, s.ls_brackt, s.ls_stmin, s.ls_stmax);
-    s.ls_fx = fxm + s.ls_stx * s.ls_gtest;
-    s.ls_fy = fym + s.ls_sty * s.ls_gtest;
-    s.ls_gx = gxm + s.ls_gtest;
-    s.ls_gy = gym + s.ls_gtest;
-  } else {
-    lb::dcstep(s.ls_stx, s.ls_fx, s.ls_gx, s.ls_sty, s.ls_fy, s.ls_gy, s.stp, f, g, s.ls_brackt, s.ls_stmin,
-               s.ls_stmax);
-  }
-  if (s.ls_brackt) {
-    if (fabs(s.ls_sty - s.ls_stx) >= 0.66 * s.ls_width1) s.stp = s.ls_stx + 0.5 * (s.ls_sty - s.ls_stx);
-    s.ls_width1 = s.ls_width;
-    s.ls_width = fabs(s.ls_sty - s.ls_stx);
-  }
-  if (s.ls_brackt) {
-    s.ls_stmin = lb::dmin(s.ls_stx, s.ls_sty);
-    s.ls_stmax = lb::dmax(s.ls_stx, s.ls_sty);
-  } else {
-    s.ls_stmin = s.stp + xtrapl * (s.stp - s.ls_stx);
-    s.ls_stmax = s.stp + xtrapu * (s.stp - s.ls_stx);
-  }
-  s.stp = lb::dmax(s.stp, stpmin);
-  s.stp = lb::dmin(s.stp, stpmax);
-  if ((s.ls_brackt && (s.stp <= s.ls_stmin || s.stp >= s.ls_stmax)) ||
-      (s.ls_brackt && s.ls_stmax - s.ls_stmin <= xtol * s.ls_stmax))
-    s.stp = s.ls_stx;
-  return 1;
-}
-
-// Start a new iteration (Cauchy point, subspace step, first entry of the line search).
-__device__ __noinline__ int new_iteration(LbwState& s, int lane) {
+// One iteration start: rebuild B, generalised Cauchy point, subspace minimisation (v3.0 projection step),
+// first entry of the line search.  xl / gl: the lane's current iterate and gradient (s.g holds g).
+template <int NMAX>
+__device__ __forceinline__ int new_iteration(LbwState& s, Regs& R, int& slot, int lane, double xl, double gl) {
   const int n = s.n;
   const bool act = lane < n;
+  const double ll = act ? s.l[lane] : 0.0, ul = act ? s.u[lane] : 0.0;
+  LBW_T0();
+#pragma unroll 1
   for (int guard = 0; guard < 4; guard++) {
-    LBW_T0();
-    cauchy(s, lane);
-    LBW_MARK(1);
-    const int nfree = __popc(__ballot_sync(0xffffffffu, act && s.iwhere[lane] <= 0));
-    bool ok = true;
-    if (nfree > 0 && s.col > 0) ok = subsm(s, lane);
-    LBW_MARK(2);
-    if (!ok) { reset_memory(s, lane); continue; }
-    const double dl = act ? s.z[lane] - s.x[lane] : 0.0;
-    const double gl = act ? s.g[lane] : 0.0;
-    const double dtd = wsum(dl * dl);
-    const double gd = wsum(gl * dl);
-    // stpmx: the sequential rule is a running minimum of the per-variable bound ratios
-    double stpmx = 1.0e10;
-    if (s.iter == 0) stpmx = 1.0;
-    else {
-      // every lane forms its bound ratio (the divisions run in parallel); lane 0 then applies the
-      // exact sequential rule of lnsrlb (the comparison uses the running value)
-      double a2 = 0.0, ratio = 0.0;
+    double Bc[NMAX];
+    rebuild_B<NMAX>(s, R, slot, lane, act, Bc);
+    LBW_MARK(0);
+    // ---- generalised Cauchy point
+    double zl = xl;
+    int iw = 0;
+    if (R.sbgnrm > 0.0) {
+      double dd = 0.0, tb = 0.0, zfix = 0.0;
+      bool hasb = false;
       if (act) {
-        a2 = (dl < 0.0) ? s.l[lane] - s.x[lane] : s.u[lane] - s.x[lane];
-        ratio = (dl != 0.0) ? a2 / dl : 0.0;
-        s.d[lane] = dl; s.dd[lane] = a2; s.tb[lane] = ratio;
+        const double neggi = -gl;
+        const double tl = xl - ll, tu = ul - xl;
+        const bool xlower = tl <= 0.0, xupper = tu <= 0.0;
+        if (xlower) { if (neggi <= 0.0) iw = 1; }
+        else if (xupper) { if (neggi >= 0.0) iw = 2; }
+        else { if (fabs(neggi) <= 0.0) iw = -3; }
+        if (iw == 0) {
+          dd = neggi;
+          if (neggi < 0.0) { tb = tl / (-neggi); hasb = true; }
+          else if (neggi > 0.0) { tb = tu / neggi; hasb = true; }
+        }
       }
-      __syncwarp();
-      if (lane == 0) {
-        double m = 1.0e10;
-        for (int i = 0; i < n; i++) {
-          const double a1 = s.d[i], b2 = s.dd[i];
-          if (a1 < 0.0) {
-            if (b2 >= 0.0) m = 0.0;
-            else if (a1 * m < b2) m = s.tb[i];
-          } else if (a1 > 0.0) {
-            if (b2 <= 0.0) m = 0.0;
-            else if (a1 * m > b2) m = s.tb[i];
+      const int nbreak0 = __popc(__ballot_sync(0xffffffffu, hasb));
+      if (__ballot_sync(0xffffffffu, dd != 0.0) != 0u) {
+        double ddv[NMAX], tmp[NMAX];
+        gather<NMAX>(s, slot, lane, dd, ddv);
+        double f1 = -vdot<NMAX>(ddv, ddv);
+        double Bd = vdot<NMAX>(Bc, ddv);
+        double f2 = allsum<NMAX>(s, slot, lane, dd * Bd);
+        const double f2_org = -R.theta * f1;
+        double dtm = -f1 / f2, tsum = 0.0, tj = 0.0;
+        int nleft = nbreak0;
+        bool vertex = false;
+        while (nleft > 0) {
+          // smallest remaining break point, lowest index on ties
+          gather<NMAX>(s, slot, lane, hasb ? tb : INFINITY, tmp);
+          double bt = INFINITY;
+          int bi = -1;
+#pragma unroll
+          for (int j = 0; j < NMAX; j++)
+            if (tmp[j] < bt) { bt = tmp[j]; bi = j; }
+          if (bi < 0) break;                               // cannot happen (nleft counts the finite entries)
+          const double tj0 = tj;
+          tj = bt;
+          const double dt = tj - tj0;
+          if (dtm < dt) break;
+          tsum += dt;
+          nleft--;
+          if (lane == bi) {
+            hasb = false;
+            const double dibp = dd;
+            dd = 0.0;
+            if (dibp > 0.0) { zfix = ul - xl; zl = ul; iw = 2; }
+            else { zfix = ll - xl; zl = ll; iw = 1; }
+          }
+          if (nleft == 0 && nbreak0 == n) { dtm = dt; vertex = true; break; }
+          const double zc = (dd != 0.0) ? tsum * dd : zfix;
+          gather<NMAX>(s, slot, lane, dd, ddv);
+          Bd = vdot<NMAX>(Bc, ddv);
+          f1 = allsum<NMAX>(s, slot, lane, gl * dd + zc * Bd);
+          f2 = allsum<NMAX>(s, slot, lane, dd * Bd);
+          f2 = lb::dmax(LB_EPSMCH * f2_org, f2);
+          if (nleft > 0) dtm = -f1 / f2;
+          else dtm = 0.0;
+        }
+        if (!vertex) {
+          if (dtm <= 0.0) dtm = 0.0;
+          tsum += dtm;
+          if (act) zl += tsum * dd;
+        }
+      }
+    }
+    LBW_MARK(1);
+    // ---- subspace minimisation over the free variables
+    const bool freev = act && iw <= 0;
+    const unsigned fm = __ballot_sync(0xffffffffu, freev);
+    bool ok = true;
+    if (fm != 0u && R.col > 0) {
+      double tmp[NMAX];
+      gather<NMAX>(s, slot, lane, act ? zl - xl : 0.0, tmp);
+      const double rr = freev ? -(gl + vdot<NMAX>(Bc, tmp)) : 0.0;
+      // Cholesky of the full matrix with identity rows / columns at the fixed variables, right-looking,
+      // row `lane` in registers; the forward substitution rides along in `y`
+      double w[NMAX];
+#pragma unroll
+      for (int j = 0; j < NMAX; j++) w[j] = (freev && ((fm >> j) & 1u)) ? Bc[j] : ((j == lane) ? 1.0 : 0.0);
+      double y = rr, my_rp = 1.0;
+#pragma unroll
+      for (int k = 0; k < NMAX; k++) {
+        if (k < n && ok) {
+          // the pivot travels by shuffle so that its reciprocal square root starts while the rest of the
+          // column is gathered
+          const double pk = __shfl_sync(0xffffffffu, w[k], k);
+          double colk[NMAX];
+          gather<NMAX>(s, slot, lane, w[k], colk);         // A[j][k] from lane j (valid for j >= k)
+          if (!(pk > 0.0)) ok = false;
+          else {
+            const double rp = rsqrt_pos(pk);
+            const double lk = w[k] * rp;                   // L[lane][k] (lane >= k); lane k: sqrt(pk)
+            if (lane == k) my_rp = rp;
+            if (lane >= k && lane < NMAX) s.L[lane][k] = lk;
+            const double yk = __shfl_sync(0xffffffffu, y, k) * rp;
+            if (lane == k) y = yk;
+            else if (lane > k) y = fma(-lk, yk, y);
+#pragma unroll
+            for (int j = k + 1; j < NMAX; j++) w[j] = fma(-lk, colk[j] * rp, w[j]);
           }
         }
-        s.stpmx = m;
       }
+      if (ok) {
+        __syncwarp();
+        double lt[NMAX];                                    // column `lane` of L: L[q][lane], q > lane
+#pragma unroll
+        for (int q = 0; q < NMAX; q++) lt[q] = (lane < NMAX && q < n) ? s.L[q][lane < NMAX ? lane : 0] : 0.0;
+#pragma unroll
+        for (int q = NMAX - 1; q >= 0; q--) {
+          if (q < n) {
+            const double xq = __shfl_sync(0xffffffffu, y * my_rp, q);
+            if (lane == q) y = xq;
+            else if (lane < q) y = fma(-lt[q], xq, y);
+          }
+        }
+        const double dsub = freev ? y : 0.0;
+        // projection step: every free lane clamps its own variable; the rare back-tracking branch (a
+        // clamp was active AND the projected direction is not a descent direction) applies the
+        // sequential rule of the published code on gathered copies, identically in every lane
+        double znew = zl;
+        bool hit = false;
+        if (freev) {
+          double xk = lb::dmax(ll, zl + dsub);
+          xk = lb::dmin(ul, xk);
+          znew = xk;
+          hit = (xk == ll || xk == ul);
+        }
+        if (__ballot_sync(0xffffffffu, hit) == 0u) zl = znew;
+        else {
+          const double dd_p = allsum<NMAX>(s, slot, lane, act ? (znew - xl) * gl : 0.0);
+          if (!(dd_p > 0.0)) zl = znew;
+          else {
+            // (out of line: rare, and a fifth of this function's code when unrolled in place)
+            double* dvs = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+            double* zvs = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+            if (lane < NMAX) { dvs[lane] = dsub; zvs[lane] = act ? zl : 0.0; }
+            __syncwarp();
+            int ibd = -1;
+            const double alpha = project_backtrack(s, dvs, zvs, fm, n, &ibd);
+            double dmine = dsub;
+            if (alpha < 1.0 && lane == ibd) {
+              if (dsub > 0.0) { zl = ul; dmine = 0.0; }
+              else if (dsub < 0.0) { zl = ll; dmine = 0.0; }
+            }
+            if (freev) zl += alpha * dmine;
+          }
+        }
+      }
+    }
+    LBW_MARK(2);
+    if (!ok) {                                              // non-PD reduced matrix: refresh memory, retry
+      R.col = 0; R.head = 0; R.theta = 1.0;
+      continue;
+    }
+    // ---- lnsrlb, first entry
+    const double dl = act ? zl - xl : 0.0;
+    // every lane forms its bound ratio for stpmx (the divisions run in parallel); ONE exchange for d, the
+    // bound distances and the ratios
+    double a2 = 0.0, ratio = 0.0;
+    if (act && R.iter != 0) {
+      a2 = (dl < 0.0) ? ll - xl : ul - xl;
+      ratio = (dl != 0.0) ? a2 / dl : 0.0;
+    }
+    double dv[NMAX], gv[NMAX], a2v[NMAX], rv[NMAX];
+    {
+      double* b0 = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+      double* b1 = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+      double* b2 = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+      if (lane < NMAX) { b0[lane] = dl; b1[lane] = a2; b2[lane] = ratio; }
       __syncwarp();
-      stpmx = s.stpmx;
+      ldvec<NMAX>(b0, dv);
+      ldvec<NMAX>(b1, a2v);
+      ldvec<NMAX>(b2, rv);
     }
-    if (act) { s.d[lane] = dl; s.t[lane] = s.x[lane]; s.r[lane] = s.g[lane]; }
-    int code = 0;      // 0: evaluate, 1: abnormal done, 2: reset and retry
-    if (lane == 0) {
-      s.dtd = dtd;
-      s.dnorm = sqrt(dtd);
-      s.stpmx = stpmx;
-      s.stp = 1.0;
-      s.fold = s.f;
-      s.ifun = 0;
-      s.iback = 0;
-      s.gd = gd;
-      s.gdold = gd;
-      if (!(gd >= 0.0)) (void)dcsrch_lane0(s, s.f, gd, 1);
-      if (gd >= 0.0) {
-        if (s.col == 0) { s.status = LB_ABNORMAL; code = 1; }
-        else code = 2;
-      } else {
-        s.ifun = 1;
-        s.nfgv += 1;
-        s.iback = 0;
-        s.phase = 1;
+    ldvec<NMAX>(s.g, gv);
+    const double dtd = vdot<NMAX>(dv, dv);
+    const double gd = vdot<NMAX>(gv, dv);
+    double stpmx = 1.0e10;
+    if (R.iter == 0) stpmx = 1.0;
+    else {
+      // the running rule of lnsrlb in index order on the gathered values
+      double m = 1.0e10;
+#pragma unroll
+      for (int i = 0; i < NMAX; i++) {
+        const double a1 = dv[i], b2 = a2v[i];
+        if (a1 < 0.0) {
+          if (b2 >= 0.0) m = 0.0;
+          else if (a1 * m < b2) m = rv[i];
+        } else if (a1 > 0.0) {
+          if (b2 <= 0.0) m = 0.0;
+          else if (a1 * m > b2) m = rv[i];
+        }
       }
+      stpmx = m;
     }
-    code = bcast_flag(s, lane, code);
-    LBW_MARK(3);
-    if (code == 1) return LB_DONE;
-    if (code == 2) { reset_memory(s, lane); continue; }
+    R.dtd = dtd;
+    R.dnorm = sqrt(dtd);
+    R.stpmx = stpmx;
+    R.stp = 1.0;
+    R.fold = R.f;
+    R.ifun = 0;
+    R.iback = 0;
+    R.gd = gd;
+    R.gdold = gd;
+    if (!(gd >= 0.0)) (void)dcsrch(R, R.f, gd, 1);
+    if (gd >= 0.0) {
+      if (R.col == 0) {
+        R.status = LB_ABNORMAL;
+        LBW_MARK(3);
+        return LB_DONE;
+      }
+      R.col = 0; R.head = 0; R.theta = 1.0;
+      continue;
+    }
+    R.ifun = 1;
+    R.nfgv += 1;
+    R.iback = 0;
+    R.phase = 1;
     if (act) {
-      if (s.stp == 1.0) s.x[lane] = s.z[lane];
-      else s.x[lane] = s.stp * s.d[lane] + s.t[lane];
+      s.d[lane] = dl; s.t[lane] = xl; s.r[lane] = gl; s.z[lane] = zl;
+      s.x[lane] = (R.stp == 1.0) ? zl : R.stp * dl + xl;
     }
-    __syncwarp();
+    LBW_MARK(3);
     return LB_EVAL;
   }
-  if (lane == 0) s.status = LB_ERROR;
-  __syncwarp();
+  R.status = LB_ERROR;
   return LB_DONE;
 }
 
@@ -505,16 +554,23 @@ __device__ __noinline__ int new_iteration(LbwState& s, int lane) {
 
 // All 32 lanes of one warp call these with identical arguments.
 __device__ inline void lbw_init(LbwState& s, int n, const double* x0, const double* l, const double* u, int lane) {
+  {
+    double* p = reinterpret_cast<double*>(&s);
+    const int nd = (int)(offsetof(LbwState, theta) / sizeof(double));
+    for (int i = lane; i < nd; i += 32) p[i] = 0.0;
+  }
+  __syncwarp();
   if (lane == 0) {
     s.n = n;
-    s.factr = 1.0e7; s.pgtol = 1.0e-5; s.maxiter = 15000; s.maxfun = 15000; s.maxls = 20;
-    s.col = 0; s.theta = 1.0;
+    s.col = 0; s.head = 0; s.theta = 1.0;
     s.iter = 0; s.nfgv = 0; s.nskip = 0; s.phase = 0; s.status = LB_ERROR;
+    s.ifun = 0; s.iback = 0;
     s.ls_brackt = 0; s.ls_stage = 1;
     s.ls_ginit = s.ls_gtest = s.ls_gx = s.ls_gy = s.ls_finit = s.ls_fx = s.ls_fy = 0.0;
     s.ls_stx = s.ls_sty = s.ls_stmin = s.ls_stmax = s.ls_width = s.ls_width1 = 0.0;
     s.stp = 1.0; s.stpmx = 1.0; s.gd = s.gdold = 0.0; s.f = s.fold = s.f_last = 0.0;
-    s.sbgnrm = 0.0; s.flag = 0;
+    s.dnorm = s.dtd = 0.0;
+    s.sbgnrm = 0.0;
   }
   if (lane < n) {
     s.l[lane] = l[lane]; s.u[lane] = u[lane];
@@ -522,110 +578,105 @@ __device__ inline void lbw_init(LbwState& s, int n, const double* x0, const doub
     if (v < l[lane]) v = l[lane];
     if (v > u[lane]) v = u[lane];
     s.x[lane] = v;
-    s.iwhere[lane] = 0;
   }
   __syncwarp();
-  lbw::rebuild_B(s, lane);
 }
 
+template <int NMAX>
 __device__ __noinline__ int lbw_feed(LbwState& s, double f, const double* g, int lane) {
   const int n = s.n;
   const bool act = lane < n;
+  const double factr = 1.0e7, pgtol = 1.0e-5;
+  const int maxiter = 15000, maxfun = 15000, maxls = 20;
   LBW_T0();
-  if (lane == 0) { s.f = f; s.f_last = f; }
-  if (act) s.g[lane] = g[lane];
+  lbw::Regs R;
+  lbw::load_regs(s, R);
+  int slot = 0;
+  double gl = act ? g[lane] : 0.0;
+  double xl = act ? s.x[lane] : 0.0;
+  const double ll = act ? s.l[lane] : 0.0, ul = act ? s.u[lane] : 0.0;
+  if (act) s.g[lane] = gl;
+  if (lane == 0) s.f_last = f;
+  R.f = f;
   __syncwarp();
-  if (s.phase == 0) {
-    const double nrm = lbw::projgr(s, lane);
-    int done = 0;
-    if (lane == 0) {
-      s.nfgv = 1;
-      s.sbgnrm = nrm;
-      if (nrm <= s.pgtol) { s.status = LB_CONV_PGTOL; done = 1; }
-    }
-    done = lbw::bcast_flag(s, lane, done);
-    if (done) return LB_DONE;
-    return lbw::new_iteration(s, lane);
-  }
-  // ---- inside the line search
-  const double gd = lbw::wsum(act ? s.g[lane] * s.d[lane] : 0.0);
-  int code = 0;   // 0: another trial point, 1: done (abnormal), 2: reset + new iteration, 3: NEW_X
-  if (lane == 0) {
-    s.gd = gd;
-    const int lsret = lbw::dcsrch_lane0(s, f, gd, 0);
-    if (lsret != 2 && lsret != 3) {
-      s.ifun += 1;
-      s.nfgv += 1;
-      s.iback = s.ifun - 1;
-      if (s.iback >= s.maxls) {
-        for (int i = 0; i < n; i++) { s.x[i] = s.t[i]; s.g[i] = s.r[i]; }
-        s.f = s.fold;
-        s.nfgv -= 1;
-        if (s.col == 0) { s.iter += 1; s.status = LB_ABNORMAL; code = 1; }
-        else code = 2;
-      }
-    } else code = 3;
-  }
-  code = lbw::bcast_flag(s, lane, code);
-  if (code == 1) return LB_DONE;
-  if (code == 2) { lbw::reset_memory(s, lane); return lbw::new_iteration(s, lane); }
-  if (code == 0) {
-    if (act) {
-      if (s.stp == 1.0) s.x[lane] = s.z[lane];
-      else s.x[lane] = s.stp * s.d[lane] + s.t[lane];
-    }
-    __syncwarp();
-    return LB_EVAL;
-  }
-  // ---- NEW_X
-  const double nrm = lbw::projgr(s, lane);
-  const double rl = act ? s.g[lane] - s.r[lane] : 0.0;
-  const double rr = lbw::wsum(rl * rl);
-  int done = 0, store = 0;
-  if (lane == 0) {
-    s.iter += 1;
-    s.sbgnrm = nrm;
-    if (s.iter >= s.maxiter) { s.status = LB_STOP_MAXITER; done = 1; }
-    else if (s.nfgv > s.maxfun) { s.status = LB_STOP_MAXFUN; done = 1; }
-    else if (nrm <= s.pgtol) { s.status = LB_CONV_PGTOL; done = 1; }
-    else {
-      const double ddum0 = lb::dmax(fabs(s.fold), lb::dmax(fabs(s.f), 1.0));
-      if ((s.fold - s.f) <= LB_EPSMCH * s.factr * ddum0) { s.status = LB_CONV_FACTR; done = 1; }
-    }
-    if (!done) {
-      double dr, ddum;
-      if (s.stp == 1.0) { dr = s.gd - s.gdold; ddum = -s.gdold; }
-      else { dr = (s.gd - s.gdold) * s.stp; ddum = -s.gdold * s.stp; }
-      if (dr <= LB_EPSMCH * ddum) s.nskip += 1;
-      else {
-        store = 1;
-        if (s.col == LB_M) store = 2;      // drop the oldest pair first
-        s.theta = rr / dr;
-      }
-    }
-  }
-  done = lbw::bcast_flag(s, lane, done ? 1 : (store ? 2 + store : 0));
-  if (done == 1) return LB_DONE;
-  if (act) {
-    s.r[lane] = rl;
-    if (s.stp != 1.0) s.d[lane] *= s.stp;
-  }
-  if (done >= 3) {
-    if (done == 4) {
-      if (act)
-        for (int k = 0; k + 1 < LB_M; k++) { s.S[k][lane] = s.S[k + 1][lane]; s.Y[k][lane] = s.Y[k + 1][lane]; }
-      if (lane == 0) s.col = LB_M - 1;
-      __syncwarp();
-    }
-    if (act) { s.S[s.col][lane] = s.d[lane]; s.Y[s.col][lane] = rl; }
-    __syncwarp();
-    if (lane == 0) s.col += 1;
-    __syncwarp();
-    LBW_MARK(4);
-    lbw::rebuild_B(s, lane);
-    LBW_MARK(0);
+  int rc = LB_DONE;
+  bool iterate = false;                     // start a new iteration (ONE call site of new_iteration)
+  if (R.phase == 0) {
+    R.nfgv = 1;
+    R.sbgnrm = lbw::projgr<NMAX>(s, slot, lane, act, xl, gl, ll, ul);
+    if (R.sbgnrm <= pgtol) R.status = LB_CONV_PGTOL;
+    else iterate = true;
   } else {
-    __syncwarp();
+    // ---- inside the line search
+    double dvv[NMAX], gvv[NMAX];
+    lbw::ldvec<NMAX>(s.d, dvv);
+    lbw::ldvec<NMAX>(s.g, gvv);
+    const double gd = lbw::vdot<NMAX>(gvv, dvv);
+    R.gd = gd;
+    const int lsret = lbw::dcsrch(R, f, gd, 0);
+    if (lsret != 2 && lsret != 3) {
+      R.ifun += 1;
+      R.nfgv += 1;
+      R.iback = R.ifun - 1;
+      if (R.iback >= maxls) {
+        // line search failed: restore the previous iterate
+        xl = act ? s.t[lane] : 0.0;
+        gl = act ? s.r[lane] : 0.0;
+        if (act) { s.x[lane] = xl; s.g[lane] = gl; }
+        __syncwarp();
+        R.f = R.fold;
+        R.nfgv -= 1;
+        if (R.col == 0) { R.iter += 1; R.status = LB_ABNORMAL; }
+        else { R.col = 0; R.head = 0; R.theta = 1.0; iterate = true; }
+      } else {
+        if (act) s.x[lane] = (R.stp == 1.0) ? s.z[lane] : R.stp * s.d[lane] + s.t[lane];
+        rc = LB_EVAL;
+      }
+    } else {
+      // ---- NEW_X
+      R.iter += 1;
+      R.sbgnrm = lbw::projgr<NMAX>(s, slot, lane, act, xl, gl, ll, ul);
+      bool done = false;
+      if (R.iter >= maxiter) { R.status = LB_STOP_MAXITER; done = true; }
+      else if (R.nfgv > maxfun) { R.status = LB_STOP_MAXFUN; done = true; }
+      else if (R.sbgnrm <= pgtol) { R.status = LB_CONV_PGTOL; done = true; }
+      else {
+        const double ddum0 = lb::dmax(fabs(R.fold), lb::dmax(fabs(R.f), 1.0));
+        if ((R.fold - R.f) <= LB_EPSMCH * factr * ddum0) { R.status = LB_CONV_FACTR; done = true; }
+      }
+      if (!done) {
+        // ---- BFGS pair
+        const double rl = act ? gl - s.r[lane] : 0.0;          // y
+        double sl = act ? s.d[lane] : 0.0;                      // s
+        double dr, ddum;
+        if (R.stp == 1.0) { dr = gd - R.gdold; ddum = -R.gdold; }
+        else { dr = (gd - R.gdold) * R.stp; sl *= R.stp; ddum = -R.gdold * R.stp; }
+        if (dr <= LB_EPSMCH * ddum) R.nskip += 1;
+        else {
+          double t1[NMAX], t2[NMAX];
+          {
+            double* b0 = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+            double* b1 = s.scr[slot]; slot = (slot + 1) & (LBW_SCR - 1);
+            if (lane < NMAX) { b0[lane] = rl * rl; b1[lane] = rl * sl; }
+            __syncwarp();
+            lbw::ldvec<NMAX>(b0, t1);
+            lbw::ldvec<NMAX>(b1, t2);
+          }
+          const double rr = lbw::vsum<NMAX>(t1), ys = lbw::vsum<NMAX>(t2);
+          int p;
+          if (R.col == LB_M) { p = R.head; R.head = (R.head + 1 == LB_M) ? 0 : R.head + 1; }
+          else { p = R.head + R.col; if (p >= LB_M) p -= LB_M; R.col += 1; }
+          if (act) { s.S[p][lane] = sl; s.Y[p][lane] = rl; }
+          if (lane == 0) s.ysinv[p] = 1.0 / ys;
+          R.theta = rr / dr;
+          __syncwarp();
+        }
+        iterate = true;
+      }
+    }
   }
-  return lbw::new_iteration(s, lane);
+  LBW_MARK(4);
+  if (iterate) rc = lbw::new_iteration<NMAX>(s, R, slot, lane, xl, gl);
+  lbw::store_regs(s, R, lane);
+  return rc;
 }
