@@ -304,6 +304,73 @@ __device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
   if constexpr (KB + 1 < T) elim_all<T, KB + 1, LOWER_ONLY>(a, c);
 }
 
+// Symmetric sweep of the augmented matrix [[K, y], [y^T, 0]] over the n pivots of K (Goodnight's SWP
+// operator = Gauss-Jordan without pivoting on an SPD matrix):  a_kk <- -1/p,  a_ik <- a_ik / p,
+// a_kj <- a_kj / p,  a_ij <- a_ij - a_ik a_kj / p.  After the n steps the registers hold -K^-1, row n holds
+// alpha = K^-1 y, element (n, n) holds -y^T K^-1 y, and the pivots are those of the Cholesky
+// factorisation (p_k = L_kk^2: same log-determinant, same positive-definiteness test).  Against the
+// L / L^-1 elimination above this needs no write-back, no back substitution for alpha and no
+// K^-1 = L^-T L^-1 contraction afterwards (12 k of 71 k cycles per evaluation at n = 60), for the same
+// per-step cost; measured against an extended-precision solve its alpha and gradient errors are no larger
+// than the Cholesky route's (cond 1e5..5e6: 1e-13..2e-11 either way).  The FULL matrix is kept (both
+// triangles, T x T tile per thread) so that pivot column k has ONE owner group -- the half-warp tx == k % 16
+// -- and the publish / consume pattern is the one of elim_block.
+template <int T, int KB>
+__device__ __forceinline__ void sweep_block(double (&a)[T][T], ElimCtx& c) {
+  constexpr int TP = (T + 1) & ~1;             // packed per-lane stride (128-bit chunks)
+  const int n = c.n, tx = c.tx, ty = c.ty;
+  const int kend = (n - 16 * KB) < 16 ? (n - 16 * KB) : 16;
+  for (int kt = 0; kt < kend; kt++) {
+    const int k = 16 * KB + kt;
+    double* buf = c.colbuf + (kt & 1) * FIT_COLBUF;
+    const bool col_eq = (tx == kt), row_eq = (ty == kt), own = col_eq && row_eq;
+    {
+#pragma unroll
+      for (int q = 0; q < TP; q += 2)
+        sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, col_eq);
+      sts2_if(buf + 384, a[KB][KB], c.ip_next, own);
+      sts1_if(c.pivs + k, a[KB][KB], own);
+    }
+    __syncthreads();
+    const double2 pp = *reinterpret_cast<const double2*>(buf + 384);
+    c.bad = c.bad || !(pp.x > 0.0);
+    const double ip = pp.y;
+    double ck[TP], f[TP];
+    {
+      const double2* c2 = reinterpret_cast<const double2*>(buf + ty * TP);
+      const double2* f2 = reinterpret_cast<const double2*>(buf + tx * TP);
+#pragma unroll
+      for (int q = 0; q < TP; q += 2) {
+        const double2 v = c2[q >> 1], w = f2[q >> 1];
+        ck[q] = v.x; ck[q + 1] = v.y; f[q] = w.x * ip; f[q + 1] = w.y * ip;
+      }
+    }
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+#pragma unroll
+      for (int ia = 0; ia < T; ia++) {
+        double v = fma(-ck[ia], f[jb], a[ia][jb]);
+        if (ia == KB) v = row_eq ? f[jb] : v;                  // row k     <- c_j / p
+        if (jb == KB) v = col_eq ? ck[ia] * ip : v;            // column k  <- c_i / p
+        if (ia == KB && jb == KB) v = own ? -ip : v;           // pivot     <- -1 / p
+        a[ia][jb] = v;
+      }
+    }
+    {
+      // speculative and branch-free: every thread inverts its own candidate for the next pivot
+      constexpr int KN = (KB + 1 < T) ? KB + 1 : KB;
+      const double pv = (kt < 15) ? a[KB][KB] : a[KN][KN];
+      c.ip_next = fast_rcp(pv);
+    }
+  }
+}
+
+template <int T, int KB>
+__device__ __forceinline__ void sweep_all(double (&a)[T][T], ElimCtx& c) {
+  if (16 * KB < c.n) sweep_block<T, KB>(a, c);
+  if constexpr (KB + 1 < T) sweep_all<T, KB + 1>(a, c);
+}
+
 // ---------------------------------------------------------------------------------------
 // Register-resident variant of steps 1-2 for n + 1 <= 16 * T.  The (n+1) x n panel lives in
 // registers, 2-D cyclically distributed over the 16 x 16 thread grid (thread (ty, tx) owns
@@ -314,14 +381,11 @@ __device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
 // On success the shared panel holds, scaled: A[i][k] (i < k) = (L^-1)_ki, A[n][k] = (L^-1 y)_k
 // and -- scale_lower: A[i][k] (i >= k) = L_ik;  else: A[k][k] = 1/L_kk, A[i][k] (i > k) = 0
 // (so that row i of the panel is column i of L^-1, zero-padded: what nll_eval_reg contracts).
-template <int T>
-__device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, const double* theta,
-                                        bool scale_lower) {
+// Steps 0-1 of the register-panel paths: column scaling and the kernel matrix (lower triangle, diagonal,
+// y row) into the shared-memory panel, pair-value caches for the gradient.  Ends with a barrier.
+__device__ __forceinline__ void kernel_panel_reg(const FitWs& S, const SpaceDesc& sp, const double* theta) {
   const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
   const int tid = threadIdx.x, NT = blockDim.x;
-  // ty = fast index: the 16 owners of a pivot column (fixed tx) sit in ONE warp, so the other
-  // seven warps skip the publish code with a uniform branch
-  const int tx = tid >> 4, ty = tid & 15;
   double* A = S.A;
   PHASE_T0();
   __syncthreads();
@@ -382,6 +446,20 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
     A[(size_t)n * lda + j] = S.y[j];
   }
   __syncthreads();
+  PHASE_MARK(1);
+}
+
+template <int T>
+__device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, const double* theta,
+                                        bool scale_lower) {
+  const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  // ty = fast index: the 16 owners of a pivot column (fixed tx) sit in ONE warp, so the other
+  // seven warps skip the publish code with a uniform branch
+  const int tx = tid >> 4, ty = tid & 15;
+  double* A = S.A;
+  kernel_panel_reg(S, sp, theta);
+  PHASE_T0();
   double a[T][T];
 #pragma unroll
   for (int ia = 0; ia < T; ia++) {
@@ -589,53 +667,74 @@ __device__ __forceinline__ void kin_all(double (&kin)[T][T], const double* A, in
   if constexpr (KB + 1 < T) kin_all<T, KB + 1>(kin, A, lda, n, ty, tx);
 }
 
-// nll_eval on the register-panel path: the gradient contraction uses the same 2-D cyclic
-// tiling -- K^-1_ij = sum_k U[i][k] U[j][k] over the zero-padded rows of the panel, T x T
-// outer products per k (2T shared loads per T^2 FMAs instead of 2 per FMA).
+// nll_eval on the register-panel path: kernel matrix, symmetric sweep (sweep_block: -K^-1, alpha, pivots in
+// ONE pass over the register tiles), W = alpha alpha^T - K^-1 published once and contracted with dK/dtheta
+// in one linear pair loop.
 template <int T, int DMAX>
 __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* theta, double* out) {
   const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
   const int tid = threadIdx.x, NT = blockDim.x;
   const int tx = tid >> 4, ty = tid & 15;
-  const bool ok = build_and_eliminate_reg<T>(S, sp, theta, false);
+  double* A = S.A;
+  kernel_panel_reg(S, sp, theta);
+  PHASE_T0();
+  const double c = exp(theta[0]);
+  const double noise = exp(theta[d + 1]);
+  // full symmetric tile of [[K, y], [y^T, 0]]: thread (ty, tx) owns rows ty + 16 ia, columns tx + 16 jb
+  double a[T][T];
+#pragma unroll
+  for (int ia = 0; ia < T; ia++) {
+    const int i = ty + 16 * ia;
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+      const int j = tx + 16 * jb;
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      a[ia][jb] = (hi <= n && lo < n) ? A[(size_t)hi * lda + lo] : 0.0;
+    }
+  }
+  PHASE_MARK(1);
+  ElimCtx ec;
+  ec.colbuf = S.colbuf; ec.pivs = S.piv; ec.n = n; ec.tx = tx; ec.ty = ty;
+  ec.diag_lower = ty >= tx; ec.own_diag = ty == tx; ec.bad = false;
+  ec.ip_next = fast_rcp(a[0][0]);
+  sweep_all<T, 0>(a, ec);
+  // row n of the swept matrix is alpha, element (n, n) is -y^T K^-1 y: published before the barrier
+#pragma unroll
+  for (int ia = 0; ia < T; ia++) {
+    if (ty + 16 * ia == n) {
+#pragma unroll
+      for (int jb = 0; jb < T; jb++) {
+        const int j = tx + 16 * jb;
+        if (j < n) S.alpha[j] = a[ia][jb];
+        else if (j == n) S.red[32 + 27] = a[ia][jb];
+      }
+    }
+  }
+  const bool ok = !__syncthreads_or(ec.bad ? 1 : 0);
+  PHASE_MARK(2);
   if (!ok) {
     if (tid == 0) out[0] = 1e25;
     if (tid < H) out[1 + tid] = 0.0;
     __syncthreads();
     return false;
   }
-  const double* A = S.A;
-  const double c = exp(theta[0]);
-  const double noise = exp(theta[d + 1]);
   double part = 0.0;
-  for (int k = tid; k < n; k += NT) {
-    const double z = A[(size_t)n * lda + k];
-    part += 0.5 * z * z + 0.5 * log(S.piv[k]);
-  }
-  PHASE_T0();
+  for (int k = tid; k < n; k += NT) part += 0.5 * log(S.piv[k]);
+  if (tid == 0) part -= 0.5 * S.red[32 + 27];
+  PHASE_MARK(3);
   const double nll_data = block_sum(part, S.red);
   PHASE_MARK(4);
-
-  double kin[T][T];
-#pragma unroll
-  for (int ia = 0; ia < T; ia++)
-#pragma unroll
-    for (int jb = 0; jb < T; jb++) kin[ia][jb] = 0.0;
-  kin_all<T, 0>(kin, A, lda, n, ty, tx);
-  // publish W = alpha alpha^T - K^-1 (strict lower part into the panel, diagonal into piv[]:
-  // both are dead by now) and contract it with dK/dtheta in ONE linear pair loop
-  __syncthreads();
-  PHASE_MARK(5);
+  // publish W = alpha alpha^T - K^-1 (strict lower part into the panel, diagonal into piv[]: both are dead
+  // by now) and contract it with dK/dtheta in ONE linear pair loop
   {
-    double* Aw = S.A;
 #pragma unroll
     for (int ia = 0; ia < T; ia++) {
       const int i = ty + 16 * ia;
 #pragma unroll
       for (int jb = 0; jb < T; jb++) {
         const int j = tx + 16 * jb;
-        if (i < n && j < i) Aw[(size_t)i * lda + j] = S.alpha[i] * S.alpha[j] - kin[ia][jb];
-        else if (i < n && j == i) S.piv[i] = S.alpha[i] * S.alpha[i] - kin[ia][jb];
+        if (i < n && j < i) A[(size_t)i * lda + j] = S.alpha[i] * S.alpha[j] + a[ia][jb];
+        else if (i < n && j == i) S.piv[i] = S.alpha[i] * S.alpha[i] + a[ia][jb];
       }
     }
   }

@@ -165,7 +165,7 @@ __device__ __forceinline__ int dcsrch(Regs& R, double f, double g, int start) {
     R.ginit = g;
     R.gtest = ftol * g;
     R.width = stpmax - stpmin;
-    R.width1 = R.width / 0.5;
+    R.width1 = R.width * 2.0;                // (width / 0.5, exactly)
     R.stx = 0.0; R.fx = f; R.gx = g;
     R.sty = 0.0; R.fy = f; R.gy = g;
     R.stmin = 0.0;
@@ -252,30 +252,21 @@ __device__ __forceinline__ void rebuild_B(LbwState& s, const Regs& R, int& slot,
                                           double (&Bc)[NMAX]) {
 #pragma unroll
   for (int j = 0; j < NMAX; j++) Bc[j] = (act && j == lane) ? R.theta : 0.0;
-  // software-pipelined: the (s, y) rows of pair k + 1 are loaded while the dependent chain of pair k
-  // (B s -> gather -> s'Bs -> reciprocal -> rank-2 update) runs
-  double sk[NMAX], yk[NMAX];
-  int p = R.head;
-  ldvec<NMAX>(s.S[p], sk);
-  ldvec<NMAX>(s.Y[p], yk);
-  double ykl = (lane < NMAX) ? s.Y[p][lane] : 0.0, yi = s.ysinv[p];
 #pragma unroll 1
   for (int k = 0; k < R.col; k++) {
-    p = (p + 1 == LB_M) ? 0 : p + 1;
-    double skn[NMAX], ykn[NMAX], bs[NMAX];
-    ldvec<NMAX>(s.S[p], skn);
-    ldvec<NMAX>(s.Y[p], ykn);
-    const double ykln = (lane < NMAX) ? s.Y[p][lane] : 0.0, yin = s.ysinv[p];
-    const double c1 = ykl * yi;
+    int p = R.head + k;
+    if (p >= LB_M) p -= LB_M;
+    double sk[NMAX], yk[NMAX], bs[NMAX];
+    ldvec<NMAX>(s.S[p], sk);
+    ldvec<NMAX>(s.Y[p], yk);
+    const double ykl = (lane < NMAX) ? s.Y[p][lane] : 0.0;
+    const double c1 = ykl * s.ysinv[p];
     const double a = vdot<NMAX>(Bc, sk);                 // (B s_k)_lane
     gather<NMAX>(s, slot, lane, a, bs);
     const double sBs = vdot<NMAX>(sk, bs);
     const double c2 = a * rcp(sBs);
 #pragma unroll
     for (int j = 0; j < NMAX; j++) Bc[j] = fma(-bs[j], c2, fma(yk[j], c1, Bc[j]));
-#pragma unroll
-    for (int j = 0; j < NMAX; j++) { sk[j] = skn[j]; yk[j] = ykn[j]; }
-    ykl = ykln; yi = yin;
   }
 }
 
