@@ -50,6 +50,16 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   __shared__ double th[TLBO_HMAX];
   __shared__ double fg[1 + TLBO_HMAX];
   __shared__ int act;
+  if (T > 0 && n + 1 > 16 * T) {
+    // capacity without room for the y row (see panel_tile_for): no restart result -> the factorisation
+    // reports status 2 for this surrogate
+    if (tid == 0) {
+      a.restart_f[(size_t)b * a.R + r] = INFINITY;
+      int32_t* info = a.restart_info + ((size_t)b * a.R + r) * 4;
+      info[0] = 0; info[1] = 0; info[2] = LB_ERROR; info[3] = 0;
+    }
+    return;
+  }
   LbfgsbState* st = reinterpret_cast<LbfgsbState*>(smem);
   LbwState* sw = reinterpret_cast<LbwState*>(smem);
   unsigned char* rest = smem + fit_state_bytes();
@@ -57,6 +67,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_fit_kernel(FitArgs a) {
   carve_ws(S, rest, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d, T, a.cache);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.p0[(size_t)r * H + tid];
+  if constexpr (T > 0) find_active_columns(S, a.sp);
   __syncthreads();
   // ONE evaluation call site (the unrolled evaluation is ~100 KB of code; a second copy costs
   // instruction-cache misses on the critical path): the evaluation at the start point doubles as
@@ -240,10 +251,15 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_nll_grad_kernel(NllArgs a) 
   const int tid = threadIdx.x;
   __shared__ double th[TLBO_HMAX];
   __shared__ double fg[1 + TLBO_HMAX];
+  if (T > 0 && n + 1 > 16 * T) {      // capacity without room for the y row (see panel_tile_for)
+    if (tid == 0) { a.nll[b] = NAN; a.status[b] = 3; }
+    return;
+  }
   FitWs S;
   carve_ws(S, smem, a.panels ? a.panels + (size_t)b * a.panel_stride : nullptr, n, a.ncap, d, T, a.cache);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
   if (tid < H) th[tid] = a.theta[(size_t)b * H + tid];
+  if constexpr (T > 0) find_active_columns(S, a.sp);
   __syncthreads();
   const bool ok = nll_eval_any<T, DMAX>(S, a.sp, th, fg);
   if (tid == 0) { a.nll[b] = fg[0]; a.status[b] = ok ? 0 : 1; }

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) gp_mcmc_kernel(McmcArgs a) {
   FitWs S;
   carve_ws(S, smem, a.panels ? a.panels + (size_t)blockIdx.x * a.panel_stride : nullptr, n, a.ncap, d, T, a.cache);
   load_problem(S, a.sp, a.X + (size_t)b * a.ncap * d, a.y + (size_t)b * a.ncap, a.ncap);
+  if constexpr (T > 0) find_active_columns(S, a.sp);     // build_and_eliminate_reg works on the varying columns
   __syncthreads();
   double* pos = a.pos + (size_t)b * W * H;
   double* lp = a.lp + (size_t)b * W;

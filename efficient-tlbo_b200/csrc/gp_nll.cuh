@@ -47,7 +47,9 @@ struct FitWs {
   int* pairs;      // [n (n-1) / 2] packed (i << 16 | j), i > j: built once per kernel (register-panel path)
   double* Kc;      // [npairs] kernel value per pair        } written by the kernel-matrix build, reused by
   double* Cg;      // [npairs] c e^{-t-hs} 5/3 (1 + t)      } the gradient contraction (NULL: recompute)
+  int* acol;       // [TLBO_HMAX] permuted column of compact column q (register-panel path: columns that vary)
   int n, lda, d, npairs;
+  int nac, nak;    // varying continuous / categorical columns (find_active_columns)
 };
 
 __host__ __device__ inline int fit_lda(int n) { return (n & 1) ? n : n + 1; }
@@ -61,7 +63,7 @@ __host__ __device__ inline size_t fit_pair_bytes(int ncap, int tile, int cache) 
 }
 __host__ inline size_t fit_small_bytes(int ncap, int d, int tile, int cache) {
   // Xr, Xs, y, piv, dinv, alpha, red, hyp, colbuf, pair tables
-  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8) +
+  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8 + 16) +
          fit_pair_bytes(ncap, tile, cache);
 }
 __host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
@@ -79,6 +81,8 @@ __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* 
   S.red = p; p += 8 * 32;
   S.hyp = p; p += 2 * TLBO_HMAX;
   S.colbuf = p; p += 2 * FIT_COLBUF;
+  S.acol = reinterpret_cast<int*>(p); p += 16;
+  S.nac = 0; S.nak = 0;
   S.npairs = n * (n - 1) / 2;
   S.pairs = nullptr; S.Kc = nullptr; S.Cg = nullptr;
   if (tile > 0) {
@@ -107,6 +111,30 @@ __device__ __forceinline__ void load_problem(const FitWs& S, const SpaceDesc& sp
     }
   }
   (void)ncap;
+}
+
+// Columns whose value is the same in every training row (the constant hyper-parameters of a search space,
+// e.g. 4 of the 9 columns of the random-forest space) contribute an exact zero to every squared distance /
+// Hamming count and to their own length-scale gradient: the register-panel path works on the compacted
+// list of VARYING columns (bit-identical results, 5 instead of 9 columns per pair for that space).
+// Call after load_problem; contains barriers.
+__device__ __forceinline__ void find_active_columns(FitWs& S, const SpaceDesc& sp) {
+  const int n = S.n, d = S.d, dc = sp.d_cont, tid = threadIdx.x;
+  __syncthreads();
+  if (tid < d) {
+    const double v0 = S.Xr[tid];
+    bool varies = false;
+    for (int i = 1; i < n; i++) varies = varies || (S.Xr[(size_t)i * d + tid] != v0);
+    S.red[tid] = varies ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  int nac = 0, nak = 0;
+  for (int p = 0; p < dc; p++)
+    if (S.red[p] != 0.0) { if (tid == 0) S.acol[nac] = p; nac++; }
+  for (int p = dc; p < d; p++)
+    if (S.red[p] != 0.0) { if (tid == 0) S.acol[nac + nak] = p; nak++; }
+  S.nac = nac; S.nak = nak;
+  __syncthreads();
 }
 
 // Steps 1-2.  Returns false (uniformly) if a pivot is not positive (Cholesky would fail).
@@ -392,53 +420,61 @@ __device__ __forceinline__ void kernel_panel_reg(const FitWs& S, const SpaceDesc
   // every thread needs the scale of "its" column (p = tid & 31 < d <= 22): one exp per thread,
   // no shared-memory round trip before the scaling pass
   const int pcol = tid & 31;
+  const int nac = S.nac, da = S.nac + S.nak;       // compact (varying) columns: continuous first
   double myscale = 1.0;
-  if (pcol < d) {
-    const double l = exp(theta[1 + pcol]);
-    myscale = (pcol < dc) ? 1.0 / l : 1.0;
-    if (tid < d) {
-      if (tid < dc) { S.hyp[tid] = l; }
-      else { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
-    }
+  if (pcol < da) {
+    const int pp = S.acol[pcol];
+    const double l = exp(theta[1 + pp]);
+    myscale = (pcol < nac) ? 1.0 / l : 1.0;
+    if (tid < da && tid >= nac) { S.hyp[tid] = 1.0 / (2.0 * l * l); S.hyp[TLBO_HMAX + tid] = 1.0 / (l * l * l); }
+    for (int i = tid >> 5; i < n; i += NT >> 5) S.Xs[(size_t)i * da + pcol] = S.Xr[(size_t)i * d + pp] * myscale;
   }
   const double c = exp(theta[0]);
   const double noise = exp(theta[d + 1]);
-  if (pcol < d)
-    for (int i = tid >> 5; i < n; i += NT >> 5) S.Xs[(size_t)i * d + pcol] = S.Xr[(size_t)i * d + pcol] * myscale;
   __syncthreads();
   PHASE_MARK(0);
   // kernel matrix (lower triangle, diagonal, y row) through shared memory: ONE copy of the
-  // exp / sqrt code over the pair table, then every thread picks up its register tile
-  // two pairs in flight per thread (independent sqrt / exp chains)
-  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
-    const int q1 = q0 + NT;
-    const bool has1 = q1 < S.npairs;
-    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
-    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
-    const double* xi0 = S.Xs + (size_t)i0 * d;
-    const double* xj0 = S.Xs + (size_t)j0 * d;
-    const double* xi1 = S.Xs + (size_t)i1 * d;
-    const double* xj1 = S.Xs + (size_t)j1 * d;
-    double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
-    for (int p = 0; p < dc; p++) {
-      const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
-      s0 += e0 * e0; s1 += e1 * e1;
+  // exp / sqrt code over the pair table, then every thread picks up its register tile.
+  // FOUR pairs in flight per thread: the sqrt / exp chains are ~60 dependent FP64 operations and only two
+  // warps share a scheduler, so the phase is latency-bound (n = 60: 7 pairs per thread in two passes)
+  constexpr int PF = 4;
+  for (int qb = tid; qb < S.npairs; qb += PF * NT) {
+    int qq[PF];
+    bool has[PF];
+    const double* xi[PF];
+    const double* xj[PF];
+    double ss[PF], hh[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int q = qb + u * NT;
+      has[u] = q < S.npairs;
+      qq[u] = has[u] ? q : qb;
+      const int ij = S.pairs[qq[u]];
+      xi[u] = S.Xs + (size_t)(ij >> 16) * da;
+      xj[u] = S.Xs + (size_t)(ij & 0xffff) * da;
+      ss[u] = 0.0; hh[u] = 0.0;
     }
-    for (int p = dc; p < d; p++) {
+    for (int p = 0; p < nac; p++) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) { const double e = xi[u][p] - xj[u][p]; ss[u] += e * e; }
+    }
+    for (int p = nac; p < da; p++) {
       const double hp = S.hyp[p];
-      h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
-      h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
+#pragma unroll
+      for (int u = 0; u < PF; u++) hh[u] += (xi[u][p] != xj[u][p]) ? hp : 0.0;
     }
-    const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
-    const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
-    // t^2 / 3 as a multiplication by the rounded 1/3 (<= 1 ulp from the IEEE quotient; the division is a
-    // ~25-instruction subroutine on the critical path of every pair)
-    const double v0 = ce0 * (1.0 + t0 + t0 * t0 * (1.0 / 3.0)), v1 = ce1 * (1.0 + t1 + t1 * t1 * (1.0 / 3.0));
-    A[(size_t)i0 * lda + j0] = v0;
-    if (S.Kc) { S.Kc[q0] = v0; S.Cg[q0] = ce0 * (5.0 / 3.0) * (t0 + 1.0); }
-    if (has1) {
-      A[(size_t)i1 * lda + j1] = v1;
-      if (S.Kc) { S.Kc[q1] = v1; S.Cg[q1] = ce1 * (5.0 / 3.0) * (t1 + 1.0); }
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const double t = sqrt_nonneg(ss[u]) * SQRT5;
+      const double ce = c * exp_nonpos(-t - hh[u]);
+      // t^2 / 3 as a multiplication by the rounded 1/3 (<= 1 ulp from the IEEE quotient; the division is a
+      // ~25-instruction subroutine on the critical path of every pair)
+      const double v = ce * (1.0 + t + t * t * (1.0 / 3.0));
+      if (has[u]) {
+        const int ij = S.pairs[qq[u]];
+        A[(size_t)(ij >> 16) * lda + (ij & 0xffff)] = v;
+        if (S.Kc) { S.Kc[qq[u]] = v; S.Cg[qq[u]] = ce * (5.0 / 3.0) * (t + 1.0); }
+      }
     }
   }
   for (int j = tid; j < n; j += NT) {
@@ -457,6 +493,7 @@ __device__ bool build_and_eliminate_reg(const FitWs& S, const SpaceDesc& sp, con
   // ty = fast index: the 16 owners of a pivot column (fixed tx) sit in ONE warp, so the other
   // seven warps skip the publish code with a uniform branch
   const int tx = tid >> 4, ty = tid & 15;
+  const int nac = S.nac, da = S.nac + S.nak;       // compact (varying) columns, see find_active_columns
   double* A = S.A;
   kernel_panel_reg(S, sp, theta);
   PHASE_T0();
@@ -675,6 +712,7 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   const int n = S.n, lda = S.lda, d = S.d, dc = sp.d_cont, H = d + 2;
   const int tid = threadIdx.x, NT = blockDim.x;
   const int tx = tid >> 4, ty = tid & 15;
+  const int nac = S.nac, da = S.nac + S.nak;       // compact (varying) columns, see find_active_columns
   double* A = S.A;
   kernel_panel_reg(S, sp, theta);
   PHASE_T0();
@@ -751,21 +789,21 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
     const double W0 = A[(size_t)i0 * lda + j0];
     const double W1 = has1 ? A[(size_t)i1 * lda + j1] : 0.0;        // a masked second pair adds zeros
-    const double* xi0 = S.Xs + (size_t)i0 * d;
-    const double* xj0 = S.Xs + (size_t)j0 * d;
-    const double* xi1 = S.Xs + (size_t)i1 * d;
-    const double* xj1 = S.Xs + (size_t)j1 * d;
+    const double* xi0 = S.Xs + (size_t)i0 * da;
+    const double* xj0 = S.Xs + (size_t)j0 * da;
+    const double* xi1 = S.Xs + (size_t)i1 * da;
+    const double* xj1 = S.Xs + (size_t)j1 * da;
     double WK0, WK1, cf0, cf1;
     if (S.Kc) {
       WK0 = W0 * S.Kc[q0]; cf0 = W0 * S.Cg[q0];
       WK1 = W1 * S.Kc[has1 ? q1 : q0]; cf1 = W1 * S.Cg[has1 ? q1 : q0];
     } else {
       double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
-      for (int p = 0; p < dc; p++) {
+      for (int p = 0; p < nac; p++) {
         const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
         s0 += e0 * e0; s1 += e1 * e1;
       }
-      for (int p = dc; p < d; p++) {
+      for (int p = nac; p < da; p++) {
         const double hp = S.hyp[p];
         h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
         h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
@@ -779,11 +817,11 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     g0 += WK1;
 #pragma unroll
     for (int p = 0; p < DMAX; p++) {
-      if (p < dc) {
+      if (p < nac) {
         const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
         gacc[p] += cf0 * (e0 * e0);
         gacc[p] += cf1 * (e1 * e1);
-      } else if (p < d) {
+      } else if (p < da) {
         const double h3 = S.hyp[TLBO_HMAX + p];
         gacc[p] += (xi0[p] != xj0[p]) ? WK0 * h3 : 0.0;
         gacc[p] += (xi1[p] != xj1[p]) ? WK1 * h3 : 0.0;
@@ -810,9 +848,10 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     if (lane == 0) {
       S.red[wid * 32 + 0] = g0;
       S.red[wid * 32 + (d + 1)] = gn;
+      for (int p = 0; p < d; p++) S.red[wid * 32 + 1 + p] = 0.0;          // constant columns: zero gradient
 #pragma unroll
-      for (int p = 0; p < DMAX; p++)
-        if (p < d) S.red[wid * 32 + 1 + p] = gacc[p];
+      for (int q = 0; q < DMAX; q++)
+        if (q < da) S.red[wid * 32 + 1 + S.acol[q]] = gacc[q];
     }
   }
   __syncthreads();
@@ -970,11 +1009,15 @@ __device__ __forceinline__ bool nll_eval_any(const FitWs& S, const SpaceDesc& sp
   if constexpr (T == 0) return nll_eval<DMAX>(S, sp, theta, out);
   else return nll_eval_reg<T, DMAX>(S, sp, theta, out);
 }
+// Register-panel tile for a batch of row capacity ncap: the panel holds n + 1 rows (the y row rides along),
+// n + 1 <= 16 T.  The tile follows the CAPACITY (T = ceil(ncap / 16)), so the caller's capacity must leave
+// room for the y row when it is a multiple of 16 (n <= ncap - 1; tlbo_b200/ops.py:batch_cap; the kernels
+// reject a violating surrogate through its status instead of computing garbage).
 __host__ inline int panel_tile_for(int ncap) {
-  if (ncap + 1 <= 64) return 4;
-  if (ncap + 1 <= 80) return 5;
-  if (ncap + 1 <= 96) return 6;
-  if (ncap + 1 <= 112) return 7;
-  if (ncap + 1 <= 128) return 8;
+  if (ncap <= 64) return 4;
+  if (ncap <= 80) return 5;
+  if (ncap <= 96) return 6;
+  if (ncap <= 112) return 7;
+  if (ncap <= 128) return 8;
   return 0;
 }

@@ -88,7 +88,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
     # ---- device pack ------------------------------------------------------------------
     def _ensure_pack(self, rows):
         from tlbo_b200 import ops
-        need = ops.round_up(max(rows, self.num_src_hpo_trial, 8), 8)
+        need = ops.batch_cap(max(rows, self.num_src_hpo_trial, 8))
         if self._pack is not None and self._pack.ncap >= need:
             return self._pack
         cap = ops.round_up(max(need, self._cap_hint), 8)

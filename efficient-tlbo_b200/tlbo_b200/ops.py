@@ -43,6 +43,16 @@ def round_up(n, m):
     return ((int(n) + m - 1) // m) * m
 
 
+def batch_cap(n):
+    """Row capacity (stride) of a training batch whose largest set has ``n`` rows: a multiple of 8 with room
+    for the extra y row of the register-panel kernels, whose tile is chosen from the capacity
+    (n + 1 <= 16 * ceil(cap / 16), csrc/gp_nll.cuh:panel_tile_for) -- so n = 57..63 runs 4 x 4 tiles."""
+    cap = round_up(max(int(n), 1), 8)
+    if cap % 16 == 0 and int(n) == cap:
+        cap += 8
+    return cap
+
+
 class _Stats(object):
     """Launch / transfer accounting for bench.py: how many of OUR kernels were launched,
     how many bytes crossed PCIe, and (when ``timing``) a CUDA-event pair around every
@@ -144,7 +154,7 @@ class SurrogatePack(object):
 
     def __init__(self, M, ncap, d):
         dev = _dev()
-        ncap = round_up(max(ncap, 8), 8)
+        ncap = batch_cap(max(ncap, 8))
         self.M, self.ncap, self.d = int(M), int(ncap), int(d)
         self.n = torch.zeros(M, dtype=torch.int32, device=dev)
         self.Xs = torch.zeros(M, ncap, d, dtype=F64, device=dev)
@@ -233,7 +243,7 @@ def prepare_jobs(X, y, ranges, outer_guard, normalize, normalize_y=True):
     assert y.dtype == np.float64 and y.flags.c_contiguous and y.ndim == 1
     n, d = X.shape
     B = len(ranges)
-    ncap = round_up(n, 8)
+    ncap = batch_cap(n)
     nx, ny = B * ncap * d, B * ncap
     buf = np.empty(nx + ny + (B + 1) // 2 + 1, dtype=np.float64)
     nh = buf[nx + ny:].view(np.int32)
@@ -307,7 +317,7 @@ def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0
     else:
         B = len(X_list)
         d = int(X_list[0].shape[1])
-        ncap = round_up(max(x.shape[0] for x in X_list), 8)
+        ncap = batch_cap(max(x.shape[0] for x in X_list))
     H = d + 2
     if ncap > pack.ncap:
         raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
@@ -347,7 +357,7 @@ def gp_factorize_batched(X_list, y_list, types, thetas, ymean, ystd, pack, slot0
     """``tlbo_gp_factorize_batched``: factorise at given theta and fill pack slots."""
     B = len(X_list)
     d = int(X_list[0].shape[1])
-    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    ncap = batch_cap(max(x.shape[0] for x in X_list))
     if ncap > pack.ncap:
         raise ValueError('pack row capacity %d < %d' % (pack.ncap, ncap))
     dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
@@ -376,7 +386,7 @@ def gp_nll_grad_batched(X_list, y_list, types, thetas):
     B = len(X_list)
     d = int(X_list[0].shape[1])
     H = d + 2
-    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    ncap = batch_cap(max(x.shape[0] for x in X_list))
     dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
     dev = dX.device
     dth = h2d(np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(B, H)))
@@ -681,7 +691,7 @@ class McmcHandle(object):
 def upload_batch(X_list, y_list):
     """Padded device batch ``(dX [B, ncap, d], dy [B, ncap], dn [B], ncap)`` (one upload)."""
     d = int(X_list[0].shape[1])
-    ncap = round_up(max(x.shape[0] for x in X_list), 8)
+    ncap = batch_cap(max(x.shape[0] for x in X_list))
     dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
     return dX, dy, dn, ncap
 

@@ -18,7 +18,7 @@ X = wl['Xt'][rows]; y = wl['yt'][rows]; y = (y - y.mean()) / y.std()
 pack = ops.SurrogatePack(1, n, 9)
 fn = _cabi.lib.tlbo_debug_phase_cycles
 buf = (ctypes.c_longlong * 24)()
-names = ['hyp+Xs scale', 'K build + tile load', 'elimination', 'writeback + alpha', 'nll_data reduce', 'kin loop',
+names = ['hyp+Xs scale', 'K build + tile load', 'symmetric sweep', 'log-det partials', 'nll_data reduce', '(unused)',
          'W publish', 'pair loop', 'grad reduce + finish', 'optimiser feed']
 for rep in range(2):
     fn(buf, 1)
