@@ -10,10 +10,14 @@ pool, random_forest-shaped space (d = 9), synthetic histories.
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
 
-Prints ONE JSON line (rank 0).  N > 1: one process per GPU (torchrun); ranks run independent
-BO trials (different target task / seed) -- the path shards by trial with no data-path
-collective ("weak" scaling); a pool-sharded run of ONE trial (tiny NCCL all-gather of the
-per-rank arg-max) is reported beside it under "pool_sharded".
+Prints ONE JSON line (rank 0).  The headline fields are the RGPE run on configs[1]; the rest of
+BASELINE.json's metric rides in the same line under "sub" (each record with its own value / e2e /
+roofline / cpu_baseline): "topo" (OBTLV, what --methods topo runs), "pool_1e6" (the north-star pool
+size), "predict_sweep" (configs[3]: 30 surrogates x n x N x d, nothing resident), "pool_strong" (ONE
+trial over a FIXED pool sharded over the N ranks: strong scaling, NCCL all-gather of 4 doubles per
+rank), and for N > 1 "distinct_trials" (every rank its own task / seed, slowest rank charged) and --
+at N = 8 -- "gp_mcmc" (configs[4]: TOPO over MCMC-marginalised GPs).  N > 1: one process per GPU
+(torchrun); the headline shards by trial with no data-path collective ("weak" scaling).
 """
 import argparse
 import json
@@ -60,7 +64,12 @@ def parse_args():
     ap.add_argument('--pool', type=int, default=100000)
     ap.add_argument('--sources', type=int, default=29)
     ap.add_argument('--n0', type=int, default=40, help='target observations before the first step')
-    ap.add_argument('--cpu-sample-rows', type=int, default=10000)
+    ap.add_argument('--cpu-sample-rows', type=int, default=0,
+                    help='reference arm: score this many pool rows per step and scale (0 = the full pool, measured)')
+    ap.add_argument('--passes', type=int, default=5, help='timed passes of exactly --steps steps each (median reported)')
+    ap.add_argument('--sub', default='auto', help="sub-records: 'auto', 'none' or a comma list of topo,pool_1e6,predict_sweep,"
+                    "pool_strong,distinct_trials,gp_mcmc")
+    ap.add_argument('--strong-pool', type=int, default=1000000, help='rows of the fixed pool of the pool_strong record')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pool-sharded', action='store_true')
     ap.add_argument('--distinct-trials', action='store_true',
@@ -89,7 +98,11 @@ def build_workload(task, seed, pool, K, n0, n_tasks=30):
         sources.append((X, fam.evaluate(k, X, rng)))
     rng = np.random.RandomState(2000 + task)
     Xt = synthetic.sample_table(rng, pool, types, const)
-    yt = fam.evaluate(task, Xt, rng)
+    if pool <= 200000:
+        yt = fam.evaluate(task, Xt, rng)
+    else:
+        # chunked: the random-feature map is a [rows, 64] temporary
+        yt = np.concatenate([fam.evaluate(task, Xt[i:i + 200000], rng) for i in range(0, pool, 200000)])
     rows0 = [0] + list(np.random.RandomState(seed + 1).choice(np.arange(1, pool), size=n0 - 1, replace=False))
     return dict(types=types, sources=sources, Xt=Xt, yt=yt, rows0=[int(r) for r in rows0], seed=seed)
 
@@ -187,10 +200,10 @@ def _oracle_facade(method, types, sources, seed, literal, surrogate='gp', mcmc_s
 
 def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, literal=True, surrogate='gp',
                  mcmc_steps=None, mcmc_full=None):
-    """Runs warmup + steps BO iterations of the oracle.  Per step: the full fit + weights
-    (timed), and EI + ordering over the first ``sample_rows`` pool rows (timed, then scaled
-    by pool / sample_rows: the work is exactly linear in the number of candidates).
-    Returns (train_s[], maximize_s_scaled[], setup_s)."""
+    """Runs warmup + steps BO iterations of the oracle.  Per step: the full fit + weights (timed) and
+    EI + ordering over the first ``sample_rows`` pool rows (timed; ``sample_rows`` = 0 or >= pool: the WHOLE
+    pool, measured; otherwise scaled by pool / sample_rows -- the work is linear in the number of candidates).
+    Returns (train_s[], maximize_s[], setup_s)."""
     from oracle.acquisition import OracleEI, first_unevaluated, sort_by_acq_value
     from oracle.facade import zero_mean_unit_var_normalization, zero_one_normalization
     wl = build_workload(task, seed, pool, K, n0)
@@ -205,6 +218,8 @@ def oracle_trial(method, task, seed, pool, K, n0, steps, warmup, sample_rows, li
     np.random.seed(seed)
     acq_rng = np.random.RandomState(seed)
     ei = OracleEI(fac)
+    if not sample_rows or sample_rows >= pool:
+        sample_rows = pool
     Xs = wl['Xt'][:sample_rows]
     evaluated = list(wl['rows0'])
     scale = float(pool) / float(sample_rows)
@@ -232,39 +247,52 @@ def _oracle_worker(args):
     return oracle_trial(*args)
 
 
-def cpu_baseline_sample(args, n_start):
-    """One reference-faithful oracle iteration on this box's host (1 core, BLAS pinned to one
-    thread as the reference mandates), bounded sample.  Runs in a child process so the thread
-    pins take effect before numpy loads."""
+def _maximise_note(sample_rows, pool):
+    if not sample_rows or sample_rows >= pool:
+        return 'EI + sort over ALL %d pool rows (measured)' % pool
+    return 'EI + sort on the first %d of %d pool rows scaled x%.0f' % (sample_rows, pool, pool / float(sample_rows))
+
+
+def cpu_baseline_sample(args, n_start, method=None, pool=None, surrogate=None):
+    """One reference-faithful oracle iteration on this box's host (1 core, BLAS pinned to one thread as the
+    reference mandates), bounded sample.  Runs in a child process so the thread pins take effect before
+    numpy loads."""
+    method = method or args.method
+    pool = pool or args.pool
+    surrogate = surrogate or args.surrogate
+    # bounded: the maximise leg is measured on the whole pool up to 2e5 rows, scaled beyond
+    sample_rows = args.cpu_sample_rows if args.cpu_sample_rows else (0 if pool <= 200000 else 100000)
+
     def child(loops):
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--ref-procs', '1', '--steps', '1',
-               '--warmup', '0', '--n0', str(n_start), '--method', args.method, '--pool', str(args.pool),
-               '--sources', str(args.sources), '--cpu-sample-rows', str(args.cpu_sample_rows),
-               '--pair-loops', loops, '--surrogate', args.surrogate, '--mcmc-steps', str(args.mcmc_steps[0]),
+               '--warmup', '0', '--n0', str(n_start), '--method', method, '--pool', str(pool),
+               '--sources', str(args.sources), '--cpu-sample-rows', str(sample_rows),
+               '--pair-loops', loops, '--surrogate', surrogate, '--mcmc-steps', str(args.mcmc_steps[0]),
                str(args.mcmc_steps[1]), '--cpu-mcmc-steps', str(args.cpu_mcmc_steps)]
         env = dict(os.environ)
         for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
             env.pop(k, None)
-        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1200)
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1800)
         if out.returncode != 0:
             raise RuntimeError('cpu baseline child failed: ' + out.stderr[-2000:])
         return json.loads(out.stdout.strip().splitlines()[-1])
     lit = child('literal')
-    vec = child('vectorised')
-    tr, mx = [lit['train_s_per_step']], [lit['maximize_s_per_step_scaled']]
-    t = tr[0] + mx[0]
-    tv = vec['train_s_per_step'] + vec['maximize_s_per_step_scaled']
-    return dict(value=1.0 / t, unit=UNIT, cores=1, kind='port',
-                sample=('1 BO iteration of the numpy/scipy oracle at target n=%d, K=%d: fit+weights at full size '
-                        '(literal Python pair loops as the reference), EI+sort on the first %d of %d pool rows '
-                        'scaled x%.0f' % (n_start, args.sources, args.cpu_sample_rows, args.pool,
-                                          args.pool / args.cpu_sample_rows)) + _mcmc_sample_note(args),
-                train_s=tr[0], maximize_s_scaled=mx[0],
-                value_vectorised_pair_count=1.0 / tv, host_cores_available=os.cpu_count())
+    t = lit['train_s_per_step'] + lit['maximize_s_per_step_scaled']
+    rec = dict(value=1.0 / t, unit=UNIT, cores=1, kind='port',
+               sample=('1 BO iteration of the numpy/scipy oracle at target n=%d, K=%d: fit+weights at full size '
+                       '(literal Python pair loops as the reference), %s' % (n_start, args.sources,
+                                                                             _maximise_note(sample_rows, pool)))
+               + _mcmc_sample_note(args, surrogate),
+               train_s=lit['train_s_per_step'], maximize_s=lit['maximize_s_per_step_scaled'],
+               host_cores_available=os.cpu_count())
+    if method in ('rgpe', 'trans_rgpe') and surrogate == 'gp':
+        vec = child('vectorised')
+        rec['value_vectorised_pair_count'] = 1.0 / (vec['train_s_per_step'] + vec['maximize_s_per_step_scaled'])
+    return rec
 
 
-def _mcmc_sample_note(args):
-    if args.surrogate != 'gp_mcmc':
+def _mcmc_sample_note(args, surrogate=None):
+    if (surrogate or args.surrogate) != 'gp_mcmc':
         return ''
     return ('; gp_mcmc: chains of %d+%d emcee steps timed, fit time scaled to %d+%d steps (linear in the number '
             'of log-probability evaluations)' % (args.cpu_mcmc_steps, args.cpu_mcmc_steps, args.mcmc_steps[0],
@@ -294,9 +322,8 @@ def run_reference_arm(args):
     total = max(per_proc)
     value = P * args.steps / total
     sample = ('%d parallel single-thread processes (one BO trial each: -- TRIALS --; as the reference pins BLAS to 1 '
-              'thread); per step: fit+weights at full size (PAIRLOOPS pair loops), EI+sort on the first %d of '
-              '%d pool rows scaled x%.0f; target n=%d..%d'
-              % (P, args.cpu_sample_rows, args.pool, args.pool / args.cpu_sample_rows, n_start + args.warmup,
+              'thread); per step: fit+weights at full size (PAIRLOOPS pair loops), %s; target n=%d..%d'
+              % (P, _maximise_note(args.cpu_sample_rows, args.pool), n_start + args.warmup,
                  n_start + args.warmup + args.steps - 1)).replace('PAIRLOOPS', args.pair_loops)
     sample = sample.replace('-- TRIALS --', 'distinct tasks / seeds' if args.distinct_trials else 'replicas of trial 0')
     sample += _mcmc_sample_note(args)
@@ -304,7 +331,7 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, 'cpu'),
+        'config': workload_config(args),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': P, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': wall,
@@ -316,96 +343,123 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, where):
+def workload_config(args, method=None, pool=None, surrogate=None, distinct=None):
+    """The workload description -- IDENTICAL in both arms (the driver compares the dicts)."""
+    method = method or args.method
+    pool = pool or args.pool
+    surrogate = surrogate or args.surrogate
+    distinct = getattr(args, 'distinct_trials', False) if distinct is None else distinct
     return {
         'workload': '%s offline BO, %d source %s x 50 obs, %d-candidate EI pool, d=9 random_forest space, '
-                    'target n=%d..%d' % (args.method, args.sources,
-                                         'GPs' if args.surrogate == 'gp' else 'MCMC-marginalised GPs (34 walkers)',
-                                         args.pool, args.n0 + args.warmup, args.n0 + args.warmup + args.steps - 1),
-        'method': args.method, 'sources': args.sources, 'pool': args.pool, 'd': 9,
-        'surrogate': args.surrogate,
-        'restarts_per_fit': 11 if args.surrogate == 'gp' else None,
-        'fits_per_iter': 6 if args.method in ('rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'obtl') else 1,
-        'mcmc': (None if args.surrogate == 'gp' else
+                    'target n=%d..%d' % (method, args.sources,
+                                         'GPs' if surrogate == 'gp' else 'MCMC-marginalised GPs (34 walkers)',
+                                         pool, args.n0 + args.warmup, args.n0 + args.warmup + args.steps - 1),
+        'method': method, 'sources': args.sources, 'pool': pool, 'd': 9,
+        'surrogate': surrogate,
+        'restarts_per_fit': 11 if surrogate == 'gp' else None,
+        'fits_per_iter': 6 if method in ('rgpe', 'trans_rgpe', 'topo', 'topo_v3', 'obtl') else 1,
+        'mcmc': (None if surrogate == 'gp' else
                  {'walkers': 34, 'burnin_steps': args.mcmc_steps[0], 'chain_steps': args.mcmc_steps[1],
                   'log_prob_evals_per_fit': 34 * (sum(args.mcmc_steps) + 2)}),
-        'l2': ('flushed before every step (256 MiB device memset inside the timed region)' if where == 'gpu'
-               else 'n/a (host)'),
+        'l2': 'CUDA arm: flushed before every step (256 MiB device memset inside the timed region); CPU arm: n/a (host)',
         'multi_gpu': ('independent BO trials per rank, no data-path collective; ' +
-                      ('distinct target task / seed per rank' if getattr(args, 'distinct_trials', False)
+                      ('distinct target task / seed per rank' if distinct
                        else 'every rank runs a replica of trial 0 (identical per-GPU work)')),
-        'resident': 'candidate pool, fitted surrogates and the source surrogates\' pool posteriors stay in HBM',
+        'resident': 'CUDA arm: candidate pool, fitted surrogates and the source surrogates\' pool posteriors stay in HBM',
     }
 
 
 # ---------------------------------------------------------------------------------------------
-def make_product(args, wl, shard=None):
+def make_product(args, wl, shard=None, method=None, surrogate=None):
     from tlbo_b200.config_space import TableSpace
     from tlbo_b200.facade.pogpe import POGPE
     from tlbo_b200.facade.rgpe import RGPE, TransBO_RGPE
     from tlbo_b200.facade.topo_variant1 import OBTL, OBTLV, TOPO_V3
     from tlbo_b200.facade.tst import TST
     from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
-    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, obtl=OBTL, tst=TST, pogpe=POGPE)[args.method]
+    method = method or args.method
+    surrogate = surrogate or args.surrogate
+    cls = dict(rgpe=RGPE, trans_rgpe=TransBO_RGPE, topo=OBTLV, topo_v3=TOPO_V3, obtl=OBTL, tst=TST, pogpe=POGPE)[method]
     cs = TableSpace(wl['types'])
     kw = {}
-    if args.surrogate == 'gp_mcmc':
+    if surrogate == 'gp_mcmc':
         kw['mcmc_steps'] = tuple(args.mcmc_steps)
-    fac = cls(cs, wl['sources'], None, wl['seed'], surrogate_type=args.surrogate, num_src_hpo_trial=50, **kw)
+    fac = cls(cs, wl['sources'], None, wl['seed'], surrogate_type=surrogate, num_src_hpo_trial=50, **kw)
     smbo = SMBO_OFFLINE((wl['Xt'], wl['yt']), cs, fac, random_seed=wl['seed'], max_runs=10 ** 9, shard=shard)
     smbo.configurations = list(wl['rows0'])
     smbo.perfs = [float(wl['yt'][r]) for r in wl['rows0']]
     return fac, smbo
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from tlbo_b200 import ops
+class Comm(object):
+    """Process-group helpers: barrier + synchronize, max / all-gather of a scalar over the ranks."""
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py (impl=ours) needs a CUDA device; there is no CPU fallback')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise RuntimeError('bench.py (impl=ours) needs a CUDA device; there is no CPU fallback')
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device('cuda', self.local_rank)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def all_ranks(x):
-        if world == 1:
+    def all_ranks(self, x):
+        if self.world == 1:
             return [x]
-        t = torch.zeros(world, dtype=torch.float64, device=dev)
-        t[rank] = x
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.dev)
+        t[self.rank] = x
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return [float(v) for v in t.tolist()]
 
-    per_rank = []
-    # N > 1: independent BO trials, one per rank, no data-path collective.  By default every rank runs a
-    # replica of trial 0 so that the per-GPU work is IDENTICAL to the N = 1 run (weak scaling then
-    # measures the system, not the trial-to-trial spread of L-BFGS-B / SLSQP iteration counts, which is
-    # +-15 % and would be charged to the slowest rank); --distinct-trials gives each rank its own task/seed.
-    trial = rank if args.distinct_trials else 0
-    wl = build_workload(trial % 30, 4465 + trial, args.pool, args.sources, args.n0)
-    fac, smbo = make_product(args, wl)
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def _peaks():
+    peaks = {}
+    pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            peaks = json.load(f)
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    hbm_src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    return hbm_peak, hbm_src
+
+
+def measure_offline(args, comm, flush, dmma_tf, method, pool, surrogate='gp', distinct=False, passes=1,
+                    want_all_surrogates=False):
+    """One offline-BO measurement: W warm-up steps, `passes` un-instrumented passes of EXACTLY K steps each
+    over the same trajectory (median reported; every pass bracketed by barrier + synchronize, max over
+    ranks), one pass with a CUDA-event pair around every C-ABI call (roofline / step breakdown), `passes`
+    end-to-end passes (candidate table re-uploaded from pinned host memory every step).  Returns the record
+    (every rank) -- the caller prints rank 0's."""
+    import torch
+    from tlbo_b200 import ops
+    K, W = args.steps, args.warmup
+    world = comm.world
+    trial = comm.rank if distinct else 0
+    wl = build_workload(trial % 30, 4465 + trial, pool, args.sources, args.n0)
+    fac, smbo = make_product(args, wl, method=method, surrogate=surrogate)
     d_cont = int((wl['types'] == 0).sum())
     d_cat = int((wl['types'] != 0).sum())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    dmma_tf = ops.fp64_peak_probe()
-    K, W = args.steps, args.warmup
 
     def step(e2e):
         flush.zero_()
@@ -414,15 +468,10 @@ def run_ours(args):
         cfg, _, _, _ = smbo.iterate()
         return cfg.index
 
-    # ---- warm-up (the clock sampler runs from here to the end of the last timed region)
-    # one sampler for the whole job (rank 0's GPU): eight nvidia-smi pollers contend for the driver
-    # lock with the ranks' own launches and synchronisations
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     for _ in range(W):
         step(False)
     snap = (list(smbo.configurations), list(smbo.perfs))
+    per_rank = []
 
     def timed(e2e, record_flops):
         smbo.configurations, smbo.perfs = list(snap[0]), list(snap[1])
@@ -431,7 +480,7 @@ def run_ours(args):
         flops = 0.0
         cached_reads = 0.0
         fitfl, fitev = 0.0, 0
-        barrier()
+        comm.barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -444,81 +493,93 @@ def run_ours(args):
                 n_src_used = sum(1 for k in range(fac.K) if not skip[k])
                 cached = bool(getattr(fac, '_pool_cache', None))
                 ns = ([] if cached else [50] * n_src_used) + [n_t]
-                if args.surrogate == 'gp_mcmc':
+                if surrogate == 'gp_mcmc':
                     ns = [n_t] * fac._G          # the target's walker GPs (tlbo_predict_pool_posteriors)
-                flops += fused_flops_per_candidate(ns, d_cont, d_cat) * args.pool
-                cached_reads += (16.0 * n_src_used * args.pool) if cached else 0.0
+                flops += fused_flops_per_candidate(ns, d_cont, d_cat) * pool
+                cached_reads += (16.0 * n_src_used * pool) if cached else 0.0
                 ff, fe = fit_flops(getattr(fac, 'last_fit_models', []), d_cont, d_cat)
                 fitfl += ff
                 fitev += fe
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        barrier()
+        comm.barrier()
         mine = e0.elapsed_time(e1)
-        ms = max_over_ranks(mine)
-        per_rank.append(all_ranks(mine))
+        ms = comm.max_over_ranks(mine)
+        per_rank.append(comm.all_ranks(mine))
         ops.STATS.timing = False
         return ms, wall, (flops, fitfl, fitev, cached_reads)
 
-    # (1) headline region: no instrumentation; (2) the same K steps again with a CUDA-event pair
-    # around every C-ABI call (kernel durations for the roofline / step breakdown)
-    ms_res, wall_res, _ = timed(False, False)
+    res_passes = [timed(False, False) for _ in range(passes)]
     launches = ops.STATS.total_launches()
     launch_detail = dict(ops.STATS.launches)
     ms_ins, _, (flops, fitfl, fitev, cached_reads) = timed(False, True)
     kms = ops.STATS.kernel_ms()
-    ms_e2e, wall_e2e, _ = timed(True, False)
-    clocks = sampler.stop()
+    e2e_passes = [timed(True, False) for _ in range(passes)]
     h2d_step = ops.STATS.h2d / float(K)
     d2h_step = ops.STATS.d2h / float(K)
+    order = sorted(range(passes), key=lambda i: res_passes[i][0])
+    mid = order[passes // 2]
+    ms_res, wall_res = res_passes[mid][0], res_passes[mid][1]
+    ms_e2e = sorted(p[0] for p in e2e_passes)[passes // 2]
 
-    # ---- pool-sharded variant of ONE trial (all ranks fit redundantly, each scores a row
-    # range, NCCL all-gather of the per-rank arg-max)
-    pool_sharded = None
-    if world > 1 and not args.no_pool_sharded:
-        from tlbo_b200.distributed import PoolShard
-        wl0 = build_workload(0, 4465, args.pool * world, args.sources, args.n0)
-        shard = PoolShard()
-        fac_s, smbo_s = make_product(args, wl0, shard=shard)
-        for _ in range(W):
-            smbo_s.iterate()
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            smbo_s.iterate()
-        e1.record()
-        torch.cuda.synchronize()
-        barrier()
-        ms_s = max_over_ranks(e0.elapsed_time(e1))
-        pool_sharded = {'value': K / (ms_s * 1e-3), 'unit': UNIT, 'pool_rows_total': args.pool * world,
-                        'collective': 'all_gather of 4 doubles per rank (NCCL)', 'ms_per_step': ms_s / K,
-                        'rows_selected': smbo_s.configurations[-3:]}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    # ---- all K + 1 surrogates evaluated over the pool, nothing resident (the reference's predict shape):
+    # the "GP predict candidates / sec" half of the metric on THIS workload
+    all_sur = None
+    if want_all_surrogates and surrogate == 'gp':
+        acq = smbo.acq_optimizer
+        saved = fac._pool_cache
+        saved_flags = getattr(fac, 'ignored_flag', None)
+        fac._pool_cache = {}
+        if saved_flags is not None:
+            fac.ignored_flag = [False] * fac.K       # weight-dilution pruning off: EVERY surrogate is evaluated
+        try:
+            keys = acq._keys_full[acq._key_cur][acq.lo:acq.hi] if acq._device_keys else acq._keys_dev
+            for _ in range(2):
+                smbo.acquisition_function.best_unevaluated(acq.X_dev, keys=keys, excluded=None, ws=acq._ws, sync=True)
+            reps = 5
+            comm.barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                flush.zero_()
+                smbo.acquisition_function.best_unevaluated(acq.X_dev, keys=keys, excluded=None, ws=acq._ws, sync=False)
+            e1.record()
+            torch.cuda.synchronize()
+            e2 = torch.cuda.Event(enable_timing=True)
+            e3 = torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for _ in range(reps):
+                flush.zero_()
+            e3.record()
+            torch.cuda.synchronize()
+            ms_all = (e0.elapsed_time(e1) - e2.elapsed_time(e3)) / reps
+        finally:
+            fac._pool_cache = saved
+            if saved_flags is not None:
+                fac.ignored_flag = saved_flags
+        n_t = len(smbo.configurations)
+        n_used = fac.K
+        fl = fused_flops_per_candidate([50] * n_used + [n_t], d_cont, d_cat) * pool
+        all_sur = {'surrogates_evaluated': n_used + 1, 'ms_per_launch': ms_all,
+                   'candidates_per_s': pool / (ms_all * 1e-3), 'tflops_algorithmic': fl / (ms_all * 1e-3) / 1e12,
+                   'frac_of_dmma_peak': fl / (ms_all * 1e-3) / 1e12 / dmma_tf[1],
+                   'note': 'fused predict + EI + arg-max with ALL K source surrogates (weight-dilution pruning off) AND '
+                           'the target evaluated per candidate, no resident posteriors, L2 flushed between launches '
+                           '(flush time subtracted)'}
 
     # ---- roofline of the fused predict + EI + arg-max kernel
-    fused_name = 'predict_ei_fused' if args.surrogate == 'gp' else 'predict_pool_posteriors'
+    fused_name = 'predict_ei_fused' if surrogate == 'gp' else 'predict_pool_posteriors'
     fused_calls, fused_ms = kms.get(fused_name, (0, 0.0))
-    peaks = {}
-    pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(pk_path):
-        with open(pk_path) as f:
-            peaks = json.load(f)
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    hbm_src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    hbm_peak, hbm_src = _peaks()
     traffic = None
     tr_path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-    if os.path.exists(tr_path):
+    if os.path.exists(tr_path) and pool == 100000 and method == 'rgpe':
         with open(tr_path) as f:
             traffic = json.load(f).get('predict_ei_fused_dram_bytes_per_launch')
     ach_tf = flops / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else 0.0
-    alg_bytes = args.pool * (8.0 * 9 + 8.0) + cached_reads / max(fused_calls, 1)
+    alg_bytes = pool * (8.0 * 9 + 8.0) + cached_reads / max(fused_calls, 1)
     ach_gbs = alg_bytes * fused_calls / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
     roofline = {
         'kernel': 'predict_ei_fused_kernel', 'bound': 'tensor', 'achieved': ach_tf, 'peak': dmma_tf[1],
@@ -532,9 +593,9 @@ def run_ours(args):
         'note': 'flops by SURVEY.md 8(d) (triangular L^-1 form) over the surrogates actually EVALUATED per launch; '
                 'the source surrogates\' posteriors over the fixed pool are computed once at maximiser construction '
                 'and read back from HBM (16 B per candidate and source, counted in algorithmic_bytes_per_launch); '
-                'arithmetic intensity ~%.0f flop/B. With every surrogate evaluated (no resident posteriors) the '
-                'same kernel sustains 17-28%% of the FP64 peak: profiles/r1_predict_sweep.json' % (
-                    flops / max(fused_calls, 1) / alg_bytes),
+                'arithmetic intensity ~%.0f flop/B. The all-surrogates figure of the same kernel is in '
+                '"predict_all_surrogates" and the "predict_sweep" sub-record' % (
+                    flops / max(fused_calls, 1) / max(alg_bytes, 1.0)),
     }
     fit_calls, fit_ms = kms.get('gp_fit', (0, 0.0))
     # launches on side streams that run UNDER other kernels (the look-ahead tie-break key generator: one CTA,
@@ -552,19 +613,6 @@ def run_ours(args):
         'back to back; the launch lasts as long as the slowest restart (see DESIGN.md 3.1, tools/phase_fit.py)',
         'peak_source': 'FP64 FMA-pipe rate measured by tlbo_fp64_peak_probe in this run',
     }
-    roofline_mcmc = None
-    if args.surrogate == 'gp_mcmc':
-        ch_calls, ch_ms = kms.get('gp_mcmc_chain', (0, 0.0))
-        half = 2 * sum(args.mcmc_steps) + 2
-        roofline_mcmc = {
-            'kernel': 'gp_mcmc_kernel (persistent cooperative launch, one CTA per (surrogate, active walker))',
-            'bound': 'latency', 'avg_launch_ms': ch_ms / max(ch_calls, 1),
-            'sequential_log_prob_evaluations_per_launch': half,
-            'us_per_half_step': 1e3 * ch_ms / max(ch_calls, 1) / half,
-            'log_prob_evaluations_per_launch': 6 * fac._G * (sum(args.mcmc_steps) + 2),
-            'note': 'one half-step = one kernel-matrix build + register-panel Cholesky + barrier among the '
-                    'W/2 CTAs of a surrogate; SURVEY 8(d): latency-bound, report time not a roofline fraction',
-        }
     step_ms = ms_res / K
     breakdown = {k: {'calls_per_step': c / float(K), 'ms_per_step': t / K, 'share_of_step': t / ms_ins}
                  for k, (c, t) in kms.items()}
@@ -573,31 +621,235 @@ def run_ours(args):
             breakdown[k]['overlapped'] = ('side stream, concurrent with the host post-processing and the next fit kernel; '
                                           'the event pair also spans its wait for SM resources behind the previous '
                                           'fused kernel -- not part of the critical path')
-    line = {
+    rec = {
         'metric': METRIC, 'value': world * K / (ms_res * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, 'gpu'),
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, method=method, pool=pool, surrogate=surrogate, distinct=distinct),
         'e2e': {'value': world * K / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_step,
                 'd2h_bytes_per_step': d2h_step, 'ms_per_step': ms_e2e / K,
                 'api': 'SMBO_OFFLINE.iterate() with the candidate table re-uploaded from pinned host memory '
                        'every step and the selected row read back'},
         'gpu_launches': launches, 'gpu_launch_detail': launch_detail,
-        'clocks': clocks, 'roofline': roofline, 'roofline_fit': roofline_fit, 'dominant_kernel': dominant,
+        'timed_passes': {'passes': passes, 'steps_per_pass': K, 'statistic': 'median pass (max over ranks per pass)',
+                         'ms_per_step': [round(p[0] / K, 4) for p in res_passes],
+                         'e2e_ms_per_step': [round(p[0] / K, 4) for p in e2e_passes],
+                         'timed_region_s_total': sum(p[0] for p in res_passes) * 1e-3},
+        'roofline': roofline, 'roofline_fit': roofline_fit, 'dominant_kernel': dominant,
         'step_breakdown': breakdown,
-        'predict_candidates_per_s': args.pool * fused_calls / (fused_ms * 1e-3) if fused_ms > 0 else None,
         'host_wall_ms_per_step': 1e3 * wall_res / K, 'instrumented_ms_per_step': ms_ins / K,
-        'per_rank_ms_per_step': [round(v / K, 4) for v in per_rank[0]],
+        'per_rank_ms_per_step': [round(v / K, 4) for v in per_rank[mid]],
     }
-    if roofline_mcmc is not None:
-        line['roofline_mcmc'] = roofline_mcmc
-        line['roofline']['kernel'] = 'predict_ei_fused_kernel (per-walker posterior mode: tlbo_predict_pool_posteriors)'
-    if pool_sharded is not None:
-        line['pool_sharded'] = pool_sharded
+    if all_sur is not None:
+        rec['predict_all_surrogates'] = all_sur
+        rec['predict_candidates_per_s'] = all_sur['candidates_per_s']
+    if surrogate == 'gp_mcmc':
+        ch_calls, ch_ms = kms.get('gp_mcmc_chain', (0, 0.0))
+        half = 2 * sum(args.mcmc_steps) + 2
+        rec['roofline_mcmc'] = {
+            'kernel': 'gp_mcmc_kernel (persistent cooperative launch, one CTA per (surrogate, active walker))',
+            'bound': 'latency', 'avg_launch_ms': ch_ms / max(ch_calls, 1),
+            'sequential_log_prob_evaluations_per_launch': half,
+            'us_per_half_step': 1e3 * ch_ms / max(ch_calls, 1) / half,
+            'log_prob_evaluations_per_launch': 6 * fac._G * (sum(args.mcmc_steps) + 2),
+            'note': 'one half-step = one kernel-matrix build + register-panel Cholesky + barrier among the '
+                    'W/2 CTAs of a surrogate; SURVEY 8(d): latency-bound, report time not a roofline fraction',
+        }
+        rec['roofline']['kernel'] = 'predict_ei_fused_kernel (per-walker posterior mode: tlbo_predict_pool_posteriors)'
+    del fac, smbo
+    torch.cuda.empty_cache()
+    return rec
+
+
+def measure_pool_strong(args, comm, flush, pool_total):
+    """ONE BO trial over a FIXED pool of `pool_total` rows sharded by rows over the ranks (strong scaling):
+    every rank fits redundantly (deterministic), scores its row range, and the ranks all-gather the 32-byte
+    (ei, key, row, #negative) quadruple and merge it on the device."""
+    import torch
+    from tlbo_b200.distributed import PoolShard
+    K, W = args.steps, args.warmup
+    wl0 = build_workload(0, 4465, pool_total, args.sources, args.n0)
+    shard = PoolShard() if comm.world > 1 else None
+    fac_s, smbo_s = make_product(args, wl0, shard=shard, method='rgpe', surrogate='gp')
+
+    def step():
+        flush.zero_()
+        smbo_s.iterate()
+    for _ in range(W):
+        step()
+    comm.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    comm.barrier()
+    ms_s = comm.max_over_ranks(e0.elapsed_time(e1))
+    rec = {'metric': METRIC, 'value': K / (ms_s * 1e-3), 'unit': UNIT, 'scaling': 'strong', 'n_gpus': comm.world,
+           'pool_rows_total': pool_total, 'pool_rows_per_rank': (pool_total + comm.world - 1) // comm.world,
+           'collective': ('all_gather of 4 doubles per rank (NCCL), merged on the device' if comm.world > 1 else 'none'),
+           'ms_per_step': ms_s / K, 'rows_selected': [int(r) for r in smbo_s.configurations[-3:]],
+           'note': 'fit + weights run redundantly on every rank (deterministic), so the strong-scaling limit of the '
+                   'step is the fit; the tie-break keys rng.rand(N) of the WHOLE pool are generated on every rank '
+                   '(MT19937 is sequential; see DESIGN.md)'}
+    del fac_s, smbo_s
+    torch.cuda.empty_cache()
+    return rec
+
+
+def predict_sweep(dmma_tf, max_rows):
+    """BASELINE configs[3]: 30 surrogates x n in {50,100,200} x N candidates x d in {5,20}, every surrogate
+    evaluated per candidate (nothing resident): candidates / s and the fraction of the FP64 DMMA peak."""
+    import torch
+    from tlbo_b200 import ops
+    dev = torch.device('cuda')
+    rows = []
+    M = 30
+    for d in (5, 20):
+        types = np.zeros(d, int)
+        for n in (50, 100, 200):
+            rng = np.random.RandomState(100 * d + n)
+            pack = ops.SurrogatePack(M, n, d)
+            Xs, ys, ths, yms, yss = [], [], [], [], []
+            for m in range(M):
+                X = rng.rand(n, d)
+                y = np.sin(X.sum(1) * (1 + 0.1 * m)) + 0.05 * rng.randn(n)
+                th = np.concatenate([[rng.uniform(-0.5, 1.0)], rng.uniform(-1.2, 0.05, d), [rng.uniform(-9, -5)]])
+                Xs.append(X); ys.append((y - y.mean()) / y.std()); ths.append(th); yms.append(y.mean()); yss.append(y.std())
+            st = ops.gp_factorize_batched(Xs, ys, types, ths, yms, yss, pack)
+            assert not np.asarray(st).any()
+            w = torch.full((M,), 1.0 / M, dtype=torch.float64, device=dev)
+            flops_per_cand = 30.0 + M * (n * (3 * d + 12) + 2 * n + n * n + 2 * n)
+            for N in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7):
+                if N > max_rows:
+                    continue
+                Xc = torch.rand(N, d, dtype=torch.float64, device=dev)
+                keys = torch.rand(N, dtype=torch.float64, device=dev)
+                ws = ops.FusedWorkspace()
+                ops.predict_ei_fused(pack, types, w, None, Xc, 0.1, keys=keys, ws=ws, nmax=n)
+                reps = 2 if N >= 10 ** 7 else (3 if N >= 10 ** 6 else 10)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    ops.predict_ei_fused(pack, types, w, None, Xc, 0.1, keys=keys, ws=ws, nmax=n, sync=False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                rows.append(dict(d=d, n=n, M=M, N=N, ms=ms, candidates_per_s=N / (ms * 1e-3),
+                                 tflops_algorithmic=flops_per_cand * N / (ms * 1e-3) / 1e12,
+                                 frac_of_dmma_peak=flops_per_cand * N / (ms * 1e-3) / 1e12 / dmma_tf[1],
+                                 hbm_gbs_algorithmic=N * 8.0 * (d + 1) / (ms * 1e-3) / 1e9))
+                del Xc, keys
+            del pack
+    torch.cuda.empty_cache()
+    best = max(rows, key=lambda r: r['frac_of_dmma_peak'])
+    return {'metric': 'GP predict candidates/sec (30 surrogates, fused mean / variance / EI / arg-max)',
+            'unit': 'candidates/s', 'rows': rows, 'dmma_peak_tflops': dmma_tf[1],
+            'best_frac_of_dmma_peak': best['frac_of_dmma_peak'],
+            'flops': 'SURVEY.md 8(d), triangular form: 30 + M (n (3 d + 12) + 2 n + n^2 + 2 n) per candidate',
+            'l2': 'pools >= 1e6 rows exceed L2 (126 MB); smaller pools are L2-resident between repetitions',
+            'parity': 'tests/test_gpu_kernels.py and tools/predict_sweep.py check the same launches against the oracle'}
+
+
+def sweep_cpu_baseline():
+    """Oracle posterior over a bounded sample for one sweep cell (30 surrogates, n = 50, d = 5), one core."""
+    from oracle import gp as ogp
+    d, n, M, rows = 5, 50, 30, 2000
+    types = np.zeros(d, int)
+    spec = ogp.KernelSpec(types)
+    rng = np.random.RandomState(100 * d + n)
+    gs = []
+    for m in range(M):
+        X = rng.rand(n, d)
+        y = np.sin(X.sum(1) * (1 + 0.1 * m)) + 0.05 * rng.randn(n)
+        th = np.concatenate([[rng.uniform(-0.5, 1.0)], rng.uniform(-1.2, 0.05, d), [rng.uniform(-9, -5)]])
+        g = ogp.OracleGP(types, 1)
+        g.X = X; g.y = (y - y.mean()) / y.std(); g.spec = spec; g.mean_y = y.mean(); g.std_y = y.std()
+        g._fit_at(th); g.is_trained = True
+        gs.append(g)
+    Xq = rng.rand(rows, d)
+    t0 = time.perf_counter()
+    for g in gs:
+        g.predict(Xq)
+    dt = time.perf_counter() - t0
+    return {'value': rows / dt, 'unit': 'candidates/s', 'cores': 1, 'kind': 'port',
+            'sample': 'oracle GaussianProcess.predict (the reference\'s K_inv_ einsum form) of %d surrogates '
+                      '(n = %d, d = %d) over %d candidates' % (M, n, d, rows)}
+
+
+def run_ours(args):
+    import torch
+    from tlbo_b200 import ops
+    comm = Comm()
+    rank, world = comm.rank, comm.world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=comm.dev)
+    dmma_tf = ops.fp64_peak_probe()
+    if args.sub == 'auto':
+        subs = ['pool_strong']
+        if world == 1:
+            subs = ['topo', 'pool_1e6', 'predict_sweep', 'pool_strong']
+        else:
+            subs = ['distinct_trials', 'pool_strong'] + (['gp_mcmc'] if world >= 8 else [])
+    elif args.sub in ('none', ''):
+        subs = []
+    else:
+        subs = [x.strip() for x in args.sub.split(',') if x.strip()]
+    if args.method != 'rgpe' or args.surrogate != 'gp' or args.pool != 100000:
+        subs = [x for x in subs if x in ('pool_strong', 'distinct_trials')] if args.sub == 'auto' else subs
+
+    # one clock sampler for the whole job (rank 0's GPU): eight nvidia-smi pollers contend for the driver
+    # lock with the ranks' own launches and synchronisations
+    sampler = ClockSampler(comm.local_rank)
+    if rank == 0:
+        sampler.start()
+    line = measure_offline(args, comm, flush, dmma_tf, args.method, args.pool, args.surrogate,
+                           distinct=args.distinct_trials, passes=max(1, args.passes), want_all_surrogates=True)
+    sub = {}
+    for name in subs:
+        t0 = time.perf_counter()
+        if name == 'topo':
+            rec = measure_offline(args, comm, flush, dmma_tf, 'topo', args.pool, 'gp', passes=2)
+        elif name == 'pool_1e6':
+            rec = measure_offline(args, comm, flush, dmma_tf, 'rgpe', 1000000, 'gp', passes=2, want_all_surrogates=True)
+        elif name == 'distinct_trials':
+            rec = measure_offline(args, comm, flush, dmma_tf, args.method, args.pool, args.surrogate, distinct=True,
+                                  passes=2)
+            rec['note'] = ('every rank runs its OWN target task / seed; the slowest rank is charged (L-BFGS-B / SLSQP '
+                           'iteration counts differ from trial to trial by about +-15 %)')
+        elif name == 'gp_mcmc':
+            rec = measure_offline(args, comm, flush, dmma_tf, 'topo', args.pool, 'gp_mcmc', distinct=True, passes=1)
+        elif name == 'pool_strong':
+            rec = measure_pool_strong(args, comm, flush, args.strong_pool)
+        elif name == 'predict_sweep':
+            rec = predict_sweep(dmma_tf, 10 ** 7) if rank == 0 else None
+            comm.barrier()
+        else:
+            continue
+        if rec is not None:
+            rec['record_wall_s'] = time.perf_counter() - t0
+        sub[name] = rec
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        comm.close()
+        return
+    line['clocks'] = clocks
     if world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline_sample(args, args.n0 + W)
+        n_start = args.n0 + args.warmup
+        line['cpu_baseline'] = cpu_baseline_sample(args, n_start)
+        if 'topo' in sub:
+            sub['topo']['cpu_baseline'] = cpu_baseline_sample(args, n_start, method='topo')
+        if 'pool_1e6' in sub:
+            sub['pool_1e6']['cpu_baseline'] = cpu_baseline_sample(args, n_start, pool=1000000)
+        if 'predict_sweep' in sub:
+            sub['predict_sweep']['cpu_baseline'] = sweep_cpu_baseline()
+    if sub:
+        line['sub'] = sub
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    comm.close()
 
 
 def main():

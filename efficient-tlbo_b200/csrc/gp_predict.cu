@@ -815,6 +815,15 @@ static int fused_entry(const tlbo_pack* pack, const int32_t* h_types, const doub
   return 0;
 }
 
+// Merge of `nparts` (ei, key, row, #negative) quadruples with the rule of the fused kernel's own final stage:
+// the exchange step of the row-sharded candidate pool (the quadruples all-gathered from the ranks).
+extern "C" int tlbo_merge_best(const double* d_quads, int nparts, double* d_best, void* stream) {
+  if (!d_quads || !d_best || nparts <= 0) { tlbo_set_error("bad arguments"); return TLBO_E_BADARG; }
+  argmax_final_kernel<<<1, ARGMAX_FINAL_THREADS, 0, (cudaStream_t)stream>>>(d_quads, nparts, d_best);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
                                      const int32_t* d_skip, const int32_t* d_order, int mode,
                                      const double* d_cand, int64_t N,

@@ -46,6 +46,7 @@ SYMBOLS = {
     'tlbo_predict_ei_fused': (c_int, [POINTER(TlboPack), _P, _P, _P, _P, c_int, _P, c_int64, c_double, c_double,
                                       c_double, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
     'tlbo_predict_ei_workspace_bytes': (c_int64, [c_int64]),
+    'tlbo_merge_best': (c_int, [_P, c_int, _P, _P]),
     'tlbo_predict_pool_posteriors': (c_int, [POINTER(TlboPack), _P, _P, c_int64, _P, _P, _P, _P]),
     'tlbo_predict_ei_fused_cached': (c_int, [POINTER(TlboPack), _P, _P, _P, _P, c_int, _P, c_int64, c_double, c_double,
                                              c_double, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),

@@ -44,6 +44,7 @@ class PoolShard(object):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        self._gather = None
 
     def row_range(self, N):
         per = (N + self.world_size - 1) // self.world_size
@@ -51,10 +52,28 @@ class PoolShard(object):
         return lo, min(lo + per, N)
 
     def reduce_best(self, best):
-        """All-gather the 4-double result of the fused kernel and merge.  ``best`` is a
-        device tensor under NCCL or a CPU tensor under gloo."""
+        """All-gather the 4-double result of the fused kernel and merge.  ``best`` is a device tensor under
+        NCCL (merged ON the device by ``tlbo_merge_best``, the fused kernel's own final merge stage -- no
+        host round trip between the collective and the merge; the merged
+        quadruple is then read back once, which the caller needs anyway to name the selected row) or a
+        CPU tensor under gloo (merged on the host)."""
         import torch
+        if best.is_cuda:
+            if self._gather is None or self._gather.device != best.device:
+                self._gather = torch.empty(self.world_size, 4, dtype=best.dtype, device=best.device)
+            self.dist.all_gather_into_tensor(self._gather, best.reshape(1, 4), group=self.group)
+            return tuple(merge_best_device(self._gather))
         out = [torch.empty_like(best) for _ in range(self.world_size)]
         self.dist.all_gather(out, best, group=self.group)
         quads = torch.stack(out).cpu().numpy()
         return merge_best(quads)
+
+
+def merge_best_device(q):
+    """``merge_best`` over a device tensor ``q [G, 4]``: ONE launch of the fused kernel's own final merge stage
+    (``tlbo_merge_best``, stream-ordered behind the collective), then the 32-byte read-back."""
+    from tlbo_b200 import ops
+    h = ops.d2h(ops.merge_best(q))
+    if h[2] < 0:
+        return (-np.inf, -np.inf, -1, int(h[3]))
+    return (float(h[0]), float(h[1]), int(h[2]), int(h[3]))

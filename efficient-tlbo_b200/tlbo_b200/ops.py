@@ -143,6 +143,15 @@ class PinnedStage(object):
         return view.to(_dev(), non_blocking=True)
 
 
+def merge_best(quads, out=None):
+    """``tlbo_merge_best``: lexicographic merge of ``quads [G, 4]`` (device) into a device 4-vector."""
+    if out is None:
+        out = torch.empty(4, dtype=F64, device=quads.device)
+    with _call('merge_best', 1):
+        check(lib.tlbo_merge_best(ptr(quads), int(quads.shape[0]), ptr(out), _stream()))
+    return out
+
+
 def d2h(t):
     """Device tensor -> numpy (counted; synchronises)."""
     STATS.d2h += t.numel() * t.element_size()

@@ -152,6 +152,13 @@ int tlbo_predict_ei_fused(const tlbo_pack* pack, const int32_t* h_types, const d
                           double par, double var_floor, const double* d_keys, const int64_t* d_excluded,
                           int n_excl, int64_t idx_offset, double* d_best, double* d_mu, double* d_var,
                           double* d_ei, void* d_work, void* stream);
+/* Exchange step of the row-sharded candidate pool (the reference has no counterpart: its
+ * _sort_configs_by_acq_value, tlbo/optimizer/ei_optimization.py:106-132, orders ONE table in one process): merges
+ * `nparts` (ei, key, global row, #negative EI) quadruples -- the per-rank results of tlbo_predict_ei_fused*,
+ * all-gathered into d_quads[nparts][4] -- with the same lexicographic rule (EI desc, key desc, row desc among
+ * row >= 0) into d_best[4], on the device. */
+int tlbo_merge_best(const double* d_quads, int nparts, double* d_best, void* stream);
+
 int64_t tlbo_predict_ei_workspace_bytes(int64_t N);
 
 /* Resident per-surrogate posteriors.  The source surrogates of a facade never change after

@@ -333,3 +333,29 @@ def test_device_mt19937_equals_numpy_legacy_random_sample():
         a, b = back.get_state(), ref.get_state()
         assert np.array_equal(a[1], b[1]) and a[2] == b[2]
         assert back.rand() == ref.rand()
+
+
+def test_merge_best_matches_host_rule():
+    """tlbo_merge_best (the exchange step of the row-sharded pool) against the host statement of the rule,
+    including ties on EI / key and shards without an unevaluated candidate."""
+    import torch
+    from tlbo_b200 import ops
+    from tlbo_b200.distributed import merge_best
+    rng = np.random.RandomState(5)
+    for G in (1, 2, 8, 37):
+        for case in range(6):
+            q = np.zeros((G, 4))
+            q[:, 0] = rng.choice([0.0, 0.25, 0.5], size=G) if case % 2 else rng.rand(G)
+            q[:, 1] = rng.choice([0.1, 0.9], size=G) if case % 3 == 0 else rng.rand(G)
+            q[:, 2] = rng.permutation(G * 10)[:G]
+            q[rng.rand(G) < 0.3, 2] = -1
+            if case == 5:
+                q[:, 2] = -1
+            q[:, 3] = rng.randint(0, 3, size=G)
+            want = merge_best(q)
+            got = ops.merge_best(torch.from_numpy(q).cuda()).cpu().numpy()
+            assert int(got[3]) == want[3]
+            if want[2] < 0:
+                assert got[2] < 0
+            else:
+                assert (float(got[0]), float(got[1]), int(got[2])) == (want[0], want[1], want[2])
