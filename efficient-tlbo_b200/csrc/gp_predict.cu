@@ -389,15 +389,17 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
     const bool myok = lane < WC && myrow < a.N;
     auto combine = [&](bool first, double wm, double mu_m, double var_m) {
       if (a.mode == 0) {
-        acc_mu += wm * mu_m;
-        acc_var += wm * wm * var_m;
+        // rgpe.py:150-152 / base_facade.py:170-171: `mu += w * mu_t`, `var += w * w * var_t` -- numpy rounds the
+        // product and the sum separately (no FMA contraction: nvcc's -fmad would fuse them)
+        acc_mu = __dadd_rn(acc_mu, __dmul_rn(wm, mu_m));
+        acc_var = __dadd_rn(acc_var, __dmul_rn(__dmul_rn(wm, wm), var_m));
       } else if (a.mode == 2) {
         const double iv = 1.0 / var_m;
         acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
         acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
       } else {
         if (first) { acc_mu = mu_m; acc_var = var_m; }
-        else { acc_mu += wm * mu_m; wsum += wm; }
+        else { acc_mu = __dadd_rn(acc_mu, __dmul_rn(wm, mu_m)); wsum = __dadd_rn(wsum, wm); }
       }
     };
     int li = 0;

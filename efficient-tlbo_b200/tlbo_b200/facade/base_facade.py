@@ -84,6 +84,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self._proto = None            # prototype of a freshly built target-side surrogate
         self._ens_cache = None        # (pack, device weights / skip / order, pack view) of acq_small
         self._pool_cache = {}         # (data_ptr, N) -> resident source posteriors over a fixed pool
+        self._pool_keepalive = None   # the registered pool tensor: while it is alive its address cannot be reused
 
     # ---- device pack ------------------------------------------------------------------
     def _ensure_pack(self, rows):
@@ -360,6 +361,9 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         key = (X_dev.data_ptr(), int(X_dev.shape[0]))
         if key in self._pool_cache:
             return
+        # the cache is keyed by address and length: hold the tensor so that the caching allocator cannot hand
+        # the same address to a different query tensor of the same length while the entry exists
+        self._pool_keepalive = X_dev
         if self._G > 1:
             import torch
             N = int(X_dev.shape[0])

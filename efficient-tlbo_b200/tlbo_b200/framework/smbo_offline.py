@@ -51,6 +51,7 @@ class SMBO_OFFLINE(object):
         self.y_max, self.y_min = np.max(self.ys), np.min(self.ys)
 
         self.configurations = list()        # evaluated ROW INDICES, evaluation order
+        self._default_row_cache = None
         self.failed_configurations = list()
         self.perfs = list()
         self.test_perfs = list()
@@ -139,12 +140,32 @@ class SMBO_OFFLINE(object):
                 sample_cnt = 0
         return rows
 
+    def _default_row(self):
+        """Row of ``config_space.get_default_configuration()`` in the table (first match, as
+        ``default_config not in self.configuration_list`` / list membership compares by value), row 0 when
+        the space has no default or the default is not a table row."""
+        if self._default_row_cache is None:
+            row = 0
+            get = getattr(self.config_space, 'get_default_configuration', None)
+            default = get() if get is not None else None
+            if default is not None:
+                vec = np.asarray(default.get_array(), dtype=np.float64).ravel()
+                if vec.shape[0] == self.X_table.shape[1]:
+                    T = self.X_table
+                    same = ((T == vec[None, :]) | (np.isnan(T) & np.isnan(vec)[None, :])).all(axis=1)
+                    hits = np.nonzero(same)[0]
+                    if len(hits):
+                        row = int(hits[0])
+            self._default_row_cache = row
+        return self._default_row_cache
+
     def choose_next(self, X, Y):
         _config_num = X.shape[0]
         if _config_num < self.init_num:
-            # default configuration if it is a table row, else row 0 (smbo_offline.py:212-215)
-            default_row = 0
-            if 0 not in self.configurations and 0 not in self.failed_configurations:
+            # smbo_offline.py:210-219: the space's default configuration if it is a table row, else the
+            # table's first row; a random unevaluated row once that one has been evaluated
+            default_row = self._default_row()
+            if default_row not in self.configurations and default_row not in self.failed_configurations:
                 return default_row
             return self.sample_random_config()[0]
 

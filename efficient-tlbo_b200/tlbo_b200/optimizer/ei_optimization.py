@@ -8,8 +8,14 @@ The reference scores ONE neighbour per acquisition call inside each hill-climb
 K + 1 GP predicts.  Here a hill-climb step scores the incumbent's WHOLE one-exchange
 neighbourhood in one fused ensemble-predict + EI launch and then takes the first improving
 neighbour -- exactly the neighbour the reference's early ``break`` would have stopped at,
-because the neighbourhood generator draws from a private ``RandomState(seed)`` (so
-materialising it eagerly changes no stream) and the acquisition is deterministic.  The ten
+because the neighbourhood generator draws its neighbours from a private ``RandomState(seed)``
+and the acquisition is deterministic.  (ConfigSpace's lazy generator additionally draws ONE
+``np.random.random()`` from the GLOBAL legacy stream per neighbour it produces -- its "only
+rigorously check every tenth configuration" test --, i.e. one per neighbour the reference's loop
+inspects; the eager path consumes that many draws after scoring, see ``_one_iter``.  Integer
+hyper-parameters are walked like floats here: ConfigSpace enumerates a finite, shuffled
+neighbour list for ``UniformIntegerHyperparameter`` -- a documented deviation, the neighbourhood
+STREAMS are parity-unpinned either way because ConfigSpace is absent from this machine.)  The ten
 start points are scored in one launch, the ~4990 random configurations in another.  Every
 draw from the shared ``rng`` (ordering keys, per-step generator seeds, the tie-break shuffle,
 the interleaving chooser) happens in the reference's order."""
@@ -81,7 +87,13 @@ class LocalSearch(_SortMixin, AcquisitionFunctionMaximizer):
                 stats['launches'] += 1
                 better = np.nonzero(acq[:, 0] > acq_val_incumbent[0])[0]
                 # the reference evaluates lazily and stops at the first improvement
-                stats['neighbours'] += int(better[0]) + 1 if len(better) else len(neighbours)
+                visited = int(better[0]) + 1 if len(better) else len(neighbours)
+                stats['neighbours'] += visited
+                # ConfigSpace's lazy generator draws one np.random.random() from the GLOBAL legacy stream per
+                # neighbour it produces ("only rigorously check every tenth configuration", util.pyx); the
+                # reference's loop produces exactly the `visited` neighbours it inspects.  Same stream position
+                # as the facades' bootstrap draws expect.
+                np.random.random(visited)
                 if len(better):
                     j = int(better[0])
                     incumbent = Configuration(incumbent.space, neighbours[j], -1)

@@ -78,11 +78,12 @@ class OracleSMBOOffline(object):
     """``SMBO_OFFLINE`` (tlbo/framework/smbo_offline.py) over a candidate table
     ``X_table float64[N, d]`` with objective values ``y_table float64[N]``.
 
-    Row 0 of the table plays the role of "default config not in the list ->
-    configuration_list[0]" (:213-215).
+    ``default`` (a configuration vector) plays ``config_space.get_default_configuration()``: the first
+    evaluation is its table row when it is one, else row 0 ("default config not in the list ->
+    configuration_list[0]", :212-215).
     """
 
-    def __init__(self, X_table, y_table, surrogate_model, random_seed, initial_runs=3, max_runs=200):
+    def __init__(self, X_table, y_table, surrogate_model, random_seed, initial_runs=3, max_runs=200, default=None):
         self.X_table = np.asarray(X_table, dtype=np.float64)
         self.y_table = np.asarray(y_table, dtype=np.float64)
         self.random_seed = random_seed
@@ -100,6 +101,11 @@ class OracleSMBOOffline(object):
         self.y_max, self.y_min = np.max(self.y_table), np.min(self.y_table)
         self.last_acq = None
         self.last_keys = None
+        self.default_row = 0
+        if default is not None:
+            hits = np.nonzero((self.X_table == np.asarray(default, dtype=np.float64)[None, :]).all(axis=1))[0]
+            if len(hits):
+                self.default_row = int(hits[0])
 
     def get_adtm(self):
         return (np.min(self.perfs) - self.y_min) / (self.y_max - self.y_min)
@@ -119,8 +125,8 @@ class OracleSMBOOffline(object):
     def choose_next(self, X, Y):
         """:208-264."""
         if X.shape[0] < self.init_num:
-            if 0 not in self.evaluated:
-                return 0
+            if self.default_row not in self.evaluated:
+                return self.default_row
             return self.sample_random_config()
         if self.chooser_rng.rand() < 0.001:                            # ChooserProb.check
             idx = self.sample_random_config()

@@ -99,6 +99,11 @@ class OracleSpace(object):
             n_left[index] -= 1
             if n_left[index] == 0:
                 used.add(index)
+            # ConfigSpace 0.4.x util.pyx: "only rigorously check every tenth configuration":
+            # `if np.random.random() > 0.95: new_configuration.is_valid_configuration()` -- one draw from the
+            # GLOBAL legacy stream per produced neighbour (the stream the facades' bootstrap draws use), and the
+            # generator is lazy, so only the neighbours the hill-climb actually inspects consume one
+            np.random.random()
             yield new_array
 
 

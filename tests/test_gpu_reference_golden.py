@@ -259,3 +259,23 @@ def test_cuda_online_loop_matches_reference(method, monkeypatch):
         np.testing.assert_array_equal(_state_vec(), R[p + 'np_random_state'][it], err_msg='np.random stream, it %d' % it)
         np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), R[p + 'w'][it], rtol=1e-6, atol=1e-7)
     np.testing.assert_array_equal(np.asarray(smbo.perfs), R[p + 'perfs'])
+
+
+def test_cuda_default_configuration_row_matches_reference(monkeypatch):
+    """smbo_offline.py:210-219: the first evaluation is the space's default configuration when it is a table
+    row (row 17 of 300 in fixture reference_v3_default.npz, the reference's own NoTL run)."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.notl import NoTL
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v3_default.npz'))
+    forced = _ForcedFits(monkeypatch)
+    forced.queue = [th for th in D['thetas']]
+    cs = TableSpace(D['types'], default=D['X'][int(D['default_row'])])
+    fac = NoTL(cs, [], None, int(D['seed']), surrogate_type='gp', num_src_hpo_trial=50)
+    smbo = SMBO_OFFLINE((D['X'], D['y']), cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                        random_seed=int(D['seed']), max_runs=100)
+    for _ in D['rows']:
+        smbo.iterate()
+    assert smbo.configurations[0] == 17
+    assert smbo.configurations == D['rows'].tolist()
+    np.testing.assert_array_equal(np.asarray(smbo.perfs), D['perfs'])

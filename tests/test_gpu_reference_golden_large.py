@@ -143,9 +143,8 @@ def test_cuda_big_loop_matches_reference_given_theta(method, monkeypatch):
 @pytest.mark.parametrize('method', ['rgpe', 'topo'])
 def test_cuda_big_loop_with_device_fit_tracks_reference(method):
     """No teacher forcing: the device's own 11-restart MAP fits of all 29 + 6 surrogates.  Two L-BFGS-B
-    implementations agree to optimiser tolerance only, so EI near-ties can resolve differently; the test states
-    the measured agreement (prefix of identical picks, fraction of common rows) and asserts the trajectory
-    quality: the first model-based picks coincide and the incumbent is as good as the reference's."""
+    implementations agree to optimiser tolerance only in general; on these fixtures the device run selects the
+    reference's row at EVERY iteration (76 of 76 RGPE picks, 40 of 40 OBTLV picks), which is what is asserted."""
     from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
     K, seed, types = int(R['big_K']), int(R['big_seed']), R['big_types']
     p = 'big_%s_' % method
@@ -161,7 +160,8 @@ def test_cuda_big_loop_with_device_fit_tracks_reference(method):
     common = len(set(got.tolist()) & set(rows.tolist()))
     print('%s (K=29, N=20000): %d of %d picks identical as a prefix, %d rows in common; best perf device %.6f reference %.6f'
           % (method, same, len(rows), common, min(smbo.perfs), R[p + 'perfs'].min()))
-    assert same >= 4
+    # measured on B200 (profiles/r2_gpu_reference_golden_large.log): the whole trajectory coincides
+    assert same == len(rows), (got.tolist(), rows.tolist())
     y = R['big_target_y']
     span = y.max() - y.min()
     assert min(smbo.perfs) <= R[p + 'perfs'].min() + 0.05 * span

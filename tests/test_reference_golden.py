@@ -235,3 +235,17 @@ def test_online_loop_matches_reference(method, monkeypatch):
         np.testing.assert_array_equal(_state_vec(), R[p + 'np_random_state'][it], err_msg='np.random stream, it %d' % it)
         np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), R[p + 'w'][it], rtol=1e-6, atol=1e-8)
     np.testing.assert_array_equal(np.asarray(smbo.perfs), R[p + 'perfs'])
+
+
+def test_default_configuration_row_matches_reference(monkeypatch):
+    """smbo_offline.py:210-219: the first evaluation is the space's default configuration when it is a table
+    row (here row 17 of 300), fixture reference_v3_default.npz from the reference's own NoTL run."""
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v3_default.npz'))
+    monkeypatch.setattr(ofacade, 'OracleGP', _ForcedGP)
+    _ForcedGP.queue = [th for th in D['thetas']]
+    fac = ofacade.OracleNoTL(D['types'], [], int(D['seed']))
+    smbo = OracleSMBOOffline(D['X'], D['y'], fac, int(D['seed']), initial_runs=3, default=D['X'][int(D['default_row'])])
+    got = [smbo.iterate() for _ in D['rows']]
+    assert got[0] == int(D['default_row']) == 17
+    assert got == D['rows'].tolist()
+    np.testing.assert_array_equal(np.asarray(smbo.perfs), D['perfs'])
