@@ -86,6 +86,24 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self._pool_cache = {}         # (data_ptr, N) -> resident source posteriors over a fixed pool
         self._pool_keepalive = None   # the registered pool tensor: while it is alive its address cannot be reused
 
+    # ---- data-set meta-features (base_facade.py:193-208; scikit-learn on the host as the reference) --------
+    def scale_fit_meta_features(self, meta_features):
+        from sklearn.impute import SimpleImputer
+        from sklearn.preprocessing import MinMaxScaler
+        meta_features = np.array(meta_features)
+        self.meta_feature_imputer = SimpleImputer(missing_values=np.nan, strategy='mean')
+        self.meta_feature_imputer.fit(meta_features)
+        meta_features = self.meta_feature_imputer.transform(meta_features)
+        self.meta_feature_scaler = MinMaxScaler()
+        self.meta_feature_scaler.fit(meta_features)
+        return self.meta_feature_scaler.transform(meta_features)
+
+    def scale_transform_meta_features(self, meta_feature):
+        _meta_features = np.array([meta_feature])
+        _meta_feature = self.meta_feature_imputer.transform(_meta_features)
+        _meta_feature = self.meta_feature_scaler.transform(_meta_feature)
+        return np.clip(_meta_feature, 0, 1)
+
     # ---- device pack ------------------------------------------------------------------
     def _ensure_pack(self, rows):
         from tlbo_b200 import ops

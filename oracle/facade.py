@@ -684,3 +684,149 @@ class OraclePOGPE(OracleFacade):
         var = 1. / tmp
         mu = np.sum(mu_buf, axis=1) * var
         return mu.reshape(-1, 1), var.reshape(-1, 1)
+
+
+# ---- meta-feature baselines ------------------------------------------------------
+def scale_fit_meta_features(meta_features):
+    """base_facade.py:193-202: mean imputation, then min-max scaling fitted on the SOURCE tasks."""
+    from sklearn.impute import SimpleImputer
+    from sklearn.preprocessing import MinMaxScaler
+    meta_features = np.array(meta_features)
+    imputer = SimpleImputer(missing_values=np.nan, strategy='mean')
+    imputer.fit(meta_features)
+    meta_features = imputer.transform(meta_features)
+    scaler = MinMaxScaler()
+    scaler.fit(meta_features)
+    return scaler.transform(meta_features), imputer, scaler
+
+
+def scale_transform_meta_features(meta_feature, imputer, scaler):
+    """base_facade.py:204-208 (the target's vector, clipped into [0, 1])."""
+    v = scaler.transform(imputer.transform(np.array([meta_feature])))
+    return np.clip(v, 0, 1)
+
+
+def transform_pairwise(X, y):
+    """tlbo/utils/rank_svm.py:7-43, literally: all within-group pairs with different targets, labels balanced by
+    the parity of the COMBINATION index k (skipped combinations count)."""
+    X_new, y_new = [], []
+    y = np.asarray(y)
+    if y.ndim == 1:
+        y = np.c_[y, np.ones(y.shape[0])]
+    for k, (i, j) in enumerate(itertools.combinations(range(X.shape[0]), 2)):
+        if y[i, 0] == y[j, 0] or y[i, 1] != y[j, 1]:
+            continue
+        X_new.append(X[i] - X[j])
+        y_new.append(np.sign(y[i, 0] - y[j, 0]))
+        if y_new[-1] != (-1) ** k:
+            y_new[-1] = -y_new[-1]
+            X_new[-1] = -X_new[-1]
+    return np.asarray(X_new), np.asarray(y_new).ravel()
+
+
+class OracleRankSVM(object):
+    """tlbo/utils/rank_svm.py:46-81 (sklearn ``SVC(kernel='linear', C=.1)`` as the reference)."""
+
+    def __init__(self):
+        from sklearn import svm
+        self.clf = svm.SVC(kernel='linear', C=.1)
+        self.coef = None
+
+    def fit(self, X, y):
+        X_trans, y_trans = transform_pairwise(X, y)
+        self.clf.fit(X_trans, y_trans)
+        self.coef = self.clf.coef_.ravel() / np.linalg.norm(self.clf.coef_)
+
+    def predict(self, X):
+        return np.dot(X, self.coef)
+
+
+class OracleSCoT(OracleFacade):
+    """tlbo/facade/scot.py: RankSVM scores over the stacked source + target rows (meta-feature columns appended),
+    then ONE surrogate on all K x 50 + n rows; ``predict`` appends the target's meta-features."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, metafeatures=None, **kw):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, **kw)
+        self.method_id = 'scot'
+        if metafeatures is None:
+            raise ValueError('SCoT needs meta-features about the datasets.')
+        assert len(metafeatures) == self.K + 1
+        self.metafeatures = np.zeros(shape=(len(metafeatures), len(metafeatures[0])))
+        self.metafeatures[:-1], imp, sc = scale_fit_meta_features(metafeatures[:-1])
+        self.metafeatures[-1] = scale_transform_meta_features(metafeatures[-1], imp, sc)
+        self.space_types = self.types
+        self.types = np.concatenate([self.types, np.zeros(self.metafeatures.shape[1], dtype=self.types.dtype)])
+        self.X, self.y = None, None
+        for i, (Xs, ys) in enumerate(self.source_hpo_data):
+            X = np.asarray(Xs, dtype=np.float64)[:self.num_src_hpo_trial]
+            y = np.array(ys, dtype=np.float64)[:self.num_src_hpo_trial]
+            X = np.c_[X, np.array([list(self.metafeatures[i]) for _ in range(len(y))])]
+            y = np.c_[y, np.array([i] * X.shape[0])]
+            if self.X is not None:
+                self.X, self.y = np.r_[self.X, X], np.r_[self.y, y]
+            else:
+                self.X, self.y = X, y
+        self.svm_coefs = []
+
+    def train(self, X, y):
+        num_sample = y.shape[0]
+        meta_vec = np.array([list(self.metafeatures[self.K]) for _ in range(num_sample)])
+        _X = np.r_[self.X, np.c_[X, meta_vec]]
+        _y = np.r_[self.y, np.c_[y, np.array([self.K] * num_sample)]]
+        rank_svm = OracleRankSVM()
+        rank_svm.fit(_X, _y)
+        self.svm_coefs.append(rank_svm.coef.copy())
+        pred_y = rank_svm.predict(_X)
+        self.target_surrogate = self.build_single_surrogate(_X, pred_y, normalize='none')
+
+    def predict(self, X):
+        meta_vec = np.array([list(self.metafeatures[self.K]) for _ in range(X.shape[0])])
+        return self.target_surrogate.predict(np.c_[X, meta_vec])
+
+    def predict_marginalized_over_instances(self, X):
+        if X.shape[1] != len(self.space_types):
+            raise ValueError('Rows in X should have %d entries but have %d!' % (len(self.space_types), X.shape[1]))
+        mean, var = self.predict(X)
+        var[var < self.var_threshold] = self.var_threshold
+        var[np.isnan(var)] = self.var_threshold
+        return mean, var
+
+
+class OracleTSTM(OracleFacade):
+    """tlbo/facade/tstm.py: TST with Epanechnikov weights from the meta-feature distance (bandwidth 1.8);
+    the reference never appends to ``target_weight`` here."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, metafeatures=None, **kw):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, **kw)
+        self.method_id = 'tst'
+        self.build_source_surrogates(normalize='scale')
+        self.w = [0.75] * (self.K + 1)
+        self.metafeatures = np.zeros(shape=(len(metafeatures), len(metafeatures[0])))
+        self.metafeatures[:-1], imp, sc = scale_fit_meta_features(metafeatures[:-1])
+        self.metafeatures[-1] = scale_transform_meta_features(metafeatures[-1], imp, sc)
+        self.bandwidth = 1.8
+        assert len(metafeatures) == self.K + 1
+        self.meta_dist = [float(np.sqrt(np.sum(np.square(self.metafeatures[self.K] - self.metafeatures[_id]))))
+                          for _id in range(self.K)]
+        self.hist_ws = list()
+        self.iteration_id = 0
+
+    def train(self, X, y):
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='scale')
+        for _id in range(self.K):
+            tmp = self.meta_dist[_id] / self.bandwidth
+            self.w[_id] = 0.75 * (1 - tmp * tmp) if tmp <= 1 else 0
+        self.hist_ws.append(self.w.copy())
+        self.iteration_id += 1
+
+    def predict(self, X):
+        """tstm.py:49-58."""
+        mu, var = self.target_surrogate.predict(X)
+        denominator = 0.75
+        for i in range(0, self.K):
+            weight = self.w[i]
+            mu_t, _ = self.source_surrogates[i].predict(X)
+            mu += weight * mu_t
+            denominator += weight
+        mu /= denominator
+        return mu, var

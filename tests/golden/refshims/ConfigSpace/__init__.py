@@ -60,6 +60,12 @@ class ConfigurationSpace(object):
     def get_forbiddens(self):
         return []
 
+    def add_condition(self, cond):
+        raise NotImplementedError('stand-in spaces have no conditions')
+
+    def add_forbidden_clause(self, clause):
+        raise NotImplementedError('stand-in spaces have no forbidden clauses')
+
 
 class Configuration(object):
     """Holds the internal (unit-hypercube / category-index) vector, as ConfigSpace does."""

@@ -279,3 +279,76 @@ def test_cuda_default_configuration_row_matches_reference(monkeypatch):
     assert smbo.configurations[0] == 17
     assert smbo.configurations == D['rows'].tolist()
     np.testing.assert_array_equal(np.asarray(smbo.perfs), D['perfs'])
+
+
+@pytest.mark.parametrize('method', ['scot', 'tstm'])
+def test_cuda_meta_feature_baselines_match_reference(method, monkeypatch):
+    """facade/scot.py (RankSVM + one GP on the stacked K x 50 + n rows with meta-feature columns) and
+    facade/tstm.py as run by the reference itself (fixture reference_v4_meta.npz): scaled meta-features, RankSVM
+    coefficients, selected rows, weights and the final posterior, device GPs at the reference's theta."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.scot import SCoT
+    from tlbo_b200.facade.tst import TSTM
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v4_meta.npz'))
+    forced = _ForcedFits(monkeypatch)
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    p = method + '_'
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    thetas = [th for th in D[p + 'thetas']]
+    nsrc = int(D[p + 'n_source_fits'])
+    forced.queue = thetas[:nsrc]
+    cs = TableSpace(types)
+    cls = dict(scot=SCoT, tstm=TSTM)[method]
+    fac = cls(cs, [(X.copy(), y.copy()) for X, y in tables[1:]], None, seed, surrogate_type='gp', num_src_hpo_trial=50,
+              metafeatures=[m for m in D['meta']])
+    assert not forced.queue
+    np.testing.assert_allclose(fac.metafeatures, D[p + 'metafeatures_scaled'], rtol=1e-14, atol=1e-15)
+    smbo = SMBO_OFFLINE(tables[0], cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                        random_seed=seed, max_runs=100)
+    used = nsrc
+    for it, row in enumerate(D[p + 'rows']):
+        nfit = int(D[p + 'fits_per_iter'][it])
+        forced.queue = thetas[used:used + nfit]
+        used += nfit
+        smbo.iterate()
+        assert not forced.queue
+        got = smbo.configurations[-1]
+        assert got == int(row), 'iteration %d: device picked row %d, reference %d' % (it, got, row)
+        if fac.w is not None:
+            np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), D[p + 'w'][it], rtol=1e-12)
+    if method == 'scot':
+        np.testing.assert_allclose(np.array(fac.svm_coefs), D[p + 'svm_coef'], rtol=1e-9, atol=1e-12)
+    mu, var = fac.predict(tables[0][0][:64])
+    np.testing.assert_allclose(mu, D[p + 'final_mu'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, D[p + 'final_var'], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize('method', ['scot', 'tstm'])
+def test_cuda_meta_feature_baselines_with_device_fit(method):
+    """The same loops with the device's own 11-restart fits (no forcing): the measured agreement is printed;
+    asserted: the first model-based picks coincide and the incumbent is as good as the reference's."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.scot import SCoT
+    from tlbo_b200.facade.tst import TSTM
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v4_meta.npz'))
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    p = method + '_'
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    cs = TableSpace(types)
+    fac = dict(scot=SCoT, tstm=TSTM)[method](cs, [(X.copy(), y.copy()) for X, y in tables[1:]], None, seed,
+                                            surrogate_type='gp', num_src_hpo_trial=50,
+                                            metafeatures=[m for m in D['meta']])
+    smbo = SMBO_OFFLINE(tables[0], cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                        random_seed=seed, max_runs=100)
+    rows = D[p + 'rows']
+    for _ in rows:
+        smbo.iterate()
+    got = np.asarray(smbo.configurations)
+    same = int(np.argmax(np.concatenate([got != rows, [True]])))
+    print('%s: %d of %d picks identical to the reference run; device %s reference %s' % (
+        method, same, len(rows), got.tolist(), rows.tolist()))
+    assert same >= 4
+    span = tables[0][1].max() - tables[0][1].min()
+    assert min(smbo.perfs) <= D[p + 'perfs'].min() + 0.05 * span

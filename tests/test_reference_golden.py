@@ -249,3 +249,41 @@ def test_default_configuration_row_matches_reference(monkeypatch):
     assert got[0] == int(D['default_row']) == 17
     assert got == D['rows'].tolist()
     np.testing.assert_array_equal(np.asarray(smbo.perfs), D['perfs'])
+
+
+META = {'scot': lambda t, s, seed, m: ofacade.OracleSCoT(t, s, seed, metafeatures=m),
+        'tstm': lambda t, s, seed, m: ofacade.OracleTSTM(t, s, seed, metafeatures=m)}
+
+
+@pytest.mark.parametrize('method', sorted(META))
+def test_meta_feature_baselines_match_reference(method, monkeypatch):
+    """facade/scot.py (RankSVM + one stacked GP with meta-feature columns) and facade/tstm.py as run by the
+    reference itself (fixture reference_v4_meta.npz): scaled meta-features, RankSVM coefficients, selected rows,
+    weights and the final posterior; the oracle's GPs take the reference's fitted theta."""
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v4_meta.npz'))
+    monkeypatch.setattr(ofacade, 'OracleGP', _ForcedGP)
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    p = method + '_'
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    thetas = [th for th in D[p + 'thetas']]
+    nsrc = int(D[p + 'n_source_fits'])
+    _ForcedGP.queue = thetas[:nsrc]
+    fac = META[method](types, [(X.copy(), y.copy()) for X, y in tables[1:]], seed, [m for m in D['meta']])
+    assert not _ForcedGP.queue
+    np.testing.assert_allclose(fac.metafeatures, D[p + 'metafeatures_scaled'], rtol=1e-14, atol=1e-15)
+    smbo = OracleSMBOOffline(tables[0][0], tables[0][1], fac, seed, initial_runs=3)
+    used = nsrc
+    for it, row in enumerate(D[p + 'rows']):
+        nfit = int(D[p + 'fits_per_iter'][it])
+        _ForcedGP.queue = thetas[used:used + nfit]
+        used += nfit
+        got = smbo.iterate()
+        assert not _ForcedGP.queue
+        assert got == int(row), 'iteration %d: oracle picked row %d, reference %d' % (it, got, row)
+        if fac.w is not None:
+            np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), D[p + 'w'][it], rtol=1e-12)
+    if method == 'scot':
+        np.testing.assert_allclose(np.array(fac.svm_coefs), D[p + 'svm_coef'], rtol=1e-9, atol=1e-12)
+    mu, var = fac.predict(tables[0][0][:64])
+    np.testing.assert_allclose(mu, D[p + 'final_mu'], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, D[p + 'final_var'], rtol=1e-6, atol=1e-12)
