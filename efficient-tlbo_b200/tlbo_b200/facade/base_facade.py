@@ -277,6 +277,17 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         view = ops.pack_view(self._pack, 0, self.K + 1)
         nmax = max([self.num_src_hpo_trial if self.K else 0, getattr(self.target_surrogate, 'n_train_', 0)] +
                    [m.n_train_ for m in (self.source_surrogates or [])])
+        from tlbo_b200.model import gp_large
+        if nmax > gp_large.LARGE_N:
+            # a surrogate beyond the fused kernel's shared-memory plan (SCoT's stacked GP): its pool posterior by
+            # the two-step large-n path, then the fused kernel in all-resident mode (combine + EI + arg-max)
+            if self.K != 0:
+                raise ValueError('large-n surrogates are supported for single-surrogate facades only')
+            mu, var = gp_large.posterior_pool(self._pack, self.K, self.types, X_dev)
+            return ops.predict_ei_fused(self._logical(), self.types, dw, dskip, X_dev, eta, par=par,
+                                        var_floor=var_floor, keys=keys, excluded=excluded, idx_offset=idx_offset,
+                                        mode=self._fused_mode, order=dorder, want_rows=want_rows, ws=ws, sync=sync,
+                                        nmax=8, cache=(mu, var))
         cache = self._pool_cache.get((X_dev.data_ptr(), int(X_dev.shape[0])))
         return ops.predict_ei_fused(view, self.types, dw, dskip, X_dev, eta, par=par, var_floor=var_floor,
                                     keys=keys, excluded=excluded, idx_offset=idx_offset, mode=self._fused_mode,

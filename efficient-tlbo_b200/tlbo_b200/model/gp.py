@@ -274,6 +274,11 @@ def fit_models_async(models, Xs, Ys, do_optimize=True):
             mdl.bind(ops.SurrogatePack(1, X.shape[0], X.shape[1]), 0)
         jobs.append((mdl, X, y, p0))
 
+    # surrogates beyond the one-CTA panel kernels' reach (SCoT's stacked GP): the device-wide large-n path
+    from tlbo_b200.model import gp_large
+    large = [j for j in jobs if j[1].shape[0] > gp_large.LARGE_N]
+    jobs = [j for j in jobs if j[1].shape[0] <= gp_large.LARGE_N]
+
     # group: same pack, consecutive slots, identical start points, same types
     groups = []
     for job in jobs:
@@ -297,6 +302,16 @@ def fit_models_async(models, Xs, Ys, do_optimize=True):
             do_optimize=do_optimize, sync=False))
 
     def finish():
+        for mdl, X, y, p0 in large:
+            theta, results, bumps = gp_large.fit_large(mdl, X, y, p0, do_optimize=do_optimize)
+            mdl.hypers = np.array(theta, dtype=np.float64)
+            mdl.kernel.theta = np.array(theta, dtype=np.float64)
+            mdl.is_trained = True
+            mdl.n_train_ = X.shape[0]
+            mdl.fit_info_ = {'restart_theta': np.array([r[0] for r in results]),
+                             'restart_f': np.array([r[1] for r in results]),
+                             'restart_info': np.array([[r[2], 0, 0, bumps] for r in results], dtype=np.int32),
+                             'path': 'large-n (cuSOLVER / cuBLAS through torch, scipy L-BFGS-B)'}
         for g, h in zip(groups, handles):
             m0 = g[0][0]
             st = h.finish()

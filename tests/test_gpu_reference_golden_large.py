@@ -165,3 +165,44 @@ def test_cuda_big_loop_with_device_fit_tracks_reference(method):
     y = R['big_target_y']
     span = y.max() - y.min()
     assert min(smbo.perfs) <= R[p + 'perfs'].min() + 0.05 * span
+
+
+@pytest.mark.parametrize('tag', ['rf200', 'c20'])
+def test_large_n_path_matches_reference(tag, monkeypatch):
+    """model/gp_large.py (the device-wide path SCoT's stacked GP takes above LARGE_N rows) against the reference's
+    own numbers: NLL + gradient, the 11-restart fit (scipy L-BFGS-B over the device likelihood), the pack slot
+    it fills (read back through the posterior kernels) and the two-step pool posterior."""
+    import torch
+    from tlbo_b200 import ops
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.model import gp_large
+    from tlbo_b200.model.model_builder import build_model
+    types, X, Xq = R['kern_%s_types' % tag], R['kern_%s_X' % tag], R['kern_%s_Xq' % tag]
+    yn, ym, ys = _norm(R['kern_%s_y' % tag])
+    P = gp_large._Problem(X, yn, types)
+    for i, theta in enumerate(R['kern_%s_thetas' % tag]):
+        f, g = gp_large.nll_grad(P, theta)
+        assert abs(f - R['nll_%s_f' % tag][i]) <= 1e-9 * abs(R['nll_%s_f' % tag][i])
+        np.testing.assert_allclose(g, R['nll_%s_g' % tag][i], rtol=1e-6, atol=1e-7)
+    # full train through the model interface with the threshold lowered so that n = 60 / 200 takes the large path
+    monkeypatch.setattr(gp_large, 'LARGE_N', 32)
+    m = build_model('gp', TableSpace(types), np.random.RandomState(7))
+    m.train(X, R['kern_%s_y' % tag].copy())
+    assert 'large-n' in m.fit_info_['path']
+    f_ref = R['fit_%s_f' % tag]
+    f_got = m.fit_info_['restart_f']
+    close = np.abs(f_got - f_ref) <= 1e-5 * np.maximum(1.0, np.abs(f_ref))
+    print('%s large-n fit: %d of %d restarts at the reference optimum; evaluations %s reference %s' % (
+        tag, close.sum(), len(f_ref), m.fit_info_['restart_info'][:, 0].tolist(), R['fit_%s_funcalls' % tag].tolist()))
+    assert close.sum() >= len(f_ref) - 2
+    assert abs(f_got.min() - f_ref.min()) <= 1e-6 * max(1.0, abs(f_ref.min()))
+    # posterior at the REFERENCE's theta* through the slot the large path fills
+    P2 = gp_large._Problem(X, yn, types)
+    m.mean_y_, m.std_y_ = ym, ys
+    gp_large.factorize_into_pack(m, P2, R['fit_%s_theta_star' % tag])
+    mu, var = m.predict(Xq)
+    np.testing.assert_allclose(mu, R['pred_%s_mu' % tag], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, R['pred_%s_var' % tag], rtol=1e-6, atol=1e-12)
+    pm, pv = gp_large.posterior_pool(m._pack, m._slot, types, torch.from_numpy(Xq).cuda(), chunk=100)
+    np.testing.assert_allclose(pm[0].cpu().numpy(), R['pred_%s_mu' % tag].ravel(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(pv[0].cpu().numpy(), R['pred_%s_var' % tag].ravel(), rtol=1e-6, atol=1e-12)
