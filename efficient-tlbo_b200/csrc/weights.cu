@@ -282,11 +282,20 @@ __device__ __forceinline__ double mt_double(uint32_t w1, uint32_t w2) {
 // b + 1 is simply not committed, exactly as numpy leaves its key array untouched until the next draw.
 #define MT_TWIST_THREADS 256
 #define MT_WRITE_THREADS 320
-__global__ void __launch_bounds__(MT_THREADS) mt19937_random_sample_kernel(uint32_t* __restrict__ state, long long N,
-                                                                           double* __restrict__ out) {
+// Grid of C CTAs: CTA c starts from its own window states_in[c] (the generator state c * S doubles further down
+// the stream, see tlbo_mt19937_jump) and delivers doubles [c * S, min((c + 1) * S, N)); the LAST CTA's final
+// state is the generator state after all N doubles and goes to state_out.  C = 1: the plain sequential walk.
+__global__ void __launch_bounds__(MT_THREADS) mt19937_random_sample_kernel(const uint32_t* __restrict__ states_in,
+                                                                           uint32_t* __restrict__ state_out,
+                                                                           long long Ntot, long long S,
+                                                                           double* __restrict__ out_all) {
   __shared__ uint32_t keybuf[2][MT_N];
   const int tid = threadIdx.x;
   const int wtid = tid - MT_TWIST_THREADS;          // >= 0: writer thread
+  const uint32_t* state = states_in + (size_t)blockIdx.x * (MT_N + 1);
+  const long long lo = (long long)blockIdx.x * S;
+  const long long N = (Ntot - lo < S) ? Ntot - lo : S;
+  double* out = out_all + lo;
   int cb = 0;
   for (int i = tid; i < MT_N; i += MT_THREADS) keybuf[0][i] = state[i];
   int pos = (int)state[MT_N];
@@ -332,14 +341,93 @@ __global__ void __launch_bounds__(MT_THREADS) mt19937_random_sample_kernel(uint3
     if (start >= MT_N && produced < N) { cb ^= 1; pos = 0; }     // commit the look-ahead block
     else pos = start;
   }
-  for (int i = tid; i < MT_N; i += MT_THREADS) state[i] = keybuf[cb][i];
-  if (tid == 0) state[MT_N] = (uint32_t)pos;
+  if (blockIdx.x == gridDim.x - 1) {
+    for (int i = tid; i < MT_N; i += MT_THREADS) state_out[i] = keybuf[cb][i];
+    if (tid == 0) state_out[MT_N] = (uint32_t)pos;
+  }
 }
 
 extern "C" int tlbo_mt19937_random_sample(uint32_t* d_state, int64_t N, double* d_out, void* stream) {
   if (!d_state || !d_out || N < 0) { tlbo_set_error("tlbo_mt19937_random_sample: bad arguments"); return TLBO_E_BADARG; }
   if (N == 0) return 0;
-  mt19937_random_sample_kernel<<<1, MT_THREADS, 0, (cudaStream_t)stream>>>(d_state, (long long)N, d_out);
+  mt19937_random_sample_kernel<<<1, MT_THREADS, 0, (cudaStream_t)stream>>>(d_state, d_state, (long long)N,
+                                                                            (long long)N, d_out);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---- multi-CTA generation: jump-ahead ---------------------------------------------------------------------
+// MT19937 is linear over GF(2): the window of 624 words that starts J words further down the word sequence is
+// g_J(F) W with g_J(t) = t^J mod phi(t) (phi: the degree-19937 characteristic polynomial, F: the one-word
+// shift), i.e. word j of the jumped window is the XOR over the set bits i of g_J of x_{i + j}.  The host
+// supplies the bit positions (tlbo_b200/utils/mt_jump.py; they depend on the slice length only and are computed
+// once per maximiser); one CTA per slice extends the base window by 32 blocks in shared memory (the same
+// three-phase twist as the generator) and XORs ~10^4 shifted copies, one word per thread.  The jump is by a
+// multiple of 624 words, so the in-block position carries over unchanged.
+#define MT_JUMP_BLOCKS 33
+#define MT_JUMP_THREADS 640
+__global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uint32_t* __restrict__ base,
+                                                                       uint32_t* __restrict__ states,
+                                                                       const int32_t* __restrict__ bitpos,
+                                                                       const int32_t* __restrict__ nbits, int stride) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* seq = reinterpret_cast<uint32_t*>(smem);
+  const int tid = threadIdx.x, c = blockIdx.x;
+  uint32_t* dst = states + (size_t)c * (MT_N + 1);
+  if (c == 0) {                                      // slice 0 starts at the base state itself
+    for (int i = tid; i <= MT_N; i += MT_JUMP_THREADS) dst[i] = base[i];
+    return;
+  }
+  for (int i = tid; i < MT_N; i += MT_JUMP_THREADS) seq[i] = base[i];
+  __syncthreads();
+  for (int b = 1; b < MT_JUMP_BLOCKS; b++) {
+    const uint32_t* cur = seq + (size_t)(b - 1) * MT_N;
+    uint32_t* nxt = seq + (size_t)b * MT_N;
+    if (tid < 227) nxt[tid] = mt_twist(cur[tid], cur[tid + 1], cur[tid + MT_M]);
+    __syncthreads();
+    if (tid < 227) nxt[227 + tid] = mt_twist(cur[227 + tid], cur[228 + tid], nxt[tid]);
+    __syncthreads();
+    if (tid < 169) nxt[454 + tid] = mt_twist(cur[454 + tid], cur[455 + tid], nxt[227 + tid]);
+    else if (tid == 169) nxt[623] = mt_twist(cur[623], nxt[0], nxt[396]);
+    __syncthreads();
+  }
+  const int32_t* bp = bitpos + (size_t)c * stride;
+  const int nb = nbits[c];
+  if (tid < MT_N) {
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    int q = 0;
+    for (; q + 4 <= nb; q += 4) {
+      r0 ^= seq[bp[q] + tid]; r1 ^= seq[bp[q + 1] + tid]; r2 ^= seq[bp[q + 2] + tid]; r3 ^= seq[bp[q + 3] + tid];
+    }
+    for (; q < nb; q++) r0 ^= seq[bp[q] + tid];
+    dst[tid] = (r0 ^ r1) ^ (r2 ^ r3);
+  }
+  if (tid == 0) dst[MT_N] = base[MT_N];
+}
+
+extern "C" int tlbo_mt19937_jump(const uint32_t* d_base, uint32_t* d_states, int C, const int32_t* d_bitpos,
+                                 const int32_t* d_nbits, int stride, void* stream) {
+  if (!d_base || !d_states || !d_bitpos || !d_nbits || C <= 0 || stride <= 0) {
+    tlbo_set_error("tlbo_mt19937_jump: bad arguments");
+    return TLBO_E_BADARG;
+  }
+  const size_t smem = (size_t)MT_JUMP_BLOCKS * MT_N * sizeof(uint32_t);
+  TLBO_CUDA_CHECK(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mt19937_jump_kernel<<<C, MT_JUMP_THREADS, smem, (cudaStream_t)stream>>>(d_base, d_states, d_bitpos, d_nbits, stride);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tlbo_mt19937_random_sample_sliced(const uint32_t* d_states, int C, int64_t N, int64_t S, double* d_out,
+                                                 uint32_t* d_state_out, void* stream) {
+  if (!d_states || !d_out || !d_state_out || N < 0 || C <= 0 || S <= 0 || (S % 312) != 0 ||
+      (int64_t)(C - 1) * S >= N + (N == 0) || (int64_t)C * S < N) {
+    tlbo_set_error("tlbo_mt19937_random_sample_sliced: bad arguments (S must be a multiple of 312, (C-1) S < N <= C S)");
+    return TLBO_E_BADARG;
+  }
+  if (N == 0) return 0;
+  mt19937_random_sample_kernel<<<C, MT_THREADS, 0, (cudaStream_t)stream>>>(d_states, d_state_out, (long long)N,
+                                                                            (long long)S, d_out);
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -61,6 +61,8 @@ SYMBOLS = {
     'tlbo_one_exchange_neighbourhood': (c_int, [_P, c_int, _P, _P, ctypes.c_uint32, c_int, c_double, _P, c_int, _P]),
     'tlbo_pair_penalty_loss_normal': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     'tlbo_mt19937_random_sample': (c_int, [_P, c_int64, _P, _P]),
+    'tlbo_mt19937_jump': (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),
+    'tlbo_mt19937_random_sample_sliced': (c_int, [_P, c_int, c_int64, c_int64, _P, _P, _P]),
     'tlbo_host_prepare_jobs': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P,
                                        _P]),
     'tlbo_fp64_peak_probe': (c_int, [_P, _P]),

@@ -591,11 +591,48 @@ def pair_penalty_loss_normal(y, z, loc, scale, sync=True):
 class DeviceRandomState(object):
     """A legacy ``np.random.RandomState`` whose MT19937 state lives on the device: ``rand_into(out)`` fills a
     device tensor with the doubles ``rng.rand(out.numel())`` would return, bit for bit, and advances the
-    state (``tlbo_mt19937_random_sample``).  ``to_host(rng)`` / ``from_host(rng)`` move the state."""
+    state (``tlbo_mt19937_random_sample``).  ``to_host(rng)`` / ``from_host(rng)`` move the state.
 
-    def __init__(self, rng):
+    ``slices > 1`` (chosen from ``n_hint``, the length of the draws to come): the stream is produced by that many
+    thread blocks at once -- slice c starts from the state jumped ahead by c * S doubles (``tlbo_mt19937_jump``,
+    polynomials from ``tlbo_b200.utils.mt_jump``, computed once) -- and the jumped states of the NEXT draw are
+    prepared right behind the current one, on the same stream."""
+
+    SLICE_MIN = 65536            # doubles per slice below which more slices do not pay
+    SLICE_MAX_COUNT = 64
+
+    def __init__(self, rng, n_hint=0):
         self.state = torch.empty(625, dtype=torch.int32, device=_dev())
+        self._slices, self._S, self._n = 1, 0, 0
+        n_hint = int(n_hint)
+        C = min(self.SLICE_MAX_COUNT, n_hint // self.SLICE_MIN)
+        if C >= 2:
+            from tlbo_b200.utils import mt_jump
+            S = round_up((n_hint + C - 1) // C, 312)
+            C = (n_hint + S - 1) // S
+            if C >= 2:
+                g1 = mt_jump.jump_poly(2 * S)                      # 2 words per double
+                polys, g = [1], 1
+                phi = mt_jump.charpoly()
+                for _ in range(1, C):
+                    g = mt_jump._mulmod(g, g1, phi)
+                    polys.append(g)
+                pos = [mt_jump.bit_positions(p) for p in polys]
+                stride = max(len(p) for p in pos)
+                tab = np.zeros((C, stride), dtype=np.int32)
+                for c, p in enumerate(pos):
+                    tab[c, :len(p)] = p
+                self._bitpos = torch.from_numpy(tab).to(_dev())
+                self._nbits = torch.from_numpy(np.array([len(p) for p in pos], dtype=np.int32)).to(_dev())
+                self._stride = int(stride)
+                self._states = torch.empty(C, 625, dtype=torch.int32, device=_dev())
+                self._slices, self._S, self._n = int(C), int(S), n_hint
         self.from_host(rng)
+
+    def _jump(self):
+        with _call('mt19937_jump', 1):
+            check(lib.tlbo_mt19937_jump(ptr(self.state), ptr(self._states), self._slices, ptr(self._bitpos),
+                                        ptr(self._nbits), self._stride, _stream()))
 
     def from_host(self, rng):
         st = rng.get_state()
@@ -604,6 +641,8 @@ class DeviceRandomState(object):
         h[:624] = st[1]
         h[624] = st[2]
         self.state.copy_(torch.from_numpy(h.view(np.int32)))
+        if self._slices > 1:
+            self._jump()
         torch.cuda.current_stream().synchronize()      # the generator runs on a side stream
         self._aux = (st[3], st[4])
 
@@ -613,8 +652,17 @@ class DeviceRandomState(object):
 
     def rand_into(self, out):
         assert out.is_cuda and out.dtype == F64 and out.is_contiguous()
+        N = int(out.numel())
+        if self._slices > 1 and N == self._n:
+            with _call('mt19937_random_sample', 1):
+                check(lib.tlbo_mt19937_random_sample_sliced(ptr(self._states), self._slices, N, self._S, ptr(out),
+                                                            ptr(self.state), _stream()))
+            self._jump()                               # the next draw's slice states, behind this one
+            return out
         with _call('mt19937_random_sample', 1):
-            check(lib.tlbo_mt19937_random_sample(ptr(self.state), int(out.numel()), ptr(out), _stream()))
+            check(lib.tlbo_mt19937_random_sample(ptr(self.state), N, ptr(out), _stream()))
+        if self._slices > 1:
+            self._jump()
         return out
 
 

@@ -64,7 +64,7 @@ class OfflineSearch(AcquisitionFunctionMaximizer):
         self._device_keys = bool(prefetch_keys) if device_keys is None else bool(device_keys)
         if self._device_keys:
             self._prefetch = False
-            self._dev_rng = ops.DeviceRandomState(self.rng)
+            self._dev_rng = ops.DeviceRandomState(self.rng, n_hint=self.N)
             # two key buffers: the keys of the NEXT maximisation (independent of the BO state) are generated
             # right after the current one has been enqueued, so the generator never sits on the critical path
             self._keys_full = [torch.empty(self.N, dtype=torch.float64, device='cuda') for _ in range(2)]

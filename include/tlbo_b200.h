@@ -285,6 +285,21 @@ int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const do
  *   d_out    double[N]                                                                                   */
 int tlbo_mt19937_random_sample(uint32_t* d_state, int64_t N, double* d_out, void* stream);
 
+/* The same stream from C thread blocks at once (the same reference call site: rng.rand(N) over the WHOLE table,
+ * 20 ms of one CTA at N = 1e7).  MT19937 is linear over GF(2): the window of 624 state words that starts J words
+ * further down the sequence is g_J(F) W with g_J(t) = t^J mod phi(t).
+ *   tlbo_mt19937_jump: d_states[c] (c = 0 .. C-1, uint32[625] each) = the generator state d_base advanced by the
+ *     jump whose polynomial's set-bit positions are d_bitpos[c * stride .. + d_nbits[c]) (slot 0 is a copy of
+ *     d_base; the jumps are multiples of 624 words, so the in-block position carries over);
+ *   tlbo_mt19937_random_sample_sliced: slice c delivers doubles [c S, min((c + 1) S, N)) from d_states[c];
+ *     S a multiple of 312 (one state block), (C - 1) S < N <= C S; d_state_out (uint32[625],
+ *     a separate buffer) receives the generator state after all N doubles -- the base of the
+ *     next call's jump and what RandomState.set_state takes.                                            */
+int tlbo_mt19937_jump(const uint32_t* d_base, uint32_t* d_states, int C, const int32_t* d_bitpos,
+                      const int32_t* d_nbits, int stride, void* stream);
+int tlbo_mt19937_random_sample_sliced(const uint32_t* d_states, int C, int64_t N, int64_t S, double* d_out,
+                                      uint32_t* d_state_out, void* stream);
+
 /* Host-side helper (no device work): the host half of build_single_surrogate + GaussianProcess._train for
  * the 1 + 5 training sets a facade builds per BO iteration from the same (X, y) -- all rows, and all rows
  * except one contiguous validation range (reference tlbo/facade/base_facade.py:93-108, rgpe.py:55-70,

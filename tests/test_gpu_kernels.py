@@ -335,6 +335,47 @@ def test_device_mt19937_equals_numpy_legacy_random_sample():
         assert back.rand() == ref.rand()
 
 
+def test_device_mt19937_sliced_jump_ahead_equals_numpy():
+    """Multi-CTA key generation (``tlbo_mt19937_jump`` + ``tlbo_mt19937_random_sample_sliced``): slice c starts from
+    the state jumped ahead by c * S doubles (polynomial jump-ahead, tlbo_b200/utils/mt_jump.py).  Consecutive
+    draws of the hinted length, a draw of another length in between (sequential walk + re-jump), odd stream
+    positions: bit-identical doubles and final state."""
+    import torch
+    from tlbo_b200 import ops
+    for seed, n, pre in ((4465, 5 * 65536 + 777, 0), (7, 2 * 65536, 3), (2 ** 31 + 7, 1000003, 1)):
+        ref = np.random.RandomState(seed)
+        for _ in range(pre):
+            ref.randint(0, 10000)
+        dev = ops.DeviceRandomState(ref, n_hint=n)
+        assert dev._slices >= 2
+        out = torch.empty(n, dtype=torch.float64, device='cuda')
+        for rep in range(3):
+            dev.rand_into(out)
+            assert np.array_equal(out.cpu().numpy(), ref.rand(n)), (seed, n, rep)
+            if rep == 1:
+                small = torch.empty(1001, dtype=torch.float64, device='cuda')
+                dev.rand_into(small)
+                assert np.array_equal(small.cpu().numpy(), ref.rand(1001))
+        back = np.random.RandomState(0)
+        torch.cuda.synchronize()
+        dev.to_host(back)
+        a, b = back.get_state(), ref.get_state()
+        assert np.array_equal(a[1], b[1]) and a[2] == b[2]
+        assert back.rand() == ref.rand()
+
+
+def test_mt_jump_polynomial_matches_numpy_stream():
+    """Host side of the jump-ahead: the window jumped by 2 * 312000 words equals numpy's key array after 312000
+    doubles (characteristic polynomial by Berlekamp-Massey, t^J mod phi, XOR of shifted windows)."""
+    from tlbo_b200.utils import mt_jump as mj
+    rs = np.random.RandomState(5)
+    rs.random_sample(1)                       # first draw regenerates the block: key = block 1, pos = 2
+    key = rs.get_state()[1].copy()
+    rs.random_sample(312 * 1000)
+    assert np.array_equal(mj.jump_window(key, mj.bit_positions(mj.jump_poly(624 * 1000))), rs.get_state()[1])
+    assert bin(mj.charpoly()).count('1') == 135 and mj.charpoly().bit_length() == 19938
+
+
 def test_merge_best_matches_host_rule():
     """tlbo_merge_best (the exchange step of the row-sharded pool) against the host statement of the rule,
     including ties on EI / key and shards without an unevaluated candidate."""
