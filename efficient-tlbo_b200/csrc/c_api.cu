@@ -23,10 +23,12 @@ extern "C" int tlbo_stream_synchronize(void* stream) {
 int tlbo_make_space(int d, const int32_t* h_types, SpaceDesc* sp) {
   if (d <= 0 || d > TLBO_MAX_D || !h_types) { tlbo_set_error("bad d / types"); return TLBO_E_BADARG; }
   sp->d = d;
+  sp->has_cond = (h_types[0] & TLBO_TYPES_HAS_CONDITIONS) ? 1 : 0;
   int k = 0;
-  for (int i = 0; i < d; i++) if (h_types[i] == 0) sp->perm[k++] = i;
+  auto ty = [&](int i) { return i == 0 ? (h_types[0] & ~TLBO_TYPES_HAS_CONDITIONS) : h_types[i]; };
+  for (int i = 0; i < d; i++) if (ty(i) == 0) sp->perm[k++] = i;
   sp->d_cont = k;
-  for (int i = 0; i < d; i++) if (h_types[i] != 0) sp->perm[k++] = i;
+  for (int i = 0; i < d; i++) if (ty(i) != 0) sp->perm[k++] = i;
   sp->d_cat = d - sp->d_cont;
   for (int i = d; i < TLBO_HMAX; i++) sp->perm[i] = 0;
   return 0;

@@ -48,6 +48,7 @@ struct FitWs {
   double* Kc;      // [npairs] kernel value per pair        } written by the kernel-matrix build, reused by
   double* Cg;      // [npairs] c e^{-t-hs} 5/3 (1 + t)      } the gradient contraction (NULL: recompute)
   int* acol;       // [TLBO_HMAX] permuted column of compact column q (register-panel path: columns that vary)
+  int* rmask;      // [n] activity pattern per row (inactive_pattern; read only when the space has conditions)
   int n, lda, d, npairs;
   int nac, nak;    // varying continuous / categorical columns (find_active_columns)
 };
@@ -63,7 +64,8 @@ __host__ __device__ inline size_t fit_pair_bytes(int ncap, int tile, int cache) 
 }
 __host__ inline size_t fit_small_bytes(int ncap, int d, int tile, int cache) {
   // Xr, Xs, y, piv, dinv, alpha, red, hyp, colbuf, pair tables
-  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8 + 16) +
+  return sizeof(double) * ((size_t)2 * ncap * d + 4 * (size_t)ncap + 8 * 32 + 2 * TLBO_HMAX + 2 * FIT_COLBUF + 8 + 16 +
+                           (size_t)ncap / 2 + 2) +
          fit_pair_bytes(ncap, tile, cache);
 }
 __host__ inline size_t fit_panel_bytes(int ncap) { return sizeof(double) * (size_t)(ncap + 1) * fit_lda(ncap); }
@@ -82,6 +84,7 @@ __device__ __forceinline__ void carve_ws(FitWs& S, unsigned char* smem, double* 
   S.hyp = p; p += 2 * TLBO_HMAX;
   S.colbuf = p; p += 2 * FIT_COLBUF;
   S.acol = reinterpret_cast<int*>(p); p += 16;
+  S.rmask = reinterpret_cast<int*>(p); p += ncap / 2 + 2;
   S.nac = 0; S.nak = 0;
   S.npairs = n * (n - 1) / 2;
   S.pairs = nullptr; S.Kc = nullptr; S.Cg = nullptr;
@@ -101,7 +104,13 @@ __device__ __forceinline__ void load_problem(const FitWs& S, const SpaceDesc& sp
     const int i = idx / d, p = idx - i * d;
     S.Xr[idx] = X[(size_t)i * d + sp.perm[p]];
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) S.y[i] = y[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    S.y[i] = y[i];
+    unsigned m = 0u;
+    if (sp.has_cond)
+      for (int p = 0; p < d; p++) m |= (X[(size_t)i * d + sp.perm[p]] <= -1.0) ? (1u << p) : 0u;
+    S.rmask[i] = (int)m;
+  }
   if (S.pairs) {
     for (int q = threadIdx.x; q < S.npairs; q += blockDim.x) {
       int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
@@ -174,6 +183,7 @@ static __device__ bool build_and_eliminate(const FitWs& S, const SpaceDesc& sp, 
       for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
       for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
       v = matern_hamming(c, s, hs);
+      if (sp.has_cond && S.rmask[i] != S.rmask[j]) v = 0.0;                       // activity mask, gp_kernels.py:21-29
     }
     A[(size_t)i * lda + j] = v;
   }
@@ -466,12 +476,13 @@ __device__ __forceinline__ void kernel_panel_reg(const FitWs& S, const SpaceDesc
 #pragma unroll
     for (int u = 0; u < PF; u++) {
       const double t = sqrt_nonneg(ss[u]) * SQRT5;
-      const double ce = c * exp_nonpos(-t - hh[u]);
+      double ce = c * exp_nonpos(-t - hh[u]);
+      const int ij = S.pairs[qq[u]];
+      if (sp.has_cond && S.rmask[ij >> 16] != S.rmask[ij & 0xffff]) ce = 0.0;     // activity mask, gp_kernels.py:21-29
       // t^2 / 3 as a multiplication by the rounded 1/3 (<= 1 ulp from the IEEE quotient; the division is a
       // ~25-instruction subroutine on the critical path of every pair)
       const double v = ce * (1.0 + t + t * t * (1.0 / 3.0));
       if (has[u]) {
-        const int ij = S.pairs[qq[u]];
         A[(size_t)(ij >> 16) * lda + (ij & 0xffff)] = v;
         if (S.Kc) { S.Kc[qq[u]] = v; S.Cg[qq[u]] = ce * (5.0 / 3.0) * (t + 1.0); }
       }
@@ -599,8 +610,12 @@ __device__ bool lml_eliminate_reg(const FitWs& S, const SpaceDesc& sp, const dou
       h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
     }
     const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
-    const double v0 = c * exp_nonpos(-t0 - h0) * (1.0 + t0 + t0 * t0 / 3.0);
-    const double v1 = c * exp_nonpos(-t1 - h1) * (1.0 + t1 + t1 * t1 / 3.0);
+    double v0 = c * exp_nonpos(-t0 - h0) * (1.0 + t0 + t0 * t0 / 3.0);
+    double v1 = c * exp_nonpos(-t1 - h1) * (1.0 + t1 + t1 * t1 / 3.0);
+    if (sp.has_cond) {
+      if (S.rmask[i0] != S.rmask[j0]) v0 = 0.0;
+      if (S.rmask[i1] != S.rmask[j1]) v1 = 0.0;
+    }
     A[(size_t)i0 * lda + j0] = v0;
     if (has1) A[(size_t)i1 * lda + j1] = v1;
   }
@@ -809,7 +824,11 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
         h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
       }
       const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
-      const double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
+      double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
+      if (sp.has_cond) {
+        if (S.rmask[i0] != S.rmask[j0]) ce0 = 0.0;
+        if (S.rmask[i1] != S.rmask[j1]) ce1 = 0.0;
+      }
       WK0 = W0 * (ce0 * (1.0 + t0 + t0 * t0 * (1.0 / 3.0))); cf0 = W0 * (ce0 * (5.0 / 3.0) * (t0 + 1.0));
       WK1 = W1 * (ce1 * (1.0 + t1 + t1 * t1 * (1.0 / 3.0))); cf1 = W1 * (ce1 * (5.0 / 3.0) * (t1 + 1.0));
     }
@@ -950,7 +969,8 @@ __device__ bool nll_eval(const FitWs& S, const SpaceDesc& sp, const double* thet
     for (int p = 0; p < dc; p++) { const double df = xi[p] - xj[p]; s += df * df; }
     for (int p = dc; p < d; p++) if (xi[p] != xj[p]) hs += S.hyp[p];
     const double t = sqrt(s) * SQRT5;
-    const double e = exp(-t), eh = exp(-hs);
+    const double e = exp(-t);
+    const double eh = (sp.has_cond && S.rmask[i] != S.rmask[j]) ? 0.0 : exp(-hs);   // activity mask (K and dK)
     const double Kc = c * ((1.0 + t + t * t / 3.0) * e) * eh;
     const double WK = W * Kc;
     g0 += WK;

@@ -55,11 +55,14 @@ __global__ void __launch_bounds__(256) gp_predict_small_kernel(PredSmallArgs a) 
     const double* Li = a.pack.d_Linv + (size_t)m * ncap * ldl;
     const double c = hyp[0], ymean = hyp[2], ystd = hyp[3], diag = hyp[4];
     __syncwarp();
+    unsigned qmask = 0u;
     if (lane < d) {
       double v = a.Xq[(size_t)q * d + a.sp.perm[lane]];
+      if (a.sp.has_cond && v <= -1.0) qmask = 1u << lane;
       if (lane < dc) v *= hyp[8 + lane];
       xq[lane] = v;
     }
+    if (a.sp.has_cond) qmask = __reduce_or_sync(0xffffffffu, qmask);
     __syncwarp();
     double mpart = 0.0;
     for (int j = lane; j < n; j += 32) {
@@ -67,7 +70,14 @@ __global__ void __launch_bounds__(256) gp_predict_small_kernel(PredSmallArgs a) 
       double s = 0.0, hs = 0.0;
       for (int p = 0; p < dc; p++) { const double df = xq[p] - xj[p]; s += df * df; }
       for (int p = dc; p < d; p++) if (xq[p] != xj[p]) hs += hyp[8 + p];
-      const double k = matern_hamming(c, s, hs);
+      double k = matern_hamming(c, s, hs);
+      if (a.sp.has_cond) {
+        // activity mask (gp_kernels.py:21-29); a training entry is inactive iff its raw value was <= -1, i.e. its
+        // stored value (continuous columns are pre-multiplied by 1 / l > 0) is <= -(1 / l)
+        unsigned jm = 0u;
+        for (int p = 0; p < d; p++) jm |= (xj[p] <= ((p < dc) ? -hyp[8 + p] : -1.0)) ? (1u << p) : 0u;
+        if (jm != qmask) k = 0.0;
+      }
       kbuf[j] = k;
       mpart += k * al[j];
     }

@@ -13,8 +13,18 @@
 // Input-space description, passed to kernels by value.
 struct SpaceDesc {
   int d, d_cont, d_cat;
+  int has_cond;          // the space has conditions: kernel values carry the activity mask of gp_kernels.py:21-29
   int perm[TLBO_HMAX];   // perm[p] = original column of permuted column p (cont first, then cat)
 };
+
+// Activity pattern of a row (reference tlbo/model/gp_kernels.py:21-29, get_conditional_hyperparameters): bit p
+// set iff x_p <= -1 (an inactive hyper-parameter after GaussianProcess._impute_inactive, base_gp.py:148-151).
+// k(x, x') is multiplied by [pattern(x) == pattern(x')] in every kernel of the stack when the space has conditions.
+__device__ __forceinline__ unsigned inactive_pattern(const double* x, int d) {
+  unsigned m = 0u;
+  for (int p = 0; p < d; p++) m |= (x[p] <= -1.0) ? (1u << p) : 0u;
+  return m;
+}
 
 void tlbo_set_error(const char* msg);
 int tlbo_make_space(int d, const int32_t* h_types, SpaceDesc* sp);

@@ -8,12 +8,29 @@ classes carry exactly that, with the attribute / method names the callers use.""
 import numpy as np
 
 
+class TypesArray(np.ndarray):
+    """``get_types``' vector with one extra fact riding along: ``has_conditions`` (the space has conditional
+    hyper-parameters, reference tlbo/model/base_gp.py:134-146 ``_set_has_conditions``).  The device kernels then
+    multiply every kernel value by the activity mask of tlbo/model/gp_kernels.py:21-29; the flag travels to the C
+    ABI as bit 30 of ``types[0]`` (``tlbo_b200.ops._types_arr``)."""
+
+    def __new__(cls, types, has_conditions=False):
+        obj = np.asarray(types, dtype=np.uint).view(cls)
+        obj.has_conditions = bool(has_conditions)
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.has_conditions = getattr(obj, 'has_conditions', False)
+
+
 class TableSpace(object):
     """Search-space descriptor: ``types[d]`` (0 = continuous / integer / constant,
-    k > 0 = categorical with k choices) and per-column bounds as ``get_types`` returns."""
+    k > 0 = categorical with k choices) and per-column bounds as ``get_types`` returns.
+    ``has_conditions``: the space has conditional hyper-parameters (``len(cs.get_conditions()) > 0``)."""
 
-    def __init__(self, types, bounds=None, default=None, const_mask=None):
-        self.types = np.asarray(types, dtype=np.uint)
+    def __init__(self, types, bounds=None, default=None, const_mask=None, has_conditions=False):
+        self.has_conditions = bool(has_conditions or getattr(types, 'has_conditions', False))
+        self.types = TypesArray(types, self.has_conditions)
         d = len(self.types)
         # columns holding a Constant hyper-parameter (encoded 0, no neighbours, never sampled)
         self.const_mask = (np.zeros(d, dtype=bool) if const_mask is None
@@ -52,7 +69,11 @@ class TableSpace(object):
         return [Configuration(self, X[i], -1) for i in range(X.shape[0])]
 
     def get_types(self):
-        return self.types.copy(), self.bounds.copy()
+        return TypesArray(self.types.copy(), self.has_conditions), self.bounds.copy()
+
+    def get_conditions(self):
+        """Non-empty iff the space has conditions (only the count is read: base_gp.py:135)."""
+        return [True] if self.has_conditions else []
 
     def get_default_configuration(self):
         return None if self.default is None else Configuration(self, self.default, -1)
@@ -94,13 +115,14 @@ class Configuration(object):
 def get_types(config_space, instance_features=None):
     """``get_types`` (reference tlbo/model/util_funcs.py:14-55) for a TableSpace or a bare
     types vector."""
-    if isinstance(config_space, TableSpace):
+    if hasattr(config_space, 'get_types'):
         types, bounds = config_space.get_types()
     else:
-        types = np.asarray(config_space, dtype=np.uint)
+        types = TypesArray(config_space, getattr(config_space, 'has_conditions', False))
         bounds = TableSpace(types).bounds
     if instance_features is not None:
-        types = np.hstack((types, np.zeros((instance_features.shape[1])))).astype(np.uint)
+        types = TypesArray(np.hstack((types, np.zeros((instance_features.shape[1])))).astype(np.uint),
+                           getattr(types, 'has_conditions', False))
     return types, bounds
 
 

@@ -55,6 +55,8 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         self.history_dataset_features = history_dataset_features
         if history_dataset_features is not None:
             assert len(history_dataset_features) == self.K
+        if surrogate_type == 'gp_mcmc' and getattr(get_types(config_space)[0], 'has_conditions', False):
+            raise ValueError('gp_mcmc surrogates over a space with conditions are not supported on the device path')
         if surrogate_type not in ('gp', 'gp_b200', 'gp_mcmc'):
             raise ValueError("surrogate_type %r is not part of the B200 hot path (use 'gp' or 'gp_mcmc')"
                              % surrogate_type)
@@ -254,6 +256,15 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
         dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
         N = int(X_dev.shape[0])
+        if getattr(self.types, 'has_conditions', False) and self._G == 1:
+            # a space with conditional hyper-parameters: every kernel value carries the activity mask of
+            # gp_kernels.py:21-29.  The masked cross-covariance lives in the per-(row, surrogate) posterior
+            # kernel (tlbo_gp_predict); the fused kernel then combines, scores and reduces the resident rows.
+            mu, var = self._predict_slots(0, self.K + 1, X_dev)
+            return ops.predict_ei_fused(self._logical(), self.types, dw, dskip, X_dev, eta, par=par,
+                                        var_floor=var_floor, keys=keys, excluded=excluded, idx_offset=idx_offset,
+                                        mode=self._fused_mode, order=dorder, want_rows=want_rows, ws=ws, sync=sync,
+                                        nmax=8, cache=(mu, var))
         if N <= SMALL_QUERY_ROWS and (X_dev.data_ptr(), N) not in self._pool_cache:
             # small ad-hoc query sets (the online scenario's neighbourhoods and sampled configurations):
             # a pool tile is scored by ONE CTA walking the surrogates in turn, which leaves the device
@@ -387,6 +398,8 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         from tlbo_b200 import ops
         if self.K == 0 or self.source_surrogates is None:
             return
+        if getattr(self.types, 'has_conditions', False):
+            return                      # masked posteriors are evaluated per call (see _fused)
         key = (X_dev.data_ptr(), int(X_dev.shape[0]))
         if key in self._pool_cache:
             return

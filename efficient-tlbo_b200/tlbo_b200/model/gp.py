@@ -55,7 +55,7 @@ class GaussianProcess(object):
     def __init__(self, configspace, types, bounds, kernel=None, alpha=0, normalize_y=True, n_opt_restarts=10,
                  seed=42, prior_rng=None):
         self.configspace = configspace
-        self.types = np.asarray(types)
+        self.types = np.asanyarray(types)        # keeps TypesArray.has_conditions
         self.bounds = bounds
         self.kernel = kernel if kernel is not None else KernelInfo(self.types)
         self._theta0 = self.kernel.theta.copy()

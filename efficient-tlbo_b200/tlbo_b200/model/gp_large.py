@@ -45,6 +45,12 @@ class _Problem(object):
         self.D2 = (self.Xc[:, None, :] - self.Xc[None, :, :]) ** 2 if cont else None           # [n, n, dc]
         self.NE = (self.Xk[:, None, :] != self.Xk[None, :, :]).to(torch.float64) if cat else None
         self.eye = torch.eye(self.n, dtype=torch.float64, device=dev)
+        # activity mask of gp_kernels.py:21-29 (spaces with conditions): 1 iff the two rows have the same set of
+        # columns <= -1
+        self.active = None
+        if getattr(types, 'has_conditions', False):
+            Xd = torch.from_numpy(X).to(dev) <= -1.0
+            self.active = (~((Xd[:, None, :] != Xd[None, :, :]).any(dim=2))).to(torch.float64)
 
 
 def _priors(theta):
@@ -90,6 +96,8 @@ def kernel_parts(P, theta):
     else:
         hs = torch.zeros(n, n, dtype=torch.float64, device=P.y.device)
     E = torch.exp(-t - hs)
+    if P.active is not None:
+        E = E * P.active                   # every term of K and dK carries E
     Km = c * ((1.0 + t + t * t / 3.0) * E)
     return Km, t, E
 
@@ -235,6 +243,14 @@ def posterior_pool(pack, slot, types, X_dev, chunk=8192):
         for q in range(dk):
             hs += (Xq[:, ki[q], None] != Xs[None, :, dc + q]).to(torch.float64) * hk[q]
         Ks = c * ((1.0 + t + t * t / 3.0) * torch.exp(-t - hs))
+        if getattr(types, 'has_conditions', False):
+            qpat = Xq <= -1.0                                             # original column order
+            tpat = torch.zeros(n, Xq.shape[1], dtype=torch.bool, device=X_dev.device)
+            if dc:
+                tpat[:, ci] = Xs[:, :dc] <= -il
+            if dk:
+                tpat[:, ki] = Xs[:, dc:dc + dk] <= -1.0
+            Ks = Ks * (~((qpat[:, None, :] != tpat[None, :, :]).any(dim=2))).to(torch.float64)
         mean = Ks @ alpha
         V = Ks @ LinvT
         yv = torch.clamp(diag - (V * V).sum(1), min=0.0)

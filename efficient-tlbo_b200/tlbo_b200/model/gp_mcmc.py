@@ -74,7 +74,7 @@ class GaussianProcessMCMC(object):
         if n_mcmc_walkers < 2 or n_mcmc_walkers % 2:
             raise ValueError('n_mcmc_walkers must be even (emcee splits the ensemble in two halves)')
         self.configspace = configspace
-        self.types = np.asarray(types)
+        self.types = np.asanyarray(types)        # keeps TypesArray.has_conditions
         self.bounds = bounds
         self.kernel = kernel if kernel is not None else KernelInfo(self.types)
         self._theta0 = self.kernel.theta.copy()

@@ -34,9 +34,16 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+TYPES_HAS_CONDITIONS = 0x40000000        # include/tlbo_b200.h: bit 30 of h_types[0]
+
+
 def _types_arr(types):
-    t = np.ascontiguousarray(np.asarray(types, dtype=np.int32))
-    return t
+    """``h_types`` of the C ABI: int32[d], with the space's ``has_conditions`` fact (a ``TypesArray`` attribute) as
+    bit 30 of element 0."""
+    t = np.array(np.asarray(types), dtype=np.int32)
+    if getattr(types, 'has_conditions', False):
+        t[0] |= TYPES_HAS_CONDITIONS
+    return np.ascontiguousarray(t)
 
 
 def round_up(n, m):

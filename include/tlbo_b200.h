@@ -35,6 +35,11 @@ extern "C" {
 #define TLBO_MAX_D 22          /* H = d + 2 <= 24 */
 #define TLBO_E_BADARG (-1)
 #define TLBO_E_TOOLARGE (-2)
+/* h_types[d] everywhere below: 0 = numerical column, k > 0 = categorical with k choices (tlbo/model/util_funcs.py:14-55
+ * get_types).  Bit 30 of h_types[0] set: the configuration space has conditions (tlbo/model/base_gp.py:134-146
+ * _set_has_conditions), and every kernel value k(x, x') is multiplied by the activity mask of
+ * tlbo/model/gp_kernels.py:21-29 -- 1 iff x and x' have the same set of columns <= -1 (inactive). */
+#define TLBO_TYPES_HAS_CONDITIONS 0x40000000
 
 const char* tlbo_last_error(void);
 int tlbo_version(void);

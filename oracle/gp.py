@@ -32,7 +32,8 @@ class KernelSpec(object):
     """Shape of the kernel tree built by ``create_gp_model``
     (tlbo/model/model_builder.py:28-72)."""
 
-    def __init__(self, types):
+    def __init__(self, types, has_conditions=False):
+        self.has_conditions = bool(has_conditions or getattr(types, 'has_conditions', False))
         types = np.asarray(types)
         self.types = types
         self.d = len(types)
@@ -112,13 +113,13 @@ def _hamming(Xk, Yk, ls, eval_gradient):
     return K, grad
 
 
-def kernel(theta, spec, X, Y=None, eval_gradient=False):
+def kernel(theta, spec, X, Y=None, eval_gradient=False, _plain=False):
     """k(X, Y) of ``c * (matern * hamming) + white`` and, optionally, dK/dtheta.
 
     Composition rules: Product ``gp_kernels.py:251-256``, Sum ``:307-313``,
     ConstantKernel ``:367-383``, WhiteKernel ``:631-650``; column selection via
-    ``operate_on`` ``:41-79``.  The conditional-activity mask (``:21-29``) is
-    not restated: none of the benchmark spaces in scope has conditions.
+    ``operate_on`` ``:41-79``; the conditional-activity mask (``:21-29``) when
+    ``spec.has_conditions``.
     """
     c, ls_cont, ls_cat, noise = spec.split(theta)
     X = np.atleast_2d(X)
@@ -126,6 +127,17 @@ def kernel(theta, spec, X, Y=None, eval_gradient=False):
     m = n if Y is None else Y.shape[0]
     if Y is not None and eval_gradient:
         raise ValueError("Gradient can only be evaluated when Y is None.")
+    if getattr(spec, 'has_conditions', False) and not _plain:
+        # gp_kernels.py:21-29 + :49-56: the top-level kernel computes the activity mask over ALL columns and hands
+        # it to every leaf, each of which multiplies its K (and dK) by it (:465, :566, :639, :720) -- the mask is
+        # 0/1, so the product carries it once: K = active * (c * matern * hamming + white)
+        X_cond = X <= -1
+        Y_cond = X_cond if Y is None else (np.atleast_2d(Y) <= -1)
+        active = ~((np.expand_dims(X_cond, axis=1) != Y_cond).any(axis=2))
+        r = kernel(theta, spec, X, Y, eval_gradient, _plain=True)
+        if eval_gradient:
+            return r[0] * active, r[1] * active[:, :, np.newaxis]
+        return r * active
 
     K2 = np.ones((n, m))
     grads2 = []
@@ -292,9 +304,9 @@ class OracleGP(object):
     ``AbstractModel.train/predict`` (base_model.py:93-200,244-249) over skopt's
     GaussianProcessRegressor semantics."""
 
-    def __init__(self, types, facade_seed, normalize_y=True, n_opt_restarts=10):
+    def __init__(self, types, facade_seed, normalize_y=True, n_opt_restarts=10, has_conditions=False):
         self.types = np.asarray(types)
-        self.spec = KernelSpec(self.types)
+        self.spec = KernelSpec(self.types, has_conditions or getattr(types, 'has_conditions', False))
         self.facade_seed = facade_seed
         self.normalize_y = normalize_y
         self.n_opt_restarts = n_opt_restarts

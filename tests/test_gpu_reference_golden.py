@@ -352,3 +352,73 @@ def test_cuda_meta_feature_baselines_with_device_fit(method):
     assert same >= 4
     span = tables[0][1].max() - tables[0][1].min()
     assert min(smbo.perfs) <= D[p + 'perfs'].min() + 0.05 * span
+
+
+def test_cuda_conditional_activity_mask_matches_reference(monkeypatch):
+    """A space WITH conditions (``TableSpace(..., has_conditions=True)``; fixture reference_v5_cond.npz from the
+    reference's own kernels): likelihood + gradient, the device fit, the posterior and EI carry the activity mask
+    of gp_kernels.py:21-29; the same through the large-n path."""
+    import torch
+    from tlbo_b200 import ops
+    from tlbo_b200.acquisition_function.acquisition import EI
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.model import gp_large
+    from tlbo_b200.model.model_builder import build_model
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v5_cond.npz'))
+    cs = TableSpace(D['types'], has_conditions=True)
+    types = cs.get_types()[0]
+    assert types.has_conditions
+    Xi = D['X'].copy(); Xi[~np.isfinite(Xi)] = -1
+    f, g, st = ops.gp_nll_grad_batched([Xi] * 3, [D['ynorm']] * 3, types, list(D['thetas']))
+    assert not np.asarray(st).any()
+    np.testing.assert_allclose(f, D['nll_f'], rtol=1e-8, atol=0)
+    np.testing.assert_allclose(g, D['nll_g'], rtol=1e-6, atol=1e-8)
+    # without the flag the numbers differ (the mask removes 74 % of the kernel matrix)
+    f0, _, _ = ops.gp_nll_grad_batched([Xi], [D['ynorm']], D['types'], [D['thetas'][0]])
+    assert abs(f0[0] - D['nll_f'][0]) > 1e-3
+    # posterior + EI at the reference's theta*
+    m = build_model('gp', cs, np.random.RandomState(7))
+    m.kernel.theta = D['theta_star'].copy()
+    m.train(D['X'], D['y'].copy(), do_optimize=False)
+    mu, var = m.predict(D['Xq'])
+    np.testing.assert_allclose(mu, D['mu'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, D['var'], rtol=1e-6, atol=1e-13)
+    ei = EI(m)
+    ei.update(model=m, eta=float(D['eta']), num_data=D['X'].shape[0])
+    # the device fit finds an optimum at least as good as the reference's
+    m2 = build_model('gp', cs, np.random.RandomState(7))
+    m2.train(D['X'], D['y'].copy())
+    spec_f = ops.gp_nll_grad_batched([Xi], [D['ynorm']], types, [D['theta_star']])[0][0]
+    got_f = ops.gp_nll_grad_batched([Xi], [D['ynorm']], types, [m2.hypers])[0][0]
+    assert got_f <= spec_f + 1e-5 * max(1.0, abs(spec_f))
+    # large-n path
+    P = gp_large._Problem(Xi, D['ynorm'], types)
+    for i, theta in enumerate(D['thetas']):
+        fl, gl = gp_large.nll_grad(P, theta)
+        assert abs(fl - D['nll_f'][i]) <= 1e-9 * abs(D['nll_f'][i])
+        np.testing.assert_allclose(gl, D['nll_g'][i], rtol=1e-6, atol=1e-8)
+    Xq = D['Xq'].copy(); Xq[~np.isfinite(Xq)] = -1
+    pm, pv = gp_large.posterior_pool(m._pack, m._slot, types, torch.from_numpy(Xq).cuda(), chunk=50)
+    np.testing.assert_allclose(pm[0].cpu().numpy(), D['mu'].ravel(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(pv[0].cpu().numpy(), D['var'].ravel(), rtol=1e-6, atol=1e-13)
+
+
+def test_cuda_facade_over_conditional_space_runs_masked_posteriors():
+    """A facade over a space with conditions scores the pool through the masked posterior kernel: the fused
+    result equals EI over the per-row posteriors of the same surrogates."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.notl import NoTL
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v5_cond.npz'))
+    cs = TableSpace(D['types'], has_conditions=True)
+    Xq = D['Xq'].copy(); Xq[~np.isfinite(Xq)] = -1
+    yq = np.sin(Xq[:, 3]) + 0.1 * Xq[:, 7]
+    fac = NoTL(cs, [], None, 3, surrogate_type='gp')
+    smbo = SMBO_OFFLINE((Xq, yq), cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3, random_seed=3,
+                        max_runs=100)
+    for _ in range(6):
+        smbo.iterate()
+    mu, var = fac.predict_marginalized_over_instances(Xq)
+    mu1, var1 = fac.target_surrogate.predict(Xq)
+    np.testing.assert_allclose(mu, mu1, rtol=1e-12)
+    assert len(set(smbo.configurations)) == 6

@@ -287,3 +287,27 @@ def test_meta_feature_baselines_match_reference(method, monkeypatch):
     mu, var = fac.predict(tables[0][0][:64])
     np.testing.assert_allclose(mu, D[p + 'final_mu'], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(var, D[p + 'final_var'], rtol=1e-6, atol=1e-12)
+
+
+def test_conditional_activity_mask_matches_reference():
+    """A space WITH conditions (fixture reference_v5_cond.npz, the reference's own kernels / GaussianProcess with
+    ``has_conditions``): the activity mask of gp_kernels.py:21-29 in K, dK/dtheta, K(X*, X), the likelihood and
+    the posterior; inactive entries arrive as NaN and are imputed to -1 (base_gp.py:148-151)."""
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v5_cond.npz'))
+    types = D['types']
+    spec = ogp.KernelSpec(types, has_conditions=True)
+    Xi, Xqi = ogp.impute_inactive(D['X']), ogp.impute_inactive(D['Xq'])
+    K, dK = ogp.kernel(D['thetas'][0], spec, Xi, eval_gradient=True)
+    np.testing.assert_allclose(K, D['K'], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(dK, D['dK'], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(ogp.kernel(D['thetas'][0], spec, Xqi, Xi), D['Ks'], rtol=1e-13, atol=1e-15)
+    assert (D['K'] == 0).mean() > 0.5
+    for i, theta in enumerate(D['thetas']):
+        f, g = ogp.nll(theta, spec, Xi, D['ynorm'])
+        assert abs(f - D['nll_f'][i]) <= 1e-10 * abs(D['nll_f'][i])
+        np.testing.assert_allclose(g, D['nll_g'][i], rtol=1e-8, atol=1e-10)
+    g = ogp.OracleGP(types, 7, has_conditions=True)
+    g.train(D['X'], D['y'].copy(), do_optimize=False, theta=D['theta_star'])
+    mu, var = g.predict(D['Xq'])
+    np.testing.assert_allclose(mu, D['mu'], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, D['var'], rtol=1e-6, atol=1e-13)
