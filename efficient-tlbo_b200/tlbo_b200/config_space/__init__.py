@@ -132,7 +132,13 @@ def convert_configurations_to_array(configs):
         return np.asarray(configs, dtype=np.float64)
     if len(configs) == 0:
         return np.zeros((0, 0), dtype=np.float64)
-    return np.array([c.get_array() for c in configs], dtype=np.float64)
+    X = np.array([c.get_array() for c in configs], dtype=np.float64)
+    cs = getattr(configs[0], 'configuration_space', None)
+    if cs is not None and hasattr(cs, 'get_hyperparameters'):
+        # tlbo/config_space/util.py:33-60: inactive (non-finite) entries take the normalised default
+        from tlbo_b200.config_space.space import impute_default_values
+        X = impute_default_values(cs, X)
+    return X
 
 
 def table_to_configurations(space, X):
