@@ -14,8 +14,8 @@ Prints ONE JSON line (rank 0).  The headline fields are the RGPE run on configs[
 BASELINE.json's metric rides in the same line under "sub" (each record with its own value / e2e /
 roofline / cpu_baseline): "topo" (OBTLV, what --methods topo runs), "pool_1e6" (the north-star pool
 size), "predict_sweep" (configs[3]: 30 surrogates x n x N x d, nothing resident), "pool_strong" (ONE
-trial over a FIXED pool sharded over the N ranks: strong scaling, NCCL all-gather of 4 doubles per
-rank), and for N > 1 "distinct_trials" (every rank its own task / seed, slowest rank charged) and --
+trial over a FIXED 1e7-row pool sharded over the N ranks: strong scaling, NCCL all-gather of 4 doubles per
+rank), "online" (configs[2]: 50 online-scenario trials sharded over the ranks), and for N > 1 "distinct_trials" (every rank its own task / seed, slowest rank charged) and --
 at N = 8 -- "gp_mcmc" (configs[4]: TOPO over MCMC-marginalised GPs).  N > 1: one process per GPU
 (torchrun); the headline shards by trial with no data-path collective ("weak" scaling).
 """
@@ -68,8 +68,8 @@ def parse_args():
                     help='reference arm: score this many pool rows per step and scale (0 = the full pool, measured)')
     ap.add_argument('--passes', type=int, default=5, help='timed passes of exactly --steps steps each (median reported)')
     ap.add_argument('--sub', default='auto', help="sub-records: 'auto', 'none' or a comma list of topo,pool_1e6,predict_sweep,"
-                    "pool_strong,distinct_trials,gp_mcmc")
-    ap.add_argument('--strong-pool', type=int, default=1000000, help='rows of the fixed pool of the pool_strong record')
+                    "pool_strong,online,distinct_trials,gp_mcmc")
+    ap.add_argument('--strong-pool', type=int, default=10000000, help='rows of the fixed pool of the pool_strong record')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pool-sharded', action='store_true')
     ap.add_argument('--distinct-trials', action='store_true',
@@ -699,6 +699,76 @@ def measure_pool_strong(args, comm, flush, pool_total):
     return rec
 
 
+def measure_online(args, comm, n_trials=50, iters=4, n0=20, num_points=5000):
+    """BASELINE configs[2]: the ONLINE scenario (tools/online_benchmark.py shape: SMBO_ONLINE with
+    InterleavedLocalAndRandomSearch -- 10 hill-climbs + ~4990 random configurations sorted by EI -- and RGPE over
+    29 sources), `n_trials` independent trials (own target task / seed) sharded round-robin over the ranks, `iters`
+    timed BO iterations each after one untimed one.  No collective on the data path; the slowest rank is charged.
+    Facade construction (the 29 source fits of a trial) is outside the timed loops and reported beside them."""
+    import torch
+    from tlbo_b200 import ops, synthetic
+    from tlbo_b200.config_space import Configuration, TableSpace
+    from tlbo_b200.facade.rgpe import RGPE
+    from tlbo_b200.framework.smbo_online import SMBO_ONLINE
+    types, const = synthetic.space_types('rf')
+    fam = synthetic.TaskFamily(types, const, n_tasks=30, seed=4466)
+    K = args.sources
+    mine = [t for t in range(n_trials) if t % comm.world == comm.rank]
+    timed_ms, build_s, launches = 0.0, 0.0, 0
+    comm.barrier()
+    for t in mine:
+        task, seed = t % 30, 4465 + t
+        ids = [i for i in range(30) if i != task]
+        np.random.RandomState(seed).shuffle(ids)
+        sources = []
+        for k in ids[:K]:
+            rng = np.random.RandomState(1000 + k)
+            X = synthetic.sample_table(rng, 50, types, const)
+            sources.append((X, fam.evaluate(k, X, rng)))
+
+        def objective(config, task=task):
+            x = config.get_array() if hasattr(config, 'get_array') else np.asarray(config)
+            return float(fam.evaluate(task, x[np.newaxis, :])[0])
+        a = time.perf_counter()
+        cs = TableSpace(types, const_mask=const)
+        cs.seed(seed)
+        fac = RGPE(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+        smbo = SMBO_ONLINE(objective, cs, fac, random_seed=seed, max_runs=10 ** 9, num_points=num_points)
+        X0 = cs.sample_array(n0)
+        for i in range(n0):
+            c = Configuration(cs, X0[i], -1)
+            smbo.configurations.append(c)
+            smbo.perfs.append(objective(c))
+            smbo.history_container.add(c, smbo.perfs[-1])
+        smbo.iterate()
+        torch.cuda.synchronize()
+        build_s += time.perf_counter() - a
+        ops.STATS.reset()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            smbo.iterate()
+        e1.record()
+        torch.cuda.synchronize()
+        timed_ms += e0.elapsed_time(e1)
+        launches += ops.STATS.total_launches()
+        del fac, smbo
+    comm.barrier()
+    ms = comm.max_over_ranks(timed_ms)
+    per_rank = comm.all_ranks(timed_ms)
+    total_iters = n_trials * iters
+    return {'metric': 'BO iters/sec, online scenario (fit + weights + interleaved local / random EI search) at %d sources' % K,
+            'value': total_iters / (ms * 1e-3), 'unit': UNIT, 'n_gpus': comm.world, 'scaling': 'strong',
+            'trials': n_trials, 'timed_iterations_per_trial': iters, 'ms_per_iteration_per_rank': ms / max(len(mine) * iters, 1),
+            'per_rank_timed_ms': [round(v, 2) for v in per_rank], 'gpu_launches_rank0': launches,
+            'construction_s_rank0': build_s,
+            'config': {'workload': 'rgpe online BO (SMBO_ONLINE + InterleavedLocalAndRandomSearch, %d challengers per '
+                                   'iteration), %d source GPs x 50 obs, d=9 random_forest space, %d trials (own task / seed) '
+                                   'sharded over the ranks, target n=%d..%d' % (num_points, K, n_trials, n0 + 1, n0 + iters)},
+            'note': 'host-bound: one hill-climb step = one neighbourhood launch + one synchronisation (DESIGN.md 3.5)'}
+
+
 def predict_sweep(dmma_tf, max_rows):
     """BASELINE configs[3]: 30 surrogates x n in {50,100,200} x N candidates x d in {5,20}, every surrogate
     evaluated per candidate (nothing resident): candidates / s and the fraction of the FP64 DMMA peak."""
@@ -791,15 +861,15 @@ def run_ours(args):
     if args.sub == 'auto':
         subs = ['pool_strong']
         if world == 1:
-            subs = ['topo', 'pool_1e6', 'predict_sweep', 'pool_strong']
+            subs = ['topo', 'pool_1e6', 'predict_sweep', 'pool_strong', 'online']
         else:
-            subs = ['distinct_trials', 'pool_strong'] + (['gp_mcmc'] if world >= 8 else [])
+            subs = ['distinct_trials', 'pool_strong', 'online'] + (['gp_mcmc'] if world >= 8 else [])
     elif args.sub in ('none', ''):
         subs = []
     else:
         subs = [x.strip() for x in args.sub.split(',') if x.strip()]
     if args.method != 'rgpe' or args.surrogate != 'gp' or args.pool != 100000:
-        subs = [x for x in subs if x in ('pool_strong', 'distinct_trials')] if args.sub == 'auto' else subs
+        subs = [x for x in subs if x in ('pool_strong', 'distinct_trials', 'online')] if args.sub == 'auto' else subs
 
     # one clock sampler for the whole job (rank 0's GPU): eight nvidia-smi pollers contend for the driver
     # lock with the ranks' own launches and synchronisations
@@ -824,6 +894,8 @@ def run_ours(args):
             rec = measure_offline(args, comm, flush, dmma_tf, 'topo', args.pool, 'gp_mcmc', distinct=True, passes=1)
         elif name == 'pool_strong':
             rec = measure_pool_strong(args, comm, flush, args.strong_pool)
+        elif name == 'online':
+            rec = measure_online(args, comm)
         elif name == 'predict_sweep':
             rec = predict_sweep(dmma_tf, 10 ** 7) if rank == 0 else None
             comm.barrier()

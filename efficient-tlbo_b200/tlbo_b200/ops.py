@@ -1,6 +1,7 @@
 """Thin, typed wrappers over the C ABI (one function per entry point of
 ``include/tlbo_b200.h``).  torch is used for device memory and streams only."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -612,7 +613,7 @@ class DeviceRandomState(object):
         self.state = torch.empty(625, dtype=torch.int32, device=_dev())
         self._slices, self._S, self._n = 1, 0, 0
         n_hint = int(n_hint)
-        C = min(self.SLICE_MAX_COUNT, n_hint // self.SLICE_MIN)
+        C = min(int(os.environ.get('TLBO_KEY_SLICES_MAX', self.SLICE_MAX_COUNT)), n_hint // self.SLICE_MIN)
         if C >= 2:
             from tlbo_b200.utils import mt_jump
             S = round_up((n_hint + C - 1) // C, 312)
