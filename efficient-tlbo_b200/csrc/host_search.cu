@@ -10,6 +10,7 @@
 // hill-climb step (about 80 scalar draws through the interpreter) -- more than the device work of the
 // step; here it is a few microseconds.  tests/test_online_search_cpu.py checks it draw for draw
 // against the Python statement of the same algorithm (tlbo_b200/config_space).
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include "tlbo_common.cuh"
@@ -272,4 +273,75 @@ extern "C" int tlbo_host_prepare_jobs(const double* h_X, double* h_y_inout, int 
   }
   delete[] tmp;
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One hill-climb of the online scenario's local search (reference tlbo/optimizer/ei_optimization.py:239-294,
+// LocalSearch._one_iter) driven from native code: per step the one-exchange neighbourhood of the incumbent
+// (generator seed = the next pre-drawn rng.randint(0, 10000)), ONE acquisition evaluation of the whole
+// neighbourhood -- the same two launches the Python path makes: tlbo_gp_predict for every (row, surrogate)
+// posterior, tlbo_predict_ei_fused_cached in all-resident mode for combine + EI -- one stream synchronisation,
+// and the reference's accept rule (first neighbour with EI > incumbent, NaN -> -DBL_MAX as
+// AbstractAcquisitionFunction.__call__ does).  A climb is ~25 such steps; in the interpreter a step costs ~50 us
+// of Python on top of the launches.  Buffers (all caller-owned): h_X pinned [cap, d] staging, d_X [cap, d],
+// d_mu / d_var [M * cap], d_mu_rows / d_var_rows [cap], h_ei mapped pinned [cap] (the fused kernel stores EI
+// straight into it), h_best mapped pinned [4].
+// Returns 0 when the climb ended (no improving neighbour or max_steps), 1 when the pre-drawn seeds ran out
+// (call again with more seeds: the incumbent / counters are up to date), < 0 / CUDA codes on error.
+extern "C" int tlbo_local_search_climb(const tlbo_pack* view, const tlbo_pack* logical, const int32_t* h_types,
+                                       const uint8_t* h_const_mask, const double* d_w, const int32_t* d_skip,
+                                       const int32_t* d_order, int mode, double eta, double par, double var_floor,
+                                       int num_neighbors, double stdev, const uint32_t* h_seeds, int n_seeds,
+                                       int max_steps, double* h_config, double* h_acq, double* h_X, double* d_X,
+                                       double* d_mu, double* d_var, double* d_mu_rows, double* d_var_rows,
+                                       double* h_ei, double* h_best, void* d_work, int cap, int32_t* h_counters,
+                                       void* stream) {
+  if (!view || !logical || !h_types || !h_seeds || !h_config || !h_acq || !h_X || !d_X || !d_mu || !d_var ||
+      !h_ei || !h_best || !d_work || !h_counters || cap <= 0) {
+    tlbo_set_error("tlbo_local_search_climb: bad arguments");
+    return TLBO_E_BADARG;
+  }
+  const int d = view->d, M = view->M;
+  cudaStream_t s = (cudaStream_t)stream;
+  // h_counters: [0] seeds consumed (= hill-climb steps), [1] neighbours the lazy reference loop inspects,
+  //             [2] acquisition evaluations, [3] rows with EI < 0 (the caller raises), [4] steps of THIS climb so far
+  int used = 0;
+  for (;;) {
+    if (used >= n_seeds) { h_counters[0] += used; return 1; }
+    int rows = 0;
+    int rc = tlbo_one_exchange_neighbourhood(h_config, d, h_types, h_const_mask, h_seeds[used], num_neighbors, stdev,
+                                             h_X, cap, &rows);
+    if (rc) return rc;
+    used++;
+    h_counters[4] += 1;
+    bool changed = false;
+    if (rows > 0) {
+      for (long i = 0; i < (long)rows * d; i++)
+        if (!isfinite(h_X[i])) h_X[i] = -1.0;               // EI._to_device / GaussianProcess._impute_inactive
+      TLBO_CUDA_CHECK(cudaMemcpyAsync(d_X, h_X, sizeof(double) * (size_t)rows * d, cudaMemcpyHostToDevice, s));
+      rc = tlbo_gp_predict(view, h_types, d_X, rows, d_mu, d_var, stream);
+      if (rc) return rc;
+      rc = tlbo_predict_ei_fused_cached(logical, h_types, d_w, d_skip, d_order, mode, d_X, rows, eta, par, var_floor,
+                                        nullptr, nullptr, 0, 0, h_best, d_mu_rows, d_var_rows, h_ei, d_mu, d_var, M,
+                                        d_work, stream);
+      if (rc) return rc;
+      TLBO_CUDA_CHECK(cudaStreamSynchronize(s));
+      h_counters[2] += 1;
+      if (h_best[3] > 0.0) { h_counters[3] += (int32_t)h_best[3]; h_counters[0] += used; return 0; }
+      int first = -1;
+      for (int j = 0; j < rows; j++) {
+        double a = h_ei[j];
+        if (a != a) a = -DBL_MAX;
+        if (a > *h_acq) { first = j; break; }
+      }
+      h_counters[1] += (first >= 0) ? first + 1 : rows;
+      if (first >= 0) {
+        for (int p = 0; p < d; p++) h_config[p] = h_X[(size_t)first * d + p];
+        double a = h_ei[first];
+        *h_acq = (a != a) ? -DBL_MAX : a;
+        changed = true;
+      }
+    }
+    if (!changed || (max_steps >= 0 && h_counters[4] == max_steps)) { h_counters[0] += used; return 0; }
+  }
 }

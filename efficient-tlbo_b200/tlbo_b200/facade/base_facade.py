@@ -342,6 +342,72 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         ops.STATS.d2h += N * 8 + 32
         return sq.ei_np[:N].copy(), int(sq.best_np[3])
 
+    def climb(self, x0, acq0, rng, eta, par, var_floor, max_steps, const_mask, num_neighbors, stdev, stats):
+        """One hill-climb of the online local search (ei_optimization.py:239-294) through the native driver
+        ``tlbo_local_search_climb``: same launches, same accept rule, same stream consumption as the per-step
+        Python loop (``rng.randint(0, 10000)`` per step: a block of seeds is drawn ahead and the generator is
+        rewound to exactly the number the climb consumed).  Returns ``(x, acq)`` or None when this facade has no
+        native path (walker groups, spaces with conditions, large-n surrogates)."""
+        import ctypes
+        from tlbo_b200 import ops
+        from tlbo_b200._cabi import check, lib, ptr
+        from tlbo_b200.model import gp_large
+        if (self._G > 1 or getattr(self.types, 'has_conditions', False) or self.target_surrogate is None
+                or getattr(self.target_surrogate, 'n_train_', 0) > gp_large.LARGE_N):
+            return None
+        d = len(self.types)
+        tarr = np.asarray(self.types, dtype=np.int64)
+        cap = int(np.sum(np.where(tarr > 0, tarr - 1, num_neighbors))) + 1
+        sq = self._small
+        if sq is None or sq.cap < cap:
+            sq = self._small = ops.SmallQuery(max(256, cap), d, self.K + 1)
+        ens = self._ens_cache
+        if ens is None or ens[0] is not self._pack:
+            w, skip, order = self._ensemble_args()
+            dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
+            dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
+            dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+            ens = self._ens_cache = (self._pack, dw, dskip, dorder, ops.pack_view(self._pack, 0, self.K + 1))
+        _, dw, dskip, dorder, view = ens
+        logical = self._logical()
+        logical.c.nmax = 8
+        view.c.nmax = 0
+        t = ops._types_arr(self.types)
+        cm = np.ascontiguousarray(const_mask, dtype=np.uint8)
+        x = np.array(x0, dtype=np.float64)
+        acq = ctypes.c_double(float(acq0))
+        counters = np.zeros(5, dtype=np.int32)
+        stream = ops._stream()
+        while True:
+            state = rng.get_state()
+            seeds = rng.randint(0, 10000, size=64).astype(np.uint32)
+            before = int(counters[0])
+            rc = lib.tlbo_local_search_climb(view.ref(), logical.ref(), ptr(t), ptr(cm), ptr(dw), ptr(dskip), ptr(dorder),
+                                             int(self._fused_mode), float(eta), float(par), float(var_floor),
+                                             int(num_neighbors), float(stdev), ptr(seeds), 64,
+                                             -1 if max_steps is None else int(max_steps), ptr(x), ctypes.byref(acq),
+                                             ptr(sq.X), ptr(sq.Xd), ptr(sq.mu), ptr(sq.var), ptr(sq.mu_rows),
+                                             ptr(sq.var_rows), ptr(sq.ei), ptr(sq.ws.best), ptr(sq.ws.work), sq.cap,
+                                             ptr(counters), stream)
+            used = int(counters[0]) - before
+            rng.set_state(state)                    # rewind to exactly the draws the climb consumed
+            if used:
+                rng.randint(0, 10000, size=used)
+            if rc not in (0, 1):
+                check(rc)
+            if rc == 0:
+                break
+        stats['steps'] += int(counters[0])
+        stats['neighbours'] += int(counters[1])
+        stats['launches'] += int(counters[2])
+        ops.STATS.launches['gp_predict_small'] = ops.STATS.launches.get('gp_predict_small', 0) + int(counters[2])
+        ops.STATS.launches['predict_ei_fused'] = ops.STATS.launches.get('predict_ei_fused', 0) + 2 * int(counters[2])
+        if counters[3] > 0:
+            raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")
+        # ConfigSpace's lazy generator: one np.random.random() from the GLOBAL stream per inspected neighbour
+        np.random.random(int(counters[1]))
+        return x, float(acq.value)
+
     # ---- MCMC-marginalised surrogates: group-level posteriors ----------------------------------
     def _logical(self):
         """K + 1 placeholder slots (n = 1) standing for the marginalised surrogates in the fused

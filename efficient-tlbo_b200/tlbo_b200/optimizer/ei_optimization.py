@@ -23,7 +23,8 @@ import logging
 
 import numpy as np
 
-from tlbo_b200.config_space import Configuration, convert_configurations_to_array, one_exchange_neighbourhood_arrays
+from tlbo_b200.config_space import (NEIGHBOUR_STDEV, NUM_NEIGHBORS, Configuration, convert_configurations_to_array,
+                                    one_exchange_neighbourhood_arrays)
 from tlbo_b200.optimizer.ei_offline_optimizer import AcquisitionFunctionMaximizer
 from tlbo_b200.optimizer.random_configuration_chooser import ChooserProb
 
@@ -45,6 +46,7 @@ class LocalSearch(_SortMixin, AcquisitionFunctionMaximizer):
         self.n_steps_plateau_walk = n_steps_plateau_walk
         self.logger = logging.getLogger(self.__module__ + '.' + self.__class__.__name__)
         self.last_stats = None
+        self.native_climb = True          # one C-ABI call per hill-climb (tlbo_local_search_climb); False: per-step Python loop
 
     def _maximize(self, runhistory, num_points, **kwargs):
         init_points = self._get_initial_points(num_points, runhistory)
@@ -74,6 +76,19 @@ class LocalSearch(_SortMixin, AcquisitionFunctionMaximizer):
     def _one_iter(self, start_point, acq_val_incumbent, stats):
         """ei_optimization.py:239-294 with the neighbourhood of each step scored in one launch."""
         incumbent = start_point
+        # native driver: the whole climb in one call (same launches, accept rule and stream consumption)
+        model = getattr(self.acquisition_function, 'model', None)
+        space = getattr(start_point, 'space', None)
+        if self.native_climb and hasattr(model, 'climb') and hasattr(space, 'const_mask'):
+            af = self.acquisition_function
+            af._require_eta()
+            res = model.climb(start_point.get_array(), float(acq_val_incumbent[0]), self.rng, af.eta, af.par,
+                              af._var_floor(), self.max_steps, space.const_mask, NUM_NEIGHBORS, NEIGHBOUR_STDEV, stats)
+            if res is not None:
+                x, acq = res
+                if not np.array_equal(x, start_point.get_array()):
+                    incumbent = Configuration(start_point.space, x, -1)
+                return np.array([acq]), incumbent
         local_search_steps = 0
         while True:
             local_search_steps += 1

@@ -283,6 +283,27 @@ int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t*
 int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const double* d_loc, const double* d_scale,
                                   int n, int S, int Mr, double* d_loss, void* stream);
 
+/* One hill-climb of the online scenario's local search (tlbo/optimizer/ei_optimization.py:239-294,
+ * LocalSearch._one_iter), native driver: per step tlbo_one_exchange_neighbourhood(h_config, seed = the next of the
+ * pre-drawn rng.randint(0, 10000) values), ONE acquisition evaluation of the whole neighbourhood (tlbo_gp_predict +
+ * tlbo_predict_ei_fused_cached in all-resident mode: the launches of the per-step Python path), one stream
+ * synchronisation, accept = first neighbour with EI > incumbent (NaN -> -DBL_MAX, acquisition.py:72-76).
+ *   view / logical: the K + 1 surrogates, and K + 1 placeholder slots (n = 1) for the all-resident fused call;
+ *   d_w / d_skip / d_order / mode / eta / par / var_floor: as tlbo_predict_ei_fused;
+ *   h_config [d], h_acq: incumbent and its EI, updated in place;
+ *   h_X pinned [cap, d]; d_X [cap, d]; d_mu, d_var [M * cap]; d_mu_rows, d_var_rows [cap]; h_ei, h_best: MAPPED
+ *   pinned host memory [cap], [4] (written by the kernels); d_work: tlbo_predict_ei_workspace_bytes(cap);
+ *   h_counters int32[5]: += seeds consumed, neighbours the lazy reference loop inspects, acquisition evaluations,
+ *   rows with EI < 0 (the caller raises as EI._compute does), steps of this climb (caller zeroes [4] per climb).
+ * Returns 0: climb ended; 1: seeds ran out (call again with more, state is up to date). */
+int tlbo_local_search_climb(const tlbo_pack* view, const tlbo_pack* logical, const int32_t* h_types,
+                            const uint8_t* h_const_mask, const double* d_w, const int32_t* d_skip,
+                            const int32_t* d_order, int mode, double eta, double par, double var_floor,
+                            int num_neighbors, double stdev, const uint32_t* h_seeds, int n_seeds, int max_steps,
+                            double* h_config, double* h_acq, double* h_X, double* d_X, double* d_mu, double* d_var,
+                            double* d_mu_rows, double* d_var_rows, double* h_ei, double* h_best, void* d_work,
+                            int cap, int32_t* h_counters, void* stream);
+
 /* numpy's LEGACY RandomState.random_sample on the device, bit for bit, with the MT19937 state resident in HBM:
  * the `rng.rand(N)` tie-break keys that `_sort_configs_by_acq_value` (reference
  * tlbo/optimizer/ei_optimization.py:106-132) draws over the whole candidate table on every maximisation.
