@@ -797,53 +797,46 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   double gacc[DMAX];
 #pragma unroll
   for (int p = 0; p < DMAX; p++) gacc[p] = 0.0;
-  for (int q0 = tid; q0 < S.npairs; q0 += 2 * NT) {
-    const int q1 = q0 + NT;
-    const bool has1 = q1 < S.npairs;
-    const int ij0 = S.pairs[q0], ij1 = S.pairs[has1 ? q1 : q0];
-    const int i0 = ij0 >> 16, j0 = ij0 & 0xffff, i1 = ij1 >> 16, j1 = ij1 & 0xffff;
-    const double W0 = A[(size_t)i0 * lda + j0];
-    const double W1 = has1 ? A[(size_t)i1 * lda + j1] : 0.0;        // a masked second pair adds zeros
-    const double* xi0 = S.Xs + (size_t)i0 * da;
-    const double* xj0 = S.Xs + (size_t)j0 * da;
-    const double* xi1 = S.Xs + (size_t)i1 * da;
-    const double* xj1 = S.Xs + (size_t)j1 * da;
-    double WK0, WK1, cf0, cf1;
-    if (S.Kc) {
-      WK0 = W0 * S.Kc[q0]; cf0 = W0 * S.Cg[q0];
-      WK1 = W1 * S.Kc[has1 ? q1 : q0]; cf1 = W1 * S.Cg[has1 ? q1 : q0];
-    } else {
-      double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
-      for (int p = 0; p < nac; p++) {
-        const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
-        s0 += e0 * e0; s1 += e1 * e1;
+  constexpr int PF = 4;                       // pairs in flight per thread (as in kernel_panel_reg)
+  for (int qb = tid; qb < S.npairs; qb += PF * NT) {
+    const double* xi[PF];
+    const double* xj[PF];
+    double WK[PF], cf[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int q = qb + u * NT;
+      const bool has = q < S.npairs;
+      const int qq = has ? q : qb;
+      const int ij = S.pairs[qq];
+      const int i = ij >> 16, j = ij & 0xffff;
+      const double W = has ? A[(size_t)i * lda + j] : 0.0;          // a masked pair adds zeros
+      xi[u] = S.Xs + (size_t)i * da;
+      xj[u] = S.Xs + (size_t)j * da;
+      if (S.Kc) {
+        WK[u] = W * S.Kc[qq];
+        cf[u] = W * S.Cg[qq];
+      } else {
+        double s = 0.0, h = 0.0;
+        for (int p = 0; p < nac; p++) { const double e = xi[u][p] - xj[u][p]; s += e * e; }
+        for (int p = nac; p < da; p++) h += (xi[u][p] != xj[u][p]) ? S.hyp[p] : 0.0;
+        const double t = sqrt_nonneg(s) * SQRT5;
+        double ce = c * exp_nonpos(-t - h);
+        if (sp.has_cond && S.rmask[i] != S.rmask[j]) ce = 0.0;
+        WK[u] = W * (ce * (1.0 + t + t * t * (1.0 / 3.0)));
+        cf[u] = W * (ce * (5.0 / 3.0) * (t + 1.0));
       }
-      for (int p = nac; p < da; p++) {
-        const double hp = S.hyp[p];
-        h0 += (xi0[p] != xj0[p]) ? hp : 0.0;
-        h1 += (xi1[p] != xj1[p]) ? hp : 0.0;
-      }
-      const double t0 = sqrt_nonneg(s0) * SQRT5, t1 = sqrt_nonneg(s1) * SQRT5;
-      double ce0 = c * exp_nonpos(-t0 - h0), ce1 = c * exp_nonpos(-t1 - h1);
-      if (sp.has_cond) {
-        if (S.rmask[i0] != S.rmask[j0]) ce0 = 0.0;
-        if (S.rmask[i1] != S.rmask[j1]) ce1 = 0.0;
-      }
-      WK0 = W0 * (ce0 * (1.0 + t0 + t0 * t0 * (1.0 / 3.0))); cf0 = W0 * (ce0 * (5.0 / 3.0) * (t0 + 1.0));
-      WK1 = W1 * (ce1 * (1.0 + t1 + t1 * t1 * (1.0 / 3.0))); cf1 = W1 * (ce1 * (5.0 / 3.0) * (t1 + 1.0));
     }
-    g0 += WK0;
-    g0 += WK1;
+#pragma unroll
+    for (int u = 0; u < PF; u++) g0 += WK[u];
 #pragma unroll
     for (int p = 0; p < DMAX; p++) {
       if (p < nac) {
-        const double e0 = xi0[p] - xj0[p], e1 = xi1[p] - xj1[p];
-        gacc[p] += cf0 * (e0 * e0);
-        gacc[p] += cf1 * (e1 * e1);
+#pragma unroll
+        for (int u = 0; u < PF; u++) { const double e = xi[u][p] - xj[u][p]; gacc[p] += cf[u] * (e * e); }
       } else if (p < da) {
         const double h3 = S.hyp[TLBO_HMAX + p];
-        gacc[p] += (xi0[p] != xj0[p]) ? WK0 * h3 : 0.0;
-        gacc[p] += (xi1[p] != xj1[p]) ? WK1 * h3 : 0.0;
+#pragma unroll
+        for (int u = 0; u < PF; u++) gacc[p] += (xi[u][p] != xj[u][p]) ? WK[u] * h3 : 0.0;
       }
     }
   }
@@ -862,7 +855,8 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
       g0 += __shfl_xor_sync(0xffffffffu, g0, o);
       gn += __shfl_xor_sync(0xffffffffu, gn, o);
 #pragma unroll
-      for (int p = 0; p < DMAX; p++) gacc[p] += __shfl_xor_sync(0xffffffffu, gacc[p], o);
+      for (int p = 0; p < DMAX; p++)
+        if (p < da) gacc[p] += __shfl_xor_sync(0xffffffffu, gacc[p], o);      // (uniform: only the varying columns)
     }
     if (lane == 0) {
       S.red[wid * 32 + 0] = g0;
