@@ -26,6 +26,7 @@
 //   EI, NaN rule, exclusion of evaluated rows, lexicographic (ei, key, idx) arg-max.
 #include "tlbo_common.cuh"
 #include <float.h>
+#include <string.h>
 
 #define PRED_THREADS 256
 #define PRED_WARPS 8
@@ -39,66 +40,157 @@ struct PredSmallArgs {
   double* mu; double* var;
 };
 
+// ---- TMA (bulk async copy) helpers: candidate tiles of the fused kernel, L^-1 of the small-query kernel ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                            unsigned long long* bar) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(gmem_src), "r"(bytes), "r"(mb)
+               : "memory");
+}
+// the copy alone: the caller has announced the byte count of several copies with one expect_tx
+__device__ __forceinline__ void tma_copy_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                            unsigned long long* bar) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(gmem_src), "r"(bytes), "r"(mb)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (int spin = 0; spin < (1 << 26); spin++) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    if (done) return;
+  }
+  asm volatile("trap;");       // never hang the device on a lost transaction
+}
+
+// Sum over the 32 lanes of each of 16 per-lane values: on return lanes r and r + 16 hold sum_lanes v[r].  Recursive
+// halving -- 16 exchanges instead of the 80 of 16 separate butterflies.
+__device__ __forceinline__ double warp_transpose_sum16(double (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int r = 0; r < h; r++) {
+      const double send = up ? v[r] : v[r + h];
+      const double keep = up ? v[r + h] : v[r];
+      v[r] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+#define SMALL_WARP_DOUBLES(ncap) ((ncap) + 2 * TLBO_HMAX)
+
+// Posterior of surrogate m at one query row by ONE warp (kbuf: SMALL_WARP_DOUBLES(ncap) doubles of warp-private
+// shared memory; xv: lane p < d holds the row's permuted column p, unscaled).  All lanes return the un-standardised
+// mean / variance.  Every global load sits in a batch of independent loads (the kernel is a chain of L2 latencies,
+// not of flops): scalars + scales, then the training rows eight columns at a time, then L^-1 sixteen rows at a time
+// with the lanes across the columns (coalesced) and one transposed reduction per row block.
+__device__ __forceinline__ void predict_small_item(const PredSmallArgs& a, int m, double xv, double* kbuf,
+                                                   double& mu_out, double& var_out) {
+  const int lane = threadIdx.x & 31;
+  const int ncap = a.pack.ncap, d = a.pack.d, dc = a.sp.d_cont, ldl = TLBO_LDL(ncap);
+  const double* Xs = a.pack.d_Xs + (size_t)m * ncap * d;
+  const double* al = a.pack.d_alpha + (size_t)m * ncap;
+  const double* L = a.pack.d_Linv + (size_t)m * ncap * ldl;
+  double* xq = kbuf + ncap;            // [TLBO_HMAX] query row, permuted, continuous columns scaled
+  double* hw = xq + TLBO_HMAX;         // [TLBO_HMAX] 1 / l of the continuous, Hamming weights of the categorical columns
+  const int n = a.pack.d_n[m];
+  const double* hyp = a.pack.d_hyp + (size_t)m * TLBO_HYP_STRIDE;
+  const double c = hyp[0], ymean = hyp[2], ystd = hyp[3], diag = hyp[4];
+  __syncwarp();
+  unsigned qmask = 0u;
+  if (lane < d) {
+    const double sc = hyp[8 + lane];
+    if (a.sp.has_cond && xv <= -1.0) qmask = 1u << lane;
+    xq[lane] = (lane < dc) ? xv * sc : xv;
+    hw[lane] = sc;
+  }
+  if (a.sp.has_cond) qmask = __reduce_or_sync(0xffffffffu, qmask);
+  __syncwarp();
+  double mpart = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    const double* xj = Xs + (size_t)j * d;
+    const double aj = al[j];
+    double s = 0.0, hs = 0.0;
+    unsigned jm = 0u;
+    for (int p0 = 0; p0 < d; p0 += 8) {
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) x[u] = (p0 + u < d) ? xj[p0 + u] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int p = p0 + u;
+        if (p < dc) { const double df = xq[p] - x[u]; s += df * df; }
+        else if (p < d) { if (xq[p] != x[u]) hs += hw[p]; }
+        // activity mask (gp_kernels.py:21-29); a training entry is inactive iff its raw value was <= -1, i.e. its
+        // stored value (continuous columns are pre-multiplied by 1 / l > 0) is <= -(1 / l)
+        if (a.sp.has_cond && p < d) jm |= (x[u] <= ((p < dc) ? -hw[p] : -1.0)) ? (1u << p) : 0u;
+      }
+    }
+    double k = matern_hamming(c, s, hs);
+    if (a.sp.has_cond && jm != qmask) k = 0.0;
+    kbuf[j] = k;
+    mpart += k * aj;
+  }
+  __syncwarp();
+  double qpart = 0.0;
+  for (int rb = 0; rb < n; rb += 16) {
+    double v[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = 0.0;
+    const int jend = (rb + 16 < n) ? rb + 16 : n;        // columns 0 .. jend - 1 reach this row block (lower triangle)
+    for (int j0 = 0; j0 < jend; j0 += 32) {
+      const int j = j0 + lane;
+      const double kj = (j < n) ? kbuf[j] : 0.0;
+      const double* col = L + (size_t)rb * ldl + j;
+      double l[16];
+#pragma unroll
+      for (int r = 0; r < 16; r++) l[r] = (rb + r < n && j <= rb + r) ? col[(size_t)r * ldl] : 0.0;   // one batch
+#pragma unroll
+      for (int r = 0; r < 16; r++) v[r] += l[r] * kj;
+    }
+    const double vi = warp_transpose_sum16(v);           // lanes r, r + 16: (L^-1 k)[rb + r]
+    if (lane < 16) qpart += vi * vi;
+  }
+  const double mean = warp_sum(mpart);
+  const double qq = warp_sum(qpart);
+  double yv = diag - qq;
+  if (yv < 0.0) yv = 0.0;
+  const double sd = sqrt(yv);
+  double var = sd * sd;
+  if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;   // np.clip keeps NaN
+  mu_out = mean * ystd + ymean;
+  var_out = var * (ystd * ystd);
+}
+
 __global__ void __launch_bounds__(256) gp_predict_small_kernel(PredSmallArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ncap = a.pack.ncap, d = a.pack.d, dc = a.sp.d_cont, ldl = TLBO_LDL(ncap);
-  double* kbuf = reinterpret_cast<double*>(smem) + (size_t)wid * (ncap + TLBO_HMAX);
-  double* xq = kbuf + ncap;
+  double* kbuf = reinterpret_cast<double*>(smem) + (size_t)wid * SMALL_WARP_DOUBLES(a.pack.ncap);
   const long long total = (long long)a.Nq * a.pack.M;
   for (long long item = (long long)blockIdx.x * warps + wid; item < total; item += (long long)gridDim.x * warps) {
     const int m = (int)(item / a.Nq), q = (int)(item - (long long)m * a.Nq);
-    const int n = a.pack.d_n[m];
-    const double* hyp = a.pack.d_hyp + (size_t)m * TLBO_HYP_STRIDE;
-    const double* Xs = a.pack.d_Xs + (size_t)m * ncap * d;
-    const double* al = a.pack.d_alpha + (size_t)m * ncap;
-    const double* Li = a.pack.d_Linv + (size_t)m * ncap * ldl;
-    const double c = hyp[0], ymean = hyp[2], ystd = hyp[3], diag = hyp[4];
-    __syncwarp();
-    unsigned qmask = 0u;
-    if (lane < d) {
-      double v = a.Xq[(size_t)q * d + a.sp.perm[lane]];
-      if (a.sp.has_cond && v <= -1.0) qmask = 1u << lane;
-      if (lane < dc) v *= hyp[8 + lane];
-      xq[lane] = v;
-    }
-    if (a.sp.has_cond) qmask = __reduce_or_sync(0xffffffffu, qmask);
-    __syncwarp();
-    double mpart = 0.0;
-    for (int j = lane; j < n; j += 32) {
-      const double* xj = Xs + (size_t)j * d;
-      double s = 0.0, hs = 0.0;
-      for (int p = 0; p < dc; p++) { const double df = xq[p] - xj[p]; s += df * df; }
-      for (int p = dc; p < d; p++) if (xq[p] != xj[p]) hs += hyp[8 + p];
-      double k = matern_hamming(c, s, hs);
-      if (a.sp.has_cond) {
-        // activity mask (gp_kernels.py:21-29); a training entry is inactive iff its raw value was <= -1, i.e. its
-        // stored value (continuous columns are pre-multiplied by 1 / l > 0) is <= -(1 / l)
-        unsigned jm = 0u;
-        for (int p = 0; p < d; p++) jm |= (xj[p] <= ((p < dc) ? -hyp[8 + p] : -1.0)) ? (1u << p) : 0u;
-        if (jm != qmask) k = 0.0;
-      }
-      kbuf[j] = k;
-      mpart += k * al[j];
-    }
-    __syncwarp();
-    double qpart = 0.0;
-    for (int i = lane; i < n; i += 32) {
-      const double* row = Li + (size_t)i * ldl;
-      double v = 0.0;
-      for (int j = 0; j <= i; j++) v += row[j] * kbuf[j];
-      qpart += v * v;
-    }
-    const double mean = warp_sum(mpart);
-    const double qq = warp_sum(qpart);
+    double mu, var;
+    const double xv = (lane < a.pack.d) ? a.Xq[(size_t)q * a.pack.d + a.sp.perm[lane]] : 0.0;
+    predict_small_item(a, m, xv, kbuf, mu, var);
     if (lane == 0) {
-      double yv = diag - qq;
-      if (yv < 0.0) yv = 0.0;
-      const double sd = sqrt(yv);
-      double var = sd * sd;
-      if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;   // np.clip keeps NaN
-      a.mu[(size_t)m * a.Nq + q] = mean * ystd + ymean;
-      a.var[(size_t)m * a.Nq + q] = var * (ystd * ystd);
+      a.mu[(size_t)m * a.Nq + q] = mu;
+      a.var[(size_t)m * a.Nq + q] = var;
     }
   }
 }
@@ -112,7 +204,7 @@ extern "C" int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, co
   if (rc) return rc;
   a.Xq = d_Xq; a.Nq = Nq; a.mu = d_mu; a.var = d_var;
   const int warps = 8;
-  const size_t smem = (size_t)warps * (pack->ncap + TLBO_HMAX) * sizeof(double);
+  const size_t smem = (size_t)warps * SMALL_WARP_DOUBLES(pack->ncap) * sizeof(double);
   if (smem > 200 * 1024) { tlbo_set_error("ncap too large for predict_small"); return TLBO_E_TOOLARGE; }
   if (smem > 48 * 1024)
     TLBO_CUDA_CHECK(cudaFuncSetAttribute(gp_predict_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -120,6 +212,306 @@ extern "C" int tlbo_gp_predict(const tlbo_pack* pack, const int32_t* h_types, co
   int grid = (int)((items + warps - 1) / warps);
   if (grid > 148 * 8) grid = 148 * 8;
   gp_predict_small_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(a);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Ensemble combination and EI of one query row from its per-surrogate posteriors, shared by the fused pool kernel
+// and the small-query kernel below (same operations in the same order: the two must agree bit for bit).
+struct EnsAcc { double mu, var, wsum; };
+
+__device__ __forceinline__ void ens_combine(int mode, bool first, double wm, double mu_m, double var_m, EnsAcc& e) {
+  if (mode == 0) {
+    // rgpe.py:150-152 / base_facade.py:170-171: `mu += w * mu_t`, `var += w * w * var_t` -- numpy rounds the
+    // product and the sum separately (no FMA contraction: nvcc's -fmad would fuse them)
+    e.mu = __dadd_rn(e.mu, __dmul_rn(wm, mu_m));
+    e.var = __dadd_rn(e.var, __dmul_rn(__dmul_rn(wm, wm), var_m));
+  } else if (mode == 2) {
+    const double iv = 1.0 / var_m;
+    e.var = __dadd_rn(e.var, __dmul_rn(iv, wm));
+    e.mu = __dadd_rn(e.mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
+  } else {
+    if (first) { e.mu = mu_m; e.var = var_m; }
+    else { e.mu = __dadd_rn(e.mu, __dmul_rn(wm, mu_m)); e.wsum = __dadd_rn(e.wsum, wm); }
+  }
+}
+
+// Final mean / variance of the ensemble (mode rules, facade variance floor) and EI
+// (acquisition.py:130-177); NaN EI is returned as NaN (the callers apply their own NaN rule).
+__device__ __forceinline__ double ens_ei(int mode, const EnsAcc& e, double eta, double par, double var_floor,
+                                         double& mu_out, double& var_out) {
+  double mu = e.mu, var = e.var;
+  if (mode == 1) mu = mu / (0.75 + e.wsum);
+  if (mode == 2) {
+    // POGPE (pogpe.py:57-60): precision-weighted product of experts
+    double tmp = e.var;
+    if (tmp == 0.0) tmp = 1e-5;
+    var = 1.0 / tmp;
+    mu = __dmul_rn(e.mu, var);
+  }
+  if (var < var_floor) var = var_floor;
+  if (var != var) var = var_floor;
+  const double s = sqrt(var);
+  double f;
+  if (s == 0.0) f = 0.0;
+  else {
+    const double dm = eta - mu - par;
+    const double z = dm / s;
+    const double cdf = 0.5 * erfc(-z * 0.7071067811865476);
+    const double pdf = exp(-0.5 * z * z) * 0.3989422804014327;
+    // two products and one sum, each rounded (numpy semantics, no FMA contraction)
+    f = __dadd_rn(__dmul_rn(dm, cdf), __dmul_rn(s, pdf));
+    // z < -37.5: Phi(z) is subnormal and the two terms (equal to ~1e-3 relative) carry
+    // no relative precision, so the sign of their difference is rounding luck of the
+    // libm in use (glibc happens to stay >= 0); EI there is < 1e-305 * s.
+    if (f < 0.0 && cdf < 2.2250738585072014e-308) f = 0.0;
+  }
+  mu_out = mu; var_out = var;
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------
+// Small-query ensemble EI in ONE launch (the online scenario's hill-climb step: ~30 neighbours x K + 1 surrogates):
+// one CTA per (query row, surrogate) -- ~800 small CTAs, five to a SM, so that the chains of dependent latencies of
+// different posteriors overlap.  The row's posteriors meet in d_mu / d_var; the LAST CTA of a row (ticket counter)
+// loads them side by side, thread 0 combines them in accumulation order, scores EI and stores it.  Xq and ei may be
+// mapped pinned HOST memory (UVA): results are written over the bus, no copy engine involved, and a host that
+// pre-filled ei[] with TLBO_EI_PENDING can spin on the rows instead of synchronising the stream.
+#define SMALL_EI_INLINE_DOUBLES 1024
+
+struct SmallEiArgs {
+  PredSmallArgs p;       // p.mu / p.var: per-surrogate posteriors [M, Nq] (scratch the combination reads)
+  const double* w; const int32_t* skip; const int32_t* order; int mode;
+  double eta, par, var_floor;
+  double* ei;            // [Nq]
+  unsigned* counter;     // [Nq], zero on entry; left zero
+  int nst;               // > 0: surrogates with n <= nst rows have Xs / alpha / L^-1 bulk-copied to shared memory
+  int inlined;           // the query rows travel in `xin` (kernel arguments, constant bank) instead of p.Xq
+  double xin[SMALL_EI_INLINE_DOUBLES];
+};
+
+#define SMALL_EI_WARPS 4
+#define SMALL_EI_THREADS (SMALL_EI_WARPS * 32)
+// doubles of the staging area: L^-1 rows at stride nst (row count rounded up to 16) | Xs | alpha  (nst even)
+#define SMALL_EI_LROWS(nst) (((nst) + 15) & ~15)          /* the matrix-vector product reads whole blocks of 16 rows */
+#define SMALL_EI_STAGE_DOUBLES(nst, d) ((size_t)SMALL_EI_LROWS(nst) * (nst) + (size_t)(nst) * (d) + (nst) + 2)
+
+// CTA (q, m): the posterior of surrogate m at query row q by four warps.
+//   stage   : (n <= nst) the surrogate's training rows, alpha and the first n columns of the first n rows of L^-1 by
+//             bulk copies (TMA; one per row of L^-1, issued by as many threads) -- in flight while the scalars load
+//   K*      : one training row per thread, k_j to shared memory, k_j alpha_j accumulated
+//   L^-1 k  : one block of 16 rows per warp and round, lanes across the columns, no predicates (the pack holds exact
+//             zeros above the diagonal), one transposed reduction per block
+//   finish  : mean / variance to d_mu / d_var; the LAST CTA of a row (ticket counter) loads the row's M posteriors
+//             side by side, thread 0 combines them in accumulation order, scores EI and stores it.
+__global__ void __launch_bounds__(SMALL_EI_THREADS, 6) ensemble_ei_small_kernel(const __grid_constant__ SmallEiArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int M = a.p.pack.M, Nq = a.p.Nq, q = blockIdx.x, m = blockIdx.y;
+  const int ncap = a.p.pack.ncap, d = a.p.pack.d, dc = a.p.sp.d_cont, nst = a.nst;
+  double* kbuf = reinterpret_cast<double*>(smem);          // [ncap] K*
+  double* xq = kbuf + ncap;                                // [TLBO_HMAX] query row, permuted, continuous columns scaled
+  double* hw = xq + TLBO_HMAX;                             // [TLBO_HMAX] 1 / l | Hamming weights
+  double* sL = hw + TLBO_HMAX;                             // staging area
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ double s_red[2 * SMALL_EI_WARPS];
+  __shared__ unsigned s_ticket;
+  const int n = a.p.pack.d_n[m];
+  const double* hyp = a.p.pack.d_hyp + (size_t)m * TLBO_HYP_STRIDE;
+  const double* Xs = a.p.pack.d_Xs + (size_t)m * ncap * d;
+  const double* al = a.p.pack.d_alpha + (size_t)m * ncap;
+  const double* L = a.p.pack.d_Linv + (size_t)m * ncap * TLBO_LDL(ncap);
+  int ldl = TLBO_LDL(ncap);
+  const bool staged = n > 0 && n <= nst;                   // uniform
+  if (n > 0) {
+    if (staged) {
+      double* sX = sL + (size_t)SMALL_EI_LROWS(nst) * nst;
+      double* sA = sX + (((size_t)nst * d + 1) & ~(size_t)1);
+      const int ne = (n + 1) & ~1;
+      const unsigned bx = (unsigned)((((size_t)n * d + 1) & ~(size_t)1) * sizeof(double));
+      const unsigned ba = (unsigned)(ne * sizeof(double)), br = (unsigned)(ne * sizeof(double));
+      if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned mb0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
+        const unsigned mb1 = (unsigned)__cvta_generic_to_shared(&s_bar[1]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb0), "r"(bx + ba) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb1), "r"(br * (unsigned)n) : "memory");
+        tma_copy_1d(sX, Xs, bx, &s_bar[0]);
+        tma_copy_1d(sA, al, ba, &s_bar[0]);
+      }
+      __syncthreads();                                     // barriers initialised and armed before any row copy
+      for (int i = tid; i < n; i += SMALL_EI_THREADS) tma_copy_1d(sL + (size_t)i * nst, L + (size_t)i * ldl, br, &s_bar[1]);
+      Xs = sX; al = sA; L = sL; ldl = nst;
+    }
+    const double c = hyp[0];
+    unsigned qm = 0u;
+    if (tid < d) {
+      const double xv = a.inlined ? a.xin[q * d + a.p.sp.perm[tid]] : a.p.Xq[(size_t)q * d + a.p.sp.perm[tid]];
+      const double sc = hyp[8 + tid];
+      if (a.p.sp.has_cond && xv <= -1.0) qm = 1u << tid;
+      xq[tid] = (tid < dc) ? xv * sc : xv;
+      hw[tid] = sc;
+    }
+    unsigned qmask = 0u;
+    if (a.p.sp.has_cond) {                                 // d <= TLBO_HMAX < 32: the pattern bits live in warp 0
+      qm = __reduce_or_sync(0xffffffffu, qm);
+      if (tid == 0) s_ticket = qm;
+    }
+    __syncthreads();
+    if (a.p.sp.has_cond) qmask = s_ticket;
+    if (staged) mbar_wait(&s_bar[0], 0);
+    double mpart = 0.0;
+    for (int j = tid; j < n; j += SMALL_EI_THREADS) {
+      const double* xj = Xs + (size_t)j * d;
+      double s = 0.0, hs = 0.0;
+      unsigned jm = 0u;
+      for (int p0 = 0; p0 < d; p0 += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) x[u] = (p0 + u < d) ? xj[p0 + u] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int p = p0 + u;
+          if (p < dc) { const double df = xq[p] - x[u]; s += df * df; }
+          else if (p < d) { if (xq[p] != x[u]) hs += hw[p]; }
+          // activity mask (gp_kernels.py:21-29), as in predict_small_item
+          if (a.p.sp.has_cond && p < d) jm |= (x[u] <= ((p < dc) ? -hw[p] : -1.0)) ? (1u << p) : 0u;
+        }
+      }
+      double k = matern_hamming(c, s, hs);
+      if (a.p.sp.has_cond && jm != qmask) k = 0.0;
+      kbuf[j] = k;
+      mpart += k * al[j];
+    }
+    __syncthreads();
+    if (staged) mbar_wait(&s_bar[1], 0);
+    double qpart = 0.0;
+    for (int rb = 16 * wid; rb < n; rb += 16 * SMALL_EI_WARPS) {
+      double v[16];
+#pragma unroll
+      for (int r = 0; r < 16; r++) v[r] = 0.0;
+      const int jend = (rb + 16 < n) ? rb + 16 : n;        // columns 0 .. jend - 1 reach this row block
+      for (int j0 = 0; j0 < jend; j0 += 32) {
+        const int j = j0 + lane;
+        const bool jok = j < n;
+        const double kj = jok ? kbuf[j] : 0.0;
+        const double* col = L + (size_t)rb * ldl + (jok ? j : 0);
+        // rows >= n of the staging area are never written: their sums are dropped below, never mixed in
+#pragma unroll
+        for (int r0 = 0; r0 < 16; r0 += 8) {               // eight loads in flight (six CTAs per SM: 80 registers)
+          double l[8];
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+            l[r] = (staged || rb + r0 + r < n) ? col[(size_t)(r0 + r) * ldl] : 0.0;
+#pragma unroll
+          for (int r = 0; r < 8; r++) v[r0 + r] += l[r] * kj;
+        }
+      }
+      const double vi = warp_transpose_sum16(v);           // lanes r, r + 16: (L^-1 k)[rb + r]
+      if (lane < 16 && rb + lane < n) qpart += vi * vi;
+    }
+    mpart = warp_sum(mpart);
+    qpart = warp_sum(qpart);
+    if (lane == 0) { s_red[wid] = mpart; s_red[SMALL_EI_WARPS + wid] = qpart; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mu = 0.0, var = 0.0;
+    if (n > 0) {
+      double mean = 0.0, qq = 0.0;
+#pragma unroll
+      for (int w = 0; w < SMALL_EI_WARPS; w++) { mean += s_red[w]; qq += s_red[SMALL_EI_WARPS + w]; }
+      const double ymean = hyp[2], ystd = hyp[3], diag = hyp[4];
+      double yv = diag - qq;
+      if (yv < 0.0) yv = 0.0;
+      const double sd = sqrt(yv);
+      var = sd * sd;
+      if (!(var >= VERY_SMALL_NUMBER)) var = (var != var) ? var : VERY_SMALL_NUMBER;   // np.clip keeps NaN
+      mu = mean * ystd + ymean;
+      var = var * (ystd * ystd);
+    }
+    a.p.mu[(size_t)m * Nq + q] = mu;
+    a.p.var[(size_t)m * Nq + q] = var;
+    __threadfence();
+    s_ticket = atomicAdd(a.counter + q, 1u);
+  }
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  // ---- last CTA of row q: every surrogate's posterior is in d_mu / d_var
+  __threadfence();
+  double* s_mu = reinterpret_cast<double*>(smem);           // reuse of the buffers above: [M] x 3 + int[M]
+  double* s_var = s_mu + M;
+  double* s_w = s_var + M;
+  int* s_m = reinterpret_cast<int*>(s_w + M);               // slot of accumulation position mi, -1: dropped
+  for (int mi = tid; mi < M; mi += blockDim.x) {
+    const int mm = a.order ? a.order[mi] : mi;
+    const bool keep = !(a.skip && a.skip[mm]) && a.p.pack.d_n[mm] > 0;
+    s_m[mi] = keep ? mm : -1;
+    s_w[mi] = a.w[mm];
+    s_mu[mi] = __ldcg(a.p.mu + (size_t)mm * Nq + q);
+    s_var[mi] = __ldcg(a.p.var + (size_t)mm * Nq + q);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    EnsAcc e; e.mu = 0.0; e.var = 0.0; e.wsum = 0.0;
+    for (int mi = 0; mi < M; mi++)
+      if (s_m[mi] >= 0) ens_combine(a.mode, mi == 0, s_w[mi], s_mu[mi], s_var[mi], e);
+    double mu, var;
+    // one 8-byte store per row, no fence: a host that pre-filled ei[] with TLBO_EI_PENDING sees each row complete
+    // the moment its value lands (system-wide fences cost ~3 us each on this path)
+    a.ei[q] = ens_ei(a.mode, e, a.eta, a.par, a.var_floor, mu, var);
+    a.counter[q] = 0u;
+  }
+}
+
+extern "C" int tlbo_ensemble_ei_small(const tlbo_pack* pack, const int32_t* h_types, const double* d_w,
+                                      const int32_t* d_skip, const int32_t* d_order, int mode, const double* Xq,
+                                      const double* h_Xq, int Nq, double eta, double par, double var_floor,
+                                      double* d_mu, double* d_var, double* ei, uint32_t* d_counter, void* stream) {
+  if (!pack || !d_w || (!Xq && !h_Xq) || Nq <= 0 || !d_mu || !d_var || !ei || !d_counter) {
+    tlbo_set_error("tlbo_ensemble_ei_small: bad arguments");
+    return TLBO_E_BADARG;
+  }
+  static SmallEiArgs a;                    // 8 KB of inline rows: not on the stack (the entry is not re-entrant)
+  a.p.pack = *pack;
+  int rc = tlbo_make_space(pack->d, h_types, &a.p.sp);
+  if (rc) return rc;
+  a.p.Xq = Xq; a.p.Nq = Nq; a.p.mu = d_mu; a.p.var = d_var;
+  a.w = d_w; a.skip = d_skip; a.order = d_order; a.mode = mode;
+  a.eta = eta; a.par = par; a.var_floor = var_floor;
+  a.ei = ei; a.counter = d_counter;
+  const int M = pack->M, d = pack->d;
+  a.inlined = (h_Xq && (long long)Nq * d <= SMALL_EI_INLINE_DOUBLES) ? 1 : 0;
+  if (a.inlined) memcpy(a.xin, h_Xq, sizeof(double) * (size_t)Nq * d);
+  else if (!Xq) { tlbo_set_error("tlbo_ensemble_ei_small: query set too large to inline and no device-readable Xq"); return TLBO_E_BADARG; }
+  // K* / query buffers + (when four CTAs still fit on an SM) the staging area for surrogates of up to nst rows --
+  // nst from the pack's nmax hint (0 = unknown: the capacity)
+  const size_t small = sizeof(double) * (size_t)SMALL_WARP_DOUBLES(pack->ncap);
+  int nst = (pack->nmax > 0 && pack->nmax < pack->ncap) ? pack->nmax : pack->ncap;
+  nst = (nst + 1) & ~1;
+  const size_t stage = sizeof(double) * SMALL_EI_STAGE_DOUBLES(nst, d);
+  a.nst = (small + stage <= 52 * 1024) ? nst : 0;
+  size_t smem = small + (a.nst ? stage : 0);
+  const size_t tail = sizeof(double) * 3 * (size_t)M + sizeof(int) * (size_t)M;
+  if (tail > smem) smem = tail;
+  if (smem > 200 * 1024 || M > 65535) { tlbo_set_error("ncap / M too large for ensemble_ei_small"); return TLBO_E_TOOLARGE; }
+  static size_t smem_set = 0;
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // ~800 CTAs of ~30 KB each must all be resident (six to a SM): ask for the largest shared-memory carve-out
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(ensemble_ei_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TLBO_CUDA_CHECK(cudaFuncSetAttribute(ensemble_ei_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid((unsigned)Nq, (unsigned)M);
+  ensemble_ei_small_kernel<<<grid, SMALL_EI_THREADS, smem, (cudaStream_t)stream>>>(a);
   TLBO_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -151,33 +543,6 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
-}
-
-// ---- TMA (bulk async copy) staging of the candidate tile -------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
-                                            unsigned long long* bar) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const unsigned mb = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(gmem_src), "r"(bytes), "r"(mb)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done = 0;
-  for (int spin = 0; spin < (1 << 26); spin++) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done)
-                 : "r"(addr), "r"(parity)
-                 : "memory");
-    if (done) return;
-  }
-  asm volatile("trap;");       // never hang the device on a lost transaction
 }
 
 struct FusedArgs {
@@ -394,23 +759,11 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
       }
     }
     // per-lane ensemble accumulators: lane cl < WC owns candidate cl of this warp
-    double acc_mu = 0.0, acc_var = 0.0, wsum = 0.0;
+    EnsAcc acc; acc.mu = 0.0; acc.var = 0.0; acc.wsum = 0.0;
     const long long myrow = row0 + wid * WC + lane;
     const bool myok = lane < WC && myrow < a.N;
     auto combine = [&](bool first, double wm, double mu_m, double var_m) {
-      if (a.mode == 0) {
-        // rgpe.py:150-152 / base_facade.py:170-171: `mu += w * mu_t`, `var += w * w * var_t` -- numpy rounds the
-        // product and the sum separately (no FMA contraction: nvcc's -fmad would fuse them)
-        acc_mu = __dadd_rn(acc_mu, __dmul_rn(wm, mu_m));
-        acc_var = __dadd_rn(acc_var, __dmul_rn(__dmul_rn(wm, wm), var_m));
-      } else if (a.mode == 2) {
-        const double iv = 1.0 / var_m;
-        acc_var = __dadd_rn(acc_var, __dmul_rn(iv, wm));
-        acc_mu = __dadd_rn(acc_mu, __dmul_rn(__dmul_rn(iv, mu_m), wm));
-      } else {
-        if (first) { acc_mu = mu_m; acc_var = var_m; }
-        else { acc_mu = __dadd_rn(acc_mu, __dmul_rn(wm, mu_m)); wsum = __dadd_rn(wsum, wm); }
-      }
+      ens_combine(a.mode, first, wm, mu_m, var_m, acc);
     };
     int li = 0;
     while (li < L) {
@@ -612,32 +965,8 @@ __global__ void __launch_bounds__(PRED_THREADS, MINB) predict_ei_fused_kernel(Fu
     if (lane < WC) {
       const long long row = row0 + wid * WC + lane;
       if (row < a.N) {
-        double mu = acc_mu, var = acc_var;
-        if (a.mode == 1) mu = mu / (0.75 + wsum);
-        if (a.mode == 2) {
-          // POGPE (pogpe.py:57-60): precision-weighted product of experts
-          double tmp = acc_var;
-          if (tmp == 0.0) tmp = 1e-5;
-          var = 1.0 / tmp;
-          mu = __dmul_rn(acc_mu, var);
-        }
-        if (var < a.var_floor) var = a.var_floor;
-        if (var != var) var = a.var_floor;
-        const double s = sqrt(var);
-        double f;
-        if (s == 0.0) f = 0.0;
-        else {
-          const double dm = a.eta - mu - a.par;
-          const double z = dm / s;
-          const double cdf = 0.5 * erfc(-z * 0.7071067811865476);
-          const double pdf = exp(-0.5 * z * z) * 0.3989422804014327;
-          // two products and one sum, each rounded (numpy semantics, no FMA contraction)
-          f = __dadd_rn(__dmul_rn(dm, cdf), __dmul_rn(s, pdf));
-          // z < -37.5: Phi(z) is subnormal and the two terms (equal to ~1e-3 relative) carry
-          // no relative precision, so the sign of their difference is rounding luck of the
-          // libm in use (glibc happens to stay >= 0); EI there is < 1e-305 * s.
-          if (f < 0.0 && cdf < 2.2250738585072014e-308) f = 0.0;
-        }
+        double mu, var;
+        double f = ens_ei(a.mode, acc, a.eta, a.par, a.var_floor, mu, var);
         if (f < 0.0) negcount += 1.0;
         if (f != f) f = -DBL_MAX;
         if (a.mu) a.mu[row] = mu;

@@ -11,6 +11,7 @@
 // step; here it is a few microseconds.  tests/test_online_search_cpu.py checks it draw for draw
 // against the Python statement of the same algorithm (tlbo_b200/config_space).
 #include <float.h>
+#include <string.h>
 #include <math.h>
 #include <stdint.h>
 #include "tlbo_common.cuh"
@@ -275,33 +276,59 @@ extern "C" int tlbo_host_prepare_jobs(const double* h_X, double* h_y_inout, int 
   return 0;
 }
 
+// Completion of a small-query launch: the kernel overwrites every EI row (pre-filled with TLBO_EI_PENDING) with one
+// 8-byte store into mapped pinned memory.  Spinning on the rows costs ~1 us after the last store lands;
+// cudaStreamSynchronize adds a driver round trip to every hill-climb step.  The stream is queried now and then so
+// that a failed launch surfaces as its CUDA error instead of a hang.
+static inline bool ei_pending(const volatile double* p) {
+  uint64_t bits;
+  const double v = *p;
+  memcpy(&bits, &v, sizeof(bits));
+  return bits == TLBO_EI_PENDING_BITS;
+}
+
+static int wait_for_rows(const double* h_ei, int rows, cudaStream_t s) {
+  int j = 0;
+  for (unsigned spin = 1;; spin++) {
+    while (j < rows && !ei_pending(h_ei + j)) j++;
+    if (j == rows) return 0;
+    if ((spin & 0x3ff) == 0) {
+      cudaError_t e = cudaStreamQuery(s);
+      if (e == cudaSuccess) {
+        while (j < rows && !ei_pending(h_ei + j)) j++;
+        if (j == rows) return 0;
+        tlbo_set_error("small-query launch finished without reporting every row");
+        return TLBO_E_BADARG;
+      }
+      if (e != cudaErrorNotReady) { tlbo_set_error(cudaGetErrorString(e)); return (int)e; }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One hill-climb of the online scenario's local search (reference tlbo/optimizer/ei_optimization.py:239-294,
 // LocalSearch._one_iter) driven from native code: per step the one-exchange neighbourhood of the incumbent
-// (generator seed = the next pre-drawn rng.randint(0, 10000)), ONE acquisition evaluation of the whole
-// neighbourhood -- the same two launches the Python path makes: tlbo_gp_predict for every (row, surrogate)
-// posterior, tlbo_predict_ei_fused_cached in all-resident mode for combine + EI -- one stream synchronisation,
-// and the reference's accept rule (first neighbour with EI > incumbent, NaN -> -DBL_MAX as
+// (generator seed = the next pre-drawn rng.randint(0, 10000)), ONE launch scoring the whole neighbourhood
+// (tlbo_ensemble_ei_small: every (row, surrogate) posterior, ensemble, EI), a spin on the EI rows as they land in
+// mapped memory, and the reference's accept rule (first neighbour with EI > incumbent, NaN -> -DBL_MAX as
 // AbstractAcquisitionFunction.__call__ does).  A climb is ~25 such steps; in the interpreter a step costs ~50 us
-// of Python on top of the launches.  Buffers (all caller-owned): h_X pinned [cap, d] staging, d_X [cap, d],
-// d_mu / d_var [M * cap], d_mu_rows / d_var_rows [cap], h_ei mapped pinned [cap] (the fused kernel stores EI
-// straight into it), h_best mapped pinned [4].
+// of Python on top of the launches.  Buffers (all caller-owned): h_X [cap, d] host staging for the neighbourhood (it
+// travels inside the kernel arguments), h_ei [cap] MAPPED pinned host memory (the kernel stores EI over the bus),
+// d_mu / d_var [M * cap] device scratch, d_counter cap zeroed device uint32 (left zero).  Not re-entrant.
 // Returns 0 when the climb ended (no improving neighbour or max_steps), 1 when the pre-drawn seeds ran out
 // (call again with more seeds: the incumbent / counters are up to date), < 0 / CUDA codes on error.
-extern "C" int tlbo_local_search_climb(const tlbo_pack* view, const tlbo_pack* logical, const int32_t* h_types,
-                                       const uint8_t* h_const_mask, const double* d_w, const int32_t* d_skip,
-                                       const int32_t* d_order, int mode, double eta, double par, double var_floor,
-                                       int num_neighbors, double stdev, const uint32_t* h_seeds, int n_seeds,
-                                       int max_steps, double* h_config, double* h_acq, double* h_X, double* d_X,
-                                       double* d_mu, double* d_var, double* d_mu_rows, double* d_var_rows,
-                                       double* h_ei, double* h_best, void* d_work, int cap, int32_t* h_counters,
-                                       void* stream) {
-  if (!view || !logical || !h_types || !h_seeds || !h_config || !h_acq || !h_X || !d_X || !d_mu || !d_var ||
-      !h_ei || !h_best || !d_work || !h_counters || cap <= 0) {
+extern "C" int tlbo_local_search_climb(const tlbo_pack* view, const int32_t* h_types, const uint8_t* h_const_mask,
+                                       const double* d_w, const int32_t* d_skip, const int32_t* d_order, int mode,
+                                       double eta, double par, double var_floor, int num_neighbors, double stdev,
+                                       const uint32_t* h_seeds, int n_seeds, int max_steps, double* h_config,
+                                       double* h_acq, double* h_X, double* d_mu, double* d_var, double* h_ei,
+                                       uint32_t* d_counter, int cap, int32_t* h_counters, void* stream) {
+  if (!view || !h_types || !h_seeds || !h_config || !h_acq || !h_X || !d_mu || !d_var || !h_ei ||
+      !d_counter || !h_counters || cap <= 0) {
     tlbo_set_error("tlbo_local_search_climb: bad arguments");
     return TLBO_E_BADARG;
   }
-  const int d = view->d, M = view->M;
+  const int d = view->d;
   cudaStream_t s = (cudaStream_t)stream;
   // h_counters: [0] seeds consumed (= hill-climb steps), [1] neighbours the lazy reference loop inspects,
   //             [2] acquisition evaluations, [3] rows with EI < 0 (the caller raises), [4] steps of THIS climb so far
@@ -318,27 +345,32 @@ extern "C" int tlbo_local_search_climb(const tlbo_pack* view, const tlbo_pack* l
     if (rows > 0) {
       for (long i = 0; i < (long)rows * d; i++)
         if (!isfinite(h_X[i])) h_X[i] = -1.0;               // EI._to_device / GaussianProcess._impute_inactive
-      TLBO_CUDA_CHECK(cudaMemcpyAsync(d_X, h_X, sizeof(double) * (size_t)rows * d, cudaMemcpyHostToDevice, s));
-      rc = tlbo_gp_predict(view, h_types, d_X, rows, d_mu, d_var, stream);
+      // one launch: every (neighbour, surrogate) posterior, the ensemble and EI; the rows go up inside the kernel
+      // arguments, EI comes back through mapped pinned host memory (no copy-engine hop, no synchronisation call)
+      {
+        double pending;
+        const uint64_t bits = TLBO_EI_PENDING_BITS;
+        memcpy(&pending, &bits, sizeof(pending));
+        for (int j = 0; j < rows; j++) h_ei[j] = pending;
+      }
+      rc = tlbo_ensemble_ei_small(view, h_types, d_w, d_skip, d_order, mode, h_X, h_X, rows, eta, par, var_floor, d_mu,
+                                  d_var, h_ei, d_counter, stream);
       if (rc) return rc;
-      rc = tlbo_predict_ei_fused_cached(logical, h_types, d_w, d_skip, d_order, mode, d_X, rows, eta, par, var_floor,
-                                        nullptr, nullptr, 0, 0, h_best, d_mu_rows, d_var_rows, h_ei, d_mu, d_var, M,
-                                        d_work, stream);
+      rc = wait_for_rows(h_ei, rows, s);
       if (rc) return rc;
-      TLBO_CUDA_CHECK(cudaStreamSynchronize(s));
       h_counters[2] += 1;
-      if (h_best[3] > 0.0) { h_counters[3] += (int32_t)h_best[3]; h_counters[0] += used; return 0; }
-      int first = -1;
+      int first = -1, negative = 0;
+      for (int j = 0; j < rows; j++) negative += (h_ei[j] < 0.0) ? 1 : 0;             // EI._compute raises on these
+      if (negative) { h_counters[3] += negative; h_counters[0] += used; return 0; }
       for (int j = 0; j < rows; j++) {
         double a = h_ei[j];
-        if (a != a) a = -DBL_MAX;
+        if (a != a) a = -DBL_MAX;                                                      // acquisition.py:72-76
         if (a > *h_acq) { first = j; break; }
       }
       h_counters[1] += (first >= 0) ? first + 1 : rows;
       if (first >= 0) {
         for (int p = 0; p < d; p++) h_config[p] = h_X[(size_t)first * d + p];
-        double a = h_ei[first];
-        *h_acq = (a != a) ? -DBL_MAX : a;
+        *h_acq = h_ei[first];
         changed = true;
       }
     }

@@ -59,9 +59,10 @@ SYMBOLS = {
     'tlbo_gp_mcmc_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int]),
     'tlbo_mcmc_marginalize': (c_int, [_P, _P, c_int, c_int, c_int64, _P, _P, _P]),
     'tlbo_one_exchange_neighbourhood': (c_int, [_P, c_int, _P, _P, ctypes.c_uint32, c_int, c_double, _P, c_int, _P]),
-    'tlbo_local_search_climb': (c_int, [POINTER(TlboPack), POINTER(TlboPack), _P, _P, _P, _P, _P, c_int, c_double,
-                                        c_double, c_double, c_int, c_double, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
-                                        _P, _P, _P, _P, _P, c_int, _P, _P]),
+    'tlbo_local_search_climb': (c_int, [POINTER(TlboPack), _P, _P, _P, _P, _P, c_int, c_double, c_double, c_double,
+                                        c_int, c_double, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
+    'tlbo_ensemble_ei_small': (c_int, [POINTER(TlboPack), _P, _P, _P, _P, c_int, _P, _P, c_int, c_double, c_double,
+                                       c_double, _P, _P, _P, _P, _P]),
     'tlbo_pair_penalty_loss_normal': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     'tlbo_mt19937_random_sample': (c_int, [_P, c_int64, _P, _P]),
     'tlbo_mt19937_jump': (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),

@@ -60,6 +60,12 @@ class TableSpace(object):
                 X[:, j] = self._rng.uniform(0.0, 1.0, size=int(size))
         return X
 
+    def sample_batch(self, size):
+        """The same draws as ``sample_configuration(size)`` (size > 1) without building ``size`` objects: a
+        ``ConfigurationBatch`` over the sampled array (the online random search scores ~5000 configurations per
+        iteration and looks at one of them)."""
+        return ConfigurationBatch(self, self.sample_array(size))
+
     def sample_configuration(self, size=1):
         """``ConfigurationSpace.sample_configuration``: one Configuration for ``size == 1``, a
         list otherwise."""
@@ -112,6 +118,32 @@ class Configuration(object):
         return 'Configuration(index=%d, %s)' % (self.index, np.array2string(self.array, precision=4))
 
 
+class ConfigurationBatch(object):
+    """A read-only list of Configurations held as the rows of one array; elements are materialised on access
+    (``batch[i]``, iteration), slices and index arrays give sub-batches.  ``convert_configurations_to_array`` returns
+    the array itself."""
+    __slots__ = ('space', 'array', 'origin')
+
+    def __init__(self, space, array, origin=None):
+        self.space = space
+        self.array = np.ascontiguousarray(array, dtype=np.float64)
+        self.origin = origin
+
+    def __len__(self):
+        return self.array.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            c = Configuration(self.space, self.array[i], -1)
+            c.origin = self.origin
+            return c
+        return ConfigurationBatch(self.space, self.array[i], self.origin)
+
+    def __iter__(self):
+        for i in range(self.array.shape[0]):
+            yield self[i]
+
+
 def get_types(config_space, instance_features=None):
     """``get_types`` (reference tlbo/model/util_funcs.py:14-55) for a TableSpace or a bare
     types vector."""
@@ -130,6 +162,8 @@ def convert_configurations_to_array(configs):
     """reference tlbo/config_space/util.py:11-30: stack ``get_array()`` rows (float64)."""
     if isinstance(configs, np.ndarray):
         return np.asarray(configs, dtype=np.float64)
+    if isinstance(configs, ConfigurationBatch):
+        return configs.array
     if len(configs) == 0:
         return np.zeros((0, 0), dtype=np.float64)
     X = np.array([c.get_array() for c in configs], dtype=np.float64)

@@ -286,8 +286,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
                                         mode=self._fused_mode, order=dorder, want_rows=want_rows, ws=ws, sync=sync,
                                         nmax=8, cache=(cmu, cvar))
         view = ops.pack_view(self._pack, 0, self.K + 1)
-        nmax = max([self.num_src_hpo_trial if self.K else 0, getattr(self.target_surrogate, 'n_train_', 0)] +
-                   [m.n_train_ for m in (self.source_surrogates or [])])
+        nmax = self._nmax()
         from tlbo_b200.model import gp_large
         if nmax > gp_large.LARGE_N:
             # a surrogate beyond the fused kernel's shared-memory plan (SCoT's stacked GP): its pool posterior by
@@ -303,6 +302,11 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         return ops.predict_ei_fused(view, self.types, dw, dskip, X_dev, eta, par=par, var_floor=var_floor,
                                     keys=keys, excluded=excluded, idx_offset=idx_offset, mode=self._fused_mode,
                                     order=dorder, want_rows=want_rows, ws=ws, sync=sync, nmax=nmax, cache=cache)
+
+    def _nmax(self):
+        """Largest training-set size among the surrogates in use (the kernels' shared-memory plans are sized by it)."""
+        return max([self.num_src_hpo_trial if self.K else 0, getattr(self.target_surrogate, 'n_train_', 0)] +
+                   [m.n_train_ for m in (self.source_surrogates or [])])
 
     def acq_small(self, X, eta, par, var_floor):
         """EI of a small host query set ``X [N, d]`` (N <= SMALL_QUERY_ROWS) through mapped pinned
@@ -331,23 +335,22 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
             ens = self._ens_cache = (self._pack, dw, dskip, dorder, ops.pack_view(self._pack, 0, self.K + 1))
         _, dw, dskip, dorder, view = ens
-        Xq = sq.Xd[:N]
-        Xq.copy_(sq.X[:N], non_blocking=True)
-        mu, var = ops.gp_predict(view, self.types, Xq, out=(sq.mu, sq.var))
-        ops.predict_ei_fused(self._logical(), self.types, dw, dskip, Xq, eta, par=par, var_floor=var_floor,
-                             mode=self._fused_mode, order=dorder, ws=sq.ws, sync=False, nmax=8, cache=(mu, var),
-                             rows=(sq.mu_rows, sq.var_rows, sq.ei))
+        view.c.nmax = self._nmax()
+        ops.ensemble_ei_small(view, self.types, dw, dskip, dorder, self._fused_mode, sq, N, eta, par, var_floor)
         ops.stream_synchronize()
         ops.STATS.h2d += N * len(self.types) * 8
         ops.STATS.d2h += N * 8 + 32
-        return sq.ei_np[:N].copy(), int(sq.best_np[3])
+        ei = sq.ei_np[:N].copy()
+        n_neg = int(np.count_nonzero(ei < 0.0))
+        ei[np.isnan(ei)] = -np.finfo(np.float64).max              # acquisition.py:72-76
+        return ei, n_neg
 
     def climb(self, x0, acq0, rng, eta, par, var_floor, max_steps, const_mask, num_neighbors, stdev, stats):
         """One hill-climb of the online local search (ei_optimization.py:239-294) through the native driver
-        ``tlbo_local_search_climb``: same launches, same accept rule, same stream consumption as the per-step
-        Python loop (``rng.randint(0, 10000)`` per step: a block of seeds is drawn ahead and the generator is
-        rewound to exactly the number the climb consumed).  Returns ``(x, acq)`` or None when this facade has no
-        native path (walker groups, spaces with conditions, large-n surrogates)."""
+        ``tlbo_local_search_climb``: same values, same accept rule, same stream consumption as the per-step Python
+        loop, one launch per step (``rng.randint(0, 10000)`` per step: a block of seeds is drawn ahead and the
+        generator is rewound to exactly the number the climb consumed).  Returns ``(x, acq)`` or None when this
+        facade has no native path (walker groups, spaces with conditions, large-n surrogates)."""
         import ctypes
         from tlbo_b200 import ops
         from tlbo_b200._cabi import check, lib, ptr
@@ -369,9 +372,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
             ens = self._ens_cache = (self._pack, dw, dskip, dorder, ops.pack_view(self._pack, 0, self.K + 1))
         _, dw, dskip, dorder, view = ens
-        logical = self._logical()
-        logical.c.nmax = 8
-        view.c.nmax = 0
+        view.c.nmax = self._nmax()
         t = ops._types_arr(self.types)
         cm = np.ascontiguousarray(const_mask, dtype=np.uint8)
         x = np.array(x0, dtype=np.float64)
@@ -382,13 +383,12 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             state = rng.get_state()
             seeds = rng.randint(0, 10000, size=64).astype(np.uint32)
             before = int(counters[0])
-            rc = lib.tlbo_local_search_climb(view.ref(), logical.ref(), ptr(t), ptr(cm), ptr(dw), ptr(dskip), ptr(dorder),
+            rc = lib.tlbo_local_search_climb(view.ref(), ptr(t), ptr(cm), ptr(dw), ptr(dskip), ptr(dorder),
                                              int(self._fused_mode), float(eta), float(par), float(var_floor),
                                              int(num_neighbors), float(stdev), ptr(seeds), 64,
                                              -1 if max_steps is None else int(max_steps), ptr(x), ctypes.byref(acq),
-                                             ptr(sq.X), ptr(sq.Xd), ptr(sq.mu), ptr(sq.var), ptr(sq.mu_rows),
-                                             ptr(sq.var_rows), ptr(sq.ei), ptr(sq.ws.best), ptr(sq.ws.work), sq.cap,
-                                             ptr(counters), stream)
+                                             ptr(sq.X), ptr(sq.mu), ptr(sq.var), ptr(sq.ei), ptr(sq.counter),
+                                             sq.cap, ptr(counters), stream)
             used = int(counters[0]) - before
             rng.set_state(state)                    # rewind to exactly the draws the climb consumed
             if used:
@@ -400,8 +400,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         stats['steps'] += int(counters[0])
         stats['neighbours'] += int(counters[1])
         stats['launches'] += int(counters[2])
-        ops.STATS.launches['gp_predict_small'] = ops.STATS.launches.get('gp_predict_small', 0) + int(counters[2])
-        ops.STATS.launches['predict_ei_fused'] = ops.STATS.launches.get('predict_ei_fused', 0) + 2 * int(counters[2])
+        ops.STATS.launches['ensemble_ei_small'] = ops.STATS.launches.get('ensemble_ei_small', 0) + int(counters[2])
         if counters[3] > 0:
             raise ValueError("Expected Improvement is smaller than 0 for at least one sample.")
         # ConfigSpace's lazy generator: one np.random.random() from the GLOBAL stream per inspected neighbour

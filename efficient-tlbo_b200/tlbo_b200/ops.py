@@ -453,9 +453,9 @@ class FusedWorkspace(object):
 
 class SmallQuery(object):
     """Buffers of the low-overhead acquisition call on a small ad-hoc query set (the online
-    scenario's neighbourhoods): the rows go up with one asynchronous copy from a pinned staging
-    buffer and EI comes back through mapped pinned host memory (UVA stores), so one call is two
-    launches and ONE stream synchronisation -- no blocking memcpy, no allocation."""
+    scenario's neighbourhoods): the kernel reads the rows from a mapped pinned staging buffer and EI comes
+    back through mapped pinned host memory (UVA loads / stores), so one call is ONE launch and one stream
+    synchronisation (or a spin on the EI rows) -- no memcpy, no allocation."""
 
     def __init__(self, cap, d, M):
         dev = _dev()
@@ -471,6 +471,17 @@ class SmallQuery(object):
         self.var = torch.zeros(M * self.cap, dtype=F64, device=dev)
         self.ws = FusedWorkspace(pinned_best=True)
         self.best_np = self.ws.best.numpy()
+        self.counter = torch.zeros(self.cap, dtype=torch.int32, device=dev)       # tlbo_ensemble_ei_small's tickets
+
+
+def ensemble_ei_small(view, types, w, skip, order, mode, sq, N, eta, par, var_floor):
+    """``tlbo_ensemble_ei_small`` over the first ``N`` rows of ``sq.X`` (pinned host staging; small sets travel
+    inside the kernel arguments): ONE launch, EI (NaN kept) in ``sq.ei_np[:N]`` once the stream is synchronised."""
+    t = _types_arr(types)
+    with _call('ensemble_ei_small', 1):
+        check(lib.tlbo_ensemble_ei_small(view.ref(), ptr(t), ptr(w), ptr(skip), ptr(order), int(mode), ptr(sq.X), ptr(sq.X),
+                                         int(N), float(eta), float(par), float(var_floor), ptr(sq.mu), ptr(sq.var),
+                                         ptr(sq.ei), ptr(sq.counter), _stream()))
 
 
 def predict_ei_fused(pack, types, w, skip, cand, eta, par=0.0, var_floor=1e-10, keys=None, excluded=None,

@@ -23,10 +23,60 @@ import logging
 
 import numpy as np
 
-from tlbo_b200.config_space import (NEIGHBOUR_STDEV, NUM_NEIGHBORS, Configuration, convert_configurations_to_array,
-                                    one_exchange_neighbourhood_arrays)
+from tlbo_b200.config_space import (NEIGHBOUR_STDEV, NUM_NEIGHBORS, Configuration, ConfigurationBatch,
+                                    convert_configurations_to_array, one_exchange_neighbourhood_arrays)
 from tlbo_b200.optimizer.ei_offline_optimizer import AcquisitionFunctionMaximizer
 from tlbo_b200.optimizer.random_configuration_chooser import ChooserProb
+
+
+class _ScoredBatch(object):
+    """``[(acq, config), ...]`` over a ``ConfigurationBatch``: the sorted random search's result without ~5000
+    tuples and Configuration objects per iteration.  Behaves as the list it stands for (len / index / iterate /
+    ``+ list``); ``InterleavedLocalAndRandomSearch.maximize`` merges it with array operations."""
+
+    def __init__(self, acq, batch):
+        self.acq = acq
+        self.batch = batch
+
+    def __len__(self):
+        return len(self.batch)
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            return (self.acq[i], self.batch[i])
+        return _ScoredBatch(self.acq[i], self.batch[i])
+
+    def __iter__(self):
+        for i in range(len(self.batch)):
+            yield (self.acq[i], self.batch[i])
+
+    def __add__(self, other):
+        return list(self) + list(other)
+
+
+class _MergedChallengers(object):
+    """The challengers of one maximisation in final order -- ``sorted(random_sorted + local, reverse=True, key=acq)``
+    (ei_optimization.py:446-456), a STABLE descending sort -- as an index permutation over the random batch and the
+    local-search results; Configurations are materialised when ``ChallengerList`` reaches them."""
+
+    def __init__(self, scored, local):
+        acq_local = np.array([float(np.asarray(a).reshape(-1)[0]) for a, _ in local], dtype=np.float64)
+        vals = np.concatenate((np.asarray(scored.acq, dtype=np.float64), acq_local))
+        self.order = np.argsort(-vals, kind='stable')
+        self.batch = scored.batch
+        self.local = [c for _, c in local]
+
+    def __len__(self):
+        return len(self.order)
+
+    def __getitem__(self, i):
+        j = int(self.order[i])
+        nb = len(self.batch)
+        return self.batch[j] if j < nb else self.local[j - nb]
+
+    def __iter__(self):
+        for i in range(len(self.order)):
+            yield self[i]
 
 
 class _SortMixin(object):
@@ -36,6 +86,9 @@ class _SortMixin(object):
         acq_values = self.acquisition_function(configs)
         random = self.rng.rand(len(acq_values))
         indices = np.lexsort((random.flatten(), acq_values.flatten()))
+        if isinstance(configs, ConfigurationBatch):
+            order = indices[::-1]
+            return _ScoredBatch(acq_values[order, 0], configs[order])
         return [(acq_values[ind][0], configs[ind]) for ind in indices[::-1]]
 
 
@@ -123,6 +176,13 @@ class LocalSearch(_SortMixin, AcquisitionFunctionMaximizer):
 class RandomSearch(_SortMixin, AcquisitionFunctionMaximizer):
     def _maximize(self, runhistory, num_points, _sorted=False, **kwargs):
         if num_points > 1:
+            if getattr(self.config_space, 'sample_batch', None) is not None:
+                # same draws, rows of one array instead of `num_points` objects
+                rand_configs = self.config_space.sample_batch(num_points)
+                rand_configs.origin = 'Random Search (sorted)' if _sorted else 'Random Search'
+                if _sorted:
+                    return self._sort_configs_by_acq_value(rand_configs)
+                return [(0, c) for c in rand_configs]
             rand_configs = self.config_space.sample_configuration(size=num_points)
         else:
             rand_configs = [self.config_space.sample_configuration(size=1)]
@@ -153,9 +213,13 @@ class InterleavedLocalAndRandomSearch(AcquisitionFunctionMaximizer):
         next_configs_by_local_search = self.local_search._maximize(runhistory, self.n_sls_iterations, **kwargs)
         next_configs_by_random_search_sorted = self.random_search._maximize(
             runhistory, num_points - len(next_configs_by_local_search), _sorted=True)
-        next_configs_by_acq_value = next_configs_by_random_search_sorted + next_configs_by_local_search
-        next_configs_by_acq_value.sort(reverse=True, key=lambda x: x[0])
-        next_configs_by_acq_value = [_[1] for _ in next_configs_by_acq_value]
+        if isinstance(next_configs_by_random_search_sorted, _ScoredBatch):
+            next_configs_by_acq_value = _MergedChallengers(next_configs_by_random_search_sorted,
+                                                           next_configs_by_local_search)
+        else:
+            next_configs_by_acq_value = next_configs_by_random_search_sorted + next_configs_by_local_search
+            next_configs_by_acq_value.sort(reverse=True, key=lambda x: x[0])
+            next_configs_by_acq_value = [_[1] for _ in next_configs_by_acq_value]
         challengers = ChallengerList(next_configs_by_acq_value, self.config_space, random_configuration_chooser)
         random_configuration_chooser.next_smbo_iteration()
         return challengers

@@ -283,26 +283,44 @@ int tlbo_one_exchange_neighbourhood(const double* h_array, int d, const int32_t*
 int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const double* d_loc, const double* d_scale,
                                   int n, int S, int Mr, double* d_loss, void* stream);
 
+/* Ensemble EI of a SMALL query set in one launch -- the acquisition call of one hill-climb step
+ * (tlbo/optimizer/ei_optimization.py:270-281 evaluates the neighbours one by one and stops at the first improvement;
+ * acquisition.py:130-177 over RGPE.predict, rgpe.py:141-153): one CTA per (query row, surrogate) computes the
+ * posterior (as tlbo_gp_predict; training rows, alpha and L^-1 staged in shared memory by bulk copies); the last CTA
+ * of a row combines its surrogates in accumulation order (d_w / d_skip / d_order / mode / var_floor as
+ * tlbo_predict_ei_fused -- same operations) and scores EI.
+ *   Xq [Nq, d] and ei [Nq] may be device memory or MAPPED pinned host memory (UVA);
+ *   h_Xq: optional HOST-readable copy of the rows (may equal Xq when that is host memory): when Nq * d <= 1024 the
+ *   rows then travel inside the kernel arguments (constant bank) and Xq is not read (may be NULL);
+ *   ei: EI per row, NaN kept (the caller applies acquisition.py:72-76).  Each row is ONE 8-byte store with no
+ *   fence behind it: a host that pre-fills ei[] with TLBO_EI_PENDING (a NaN payload no computation produces) may
+ *   spin until no row holds it instead of synchronising the stream;
+ *   d_mu, d_var: [M, Nq] per-surrogate posteriors (scratch the combination reads; left there);
+ *   d_counter: Nq device uint32, zero on entry, zero on completion.  Not re-entrant.                        */
+#define TLBO_EI_PENDING_BITS 0x7ff8dead0000beefULL
+int tlbo_ensemble_ei_small(const tlbo_pack* pack, const int32_t* h_types, const double* d_w, const int32_t* d_skip,
+                           const int32_t* d_order, int mode, const double* Xq, const double* h_Xq, int Nq, double eta,
+                           double par, double var_floor, double* d_mu, double* d_var, double* ei, uint32_t* d_counter,
+                           void* stream);
+
 /* One hill-climb of the online scenario's local search (tlbo/optimizer/ei_optimization.py:239-294,
  * LocalSearch._one_iter), native driver: per step tlbo_one_exchange_neighbourhood(h_config, seed = the next of the
- * pre-drawn rng.randint(0, 10000) values), ONE acquisition evaluation of the whole neighbourhood (tlbo_gp_predict +
- * tlbo_predict_ei_fused_cached in all-resident mode: the launches of the per-step Python path), one stream
- * synchronisation, accept = first neighbour with EI > incumbent (NaN -> -DBL_MAX, acquisition.py:72-76).
- *   view / logical: the K + 1 surrogates, and K + 1 placeholder slots (n = 1) for the all-resident fused call;
- *   d_w / d_skip / d_order / mode / eta / par / var_floor: as tlbo_predict_ei_fused;
+ * pre-drawn rng.randint(0, 10000) values), ONE launch scoring the whole neighbourhood
+ * (tlbo_ensemble_ei_small), a spin on the EI rows, accept = the first neighbour with EI > incumbent.
+ *   view: the K + 1 surrogates; d_w / d_skip / d_order / mode / eta / par / var_floor: as tlbo_predict_ei_fused;
  *   h_config [d], h_acq: incumbent and its EI, updated in place;
- *   h_X pinned [cap, d]; d_X [cap, d]; d_mu, d_var [M * cap]; d_mu_rows, d_var_rows [cap]; h_ei, h_best: MAPPED
- *   pinned host memory [cap], [4] (written by the kernels); d_work: tlbo_predict_ei_workspace_bytes(cap);
+ *   h_X [cap, d] host staging for the neighbourhood; h_ei [cap]: MAPPED pinned host memory (EI written by the
+ *   kernel over the bus, polled row by row);
+ *   d_mu, d_var [M * cap] device scratch; d_counter: cap zeroed device uint32 (left zero);
  *   h_counters int32[5]: += seeds consumed, neighbours the lazy reference loop inspects, acquisition evaluations,
  *   rows with EI < 0 (the caller raises as EI._compute does), steps of this climb (caller zeroes [4] per climb).
- * Returns 0: climb ended; 1: seeds ran out (call again with more, state is up to date). */
-int tlbo_local_search_climb(const tlbo_pack* view, const tlbo_pack* logical, const int32_t* h_types,
-                            const uint8_t* h_const_mask, const double* d_w, const int32_t* d_skip,
-                            const int32_t* d_order, int mode, double eta, double par, double var_floor,
-                            int num_neighbors, double stdev, const uint32_t* h_seeds, int n_seeds, int max_steps,
-                            double* h_config, double* h_acq, double* h_X, double* d_X, double* d_mu, double* d_var,
-                            double* d_mu_rows, double* d_var_rows, double* h_ei, double* h_best, void* d_work,
-                            int cap, int32_t* h_counters, void* stream);
+ * Returns 0: climb ended; 1: seeds ran out (call again with more, state is up to date).  Not re-entrant. */
+int tlbo_local_search_climb(const tlbo_pack* view, const int32_t* h_types, const uint8_t* h_const_mask,
+                            const double* d_w, const int32_t* d_skip, const int32_t* d_order, int mode, double eta,
+                            double par, double var_floor, int num_neighbors, double stdev, const uint32_t* h_seeds,
+                            int n_seeds, int max_steps, double* h_config, double* h_acq, double* h_X, double* d_mu,
+                            double* d_var, double* h_ei, uint32_t* d_counter, int cap, int32_t* h_counters,
+                            void* stream);
 
 /* numpy's LEGACY RandomState.random_sample on the device, bit for bit, with the MT19937 state resident in HBM:
  * the `rng.rand(N)` tie-break keys that `_sort_configs_by_acq_value` (reference

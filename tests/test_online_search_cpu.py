@@ -150,3 +150,51 @@ def test_native_neighbourhood_reproduces_numpys_legacy_stream():
     c = Configuration(sp, np.array([0.3, np.nan, 1.0]), -1)
     a, b = one_exchange_neighbourhood_arrays(c, 5), one_exchange_neighbourhood_arrays_py(c, 5)
     assert a.shape == (10, 3) and np.array_equal(a, b, equal_nan=True)   # 8 numerical + 2 categorical
+
+
+class TiedAcq(FakeAcq):
+    """Coarsely quantised values: many exact ties between random-search rows and local-search results."""
+
+    def __call__(self, configs):
+        return np.round(FakeAcq.__call__(self, configs), 1)
+
+
+@pytest.mark.parametrize('acq_cls', [FakeAcq, TiedAcq])
+def test_lazy_challenger_batch_equals_the_eager_list_path(acq_cls):
+    """The sorted random search over a ConfigurationBatch + array merge (no per-row objects) yields the challengers
+    of the reference's list path -- sort by lexsort((rand, acq)), concatenate, STABLE descending sort
+    (ei_optimization.py:106-132,446-456) -- element for element, ties included, with the same stream consumption."""
+    from tlbo_b200.config_space import Configuration, TableSpace
+    from tlbo_b200.optimizer.ei_optimization import (HistoryContainer, InterleavedLocalAndRandomSearch,
+                                                     _MergedChallengers)
+    from tlbo_b200.optimizer.random_configuration_chooser import ChooserProb
+
+    class EagerSpace(TableSpace):
+        sample_batch = None                                   # hasattr() is False -> the list path
+
+    out, states = [], []
+    for cls in (TableSpace, EagerSpace):
+        sp = cls(RF_TYPES, const_mask=RF_CONST)
+        if cls is EagerSpace:
+            assert not hasattr(sp, 'sample_batch') or sp.sample_batch is None
+        sp.seed(3)
+        hist = HistoryContainer()
+        X0 = sp.sample_array(12)
+        for i in range(12):
+            hist.add(Configuration(sp, X0[i], -1), float(i))
+        rng = np.random.RandomState(9)
+        opt = InterleavedLocalAndRandomSearch(acq_cls(RF_TYPES), sp, rng=rng, n_sls_iterations=10, rand_prob=0.0)
+        opt.local_search.native_climb = False
+        np.random.seed(1)
+        ch = opt.maximize(hist, 600, random_configuration_chooser=ChooserProb(prob=0.0, rng=np.random.RandomState(1)))
+        if cls is TableSpace:
+            assert isinstance(ch.challengers, _MergedChallengers)
+        else:
+            assert isinstance(ch.challengers, list)
+        out.append(list(ch))
+        states.append((rng.get_state()[1].copy(), rng.get_state()[2], sp._rng.get_state()[1].copy()))
+    a, b = out
+    assert len(a) == len(b) == 600
+    assert all(x == y and x.origin == y.origin for x, y in zip(a, b))
+    assert np.array_equal(states[0][0], states[1][0]) and states[0][1] == states[1][1]
+    assert np.array_equal(states[0][2], states[1][2])
