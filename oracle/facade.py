@@ -830,3 +830,80 @@ class OracleTSTM(OracleFacade):
             denominator += weight
         mu /= denominator
         return mu, var
+
+
+class OracleSGPR(OracleFacade):
+    """tlbo/facade/stacking_gpr.py:7-128 ``SGPR``: a stack of residual GPs.  For every source history in turn (and
+    finally for the target observations) ONE freshly built model is trained twice -- on ``y``, then on ``y`` minus
+    the prior mean cached at those configurations (the second fit starts from the first fit's optimum and the
+    model's continuing random streams) -- and its posterior over the union of all configurations updates the cached
+    prior: ``mu += mu_top``, ``sigma = sigma_top ** beta * sigma ** (1 - beta)`` with
+    ``beta = alpha n / (alpha n + prior_size)`` (``sigma_top`` is the VARIANCE ``model.predict`` returns).
+    ``predict`` looks configurations up in that cache.
+
+    ``target_hp_configs``: float64[N, d], the target's candidate table."""
+
+    def __init__(self, types, source_hpo_data, seed, target_hp_configs, num_src_hpo_trial=50, literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, literal_loops)
+        self.method_id = 'sgpr'
+        self.target_hp_configs = np.asarray(target_hp_configs, dtype=np.float64)
+        self.alpha = 0.95
+        self.iteration_id = 0
+        self.get_regressor()
+
+    @staticmethod
+    def _key(row):
+        return str(list(row))                                   # stacking_gpr.py:41-42,77
+
+    def get_regressor(self):
+        """stacking_gpr.py:25-63."""
+        configs, self.index_mapper = [], dict()
+        rows = [np.asarray(X, dtype=np.float64)[:self.num_src_hpo_trial] for X, _ in self.source_hpo_data]
+        for X in rows + [self.target_hp_configs]:
+            for x in X:
+                k = self._key(x)
+                if k not in self.index_mapper:                  # `_config not in configs_list`
+                    self.index_mapper[k] = len(configs)
+                    configs.append(np.array(x))
+        self.configs_X = np.array(configs)
+        n = len(configs)
+        self.cached_prior_mu, self.cached_prior_sigma = np.zeros(n), np.ones(n)
+        self.cached_stacking_mu, self.cached_stacking_sigma = np.zeros(n), np.ones(n)
+        self.prior_size = 0
+        for X, y in self.source_hpo_data:
+            X = np.asarray(X, dtype=np.float64)[:self.num_src_hpo_trial]
+            y = np.array(y, dtype=np.float64)[:self.num_src_hpo_trial]
+            self.train_regressor(X, y)
+            self.prior_size = len(y)
+
+    def train_regressor(self, X, y, is_top=False):
+        """stacking_gpr.py:65-99."""
+        model = self._new_model()
+        model.train(X, y)
+        idxs = [self.index_mapper[self._key(x)] for x in X]
+        prior_mu = np.array(self.cached_prior_mu[idxs])
+        model.train(X, y - prior_mu)
+        top_size = len(y)
+        beta = self.alpha * top_size / (self.alpha * top_size + self.prior_size)
+        mu_top, sigma_top = model.predict(self.configs_X)
+        mu_top, sigma_top = mu_top.flatten(), sigma_top.flatten()
+        if is_top:
+            self.cached_stacking_mu = self.cached_prior_mu + mu_top
+            self.cached_stacking_sigma = np.power(sigma_top, beta) * np.power(self.cached_prior_sigma, 1 - beta)
+        else:
+            self.cached_prior_mu += mu_top.flatten()
+            self.cached_prior_sigma = np.power(sigma_top, beta) * np.power(self.cached_prior_sigma, 1 - beta)
+        self.last_model = model
+
+    def train(self, X, y):
+        """stacking_gpr.py:101-114."""
+        if any(self._key(x) not in self.index_mapper for x in X):
+            self.get_regressor()
+        self.train_regressor(X, y, is_top=True)
+        self.iteration_id += 1
+
+    def predict(self, X):
+        """stacking_gpr.py:116-124."""
+        idx = [self.index_mapper[self._key(x)] for x in X]
+        return (np.array(self.cached_stacking_mu[idx]).reshape(-1, 1),
+                np.array(self.cached_stacking_sigma[idx]).reshape(-1, 1))

@@ -422,3 +422,101 @@ def test_cuda_facade_over_conditional_space_runs_masked_posteriors():
     mu1, var1 = fac.target_surrogate.predict(Xq)
     np.testing.assert_allclose(mu, mu1, rtol=1e-12)
     assert len(set(smbo.configurations)) == 6
+
+
+def _sgpr_setup():
+    from tlbo_b200.config_space import TableSpace
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v6_sgpr.npz'))
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    return D, K, seed, TableSpace(types), tables
+
+
+def test_cuda_sgpr_matches_reference(monkeypatch):
+    """facade/stacking_gpr.py as run by the reference itself (fixture reference_v6_sgpr.npz: sources and target
+    share configurations): the prior after the K source regressors, the stacked mean / sigma after every
+    iteration, the selected rows and the final prediction -- device GPs at the reference's theta (two fits per
+    regressor), pool posteriors, element-wise updates and the all-resident fused EI + arg-max on the device."""
+    import tlbo_b200.model.gp as G
+    from tlbo_b200.facade.stacking_gpr import SGPR
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D, K, seed, cs, tables = _sgpr_setup()
+    forced = _ForcedFits(monkeypatch)
+    orig = G.fit_models_async
+
+    def forced_fit(models, Xs, Ys, do_optimize=True):
+        for m in models:
+            m.kernel.theta = np.array(forced.queue.pop(0), dtype=np.float64)
+        return orig(models, Xs, Ys, do_optimize=False)
+    monkeypatch.setattr(G, 'fit_models_async', forced_fit)
+    thetas = [th for th in D['thetas']]
+    nsrc = int(D['n_source_fits'])
+    forced.queue = thetas[:nsrc]
+    fac = SGPR(cs, [(X.copy(), y.copy()) for X, y in tables[1:]], tables[0][0], seed, surrogate_type='gp',
+               num_src_hpo_trial=50)
+    assert not forced.queue
+    np.testing.assert_array_equal(fac.configs_X, D['configs_X'])
+    np.testing.assert_allclose(fac.cached_prior_mu, D['prior_mu'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(fac.cached_prior_sigma, D['prior_sigma'], rtol=1e-6, atol=1e-12)
+    smbo = SMBO_OFFLINE(tables[0], cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                        random_seed=seed, max_runs=100)
+    used = nsrc
+    for it, row in enumerate(D['rows']):
+        if it >= 3:
+            forced.queue = thetas[used:used + 2]
+            used += 2
+        smbo.iterate()
+        assert not forced.queue
+        got = smbo.configurations[-1]
+        assert got == int(row), 'iteration %d: device picked row %d, reference %d' % (it, got, row)
+        if it >= 3:
+            np.testing.assert_allclose(fac.cached_stacking_mu, D['stack_mu'][it], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(fac.cached_stacking_sigma, D['stack_sigma'][it], rtol=1e-6, atol=1e-12)
+    assert used == len(thetas)
+    mu, var = fac.predict(tables[0][0][:64])
+    np.testing.assert_allclose(mu, D['final_mu'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, D['final_var'], rtol=1e-6, atol=1e-12)
+    with pytest.raises(KeyError):
+        fac.predict(np.full((1, tables[0][0].shape[1]), 0.123))
+
+
+def test_cuda_sgpr_with_device_fit_tracks_reference():
+    """The same run with the device's own fits (no forcing): every regressor is trained twice on one model -- the
+    second fit starts at the first optimum and continues the model's random streams -- so the reference's fitted
+    theta sequence is reproduced fit by fit (printed: the measured agreement)."""
+    import tlbo_b200.model.gp as G
+    from tlbo_b200.facade.stacking_gpr import SGPR
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D, K, seed, cs, tables = _sgpr_setup()
+    seen = []
+    orig = G.fit_models_async
+
+    def spy(models, Xs, Ys, do_optimize=True):
+        fin = orig(models, Xs, Ys, do_optimize)
+
+        def finish():
+            r = fin()
+            seen.extend(np.array(m.hypers, dtype=np.float64) for m in models)
+            return r
+        return finish
+    G.fit_models_async = spy
+    try:
+        fac = SGPR(cs, [(X.copy(), y.copy()) for X, y in tables[1:]], tables[0][0], seed, surrogate_type='gp',
+                   num_src_hpo_trial=50)
+        smbo = SMBO_OFFLINE(tables[0], cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                            random_seed=seed, max_runs=100)
+        for _ in D['rows']:
+            smbo.iterate()
+    finally:
+        G.fit_models_async = orig
+    got = np.asarray(smbo.configurations)
+    rows = D['rows']
+    same = int(np.argmax(np.concatenate([got != rows, [True]])))
+    dth = [float(np.max(np.abs(a - b))) for a, b in zip(seen, D['thetas'])]
+    print('sgpr: %d of %d picks identical to the reference run; %d fits, max |theta - reference| per fit %s' % (
+        same, len(rows), len(seen), ['%.1e' % v for v in dth]))
+    assert len(seen) == len(D['thetas'])
+    assert max(dth[:int(D['n_source_fits'])]) < 1e-4        # the source regressors: the reference's optima
+    assert same >= 4
+    span = tables[0][1].max() - tables[0][1].min()
+    assert min(smbo.perfs) <= D['perfs'].min() + 0.05 * span

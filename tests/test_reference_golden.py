@@ -311,3 +311,42 @@ def test_conditional_activity_mask_matches_reference():
     mu, var = g.predict(D['Xq'])
     np.testing.assert_allclose(mu, D['mu'], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(var, D['var'], rtol=1e-6, atol=1e-13)
+
+
+def test_sgpr_matches_reference(monkeypatch):
+    """The stacking-GP baseline (tlbo/facade/stacking_gpr.py) against a run of the reference itself (fixture
+    reference_v6_sgpr.npz; sources and target share configurations, so the de-duplicated configuration set is
+    exercised): the prior after the K source regressors, the stacked mean / "sigma" after every iteration, the
+    selected rows and the final prediction.  The oracle's GPs take the reference's fitted theta (two fits per
+    regressor: on y, then on the residual)."""
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v6_sgpr.npz'))
+    monkeypatch.setattr(ofacade, 'OracleGP', _ForcedGP)
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    thetas = [th for th in D['thetas']]
+    nsrc = int(D['n_source_fits'])
+    assert nsrc == 2 * K
+    _ForcedGP.queue = thetas[:nsrc]
+    fac = ofacade.OracleSGPR(types, [(X.copy(), y.copy()) for X, y in tables[1:]], seed, tables[0][0])
+    assert not _ForcedGP.queue
+    assert len(fac.configs_X) == int(D['n_configs']) < (K + 1) * 50 + 300 - 40
+    np.testing.assert_array_equal(fac.configs_X, D['configs_X'])
+    np.testing.assert_allclose(fac.cached_prior_mu, D['prior_mu'], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(fac.cached_prior_sigma, D['prior_sigma'], rtol=1e-6, atol=1e-12)
+    smbo = OracleSMBOOffline(tables[0][0], tables[0][1], fac, seed, initial_runs=3)
+    used, trained = nsrc, 0
+    for it, row in enumerate(D['rows']):
+        if it >= 3:
+            _ForcedGP.queue = thetas[used:used + 2]
+            used += 2
+        got = smbo.iterate()
+        assert not _ForcedGP.queue
+        assert got == int(row), 'iteration %d: oracle picked row %d, reference %d' % (it, got, row)
+        if it >= 3:
+            trained += 1
+            np.testing.assert_allclose(fac.cached_stacking_mu, D['stack_mu'][it], rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(fac.cached_stacking_sigma, D['stack_sigma'][it], rtol=1e-6, atol=1e-12)
+    assert trained == 5 and used == len(thetas)
+    mu, var = fac.predict(tables[0][0][:64])
+    np.testing.assert_allclose(mu, D['final_mu'], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, D['final_var'], rtol=1e-6, atol=1e-12)
