@@ -287,3 +287,79 @@ def test_mcmc_facade_predict_rows_match_oracle():
     mu, var = prod.predict_marginalized_over_instances(Xq)
     wmu, wvar = ora.predict_marginalized_over_instances(Xq)
     assert np.allclose(mu, wmu, rtol=1e-6, atol=1e-9) and np.allclose(var, wvar, rtol=1e-6, atol=1e-13)
+
+
+def test_chain_samples_the_hyperparameter_posterior():
+    """Statistical contract of the sampler, independent of any stream order: the stationary distribution of the
+    stretch-move chain is the hyper-parameter posterior exp(_ll).  A one-column problem (H = 3: amplitude, length
+    scale, noise) is small enough for quadrature: posterior mean and spread from a two-level grid (coarse over the
+    prior box, fine over the region holding the mass; grid values from the device's own batched ``_ll``, which
+    ``test_log_probability_matches_oracle`` pins to the oracle at 1e-9) against the final ensembles of 64
+    independent 16-walker chains after 400 steps (1 024 draws; a wrong proposal density, e.g. a missing
+    ``(ndim - 1) log z`` factor, or a broken accept rule shifts these moments by far more than the tolerances)."""
+    from tlbo_b200 import ops
+    from tlbo_b200.model.gp_mcmc import stretch_move_tables
+    types = np.zeros(1, int)
+    spec = ogp.KernelSpec(types)
+    H = spec.H
+    assert H == 3
+    rng = np.random.RandomState(77)
+    X = rng.rand(14, 1)
+    y = np.sin(4 * X[:, 0]) + 0.15 * rng.randn(14)
+    y = (y - y.mean()) / y.std()
+    braw = _bounds_raw(spec)
+    lo, hi = np.log(braw[:, 0]), np.log(braw[:, 1])
+    GB, GW = 8, 128                                   # 1 024 grid points per evaluation call
+    rep = ops.upload_batch([X] * GB, [y] * GB)
+
+    def grid_lp(axes):
+        G = np.stack(np.meshgrid(*axes, indexing='ij'), axis=-1).reshape(-1, H)
+        out = np.empty(len(G))
+        for s in range(0, len(G), GB * GW):
+            blk = G[s:s + GB * GW]
+            pad = np.vstack([blk, np.repeat(blk[-1:], GB * GW - len(blk), axis=0)])
+            h = ops.gp_mcmc_chain(rep, types, GW, 0, pad.reshape(GB, GW, H), None, None, braw, spec.default_theta())
+            st, _, lp, _ = h.finish()
+            assert np.all(st == 0)
+            out[s:s + len(blk)] = lp.reshape(-1)[:len(blk)]
+        return G, out
+
+    eps = 1e-9
+    coarse = [np.linspace(lo[k] + eps, hi[k] - eps, 28) for k in range(H)]
+    G, lp = grid_lp(coarse)
+    keep = lp > lp.max() - 30.0
+    step = np.array([c[1] - c[0] for c in coarse])
+    blo = np.maximum(G[keep].min(axis=0) - step, lo + eps)
+    bhi = np.minimum(G[keep].max(axis=0) + step, hi - eps)
+    fine = [np.linspace(blo[k], bhi[k], 44) for k in range(H)]
+    G, lp = grid_lp(fine)
+    w = np.exp(lp - lp.max())
+    # trapezoid weights on the uniform fine grid
+    tw = np.ones((44,) * H)
+    for k in range(H):
+        sl = [slice(None)] * H
+        for edge in (0, -1):
+            sl[k] = edge
+            tw[tuple(sl)] *= 0.5
+    w = w * tw.reshape(-1)
+    w /= w.sum()
+    mean_q = (w[:, None] * G).sum(axis=0)
+    std_q = np.sqrt((w[:, None] * (G - mean_q) ** 2).sum(axis=0))
+
+    B, W, nsteps = 64, 16, 400
+    p0 = np.empty((B, W, H))
+    for k in range(H):
+        p0[:, :, k] = rng.uniform(blo[k], bhi[k], size=(B, W))
+    tabs = [stretch_move_tables(np.random.RandomState(500 + b), W, H, nsteps) for b in range(B)]
+    batch = ops.upload_batch([X] * B, [y] * B)
+    h = ops.gp_mcmc_chain(batch, types, W, nsteps, p0, ops.McmcTables(tabs), list(range(B)), braw, spec.default_theta())
+    st, pos, lpc, nacc = h.finish()
+    assert np.all(st == 0) and np.all(np.isfinite(lpc))
+    acc = nacc.sum() / float(B * W * nsteps)
+    S = pos.reshape(-1, H)
+    mean_c, std_c = S.mean(axis=0), S.std(axis=0)
+    print('posterior mean quadrature %s chain %s; std quadrature %s chain %s; acceptance %.2f' % (
+        np.round(mean_q, 3), np.round(mean_c, 3), np.round(std_q, 3), np.round(std_c, 3), acc))
+    assert 0.2 < acc < 0.8
+    assert np.all(np.abs(mean_c - mean_q) <= 0.25 * std_q), (mean_c, mean_q, std_q)
+    assert np.all(std_c / std_q > 0.75) and np.all(std_c / std_q < 1.3), (std_c, std_q)
