@@ -353,21 +353,99 @@ __device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
 // than the Cholesky route's (cond 1e5..5e6: 1e-13..2e-11 either way).  The FULL matrix is kept (both
 // triangles, T x T tile per thread) so that pivot column k has ONE owner group -- the half-warp tx == k % 16
 // -- and the publish / consume pattern is the one of elim_block.
+//
+// PAIRS of pivots and select-free updates (round 2).  ncu and the phase clocks show the sweep bound by the
+// instruction stream of a step (~100 instructions per thread and pivot, two warps per scheduler), not by its
+// latency chain, so a step now does more arithmetic per instruction of overhead:
+//  * the pivots k = kt + 16 KB and k' = k + 16 (tile columns KB, KB + 1 of the SAME owner half-warp tx == kt; the
+//    2 x 2 pivot block P lives in ONE thread's tile) are swept together -- a block sweep equals the two single
+//    sweeps (any pivot order is a valid sweep of an SPD matrix: same -K^-1, same product of pivots, positive
+//    pivots iff K is positive definite): one publish / barrier / consume and one pass over the tile
+//    (a_ij -= c_i u_j + c'_i u'_j with (u, u') = P^-1 (c, c')) per TWO pivots;
+//  * the special cases of the sweep operator (pivot rows <- P^-1 rows, pivot columns likewise, pivot block <- -P^-1)
+//    fall out of the SAME rank-2 formula when the published pivot columns carry P - I in the pivot rows: then
+//    rows k, k' come out as (u_j, u'_j), columns as (u_i, u'_i), and the pivot block as 2 I - P^-1 -- the owner
+//    subtracts 2 from its two diagonal elements.  No per-element selects (the single-pivot step had 9 double selects
+//    and 4 extra multiplies per thread);
+//  * P^-1 (determinant, one reciprocal, three products) is formed by the ONE owner thread behind a branch instead of
+//    a speculative reciprocal in all 256 threads.
+// Pivots without a partner (n - 16 KB < 16 leaves tile column KB + 1 short, odd T) take the single-pivot step in the
+// same select-free form (published diagonal entry p - 1, owner fix -2).  piv[] receives det P and 1 for a pair
+// (only the sum of logarithms and the signs are used).
 template <int T, int KB>
-__device__ __forceinline__ void sweep_block(double (&a)[T][T], ElimCtx& c) {
-  constexpr int TP = (T + 1) & ~1;             // packed per-lane stride (128-bit chunks)
-  const int n = c.n, tx = c.tx, ty = c.ty;
-  const int kend = (n - 16 * KB) < 16 ? (n - 16 * KB) : 16;
+__device__ __forceinline__ void sweep_pair_steps(double (&a)[T][T], ElimCtx& c, int kend, int& par) {
+  constexpr int TP = (T + 1) & ~1;
+  constexpr int K2 = KB + 1;
+  static_assert(K2 < T, "pair needs two tile columns");
+  const int tx = c.tx, ty = c.ty;
+#pragma unroll 1
   for (int kt = 0; kt < kend; kt++) {
-    const int k = 16 * KB + kt;
-    double* buf = c.colbuf + (kt & 1) * FIT_COLBUF;
-    const bool col_eq = (tx == kt), row_eq = (ty == kt), own = col_eq && row_eq;
-    {
+    double* buf = c.colbuf + par * FIT_COLBUF;
+    par ^= 1;
+    const bool pub = (tx == kt), own = pub && (ty == kt);
 #pragma unroll
-      for (int q = 0; q < TP; q += 2)
-        sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, col_eq);
-      sts2_if(buf + 384, a[KB][KB], c.ip_next, own);
-      sts1_if(c.pivs + k, a[KB][KB], own);
+    for (int q = 0; q < TP; q += 2) {
+      sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, pub);
+      sts2_if(buf + 128 + ty * TP + q, a[q][K2], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][K2] : 0.0, pub);
+    }
+    if (own) {                                                 // one thread of one warp
+      const double p11 = a[KB][KB], p12 = a[K2][KB], p22 = a[K2][K2];
+      const double det = fma(p11, p22, -(p12 * p12));
+      const double idet = fast_rcp(det);
+      *reinterpret_cast<double2*>(buf + 384) = make_double2(p22 * idet, -(p12 * idet));
+      *reinterpret_cast<double2*>(buf + 386) = make_double2(p11 * idet, (p11 > 0.0 && det > 0.0) ? 1.0 : -1.0);
+      buf[ty * TP + KB] = p11 - 1.0;                           // P - I in the pivot rows
+      buf[128 + ty * TP + K2] = p22 - 1.0;
+      c.pivs[16 * KB + kt] = det;
+      c.pivs[16 * K2 + kt] = 1.0;
+    }
+    __syncthreads();
+    const double2 qa = *reinterpret_cast<const double2*>(buf + 384);
+    const double2 qb = *reinterpret_cast<const double2*>(buf + 386);
+    c.bad = c.bad || !(qb.y > 0.0);
+    const double q11 = qa.x, q12 = qa.y, q22 = qb.x;
+    double ck[TP], dk[TP], u[TP], v[TP];
+    {
+      const double2* c2 = reinterpret_cast<const double2*>(buf + ty * TP);
+      const double2* d2 = reinterpret_cast<const double2*>(buf + 128 + ty * TP);
+      const double2* e2 = reinterpret_cast<const double2*>(buf + tx * TP);
+      const double2* g2 = reinterpret_cast<const double2*>(buf + 128 + tx * TP);
+#pragma unroll
+      for (int q = 0; q < TP; q += 2) {
+        const double2 cc = c2[q >> 1], dd = d2[q >> 1], ee = e2[q >> 1], gg = g2[q >> 1];
+        ck[q] = cc.x; ck[q + 1] = cc.y; dk[q] = dd.x; dk[q + 1] = dd.y;
+        u[q] = fma(q11, ee.x, q12 * gg.x); u[q + 1] = fma(q11, ee.y, q12 * gg.y);
+        v[q] = fma(q12, ee.x, q22 * gg.x); v[q + 1] = fma(q12, ee.y, q22 * gg.y);
+      }
+    }
+#pragma unroll
+    for (int jb = 0; jb < T; jb++) {
+#pragma unroll
+      for (int ia = 0; ia < T; ia++) a[ia][jb] = fma(-ck[ia], u[jb], fma(-dk[ia], v[jb], a[ia][jb]));
+    }
+    const double two = own ? 2.0 : 0.0;                        // pivot block: 2 I - P^-1  ->  -P^-1
+    a[KB][KB] -= two;
+    a[K2][K2] -= two;
+  }
+}
+
+template <int T, int KB>
+__device__ __forceinline__ void sweep_single_steps(double (&a)[T][T], ElimCtx& c, int kt0, int kt1, int& par) {
+  constexpr int TP = (T + 1) & ~1;
+  const int tx = c.tx, ty = c.ty;
+#pragma unroll 1
+  for (int kt = kt0; kt < kt1; kt++) {
+    double* buf = c.colbuf + par * FIT_COLBUF;
+    par ^= 1;
+    const bool pub = (tx == kt), own = pub && (ty == kt);
+#pragma unroll
+    for (int q = 0; q < TP; q += 2)
+      sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, pub);
+    if (own) {
+      const double pv = a[KB][KB];
+      *reinterpret_cast<double2*>(buf + 384) = make_double2(pv, fast_rcp(pv));
+      buf[ty * TP + KB] = pv - 1.0;
+      c.pivs[16 * KB + kt] = pv;
     }
     __syncthreads();
     const double2 pp = *reinterpret_cast<const double2*>(buf + 384);
@@ -379,34 +457,37 @@ __device__ __forceinline__ void sweep_block(double (&a)[T][T], ElimCtx& c) {
       const double2* f2 = reinterpret_cast<const double2*>(buf + tx * TP);
 #pragma unroll
       for (int q = 0; q < TP; q += 2) {
-        const double2 v = c2[q >> 1], w = f2[q >> 1];
-        ck[q] = v.x; ck[q + 1] = v.y; f[q] = w.x * ip; f[q + 1] = w.y * ip;
+        const double2 vv = c2[q >> 1], w = f2[q >> 1];
+        ck[q] = vv.x; ck[q + 1] = vv.y; f[q] = w.x * ip; f[q + 1] = w.y * ip;
       }
     }
 #pragma unroll
     for (int jb = 0; jb < T; jb++) {
 #pragma unroll
-      for (int ia = 0; ia < T; ia++) {
-        double v = fma(-ck[ia], f[jb], a[ia][jb]);
-        if (ia == KB) v = row_eq ? f[jb] : v;                  // row k     <- c_j / p
-        if (jb == KB) v = col_eq ? ck[ia] * ip : v;            // column k  <- c_i / p
-        if (ia == KB && jb == KB) v = own ? -ip : v;           // pivot     <- -1 / p
-        a[ia][jb] = v;
-      }
+      for (int ia = 0; ia < T; ia++) a[ia][jb] = fma(-ck[ia], f[jb], a[ia][jb]);
     }
-    {
-      // speculative and branch-free: every thread inverts its own candidate for the next pivot
-      constexpr int KN = (KB + 1 < T) ? KB + 1 : KB;
-      const double pv = (kt < 15) ? a[KB][KB] : a[KN][KN];
-      c.ip_next = fast_rcp(pv);
-    }
+    a[KB][KB] -= own ? 2.0 : 0.0;                              // 2 - 1/p  ->  -1/p
   }
 }
 
 template <int T, int KB>
+__device__ __forceinline__ void sweep_blocks(double (&a)[T][T], ElimCtx& c, int& par) {
+  const int n = c.n;
+  const int nk = (n - 16 * KB) < 0 ? 0 : ((n - 16 * KB) < 16 ? (n - 16 * KB) : 16);        // pivots in tile column KB
+  if constexpr (KB + 1 < T) {
+    const int np = (n - 16 * (KB + 1)) < 0 ? 0 : ((n - 16 * (KB + 1)) < 16 ? (n - 16 * (KB + 1)) : 16);
+    sweep_pair_steps<T, KB>(a, c, np, par);
+    sweep_single_steps<T, KB>(a, c, np, nk, par);
+    if constexpr (KB + 2 < T) sweep_blocks<T, KB + 2>(a, c, par);
+  } else {
+    sweep_single_steps<T, KB>(a, c, 0, nk, par);
+  }
+}
+
+template <int T>
 __device__ __forceinline__ void sweep_all(double (&a)[T][T], ElimCtx& c) {
-  if (16 * KB < c.n) sweep_block<T, KB>(a, c);
-  if constexpr (KB + 1 < T) sweep_all<T, KB + 1>(a, c);
+  int par = 0;
+  sweep_blocks<T, 0>(a, c, par);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -749,8 +830,8 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   ElimCtx ec;
   ec.colbuf = S.colbuf; ec.pivs = S.piv; ec.n = n; ec.tx = tx; ec.ty = ty;
   ec.diag_lower = ty >= tx; ec.own_diag = ty == tx; ec.bad = false;
-  ec.ip_next = fast_rcp(a[0][0]);
-  sweep_all<T, 0>(a, ec);
+  ec.ip_next = 0.0;
+  sweep_all<T>(a, ec);
   // row n of the swept matrix is alpha, element (n, n) is -y^T K^-1 y: published before the barrier
 #pragma unroll
   for (int ia = 0; ia < T; ia++) {
