@@ -350,9 +350,10 @@ __device__ __forceinline__ void elim_all(double (&a)[T][T], ElimCtx& c) {
 // L / L^-1 elimination above this needs no write-back, no back substitution for alpha and no
 // K^-1 = L^-T L^-1 contraction afterwards (12 k of 71 k cycles per evaluation at n = 60), for the same
 // per-step cost; measured against an extended-precision solve its alpha and gradient errors are no larger
-// than the Cholesky route's (cond 1e5..5e6: 1e-13..2e-11 either way).  The FULL matrix is kept (both
-// triangles, T x T tile per thread) so that pivot column k has ONE owner group -- the half-warp tx == k % 16
-// -- and the publish / consume pattern is the one of elim_block.
+// than the Cholesky route's (cond 1e5..5e6: 1e-13..2e-11 either way).  Thread (ty, tx) keeps the tiles ia >= jb of
+// its T x T register tile (the lower triangle of the tile grid, diagonal tiles in full: 20 instead of 32 FMAs per pair
+// step); the entries of a pivot column that sit in dropped tiles are published by the ROW owners (ty == kt) by symmetry.
+// Launch time 1.80 -> 1.75 ms (n = 60), 1.77 -> 1.62 ms (n = 45) against full tiles.
 //
 // PAIRS of pivots and select-free updates (round 2).  ncu and the phase clocks show the sweep bound by the
 // instruction stream of a step (~100 instructions per thread and pivot, two warps per scheduler), not by its
@@ -383,10 +384,15 @@ __device__ __forceinline__ void sweep_pair_steps(double (&a)[T][T], ElimCtx& c, 
     double* buf = c.colbuf + par * FIT_COLBUF;
     par ^= 1;
     const bool pub = (tx == kt), own = pub && (ty == kt);
+    // only tiles ia >= jb are kept (the matrix is symmetric): rows of tile-row blocks >= the pivot's come from the
+    // column owners (tx == kt), the others from the row owners (ty == kt) by symmetry
+    const bool rpub = (ty == kt);
 #pragma unroll
-    for (int q = 0; q < TP; q += 2) {
-      sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, pub);
-      sts2_if(buf + 128 + ty * TP + q, a[q][K2], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][K2] : 0.0, pub);
+    for (int q = 0; q < T; q++) {
+      if (q >= KB) sts1_if(buf + ty * TP + q, a[q][KB], pub);
+      else sts1_if(buf + tx * TP + q, a[KB][q], rpub);
+      if (q >= K2) sts1_if(buf + 128 + ty * TP + q, a[q][K2], pub);
+      else sts1_if(buf + 128 + tx * TP + q, a[K2][q], rpub);
     }
     if (own) {                                                 // one thread of one warp
       const double p11 = a[KB][KB], p12 = a[K2][KB], p22 = a[K2][K2];
@@ -421,7 +427,7 @@ __device__ __forceinline__ void sweep_pair_steps(double (&a)[T][T], ElimCtx& c, 
 #pragma unroll
     for (int jb = 0; jb < T; jb++) {
 #pragma unroll
-      for (int ia = 0; ia < T; ia++) a[ia][jb] = fma(-ck[ia], u[jb], fma(-dk[ia], v[jb], a[ia][jb]));
+      for (int ia = jb; ia < T; ia++) a[ia][jb] = fma(-ck[ia], u[jb], fma(-dk[ia], v[jb], a[ia][jb]));
     }
     const double two = own ? 2.0 : 0.0;                        // pivot block: 2 I - P^-1  ->  -P^-1
     a[KB][KB] -= two;
@@ -438,9 +444,12 @@ __device__ __forceinline__ void sweep_single_steps(double (&a)[T][T], ElimCtx& c
     double* buf = c.colbuf + par * FIT_COLBUF;
     par ^= 1;
     const bool pub = (tx == kt), own = pub && (ty == kt);
+    const bool rpub = (ty == kt);
 #pragma unroll
-    for (int q = 0; q < TP; q += 2)
-      sts2_if(buf + ty * TP + q, a[q][KB], (q + 1 < T) ? a[(q + 1 < T) ? q + 1 : q][KB] : 0.0, pub);
+    for (int q = 0; q < T; q++) {
+      if (q >= KB) sts1_if(buf + ty * TP + q, a[q][KB], pub);
+      else sts1_if(buf + tx * TP + q, a[KB][q], rpub);
+    }
     if (own) {
       const double pv = a[KB][KB];
       *reinterpret_cast<double2*>(buf + 384) = make_double2(pv, fast_rcp(pv));
@@ -464,7 +473,7 @@ __device__ __forceinline__ void sweep_single_steps(double (&a)[T][T], ElimCtx& c
 #pragma unroll
     for (int jb = 0; jb < T; jb++) {
 #pragma unroll
-      for (int ia = 0; ia < T; ia++) a[ia][jb] = fma(-ck[ia], f[jb], a[ia][jb]);
+      for (int ia = jb; ia < T; ia++) a[ia][jb] = fma(-ck[ia], f[jb], a[ia][jb]);
     }
     a[KB][KB] -= own ? 2.0 : 0.0;                              // 2 - 1/p  ->  -1/p
   }
@@ -528,7 +537,7 @@ __device__ __forceinline__ void kernel_panel_reg(const FitWs& S, const SpaceDesc
   // exp / sqrt code over the pair table, then every thread picks up its register tile.
   // FOUR pairs in flight per thread: the sqrt / exp chains are ~60 dependent FP64 operations and only two
   // warps share a scheduler, so the phase is latency-bound (n = 60: 7 pairs per thread in two passes)
-  constexpr int PF = 4;
+  constexpr int PF = 8;
   for (int qb = tid; qb < S.npairs; qb += PF * NT) {
     int qq[PF];
     bool has[PF];
@@ -823,7 +832,7 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
     for (int jb = 0; jb < T; jb++) {
       const int j = tx + 16 * jb;
       const int hi = i > j ? i : j, lo = i > j ? j : i;
-      a[ia][jb] = (hi <= n && lo < n) ? A[(size_t)hi * lda + lo] : 0.0;
+      a[ia][jb] = (ia >= jb && hi <= n && lo < n) ? A[(size_t)hi * lda + lo] : 0.0;      // tiles ia < jb are never used
     }
   }
   PHASE_MARK(1);
@@ -854,6 +863,38 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   }
   double part = 0.0;
   for (int k = tid; k < n; k += NT) part += 0.5 * log(S.piv[k]);
+  // While the first warps take the logarithms of the pivots, four lanes of the LAST warp (no pivots: n + 1 <= 16 T
+  // < NT - 32) evaluate the log-priors of GaussianProcess._nll -- the reference's formulas (nll_finish states them for
+  // one thread) with two lock-step logarithms instead of seven sequential transcendental calls; range-specialised log
+  // and reciprocals (<= 2 ulp).  S.red[32 + 24 .. 26] is not touched until the finish.
+  if ((tid >> 5) == (NT >> 5) - 1 && (tid & 31) < 4) {
+    const int pl = tid & 31;
+    const double s2 = 0.1 * 0.1, vn2 = noise * noise;
+    const double ivn2 = fast_rcp(vn2);
+    const double arg = (pl == 0) ? 1.0 + 3.0 * (s2 * ivn2)
+                     : (pl == 1) ? 3.0 * s2 * ivn2 + 1.0
+                     : (pl == 2) ? c : 2.5066282746310002 * c;
+    const double lg = log_pos(arg);
+    const double lg_b = __shfl_sync(0xfu, lg, 1), lv = __shfl_sync(0xfu, lg, 2), l25 = __shfl_sync(0xfu, lg, 3);
+    if (pl == 0) {
+      // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
+      double lp0, gp0;
+      if (c <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
+      else { lp0 = -(lv * lv) / 2.0 - l25; gp0 = -(1.0 + lv) * fast_rcp(c) * c; }
+      // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
+      double lpn, gpn;
+      if (noise == 0.0) { lpn = INFINITY; gpn = INFINITY; }
+      else {
+        lpn = log_pos(lg + VERY_SMALL_NUMBER);
+        double bq = (3.0 * s2 + vn2) * lg_b;
+        bq = fmax(bq, 1e-14);
+        gpn = -(6.0 * s2) * fast_rcp(bq);
+      }
+      S.red[32 + 24] = lp0 + lpn;
+      S.red[32 + 25] = gp0;
+      S.red[32 + 26] = gpn;
+    }
+  }
   if (tid == 0) part -= 0.5 * S.red[32 + 27];
   PHASE_MARK(3);
   const double nll_data = block_sum(part, S.red);
@@ -929,62 +970,36 @@ __device__ bool nll_eval_reg(const FitWs& S, const SpaceDesc& sp, const double* 
   PHASE_MARK(7);
   const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
   {
-    // one interleaved butterfly over all H slots (independent shuffles pipeline); S.red was last read
-    // before the barrier in front of the W publish, so no barrier is needed here
+    // g0, gn and the da varying columns' sums in COMPACT order through transposed warp reductions (16 values in 16
+    // exchanges; the per-value butterflies were 5 exchanges each behind a branch per column): lanes r < 16 hold the
+    // warp total of value r.  S.red was last read before the barrier in front of the W publish: no barrier here
+    double vals[16];
+    vals[0] = g0; vals[1] = gn;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-      gn += __shfl_xor_sync(0xffffffffu, gn, o);
+    for (int p = 0; p < 14; p++) vals[2 + p] = (p < DMAX) ? gacc[p < DMAX ? p : 0] : 0.0;
+    const double tot = warp_transpose_sum16(vals);
+    if (lane < 16) S.red[wid * 32 + lane] = tot;
+    if constexpr (DMAX > 14) {
 #pragma unroll
-      for (int p = 0; p < DMAX; p++)
-        if (p < da) gacc[p] += __shfl_xor_sync(0xffffffffu, gacc[p], o);      // (uniform: only the varying columns)
-    }
-    if (lane == 0) {
-      S.red[wid * 32 + 0] = g0;
-      S.red[wid * 32 + (d + 1)] = gn;
-      for (int p = 0; p < d; p++) S.red[wid * 32 + 1 + p] = 0.0;          // constant columns: zero gradient
-#pragma unroll
-      for (int q = 0; q < DMAX; q++)
-        if (q < da) S.red[wid * 32 + 1 + S.acol[q]] = gacc[q];
+      for (int p = 0; p < 16; p++) vals[p] = (14 + p < DMAX) ? gacc[14 + p < DMAX ? 14 + p : 0] : 0.0;
+      const double tot2 = warp_transpose_sum16(vals);
+      if (lane < 8) S.red[wid * 32 + 16 + lane] = tot2;       // da <= d <= 22: compact slots 16 .. 23
     }
   }
   __syncthreads();
-  // warp 0 sums the per-warp partials while four lanes of warp 1 evaluate the log-priors of
-  // GaussianProcess._nll (the reference's formulas, operation for operation: nll_finish states them
-  // for one thread) with TWO lock-step log calls instead of seven sequential transcendental calls
+  // warp 0 sums the per-warp partials and applies the final rules
   double gsum = 0.0;
   if (wid == 0) {
-    if (lane < H)
-      for (int w = 0; w < nw; w++) gsum += S.red[w * 32 + lane];       // d LML / d theta_h (without priors)
-  } else if (wid == 1 && lane < 4) {
-    const double s2 = 0.1 * 0.1, vn2 = noise * noise;
-    const double arg = (lane == 0) ? 1.0 + 3.0 * (s2 / vn2)
-                     : (lane == 1) ? 3.0 * s2 * (1.0 / vn2) + 1.0
-                     : (lane == 2) ? c : 2.5066282746310002 * c;
-    const double lg = log(arg);
-    const double lg_b = __shfl_sync(0xfu, lg, 1), lv = __shfl_sync(0xfu, lg, 2), l25 = __shfl_sync(0xfu, lg, 3);
-    if (lane == 0) {
-      // lognormal prior on c (gp_base_prior.py:389-449), sigma = 1, mean = 0
-      double lp0, gp0;
-      if (c <= 0.0) { lp0 = -1e25; gp0 = 0.0; }
-      else { lp0 = -(lv * lv) / 2.0 - l25; gp0 = -(1.0 + lv) / c * c; }
-      // horseshoe prior on s2 (gp_base_prior.py:289-355), scale = 0.1
-      double lpn, gpn;
-      if (noise == 0.0) { lpn = INFINITY; gpn = INFINITY; }
-      else {
-        lpn = log(lg + VERY_SMALL_NUMBER);
-        double bq = (3.0 * s2 + vn2) * lg_b;
-        bq = fmax(bq, 1e-14);
-        gpn = -(6.0 * s2) / bq;
-      }
-      S.red[32 + 24] = lp0 + lpn;
-      S.red[32 + 25] = gp0;
-      S.red[32 + 26] = gpn;
+    if (lane < H) {
+      // theta_h  ->  compact slot: amplitude 0, noise 1, varying column q at 2 + q; constant columns: zero gradient
+      int r = (lane == 0) ? 0 : ((lane == H - 1) ? 1 : -1);
+      for (int q = 0; q < da; q++)
+        if (S.acol[q] == lane - 1 && lane < H - 1) r = 2 + q;
+      if (r >= 0)
+        for (int w = 0; w < nw; w++) gsum += S.red[w * 32 + r];       // d LML / d theta_h (without priors)
     }
-  }
-  __syncthreads();
-  if (wid == 0) {
-    // final sign / finiteness rules of GaussianProcess._nll (gp.py:183-197)
+    // final sign / finiteness rules of GaussianProcess._nll (gp.py:183-197); the log-priors were computed by warp 1
+    // at the start of the evaluation
     const double lml = -nll_data - 0.5 * (double)n * LOG_2PI + S.red[32 + 24];
     if (lane == 0) gsum += S.red[32 + 25];
     if (lane == H - 1) gsum += S.red[32 + 26];

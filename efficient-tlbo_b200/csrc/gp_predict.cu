@@ -76,23 +76,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   asm volatile("trap;");       // never hang the device on a lost transaction
 }
 
-// Sum over the 32 lanes of each of 16 per-lane values: on return lanes r and r + 16 hold sum_lanes v[r].  Recursive
-// halving -- 16 exchanges instead of the 80 of 16 separate butterflies.
-__device__ __forceinline__ double warp_transpose_sum16(double (&v)[16]) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int h = 8; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int r = 0; r < h; r++) {
-      const double send = up ? v[r] : v[r + h];
-      const double keep = up ? v[r + h] : v[r];
-      v[r] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
-
 #define SMALL_WARP_DOUBLES(ncap) ((ncap) + 2 * TLBO_HMAX)
 
 // Posterior of surrogate m at one query row by ONE warp (kbuf: SMALL_WARP_DOUBLES(ncap) doubles of warp-private

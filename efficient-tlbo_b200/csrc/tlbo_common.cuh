@@ -44,6 +44,23 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sum over the 32 lanes of each of 16 per-lane values: on return lanes r and r + 16 hold sum_lanes v[r].  Recursive
+// halving -- 16 exchanges instead of the 80 of 16 separate butterflies.
+__device__ __forceinline__ double warp_transpose_sum16(double (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int r = 0; r < h; r++) {
+      const double send = up ? v[r] : v[r + h];
+      const double keep = up ? v[r + h] : v[r];
+      v[r] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // Block-wide sum; `red` is shared scratch of >= 32 doubles.  All threads get the result.
 __device__ __forceinline__ double block_sum(double v, double* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -81,6 +98,46 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   p = fma(p, r, 1.0);
   const int k = (int)kf;                                // -1022 < k <= 0 here
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// log(x) for finite normal x > 0: x = m 2^e with m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(s), s = (m - 1) / (m + 1)
+// (|s| <= 0.1716: eleven terms of the odd series), the reciprocal from the hardware seed + two Newton steps.
+// Error <= 2 ulp; ~35 FP64 operations on one dependent chain of ~300 cycles where the libm call (special cases,
+// table look-ups, IEEE division) takes 2-3 times as long -- it sits in a phase other warps wait for.
+__device__ __forceinline__ double log_pos(double x) {
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, lo);
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double den = m + 1.0;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  double t = fma(-den, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-den, r, 1.0);
+  r = fma(r, t, r);
+  const double num = m - 1.0;
+  double s = num * r;
+  s = fma(fma(-s, den, num), r, s);                   // one correction step: s = (m - 1) / (m + 1) to < 1 ulp
+  const double z = s * s;
+  double p = 1.0 / 25.0;
+  p = fma(p, z, 1.0 / 23.0);
+  p = fma(p, z, 1.0 / 21.0);
+  p = fma(p, z, 1.0 / 19.0);
+  p = fma(p, z, 1.0 / 17.0);
+  p = fma(p, z, 1.0 / 15.0);
+  p = fma(p, z, 1.0 / 13.0);
+  p = fma(p, z, 1.0 / 11.0);
+  p = fma(p, z, 1.0 / 9.0);
+  p = fma(p, z, 1.0 / 7.0);
+  p = fma(p, z, 1.0 / 5.0);
+  p = fma(p, z, 1.0 / 3.0);
+  const double lm = fma(2.0 * s, z * p, 2.0 * s);     // 2 atanh(s)
+  const double ef = (double)e;
+  return fma(ef, LN2_HI, fma(ef, LN2_LO, lm));
 }
 
 // sqrt(s) for s >= 0 from the hardware reciprocal-square-root seed and two Newton steps
