@@ -396,7 +396,10 @@ __device__ __forceinline__ void sweep_pair_steps(double (&a)[T][T], ElimCtx& c, 
     }
     if (own) {                                                 // one thread of one warp
       const double p11 = a[KB][KB], p12 = a[K2][KB], p22 = a[K2][K2];
-      const double det = fma(p11, p22, -(p12 * p12));
+      // p11 p22 - p12^2 with the rounding error of the square recovered (the conditional variance of the second
+      // pivot is a small difference of O(1) products for strongly correlated rows)
+      const double sq = p12 * p12, sqe = fma(p12, p12, -sq);
+      const double det = fma(p11, p22, -sq) - sqe;
       const double idet = fast_rcp(det);
       *reinterpret_cast<double2*>(buf + 384) = make_double2(p22 * idet, -(p12 * idet));
       *reinterpret_cast<double2*>(buf + 386) = make_double2(p11 * idet, (p11 > 0.0 && det > 0.0) ? 1.0 : -1.0);
