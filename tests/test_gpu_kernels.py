@@ -400,3 +400,71 @@ def test_merge_best_matches_host_rule():
                 assert got[2] < 0
             else:
                 assert (float(got[0]), float(got[1]), int(got[2])) == (want[0], want[1], want[2])
+
+
+@pytest.mark.parametrize('types,ns,N,mode,ncap,nmax', [
+    (RF_TYPES, [50] * 29 + [33], 26, 0, 72, 50),          # the online hill-climb step: staged slabs, rows in the arguments
+    (RF_TYPES, [50] * 5 + [20], 200, 0, 56, 0),           # 1 800 doubles of rows: read through the pointer, nmax unknown
+    (RF_TYPES, [7, 50, 50, 50], 31, 1, 64, 50),           # TST combination (mode 1), first entry initialises
+    (np.zeros(5, int), [100] * 3, 17, 0, 104, 100),       # staging plan beyond the shared-memory budget: global path
+    (np.zeros(20, int), [60, 50], 9, 2, 64, 60),          # POGPE combination (mode 2)
+    (RF_TYPES, [3, 50, 0], 5, 0, 56, 50),                 # an empty slot (n = 0) is dropped
+])
+def test_ensemble_ei_small_matches_oracle_and_fused(types, ns, N, mode, ncap, nmax):
+    """``tlbo_ensemble_ei_small`` (one CTA per (row, surrogate), last CTA of a row combines): EI of a small query set
+    against the oracle's ensemble EI and -- value for value -- against ``tlbo_gp_predict`` + the fused kernel in
+    all-resident mode; the counters are left zero and untouched rows keep their sentinel."""
+    import torch
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(len(ns) * 100 + N)
+    live = [n for n in ns if n > 0]
+    pack, ogs = _fitted_pack(rng, types, live, ncap=ncap)
+    if len(live) < len(ns):                                # append empty slots
+        full = ops.SurrogatePack(len(ns), ncap, len(types))
+        for m in range(len(live)):
+            full.copy_slot_from(m, pack, m)
+        pack = full
+    M = len(ns)
+    w = rng.rand(M) + 0.1
+    skip = np.zeros(M, dtype=np.int32)
+    if mode == 0:
+        w = w / w.sum()
+        if M > 3:
+            skip[1] = 1
+    order = np.arange(M, dtype=np.int32)
+    if mode == 0 and M > 2:
+        order = np.concatenate([[M - 1], np.arange(M - 1)]).astype(np.int32)      # RGPE: target first
+        if ns[-1] == 0:
+            order = np.arange(M, dtype=np.int32)
+    Xq, _ = _data(rng, N, types)
+    Xq[0] = ogs[0].X[0]                                    # a training row: variance cancellation path
+    eta = float(np.min(ogs[-1].y)) * ogs[-1].std_y + ogs[-1].mean_y
+    dev = torch.device('cuda')
+    dw, dskip, dorder = (torch.from_numpy(a).to(dev) for a in (w, skip, order))
+    sq = ops.SmallQuery(max(256, N), len(types), M)
+    sq.X_np[:N] = Xq
+    sq.ei_np[:] = -7.0
+    pack.c.nmax = nmax
+    ops.ensemble_ei_small(pack, types, dw, dskip, dorder, mode, sq, N, eta, 0.0, 1e-10)
+    ops.stream_synchronize()
+    got = sq.ei_np[:N].copy()
+    assert np.all(sq.ei_np[N:] == -7.0)
+    assert int(sq.counter.abs().sum().item()) == 0
+    # (a) the same posteriors through tlbo_gp_predict and the fused kernel in all-resident mode
+    Xd = torch.from_numpy(Xq).to(dev)
+    mu, var = ops.gp_predict(pack, types, Xd)
+    logical = ops.SurrogatePack(M, 8, len(types))
+    logical.n.copy_(pack.n.clamp(max=1))
+    res, _, _, ei2 = ops.predict_ei_fused(logical, types, dw, dskip, Xd, eta, var_floor=1e-10, mode=mode, order=dorder,
+                                          want_rows=True, nmax=8, cache=(mu, var))
+    np.testing.assert_allclose(got, ei2.cpu().numpy(), rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(sq.mu[:M * N].view(M, N).cpu().numpy(), mu.cpu().numpy(), rtol=1e-10, atol=1e-12)
+    # (b) the oracle (modes 0 / 1; accumulation order does not change the value beyond rounding)
+    if mode in (0, 1) and 0 not in ns:
+        ens = _Ens(ogs, w, skip if mode == 0 else None, mode, 1e-10)
+        if mode == 1:
+            ens = _Ens([ogs[i] for i in order], w[order], None, 1, 1e-10)
+        ei_o = OracleEI(ens)
+        ei_o.update(eta=eta)
+        acq = ei_o(Xq).ravel()
+        np.testing.assert_allclose(got, acq, rtol=RTOL, atol=1e-12 + 1e-6 * acq.max())
