@@ -91,6 +91,68 @@ extern "C" int tlbo_rank_loss_counts_normal(const double* d_y, const double* d_z
 }
 
 // ---------------------------------------------------------------------------------------
+// RGPE weights from the pair-count table, on the device (reference tlbo/facade/rgpe.py:106-133): losses[s][k] =
+// counts[s][k] for the K sources and the sum of the fold counts for the target (n^2 when there are no folds);
+// w_k = #{s : argmin_k' losses[s][k'] == k} / S (np.argmin: first minimum); a source is ignored when the median of
+// its losses exceeds the 95th-percentile loss of the target (sorted(column)[int(S * 0.5)] > sorted(target)[int(S *
+// 0.95)]).  Integer arithmetic and one division per weight: the same doubles as numpy.  One CTA; it lets the fused
+// predict + EI launch follow the count kernel on the stream without a host round trip (the host recomputes the same
+// table later for its own bookkeeping).
+#define RW_MAXS 32
+#define RW_MAXM 127
+
+__global__ void __launch_bounds__(128) rgpe_weights_kernel(const int64_t* __restrict__ counts, int S, int K, int n_folds,
+                                                           long long n_sq, double* __restrict__ w,
+                                                           int32_t* __restrict__ skip) {
+  __shared__ long long L[RW_MAXS][RW_MAXM + 1];
+  __shared__ int hist[RW_MAXM + 1];
+  __shared__ long long thr;
+  const int tid = threadIdx.x, M = K + 1, Mr = K + n_folds;
+  for (int idx = tid; idx < S * M; idx += blockDim.x) {
+    const int s = idx / M, k = idx - s * M;
+    long long v;
+    if (k < K) v = counts[(size_t)s * Mr + k];
+    else if (n_folds == 0) v = n_sq;
+    else { v = 0; for (int f = 0; f < n_folds; f++) v += counts[(size_t)s * Mr + K + f]; }
+    L[s][k] = v;
+  }
+  for (int k = tid; k < M; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  for (int s = tid; s < S; s += blockDim.x) {
+    int best = 0;
+    for (int k = 1; k < M; k++) if (L[s][k] < L[s][best]) best = k;
+    atomicAdd(&hist[best], 1);
+  }
+  // order statistic r of column k: the value x with #less <= r < #less + #equal
+  auto kth = [&](int k, int r) -> long long {
+    for (int i = 0; i < S; i++) {
+      const long long x = L[i][k];
+      int less = 0, eq = 0;
+      for (int j = 0; j < S; j++) { less += L[j][k] < x; eq += L[j][k] == x; }
+      if (less <= r && r < less + eq) return x;
+    }
+    return 0;
+  };
+  if (tid == 0) thr = kth(K, (int)(S * 0.95));
+  __syncthreads();
+  for (int k = tid; k < M; k += blockDim.x) {
+    w[k] = (double)hist[k] / (double)S;
+    skip[k] = (k < K && kth(k, (int)(S * 0.5)) > thr) ? 1 : 0;
+  }
+}
+
+extern "C" int tlbo_rgpe_weights(const int64_t* d_counts, int S, int K, int n_folds, int64_t n_sq, double* d_w,
+                                 int32_t* d_skip, void* stream) {
+  if (!d_counts || !d_w || !d_skip || S <= 0 || S > RW_MAXS || K < 0 || K + 1 > RW_MAXM + 1 || n_folds < 0) {
+    tlbo_set_error("tlbo_rgpe_weights: bad arguments");
+    return TLBO_E_BADARG;
+  }
+  rgpe_weights_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(d_counts, S, K, n_folds, (long long)n_sq, d_w, d_skip);
+  TLBO_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 #define PL_THREADS 256
 #define PL_MAXM 64
 

@@ -63,6 +63,7 @@ SYMBOLS = {
                                         c_int, c_double, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     'tlbo_ensemble_ei_small': (c_int, [POINTER(TlboPack), _P, _P, _P, _P, c_int, _P, _P, c_int, c_double, c_double,
                                        c_double, _P, _P, _P, _P, _P]),
+    'tlbo_rgpe_weights': (c_int, [_P, c_int, c_int, c_int, c_int64, _P, _P, _P]),
     'tlbo_pair_penalty_loss_normal': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     'tlbo_mt19937_random_sample': (c_int, [_P, c_int64, _P, _P]),
     'tlbo_mt19937_jump': (c_int, [_P, _P, c_int, _P, _P, c_int, _P]),

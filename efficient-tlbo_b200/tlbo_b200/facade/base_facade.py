@@ -248,13 +248,22 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         kernel; subclasses override."""
         return np.asarray(self.w, dtype=np.float64), None, None
 
+    def _ensemble_args_dev(self):
+        """``_ensemble_args`` as device tensors (host arrays go through the small-constant upload cache; a facade
+        whose weights were formed on the device hands its tensors through)."""
+        from tlbo_b200 import ops
+
+        def dev(a, dt):
+            if a is None or hasattr(a, 'data_ptr'):
+                return a
+            return ops.cached_upload(np.ascontiguousarray(a, dtype=dt))
+        w, skip, order = self._ensemble_args()
+        return dev(w, np.float64), dev(skip, np.int32), dev(order, np.int32)
+
     def _fused(self, X_dev, eta=0.0, par=0.0, var_floor=0.0, keys=None, excluded=None, idx_offset=0,
                want_rows=False, ws=None, sync=True):
         from tlbo_b200 import ops
-        w, skip, order = self._ensemble_args()
-        dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
-        dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
-        dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+        dw, dskip, dorder = self._ensemble_args_dev()
         N = int(X_dev.shape[0])
         if getattr(self.types, 'has_conditions', False) and self._G == 1:
             # a space with conditional hyper-parameters: every kernel value carries the activity mask of
@@ -329,10 +338,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
         # (this path runs a few hundred times per online BO iteration)
         ens = self._ens_cache
         if ens is None or ens[0] is not self._pack:
-            w, skip, order = self._ensemble_args()
-            dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
-            dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
-            dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+            dw, dskip, dorder = self._ensemble_args_dev()
             ens = self._ens_cache = (self._pack, dw, dskip, dorder, ops.pack_view(self._pack, 0, self.K + 1))
         _, dw, dskip, dorder, view = ens
         view.c.nmax = self._nmax()
@@ -366,10 +372,7 @@ class BaseFacade(object, metaclass=abc.ABCMeta):
             sq = self._small = ops.SmallQuery(max(256, cap), d, self.K + 1)
         ens = self._ens_cache
         if ens is None or ens[0] is not self._pack:
-            w, skip, order = self._ensemble_args()
-            dw = ops.cached_upload(np.ascontiguousarray(w, dtype=np.float64))
-            dskip = None if skip is None else ops.cached_upload(np.ascontiguousarray(skip, dtype=np.int32))
-            dorder = None if order is None else ops.cached_upload(np.ascontiguousarray(order, dtype=np.int32))
+            dw, dskip, dorder = self._ensemble_args_dev()
             ens = self._ens_cache = (self._pack, dw, dskip, dorder, ops.pack_view(self._pack, 0, self.K + 1))
         _, dw, dskip, dorder, view = ens
         view.c.nmax = self._nmax()

@@ -27,6 +27,11 @@ class _BootstrapRankingFacade(BaseFacade):
     def _ranking_losses(self, X, y):
         """Everything of rgpe.py:24-109 up to (and including) the loss table
         ``int64[num_sample, K + 1]`` and the arg-min histogram."""
+        return self._ranking_finish(self._ranking_enqueue(X, y))
+
+    def _ranking_enqueue(self, X, y):
+        """Device half: the batched fit, the K + folds predicts at the target points and the pair counts are
+        ENQUEUED; returns what ``_ranking_finish`` needs to read them back."""
         import torch
         from tlbo_b200 import ops
         K = self.K
@@ -109,8 +114,21 @@ class _BootstrapRankingFacade(BaseFacade):
         # K source predicts + fold predicts at the target points (one launch), pair counts
         mu_dev, var_dev = self._predict_slots(0, K + 1 + n_folds, X_dev)
         counts_dev = ops.rank_loss_counts_normal(y_dev, z_dev, mu_dev, var_dev, src_dev, lo_dev, hi_dev, sync=False)
-        finish_fit()                                   # first synchronisation of the iteration
-        counts = ops.d2h(counts_dev)
+        return dict(finish_fit=finish_fit, counts_dev=counts_dev, n_folds=n_folds, instance_num=instance_num,
+                    native=native, counts_host=None, counts_event=None)
+
+    def _ranking_finish(self, pend):
+        """Host half: fit status / theta and the count table read back (the first synchronisation of the
+        iteration, or pinned snapshots taken earlier), loss table and arg-min histogram."""
+        from tlbo_b200 import ops
+        K, S = self.K, self.num_sample
+        n_folds, instance_num = pend['n_folds'], pend['instance_num']
+        pend['finish_fit']()
+        if pend['counts_host'] is not None:
+            pend['counts_event'].synchronize()
+            counts = pend['counts_host'].numpy()
+        else:
+            counts = ops.d2h(pend['counts_dev'])
         losses = np.empty((S, K + 1), dtype=np.int64)
         losses[:, :K] = counts[:, :K]
         losses[:, K] = counts[:, K:].sum(axis=1) if n_folds else instance_num * instance_num
@@ -157,7 +175,77 @@ class RGPE(_BootstrapRankingFacade):
         self._init_common(only_source)
         self.w = [1. / self.K] * self.K + [0.]
 
+    # ---- deferred host bookkeeping -------------------------------------------------------------------------
+    # The weights and dilution flags the NEXT launch needs are formed on the device (tlbo_rgpe_weights) right behind
+    # the pair counts, so the fused predict + EI launch follows without a host round trip; the host's own copies
+    # (w, ignored_flag, hist_ws, target_weight, the fitted theta of the models) are brought up to date from pinned
+    # snapshots later -- under the NEXT iteration's fit, or the moment anything reads them.
+    defer_host_weights = True
+    _LAZY = ('w', 'ignored_flag', 'hist_ws', 'target_weight', 'last_losses', 'iteration_id')
+
+    def _resolve(self):
+        pend = self.__dict__.get('_pending')
+        if pend is not None:
+            self.__dict__['_pending'] = None
+            self._apply_weights(*self._ranking_finish(pend)[:2])
+
+    def _ensemble_args(self):
+        pend = self.__dict__.get('_pending')
+        if pend is not None:
+            return pend['w_dev'], pend['skip_dev'], self._order_dev()
+        return super()._ensemble_args()
+
+    def _order_dev(self):
+        from tlbo_b200 import ops
+        return ops.cached_upload(np.array([self.K] + list(range(self.K)), dtype=np.int32))
+
+    def _apply_weights(self, losses, argmin_list):
+        for id in range(self.K + 1):
+            self.w[id] = argmin_list[id] / self.num_sample
+        self._dilution_flags(losses)
+        self._log_weights()
+
     def train(self, X, y):
+        if self.defer_host_weights and not self.only_source:
+            import torch
+            from tlbo_b200 import ops
+            prev = self.__dict__.get('_pending')
+            self.__dict__['_pending'] = None
+            pend = self._ranking_enqueue(X, y)
+            snap = getattr(pend['finish_fit'], 'snapshot_async', None)
+            if snap is None:                                # numpy host-prep path: no snapshot facility
+                if prev is not None:
+                    self._apply_weights(*self._ranking_finish(prev)[:2])
+                self._apply_weights(*self._ranking_finish(pend)[:2])
+                return
+            n = pend['instance_num']
+            bufs = self.__dict__.get('_wbufs')
+            if bufs is None:
+                dev = pend['counts_dev'].device
+                bufs = self.__dict__['_wbufs'] = [
+                    (torch.zeros(self.K + 1, dtype=torch.float64, device=dev),
+                     torch.zeros(self.K + 1, dtype=torch.int32, device=dev)) for _ in range(2)]
+                self.__dict__['_wflip'] = 0
+            self.__dict__['_wflip'] ^= 1
+            pend['w_dev'], pend['skip_dev'] = ops.rgpe_weights(pend['counts_dev'], self.K, pend['n_folds'], n * n,
+                                                               bufs[self.__dict__['_wflip']])
+            # pinned snapshots of everything the host will want (status, theta, counts), behind the kernels above
+            snap()
+            ch = torch.empty(pend['counts_dev'].shape, dtype=torch.int64, pin_memory=True)
+            ch.copy_(pend['counts_dev'], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pend['counts_host'], pend['counts_event'] = ch, ev
+            ops.STATS.d2h += ch.numel() * 8
+            self._ens_cache = None
+            self.__dict__['_pending'] = pend
+            if prev is not None:
+                # the PREVIOUS iteration's host bookkeeping, while the device runs this iteration's fit
+                self.__dict__['_pending'] = None
+                self._apply_weights(*self._ranking_finish(prev)[:2])
+                self.__dict__['_pending'] = pend
+            return
+        self._resolve()
         losses, argmin_list, _ = self._ranking_losses(X, y)
         for id in range(self.K + 1):
             self.w[id] = argmin_list[id] / self.num_sample
@@ -169,6 +257,25 @@ class RGPE(_BootstrapRankingFacade):
             else:
                 self.w[:-1] = np.array(self.w[:-1]) / np.sum(self.w[:-1])
         self._log_weights()
+
+
+def _lazy_property(name):
+    key = '_lz_' + name
+
+    def getter(self):
+        if self.__dict__.get('_pending') is not None:
+            self._resolve()
+        return self.__dict__[key]
+
+    def setter(self, value):
+        if self.__dict__.get('_pending') is not None:
+            self._resolve()
+        self.__dict__[key] = value
+    return property(getter, setter)
+
+
+for _name in RGPE._LAZY:                 # data descriptors: every other attribute keeps the plain fast path
+    setattr(RGPE, _name, _lazy_property(_name))
 
 
 class TransBO_RGPE(_BootstrapRankingFacade):

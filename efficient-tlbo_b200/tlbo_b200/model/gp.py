@@ -224,13 +224,35 @@ def fit_prepared_async(models, prep):
         assert mdl._pack is m0._pack and mdl._slot == m0._slot + b and mdl.normalize_y
         assert mdl._start_points() is p0 or np.array_equal(mdl._start_points(), p0)
         mdl.mean_y_, mdl.std_y_ = float(prep.ymean[b]), float(prep.ystd[b])
+        mdl.n_train_ = int(prep.n[b])          # known now: the kernels' shared-memory plans are sized by it before finish()
     lb = m0.kernel.bounds
     h = ops.gp_fit_batched(None, None, m0.types, p0, lb[:, 0], lb[:, 1], None, None, m0._pack, slot0=m0._slot,
                            sync=False, prepared=prep)
 
+    snap = {}
+
+    def snapshot_async():
+        """Enqueue pinned copies of the fit's status and fitted theta NOW (behind the fit on the current stream):
+        ``finish`` then reads those instead of the pack -- it may run after the pack slots have been refitted and
+        never waits for work enqueued later."""
+        import torch
+        st_h = torch.empty(h.status.shape, dtype=h.status.dtype, pin_memory=True)
+        th_dev = m0._pack.theta[m0._slot:m0._slot + len(models)]
+        th_h = torch.empty(th_dev.shape, dtype=th_dev.dtype, pin_memory=True)
+        st_h.copy_(h.status, non_blocking=True)
+        th_h.copy_(th_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        snap.update(st=st_h, th=th_h, ev=ev)
+        ops.STATS.d2h += st_h.numel() * st_h.element_size() + th_h.numel() * 8
+
     def finish():
-        st = h.finish()
-        thetas = ops.d2h(m0._pack.theta[m0._slot:m0._slot + len(models)])
+        if snap:
+            snap['ev'].synchronize()
+            st, thetas = snap['st'].numpy(), snap['th'].numpy()
+        else:
+            st = h.finish()
+            thetas = ops.d2h(m0._pack.theta[m0._slot:m0._slot + len(models)])
         lazy = _LazyFitInfo(h)
         for b, mdl in enumerate(models):
             if st[b] == 1:
@@ -243,6 +265,7 @@ def fit_prepared_async(models, prep):
             mdl.n_train_ = int(prep.n[b])
             mdl.fit_info_ = _FitInfoView(lazy, b)
         return models
+    finish.snapshot_async = snapshot_async
     return finish
 
 

@@ -590,6 +590,17 @@ def rank_loss_counts_normal(y, z, loc, scale, src, row_lo, row_hi, sync=True):
     return d2h(counts)
 
 
+def rgpe_weights(counts, K, n_folds, n_sq, out):
+    """``tlbo_rgpe_weights``: RGPE weights and weight-dilution flags from the device pair-count table
+    ``counts int64[S, K + n_folds]`` into ``out = (w float64[K + 1], skip int32[K + 1])`` (device tensors)."""
+    w, skip = out
+    S = int(counts.shape[0])
+    assert counts.is_contiguous() and int(counts.shape[1]) == K + n_folds and w.numel() == K + 1 == skip.numel()
+    with _call('rgpe_weights', 1):
+        check(lib.tlbo_rgpe_weights(ptr(counts), S, int(K), int(n_folds), int(n_sq), ptr(w), ptr(skip), _stream()))
+    return w, skip
+
+
 def pair_penalty_loss_normal(y, z, loc, scale, sync=True):
     """``tlbo_pair_penalty_loss_normal`` (OBTL's sampled ranking loss): y [n], z [S, Mr, n] device or host,
     loc / scale [Mr, n] device -> loss float64[S, Mr]."""

@@ -195,6 +195,16 @@ int tlbo_predict_ei_fused_cached(const tlbo_pack* pack, const int32_t* h_types, 
 int tlbo_rank_loss_counts(const double* d_y, const double* d_ys, int n, int S, int Mr, const int32_t* d_row_lo,
                           const int32_t* d_row_hi, int upper_only, int64_t* d_counts, void* stream);
 
+/* RGPE weights and weight-dilution flags from the pair-count table, on the device -- replaces the host tail of
+ * RGPE.train (tlbo/facade/rgpe.py:106-133: np.argmin per bootstrap sample, the histogram / num_sample, and
+ * `median(source losses) > sorted(target losses)[int(0.95 S)]`), so that the fused predict + EI launch can follow the
+ * count kernel on the stream without a host round trip.
+ *   d_counts [S, K + n_folds] int64 (tlbo_rank_loss_counts[_normal]); target loss = sum of its fold columns, or
+ *   n_sq when n_folds == 0 (rgpe.py:84-87); d_w [K + 1] = histogram / S; d_skip [K + 1] int32 (1 = ignored source,
+ *   0 for the target).  Bit-exact against numpy (integer arithmetic, one division per weight).  S <= 32, K <= 127. */
+int tlbo_rgpe_weights(const int64_t* d_counts, int S, int K, int n_folds, int64_t n_sq, double* d_w, int32_t* d_skip,
+                      void* stream);
+
 /* Same counts with the bootstrap draws formed on the device: d_z [S, Mr, n] are STANDARD normal
  * draws (host, legacy np.random stream, reference draw order); the sampled values of
  * rgpe.py:77,97  np.random.normal(mu, var)  are loc + scale * z with loc = d_loc[d_src[m]],

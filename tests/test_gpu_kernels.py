@@ -468,3 +468,26 @@ def test_ensemble_ei_small_matches_oracle_and_fused(types, ns, N, mode, ncap, nm
         ei_o.update(eta=eta)
         acq = ei_o(Xq).ravel()
         np.testing.assert_allclose(got, acq, rtol=RTOL, atol=1e-12 + 1e-6 * acq.max())
+
+
+@pytest.mark.parametrize('S,K,n_folds,n', [(30, 29, 5, 41), (30, 3, 0, 4), (30, 29, 5, 75), (7, 1, 2, 10)])
+def test_rgpe_weights_kernel_bit_exact(S, K, n_folds, n):
+    """``tlbo_rgpe_weights`` against numpy's statement of rgpe.py:106-133 (np.argmin ties, histogram / num_sample,
+    median-vs-95th-percentile dilution flags) on count tables with many ties."""
+    import torch
+    from tlbo_b200 import ops
+    rng = np.random.RandomState(S * 100 + K)
+    for trial in range(6):
+        hi = [n * n, 40, 3, 2][trial % 4]                       # small ranges: many exact ties
+        counts = rng.randint(0, hi + 1, size=(S, K + n_folds)).astype(np.int64)
+        losses = np.empty((S, K + 1), dtype=np.int64)
+        losses[:, :K] = counts[:, :K]
+        losses[:, K] = counts[:, K:].sum(axis=1) if n_folds else n * n
+        w_want = np.bincount(np.argmin(losses, axis=1), minlength=K + 1) / S
+        srt = np.sort(losses, axis=0)
+        skip_want = np.array([bool(m > srt[int(S * 0.95), -1]) for m in srt[int(S * 0.5), :K]] + [False], dtype=np.int32)
+        w = torch.zeros(K + 1, dtype=torch.float64, device='cuda')
+        skip = torch.zeros(K + 1, dtype=torch.int32, device='cuda')
+        ops.rgpe_weights(torch.from_numpy(counts).cuda(), K, n_folds, n * n, (w, skip))
+        assert np.array_equal(w.cpu().numpy(), w_want), trial
+        assert np.array_equal(skip.cpu().numpy(), skip_want), trial
