@@ -123,21 +123,24 @@ __global__ void __launch_bounds__(128) rgpe_weights_kernel(const int64_t* __rest
     for (int k = 1; k < M; k++) if (L[s][k] < L[s][best]) best = k;
     atomicAdd(&hist[best], 1);
   }
-  // order statistic r of column k: the value x with #less <= r < #less + #equal
+  // order statistic r of column k by ONE WARP (S <= 32: lane i ranks sample i against the column): the value x with
+  // #less <= r < #less + #equal
+  const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   auto kth = [&](int k, int r) -> long long {
-    for (int i = 0; i < S; i++) {
-      const long long x = L[i][k];
-      int less = 0, eq = 0;
-      for (int j = 0; j < S; j++) { less += L[j][k] < x; eq += L[j][k] == x; }
-      if (less <= r && r < less + eq) return x;
-    }
-    return 0;
+    const long long x = (lane < S) ? L[lane][k] : 0;
+    int less = 0, eq = 0;
+    for (int j = 0; j < S; j++) { const long long v = L[j][k]; less += v < x; eq += v == x; }
+    const unsigned hit = __ballot_sync(0xffffffffu, lane < S && less <= r && r < less + eq);
+    return __shfl_sync(0xffffffffu, x, __ffs(hit) - 1);
   };
-  if (tid == 0) thr = kth(K, (int)(S * 0.95));
+  if (wid == 0) { const long long t = kth(K, (int)(S * 0.95)); if (lane == 0) thr = t; }
   __syncthreads();
-  for (int k = tid; k < M; k += blockDim.x) {
-    w[k] = (double)hist[k] / (double)S;
-    skip[k] = (k < K && kth(k, (int)(S * 0.5)) > thr) ? 1 : 0;
+  for (int k = wid; k < M; k += nw) {
+    const long long med = (k < K) ? kth(k, (int)(S * 0.5)) : 0;
+    if (lane == 0) {
+      w[k] = (double)hist[k] / (double)S;
+      skip[k] = (k < K && med > thr) ? 1 : 0;
+    }
   }
 }
 
