@@ -907,3 +907,19 @@ class OracleSGPR(OracleFacade):
         idx = [self.index_mapper[self._key(x)] for x in X]
         return (np.array(self.cached_stacking_mu[idx]).reshape(-1, 1),
                 np.array(self.cached_stacking_sigma[idx]).reshape(-1, 1))
+
+
+class OracleRandomSearch(OracleFacade):
+    """tlbo/facade/random_surrogate.py:5-19: ``predict`` is ``rng.rand(n, 1)`` with variance 1e-5."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, literal_loops)
+        self.method_id = 'rs'
+        self.rng = np.random.RandomState(seed)
+
+    def train(self, X, y):
+        pass
+
+    def predict(self, X):
+        n = X.shape[0]
+        return self.rng.rand(n, 1), np.array([1e-5] * n).reshape(-1, 1)

@@ -520,3 +520,23 @@ def test_cuda_sgpr_with_device_fit_tracks_reference():
     assert same >= 4
     span = tables[0][1].max() - tables[0][1].min()
     assert min(smbo.perfs) <= D['perfs'].min() + 0.05 * span
+
+
+def test_cuda_random_search_baseline_matches_reference():
+    """``--methods rs`` on the device path: the facade's MT19937 stream is generated on the device (bit-identical to
+    numpy) and scored by the fused kernel in all-resident mode -- rows, perfs and the generator's final state of the
+    reference's own run (fixture reference_v7_rs.npz)."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.random_surrogate import RandomSearch
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v7_rs.npz'))
+    cs = TableSpace(D['types'])
+    fac = RandomSearch(cs, [], D['X'], int(D['seed']), surrogate_type='gp')
+    smbo = SMBO_OFFLINE((D['X'], D['y']), cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                        random_seed=int(D['seed']), max_runs=100)
+    for _ in D['rows']:
+        smbo.iterate()
+    assert smbo.configurations == D['rows'].tolist()
+    np.testing.assert_array_equal(np.asarray(smbo.perfs), D['perfs'])
+    st = fac.rng.get_state()
+    assert np.array_equal(st[1], D['rng_key']) and st[2] == int(D['rng_pos'])

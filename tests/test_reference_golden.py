@@ -350,3 +350,15 @@ def test_sgpr_matches_reference(monkeypatch):
     mu, var = fac.predict(tables[0][0][:64])
     np.testing.assert_allclose(mu, D['final_mu'], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(var, D['final_var'], rtol=1e-6, atol=1e-12)
+
+
+def test_random_search_baseline_matches_reference():
+    """``--methods rs`` (facade/random_surrogate.py) against a run of the reference itself (fixture
+    reference_v7_rs.npz): selected rows, perfs and the facade generator's final state."""
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v7_rs.npz'))
+    fac = ofacade.OracleRandomSearch(D['types'], [], int(D['seed']))
+    smbo = OracleSMBOOffline(D['X'], D['y'], fac, int(D['seed']), initial_runs=3)
+    for it, row in enumerate(D['rows']):
+        assert smbo.iterate() == int(row), it
+    st = fac.rng.get_state()
+    assert np.array_equal(st[1], D['rng_key']) and st[2] == int(D['rng_pos'])
