@@ -212,6 +212,11 @@ class OBTL(OBTLV):
         self.method_id = 'obtl'
         self.last_sample_losses = None
 
+    def _source_weights_for_update(self):
+        """obtl.py:46: ``w_source = self.w[:self.K]`` -- a VIEW: the in-place ``w_source *= (1 - w_target)`` below also
+        scales the OLD weights that enter the exponential smoothing (kept as the reference has it)."""
+        return self.w[:self.K]
+
     def train(self, X, y):
         import torch
         from tlbo_b200 import ops
@@ -256,7 +261,7 @@ class OBTL(OBTLV):
         if do_cv:
             mu_cv_dev, var_cv_dev = self._predict_slots(K + 1, len(folds), X_dev)
         finish_fit()
-        w_source = self.w[:K]
+        w_source = self._source_weights_for_update()
         w_target = 0.
         if do_cv:
             # cross-validated target posterior: fold i's model at its own validation rows (obtl.py:73-93)
@@ -280,3 +285,58 @@ class OBTL(OBTLV):
         self.w = rho * w_new + (1 - rho) * self.w
         self.hist_ws.append(self.w.copy())
         self.iteration_id += 1
+
+
+class ES(OBTL):
+    """``--methods es`` (reference tlbo/facade/obtl_es.py:9-214, tools/offline_benchmark.py:290-291): OBTL with the
+    source weights chosen by greedy ENSEMBLE SELECTION instead of the SLSQP solve -- 50 rounds, each adding the source
+    surrogate whose inclusion gives the mean prediction ``mean(ensemble + [mu_i])`` the smallest soft ranking loss
+    (``calculate_ranking_loss``, the ``pair_penalty_kernel`` with zero spread: one launch scores all K candidates of
+    a round); weights = selection counts / 50.  Target weight by sampling, smoothing (rho = 0.6) as OBTL -- except
+    that ``w_source`` is a fresh array here, so the old weights enter the smoothing unscaled (obtl_es.py:82-97)."""
+
+    def __init__(self, config_space, source_hpo_data, target_hp_configs, seed, surrogate_type='gp',
+                 num_src_hpo_trial=50, fusion_method='idp_lc', **kw):
+        super().__init__(config_space, source_hpo_data, target_hp_configs, seed, surrogate_type=surrogate_type,
+                         num_src_hpo_trial=num_src_hpo_trial, fusion_method=fusion_method, **kw)
+        self.method_id = 'es'
+        self._es_w_source = None
+        self.last_selection = None
+
+    def learn_source_weights(self, pred_y, true_y):
+        """obtl_es.py:61-87.  ``pred_y [n, K]``: the source surrogates' means at the target points."""
+        import torch
+        from tlbo_b200 import ops
+        base = np.ascontiguousarray(np.asarray(pred_y, dtype=np.float64).T)          # [K, n]
+        K, n = base.shape
+        y = np.ascontiguousarray(np.asarray(true_y, dtype=np.float64).reshape(-1))
+        y_dev = ops.h2d(y)
+        base_dev = ops.h2d(base)
+        zero = torch.zeros(1, K, n, dtype=torch.float64, device=base_dev.device)
+        run = torch.zeros(n, dtype=torch.float64, device=base_dev.device)             # running sum of the ensemble
+        picks = []
+        for m in range(self.ensemble_size):
+            # np.mean(ensemble + [mu_i], axis=0): the rows added in order, then one division by the count
+            cand = base_dev if m == 0 else (run[None, :] + base_dev) / float(m + 1)
+            losses = ops.pair_penalty_loss_normal(y_dev, zero, cand.contiguous(), zero[0])
+            idx = int(np.argmin(losses[0]))
+            picks.append(idx)
+            run = run + base_dev[idx] if m else base_dev[idx].clone()
+        w_source = np.zeros(K)
+        for idx in picks:
+            w_source[idx] += 1
+        self._es_w_source = w_source / np.sum(w_source)
+        self.last_selection = picks
+
+    def _source_weights_for_update(self):
+        return self._es_w_source
+
+    def _ensemble_args(self):
+        # obtl_es.py:190-207: the target first, then the sources with a POSITIVE weight in order
+        w = np.asarray(self.w, dtype=np.float64)
+        skip = np.array([0 if w[i] > 0 else 1 for i in range(self.K)] + [0], dtype=np.int32)
+        order = np.array([self.K] + list(range(self.K)), dtype=np.int32)
+        return w, skip, order
+
+    def predict(self, X):
+        return self._predict_rows(X, 0.0)

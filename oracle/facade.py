@@ -923,3 +923,66 @@ class OracleRandomSearch(OracleFacade):
     def predict(self, X):
         n = X.shape[0]
         return self.rng.rand(n, 1), np.array([1e-5] * n).reshape(-1, 1)
+
+
+class OracleES(OracleOBTL):
+    """tlbo/facade/obtl_es.py (``--methods es``): source weights by greedy ensemble selection over the soft ranking
+    loss (:61-87), target weight by sampling, rho = 0.6; ``predict`` accumulates the target first and then the
+    sources with a positive weight (:190-207)."""
+
+    def __init__(self, types, source_hpo_data, seed, num_src_hpo_trial=50, fusion_method='idp_lc', literal_loops=False):
+        super().__init__(types, source_hpo_data, seed, num_src_hpo_trial, fusion_method, literal_loops)
+        self.method_id = 'es'
+        self.last_selection = None
+
+    def train(self, X, y):
+        """obtl_es.py:54-106."""
+        instance_num = X.shape[0]
+        self.target_surrogate = self.build_single_surrogate(X, y, normalize='standardize')
+        self.target_y_range = 0.5 * (np.max(y) - np.min(y))
+        base_predictions, surrogate_ensemble, surrogate_idx = [], [], []
+        for i in range(self.K):
+            mean, _ = self.source_surrogates[i].predict(X)
+            base_predictions.append(mean.flatten())
+        for _ in range(self.ensemble_size):
+            loss_list = []
+            for i in range(self.K):
+                if len(surrogate_ensemble) == 0:
+                    _predictions = base_predictions[i]
+                else:
+                    _predictions = np.mean(surrogate_ensemble + [base_predictions[i]], axis=0)
+                loss_list.append(obtl_ranking_loss(_predictions, y, self.literal_loops))
+            argmin_idx = np.argmin(loss_list)
+            surrogate_ensemble.append(base_predictions[argmin_idx])
+            surrogate_idx.append(int(argmin_idx))
+        self.last_selection = surrogate_idx
+        w_source = np.zeros(self.K)
+        for idx in surrogate_idx:
+            w_source[idx] += 1
+        w_source = w_source / np.sum(w_source)
+        w_target = 0.
+        if instance_num >= self.min_num_y:
+            w_target = self.calculate_weight_by_sampling(X, y)
+            if instance_num >= 2 * self.min_num_y:
+                w_target = np.max([w_target, self.w[-1]])
+            w_source *= (1 - w_target)
+        w_new = np.asarray(list(w_source) + [w_target])
+        rho = 0.6
+        self.w = rho * w_new + (1 - rho) * self.w
+        self.hist_ws.append(self.w.copy())
+        self.iteration_id += 1
+
+    def predict(self, X):
+        w = self.w.copy()
+        if self.target_surrogate is not None:
+            mu, var = self.target_surrogate.predict(X)
+        else:
+            mu, var = np.zeros((X.shape[0], 1)), np.zeros((X.shape[0], 1))
+        mu *= w[-1]
+        var *= (w[-1] * w[-1])
+        for i in range(0, self.K):
+            if w[i] > 0:
+                mu_t, var_t = self.source_surrogates[i].predict(X)
+                mu += (w[i] * mu_t)
+                var += (w[i] * w[i] * var_t)
+        return mu, var

@@ -540,3 +540,40 @@ def test_cuda_random_search_baseline_matches_reference():
     np.testing.assert_array_equal(np.asarray(smbo.perfs), D['perfs'])
     st = fac.rng.get_state()
     assert np.array_equal(st[1], D['rng_key']) and st[2] == int(D['rng_pos'])
+
+
+def test_cuda_ensemble_selection_facade_matches_reference(monkeypatch):
+    """``--methods es`` on the device path (fixture reference_v8_es.npz, the reference's own run): the greedy
+    ensemble selection scored by the pair-penalty kernel, the sampled target weight, the target-first accumulation
+    with positive-weight sources -- rows, weight history, np.random states and the final posterior; device GPs at
+    the reference's theta."""
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.topo_variant1 import ES
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v8_es.npz'))
+    forced = _ForcedFits(monkeypatch)
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    thetas = [th for th in D['thetas']]
+    nsrc = int(D['n_source_fits'])
+    forced.queue = thetas[:nsrc]
+    cs = TableSpace(types)
+    fac = ES(cs, [(X.copy(), y.copy()) for X, y in tables[1:]], None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+    assert not forced.queue
+    smbo = SMBO_OFFLINE(tables[0], cs, fac, source_hpo_data=None, surrogate_type='gp', initial_runs=3,
+                        random_seed=seed, max_runs=100)
+    used = nsrc
+    for it, row in enumerate(D['rows']):
+        nfit = int(D['fits_per_iter'][it])
+        forced.queue = thetas[used:used + nfit]
+        used += nfit
+        smbo.iterate()
+        assert not forced.queue
+        got = smbo.configurations[-1]
+        assert got == int(row), 'iteration %d: device picked row %d, reference %d' % (it, got, row)
+        np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), D['w'][it], rtol=1e-9, atol=1e-12)
+        st = np.random.get_state()
+        assert np.array_equal(np.concatenate([st[1].astype(np.int64), [st[2]]]), D['np_random_states'][it]), it
+    mu, var = fac.predict(tables[0][0][:64])
+    np.testing.assert_allclose(mu, D['final_mu'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(var, D['final_var'], rtol=1e-6, atol=1e-12)

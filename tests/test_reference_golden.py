@@ -362,3 +362,33 @@ def test_random_search_baseline_matches_reference():
         assert smbo.iterate() == int(row), it
     st = fac.rng.get_state()
     assert np.array_equal(st[1], D['rng_key']) and st[2] == int(D['rng_pos'])
+
+
+def test_ensemble_selection_facade_matches_reference(monkeypatch):
+    """``--methods es`` (facade/obtl_es.py: greedy ensemble selection of the source weights, target weight by
+    sampling) against a run of the reference itself (fixture reference_v8_es.npz): rows, the weight history to
+    1e-12, the global np.random state after every iteration and the final posterior; GPs at the reference's theta."""
+    D = np.load(os.path.join(HERE, 'golden', 'reference_v8_es.npz'))
+    monkeypatch.setattr(ofacade, 'OracleGP', _ForcedGP)
+    K, seed, types = int(D['K']), int(D['seed']), D['types']
+    tables = [(D['task%d_X' % t], D['task%d_y' % t]) for t in range(K + 1)]
+    thetas = [th for th in D['thetas']]
+    nsrc = int(D['n_source_fits'])
+    _ForcedGP.queue = thetas[:nsrc]
+    fac = ofacade.OracleES(types, [(X.copy(), y.copy()) for X, y in tables[1:]], seed, literal_loops=True)
+    assert not _ForcedGP.queue
+    smbo = OracleSMBOOffline(tables[0][0], tables[0][1], fac, seed, initial_runs=3)
+    used = nsrc
+    for it, row in enumerate(D['rows']):
+        nfit = int(D['fits_per_iter'][it])
+        _ForcedGP.queue = thetas[used:used + nfit]
+        used += nfit
+        got = smbo.iterate()
+        assert not _ForcedGP.queue
+        assert got == int(row), 'iteration %d: oracle picked row %d, reference %d' % (it, got, row)
+        np.testing.assert_allclose(np.asarray(fac.w, dtype=np.float64).ravel(), D['w'][it], rtol=1e-12, atol=1e-15)
+        st = np.random.get_state()
+        assert np.array_equal(np.concatenate([st[1].astype(np.int64), [st[2]]]), D['np_random_states'][it]), it
+    mu, var = fac.predict(tables[0][0][:64])
+    np.testing.assert_allclose(mu, D['final_mu'], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, D['final_var'], rtol=1e-6, atol=1e-12)
