@@ -297,6 +297,8 @@ class FitHandle(object):
 
 
 _CONST_CACHE = {}
+_P0_CACHE = {}          # id(start-point array) -> (array, device copy, restarts)
+_WS_BYTES = {}          # (B, R, ncap, d) -> tlbo_gp_fit_workspace_bytes
 
 
 def _cached_const(a):
@@ -355,20 +357,39 @@ def gp_fit_batched(X_list, y_list, types, p0, lo, hi, ymean, ystd, pack, slot0=0
     else:
         dX, dy, dn = _pad_batch(X_list, y_list, ncap, d)
     dev = dX.device
-    p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, H))
-    R = p0.shape[0]
-    dp0 = _cached_const(p0)
+    # the start points of a facade are ONE array object reused by every fit (same seed -> same draws): its device copy
+    # is looked up by identity, not by hashing a kilobyte of floats per launch
+    hit = _P0_CACHE.get(id(p0))
+    if hit is not None and hit[0] is p0:
+        dp0, R = hit[1], hit[2]
+    else:
+        p0c = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(-1, H))
+        R = p0c.shape[0]
+        dp0 = _cached_const(p0c)
+        if len(_P0_CACHE) > 64:
+            _P0_CACHE.clear()
+        _P0_CACHE[id(p0)] = (p0, dp0, R)
     dlo = _cached_const(lo)
     dhi = _cached_const(hi)
     hym = np.ascontiguousarray(ymean, dtype=np.float64)
     hys = np.ascontiguousarray(ystd, dtype=np.float64)
     STATS.h2d += hym.nbytes + hys.nbytes
-    status = torch.zeros(B, dtype=torch.int32, device=dev)
-    wbytes = int(lib.tlbo_gp_fit_workspace_bytes(B, R, ncap, d))
-    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    rt = torch.empty(B, R, H, dtype=F64, device=dev)
-    rf = torch.empty(B, R, dtype=F64, device=dev)
-    ri = torch.empty(B, R, 4, dtype=torch.int32, device=dev)
+    wkey = (B, R, ncap, d)
+    wbytes = _WS_BYTES.get(wkey)
+    if wbytes is None:
+        wbytes = _WS_BYTES[wkey] = int(lib.tlbo_gp_fit_workspace_bytes(B, R, ncap, d))
+    # ONE allocation for every per-launch buffer: rt | rf | work | ri | status (the factorisation kernel writes the
+    # status of every surrogate on all of its paths: no zero fill needed)
+    o_rf = 8 * B * R * H
+    o_work = round_up(o_rf + 8 * B * R, 256)
+    o_ri = round_up(o_work + wbytes, 16)
+    o_st = o_ri + 16 * B * R
+    blob = torch.empty(o_st + 4 * B, dtype=torch.uint8, device=dev)
+    rt = blob[:o_rf].view(F64).view(B, R, H)
+    rf = blob[o_rf:o_rf + 8 * B * R].view(F64).view(B, R)
+    work = blob[o_work:o_work + wbytes]
+    ri = blob[o_ri:o_st].view(torch.int32).view(B, R, 4)
+    status = blob[o_st:o_st + 4 * B].view(torch.int32)
     t = _types_arr(types)
     with _call('gp_fit', 2):            # gp_fit_kernel + gp_factorize_kernel
         check(lib.tlbo_gp_fit_batched(ptr(dX), ptr(dy), ptr(dn), B, ncap, d, ptr(t), ptr(dp0), R, ptr(dlo),
