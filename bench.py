@@ -68,7 +68,8 @@ def parse_args():
                     help='reference arm: score this many pool rows per step and scale (0 = the full pool, measured)')
     ap.add_argument('--passes', type=int, default=5, help='timed passes of exactly --steps steps each (median reported)')
     ap.add_argument('--sub', default='auto', help="sub-records: 'auto', 'none' or a comma list of topo,pool_1e6,predict_sweep,"
-                    "pool_strong,online,distinct_trials,gp_mcmc")
+                    "pool_strong,online,distinct_trials,trials_per_gpu,gp_mcmc")
+    ap.add_argument('--trials-per-gpu', type=int, default=3, help='concurrent trials (threads) of the trials_per_gpu record')
     ap.add_argument('--strong-pool', type=int, default=10000000, help='rows of the fixed pool of the pool_strong record')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pool-sharded', action='store_true')
@@ -661,6 +662,98 @@ def measure_offline(args, comm, flush, dmma_tf, method, pool, surrogate='gp', di
     return rec
 
 
+def measure_trials_per_gpu(args, comm, n_threads=2):
+    """SEVERAL independent trials per GPU, concurrently: one thread + one CUDA stream + one private copy of the
+    "process-global" np.random stream (tlbo_b200.utils.global_stream) per trial, so that the trials' fit kernels (66
+    CTAs each) share the 148 SMs.  Each trial is a distinct task / seed and selects exactly the rows it selects when it
+    runs alone (tests/test_gpu_bo_loop.py::test_two_trials_in_one_process_...).  W warm-up steps per trial, then K
+    timed steps per trial between two device-wide synchronisations, every step behind a 256 MiB L2 flush on the
+    trial's own stream; value = trials x K / time, summed over the ranks (slowest rank charged).  A second leg (e2e)
+    re-uploads every trial's candidate table from pinned host memory in every step.  The single-trial step time of
+    the same run is reported beside it."""
+    import threading
+    import torch
+    from tlbo_b200.utils.global_stream import thread_stream
+    K, W = args.steps, args.warmup
+    T = int(n_threads)
+    trials = [comm.rank * T + t for t in range(T)]
+    legs = (False, True)
+    state = {}
+    errors = []
+    ready = threading.Barrier(T + 1)
+    go = threading.Barrier(T + 1)
+    done = threading.Barrier(T + 1)
+
+    def run(t, trial):
+        try:
+            torch.cuda.set_device(comm.local_rank)
+            stream = torch.cuda.Stream()
+            with thread_stream(), torch.cuda.stream(stream):
+                flush = torch.empty(256 << 20, dtype=torch.uint8, device=comm.dev)
+                wl = build_workload(trial % 30, 4465 + trial, args.pool, args.sources, args.n0)
+                fac, smbo = make_product(args, wl, method='rgpe', surrogate='gp')
+                for _ in range(W):
+                    flush.zero_()
+                    smbo.iterate()
+                snap = (list(smbo.configurations), list(smbo.perfs))
+                for e2e in legs:
+                    smbo.configurations, smbo.perfs = list(snap[0]), list(snap[1])
+                    stream.synchronize()
+                    ready.wait()
+                    go.wait()
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    for _ in range(K):
+                        flush.zero_()
+                        if e2e:
+                            smbo.acq_optimizer.reupload()
+                        smbo.iterate()
+                    e1.record(stream)
+                    stream.synchronize()
+                    state[(t, e2e)] = e0.elapsed_time(e1)
+                    done.wait()
+        except Exception as ex:                               # pragma: no cover
+            errors.append(repr(ex))
+            for b in (ready, go, done):
+                b.abort()
+
+    threads = [threading.Thread(target=run, args=(t, tr), daemon=True) for t, tr in enumerate(trials)]
+    for th in threads:
+        th.start()
+    ms = {}
+    try:
+        for e2e in legs:
+            ready.wait()
+            comm.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            go.wait()
+            done.wait()
+            torch.cuda.synchronize()
+            ms[e2e] = comm.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    except threading.BrokenBarrierError:
+        pass
+    for th in threads:
+        th.join()
+    if errors:
+        raise RuntimeError('trial thread failed: %s' % errors[0])
+    pool_bytes = float(args.pool) * 9 * 8
+    return {'metric': METRIC + ', %d concurrent trials per GPU' % T, 'value': comm.world * T * K / (ms[False] * 1e-3),
+            'unit': UNIT, 'n_gpus': comm.world, 'steps': K, 'warmup': W, 'trials_per_gpu': T,
+            'ms_per_step_per_gpu': ms[False] / (T * K),
+            'single_trial_ms_per_step_under_sharing': [state[(t, False)] / K for t in range(T)],
+            'e2e': {'value': comm.world * T * K / (ms[True] * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': pool_bytes, 'ms_per_step_per_gpu': ms[True] / (T * K),
+                    'single_trial_ms_per_step_under_sharing': [state[(t, True)] / K for t in range(T)],
+                    'api': 'SMBO_OFFLINE.iterate() in every trial thread, that trial\'s candidate table re-uploaded '
+                           'from pinned host memory every step and the selected row read back'},
+            'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f64', 'data': 'synthetic',
+            'timing': 'wall clock between two device-wide synchronisations (the trials run on %d streams), max over '
+                      'ranks; per-trial figures from CUDA events on each trial\'s stream' % T,
+            'config': workload_config(args, method='rgpe', pool=args.pool, surrogate='gp', distinct=True)}
+
+
 def measure_pool_strong(args, comm, flush, pool_total):
     """ONE BO trial over a FIXED pool of `pool_total` rows sharded by rows over the ranks (strong scaling):
     every rank fits redundantly (deterministic), scores its row range, and the ranks all-gather the 32-byte
@@ -861,15 +954,15 @@ def run_ours(args):
     if args.sub == 'auto':
         subs = ['pool_strong']
         if world == 1:
-            subs = ['topo', 'pool_1e6', 'predict_sweep', 'pool_strong', 'online']
+            subs = ['topo', 'pool_1e6', 'predict_sweep', 'pool_strong', 'online', 'trials_per_gpu']
         else:
-            subs = ['distinct_trials', 'pool_strong', 'online'] + (['gp_mcmc'] if world >= 8 else [])
+            subs = ['distinct_trials', 'trials_per_gpu', 'pool_strong', 'online'] + (['gp_mcmc'] if world >= 8 else [])
     elif args.sub in ('none', ''):
         subs = []
     else:
         subs = [x.strip() for x in args.sub.split(',') if x.strip()]
     if args.method != 'rgpe' or args.surrogate != 'gp' or args.pool != 100000:
-        subs = [x for x in subs if x in ('pool_strong', 'distinct_trials', 'online')] if args.sub == 'auto' else subs
+        subs = [x for x in subs if x in ('pool_strong', 'distinct_trials', 'online', 'trials_per_gpu')] if args.sub == 'auto' else subs
 
     # one clock sampler for the whole job (rank 0's GPU): eight nvidia-smi pollers contend for the driver
     # lock with the ranks' own launches and synchronisations
@@ -885,6 +978,8 @@ def run_ours(args):
             rec = measure_offline(args, comm, flush, dmma_tf, 'topo', args.pool, 'gp', passes=3)
         elif name == 'pool_1e6':
             rec = measure_offline(args, comm, flush, dmma_tf, 'rgpe', 1000000, 'gp', passes=3, want_all_surrogates=True)
+        elif name == 'trials_per_gpu':
+            rec = measure_trials_per_gpu(args, comm, args.trials_per_gpu)
         elif name == 'distinct_trials':
             rec = measure_offline(args, comm, flush, dmma_tf, args.method, args.pool, args.surrogate, distinct=True,
                                   passes=3)

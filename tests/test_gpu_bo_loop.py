@@ -280,3 +280,52 @@ def test_offline_search_full_order_and_head_share_one_key_stream(forced):
     assert idx == want and search.last_best[1] == keys[want]
     a, b = search.sync_host_rng().get_state(), orng.get_state()
     assert (a[1] == b[1]).all() and a[2] == b[2]
+
+
+def test_two_trials_in_one_process_select_the_rows_of_their_solo_runs():
+    """Two RGPE trials (different tasks / seeds) run CONCURRENTLY in one process -- a thread, a CUDA stream and a
+    private copy of the "process-global" np.random stream each (utils/global_stream.py) -- pick exactly the rows each
+    of them picks when it runs alone in the process."""
+    import threading
+    import torch
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.rgpe import RGPE
+    from tlbo_b200.framework.smbo_offline import SMBO_OFFLINE
+    from tlbo_b200.utils.global_stream import thread_stream
+    K, N, iters = 4, 1500, 14
+
+    def make(trial):
+        types, sources, (Xt, yt) = _bench(K, N, 100 + trial)
+        cs = TableSpace(types)
+        fac = RGPE(cs, sources, None, 7 + trial, surrogate_type='gp', num_src_hpo_trial=50)
+        return SMBO_OFFLINE((Xt, yt), cs, fac, random_seed=7 + trial, max_runs=10 ** 6)
+
+    solo = []
+    for trial in (0, 1):
+        smbo = make(trial)
+        for _ in range(iters):
+            smbo.iterate()
+        solo.append(list(smbo.configurations))
+    got, errs = {}, []
+    bar = threading.Barrier(2)
+
+    def run(trial):
+        try:
+            with thread_stream(), torch.cuda.stream(torch.cuda.Stream()):
+                smbo = make(trial)
+                bar.wait()
+                for _ in range(iters):
+                    smbo.iterate()
+                torch.cuda.current_stream().synchronize()
+                got[trial] = list(smbo.configurations)
+        except Exception as ex:                      # pragma: no cover
+            errs.append(repr(ex))
+            bar.abort()
+    ts = [threading.Thread(target=run, args=(t,)) for t in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert got[0] == solo[0] and got[1] == solo[1]
+    assert solo[0] != solo[1]

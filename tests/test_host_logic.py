@@ -188,3 +188,40 @@ def test_prepare_jobs_wrapper_layout():
     yj = prep.buf[nx:nx + ny].reshape(3, 24)
     assert abs(yj[0, :23].mean()) < 1e-12 and abs(yj[0, :23].std() - 1) < 1e-12
     assert np.array_equal(prep.buf[:nx].reshape(3, 24, 4)[1, :19], X[4:])
+
+
+def test_thread_local_global_stream_equals_numpys():
+    """``utils/global_stream.thread_stream``: two threads drawing through the module-level functions, interleaved,
+    each see the stream a lone process would after ``np.random.seed``; threads outside keep numpy's own stream."""
+    import threading
+    from tlbo_b200.utils.global_stream import thread_stream
+    want = {}
+    for s in (5, 6):
+        np.random.seed(s)
+        want[s] = (np.random.standard_normal((3, 4)), np.random.random(5), np.random.standard_normal(2))
+    np.random.seed(99)
+    ref_outside = np.random.random(3)
+    got = {}
+    bar = threading.Barrier(2)
+
+    def work(s):
+        with thread_stream():
+            np.random.seed(s)
+            bar.wait()
+            a = np.random.standard_normal((3, 4))
+            bar.wait()
+            b = np.random.random(5)
+            bar.wait()
+            c = np.random.standard_normal(2)
+            got[s] = (a, b, c)
+    np.random.seed(99)
+    ts = [threading.Thread(target=work, args=(s,)) for s in (5, 6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for s in (5, 6):
+        for x, y in zip(got[s], want[s]):
+            assert np.array_equal(x, y)
+    assert np.array_equal(np.random.random(3), ref_outside)        # the process-global stream was not touched
+    assert np.random.seed.__module__.startswith('numpy') or np.random.seed.__name__ == 'seed'
