@@ -8,6 +8,7 @@ import torch
 
 from tlbo_b200 import _cabi
 from tlbo_b200._cabi import HYP_STRIDE, TlboPack, check, ldl, lib, ptr
+from tlbo_b200.utils.global_stream import waiting
 
 F64 = torch.float64
 
@@ -163,7 +164,8 @@ def merge_best(quads, out=None):
 def d2h(t):
     """Device tensor -> numpy (counted; synchronises)."""
     STATS.d2h += t.numel() * t.element_size()
-    return t.cpu().numpy()
+    with waiting():                    # a trial thread gives its host turn away while it blocks (utils/global_stream.py)
+        return t.cpu().numpy()
 
 
 class SurrogatePack(object):

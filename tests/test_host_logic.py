@@ -225,3 +225,40 @@ def test_thread_local_global_stream_equals_numpys():
             assert np.array_equal(x, y)
     assert np.array_equal(np.random.random(3), ref_outside)        # the process-global stream was not touched
     assert np.random.seed.__module__.startswith('numpy') or np.random.seed.__name__ == 'seed'
+
+
+def test_host_turns_are_exclusive_and_given_up_while_waiting():
+    """``thread_stream(turns=True)``: only one trial thread runs its host segment at a time; inside ``waiting()`` (and
+    inside a large ``standard_normal`` draw) the turn is free for the others; draws stay the private stream's."""
+    import threading
+    import time
+    from tlbo_b200.utils.global_stream import thread_stream, waiting
+    inside = [0]
+    overlap = [0]
+    met = threading.Barrier(2)
+    got = {}
+
+    def work(s):
+        with thread_stream(turns=True):
+            np.random.seed(s)
+            for _ in range(20):
+                inside[0] += 1
+                overlap[0] = max(overlap[0], inside[0])
+                time.sleep(0.0005)
+                inside[0] -= 1
+                with waiting():
+                    time.sleep(0.0005)
+            with waiting():
+                met.wait(timeout=20)                 # both threads are inside their blocks here: no deadlock
+            got[s] = np.random.standard_normal((70, 70))
+    ts = [threading.Thread(target=work, args=(s,)) for s in (11, 12)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(30)
+    assert not any(t.is_alive() for t in ts)
+    assert overlap[0] == 1
+    for s in (11, 12):
+        assert np.array_equal(got[s], np.random.RandomState(s).standard_normal((70, 70)))
+    with waiting():                                   # a thread without a turn: no-op
+        pass
