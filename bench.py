@@ -341,7 +341,7 @@ def run_reference_arm(args):
         'maximize_s_per_step_scaled': float(np.mean([np.mean(r[1]) for r in res])),
         'pair_loops': args.pair_loops,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, method=None, pool=None, surrogate=None, distinct=None):
@@ -1032,12 +1032,33 @@ def run_ours(args):
             sub['predict_sweep']['cpu_baseline'] = sweep_cpu_baseline()
     if sub:
         line['sub'] = sub
-    print(json.dumps(line), flush=True)
+    tp = sub.get('trials_per_gpu')
+    if tp:
+        # per-GPU THROUGHPUT with several concurrent trials per GPU, next to the single-trial headline (latency)
+        line['throughput_concurrent_trials'] = {
+            'value': tp['value'], 'unit': UNIT, 'trials_per_gpu': tp['trials_per_gpu'], 'e2e_value': tp['e2e']['value'],
+            'note': 'sub-record trials_per_gpu: the same BO steps, %d independent trials per GPU on their own threads '
+                    'and streams; the headline "value" above is ONE trial per GPU' % tp['trials_per_gpu']}
+    emit(line)
     comm.close()
+
+
+_JSON_OUT = [None]
+
+
+def emit(line):
+    out = _JSON_OUT[0] or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
     args = parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints
+    # "NCCL version ..." there under NCCL_DEBUG=VERSION/WARN) are sent to stderr
+    sys.stdout.flush()
+    _JSON_OUT[0] = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference_arm(args)
     else:
