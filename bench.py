@@ -731,23 +731,33 @@ def measure_trials_per_gpu(args, comm, n_threads=2):
     for th in threads:
         th.start()
     ms = {}
-    try:
-        for e2e in legs:
-            ready.wait()
-            comm.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            go.wait()
-            done.wait()
-            torch.cuda.synchronize()
-            ms.setdefault(e2e, []).append(comm.max_over_ranks((time.perf_counter() - t0) * 1e3))
-    except threading.BrokenBarrierError:
-        pass
+    broken = False
+    for e2e in legs:
+        # every rank makes the SAME collective calls whatever happens in its trial threads (a failed thread must not
+        # leave the other ranks waiting in a barrier)
+        try:
+            if not broken:
+                ready.wait()
+        except threading.BrokenBarrierError:
+            broken = True
+        comm.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        try:
+            if not broken:
+                go.wait()
+                done.wait()
+        except threading.BrokenBarrierError:
+            broken = True
+        torch.cuda.synchronize()
+        ms.setdefault(e2e, []).append(comm.max_over_ranks((time.perf_counter() - t0) * 1e3))
     for th in threads:
-        th.join()
+        th.join(60)
     sys.setswitchinterval(old_switch)
-    if errors:
-        raise RuntimeError('trial thread failed: %s' % errors[0])
+    failed = comm.max_over_ranks(1.0 if (broken or errors) else 0.0)
+    if failed:
+        return {'metric': METRIC + ', %d concurrent trials per GPU' % T, 'value': None, 'unit': UNIT,
+                'error': (errors[0] if errors else 'a trial thread failed on another rank')}
     pool_bytes = float(args.pool) * 9 * 8
     all_ms = {k: [round(x / (T * K), 4) for x in v] for k, v in ms.items()}
     pick = {k: sorted(range(reps), key=lambda i: v[i])[(reps - 1) // 2] for k, v in ms.items()}
@@ -1033,7 +1043,7 @@ def run_ours(args):
     if sub:
         line['sub'] = sub
     tp = sub.get('trials_per_gpu')
-    if tp:
+    if tp and tp.get('value'):
         # per-GPU THROUGHPUT with several concurrent trials per GPU, next to the single-trial headline (latency)
         line['throughput_concurrent_trials'] = {
             'value': tp['value'], 'unit': UNIT, 'trials_per_gpu': tp['trials_per_gpu'], 'e2e_value': tp['e2e']['value'],
