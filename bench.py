@@ -819,48 +819,58 @@ def measure_pool_strong(args, comm, flush, pool_total):
     return rec
 
 
-def measure_online(args, comm, n_trials=50, iters=4, n0=20, num_points=5000):
-    """BASELINE configs[2]: the ONLINE scenario (tools/online_benchmark.py shape: SMBO_ONLINE with
-    InterleavedLocalAndRandomSearch -- 10 hill-climbs + ~4990 random configurations sorted by EI -- and RGPE over
-    29 sources), `n_trials` independent trials (own target task / seed) sharded round-robin over the ranks, `iters`
-    timed BO iterations each after one untimed one.  No collective on the data path; the slowest rank is charged.
-    Facade construction (the 29 source fits of a trial) is outside the timed loops and reported beside them."""
-    import torch
-    from tlbo_b200 import ops, synthetic
+def _online_trial(K, t, n0, num_points):
+    """One online-scenario trial (own target task / seed), built and advanced by ONE untimed iteration."""
+    from tlbo_b200 import synthetic
     from tlbo_b200.config_space import Configuration, TableSpace
     from tlbo_b200.facade.rgpe import RGPE
     from tlbo_b200.framework.smbo_online import SMBO_ONLINE
     types, const = synthetic.space_types('rf')
     fam = synthetic.TaskFamily(types, const, n_tasks=30, seed=4466)
+    task, seed = t % 30, 4465 + t
+    ids = [i for i in range(30) if i != task]
+    np.random.RandomState(seed).shuffle(ids)
+    sources = []
+    for k in ids[:K]:
+        rng = np.random.RandomState(1000 + k)
+        X = synthetic.sample_table(rng, 50, types, const)
+        sources.append((X, fam.evaluate(k, X, rng)))
+
+    def objective(config, task=task):
+        x = config.get_array() if hasattr(config, 'get_array') else np.asarray(config)
+        return float(fam.evaluate(task, x[np.newaxis, :])[0])
+    cs = TableSpace(types, const_mask=const)
+    cs.seed(seed)
+    fac = RGPE(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+    smbo = SMBO_ONLINE(objective, cs, fac, random_seed=seed, max_runs=10 ** 9, num_points=num_points)
+    X0 = cs.sample_array(n0)
+    for i in range(n0):
+        c = Configuration(cs, X0[i], -1)
+        smbo.configurations.append(c)
+        smbo.perfs.append(objective(c))
+        smbo.history_container.add(c, smbo.perfs[-1])
+    smbo.iterate()
+    return smbo
+
+
+def measure_online(args, comm, n_trials=50, iters=4, n0=20, num_points=5000):
+    """BASELINE configs[2]: the ONLINE scenario (tools/online_benchmark.py shape: SMBO_ONLINE with
+    InterleavedLocalAndRandomSearch -- 10 hill-climbs + ~4990 random configurations sorted by EI -- and RGPE over
+    29 sources), `n_trials` independent trials (own target task / seed) sharded round-robin over the ranks, `iters`
+    timed BO iterations each after one untimed one.  No collective on the data path; the slowest rank is charged.
+    Facade construction (the 29 source fits of a trial) is outside the timed loops and reported beside them.
+    A second pass (``concurrent``) runs the rank's trials on --trials-per-gpu threads (a CUDA stream and a private copy
+    of the global np.random stream each, as the trials_per_gpu record): wall clock over all timed loops."""
+    import torch
+    from tlbo_b200 import ops
     K = args.sources
     mine = [t for t in range(n_trials) if t % comm.world == comm.rank]
     timed_ms, build_s, launches = 0.0, 0.0, 0
+    picked = {}
     comm.barrier()
     for t in mine:
-        task, seed = t % 30, 4465 + t
-        ids = [i for i in range(30) if i != task]
-        np.random.RandomState(seed).shuffle(ids)
-        sources = []
-        for k in ids[:K]:
-            rng = np.random.RandomState(1000 + k)
-            X = synthetic.sample_table(rng, 50, types, const)
-            sources.append((X, fam.evaluate(k, X, rng)))
-
-        def objective(config, task=task):
-            x = config.get_array() if hasattr(config, 'get_array') else np.asarray(config)
-            return float(fam.evaluate(task, x[np.newaxis, :])[0])
         a = time.perf_counter()
-        cs = TableSpace(types, const_mask=const)
-        cs.seed(seed)
-        fac = RGPE(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
-        smbo = SMBO_ONLINE(objective, cs, fac, random_seed=seed, max_runs=10 ** 9, num_points=num_points)
-        X0 = cs.sample_array(n0)
-        for i in range(n0):
-            c = Configuration(cs, X0[i], -1)
-            smbo.configurations.append(c)
-            smbo.perfs.append(objective(c))
-            smbo.history_container.add(c, smbo.perfs[-1])
-        smbo.iterate()
+        smbo = _online_trial(K, t, n0, num_points)
         torch.cuda.synchronize()
         build_s += time.perf_counter() - a
         ops.STATS.reset()
@@ -873,20 +883,90 @@ def measure_online(args, comm, n_trials=50, iters=4, n0=20, num_points=5000):
         torch.cuda.synchronize()
         timed_ms += e0.elapsed_time(e1)
         launches += ops.STATS.total_launches()
-        del fac, smbo
+        picked[t] = [tuple(np.asarray(c.get_array(), dtype=np.float64).tolist()) for c in smbo.configurations[-iters:]]
+        del smbo
     comm.barrier()
     ms = comm.max_over_ranks(timed_ms)
     per_rank = comm.all_ranks(timed_ms)
     total_iters = n_trials * iters
-    return {'metric': 'BO iters/sec, online scenario (fit + weights + interleaved local / random EI search) at %d sources' % K,
-            'value': total_iters / (ms * 1e-3), 'unit': UNIT, 'n_gpus': comm.world, 'scaling': 'strong',
-            'trials': n_trials, 'timed_iterations_per_trial': iters, 'ms_per_iteration_per_rank': ms / max(len(mine) * iters, 1),
-            'per_rank_timed_ms': [round(v, 2) for v in per_rank], 'gpu_launches_rank0': launches,
-            'construction_s_rank0': build_s,
-            'config': {'workload': 'rgpe online BO (SMBO_ONLINE + InterleavedLocalAndRandomSearch, %d challengers per '
-                                   'iteration), %d source GPs x 50 obs, d=9 random_forest space, %d trials (own task / seed) '
-                                   'sharded over the ranks, target n=%d..%d' % (num_points, K, n_trials, n0 + 1, n0 + iters)},
-            'note': 'host-bound: one hill-climb step = one neighbourhood launch + one synchronisation (DESIGN.md 3.5)'}
+    rec = {'metric': 'BO iters/sec, online scenario (fit + weights + interleaved local / random EI search) at %d sources' % K,
+           'value': total_iters / (ms * 1e-3), 'unit': UNIT, 'n_gpus': comm.world, 'scaling': 'strong',
+           'trials': n_trials, 'timed_iterations_per_trial': iters, 'ms_per_iteration_per_rank': ms / max(len(mine) * iters, 1),
+           'per_rank_timed_ms': [round(v, 2) for v in per_rank], 'gpu_launches_rank0': launches,
+           'construction_s_rank0': build_s,
+           'config': {'workload': 'rgpe online BO (SMBO_ONLINE + InterleavedLocalAndRandomSearch, %d challengers per '
+                                  'iteration), %d source GPs x 50 obs, d=9 random_forest space, %d trials (own task / seed) '
+                                  'sharded over the ranks, target n=%d..%d' % (num_points, K, n_trials, n0 + 1, n0 + iters)},
+           'note': 'host-bound: one hill-climb step = one neighbourhood launch + one synchronisation (DESIGN.md 3.5)'}
+    T = int(getattr(args, 'trials_per_gpu', 0) or 0)
+    if T > 1:
+        rec['concurrent'] = _online_concurrent(comm, K, mine, T, iters, n0, num_points, total_iters, picked)
+    return rec
+
+
+def _online_concurrent(comm, K, mine, T, iters, n0, num_points, total_iters, picked):
+    """The rank's online trials on T threads: every thread builds its trials (untimed, the private np.random state
+    saved with each), then -- between two barriers -- runs their timed iterations.  Also checks that every trial
+    selected the configurations of its sequential run."""
+    import threading
+    import torch
+    from tlbo_b200.utils.global_stream import thread_stream
+    errors, same = [], []
+    ready = threading.Barrier(T + 1)
+    done = threading.Barrier(T + 1)
+
+    def run(w):
+        try:
+            torch.cuda.set_device(comm.local_rank)
+            stream = torch.cuda.Stream()
+            with thread_stream(), torch.cuda.stream(stream):
+                built = []
+                for t in mine[w::T]:
+                    smbo = _online_trial(K, t, n0, num_points)
+                    built.append((t, smbo, np.random.get_state()))
+                stream.synchronize()
+                ready.wait()
+                for t, smbo, st in built:
+                    np.random.set_state(st)
+                    for _ in range(iters):
+                        smbo.iterate()
+                stream.synchronize()
+                done.wait()
+                for t, smbo, _ in built:
+                    got = [tuple(np.asarray(c.get_array(), dtype=np.float64).tolist())
+                           for c in smbo.configurations[-iters:]]
+                    same.append(got == picked[t])
+        except Exception as ex:                               # pragma: no cover
+            errors.append(repr(ex))
+            ready.abort()
+            done.abort()
+
+    threads = [threading.Thread(target=run, args=(w,), daemon=True) for w in range(T)]
+    for th in threads:
+        th.start()
+    broken = False
+    try:
+        ready.wait()
+    except threading.BrokenBarrierError:
+        broken = True
+    comm.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    try:
+        if not broken:
+            done.wait()
+    except threading.BrokenBarrierError:
+        broken = True
+    torch.cuda.synchronize()
+    ms = comm.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    for th in threads:
+        th.join(60)
+    if comm.max_over_ranks(1.0 if (broken or errors) else 0.0):
+        return {'error': errors[0] if errors else 'a trial thread failed on another rank'}
+    return {'value': total_iters / (ms * 1e-3), 'unit': UNIT, 'threads_per_gpu': T, 'wall_ms': ms,
+            'trials_matching_their_sequential_run_rank0': '%d of %d' % (sum(same), len(same)),
+            'timing': 'wall clock over the timed iterations of all trials of a rank (T threads, own streams), max over '
+                      'ranks; construction outside'}
 
 
 def predict_sweep(dmma_tf, max_rows):

@@ -458,7 +458,7 @@ extern "C" int tlbo_ensemble_ei_small(const tlbo_pack* pack, const int32_t* h_ty
     tlbo_set_error("tlbo_ensemble_ei_small: bad arguments");
     return TLBO_E_BADARG;
   }
-  static SmallEiArgs a;                    // 8 KB of inline rows: not on the stack (the entry is not re-entrant)
+  static thread_local SmallEiArgs a;       // 8 KB of inline rows: not on the stack; one per calling thread (trial threads)
   a.p.pack = *pack;
   int rc = tlbo_make_space(pack->d, h_types, &a.p.sp);
   if (rc) return rc;

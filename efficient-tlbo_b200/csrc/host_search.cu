@@ -314,7 +314,7 @@ static int wait_for_rows(const double* h_ei, int rows, cudaStream_t s) {
 // AbstractAcquisitionFunction.__call__ does).  A climb is ~25 such steps; in the interpreter a step costs ~50 us
 // of Python on top of the launches.  Buffers (all caller-owned): h_X [cap, d] host staging for the neighbourhood (it
 // travels inside the kernel arguments), h_ei [cap] MAPPED pinned host memory (the kernel stores EI over the bus),
-// d_mu / d_var [M * cap] device scratch, d_counter cap zeroed device uint32 (left zero).  Not re-entrant.
+// d_mu / d_var [M * cap] device scratch, d_counter cap zeroed device uint32 (left zero).  Re-entrant across threads with their own buffers.
 // Returns 0 when the climb ended (no improving neighbour or max_steps), 1 when the pre-drawn seeds ran out
 // (call again with more seeds: the incumbent / counters are up to date), < 0 / CUDA codes on error.
 extern "C" int tlbo_local_search_climb(const tlbo_pack* view, const int32_t* h_types, const uint8_t* h_const_mask,

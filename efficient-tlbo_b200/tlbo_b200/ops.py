@@ -306,10 +306,12 @@ _WS_BYTES = {}          # (B, R, ncap, d) -> tlbo_gp_fit_workspace_bytes
 def _cached_const(a):
     """Small read-only device constants (start points, bounds): uploaded once per value."""
     a = np.ascontiguousarray(a, dtype=np.float64)
-    key = (a.shape, a.tobytes(), torch.cuda.current_device())
+    # per STREAM: an entry is uploaded on the stream that first asks for it, and a trial running on another stream
+    # (several trials per process) must not consume it before that copy has completed there
+    key = (a.shape, a.tobytes(), _stream().value)
     t = _CONST_CACHE.get(key)
     if t is None:
-        if len(_CONST_CACHE) > 256:
+        if len(_CONST_CACHE) > 1024:
             _CONST_CACHE.clear()
         t = h2d(a)
         _CONST_CACHE[key] = t
@@ -320,10 +322,10 @@ def cached_upload(a):
     """Small host arrays that repeat from call to call (ensemble weights / skip flags / slot order
     within one maximisation): uploaded once per distinct value."""
     a = np.ascontiguousarray(a)
-    key = (a.dtype.str, a.shape, a.tobytes(), torch.cuda.current_device())
+    key = (a.dtype.str, a.shape, a.tobytes(), _stream().value)
     t = _CONST_CACHE.get(key)
     if t is None:
-        if len(_CONST_CACHE) > 256:
+        if len(_CONST_CACHE) > 1024:
             _CONST_CACHE.clear()
         t = h2d(a)
         _CONST_CACHE[key] = t

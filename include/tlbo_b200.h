@@ -306,7 +306,7 @@ int tlbo_pair_penalty_loss_normal(const double* d_y, const double* d_z, const do
  *   fence behind it: a host that pre-fills ei[] with TLBO_EI_PENDING (a NaN payload no computation produces) may
  *   spin until no row holds it instead of synchronising the stream;
  *   d_mu, d_var: [M, Nq] per-surrogate posteriors (scratch the combination reads; left there);
- *   d_counter: Nq device uint32, zero on entry, zero on completion.  Not re-entrant.                        */
+ *   d_counter: Nq device uint32, zero on entry, zero on completion.  Thread-safe (own buffers).                     */
 #define TLBO_EI_PENDING_BITS 0x7ff8dead0000beefULL
 int tlbo_ensemble_ei_small(const tlbo_pack* pack, const int32_t* h_types, const double* d_w, const int32_t* d_skip,
                            const int32_t* d_order, int mode, const double* Xq, const double* h_Xq, int Nq, double eta,
@@ -324,7 +324,7 @@ int tlbo_ensemble_ei_small(const tlbo_pack* pack, const int32_t* h_types, const 
  *   d_mu, d_var [M * cap] device scratch; d_counter: cap zeroed device uint32 (left zero);
  *   h_counters int32[5]: += seeds consumed, neighbours the lazy reference loop inspects, acquisition evaluations,
  *   rows with EI < 0 (the caller raises as EI._compute does), steps of this climb (caller zeroes [4] per climb).
- * Returns 0: climb ended; 1: seeds ran out (call again with more, state is up to date).  Not re-entrant. */
+ * Returns 0: climb ended; 1: seeds ran out (call again with more, state is up to date).  Thread-safe with per-thread buffers. */
 int tlbo_local_search_climb(const tlbo_pack* view, const int32_t* h_types, const uint8_t* h_const_mask,
                             const double* d_w, const int32_t* d_skip, const int32_t* d_order, int mode, double eta,
                             double par, double var_floor, int num_neighbors, double stdev, const uint32_t* h_seeds,
