@@ -72,3 +72,56 @@ def test_online_loop_matches_oracle(method, K, iters, forced):
     # every random stream ended in the same state
     assert (smbo.acq_optimizer.rng.get_state()[1] == osmbo.acq_rng.get_state()[1]).all()
     assert (cs._rng.get_state()[1] == osmbo.space.rng.get_state()[1]).all()
+
+
+def test_online_trials_on_threads_select_the_configurations_of_their_solo_runs():
+    """Three online-scenario RGPE trials on three threads (a CUDA stream and a private copy of the process-global
+    np.random stream each, tlbo_b200/utils/global_stream.py) propose exactly the configurations each proposes alone:
+    the hill-climb entry points (tlbo_local_search_climb / tlbo_ensemble_ei_small) are thread-safe."""
+    import threading
+    import torch
+    from tlbo_b200 import synthetic
+    from tlbo_b200.config_space import TableSpace
+    from tlbo_b200.facade.rgpe import RGPE
+    from tlbo_b200.framework.smbo_online import SMBO_ONLINE
+    from tlbo_b200.utils.global_stream import thread_stream
+    K, iters = 3, 6
+
+    def run_trial(trial):
+        seed = 4465 + trial
+        b = synthetic.make_benchmark(n_tasks=K + 1, T=200, seed=seed)
+        sources, _ = synthetic.leave_one_out_sources(b['tables'], 0, K, seed)
+        types, const, fam = b['types'], b['const_mask'], b['family']
+
+        def objective(config):
+            return float(fam.evaluate(0, np.asarray(config.get_array())[np.newaxis, :])[0])
+        cs = TableSpace(types, const_mask=const)
+        cs.seed(seed)
+        fac = RGPE(cs, sources, None, seed, surrogate_type='gp', num_src_hpo_trial=50)
+        smbo = SMBO_ONLINE(objective, cs, fac, random_seed=seed, max_runs=10 ** 6, num_points=400)
+        for _ in range(iters):
+            smbo.iterate()
+        return [c.get_array().tobytes() for c in smbo.configurations]
+
+    solo = [run_trial(t) for t in range(3)]
+    got, errs = {}, []
+    bar = threading.Barrier(3)
+
+    def work(t):
+        try:
+            with thread_stream(), torch.cuda.stream(torch.cuda.Stream()):
+                bar.wait()
+                got[t] = run_trial(t)
+                torch.cuda.current_stream().synchronize()
+        except Exception as ex:                      # pragma: no cover
+            errs.append(repr(ex))
+            bar.abort()
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for t in range(3):
+        assert got[t] == solo[t]
+    assert solo[0] != solo[1]
