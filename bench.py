@@ -662,7 +662,7 @@ def measure_offline(args, comm, flush, dmma_tf, method, pool, surrogate='gp', di
     return rec
 
 
-def measure_trials_per_gpu(args, comm, n_threads=2):
+def measure_trials_per_gpu(args, comm, n_threads=2, method='rgpe'):
     """SEVERAL independent trials per GPU, concurrently: one thread + one CUDA stream + one private copy of the
     "process-global" np.random stream (tlbo_b200.utils.global_stream) per trial, so that the trials' fit kernels (66
     CTAs each) share the 148 SMs.  Each trial is a distinct task / seed and selects exactly the rows it selects when it
@@ -693,7 +693,7 @@ def measure_trials_per_gpu(args, comm, n_threads=2):
             with thread_stream(turns=turns), torch.cuda.stream(stream):
                 flush = torch.empty(256 << 20, dtype=torch.uint8, device=comm.dev)
                 wl = build_workload(trial % 30, 4465 + trial, args.pool, args.sources, args.n0)
-                fac, smbo = make_product(args, wl, method='rgpe', surrogate='gp')
+                fac, smbo = make_product(args, wl, method=method, surrogate='gp')
                 for _ in range(W):
                     flush.zero_()
                     smbo.iterate()
@@ -778,7 +778,7 @@ def measure_trials_per_gpu(args, comm, n_threads=2):
             'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f64', 'data': 'synthetic',
             'timing': 'wall clock between two device-wide synchronisations (the trials run on %d streams), max over '
                       'ranks; per-trial figures from CUDA events on each trial\'s stream' % T,
-            'config': workload_config(args, method='rgpe', pool=args.pool, surrogate='gp', distinct=True)}
+            'config': workload_config(args, method=method, pool=args.pool, surrogate='gp', distinct=True)}
 
 
 def measure_pool_strong(args, comm, flush, pool_total):
@@ -1087,6 +1087,8 @@ def run_ours(args):
             rec = measure_offline(args, comm, flush, dmma_tf, 'rgpe', 1000000, 'gp', passes=3, want_all_surrogates=True)
         elif name == 'trials_per_gpu':
             rec = measure_trials_per_gpu(args, comm, args.trials_per_gpu)
+        elif name == 'topo_trials_per_gpu':
+            rec = measure_trials_per_gpu(args, comm, args.trials_per_gpu, method='topo')
         elif name == 'distinct_trials':
             rec = measure_offline(args, comm, flush, dmma_tf, args.method, args.pool, args.surrogate, distinct=True,
                                   passes=3)

@@ -262,3 +262,36 @@ def test_host_turns_are_exclusive_and_given_up_while_waiting():
         assert np.array_equal(got[s], np.random.RandomState(s).standard_normal((70, 70)))
     with waiting():                                   # a thread without a turn: no-op
         pass
+
+
+def test_slsqp_simplex_equals_scipy_minimize():
+    """``utils/scipy_solver.slsqp_simplex`` (the SLSQP core driven directly) returns bit for bit what
+    ``scipy.optimize.minimize`` returns for the reference's problem set-up (tlbo/utils/scipy_solver.py:81-115):
+    pairwise-logistic ranking losses of several shapes, including one that ends on an exit mode other than 0."""
+    from scipy.optimize import minimize
+    from tlbo_b200.utils import scipy_solver as ss
+    if ss._slsqp_core is None:
+        pytest.skip('scipy without _slsqplib: scipy_solve goes through minimize itself')
+    rng = np.random.RandomState(3)
+    for n, m, maxiter in [(12, 3, 100), (30, 8, 100), (45, 30, 100), (45, 30, 3), (20, 1, 100)]:
+        A = rng.standard_normal((n, m))
+        b = rng.standard_normal(n)
+        iu = np.triu_indices(n, 1)
+        sgn = np.sign(b[iu[0]] - b[iu[1]])
+        D = A[iu[0]] - A[iu[1]]
+        calls = []
+
+        def fg(x):
+            z = -sgn * (D @ x)
+            calls.append(np.array(x))
+            return float(np.sum(np.logaddexp(0., z))), D.T @ (-sgn / (1. + np.exp(-z)))
+        x1, ok1 = ss.slsqp_simplex(fg, m, maxiter=maxiter)
+        n_lean = len(calls)
+        eye_m, ones_m = np.eye(m), np.array([1.] * m)
+        res = minimize(lambda x: fg(x)[0], np.array([1. / m] * m), method='SLSQP', jac=lambda x: fg(x)[1],
+                       constraints=[{'type': 'eq', 'fun': lambda x: np.array([sum(x) - 1]), 'jac': lambda x: ones_m},
+                                    {'type': 'ineq', 'fun': lambda x: np.array(x), 'jac': lambda x: eye_m}],
+                       options={'ftol': 1e-8, 'disp': False, 'maxiter': maxiter})
+        assert np.array_equal(x1, res.x), (n, m, x1, res.x)
+        assert ok1 == res.success
+        assert n_lean <= len(calls) - n_lean          # never more evaluations than minimize makes
