@@ -253,6 +253,38 @@ extern "C" int tlbo_pairwise_logistic_loss_grad_hw(const double* d_A, const doub
   return pair_logistic_launch(d_A, d_y, nullptr, h_w, n, m, d_out, stream);
 }
 
+// One SLSQP callback in one call: h_out (MAPPED pinned host memory, 2 + m doubles) is pre-filled with the
+// TLBO_EI_PENDING payload, the kernel overwrites every entry with one 8-byte store, and the host spins until no entry
+// holds the payload -- no cudaStreamSynchronize (a driver round trip of ~10 us, ~30 times per TOPO iteration).  The
+// stream is queried now and then so that a failed launch surfaces as its error instead of a hang.
+extern "C" int tlbo_pairwise_logistic_loss_grad_hw_wait(const double* d_A, const double* d_y, const double* h_w, int n,
+                                                        int m, double* h_out, void* stream) {
+  if (!h_w || !h_out) { tlbo_set_error("NULL h_w / h_out"); return TLBO_E_BADARG; }
+  double pending;
+  const uint64_t bits = TLBO_EI_PENDING_BITS;
+  memcpy(&pending, &bits, sizeof(pending));
+  const int rows = 2 + m;
+  for (int j = 0; j < rows; j++) h_out[j] = pending;
+  int rc = pair_logistic_launch(d_A, d_y, nullptr, h_w, n, m, h_out, stream);
+  if (rc) return rc;
+  const volatile uint64_t* q = reinterpret_cast<const volatile uint64_t*>(h_out);
+  int j = 0;
+  for (unsigned spin = 1;; spin++) {
+    while (j < rows && q[j] != bits) j++;
+    if (j == rows) return 0;
+    if ((spin & 0x3ff) == 0) {
+      cudaError_t e = cudaStreamQuery((cudaStream_t)stream);
+      if (e == cudaSuccess) {
+        while (j < rows && q[j] != bits) j++;
+        if (j == rows) return 0;
+        tlbo_set_error("pairwise_logistic launch finished without reporting every output");
+        return TLBO_E_BADARG;
+      }
+      if (e != cudaErrorNotReady) { tlbo_set_error(cudaGetErrorString(e)); return (int)e; }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // OBTL's sampled ranking loss (reference tlbo/facade/obtl.py:95-147): for every bootstrap sample s and
 // surrogate m, y_pred = normal(mu_m, var_m) (scale = the predictive VARIANCE, as written there) and

@@ -54,6 +54,7 @@ SYMBOLS = {
     'tlbo_rank_loss_counts_normal': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     'tlbo_pairwise_logistic_loss_grad': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     'tlbo_pairwise_logistic_loss_grad_hw': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
+    'tlbo_pairwise_logistic_loss_grad_hw_wait': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     'tlbo_gp_mcmc_chain': (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _P, _P, _P, _P, _P, _P]),
     'tlbo_gp_mcmc_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int]),

@@ -753,6 +753,7 @@ class PairLogistic(object):
         # ~20 us per SLSQP callback)
         self._stream = torch.cuda.current_stream()
         self._sptr = ctypes.c_void_p(self._stream.cuda_stream)
+        self._pA, self._py, self._pout = ptr(self.dA), ptr(self.dy), ptr(self.out)
 
     def __call__(self, w):
         w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
@@ -761,14 +762,15 @@ class PairLogistic(object):
         stream, sptr = self._stream, self._sptr
         with _call('pairwise_logistic', 1):
             if self.host_w:
-                check(lib.tlbo_pairwise_logistic_loss_grad_hw(ptr(self.dA), ptr(self.dy), ptr(w), self.n, self.m,
-                                                              ptr(self.out), sptr))
+                # launch + spin on the mapped result words inside ONE C call (no stream synchronisation)
+                check(lib.tlbo_pairwise_logistic_loss_grad_hw_wait(self._pA, self._py, ptr(w), self.n, self.m,
+                                                                   self._pout, sptr))
             else:
                 self.dw.copy_(torch.from_numpy(w))
                 check(lib.tlbo_pairwise_logistic_loss_grad(ptr(self.dA), ptr(self.dy), ptr(self.dw), self.n, self.m,
                                                            ptr(self.out), sptr))
+                stream.synchronize()
         STATS.h2d += w.nbytes
-        stream.synchronize()
         STATS.d2h += self.out_np.nbytes
         o = self.out_np
         self._cache_w = w.copy()

@@ -225,6 +225,11 @@ int tlbo_pairwise_logistic_loss_grad(const double* d_A, const double* d_y, const
  * memory (unified addressing), so the callback only has to synchronise the stream.           */
 int tlbo_pairwise_logistic_loss_grad_hw(const double* d_A, const double* d_y, const double* h_w, int n, int m,
                                         double* d_out, void* stream);
+/* Same, and WAITS for the result: h_out must be mapped pinned host memory; it is pre-filled with the
+ * TLBO_EI_PENDING payload and the call returns when the kernel's 2 + m eight-byte stores have all landed (a spin on
+ * the mapped words instead of a stream synchronisation: one SLSQP callback = one C call).                          */
+int tlbo_pairwise_logistic_loss_grad_hw_wait(const double* d_A, const double* d_y, const double* h_w, int n, int m,
+                                             double* h_out, void* stream);
 
 /* MCMC marginalisation of the GP hyper-parameters (BASELINE config 5) -- replaces
  * GaussianProcessMCMC._train / _ll (tlbo/model/gp_mcmc.py:116-282,294-332): the
